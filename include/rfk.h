@@ -1,0 +1,164 @@
+/*
+ * rfk.h -- C ABI of librfk.so: sm_100a CUDA kernels for the Glow flow step and the
+ * ConvLSTM cell of cdglissov/recurrent-flows-msc.
+ *
+ * The reference has no FFI: the hot path sits behind plain torch.nn.Module classes
+ * (SURVEY.md section 8b).  This header is the boundary a host binding (ctypes in this
+ * repo; cffi / pybind / a C++ trainer elsewhere) links against.  Every entry point names
+ * the reference code it replaces (paths relative to the reference repository root).
+ *
+ * Conventions
+ *   - every pointer is a caller-owned DEVICE pointer unless it says "host"; no entry
+ *     point allocates, frees, or synchronises; work is enqueued on `stream`
+ *     (a cudaStream_t passed as void*; NULL = legacy default stream);
+ *   - "NCHW f32" tensors are contiguous float32 [B,C,H,W]; "NHWC bf16" tensors are
+ *     bfloat16 [B,H,W,ld] with `ld` (elements) >= the channels used;
+ *   - return value: 0 on success, a negative RFK_E* code otherwise, with a
+ *     human-readable message available from rfk_last_error() (thread-local);
+ *   - nothing here falls back to the CPU: without an sm_100 device the launch fails and
+ *     the error is returned.
+ */
+#ifndef RFK_H_
+#define RFK_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RFK_VERSION 1
+
+#define RFK_OK 0
+#define RFK_EINVAL (-1)   /* bad argument (shape, alignment, enum)           */
+#define RFK_ECUDA (-2)    /* CUDA runtime / driver error at launch           */
+#define RFK_EUNSUPPORTED (-3)
+
+/* activation after the per-channel affine of a conv epilogue (Utils/modules.py:8-19) */
+#define RFK_ACT_NONE 0
+#define RFK_ACT_RELU 1
+#define RFK_ACT_LEAKY 2   /* LeakyReLU(0.2) */
+
+/* log-scale clamp of the affine coupling (Flow/glow_modules.py:252-268) */
+#define RFK_CLAMP_NONE 0
+#define RFK_CLAMP_REALNVP 1   /* scale[j]*tanh(s)+scale_shift[j] */
+#define RFK_CLAMP_GLOW 2      /* log(sigmoid(s+2))               */
+#define RFK_CLAMP_SOFT 3      /* 2.5*0.636*atan(s/2.5)           */
+
+/* how (mean, raw log-scale) are interleaved in a parameter tensor (Utils/utils.py:86-91) */
+#define RFK_PAIR_CROSS 0   /* mean = ch 2j, raw = ch 2j+1      (coupling, Split2d) */
+#define RFK_PAIR_SPLIT 1   /* mean = ch j,  raw = ch n+j       (ListGlow prior)    */
+
+/* std from the raw log-scale (Flow/glow_modules.py:340-344, Flow/glow.py:139) */
+#define RFK_STD_SOFTPLUS 0 /* softplus(raw)+1e-8 */
+#define RFK_STD_EXP 1      /* exp(raw)           */
+
+/* output kind of rfk_conv_gemm */
+#define RFK_OUT_NHWC_BF16 0
+#define RFK_OUT_NCHW_F32 1
+
+int rfk_version(void);
+const char* rfk_last_error(void);
+/* host out-params; returns RFK_ECUDA when no device is visible */
+int rfk_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- a4  Squeeze2d.forward (Flow/glow_modules.py:298-310) -------------------------------
+ * undo=0: x [B,C,H,W] -> y [B,4C,H/2,W/2], y[b,4c+2dy+dx,i,j] = x[b,c,2i+dy,2j+dx]
+ * undo=1: x [B,C,H,W] -> y [B,C/4,2H,2W]  (exact inverse).  B,C,H,W describe x. Bit exact. */
+int rfk_squeeze2d(const float* x, float* y, int B, int C, int H, int W, int undo, void* stream);
+
+/* ---- a1  ActNorm.forward (Flow/glow_modules.py:38-54) ------------------------------------
+ * reverse=0: y = (x + bias[c]) * exp(logs[c]);  reverse=1: y = x*exp(-logs[c]) - bias[c].
+ * The scalar log-det term H*W*sum(logs) is the caller's (it needs no kernel). */
+int rfk_actnorm(const float* x, float* y, const float* bias, const float* logs,
+                int B, int C, int HW, int reverse, void* stream);
+
+/* ---- a1  ActNorm.initialize (Flow/glow_modules.py:26-31) ---------------------------------
+ * Per-channel statistics of x [B,C,HW] over (B,HW): bias[c] = -mean,
+ * logs[c] = log(1/(std_unbiased + 1e-6)).  mean_out/std_out (nullable) receive the raw stats. */
+int rfk_actnorm_init(const float* x, float* bias, float* logs, float* mean_out, float* std_out,
+                     int B, int C, int HW, void* stream);
+
+/* ---- a2 (+a1 folded)  InvConv.forward apply (Flow/glow_modules.py:213,218) ----------------
+ * y[b,o,p] = sum_i Wm[o,i] * x[b,i,p] + bvec[o]   (Wm [C,C] row-major f32, bvec nullable).
+ * With Wm = W*diag(exp(logs)), bvec = Wm*bias this is ActNorm followed by InvConv in one pass.
+ * Optional side output: channels [0,side_n) of y are also written as bf16 into an NHWC buffer
+ * at channel offset side_off with row stride side_ld (the coupling network's z1 input). */
+int rfk_mix1x1(const float* x, float* y, const float* Wm, const float* bvec, int B, int C, int HW,
+               void* side_nhwc_bf16, int side_n, int side_off, int side_ld, void* stream);
+
+/* ---- layout helpers -----------------------------------------------------------------------
+ * pack: channels [c_lo, c_lo+n) of src NCHW f32 [B,Csrc,HW] (batch stride src_bstride elements,
+ * 0 = dense) -> dst NHWC bf16 at channel dst_off (row stride dst_ld).  Replaces torch.cat([z1, condition]) (Flow/glow_modules.py:273,355). */
+int rfk_pack_nhwc_bf16(const float* src, long long src_bstride, int B, int Csrc, int HW, int c_lo, int n,
+                       void* dst, int dst_off, int dst_ld, void* stream);
+/* dst[b, dst_off+j, p] = src[b, src_off+j, p] for j<n  (the torch.cat halves, glow_modules.py:290,368) */
+int rfk_copy_channels(const float* src, int src_C, int src_off, float* dst, int dst_C, int dst_off,
+                      int n, int B, int HW, void* stream);
+
+/* ---- a3/a5/a7/a9  convolution as implicit GEMM on tcgen05 (Flow/glow_modules.py:111,129,
+ * Utils/modules.py:338-343) -------------------------------------------------------------------
+ * act : NHWC bf16 [B,H,W,act_ld]; the first cin_pad channels (multiple of 64) are consumed.
+ * wgt : bf16 [n_pad, taps*cin_pad] row-major, k = tap*cin_pad + c, tap = 3*ky+kx (taps = 1 or 9,
+ *       'same' zero padding); rows >= n are zero; n_pad is a multiple of 16.
+ * epilogue: v = acc*scale[o] + shift[o] (either nullable), then act_fn, then
+ *   out_kind RFK_OUT_NHWC_BF16: out bf16 [B,H,W,out_ld] at channel offset out_off
+ *   out_kind RFK_OUT_NCHW_F32 : out f32 [B,n,H,W]  (out_ld/out_off ignored)
+ * ActNorm after the conv (Conv2dNorm) is scale=exp(logs), shift=bias*exp(logs);
+ * Conv2dZeros is scale=exp(3*logs), shift=conv.bias*exp(3*logs). */
+int rfk_conv_gemm(const void* act, int B, int H, int W, int act_ld, int cin_pad,
+                  const void* wgt, int n, int n_pad, int taps,
+                  const float* scale, const float* shift, int act_fn,
+                  int out_kind, void* out, int out_ld, int out_off, void* stream);
+
+/* Same GEMM with the affine-coupling tail fused into the epilogue
+ * (Flow/glow_modules.py:275-290): n = C output channels as (shift_j, raw_j) pairs;
+ * z [B,C,H,W] f32 is updated IN PLACE on channels [C/2, C):
+ *   reverse=0: z2 = (z2 + shift)*exp(ls), logdet[b] += sum ls
+ *   reverse=1: z2 = z2*exp(-ls) - shift,  logdet[b] -= sum ls
+ * ls = clamp(raw) with clamp_scale/clamp_shift [C/2] for RFK_CLAMP_REALNVP. logdet nullable. */
+int rfk_conv_gemm_coupling(const void* act, int B, int H, int W, int act_ld, int cin_pad,
+                           const void* wgt, int n, int n_pad, int taps,
+                           const float* scale, const float* shift,
+                           float* z, int clamp_type, const float* clamp_scale, const float* clamp_shift,
+                           float* logdet, int reverse, void* stream);
+
+/* Same GEMM with the ConvLSTM cell update fused into the epilogue (Utils/modules.py:367-377).
+ * wgt rows are tile-interleaved: row (t*4+g)*ht_pad + j holds gate g in (i,f,o,g) of hidden
+ * channel t*ht + j (rows with j >= ht are zero); n_pad = n_tiles*4*ht_pad; bias likewise.
+ * c_prev, c_next, h_out: f32 NCHW with batch strides (elements) so h_out can alias a slice of the
+ * [B,T,Hc,H,W] output stack; peep (nullable) = Wci,Wcf,Wco as [3,Hc,H,W];
+ * h_nhwc (nullable): bf16 copy of h' into the next step's NHWC input at channel h_off, stride h_ld. */
+int rfk_conv_gemm_lstm(const void* act, int B, int H, int W, int act_ld, int cin_pad,
+                       const void* wgt, int hidden, int ht, int ht_pad, int taps, const float* bias,
+                       const float* c_prev, long long c_prev_bstride, const float* peep,
+                       float* c_next, long long c_next_bstride, float* h_out, long long h_bstride,
+                       void* h_nhwc, int h_off, int h_ld, void* stream);
+
+/* ---- a3  coupling tail, standalone (Flow/glow_modules.py:275-290) -------------------------
+ * nn_out [B,C,H,W] f32 = output of the coupling network; z as in rfk_conv_gemm_coupling. */
+int rfk_coupling_tail(const float* nn_out, float* z, int B, int C, int HW,
+                      int clamp_type, const float* clamp_scale, const float* clamp_shift,
+                      float* logdet, int reverse, void* stream);
+
+/* ---- a5/a7  Gaussian log-density and sampling (Flow/glow_modules.py:362-368, glow.py:139,154)
+ * params [B,2n,HW] f32 (nullable = zeros) holds (mean, raw) per `pairing`; std per `std_kind`.
+ * logp : logdet[b] += sum_{j<n,p} log N(z[b,z_off+j,p]; mean, std)        (z has z_C channels)
+ * sample: out[b,out_off+j,p] = mean + std*temperature*eps[b,j,p]           (out has out_C channels) */
+int rfk_gauss_logp(const float* z, int z_C, int z_off, const float* params, int n, int B, int HW,
+                   int pairing, int std_kind, float* logdet, void* stream);
+int rfk_gauss_sample(const float* eps, const float* params, int n, int B, int HW, int pairing,
+                     int std_kind, float temperature, float* out, int out_C, int out_off, void* stream);
+
+/* ---- a9  ConvLSTM cell update, standalone (Utils/modules.py:369-377) ----------------------
+ * cc [B,4Hc,HW] f32 in gate order i,f,o,g (bias already added); peep nullable [3,Hc,HW]. */
+int rfk_convlstm_pointwise(const float* cc, const float* c_prev, const float* peep,
+                           float* h_out, float* c_next, int B, int Hc, int HW, void* stream);
+
+/* logdet[b] += *addend  (device scalar; the parameter-only log-det terms of ActNorm / InvConv) */
+int rfk_add_scalar(float* logdet, const float* addend, float alpha, int B, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RFK_H_ */

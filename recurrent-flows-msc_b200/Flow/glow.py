@@ -1,0 +1,260 @@
+"""GlowStep and the multi-scale conditional ListGlow on librfk's sm_100a kernels.
+
+Mirrors ``Flow/glow.py`` of cdglissov/recurrent-flows-msc (class names, constructor arguments,
+method signatures, ``state_dict`` keys).  One GlowStep forward is four kernel launches:
+
+  1. rfk_mix1x1              ActNorm folded into the invertible 1x1 conv, + bf16 z1 side output
+  2. rfk_conv_gemm           conv3x3 -> ActNorm -> ReLU               (tcgen05, bf16 NHWC out)
+  3. rfk_conv_gemm           conv1x1 -> ActNorm -> ReLU               (tcgen05, bf16 NHWC out)
+  4. rfk_conv_gemm_coupling  conv3x3 -> Conv2dZeros scale -> cross split -> clamp -> affine ->
+                             per-sample log-det                       (tcgen05, z2 updated in place)
+
+with no host synchronisation (the reference issues ~186 ATen ops and three .item() syncs per step).
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import ops
+from ..Utils.modules import ActFun
+from .glow_modules import (ActNorm, AffineCoupling, BatchNormFlow, Conv2dNorm, Conv2dZeros, InvConv,  # noqa: F401
+                           Split2d, Squeeze2d, _Ctx, _ld_begin, _ld_end, _require_no_grad, _Versioned)
+
+
+class GlowStep(nn.Module):
+    """Flow/glow.py:10-41: norm -> invconv -> affine coupling (and the exact inverse)."""
+
+    def __init__(self, x_size, condition_size, args):
+        super().__init__()
+        self.n_units_affine = args.n_units_affine
+        self.non_lin_glow = args.non_lin_glow
+        self.clamp_type = args.clamp_type
+        b, c, h, w = x_size
+        if args.flow_norm == 'batchnorm':
+            self.norm = BatchNormFlow(x_size, momentum=args.flow_batchnorm_momentum)
+        else:
+            self.norm = ActNorm(c)
+        self.invconv = InvConv(c, LU_decomposed=args.LU_decomposed)
+        self.affine = AffineCoupling(x_size, condition_size, hidden_units=self.n_units_affine,
+                                     non_lin=self.non_lin_glow, clamp_type=self.clamp_type)
+        self._cache = _Versioned()
+
+    def _folded(self):
+        """ActNorm folded into the 1x1 conv, both directions, plus the parameter-only log-det.
+
+        fwd: y = W((x+b)*e^logs)          = (W diag(e^logs)) x + (W diag(e^logs)) b
+        rev: x = (W^-1 y)*e^-logs - b     = (diag(e^-logs) W^-1) y - b
+        per-pixel log-det = sum(logs) + log|det W|   (Flow/glow_modules.py:43,196)
+        """
+        def build():
+            W, W_inv, per_pixel = self.invconv.matrices()
+            logs = self.norm.logs.detach().float().reshape(-1)
+            bias = self.norm.bias.detach().float().reshape(-1)
+            s = torch.exp(logs)
+            Wf = (W * s[None, :]).contiguous()
+            bf = torch.mv(Wf, bias).contiguous()
+            Wr = (W_inv / s[:, None]).contiguous()
+            br = (-bias).contiguous()
+            return Wf, bf, Wr, br, (per_pixel + logs.sum()).reshape(())
+        return self._cache.get("fold", (self.norm.bias, self.norm.logs) + self.invconv._params(), build)
+
+    def forward(self, x, condition, logdet, reverse, _ctx=None):
+        _require_no_grad()
+        x = ops.f32c(x)
+        B, C, H, W = x.shape
+        own_ctx = _ctx is None
+        if own_ctx:
+            cc = condition.shape[1]
+            nn_in = ops.workspace(("cpl_in", C // 2 + cc), (B, H, W, ops.pad_to(C // 2 + cc, 64)), x.device)
+            ops.pack_nhwc(ops.f32c(condition), 0, cc, nn_in, 0)
+            _ctx = _Ctx(nn_in, cc)
+        cc = _ctx.cond_channels
+        ld, extra = _ld_begin(logdet, B, x.device, inplace=not own_ctx)
+        if not reverse:
+            self.norm.maybe_initialize(x)
+            Wf, bf, _, _, per_pixel = self._folded()
+            y = ops.mix1x1(x, Wf, bf, side=_ctx.nn_in, side_n=C // 2, side_off=cc)
+            _ctx.z1_packed = True
+            y, ld = self.affine(y, condition, ld, False, _ctx=_ctx)
+            _ctx.z1_packed = False
+            if ld is not None:
+                ld.add_(per_pixel * (H * W))
+            return y, _ld_end(ld, extra)
+        if own_ctx:
+            x = x.clone()  # the coupling inverse below works in place
+        y, ld = self.affine(x, condition, ld, True, _ctx=_ctx)
+        self.norm.maybe_initialize(y)
+        _, _, Wr, br, per_pixel = self._folded()
+        out = ops.mix1x1(y, Wr, br, side=_ctx.nn_in, side_n=C // 2, side_off=cc)
+        _ctx.z1_packed = True   # the next reverse step of this level reads this z1
+        if ld is not None:
+            ld.sub_(per_pixel * (H * W))
+        return out, _ld_end(ld, extra)
+
+
+class ListGlow(nn.Module):
+    """Flow/glow.py:43-160: L levels of (Squeeze2d, K x GlowStep, Split2d) with a learned or N(0,1) prior."""
+
+    def __init__(self, x_size, condition_size, base_dist_size, args):
+        super().__init__()
+        assert isinstance(condition_size, list), "condition_size is not a list, make sure it fits L"
+        self.learn_prior = args.learn_prior
+        self.n_units_prior = args.n_units_prior
+        self.make_conditional = args.make_conditional
+        self.base_norm = args.base_norm
+        self.non_lin_glow = args.non_lin_glow
+        self.conditional_clamp_function = args.split2d_act
+        self.L = args.L
+        self.K = args.K
+        self.n_bits = args.n_bits
+        Bx, Cx, Hx, Wx = x_size
+        Bc, Cc, Hc, Wc = base_dist_size
+        layers = []
+        for l in range(0, self.L):
+            layers.append(Squeeze2d())
+            Cx, Hx, Wx = Cx * 4, Hx // 2, Wx // 2
+            x_size = [Bx, Cx, Hx, Wx]
+            condition_size_cur = condition_size[l]
+            for i in range(0, self.K):
+                layers.append(GlowStep(x_size, condition_size_cur, args))
+            if l < (self.L - 1):
+                layers.append(Split2d(x_size, condition_size_cur, self.make_conditional,
+                                      self.conditional_clamp_function))
+                Cx = Cx // 2
+                x_size = [Bx, Cx, Hx, Wx]
+        self.glow_frame = nn.ModuleList(layers)
+        self._z_channels = Cx
+        if self.learn_prior:
+            self.prior = nn.Sequential(
+                Conv2dNorm(Cc, self.n_units_prior, norm=self.base_norm),
+                ActFun(self.non_lin_glow),
+                Conv2dNorm(self.n_units_prior, self.n_units_prior // 2, norm=self.base_norm),
+                ActFun(self.non_lin_glow),
+                Conv2dZeros(in_channel=self.n_units_prior // 2, out_channel=2 * Cx),
+            )
+            self._base_channels = Cc
+        # learn_prior == False: the reference's zero `prior_in` is mean = log_scale = 0, which the
+        # Gaussian kernels take as a null parameter pointer.
+
+    # -- level bookkeeping ------------------------------------------------------------------
+    def _level_ctx(self, z, cond):
+        B, C, H, W = z.shape
+        cc = cond.shape[1]
+        assert cond.shape[2:4] == z.shape[2:4], "condition and x in affine needs to match"
+        nn_in = ops.workspace(("lvl_in", C // 2 + cc), (B, H, W, ops.pad_to(C // 2 + cc, 64)), z.device)
+        ops.pack_nhwc(ops.f32c(cond), 0, cc, nn_in, 0)
+        return _Ctx(nn_in, cc)
+
+    def g(self, z, condition, logdet, temperature, eps_list=None):
+        """z -> x (Flow/glow.py:90-102).  ``eps_list[l]`` optionally injects level l's Split2d draw."""
+        _require_no_grad()
+        x = ops.f32c(z).clone()
+        l = len(condition) - 1
+        ld, extra = _ld_begin(logdet, x.shape[0], x.device)
+        ctx = None
+        for step in reversed(self.glow_frame):
+            if isinstance(step, Squeeze2d):
+                x = step(x, undo_squeeze=True)
+                ctx = None
+            elif isinstance(step, Split2d):
+                l = l - 1
+                ctx = self._level_ctx_for_split(x, condition[l], step)
+                x, ld = step(x, condition[l], logdet=ld, reverse=True, temperature=temperature, _ctx=ctx,
+                             eps=None if eps_list is None else eps_list[l])
+            else:
+                if ctx is None:
+                    ctx = self._level_ctx(x, condition[l])
+                x, ld = step(x, condition[l], logdet=ld, reverse=True, _ctx=ctx)
+        return x, _ld_end(ld, extra)
+
+    def _level_ctx_for_split(self, z1, cond, split):
+        # reverse direction: the level's tensor has 2*half channels once Split2d has re-attached z2
+        B, half, H, W = z1.shape
+        cc = cond.shape[1]
+        nn_in = ops.workspace(("lvl_in", half + cc), (B, H, W, ops.pad_to(half + cc, 64)), z1.device)
+        ops.pack_nhwc(ops.f32c(cond), 0, cc, nn_in, 0)
+        return _Ctx(nn_in, cc)
+
+    def f(self, x, condition, logdet):
+        """x -> z (Flow/glow.py:105-117)."""
+        _require_no_grad()
+        z = ops.f32c(x)
+        l = 0
+        ld, extra = _ld_begin(logdet, z.shape[0], z.device)
+        ctx = None
+        for step in self.glow_frame:
+            if isinstance(step, Squeeze2d):
+                z = step(z, undo_squeeze=False)
+                ctx = self._level_ctx(z, condition[l])
+            elif isinstance(step, Split2d):
+                z, ld = step(z, condition[l], logdet=ld, reverse=False, _ctx=ctx)
+                l = l + 1
+            else:
+                z, ld = step(z, condition[l], logdet=ld, reverse=False, _ctx=ctx)
+        return z, _ld_end(ld, extra)
+
+    def uniform_binning_correction(self, x):
+        """Flow/glow.py:119-126 (the U(0, 2^-n_bits) draw stays in torch's generator)."""
+        n_bins = 2 ** self.n_bits
+        b, c, h, w = x.size()
+        x_noise = x + torch.zeros_like(x).uniform_(0, 1.0 / n_bins)
+        objective = -np.log(n_bins) * (c * h * w) * torch.ones(b, device=x.device)
+        return x_noise, objective
+
+    def _prior_params(self, base_condition):
+        if not self.learn_prior:
+            return None
+        bc = ops.f32c(base_condition)
+        B, Cb, H, W = bc.shape
+        dev = bc.device
+        u1, u2 = self.n_units_prior, self.n_units_prior // 2
+        a0 = ops.workspace(("pr_in", Cb), (B, H, W, ops.pad_to(Cb, 64)), dev)
+        a1 = ops.workspace(("pr_h1", u1), (B, H, W, ops.pad_to(u1, 64)), dev)
+        a2 = ops.workspace(("pr_h2", u2), (B, H, W, ops.pad_to(u2, 64)), dev)
+        ops.pack_nhwc(bc, 0, Cb, a0, 0)
+        self.prior[0].fused(a0, a1, self.non_lin_glow)
+        self.prior[2].fused(a1, a2, self.non_lin_glow)
+        params = torch.empty(B, 2 * self._z_channels, H, W, device=dev, dtype=torch.float32)
+        return self.prior[4].fused(a2, params)
+
+    def log_prob(self, x, condition, base_condition, logdet=0, noise=None):
+        """Flow/glow.py:128-141.  Returns (z, nll[B]).  ``noise`` optionally injects the dequantisation draw."""
+        _require_no_grad()
+        assert isinstance(condition, list), "Condition is not a list, make sure it fits L"
+        if noise is None:
+            x, obj_unif = self.uniform_binning_correction(x)
+        else:
+            b, c, h, w = x.size()
+            obj_unif = -np.log(2 ** self.n_bits) * (c * h * w) * torch.ones(b, device=x.device)
+            x = x + noise
+        z, obj = self.f(x, condition, logdet)
+        if not torch.is_tensor(obj) or obj.dim() != 1:
+            obj = torch.zeros(z.shape[0], device=z.device) + obj
+        obj = obj + obj_unif
+        ops.gauss_logp(z, 0, self._prior_params(base_condition), z.shape[1], ops.PAIR_SPLIT, "exp", obj)
+        return z, -obj
+
+    def sample(self, z, condition, base_condition, num_samples=32, temperature=0.8, eval_params=False,
+               eps_prior=None, eps_list=None):
+        """Flow/glow.py:143-160."""
+        with torch.no_grad():
+            mean = std = None
+            if z is None:
+                params = self._prior_params(base_condition)
+                ref = ops.f32c(condition[-1])
+                hh, ww = ref.shape[2], ref.shape[3]
+                n = params.shape[0] if params is not None else num_samples
+                cz = self._z_channels
+                if eps_prior is None:
+                    eps_prior = torch.randn(n, cz, hh, ww, device=ref.device, dtype=torch.float32)
+                z = torch.empty(n, cz, hh, ww, device=ref.device, dtype=torch.float32)
+                ops.gauss_sample(ops.f32c(eps_prior), params, cz, ops.PAIR_SPLIT, "exp", temperature, z, 0)
+                if eval_params:
+                    if params is None:
+                        mean, std = torch.zeros_like(z), torch.ones_like(z)
+                    else:
+                        mean, std = params[:, :cz], torch.exp(params[:, cz:])
+            x, _ = self.g(z, condition, logdet=None, temperature=temperature, eps_list=eps_list)
+        if eval_params:
+            return x, (mean, std)
+        return x

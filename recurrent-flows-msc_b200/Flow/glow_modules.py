@@ -1,0 +1,423 @@
+"""Glow primitives with the reference's module interface, running on librfk's sm_100a kernels.
+
+Mirrors ``Flow/glow_modules.py`` of cdglissov/recurrent-flows-msc: same class names,
+constructor arguments, ``forward`` signatures and ``state_dict`` keys, so a
+checkpoint of the reference loads unchanged.  The arithmetic is not PyTorch's: every forward
+enqueues hand-written CUDA kernels through the C ABI (include/rfk.h).  There is no CPU path.
+
+Round-1 scope: forward / reverse evaluation (density, sampling).  Backward kernels are not
+written yet, so the modules refuse to run with autograd recording enabled instead of silently
+returning tensors without a graph.
+"""
+import torch
+import torch.nn as nn
+
+from .. import ops
+from ..Utils.utils import split_feature  # noqa: F401  (re-exported like the reference)
+from ..Utils.modules import ActFun
+
+
+def _require_no_grad():
+    if torch.is_grad_enabled():
+        raise RuntimeError("recurrent-flows-msc_b200: backward kernels are not implemented yet; "
+                           "call the flow under torch.no_grad() (density evaluation / sampling)")
+
+
+class _Versioned:
+    """Cache of tensors derived from parameters, rebuilt when a parameter is modified in place
+    (optimizer step, load_state_dict) or re-allocated (.to(), .cuda())."""
+
+    def __init__(self):
+        self._store = {}
+
+    def get(self, key, params, build):
+        ver = tuple((p.data_ptr(), p._version) for p in params)
+        hit = self._store.get(key)
+        if hit is None or hit[0] != ver:
+            with torch.no_grad():
+                hit = (ver, build())
+            self._store[key] = hit
+        return hit[1]
+
+    def clear(self):
+        self._store.clear()
+
+
+def _ld_begin(logdet, B, device, inplace=False):
+    """Normalise the reference's logdet argument (None | number | 0-dim | [B]) to a [B] f32
+    accumulator the kernels add into, plus whatever must be added back afterwards."""
+    if logdet is None:
+        return None, None
+    if torch.is_tensor(logdet) and logdet.dim() == 1 and logdet.shape[0] == B and logdet.is_cuda:
+        buf = logdet.detach()
+        if buf.dtype != torch.float32 or not buf.is_contiguous() or not inplace:
+            buf = buf.to(torch.float32).clone()
+        return buf, None
+    return torch.zeros(B, device=device, dtype=torch.float32), logdet
+
+
+def _ld_end(buf, extra):
+    if buf is None:
+        return None
+    if extra is None or (not torch.is_tensor(extra) and extra == 0):
+        return buf
+    return buf + extra
+
+
+class _Ctx:
+    """Per-level state ListGlow threads through its modules: the coupling network's NHWC input
+    buffer with the condition already packed, and which other parts are already in place."""
+
+    def __init__(self, nn_in, cond_channels):
+        self.nn_in = nn_in
+        self.cond_channels = cond_channels
+        self.z1_packed = False
+
+
+# ----------------------------------------------------------------------------------------
+class ActNorm(nn.Module):
+    """Flow/glow_modules.py:10-54."""
+
+    def __init__(self, num_channels):
+        super().__init__()
+        size = [1, num_channels, 1, 1]
+        self.register_parameter("bias", nn.Parameter(torch.zeros(*size), requires_grad=True))
+        self.register_parameter("logs", nn.Parameter(torch.zeros(*size), requires_grad=True))
+        self.register_buffer("initialized", torch.tensor(0, dtype=torch.uint8))
+        self._init_known = None  # host mirror of `initialized`: no .item() sync per call
+        self._cache = _Versioned()
+
+    def _load_from_state_dict(self, *a, **k):
+        super()._load_from_state_dict(*a, **k)
+        self._init_known = None
+        self._cache.clear()
+
+    def is_initialized(self):
+        if self._init_known is None:
+            self._init_known = bool(self.initialized.item() != 0)  # one sync, then cached
+        return self._init_known
+
+    def mark_initialized(self):
+        self.initialized.fill_(1)
+        self._init_known = True
+
+    def initialize(self, input):
+        """Flow/glow_modules.py:22-31: only in training mode; unbiased std, +1e-6."""
+        if not self.training:
+            return
+        with torch.no_grad():
+            ops.actnorm_init(ops.f32c(input), self.bias.data, self.logs.data)
+        self._cache.clear()
+
+    def maybe_initialize(self, input):
+        if not self.is_initialized():
+            self.initialize(input)
+            self.mark_initialized()
+
+    def affine(self):
+        """(scale, shift) with y = x*scale + shift == (x + bias)*exp(logs); cached."""
+        def build():
+            s = torch.exp(self.logs.detach().float().reshape(-1))
+            return s.contiguous(), (self.bias.detach().float().reshape(-1) * s).contiguous()
+        return self._cache.get("affine", (self.bias, self.logs), build)
+
+    def forward(self, input, logdet, reverse):
+        _require_no_grad()
+        self.maybe_initialize(input)
+        x = ops.f32c(input)
+        y = ops.actnorm(x, self.bias.data, self.logs.data, reverse)
+        if logdet is not None:
+            dlogdet = torch.sum(self.logs.detach()) * (x.shape[2] * x.shape[3])
+            logdet = logdet - dlogdet if reverse else logdet + dlogdet
+        return y, logdet
+
+
+class Conv2dZeros(nn.Module):
+    """Flow/glow_modules.py:106-121: zero-initialised conv, output * exp(3*logs)."""
+
+    def __init__(self, in_channel, out_channel, kernel_size=[3, 3], stride=[1, 1]):
+        super().__init__()
+        assert list(stride) == [1, 1], "only stride 1 is used on this path"
+        padding = (kernel_size[0] - 1) // 2
+        self.conv = nn.Conv2d(in_channel, out_channel, kernel_size, stride, padding)
+        self.logscale_factor = 3
+        self.register_parameter("logs", nn.Parameter(torch.zeros(out_channel, 1, 1)))
+        self.conv.weight.data.zero_()
+        self.conv.bias.data.zero_()
+        self.taps = kernel_size[0] * kernel_size[1]
+        assert self.taps in (1, 9), "kernel must be 1x1 or 3x3"
+        self._cache = _Versioned()
+
+    def packed(self, key="id", in_perm=None):
+        return self._cache.get(("w", key), (self.conv.weight,), lambda: ops.pack_conv_weight(self.conv.weight, in_perm))
+
+    def affine(self):
+        def build():
+            s = torch.exp(self.logs.detach().float().reshape(-1) * self.logscale_factor)
+            return s.contiguous(), (self.conv.bias.detach().float() * s).contiguous()
+        return self._cache.get("affine", (self.logs, self.conv.bias), build)
+
+    def fused(self, act, out, key="id", in_perm=None):
+        """act NHWC bf16 -> out NCHW f32 = (conv + bias) * exp(3 logs)."""
+        wgt, cin_pad = self.packed(key, in_perm)
+        scale, shift = self.affine()
+        return ops.conv_gemm(act, cin_pad, wgt, self.conv.out_channels, self.taps, scale, shift, "none", out)
+
+    def forward(self, input):
+        _require_no_grad()
+        x = ops.f32c(input)
+        B, C, H, W = x.shape
+        act = ops.workspace(("cz_in", C), (B, H, W, ops.pad_to(C, 64)), x.device)
+        ops.pack_nhwc(x, 0, C, act, 0)
+        out = torch.empty(B, self.conv.out_channels, H, W, device=x.device, dtype=torch.float32)
+        return self.fused(act, out)
+
+
+class Conv2dNorm(nn.Module):
+    """Flow/glow_modules.py:123-147: bias-free conv followed by ActNorm."""
+
+    def __init__(self, in_channels, out_channels, kernel_size=[3, 3], stride=[1, 1], norm="actnorm"):
+        super().__init__()
+        assert list(stride) == [1, 1], "only stride 1 is used on this path"
+        if norm != "actnorm":
+            raise NotImplementedError("Conv2dNorm(norm='batchnorm') is outside the B200 hot-path scope (SURVEY 8f3)")
+        padding = [(kernel_size[0] - 1) // 2, (kernel_size[1] - 1) // 2]
+        self.conv = nn.Conv2d(in_channels, out_channels, kernel_size, stride, padding, bias=False)
+        self.conv.weight.data.normal_(mean=0.0, std=0.05)
+        self.norm = norm
+        self.norm_type = ActNorm(out_channels)
+        self.taps = kernel_size[0] * kernel_size[1]
+        assert self.taps in (1, 9), "kernel must be 1x1 or 3x3"
+        self._cache = _Versioned()
+
+    def packed(self, key="id", in_perm=None):
+        return self._cache.get(("w", key), (self.conv.weight,), lambda: ops.pack_conv_weight(self.conv.weight, in_perm))
+
+    def fused(self, act, out, act_fn="none", key="id", in_perm=None, out_off=0):
+        """act NHWC bf16 -> out (NHWC bf16 at channel out_off, or NCHW f32) = act_fn(ActNorm(conv(act)))."""
+        wgt, cin_pad = self.packed(key, in_perm)
+        n = self.conv.out_channels
+        an = self.norm_type
+        if not an.is_initialized():
+            if an.training:  # data-dependent init on the raw convolution output (glow_modules.py:140-142)
+                B, H, W, _ = act.shape
+                raw = torch.empty(B, n, H, W, device=act.device, dtype=torch.float32)
+                ops.conv_gemm(act, cin_pad, wgt, n, self.taps, None, None, "none", raw)
+                an.initialize(raw)
+            an.mark_initialized()
+        scale, shift = an.affine()
+        return ops.conv_gemm(act, cin_pad, wgt, n, self.taps, scale, shift, act_fn, out, out_off)
+
+    def forward(self, input):
+        _require_no_grad()
+        x = ops.f32c(input)
+        B, C, H, W = x.shape
+        act = ops.workspace(("cn_in", C), (B, H, W, ops.pad_to(C, 64)), x.device)
+        ops.pack_nhwc(x, 0, C, act, 0)
+        out = torch.empty(B, self.conv.out_channels, H, W, device=x.device, dtype=torch.float32)
+        return self.fused(act, out)
+
+
+class InvConv(nn.Module):
+    """Flow/glow_modules.py:150-221: invertible 1x1 convolution, optionally LU-parameterised."""
+
+    def __init__(self, num_channels, LU_decomposed):
+        super().__init__()
+        w_shape = [num_channels, num_channels]
+        w_init = torch.linalg.qr(torch.randn(*w_shape))[0]
+        if not LU_decomposed:
+            self.weight = nn.Parameter(torch.Tensor(w_init))
+        else:
+            p, lower, upper = torch.linalg.lu(w_init)
+            s = torch.diag(upper)
+            self.register_buffer("p", p)
+            self.register_buffer("sign_s", torch.sign(s))
+            self.lower = nn.Parameter(lower)
+            self.log_s = nn.Parameter(torch.log(torch.abs(s)))
+            self.upper = nn.Parameter(torch.triu(upper, 1))
+            self.l_mask = torch.tril(torch.ones(w_shape), -1)
+            self.eye = torch.eye(*w_shape)
+        self.w_shape = w_shape
+        self.LU_decomposed = LU_decomposed
+        self._cache = _Versioned()
+
+    def _params(self):
+        return (self.lower, self.upper, self.log_s) if self.LU_decomposed else (self.weight,)
+
+    def matrices(self):
+        """(W, W^-1, per-pixel log|det W|) as device tensors; cached until a parameter changes.
+        Follows Flow/glow_modules.py:188-205 (three triangular inverses in the LU form)."""
+        def build():
+            if not self.LU_decomposed:
+                w = self.weight.detach().float()
+                return w.contiguous(), torch.linalg.inv(w).contiguous(), torch.linalg.slogdet(w)[1]
+            dev = self.lower.device
+            l_mask, eye = self.l_mask.to(dev), self.eye.to(dev)
+            lower = self.lower.detach() * l_mask + eye
+            u = self.upper.detach() * l_mask.transpose(0, 1).contiguous()
+            u = u + torch.diag(self.sign_s * torch.exp(self.log_s.detach()))
+            w = torch.matmul(self.p, torch.matmul(lower, u))
+            w_inv = torch.matmul(torch.linalg.inv(u), torch.matmul(torch.linalg.inv(lower), torch.linalg.inv(self.p)))
+            return w.contiguous(), w_inv.contiguous(), torch.sum(self.log_s.detach())
+        return self._cache.get("m", self._params(), build)
+
+    def get_weight(self, input, reverse):
+        b, c, h, w = input.shape
+        W, W_inv, per_pixel = self.matrices()
+        weight = W_inv if reverse else W
+        return weight.view(self.w_shape[0], self.w_shape[1], 1, 1), per_pixel * h * w
+
+    def forward(self, input, logdet, reverse):
+        _require_no_grad()
+        x = ops.f32c(input)
+        weight, dlogdet = self.get_weight(x, reverse)
+        z = ops.mix1x1(x, weight.view(self.w_shape))
+        if logdet is not None:
+            logdet = logdet - dlogdet if reverse else logdet + dlogdet
+        return z, logdet
+
+
+class AffineCoupling(nn.Module):
+    """Flow/glow_modules.py:223-291.  Three tensor-core convolutions; the ActNorm+ReLU of the hidden
+    layers and the whole coupling tail (cross split, clamp, affine, per-sample log-det) are epilogues."""
+
+    def __init__(self, x_size, condition_size, hidden_units=256, non_lin='relu', clamp_type="realnvp"):
+        super().__init__()
+        Bx, Cx, Hx, Wx = x_size
+        B, C, H, W = condition_size
+        channels = Cx // 2 + C
+        self.net = nn.Sequential(
+            Conv2dNorm(channels, hidden_units),
+            ActFun(non_lin),
+            Conv2dNorm(hidden_units, hidden_units, kernel_size=[1, 1]),
+            ActFun(non_lin),
+            Conv2dZeros(hidden_units, Cx),
+        )
+        self.non_lin = non_lin
+        self.hidden_units = hidden_units
+        self.clamp_type = clamp_type if clamp_type in ("glow", "softclamp", "realnvp") else "none"
+        if clamp_type == "realnvp":
+            self.scale = nn.Parameter(torch.zeros(Cx // 2, 1, 1), requires_grad=True)
+            self.scale_shift = nn.Parameter(torch.zeros(Cx // 2, 1, 1), requires_grad=True)
+        self._half, self._cond = Cx // 2, C
+
+    def _perm(self, device):
+        # NHWC staging order is [condition | z1]; the reference's weight expects cat[z1, condition]
+        half, cc = self._half, self._cond
+        return torch.cat([torch.arange(half, half + cc, device=device), torch.arange(0, half, device=device)])
+
+    def forward(self, x, condition, logdet, reverse, _ctx=None):
+        _require_no_grad()
+        assert condition.shape[2:4] == x.shape[2:4], "condition and x in affine needs to match"
+        z = ops.f32c(x)
+        B, C, H, W = z.shape
+        half, cc = C // 2, condition.shape[1]
+        dev = z.device
+        if _ctx is None:
+            nn_in = ops.workspace(("cpl_in", half + cc), (B, H, W, ops.pad_to(half + cc, 64)), dev)
+            ops.pack_nhwc(ops.f32c(condition), 0, cc, nn_in, 0)
+            ops.pack_nhwc(z, 0, half, nn_in, cc)
+            out = z.clone()          # module contract: inputs are never modified
+        else:
+            nn_in = _ctx.nn_in
+            if not _ctx.z1_packed:
+                ops.pack_nhwc(z, 0, half, nn_in, cc)
+            out = z                  # ListGlow owns this intermediate: update z2 in place
+        hp = ops.pad_to(self.hidden_units, 64)
+        h1 = ops.workspace(("cpl_h1", self.hidden_units), (B, H, W, hp), dev)
+        h2 = ops.workspace(("cpl_h2", self.hidden_units), (B, H, W, hp), dev)
+        self.net[0].fused(nn_in, h1, self.non_lin, "cz", self._perm(dev))
+        self.net[2].fused(h1, h2, self.non_lin)
+        last = self.net[4]
+        wgt, cin_pad = last.packed()
+        scale, shift = last.affine()
+        ld, extra = _ld_begin(logdet, B, dev, inplace=_ctx is not None)
+        cs = self.scale.detach().reshape(-1) if self.clamp_type == "realnvp" else None
+        csh = self.scale_shift.detach().reshape(-1) if self.clamp_type == "realnvp" else None
+        ops.conv_gemm_coupling(h2, cin_pad, wgt, C, last.taps, scale, shift, out, self.clamp_type, cs, csh, ld, reverse)
+        return out, _ld_end(ld, extra)
+
+
+class Squeeze2d(nn.Module):
+    """Flow/glow_modules.py:294-310 (bit exact)."""
+
+    def forward(self, x, undo_squeeze):
+        _require_no_grad()
+        return ops.squeeze2d(ops.f32c(x), bool(undo_squeeze))
+
+
+class Split2d(nn.Module):
+    """Flow/glow_modules.py:312-369."""
+
+    def __init__(self, x_size, condition_size, make_conditional=True, clamp_function='softplus'):
+        super().__init__()
+        self.make_conditional = make_conditional
+        Bx, Cx, Hx, Wx = x_size
+        non_lin = 'relu'
+        if make_conditional:
+            B, C, H, W = condition_size
+            channels = Cx // 2 + C
+            self.convcond = nn.Sequential(
+                Conv2dNorm(C, C),
+                ActFun(non_lin),
+                Conv2dNorm(C, C, kernel_size=[1, 1]),
+                ActFun(non_lin),
+            )
+            self._cond = C
+        else:
+            channels = Cx // 2
+            self._cond = 0
+        self.conv = nn.Sequential(Conv2dZeros(channels, Cx),)
+        self._half = Cx // 2
+        if clamp_function not in ('softplus', 'exp'):
+            assert False, 'Please specify a clamp function for the split2d from the set {softplus, exp}'
+        self.clamp_function = clamp_function
+
+    def _params(self, z1_src, condition, _ctx):
+        """(mean, raw log-scale) tensor [B, 2*half, H, W] from z1 = first `half` channels of z1_src."""
+        B, _, H, W = z1_src.shape
+        half, cc, dev = self._half, self._cond, z1_src.device
+        sp_in = ops.workspace(("sp_in", half + cc), (B, H, W, ops.pad_to(half + cc, 64)), dev)
+        perm = None
+        if self.make_conditional:
+            if _ctx is None:
+                cbuf = ops.workspace(("sp_c", cc), (B, H, W, ops.pad_to(cc, 64)), dev)
+                ops.pack_nhwc(ops.f32c(condition), 0, cc, cbuf, 0)
+            else:
+                cbuf = _ctx.nn_in   # condition already packed at channels [0, cc)
+            t1 = ops.workspace(("sp_t1", cc), (B, H, W, ops.pad_to(cc, 64)), dev)
+            self.convcond[0].fused(cbuf, t1, "relu")
+            self.convcond[2].fused(t1, sp_in, "relu")
+            perm = torch.cat([torch.arange(half, half + cc, device=dev), torch.arange(0, half, device=dev)])
+        ops.pack_nhwc(z1_src, 0, half, sp_in, cc)
+        params = torch.empty(B, 2 * half, H, W, device=dev, dtype=torch.float32)
+        return self.conv[0].fused(sp_in, params, "cz", perm)
+
+    def forward(self, x, condition, logdet, reverse, temperature=None, _ctx=None, eps=None):
+        _require_no_grad()
+        x = ops.f32c(x)
+        B, _, H, W = x.shape
+        half = self._half
+        params = self._params(x, condition, _ctx)
+        if not reverse:
+            z1 = torch.empty(B, half, H, W, device=x.device, dtype=torch.float32)
+            ops.copy_channels(x, 0, z1, 0, half)
+            ld, extra = _ld_begin(logdet, B, x.device, inplace=_ctx is not None)
+            if ld is not None:
+                ops.gauss_logp(x, half, params, half, ops.PAIR_CROSS, self.clamp_function, ld)
+            return z1, _ld_end(ld, extra)
+        z = torch.empty(B, 2 * half, H, W, device=x.device, dtype=torch.float32)
+        ops.copy_channels(x, 0, z, 0, half)
+        if eps is None:  # the N(0,1) draw stays in torch's generator (last row)
+            eps = torch.randn(B, half, H, W, device=x.device, dtype=torch.float32)
+        ops.gauss_sample(ops.f32c(eps), params, half, ops.PAIR_CROSS, self.clamp_function, temperature, z, half)
+        return z, logdet
+
+
+class BatchNormFlow(nn.Module):
+    """Flow/glow_modules.py:56-104 -- alternative flow_norm; SURVEY 8(f3) 'next' row, not built yet."""
+
+    def __init__(self, x_size, momentum=0.1, eps=1e-5):
+        super().__init__()
+        raise NotImplementedError("BatchNormFlow (flow_norm='batchnorm') is a 'next' row (SURVEY 8f3); "
+                                  "use flow_norm='actnorm'")

@@ -1,0 +1,80 @@
+"""ctypes binding of librfk.so (include/rfk.h).
+
+The library is the product; there is no fallback.  If it is missing, cannot be
+loaded, or a call returns a non-zero code, an exception is raised.
+"""
+import ctypes
+import os
+from ctypes import c_float, c_int, c_longlong, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librfk.so")
+
+# name -> argtypes; every function returns int except rfk_last_error
+SIGNATURES = {
+    "rfk_version": [],
+    "rfk_device_info": [c_void_p, c_void_p, c_void_p],
+    "rfk_squeeze2d": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    "rfk_actnorm": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
+    "rfk_actnorm_init": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
+    "rfk_mix1x1": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                   c_void_p, c_int, c_int, c_int, c_void_p],
+    "rfk_pack_nhwc_bf16": [c_void_p, c_longlong, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p],
+    "rfk_copy_channels": [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    "rfk_conv_gemm": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int,
+                      c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p],
+    "rfk_conv_gemm_coupling": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int,
+                               c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p],
+    "rfk_conv_gemm_lstm": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int,
+                           c_void_p, c_void_p, c_longlong, c_void_p, c_void_p, c_longlong, c_void_p, c_longlong,
+                           c_void_p, c_int, c_int, c_void_p],
+    "rfk_coupling_tail": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int,
+                          c_void_p],
+    "rfk_gauss_logp": [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
+    "rfk_gauss_sample": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_int, c_int,
+                         c_void_p],
+    "rfk_convlstm_pointwise": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
+    "rfk_add_scalar": [c_void_p, c_void_p, c_float, c_int, c_void_p],
+}
+
+# enums of rfk.h
+ACT = {"none": 0, "relu": 1, "leakyrelu": 2}
+CLAMP = {"none": 0, "realnvp": 1, "glow": 2, "softclamp": 3}
+PAIR_CROSS, PAIR_SPLIT = 0, 1
+STD = {"softplus": 0, "exp": 1}
+OUT_NHWC_BF16, OUT_NCHW_F32 = 0, 1
+
+
+class RfkError(RuntimeError):
+    pass
+
+
+_lib = None
+launches = 0  # kernels enqueued through this binding (bench.py reports it as gpu_launches)
+
+
+def lib():
+    """Load librfk.so once; raise if it is absent (build with __graft_entry__.build())."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RfkError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(nvcc, sm_100a). There is no CPU fallback.")
+        l = ctypes.CDLL(LIB_PATH)
+        for name, argtypes in SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.argtypes = argtypes
+            fn.restype = c_int
+        l.rfk_last_error.argtypes = []
+        l.rfk_last_error.restype = ctypes.c_char_p
+        _lib = l
+    return _lib
+
+
+def call(name, *args):
+    global launches
+    rc = getattr(lib(), name)(*args)
+    if rc != 0:
+        raise RfkError(f"{name} failed ({rc}): {lib().rfk_last_error().decode()}")
+    launches += 1
+    return rc

@@ -1,0 +1,48 @@
+// librfk: error reporting and device queries.
+#include <stdlib.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace rfk {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;  // B200
+  }
+  return n;
+}
+
+}  // namespace rfk
+
+extern "C" int rfk_version(void) { return RFK_VERSION; }
+
+extern "C" const char* rfk_last_error(void) { return rfk::g_err; }
+
+extern "C" int rfk_device_info(int* sm_count, int* cc_major, int* cc_minor) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  cudaDeviceProp prop;
+  if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, dev);
+  if (e != cudaSuccess) {
+    rfk::set_error("rfk_device_info: %s", cudaGetErrorString(e));
+    return RFK_ECUDA;
+  }
+  if (sm_count) *sm_count = prop.multiProcessorCount;
+  if (cc_major) *cc_major = prop.major;
+  if (cc_minor) *cc_minor = prop.minor;
+  return RFK_OK;
+}

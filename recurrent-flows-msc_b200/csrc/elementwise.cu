@@ -1,0 +1,606 @@
+// Bandwidth-bound kernels of the Glow step and the ConvLSTM cell (sm_100a).
+// Every kernel streams its tensors once with 128-bit accesses where the shape allows it and
+// reduces per-sample sums with warp shuffles + one atomic per CTA.
+#include "common.cuh"
+
+namespace rfk {
+
+constexpr int kThreads = 256;
+
+// ------------------------------------------------------------------------------------------
+// a4  Squeeze2d  (Flow/glow_modules.py:298-310)
+// ------------------------------------------------------------------------------------------
+// forward, W % 8 == 0: one thread reads 8 consecutive pixels of one input row (2 x 128 bit) and
+// writes 4 pixels to each of the two dx planes (1 x 128 bit each).
+__global__ void __launch_bounds__(kThreads) squeeze_fwd_v8(const float* __restrict__ x, float* __restrict__ y,
+                                                           int C, int H, int W, long long total8) {
+  const int W8 = W >> 3, Ho = H >> 1, Wo = W >> 1;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total8;
+       t += (long long)gridDim.x * blockDim.x) {
+    int x8 = (int)(t % W8);
+    long long r = t / W8;
+    int row = (int)(r % H);
+    long long bc = r / H;  // b*C + c
+    const float4* src = reinterpret_cast<const float4*>(x + (bc * H + row) * W + x8 * 8);
+    float4 a = ld_stream(src), b = ld_stream(src + 1);
+    int dy = row & 1, i = row >> 1;
+    long long b_ = bc / C;
+    int c = (int)(bc % C);
+    float* d0 = y + (((b_ * 4 * C + 4 * c + 2 * dy) * Ho + i) * (long long)Wo) + x8 * 4;
+    st_stream(reinterpret_cast<float4*>(d0), make_float4(a.x, a.z, b.x, b.z));
+    st_stream(reinterpret_cast<float4*>(d0 + (long long)Ho * Wo), make_float4(a.y, a.w, b.y, b.w));
+  }
+}
+
+// undo, Wout % 8 == 0: inverse of the above (reads 2 x 128 bit from the two dx planes, writes 2 x 128 bit)
+__global__ void __launch_bounds__(kThreads) squeeze_undo_v8(const float* __restrict__ x, float* __restrict__ y,
+                                                            int Co, int Hout, int Wout, long long total8) {
+  const int W8 = Wout >> 3, Hi = Hout >> 1, Wi = Wout >> 1;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total8;
+       t += (long long)gridDim.x * blockDim.x) {
+    int x8 = (int)(t % W8);
+    long long r = t / W8;
+    int row = (int)(r % Hout);
+    long long bc = r / Hout;  // b*Co + c  (output channel)
+    int dy = row & 1, i = row >> 1;
+    long long b_ = bc / Co;
+    int c = (int)(bc % Co);
+    const float* s0 = x + (((b_ * 4 * Co + 4 * c + 2 * dy) * Hi + i) * (long long)Wi) + x8 * 4;
+    float4 e = ld_stream(reinterpret_cast<const float4*>(s0));
+    float4 o = ld_stream(reinterpret_cast<const float4*>(s0 + (long long)Hi * Wi));
+    float4* dst = reinterpret_cast<float4*>(y + (bc * Hout + row) * Wout + x8 * 8);
+    st_stream(dst, make_float4(e.x, o.x, e.y, o.y));
+    st_stream(dst + 1, make_float4(e.z, o.z, e.w, o.w));
+  }
+}
+
+// generic scalar version for narrow maps (W in {2,4,6,...}); indexed by OUTPUT element
+__global__ void __launch_bounds__(kThreads) squeeze_scalar(const float* __restrict__ x, float* __restrict__ y,
+                                                           int C, int H, int W, int undo, long long total) {
+  // C,H,W describe the un-squeezed ("big") tensor [B,C,H,W]; the squeezed one is [B,4C,H/2,W/2]
+  const int Ho = H >> 1, Wo = W >> 1;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    // decode t as an index into the squeezed tensor
+    int j = (int)(t % Wo);
+    long long r = t / Wo;
+    int i = (int)(r % Ho);
+    r /= Ho;
+    int cs = (int)(r % (4 * C));
+    long long b = r / (4 * C);
+    int c = cs >> 2, dy = (cs >> 1) & 1, dx = cs & 1;
+    long long big = ((b * C + c) * H + 2 * i + dy) * (long long)W + 2 * j + dx;
+    if (undo) y[big] = x[t]; else y[t] = x[big];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// a1  ActNorm apply  (Flow/glow_modules.py:38-54)
+// ------------------------------------------------------------------------------------------
+template <bool kVec>
+__global__ void __launch_bounds__(kThreads) actnorm_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                           const float* __restrict__ bias,
+                                                           const float* __restrict__ logs, int C, int HW,
+                                                           int reverse, long long total) {
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    long long e = kVec ? t * 4 : t;
+    int c = (int)((e / HW) % C);
+    float b = __ldg(bias + c), l = __ldg(logs + c);
+    if (kVec) {
+      float4 v = ld_stream(reinterpret_cast<const float4*>(x) + t);
+      if (!reverse) {
+        float s = expf(l);
+        v.x = (v.x + b) * s; v.y = (v.y + b) * s; v.z = (v.z + b) * s; v.w = (v.w + b) * s;
+      } else {
+        float s = expf(-l);
+        v.x = v.x * s - b; v.y = v.y * s - b; v.z = v.z * s - b; v.w = v.w * s - b;
+      }
+      st_stream(reinterpret_cast<float4*>(y) + t, v);
+    } else {
+      float v = x[t];
+      y[t] = reverse ? v * expf(-l) - b : (v + b) * expf(l);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// a1  ActNorm data-dependent init  (Flow/glow_modules.py:26-31): one CTA per channel,
+// two passes (mean, then centred sum of squares) accumulated in double.
+// ------------------------------------------------------------------------------------------
+__device__ double block_sum(double v, double* sh) {
+  v = warp_sum(v);
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  double r = 0.0;
+  int nw = blockDim.x >> 5;
+  if (threadIdx.x < 32) {
+    r = lane < nw ? sh[lane] : 0.0;
+    r = warp_sum(r);
+    if (lane == 0) sh[32] = r;
+  }
+  __syncthreads();
+  return sh[32];
+}
+
+__global__ void __launch_bounds__(512) actnorm_init_kernel(const float* __restrict__ x, float* __restrict__ bias,
+                                                           float* __restrict__ logs, float* __restrict__ mean_out,
+                                                           float* __restrict__ std_out, int B, int C, int HW) {
+  __shared__ double sh[33];
+  const int c = blockIdx.x;
+  const long long n = (long long)B * HW;
+  double s = 0.0;
+  for (long long t = threadIdx.x; t < n; t += blockDim.x) {
+    long long b = t / HW;
+    int p = (int)(t % HW);
+    s += (double)x[(b * C + c) * HW + p];
+  }
+  const double mean = block_sum(s, sh) / (double)n;
+  double q = 0.0;
+  for (long long t = threadIdx.x; t < n; t += blockDim.x) {
+    long long b = t / HW;
+    int p = (int)(t % HW);
+    double d = (double)x[(b * C + c) * HW + p] - mean;
+    q += d * d;
+  }
+  const double var = block_sum(q, sh) / (double)(n - 1);
+  if (threadIdx.x == 0) {
+    float sd = (float)sqrt(var);
+    if (bias) bias[c] = -(float)mean;
+    if (logs) logs[c] = logf(1.0f / (sd + 1e-6f));
+    if (mean_out) mean_out[c] = (float)mean;
+    if (std_out) std_out[c] = sd;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// a2  1x1 channel mix  y[b,o,p] = sum_i Wm[o,i] x[b,i,p] + bvec[o]   (Flow/glow_modules.py:213)
+// HBM-bound (AI = C/4 flop/B): one thread per pixel, x tile and Wm staged in shared memory,
+// 8 output channels register-blocked.  Optional bf16 NHWC side output of the first side_n channels.
+// ------------------------------------------------------------------------------------------
+constexpr int kMixPix = 128;  // pixels per CTA
+
+__global__ void __launch_bounds__(kMixPix) mix1x1_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                         const float* __restrict__ Wm,
+                                                         const float* __restrict__ bvec, int C, int HW,
+                                                         long long npix, __nv_bfloat16* __restrict__ side,
+                                                         int side_n, int side_off, int side_ld, int w_smem) {
+  extern __shared__ float smem[];
+  float* bs = smem;                 // [C]
+  float* xs = bs + C;               // [C][kMixPix]
+  const float* ws = Wm;             // [C][C]: shared memory when it fits, else L1-cached broadcast loads
+  if (w_smem) {
+    float* wsm = xs + C * kMixPix;
+    for (int i = threadIdx.x; i < C * C; i += blockDim.x) wsm[i] = Wm[i];
+    ws = wsm;
+  }
+  for (int i = threadIdx.x; i < C; i += blockDim.x) bs[i] = bvec ? bvec[i] : 0.0f;
+  const long long pix = blockIdx.x * (long long)kMixPix + threadIdx.x;
+  const bool ok = pix < npix;
+  const long long b = ok ? pix / HW : 0;
+  const int p = ok ? (int)(pix % HW) : 0;
+  const float* xp = x + b * C * HW + p;
+  for (int i = 0; i < C; ++i) xs[i * kMixPix + threadIdx.x] = ok ? xp[(long long)i * HW] : 0.0f;
+  __syncthreads();
+  float* yp = y + b * C * HW + p;
+  for (int o0 = 0; o0 < C; o0 += 8) {
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = (o0 + j < C) ? bs[o0 + j] : 0.0f;
+    for (int i = 0; i < C; ++i) {
+      float xv = xs[i * kMixPix + threadIdx.x];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (o0 + j < C) acc[j] = fmaf(ws[(o0 + j) * C + i], xv, acc[j]);
+    }
+    if (ok) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        int o = o0 + j;
+        if (o < C) {
+          yp[(long long)o * HW] = acc[j];
+          if (side && o < side_n) side[pix * side_ld + side_off + o] = __float2bfloat16(acc[j]);
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// layout helpers
+// ------------------------------------------------------------------------------------------
+// NCHW f32 channel slice -> NHWC bf16 (thread per pixel: coalesced reads per channel, 16 B writes)
+__global__ void __launch_bounds__(kThreads) pack_nhwc_kernel(const float* __restrict__ src, long long src_bs,
+                                                             int HW, int c_lo, int n, __nv_bfloat16* __restrict__ dst,
+                                                             int dst_off, int dst_ld, long long npix, int vec_ok) {
+  for (long long pix = blockIdx.x * (long long)blockDim.x + threadIdx.x; pix < npix;
+       pix += (long long)gridDim.x * blockDim.x) {
+    long long b = pix / HW;
+    int p = (int)(pix % HW);
+    const float* sp = src + b * src_bs + (long long)c_lo * HW + p;
+    __nv_bfloat16* dp = dst + pix * dst_ld + dst_off;
+    int j = 0;
+    if (vec_ok) {
+      for (; j + 8 <= n; j += 8) {
+        __nv_bfloat162 h[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          h[k] = __floats2bfloat162_rn(sp[(long long)(j + 2 * k) * HW], sp[(long long)(j + 2 * k + 1) * HW]);
+        *reinterpret_cast<uint4*>(dp + j) = *reinterpret_cast<uint4*>(h);
+      }
+    }
+    for (; j < n; ++j) dp[j] = __float2bfloat16(sp[(long long)j * HW]);
+  }
+}
+
+template <bool kVec>
+__global__ void __launch_bounds__(kThreads) copy_channels_kernel(const float* __restrict__ src, int src_C,
+                                                                 int src_off, float* __restrict__ dst, int dst_C,
+                                                                 int dst_off, int n, int HW, long long total) {
+  const long long per = (long long)n * HW;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    long long e = kVec ? t * 4 : t;
+    long long b = e / per, r = e % per;
+    const float* s = src + (b * src_C + src_off) * HW + r;
+    float* d = dst + (b * dst_C + dst_off) * HW + r;
+    if (kVec) st_stream(reinterpret_cast<float4*>(d), ld_stream(reinterpret_cast<const float4*>(s)));
+    else *d = *s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// a3  coupling tail  (Flow/glow_modules.py:275-290).  grid = (chunks, B)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cta_atomic_add(float v, float* dst, float* sh) {
+  v = warp_sum(v);
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float r = lane < (blockDim.x >> 5) ? sh[lane] : 0.0f;
+    r = warp_sum(r);
+    if (lane == 0) atomicAdd(dst, r);
+  }
+}
+
+template <bool kVec>
+__global__ void __launch_bounds__(kThreads) coupling_tail_kernel(const float* __restrict__ nn, float* __restrict__ z,
+                                                                 int C, int HW, int clamp_type,
+                                                                 const float* __restrict__ cs,
+                                                                 const float* __restrict__ csh,
+                                                                 float* __restrict__ logdet, int reverse) {
+  __shared__ float sh[32];
+  const int b = blockIdx.y, half = C >> 1;
+  const long long per = (long long)half * HW;   // elements of z2 per sample
+  const long long units = kVec ? per >> 2 : per;
+  const float* nb = nn + (long long)b * C * HW;
+  float* zb = z + ((long long)b * C + half) * HW;
+  float acc = 0.0f;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < units;
+       t += (long long)gridDim.x * blockDim.x) {
+    long long e = kVec ? t * 4 : t;
+    int j = (int)(e / HW), p = (int)(e % HW);
+    float a = 0.0f, sft = 0.0f;
+    if (clamp_type == RFK_CLAMP_REALNVP) { a = __ldg(cs + j); sft = __ldg(csh + j); }
+    const float* shp = nb + (long long)(2 * j) * HW + p;
+    if (kVec) {
+      float4 s4 = ld_stream(reinterpret_cast<const float4*>(shp));
+      float4 r4 = ld_stream(reinterpret_cast<const float4*>(shp + HW));
+      float4 v = *reinterpret_cast<const float4*>(zb + e);
+      float sv[4] = {s4.x, s4.y, s4.z, s4.w}, rv[4] = {r4.x, r4.y, r4.z, r4.w}, zv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float ls = clamp_ls(rv[k], clamp_type, a, sft);
+        acc += ls;
+        zv[k] = reverse ? zv[k] * expf(-ls) - sv[k] : (zv[k] + sv[k]) * expf(ls);
+      }
+      *reinterpret_cast<float4*>(zb + e) = make_float4(zv[0], zv[1], zv[2], zv[3]);
+    } else {
+      float ls = clamp_ls(shp[HW], clamp_type, a, sft);
+      acc += ls;
+      float v = zb[e];
+      zb[e] = reverse ? v * expf(-ls) - shp[0] : (v + shp[0]) * expf(ls);
+    }
+  }
+  if (logdet) cta_atomic_add(reverse ? -acc : acc, logdet + b, sh);
+}
+
+// ------------------------------------------------------------------------------------------
+// a5/a7  Gaussian log-density / sampling.  grid = (chunks, B)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) gauss_logp_kernel(const float* __restrict__ z, int z_C, int z_off,
+                                                              const float* __restrict__ params, int n, int HW,
+                                                              int pairing, int std_kind,
+                                                              float* __restrict__ logdet) {
+  __shared__ float sh[32];
+  const int b = blockIdx.y;
+  const long long per = (long long)n * HW;
+  const float* zb = z + ((long long)b * z_C + z_off) * HW;
+  const float* pb = params ? params + (long long)b * 2 * n * HW : nullptr;
+  float acc = 0.0f;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < per;
+       t += (long long)gridDim.x * blockDim.x) {
+    int j = (int)(t / HW), p = (int)(t % HW);
+    float mean = 0.0f, raw = 0.0f;
+    if (pb) {
+      int cm = pairing == RFK_PAIR_CROSS ? 2 * j : j;
+      int cr = pairing == RFK_PAIR_CROSS ? 2 * j + 1 : n + j;
+      mean = pb[(long long)cm * HW + p];
+      raw = pb[(long long)cr * HW + p];
+    }
+    float sd = std_from_raw(raw, std_kind);
+    // exp-parameterised std: log(std) is raw itself (avoids exp/log round trip)
+    float lsd = std_kind == RFK_STD_EXP ? raw : logf(sd);
+    float d = zb[t] - mean;
+    acc += -(d * d) / (2.0f * sd * sd) - lsd - 0.91893853320467274178f;
+  }
+  cta_atomic_add(acc, logdet + b, sh);
+}
+
+__global__ void __launch_bounds__(kThreads) gauss_sample_kernel(const float* __restrict__ eps,
+                                                                const float* __restrict__ params, int n, int HW,
+                                                                int pairing, int std_kind, float temperature,
+                                                                float* __restrict__ out, int out_C, int out_off) {
+  const int b = blockIdx.y;
+  const long long per = (long long)n * HW;
+  const float* pb = params ? params + (long long)b * 2 * n * HW : nullptr;
+  const float* eb = eps + (long long)b * per;
+  float* ob = out + ((long long)b * out_C + out_off) * HW;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < per;
+       t += (long long)gridDim.x * blockDim.x) {
+    int j = (int)(t / HW), p = (int)(t % HW);
+    float mean = 0.0f, raw = 0.0f;
+    if (pb) {
+      int cm = pairing == RFK_PAIR_CROSS ? 2 * j : j;
+      int cr = pairing == RFK_PAIR_CROSS ? 2 * j + 1 : n + j;
+      mean = pb[(long long)cm * HW + p];
+      raw = pb[(long long)cr * HW + p];
+    }
+    ob[t] = mean + std_from_raw(raw, std_kind) * temperature * eb[t];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// a9  ConvLSTM cell update  (Utils/modules.py:369-377), gate order i,f,o,g; o peeps at c_next
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void lstm_point(float ci, float cf, float co, float cg, float c, float wi, float wf,
+                                           float wo, float& h, float& cn) {
+  float i = sigmoidf_(ci + wi * c);
+  float f = sigmoidf_(cf + wf * c);
+  float g = tanhf(cg);
+  cn = f * c + i * g;
+  float o = sigmoidf_(co + wo * cn);
+  h = o * tanhf(cn);
+}
+
+template <bool kVec>
+__global__ void __launch_bounds__(kThreads) lstm_pointwise_kernel(const float* __restrict__ cc,
+                                                                  const float* __restrict__ c_prev,
+                                                                  const float* __restrict__ peep,
+                                                                  float* __restrict__ h_out,
+                                                                  float* __restrict__ c_next, int Hc, int HW,
+                                                                  long long total) {
+  const long long per = (long long)Hc * HW;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    long long e = kVec ? t * 4 : t;
+    long long b = e / per, r = e % per;  // r = ch*HW + p
+    const float* g0 = cc + b * 4 * per + r;
+    if (kVec) {
+      float4 vi = ld_stream(reinterpret_cast<const float4*>(g0));
+      float4 vf = ld_stream(reinterpret_cast<const float4*>(g0 + per));
+      float4 vo = ld_stream(reinterpret_cast<const float4*>(g0 + 2 * per));
+      float4 vg = ld_stream(reinterpret_cast<const float4*>(g0 + 3 * per));
+      float4 vc = ld_stream(reinterpret_cast<const float4*>(c_prev + e));
+      float4 wi = make_float4(0, 0, 0, 0), wf = wi, wo = wi;
+      if (peep) {
+        wi = *reinterpret_cast<const float4*>(peep + r);
+        wf = *reinterpret_cast<const float4*>(peep + per + r);
+        wo = *reinterpret_cast<const float4*>(peep + 2 * per + r);
+      }
+      float4 h, cn;
+      lstm_point(vi.x, vf.x, vo.x, vg.x, vc.x, wi.x, wf.x, wo.x, h.x, cn.x);
+      lstm_point(vi.y, vf.y, vo.y, vg.y, vc.y, wi.y, wf.y, wo.y, h.y, cn.y);
+      lstm_point(vi.z, vf.z, vo.z, vg.z, vc.z, wi.z, wf.z, wo.z, h.z, cn.z);
+      lstm_point(vi.w, vf.w, vo.w, vg.w, vc.w, wi.w, wf.w, wo.w, h.w, cn.w);
+      st_stream(reinterpret_cast<float4*>(h_out + e), h);
+      st_stream(reinterpret_cast<float4*>(c_next + e), cn);
+    } else {
+      float wi = 0, wf = 0, wo = 0;
+      if (peep) { wi = peep[r]; wf = peep[per + r]; wo = peep[2 * per + r]; }
+      float h, cn;
+      lstm_point(g0[0], g0[per], g0[2 * per], g0[3 * per], c_prev[e], wi, wf, wo, h, cn);
+      h_out[e] = h;
+      c_next[e] = cn;
+    }
+  }
+}
+
+__global__ void add_scalar_kernel(float* __restrict__ logdet, const float* __restrict__ addend, float alpha, int B) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B) logdet[i] += alpha * (*addend);
+}
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace rfk
+
+using namespace rfk;
+
+extern "C" int rfk_squeeze2d(const float* x, float* y, int B, int C, int H, int W, int undo, void* stream) {
+  RFK_REQUIRE(x && y && B > 0 && C > 0 && H > 0 && W > 0, "rfk_squeeze2d: null pointer or empty shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  long long total = (long long)B * C * H * W;
+  if (!undo) {
+    RFK_REQUIRE(H % 2 == 0 && W % 2 == 0, "rfk_squeeze2d: H=%d, W=%d must be even", H, W);
+    if (W % 8 == 0 && aligned16(x) && aligned16(y)) {
+      long long t8 = total / 8;
+      squeeze_fwd_v8<<<stream_grid(t8, kThreads, 8), kThreads, 0, st>>>(x, y, C, H, W, t8);
+    } else {
+      squeeze_scalar<<<stream_grid(total, kThreads, 8), kThreads, 0, st>>>(x, y, C, H, W, 0, total);
+    }
+  } else {
+    RFK_REQUIRE(C % 4 == 0, "rfk_squeeze2d(undo): C=%d must be a multiple of 4", C);
+    int Co = C / 4, Hout = 2 * H, Wout = 2 * W;
+    if (Wout % 8 == 0 && aligned16(x) && aligned16(y)) {
+      long long t8 = total / 8;
+      squeeze_undo_v8<<<stream_grid(t8, kThreads, 8), kThreads, 0, st>>>(x, y, Co, Hout, Wout, t8);
+    } else {
+      squeeze_scalar<<<stream_grid(total, kThreads, 8), kThreads, 0, st>>>(x, y, Co, Hout, Wout, 1, total);
+    }
+  }
+  return check_launch("rfk_squeeze2d");
+}
+
+extern "C" int rfk_actnorm(const float* x, float* y, const float* bias, const float* logs, int B, int C, int HW,
+                           int reverse, void* stream) {
+  RFK_REQUIRE(x && y && bias && logs && B > 0 && C > 0 && HW > 0, "rfk_actnorm: null pointer or empty shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  long long total = (long long)B * C * HW;
+  if (HW % 4 == 0 && aligned16(x) && aligned16(y)) {
+    long long t4 = total / 4;
+    actnorm_kernel<true><<<stream_grid(t4, kThreads, 8), kThreads, 0, st>>>(x, y, bias, logs, C, HW, reverse, t4);
+  } else {
+    actnorm_kernel<false><<<stream_grid(total, kThreads, 8), kThreads, 0, st>>>(x, y, bias, logs, C, HW, reverse,
+                                                                                 total);
+  }
+  return check_launch("rfk_actnorm");
+}
+
+extern "C" int rfk_actnorm_init(const float* x, float* bias, float* logs, float* mean_out, float* std_out, int B,
+                                int C, int HW, void* stream) {
+  RFK_REQUIRE(x && B > 0 && C > 0 && HW > 0, "rfk_actnorm_init: null pointer or empty shape");
+  RFK_REQUIRE((long long)B * HW > 1, "rfk_actnorm_init: unbiased std needs more than one element per channel");
+  actnorm_init_kernel<<<C, 512, 0, (cudaStream_t)stream>>>(x, bias, logs, mean_out, std_out, B, C, HW);
+  return check_launch("rfk_actnorm_init");
+}
+
+extern "C" int rfk_mix1x1(const float* x, float* y, const float* Wm, const float* bvec, int B, int C, int HW,
+                          void* side, int side_n, int side_off, int side_ld, void* stream) {
+  RFK_REQUIRE(x && y && Wm && B > 0 && C > 0 && HW > 0, "rfk_mix1x1: null pointer or empty shape");
+  RFK_REQUIRE(x != y, "rfk_mix1x1: in-place is not supported");
+  size_t smem = ((size_t)C + (size_t)C * kMixPix) * sizeof(float);
+  RFK_REQUIRE(smem <= 200 * 1024, "rfk_mix1x1: C=%d too large for the shared-memory tile", C);
+  const int w_smem = smem + (size_t)C * C * sizeof(float) <= 96 * 1024;
+  if (w_smem) smem += (size_t)C * C * sizeof(float);
+  if (side) RFK_REQUIRE(side_n >= 0 && side_n <= C && side_off >= 0 && side_off + side_n <= side_ld,
+                        "rfk_mix1x1: bad side-output window");
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(mix1x1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("rfk_mix1x1: %s", cudaGetErrorString(e)); return RFK_ECUDA; }
+    configured = smem;
+  }
+  long long npix = (long long)B * HW;
+  mix1x1_kernel<<<ceil_div(npix, kMixPix), kMixPix, smem, (cudaStream_t)stream>>>(
+      x, y, Wm, bvec, C, HW, npix, (__nv_bfloat16*)side, side ? side_n : 0, side_off, side_ld, w_smem);
+  return check_launch("rfk_mix1x1");
+}
+
+extern "C" int rfk_pack_nhwc_bf16(const float* src, long long src_bstride, int B, int Csrc, int HW, int c_lo, int n,
+                                  void* dst, int dst_off, int dst_ld, void* stream) {
+  RFK_REQUIRE(src && dst && B > 0 && HW > 0, "rfk_pack_nhwc_bf16: null pointer or empty shape");
+  RFK_REQUIRE(c_lo >= 0 && n >= 0 && c_lo + n <= Csrc && dst_off >= 0 && dst_off + n <= dst_ld,
+              "rfk_pack_nhwc_bf16: bad channel window");
+  if (n == 0) return RFK_OK;
+  long long npix = (long long)B * HW;
+  int vec_ok = (dst_ld % 8 == 0) && (dst_off % 8 == 0) && aligned16(dst);
+  pack_nhwc_kernel<<<stream_grid(npix, kThreads, 8), kThreads, 0, (cudaStream_t)stream>>>(
+      src, src_bstride > 0 ? src_bstride : (long long)Csrc * HW, HW, c_lo, n, (__nv_bfloat16*)dst, dst_off, dst_ld,
+      npix, vec_ok);
+  return check_launch("rfk_pack_nhwc_bf16");
+}
+
+extern "C" int rfk_copy_channels(const float* src, int src_C, int src_off, float* dst, int dst_C, int dst_off,
+                                 int n, int B, int HW, void* stream) {
+  RFK_REQUIRE(src && dst && B > 0 && HW > 0 && n >= 0, "rfk_copy_channels: null pointer or empty shape");
+  RFK_REQUIRE(src_off >= 0 && src_off + n <= src_C && dst_off >= 0 && dst_off + n <= dst_C,
+              "rfk_copy_channels: bad channel window");
+  if (n == 0) return RFK_OK;
+  long long total = (long long)B * n * HW;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (HW % 4 == 0 && aligned16(src) && aligned16(dst)) {
+    copy_channels_kernel<true><<<stream_grid(total / 4, kThreads, 8), kThreads, 0, st>>>(
+        src, src_C, src_off, dst, dst_C, dst_off, n, HW, total / 4);
+  } else {
+    copy_channels_kernel<false><<<stream_grid(total, kThreads, 8), kThreads, 0, st>>>(
+        src, src_C, src_off, dst, dst_C, dst_off, n, HW, total);
+  }
+  return check_launch("rfk_copy_channels");
+}
+
+extern "C" int rfk_coupling_tail(const float* nn_out, float* z, int B, int C, int HW, int clamp_type,
+                                 const float* clamp_scale, const float* clamp_shift, float* logdet, int reverse,
+                                 void* stream) {
+  RFK_REQUIRE(nn_out && z && B > 0 && C > 0 && C % 2 == 0 && HW > 0, "rfk_coupling_tail: bad shape (C must be even)");
+  RFK_REQUIRE(clamp_type >= 0 && clamp_type <= 3, "rfk_coupling_tail: unknown clamp_type %d", clamp_type);
+  RFK_REQUIRE(clamp_type != RFK_CLAMP_REALNVP || (clamp_scale && clamp_shift),
+              "rfk_coupling_tail: realnvp clamp needs scale and scale_shift");
+  long long per = (long long)(C / 2) * HW;
+  bool vec = HW % 4 == 0 && aligned16(nn_out) && aligned16(z);
+  int chunks = ceil_div(vec ? per / 4 : per, kThreads);
+  int cap = ceil_div((long long)sm_count() * 8, B);
+  if (chunks > cap) chunks = cap;
+  dim3 grid(chunks, B);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (vec)
+    coupling_tail_kernel<true><<<grid, kThreads, 0, st>>>(nn_out, z, C, HW, clamp_type, clamp_scale, clamp_shift,
+                                                          logdet, reverse);
+  else
+    coupling_tail_kernel<false><<<grid, kThreads, 0, st>>>(nn_out, z, C, HW, clamp_type, clamp_scale, clamp_shift,
+                                                           logdet, reverse);
+  return check_launch("rfk_coupling_tail");
+}
+
+extern "C" int rfk_gauss_logp(const float* z, int z_C, int z_off, const float* params, int n, int B, int HW,
+                              int pairing, int std_kind, float* logdet, void* stream) {
+  RFK_REQUIRE(z && logdet && B > 0 && n > 0 && HW > 0, "rfk_gauss_logp: null pointer or empty shape");
+  RFK_REQUIRE(z_off >= 0 && z_off + n <= z_C, "rfk_gauss_logp: bad z channel window");
+  long long per = (long long)n * HW;
+  int chunks = ceil_div(per, kThreads);
+  int cap = ceil_div((long long)sm_count() * 8, B);
+  if (chunks > cap) chunks = cap;
+  gauss_logp_kernel<<<dim3(chunks, B), kThreads, 0, (cudaStream_t)stream>>>(z, z_C, z_off, params, n, HW, pairing,
+                                                                            std_kind, logdet);
+  return check_launch("rfk_gauss_logp");
+}
+
+extern "C" int rfk_gauss_sample(const float* eps, const float* params, int n, int B, int HW, int pairing,
+                                int std_kind, float temperature, float* out, int out_C, int out_off,
+                                void* stream) {
+  RFK_REQUIRE(eps && out && B > 0 && n > 0 && HW > 0, "rfk_gauss_sample: null pointer or empty shape");
+  RFK_REQUIRE(out_off >= 0 && out_off + n <= out_C, "rfk_gauss_sample: bad output channel window");
+  long long per = (long long)n * HW;
+  int chunks = ceil_div(per, kThreads);
+  int cap = ceil_div((long long)sm_count() * 8, B);
+  if (chunks > cap) chunks = cap;
+  gauss_sample_kernel<<<dim3(chunks, B), kThreads, 0, (cudaStream_t)stream>>>(eps, params, n, HW, pairing, std_kind,
+                                                                              temperature, out, out_C, out_off);
+  return check_launch("rfk_gauss_sample");
+}
+
+extern "C" int rfk_convlstm_pointwise(const float* cc, const float* c_prev, const float* peep, float* h_out,
+                                      float* c_next, int B, int Hc, int HW, void* stream) {
+  RFK_REQUIRE(cc && c_prev && h_out && c_next && B > 0 && Hc > 0 && HW > 0,
+              "rfk_convlstm_pointwise: null pointer or empty shape");
+  long long total = (long long)B * Hc * HW;
+  cudaStream_t st = (cudaStream_t)stream;
+  bool vec = HW % 4 == 0 && aligned16(cc) && aligned16(c_prev) && aligned16(h_out) && aligned16(c_next) &&
+             (!peep || aligned16(peep));
+  if (vec)
+    lstm_pointwise_kernel<true><<<stream_grid(total / 4, kThreads, 8), kThreads, 0, st>>>(cc, c_prev, peep, h_out,
+                                                                                          c_next, Hc, HW, total / 4);
+  else
+    lstm_pointwise_kernel<false><<<stream_grid(total, kThreads, 8), kThreads, 0, st>>>(cc, c_prev, peep, h_out,
+                                                                                       c_next, Hc, HW, total);
+  return check_launch("rfk_convlstm_pointwise");
+}
+
+extern "C" int rfk_add_scalar(float* logdet, const float* addend, float alpha, int B, void* stream) {
+  RFK_REQUIRE(logdet && addend && B > 0, "rfk_add_scalar: null pointer or empty shape");
+  add_scalar_kernel<<<ceil_div(B, 256), 256, 0, (cudaStream_t)stream>>>(logdet, addend, alpha, B);
+  return check_launch("rfk_add_scalar");
+}

@@ -1,0 +1,202 @@
+"""Tensor-level wrappers over the C ABI (include/rfk.h).
+
+PyTorch is used here for device memory and the current stream only; every
+function enqueues exactly the kernel it names on ``torch.cuda.current_stream()``.
+"""
+import torch
+
+from . import _lib
+from ._lib import ACT, CLAMP, OUT_NCHW_F32, OUT_NHWC_BF16, PAIR_CROSS, PAIR_SPLIT, STD, call  # noqa: F401
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _chk(t, dtype=torch.float32, name="tensor"):
+    if not t.is_cuda:
+        raise _lib.RfkError(f"{name} must be a CUDA tensor: this path has no CPU implementation")
+    if t.dtype != dtype:
+        raise _lib.RfkError(f"{name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise _lib.RfkError(f"{name} must be contiguous")
+    return t
+
+
+def f32c(t):
+    """Contiguous float32 CUDA view/copy of a user tensor (plumbing, not compute)."""
+    if not t.is_cuda:
+        raise _lib.RfkError("input must be a CUDA tensor: this path has no CPU implementation")
+    return t.detach().to(torch.float32).contiguous()
+
+
+def pad_to(v, m):
+    return (v + m - 1) // m * m
+
+
+# --------------------------------------------------------------------------------------
+def squeeze2d(x, undo=False):
+    _chk(x, name="x")
+    B, C, H, W = x.shape
+    y = torch.empty((B, C // 4, 2 * H, 2 * W) if undo else (B, 4 * C, H // 2, W // 2), device=x.device, dtype=x.dtype)
+    call("rfk_squeeze2d", x.data_ptr(), y.data_ptr(), B, C, H, W, int(undo), _stream())
+    return y
+
+
+def actnorm(x, bias, logs, reverse=False):
+    _chk(x, name="x")
+    B, C, H, W = x.shape
+    y = torch.empty_like(x)
+    call("rfk_actnorm", x.data_ptr(), y.data_ptr(), _chk(bias).data_ptr(), _chk(logs).data_ptr(), B, C, H * W,
+         int(reverse), _stream())
+    return y
+
+
+def actnorm_init(x, bias, logs):
+    """Writes bias/logs in place from the statistics of x [B,C,H,W]."""
+    _chk(x, name="x")
+    B, C, H, W = x.shape
+    call("rfk_actnorm_init", x.data_ptr(), _chk(bias).data_ptr(), _chk(logs).data_ptr(), 0, 0, B, C, H * W, _stream())
+
+
+def mix1x1(x, Wm, bvec=None, side=None, side_n=0, side_off=0):
+    _chk(x, name="x")
+    B, C, H, W = x.shape
+    y = torch.empty_like(x)
+    side_ld = side.shape[-1] if side is not None else 0
+    call("rfk_mix1x1", x.data_ptr(), y.data_ptr(), _chk(Wm).data_ptr(), _p(bvec), B, C, H * W,
+         _p(side), side_n, side_off, side_ld, _stream())
+    return y
+
+
+def pack_nhwc(src, c_lo, n, dst, dst_off):
+    """src NCHW f32 channels [c_lo,c_lo+n) -> dst NHWC bf16 [B,H,W,ld] at channel dst_off.
+    src may be a batch-strided slice (e.g. x[:, t] of a [B,T,C,H,W] sequence)."""
+    B, C, H, W = src.shape
+    if not src.is_cuda or src.dtype != torch.float32 or src[0].is_contiguous() is False:
+        raise _lib.RfkError("src must be a float32 CUDA tensor, dense within each sample")
+    _chk(dst, torch.bfloat16, "dst")
+    call("rfk_pack_nhwc_bf16", src.data_ptr(), src.stride(0), B, C, H * W, c_lo, n, dst.data_ptr(), dst_off,
+         dst.shape[-1], _stream())
+
+
+def copy_channels(src, src_off, dst, dst_off, n):
+    _chk(src, name="src")
+    _chk(dst, name="dst")
+    B, Cs, H, W = src.shape
+    call("rfk_copy_channels", src.data_ptr(), Cs, src_off, dst.data_ptr(), dst.shape[1], dst_off, n, B, H * W, _stream())
+
+
+def conv_gemm(act, cin_pad, wgt, n, taps, scale, shift, act_fn, out, out_off=0):
+    """act NHWC bf16 [B,H,W,ld]; wgt bf16 [n_pad, taps*cin_pad]; out NHWC bf16 (4-D, channel last) or NCHW f32."""
+    _chk(act, torch.bfloat16, "act")
+    _chk(wgt, torch.bfloat16, "wgt")
+    B, H, W, ld = act.shape
+    if out.dtype == torch.bfloat16:
+        kind, out_ld = OUT_NHWC_BF16, out.shape[-1]
+        _chk(out, torch.bfloat16, "out")
+    else:
+        kind, out_ld = OUT_NCHW_F32, 0
+        _chk(out, name="out")
+    call("rfk_conv_gemm", act.data_ptr(), B, H, W, ld, cin_pad, wgt.data_ptr(), n, wgt.shape[0], taps,
+         _p(scale), _p(shift), ACT[act_fn], kind, out.data_ptr(), out_ld, out_off, _stream())
+    return out
+
+
+def conv_gemm_coupling(act, cin_pad, wgt, n, taps, scale, shift, z, clamp_type, clamp_scale, clamp_shift,
+                       logdet, reverse):
+    _chk(act, torch.bfloat16, "act")
+    _chk(z, name="z")
+    B, H, W, ld = act.shape
+    call("rfk_conv_gemm_coupling", act.data_ptr(), B, H, W, ld, cin_pad, _chk(wgt, torch.bfloat16).data_ptr(), n,
+         wgt.shape[0], taps, _p(scale), _p(shift), z.data_ptr(), CLAMP[clamp_type], _p(clamp_scale), _p(clamp_shift),
+         _p(logdet), int(reverse), _stream())
+
+
+def conv_gemm_lstm(act, cin_pad, wgt, hidden, ht, ht_pad, taps, bias, c_prev, peep, c_next, h_out, h_nhwc, h_off):
+    _chk(act, torch.bfloat16, "act")
+    B, H, W, ld = act.shape
+    call("rfk_conv_gemm_lstm", act.data_ptr(), B, H, W, ld, cin_pad, _chk(wgt, torch.bfloat16).data_ptr(), hidden, ht,
+         ht_pad, taps, _p(bias), _p(c_prev), c_prev.stride(0) if c_prev is not None else 0, _p(peep),
+         c_next.data_ptr(), c_next.stride(0), h_out.data_ptr(), h_out.stride(0),
+         _p(h_nhwc), h_off, h_nhwc.shape[-1] if h_nhwc is not None else 0, _stream())
+
+
+def coupling_tail(nn_out, z, clamp_type, clamp_scale, clamp_shift, logdet, reverse):
+    _chk(nn_out, name="nn_out")
+    _chk(z, name="z")
+    B, C, H, W = z.shape
+    call("rfk_coupling_tail", nn_out.data_ptr(), z.data_ptr(), B, C, H * W, CLAMP[clamp_type], _p(clamp_scale),
+         _p(clamp_shift), _p(logdet), int(reverse), _stream())
+
+
+def gauss_logp(z, z_off, params, n, pairing, std_kind, logdet):
+    _chk(z, name="z")
+    B, zC, H, W = z.shape
+    call("rfk_gauss_logp", z.data_ptr(), zC, z_off, _p(params), n, B, H * W, pairing, STD[std_kind],
+         _chk(logdet).data_ptr(), _stream())
+
+
+def gauss_sample(eps, params, n, pairing, std_kind, temperature, out, out_off):
+    _chk(eps, name="eps")
+    _chk(out, name="out")
+    B, oC, H, W = out.shape
+    call("rfk_gauss_sample", eps.data_ptr(), _p(params), n, B, H * W, pairing, STD[std_kind], float(temperature),
+         out.data_ptr(), oC, out_off, _stream())
+
+
+def convlstm_pointwise(cc, c_prev, peep):
+    _chk(cc, name="cc")
+    _chk(c_prev, name="c_prev")
+    B, Hc, H, W = c_prev.shape
+    h = torch.empty_like(c_prev)
+    c = torch.empty_like(c_prev)
+    call("rfk_convlstm_pointwise", cc.data_ptr(), c_prev.data_ptr(), _p(peep), h.data_ptr(), c.data_ptr(), B, Hc,
+         H * W, _stream())
+    return h, c
+
+
+# --------------------------------------------------------------------------------------
+# workspace pool: NHWC bf16 staging buffers shared by all modules of one shape (one stream, in order)
+# --------------------------------------------------------------------------------------
+_WS = {}
+
+
+def workspace(tag, shape, device, dtype=torch.bfloat16):
+    key = (tag, tuple(shape), str(device), dtype)
+    t = _WS.get(key)
+    if t is None:
+        t = torch.zeros(shape, device=device, dtype=dtype)
+        _WS[key] = t
+    return t
+
+
+def clear_workspaces():
+    _WS.clear()
+
+
+# --------------------------------------------------------------------------------------
+# weight repacking (tiny host-driven torch ops on the device, cached by the callers)
+# --------------------------------------------------------------------------------------
+def pack_conv_weight(weight, in_perm=None, row_perm=None, n_pad=None):
+    """[N, Cin, kh, kw] f32 -> bf16 [n_pad, taps*cin_pad] with k = tap*cin_pad + c (tap = 3*ky + kx)."""
+    w = weight.detach().float()
+    N, Cin, kh, kw = w.shape
+    if in_perm is not None:
+        w = w[:, in_perm]
+    cin_pad = pad_to(max(Cin, 1), 64)
+    w = w.permute(0, 2, 3, 1).reshape(N, kh * kw, Cin)
+    if row_perm is not None:
+        rows = row_perm.numel()
+        full = torch.zeros(rows, kh * kw, Cin, device=w.device)
+        valid = row_perm >= 0
+        full[valid] = w[row_perm[valid]]
+        w, N = full, rows
+    n_pad = n_pad or pad_to(N, 16)
+    out = torch.zeros(n_pad, kh * kw, cin_pad, device=w.device, dtype=torch.bfloat16)
+    out[:N, :, :Cin] = w.to(torch.bfloat16)
+    return out.reshape(n_pad, kh * kw * cin_pad).contiguous(), cin_pad

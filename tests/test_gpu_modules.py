@@ -1,0 +1,321 @@
+"""GPU parity of the reference-interface modules: golden fixtures made from the reference's own
+modules are replayed through the CUDA path, and larger configurations are checked against the CPU
+oracle on identical inputs and weights.
+
+Tolerances (BASELINE.json north_star): bit exact for indexing; the coupling / ConvLSTM convolutions
+run in bf16 with fp32 accumulation, so tensors that pass through them are held to 1e-2 of the
+reference tensor's max-norm, and logdet / nll / bits-per-dim to 1e-2 relative (plus a small absolute
+term for near-zero log-dets); fp32-only pieces (ActNorm, InvConv) to 1e-5."""
+import math
+import types
+
+import pytest
+import torch
+
+import oracle as O
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+BF16_TOL = 1e-2
+
+
+@pytest.fixture(scope="module")
+def rf():
+    import recurrent_flows_msc_b200 as r
+    return r
+
+
+def max_rel(a, b):
+    b = b.double().cpu()
+    return float((a.double().cpu() - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def assert_ld(a, b, rtol=BF16_TOL, atol=5e-2):
+    torch.testing.assert_close(a.cpu().float(), b.cpu().float(), rtol=rtol, atol=atol)
+
+
+def cuda_sd(sd):
+    return {k: v.cuda() for k, v in sd.items()}
+
+
+def ns(d):
+    return types.SimpleNamespace(**d)
+
+
+# ---------------------------------------------------------------------------- fp32 modules
+def test_actnorm_module_golden(rf):
+    g = load_golden("actnorm")
+    with torch.no_grad():
+        m = rf.ActNorm(5).cuda().train()
+        y, ld = m(g["x"].cuda(), logdet=torch.zeros(3).cuda(), reverse=False)   # data-dependent init
+        torch.testing.assert_close(y.cpu(), g["y_init_train"], rtol=1e-5, atol=1e-5)
+        torch.testing.assert_close(ld.cpu(), g["logdet_init_train"], rtol=1e-5, atol=1e-5)
+        torch.testing.assert_close(m.bias.cpu(), g["sd_after_init"]["bias"], rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(m.logs.cpu(), g["sd_after_init"]["logs"], rtol=1e-5, atol=1e-6)
+        assert int(m.initialized) == 1
+        xr, ldr = m(y, logdet=ld, reverse=True)
+        torch.testing.assert_close(xr.cpu(), g["x_rev"], rtol=1e-5, atol=1e-5)
+        torch.testing.assert_close(ldr.cpu(), g["logdet_rev"], rtol=1e-5, atol=1e-4)
+        m2 = rf.ActNorm(5).cuda().eval()   # quirk: first eval call marks initialised without initialising
+        y2, none = m2(g["x"].cuda(), logdet=None, reverse=False)
+        assert none is None and int(m2.initialized) == 1
+        torch.testing.assert_close(y2.cpu(), g["y_eval_first"], rtol=1e-6, atol=1e-6)
+        assert float(m2.logs.abs().max()) == 0
+        y3, ld3 = m(g["x3"].cuda(), logdet=0.0, reverse=False)
+        torch.testing.assert_close(y3.cpu(), g["y3"], rtol=1e-5, atol=1e-5)
+        assert ld3.dim() == 0
+        torch.testing.assert_close(ld3.cpu(), g["logdet3"], rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("name,lu", [("invconv_lu", True), ("invconv_plain", False)])
+def test_invconv_module_golden(rf, name, lu):
+    g = load_golden(name)
+    with torch.no_grad():
+        m = rf.InvConv(6, LU_decomposed=lu).cuda()
+        m.load_state_dict(cuda_sd(g["sd"]))
+        z, ld = m(g["x"].cuda(), logdet=torch.zeros(2).cuda(), reverse=False)
+        torch.testing.assert_close(z.cpu(), g["z"], rtol=1e-5, atol=1e-5)
+        torch.testing.assert_close(ld.cpu(), g["logdet"], rtol=1e-5, atol=1e-5)
+        xr, ldr = m(z, logdet=ld, reverse=True)
+        torch.testing.assert_close(xr.cpu(), g["x_rev"], rtol=1e-4, atol=1e-4)
+        torch.testing.assert_close(ldr.cpu(), g["logdet_rev"], rtol=1e-5, atol=1e-4)
+
+
+def test_squeeze_module_golden(rf):
+    g = load_golden("squeeze")
+    with torch.no_grad():
+        m = rf.Squeeze2d()
+        assert torch.equal(m(g["x"].cuda(), undo_squeeze=False).cpu(), g["y"])
+        assert torch.equal(m(g["y"].cuda(), undo_squeeze=True).cpu(), g["undo"])
+
+
+# ---------------------------------------------------------------------------- bf16-conv modules
+@pytest.mark.parametrize("clamp", ["realnvp", "glow", "softclamp", "none"])
+def test_coupling_module_golden(rf, clamp):
+    g = load_golden(f"coupling_{clamp}")
+    with torch.no_grad():
+        m = rf.AffineCoupling([2, 8, 6, 6], [2, 5, 6, 6], hidden_units=16, non_lin=g["non_lin"], clamp_type=clamp).cuda().eval()
+        m.load_state_dict(cuda_sd(g["sd"]))
+        x = g["x"].cuda()
+        z, ld = m(x, g["cond"].cuda(), logdet=torch.zeros(2).cuda(), reverse=False)
+        assert torch.equal(x.cpu(), g["x"]), "input must not be modified"
+        assert torch.equal(z[:, :4].cpu(), g["x"][:, :4]), "z1 passes through bit exact"
+        assert max_rel(z, g["z"]) < BF16_TOL
+        assert_ld(ld, g["logdet"])
+        xr, ldr = m(g["z"].cuda(), g["cond"].cuda(), logdet=g["logdet"].cuda(), reverse=True)
+        assert max_rel(xr, g["x_rev"]) < BF16_TOL
+        assert_ld(ldr, g["logdet_rev"])
+
+
+@pytest.mark.parametrize("name", ["split2d_cond_softplus", "split2d_uncond_exp"])
+def test_split2d_module_golden(rf, name):
+    g = load_golden(name)
+    with torch.no_grad():
+        m = rf.Split2d([2, 8, 4, 4], [2, 6, 4, 4], make_conditional=g["make_conditional"],
+                       clamp_function=g["clamp_function"]).cuda().eval()
+        m.load_state_dict(cuda_sd(g["sd"]))
+        z1, ld = m(g["x"].cuda(), g["cond"].cuda(), logdet=torch.zeros(2).cuda(), reverse=False)
+        assert torch.equal(z1.cpu(), g["z1"])
+        assert_ld(ld, g["logdet"])
+        xr, _ = m(g["z1"].cuda(), g["cond"].cuda(), logdet=None, reverse=True, temperature=g["temperature"],
+                  eps=g["eps"].cuda())
+        assert torch.equal(xr[:, :4].cpu(), g["z1"])
+        assert max_rel(xr, g["x_rev"]) < BF16_TOL
+
+
+def test_glowstep_module_golden(rf):
+    g = load_golden("glowstep")
+    args = ns(dict(LU_decomposed=True, n_units_affine=16, non_lin_glow="relu", clamp_type="realnvp",
+                   flow_norm="actnorm", flow_batchnorm_momentum=0.0))
+    with torch.no_grad():
+        m = rf.GlowStep([2, 8, 4, 4], [2, 3, 4, 4], args).cuda().eval()
+        m.load_state_dict(cuda_sd(g["sd"]))
+        z, ld = m(g["x"].cuda(), g["cond"].cuda(), logdet=torch.zeros(2).cuda(), reverse=False)
+        assert max_rel(z, g["z"]) < BF16_TOL
+        assert_ld(ld, g["logdet"])
+        xr, ldr = m(z, g["cond"].cuda(), logdet=ld, reverse=True)   # exact inverse of the CUDA forward
+        assert max_rel(xr, g["x"]) < 1e-4
+        assert float(ldr.abs().max()) < 1e-3
+        xr2, ldr2 = m(g["z"].cuda(), g["cond"].cuda(), logdet=g["logdet"].cuda(), reverse=True)
+        assert max_rel(xr2, g["x_rev"]) < BF16_TOL
+        assert_ld(ldr2, g["logdet_rev"])
+
+
+def build_listglow(rf, g):
+    a = ns(g["args"])
+    m = rf.ListGlow(g["x_size"], g["cond_sizes"], g["base_size"], a).cuda().eval()
+    m.load_state_dict(cuda_sd(g["sd"]))
+    return m, a
+
+
+def test_listglow_cond_golden(rf):
+    g = load_golden("listglow_cond")
+    with torch.no_grad():
+        m, a = build_listglow(rf, g)
+        conds = [c.cuda() for c in g["cond"]]
+        z, ld = m.f(g["x"].cuda(), conds, logdet=0.0)
+        assert max_rel(z, g["z_f"]) < BF16_TOL
+        assert_ld(ld, g["logdet_f"], atol=0.2)
+        z2, nll = m.log_prob(g["x"].cuda(), conds, g["base"].cuda(), logdet=0, noise=g["noise"].cuda())
+        assert max_rel(z2, g["z_logprob"]) < BF16_TOL
+        assert_ld(nll, g["nll"], atol=0.2)
+        bpd = nll / (math.log(2.0) * 256)
+        torch.testing.assert_close(bpd.cpu(), g["bpd"], rtol=BF16_TOL, atol=1e-3)
+        xs = m.sample(None, conds, g["base"].cuda(), num_samples=2, temperature=g["temperature"],
+                      eps_prior=g["eps_prior"].cuda(), eps_list=[e.cuda() for e in g["eps_split"]])
+        assert max_rel(xs, g["x_sample"]) < BF16_TOL
+        # with random noise the call still works and stays close (noise < 1/256)
+        z3, nll3 = m.log_prob(g["x"].cuda(), conds, g["base"].cuda())
+        assert torch.isfinite(nll3).all()
+
+
+def test_listglow_uncond_golden(rf):
+    g = load_golden("listglow_uncond")
+    with torch.no_grad():
+        m, a = build_listglow(rf, g)
+        conds = [torch.zeros(*s).cuda() for s in g["cond_sizes"]]
+        z, nll = m.log_prob(g["x"].cuda(), conds, None, logdet=0, noise=g["noise"].cuda())
+        assert max_rel(z, g["z_logprob"]) < BF16_TOL
+        assert_ld(nll, g["nll"], atol=0.2)
+        xs = m.sample(None, conds, None, num_samples=2, temperature=g["temperature"],
+                      eps_prior=g["eps_prior"].cuda(), eps_list=[e.cuda() for e in g["eps_split"]])
+        assert max_rel(xs, g["x_sample"]) < BF16_TOL
+
+
+def trained_like(m, seed):
+    """Same perturbation idea as tests/golden/make_golden.py: make zero-initialised tensors non-trivial."""
+    gen = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for name, p in m.named_parameters():
+            s = 0.03 if "conv.weight" in name else 0.1
+            p.add_((torch.randn(p.shape, generator=gen) * s).to(p.device))
+        for name, b in m.named_buffers():
+            if name.endswith("initialized"):
+                b.fill_(1)
+
+
+GLOW_ARGS = dict(LU_decomposed=True, n_units_affine=256, non_lin_glow="relu", clamp_type="realnvp",
+                 flow_norm="actnorm", flow_batchnorm_momentum=0.0, learn_prior=True, n_units_prior=512,
+                 make_conditional=True, base_norm="actnorm", split2d_act="softplus", L=3, K=8, n_bits=8)
+
+
+def test_listglow_cfg1_vs_oracle(rf):
+    """BASELINE config 0: Glow L=3 K=8 hidden 256 on a 1x32x32 batch of 16, unconditional, fixed prior."""
+    B = 16
+    a = dict(GLOW_ARGS, learn_prior=False, make_conditional=False)
+    cond_sizes = [[B, 0, 16, 16], [B, 0, 8, 8], [B, 0, 4, 4]]
+    torch.manual_seed(0)
+    with torch.no_grad():
+        m = rf.ListGlow([B, 1, 32, 32], cond_sizes, [B, 0, 4, 4], ns(a)).eval()
+        trained_like(m, 1)
+        sd = {k: v.clone() for k, v in m.state_dict().items()}
+        m = m.cuda()
+        g = torch.Generator().manual_seed(0)
+        x = torch.floor(torch.rand(B, 1, 32, 32, generator=g) * 256) / 256 - 0.5
+        noise = torch.rand(B, 1, 32, 32, generator=g) / 256
+        conds = [torch.zeros(*s) for s in cond_sizes]
+        z_ref, nll_ref = O.listglow_log_prob(x, conds, None, sd, 3, 8, 8, noise=noise, learn_prior=False,
+                                             clamp_type="realnvp", non_lin="relu", make_conditional=False)
+        z, nll = m.log_prob(x.cuda(), [c.cuda() for c in conds], None, logdet=0, noise=noise.cuda())
+        assert max_rel(z, z_ref) < BF16_TOL
+        bpd, bpd_ref = nll.cpu() / (math.log(2) * 1024), nll_ref / (math.log(2) * 1024)
+        torch.testing.assert_close(bpd, bpd_ref, rtol=BF16_TOL, atol=2e-3)
+        # z -> x through g with the draws that f discarded replaced by fresh eps: x must be finite and,
+        # for the last level (no split), g inverts f exactly -- checked through GlowStep round trips above
+        xs = m.sample(None, [c.cuda() for c in conds], None, num_samples=B, temperature=0.7)
+        assert torch.isfinite(xs).all() and xs.shape == (B, 1, 32, 32)
+
+
+def test_listglow_rfn_shape_vs_oracle(rf):
+    """RFN job-script decoder shape (L=5, hidden 256, cond channels 16..256, learned prior) at K=2, B=3."""
+    B = 3
+    a = dict(GLOW_ARGS, L=5, K=2)
+    cond_sizes = [[B, 16, 32, 32], [B, 32, 16, 16], [B, 64, 8, 8], [B, 128, 4, 4], [B, 256, 2, 2]]
+    torch.manual_seed(0)
+    with torch.no_grad():
+        m = rf.ListGlow([B, 1, 64, 64], cond_sizes, [B, 256, 2, 2], ns(a)).eval()
+        trained_like(m, 2)
+        sd = {k: v.clone() for k, v in m.state_dict().items()}
+        m = m.cuda()
+        g = torch.Generator().manual_seed(3)
+        x = torch.floor(torch.rand(B, 1, 64, 64, generator=g) * 256) / 256 - 0.5
+        noise = torch.rand(B, 1, 64, 64, generator=g) / 256
+        conds = [torch.randn(*s, generator=g) for s in cond_sizes]
+        base = torch.randn(B, 256, 2, 2, generator=g)
+        z_ref, nll_ref = O.listglow_log_prob(x, conds, base, sd, 5, 2, 8, noise=noise, learn_prior=True)
+        z, nll = m.log_prob(x.cuda(), [c.cuda() for c in conds], base.cuda(), logdet=0, noise=noise.cuda())
+        assert max_rel(z, z_ref) < BF16_TOL
+        torch.testing.assert_close(nll.cpu() / (math.log(2) * 4096), nll_ref / (math.log(2) * 4096), rtol=BF16_TOL, atol=2e-3)
+        eps_prior = torch.randn(B, 64, 2, 2, generator=g)
+        eps = [torch.randn(B, 2 << l, 32 >> l, 32 >> l, generator=g) for l in range(4)]
+        x_ref = O.listglow_sample(conds, base, sd, 5, 2, eps_prior, eps, 0.7, learn_prior=True)
+        xs = m.sample(None, [c.cuda() for c in conds], base.cuda(), num_samples=B, temperature=0.7,
+                      eps_prior=eps_prior.cuda(), eps_list=[e.cuda() for e in eps])
+        assert max_rel(xs, x_ref) < 2 * BF16_TOL
+
+
+def test_hidden_actnorm_data_dependent_init(rf):
+    """First training-mode call initialises every ActNorm (flow and hidden) from the batch, like the reference."""
+    B = 4
+    a = dict(GLOW_ARGS, L=2, K=2, n_units_affine=64, n_units_prior=32)
+    cond_sizes = [[B, 4, 8, 8], [B, 8, 4, 4]]
+    torch.manual_seed(5)
+    with torch.no_grad():
+        m = rf.ListGlow([B, 1, 16, 16], cond_sizes, [B, 6, 4, 4], ns(a)).train()
+        sd0 = {k: v.clone() for k, v in m.state_dict().items()}
+        m = m.cuda()
+        g = torch.Generator().manual_seed(6)
+        x = torch.rand(B, 1, 16, 16, generator=g) - 0.5
+        conds = [torch.randn(*s, generator=g) for s in cond_sizes]
+        base = torch.randn(B, 6, 4, 4, generator=g)
+        z, nll = m.log_prob(x.cuda(), [c.cuda() for c in conds], base.cuda(), noise=torch.zeros_like(x).cuda())
+        assert all(int(v) == 1 for k, v in m.state_dict().items() if k.endswith("initialized"))
+        # first flow ActNorm: mean 0 / std 1 statistics of the squeezed input
+        xs = O.squeeze2d(x)
+        b_ref, l_ref = O.actnorm_init(xs)
+        torch.testing.assert_close(m.glow_frame[1].norm.bias.cpu(), b_ref, rtol=1e-4, atol=1e-5)
+        torch.testing.assert_close(m.glow_frame[1].norm.logs.cpu(), l_ref, rtol=1e-4, atol=1e-5)
+        # first hidden ActNorm: statistics of the raw conv output (conv weights are bf16 on the GPU)
+        st = m.glow_frame[1]
+        y, _ = O.actnorm(xs, b_ref, l_ref)
+        y, _ = O.invconv(y, sd0, "glow_frame.1.invconv.")
+        h = torch.nn.functional.conv2d(torch.cat([y[:, :2], conds[0]], 1), sd0["glow_frame.1.affine.net.0.conv.weight"], None, 1, 1)
+        bh, lh = O.actnorm_init(h)
+        torch.testing.assert_close(st.affine.net[0].norm_type.logs.cpu(), lh, rtol=2e-2, atol=2e-2)
+        torch.testing.assert_close(st.affine.net[0].norm_type.bias.cpu(), bh, rtol=2e-2, atol=2e-2)
+        assert torch.isfinite(nll).all()
+
+
+# ---------------------------------------------------------------------------- ConvLSTM
+def test_convlstm_golden(rf):
+    g = load_golden("convlstm")
+    with torch.no_grad():
+        m = rf.ConvLSTM(in_channels=3, hidden_channels=4, kernel_size=[3, 3], bias=True, peephole=True).cuda()
+        m.load_state_dict(cuda_sd(g["sd"]))
+        out, h, c = m(g["x"].cuda())
+        assert max_rel(out, g["out"]) < BF16_TOL and max_rel(h, g["h"]) < BF16_TOL and max_rel(c, g["c"]) < BF16_TOL
+        out2, h2, c2 = m(g["x"][:, :1].cuda(), g["h0"].cuda(), g["c0"].cuda())
+        assert max_rel(out2, g["out2"]) < BF16_TOL and max_rel(c2, g["c2"]) < BF16_TOL
+        assert set(m.state_dict().keys()) == {"LSTMlayer.conv.0.weight", "LSTMlayer.conv.0.bias"}
+
+
+def test_convlstm_cfg2_shape_vs_oracle(rf):
+    """BASELINE config 1 shape (64 hidden, 3x3, 64x64 maps) at B=2, T=3."""
+    torch.manual_seed(0)
+    with torch.no_grad():
+        m = rf.ConvLSTM(64, 64, [3, 3]).eval()
+        w, b = m.LSTMlayer.conv[0].weight.clone(), m.LSTMlayer.conv[0].bias.clone()
+        m = m.cuda()
+        x = torch.randn(2, 3, 64, 64, 64)
+        out_ref, h_ref, c_ref = O.convlstm(x, w, b)
+        out, h, c = m(x.cuda())
+        assert max_rel(out, out_ref) < BF16_TOL and max_rel(c, c_ref) < BF16_TOL
+        assert torch.equal(h, out[:, -1])
+
+
+def test_requires_no_grad_and_cuda(rf):
+    m = rf.Squeeze2d()
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 1, 2, 2, device="cuda"), undo_squeeze=False)
+    with torch.no_grad(), pytest.raises(RuntimeError):
+        m(torch.zeros(1, 1, 2, 2), undo_squeeze=False)

@@ -1,0 +1,157 @@
+"""Host-side logic that needs no GPU: state_dict compatibility with the reference, weight repacking,
+the ConvLSTM gate-row interleave, batch sharding, and the world_size-2 (gloo) replica sync."""
+import os
+import types
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+import recurrent_flows_msc_b200 as rf
+from conftest import load_golden
+
+
+def test_state_dict_keys_match_reference_fixtures():
+    g = load_golden("listglow_cond")
+    m = rf.ListGlow(g["x_size"], g["cond_sizes"], g["base_size"], types.SimpleNamespace(**g["args"]))
+    assert set(m.state_dict().keys()) == set(g["sd"].keys())
+    for k, v in m.state_dict().items():
+        assert tuple(v.shape) == tuple(g["sd"][k].shape), k
+    m.load_state_dict(g["sd"])
+    g2 = load_golden("glowstep")
+    a = types.SimpleNamespace(LU_decomposed=True, n_units_affine=16, non_lin_glow="relu", clamp_type="realnvp",
+                              flow_norm="actnorm", flow_batchnorm_momentum=0.0)
+    assert set(rf.GlowStep([2, 8, 4, 4], [2, 3, 4, 4], a).state_dict().keys()) == set(g2["sd"].keys())
+    g3 = load_golden("invconv_plain")
+    assert set(rf.InvConv(6, False).state_dict().keys()) == set(g3["sd"].keys())
+    g4 = load_golden("convlstm")
+    assert set(rf.ConvLSTM(3, 4, [3, 3]).state_dict().keys()) == set(g4["sd"].keys())
+    g5 = load_golden("split2d_cond_softplus")
+    assert set(rf.Split2d([2, 8, 4, 4], [2, 6, 4, 4]).state_dict().keys()) == set(g5["sd"].keys())
+
+
+def test_invconv_init_is_orthogonal_lu():
+    torch.manual_seed(0)
+    m = rf.InvConv(12, True)
+    W, W_inv, per_pixel = m.matrices()
+    assert (W.t() @ W - torch.eye(12)).abs().max() < 1e-5        # SURVEY section 4 probe
+    assert (W @ W_inv - torch.eye(12)).abs().max() < 1e-5
+    assert abs(float(per_pixel)) < 1e-4
+    w2, dl = m.get_weight(torch.zeros(2, 12, 3, 5), reverse=True)
+    assert w2.shape == (12, 12, 1, 1) and abs(float(dl)) < 1e-3
+
+
+def test_bad_enums_assert_like_reference():
+    with pytest.raises(AssertionError):
+        rf.Split2d([2, 8, 4, 4], [2, 6, 4, 4], clamp_function="tanh")
+    with pytest.raises(AssertionError):
+        rf.ActFun("gelu")
+    with pytest.raises(NotImplementedError):
+        rf.Conv2dNorm(4, 4, norm="batchnorm")
+
+
+def im2col_gemm(x, wp, cin_pad, N, k):
+    """Reference of the kernel's GEMM view: A[pixel, tap*cin_pad + c] * Wp^T with zero 'same' padding."""
+    B, C, H, W = x.shape
+    p = (k - 1) // 2
+    xp = F.pad(x, (p, p, p, p))
+    cols = []
+    for ky in range(k):
+        for kx in range(k):
+            t = xp[:, :, ky:ky + H, kx:kx + W]
+            cols.append(F.pad(t, (0, 0, 0, 0, 0, cin_pad - C)))
+    A = torch.cat(cols, 1).permute(0, 2, 3, 1).reshape(B * H * W, k * k * cin_pad)
+    out = A @ wp.float().t()
+    return out[:, :N].reshape(B, H, W, N).permute(0, 3, 1, 2)
+
+
+@pytest.mark.parametrize("k", [1, 3])
+def test_pack_conv_weight_layout(k):
+    torch.manual_seed(1)
+    x = torch.randn(2, 5, 4, 6).to(torch.bfloat16).float()
+    w = torch.randn(7, 5, k, k).to(torch.bfloat16).float()
+    wp, cin_pad = rf.ops.pack_conv_weight(w)
+    assert wp.shape == (16, k * k * 64) and cin_pad == 64 and wp.dtype == torch.bfloat16
+    torch.testing.assert_close(im2col_gemm(x, wp, cin_pad, 7, k), F.conv2d(x, w, None, 1, (k - 1) // 2), rtol=1e-4, atol=1e-4)
+    perm = torch.tensor([3, 4, 0, 1, 2])   # staging order [cond | z1] vs the reference's cat[z1, cond]
+    wp2, _ = rf.ops.pack_conv_weight(w, perm)
+    torch.testing.assert_close(im2col_gemm(x[:, perm], wp2, cin_pad, 7, k), F.conv2d(x, w, None, 1, (k - 1) // 2), rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("hidden", [4, 60, 64, 200, 256])
+def test_lstm_gate_row_interleave(hidden):
+    torch.manual_seed(2)
+    cell = rf.ConvLSTMLayer(3, hidden, [3, 3], True)
+    wgt, cin_pad, b, ht, ht_pad = cell._weights()
+    assert hidden % ht == 0 and 4 * ht_pad <= 256 and ht_pad % 8 == 0
+    n_tiles = hidden // ht
+    assert wgt.shape[0] == n_tiles * 4 * ht_pad
+    w = cell.conv[0].weight.detach()
+    ref, _ = rf.ops.pack_conv_weight(w)
+    for t in range(n_tiles):
+        for gate in range(4):
+            rows = slice((t * 4 + gate) * ht_pad, (t * 4 + gate) * ht_pad + ht)
+            src = slice(gate * hidden + t * ht, gate * hidden + t * ht + ht)
+            assert torch.equal(wgt[rows], ref[src])
+            assert torch.equal(b[rows], cell.conv[0].bias.detach()[src])
+            assert float(wgt[(t * 4 + gate) * ht_pad + ht:(t * 4 + gate + 1) * ht_pad].float().abs().sum()) == 0
+
+
+def test_versioned_cache_tracks_inplace_updates():
+    m = rf.Conv2dZeros(4, 6)
+    s0, _ = m.affine()
+    with torch.no_grad():
+        m.logs.add_(1.0)
+    s1, _ = m.affine()
+    assert not torch.equal(s0, s1)
+    assert m.affine()[0] is s1
+
+
+def test_shard_range_covers_batch():
+    for n in (0, 1, 7, 30, 570):
+        for ws in (1, 2, 3, 8):
+            spans = [rf.shard_range(n, r, ws) for r in range(ws)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(ws - 1))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+    x = torch.arange(10)
+    assert torch.equal(torch.cat([rf.shard_batch(x, r, 3) for r in range(3)]), x)
+    a, b = rf.shard_batch([x, [x, None]], 1, 2)
+    assert torch.equal(a, x[5:]) and b[1] is None
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(100 + rank)      # replicas start different (as after a per-shard ActNorm init)
+        a = types.SimpleNamespace(LU_decomposed=True, n_units_affine=8, non_lin_glow="relu", clamp_type="realnvp",
+                                  flow_norm="actnorm", flow_batchnorm_momentum=0.0)
+        m = rf.GlowStep([2, 4, 4, 4], [2, 2, 4, 4], a)
+        with torch.no_grad():
+            m.norm.logs.normal_()
+        n = rf.sync_module_state(m, src=0)
+        flat = torch.cat([t.detach().float().reshape(-1) for t in list(m.parameters()) + list(m.buffers())])
+        got = rf.parallel.gather_batch(flat[None])
+        lo, hi = rf.shard_range(7, rank, world)
+        q.put((rank, n, bool(torch.equal(got[0], got[1])), (lo, hi)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_sync_and_shards():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert all(same for _, _, same, _ in res)
+    assert res[0][1] > 0 and res[0][3] == (0, 4) and res[1][3] == (4, 7)
