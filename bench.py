@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""Benchmark of the RFN hot path (Glow decoder + ConvLSTM recurrence) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (config.workload = "rfn_J_hotpath_fwd"): the hot path of ONE RFN training batch of the
+reference's job-script configuration J (RFN/default_rfn_job.sh: B=30 sequences, 1x64x64, 10+10 frames,
+L=5, K=10, hidden 256, h=200, z=56):
+  * 19 ConvLSTM cell steps (512 -> 200 hidden channels, 3x3, 2x2 maps, batch 30), and
+  * ListGlow.log_prob (dequantise, f: 5 levels x 10 GlowSteps + 4 Split2d, learned prior) on the
+    B*(T-1) = 570 predicted frames, time-batched into one call (exact because nothing the
+    flow produces feeds back into the recurrence).
+One step = one such batch, forward direction (density evaluation).  Backward kernels do not exist yet, so
+this is NOT a full training step; the JSON line says so in config.pass.  value = frames / s with inputs
+resident in HBM; e2e = same through the public nn.Module API from pinned HOST buffers (H2D of x, the
+condition pyramid and the ConvLSTM input, D2H of nll and h) inside the timed region.
+
+With --gpus N (torchrun) every rank processes its own batch of 30 sequences (weak scaling, no data-path
+collective); time = max over ranks.
+"""
+import argparse
+import contextlib
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+import types
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "RFN 64x64 frames/sec (Glow decoder + ConvLSTM hot path, forward)"
+J = dict(B=30, T=20, L=5, K=10, hidden=256, n_units_prior=512, cond_ch=[16, 32, 64, 128, 256],
+         base_ch=256, lstm_in=512, lstm_hidden=200, n_bits=8)
+
+
+def glow_args():
+    return types.SimpleNamespace(LU_decomposed=True, n_units_affine=J["hidden"], non_lin_glow="relu",
+                                 clamp_type="realnvp", flow_norm="actnorm", flow_batchnorm_momentum=0.0,
+                                 learn_prior=True, n_units_prior=J["n_units_prior"], make_conditional=True,
+                                 base_norm="actnorm", split2d_act="softplus", L=J["L"], K=J["K"], n_bits=J["n_bits"])
+
+
+def cond_sizes(n):
+    return [[n, c, 32 >> l, 32 >> l] for l, c in enumerate(J["cond_ch"])]
+
+
+def trained_like(module, seed=0):
+    """Random-init weights made non-trivial (zero-init Conv2dZeros / realnvp scale would make every
+    coupling the identity); ActNorms marked initialised.  No checkpoint exists offline."""
+    gen = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for name, p in module.named_parameters():
+            p.add_(torch.randn(p.shape, generator=gen) * (0.01 if "conv.weight" in name else 0.05))
+        for name, b in module.named_buffers():
+            if name.endswith("initialized"):
+                b.fill_(1)
+
+
+def synth_inputs(n_frames, n_seq, seed):
+    """Solver.preprocess-shaped data (RFN/trainer.py:165-175): floor(u*256)/256 - 0.5; SM-MNIST-like sparsity."""
+    g = torch.Generator().manual_seed(seed)
+    u = torch.rand(n_frames, 1, 64, 64, generator=g)
+    mask = (torch.rand(n_frames, 1, 64, 64, generator=g) < 0.1).float()  # ~90 % black canvas
+    x = torch.floor(u * mask * 256) / 256 - 0.5
+    conds = [torch.randn(*s, generator=g) for s in cond_sizes(n_frames)]
+    base = torch.randn(n_frames, J["base_ch"], 2, 2, generator=g)
+    feats = torch.randn(n_seq, J["T"] - 1, J["lstm_in"], 2, 2, generator=g)
+    return x, conds, base, feats
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port (the reference is pure Python and cannot travel to the GPU box)
+# ------------------------------------------------------------------------------------------------
+def cpu_step_builder(n_frames):
+    import oracle as O
+    import recurrent_flows_msc_b200 as rf
+    torch.manual_seed(0)
+    flow = rf.ListGlow([n_frames, 1, 64, 64], cond_sizes(n_frames), [n_frames, J["base_ch"], 2, 2], glow_args()).eval()
+    trained_like(flow, 0)
+    sd = {k: v.clone() for k, v in flow.state_dict().items()}
+    lstm = rf.ConvLSTM(J["lstm_in"], J["lstm_hidden"], [3, 3])
+    w, b = lstm.LSTMlayer.conv[0].weight.detach().clone(), lstm.LSTMlayer.conv[0].bias.detach().clone()
+    x, conds, base, _ = synth_inputs(n_frames, 1, 1)
+    feats = torch.randn(n_frames, 1, J["lstm_in"], 2, 2)
+    noise = torch.rand(n_frames, 1, 64, 64) / 256
+
+    def step():
+        with torch.no_grad():
+            O.convlstm(feats, w, b)
+            _, nll = O.listglow_log_prob(x, conds, base, sd, J["L"], J["K"], J["n_bits"], noise=noise, learn_prior=True)
+        return nll
+    return step
+
+
+def time_cpu(n_frames, steps, warmup):
+    torch.set_num_threads(os.cpu_count() or 1)
+    step = cpu_step_builder(n_frames)
+    for _ in range(warmup):
+        step()
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        step()
+        ts.append(time.perf_counter() - t0)
+    return n_frames / statistics.median(ts), statistics.median(ts), torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = 64
+    fps, t, cores = time_cpu(n, max(1, args.steps), max(0, args.warmup))
+    sample = f"{n} frames per step: oracle ListGlow.log_prob (config J) + 1 ConvLSTM cell step at batch {n}, fp32, torch CPU"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "rfn_J_hotpath_fwd", "pass": "forward (density evaluation); no backward", "frames_per_step": n},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-lms", "50", "-i", str(index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [f.strip() for f in line.split(",")]))
+
+    def summary(self, t0, t1):
+        if self.proc is not None:
+            self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 <= t <= t1 + 0.06] or [r for _, r in self.rows[-3:]]
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for nme, v in zip(names, r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+class KernelTimer:
+    """CUDA-event timing of every librfk launch on the launching (current) stream."""
+
+    def __init__(self):
+        self.rec = []
+
+    @contextlib.contextmanager
+    def __call__(self, name, meta):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        yield
+        b.record()
+        self.rec.append((name, meta, a, b))
+
+    def table(self):
+        torch.cuda.synchronize()
+        agg = {}
+        for name, meta, a, b in self.rec:
+            d = agg.setdefault(name, {"launches": 0, "ms": 0.0, "flops": 0.0, "flops_padded": 0.0})
+            d["launches"] += 1
+            d["ms"] += a.elapsed_time(b)
+            if meta:
+                d["flops"] += meta["flops"]
+                d["flops_padded"] += meta["flops_padded"]
+        return agg
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    import recurrent_flows_msc_b200 as rf
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; this path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, T = J["B"], J["T"]
+    n_frames = B * (T - 1)
+
+    # identical replicas (same seed); each rank draws its own shard of sequences
+    torch.manual_seed(0)
+    flow = rf.ListGlow([n_frames, 1, 64, 64], cond_sizes(n_frames), [n_frames, J["base_ch"], 2, 2], glow_args()).eval()
+    trained_like(flow, 0)
+    lstm = rf.ConvLSTM(J["lstm_in"], J["lstm_hidden"], [3, 3]).eval()
+    flow, lstm = flow.to(dev), lstm.to(dev)
+    hx, hconds, hbase, hfeats = synth_inputs(n_frames, B, 1 + rank)
+    host = [t.pin_memory() for t in [hx, hbase, hfeats] + hconds]
+    h2d_bytes = sum(t.numel() * t.element_size() for t in host)
+    nll_host = torch.empty(n_frames, dtype=torch.float32).pin_memory()
+    h_host = torch.empty(B, J["lstm_hidden"], 2, 2, dtype=torch.float32).pin_memory()
+    d2h_bytes = nll_host.numel() * 4 + h_host.numel() * 4
+
+    def upload():
+        dx, dbase, dfeats, *dconds = [t.to(dev, non_blocking=True) for t in host]
+        return dx, dconds, dbase, dfeats
+
+    def hot_path(dx, dconds, dbase, dfeats):
+        with torch.no_grad():
+            _, h_last, _ = lstm(dfeats)
+            _, nll = flow.log_prob(dx, dconds, dbase)
+        return nll, h_last
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    resident = upload()
+    for _ in range(max(args.warmup, 3)):
+        nll, _ = hot_path(*resident)
+    torch.cuda.synchronize()
+    assert torch.isfinite(nll).all(), "non-finite nll in warm-up"
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    # ---- device-resident timing ---------------------------------------------------------------
+    barrier()
+    l0 = rf._lib.launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.time()
+    ev0.record()
+    for _ in range(args.steps):
+        hot_path(*resident)
+    ev1.record()
+    barrier()
+    t_wall1 = time.time()
+    launches = rf._lib.launches - l0
+    ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+    # ---- end-to-end from pinned host buffers ------------------------------------------------------
+    for _ in range(2):
+        nll, h_last = hot_path(*upload())
+    barrier()
+    ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev2.record()
+    for _ in range(args.steps):
+        nll, h_last = hot_path(*upload())
+        nll_host.copy_(nll, non_blocking=True)
+        h_host.copy_(h_last, non_blocking=True)
+    ev3.record()
+    barrier()
+    ms_e2e = torch.tensor([ev2.elapsed_time(ev3)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ms_e2e, op=dist.ReduceOp.MAX)
+    clocks = sampler.summary(t_wall0, t_wall1) if sampler else None
+
+    if rank == 0:
+        ms_step = float(ms) / args.steps
+        ms_step_e2e = float(ms_e2e) / args.steps
+        value = world * n_frames / (ms_step / 1e3)
+        e2e = world * n_frames / (ms_step_e2e / 1e3)
+        # ---- per-kernel CUDA-event pass (same step, outside the timed regions) -> roofline of the dominant kernel
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        kt = KernelTimer()
+        rf._lib.tracer = kt
+        torch.cuda.profiler.start()   # `ncu --profile-from-start off` captures exactly this one step
+        hot_path(*resident)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        rf._lib.tracer = None
+        table = kt.table()
+        total_ms = sum(d["ms"] for d in table.values())
+        top = max(table, key=lambda k: table[k]["ms"])
+        d = table[top]
+        peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+        ach = d["flops"] / (d["ms"] / 1e3) / 1e12 if d["flops"] else None
+        roofline = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
+                    "frac": (ach / peak_tf) if ach else None, "traffic": None,
+                    "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"
+                    if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)",
+                    "share_of_step": d["ms"] / total_ms, "launches_per_step": d["launches"],
+                    "avg_launch_us": 1e3 * d["ms"] / d["launches"],
+                    "issued_tflops_incl_padding": d["flops_padded"] / (d["ms"] / 1e3) / 1e12}
+        kernels = {k: {"launches": v["launches"], "ms": round(v["ms"], 4),
+                       "tflops": round(v["flops"] / (v["ms"] / 1e3) / 1e12, 1) if v["flops"] else None}
+                   for k, v in sorted(table.items(), key=lambda kv: -kv[1]["ms"])}
+        n_cpu = 64
+        cpu_fps, cpu_t, cores = time_cpu(n_cpu, 3, 1)
+        out = {
+            "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "rfn_J_hotpath_fwd",
+                       "pass": "forward (density evaluation): 19 ConvLSTM steps + ListGlow.log_prob on 570 frames; no backward yet",
+                       "frames_per_step_per_gpu": n_frames, "sequences_per_gpu": B, "L": J["L"], "K": J["K"],
+                       "hidden": J["hidden"], "conv_dtype": "bf16 in / fp32 accumulate", "flow_dtype": "f32",
+                       "l2": "inputs_exceed_L2 (>=300 MB of activations per level-1 GlowStep vs 126 MB L2)",
+                       "parallelism": f"batch-sharded x{world}, no data-path collective"},
+            "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                    "ms_per_step": ms_step_e2e},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernels_ms_per_step": kernels,
+            "cpu_baseline": {"value": cpu_fps, "unit": "frames/s", "cores": cores, "kind": "port",
+                             "sample": f"{n_cpu} frames: oracle ListGlow.log_prob (config J) + 1 ConvLSTM step at batch {n_cpu}, "
+                                       f"median of 3 after 1 warm-up ({cpu_t:.2f} s each)"},
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

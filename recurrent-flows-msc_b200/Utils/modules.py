@@ -110,7 +110,7 @@ class ConvLSTMLayer(nn.Module):
                            c_next, h_out, next_buf, self.in_channels)
         return c_next
 
-    def _buffers(self, B, H, W, device):
+    def _staging(self, B, H, W, device):
         cin = self.in_channels + self.hidden_channels
         shape = (B, H, W, ops.pad_to(cin, 64))
         return [ops.workspace(("lstm_in", cin, i), shape, device) for i in range(2)]
@@ -124,7 +124,7 @@ class ConvLSTMLayer(nn.Module):
         if not self.init_done:
             self.initialize_peephole(h, w, x.device)
             self.init_done = True
-        buf = self._buffers(b, h, w, x.device)[0]
+        buf = self._staging(b, h, w, x.device)[0]
         ops.pack_nhwc(x, 0, c, buf, 0)
         if cur_state[0] is None:
             buf[..., c:c + self.hidden_channels].zero_()
@@ -159,7 +159,7 @@ class ConvLSTM(nn.Module):
         if not cell.init_done:
             cell.initialize_peephole(h, w, x.device)
             cell.init_done = True
-        bufs = cell._buffers(b, h, w, x.device)
+        bufs = cell._staging(b, h, w, x.device)
         out = torch.empty(b, seq_len, hc, h, w, device=x.device, dtype=torch.float32)
         if ht is None:
             bufs[0][..., channel:channel + hc].zero_()

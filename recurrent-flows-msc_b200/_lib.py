@@ -71,9 +71,16 @@ def lib():
     return _lib
 
 
-def call(name, *args):
+tracer = None  # optional callable(name, meta) -> context manager; bench.py uses it to time kernels with CUDA events
+
+
+def call(name, *args, meta=None):
     global launches
-    rc = getattr(lib(), name)(*args)
+    if tracer is not None:
+        with tracer(name, meta):
+            rc = getattr(lib(), name)(*args)
+    else:
+        rc = getattr(lib(), name)(*args)
     if rc != 0:
         raise RfkError(f"{name} failed ({rc}): {lib().rfk_last_error().decode()}")
     launches += 1

@@ -77,6 +77,8 @@ def pack_nhwc(src, c_lo, n, dst, dst_off):
     """src NCHW f32 channels [c_lo,c_lo+n) -> dst NHWC bf16 [B,H,W,ld] at channel dst_off.
     src may be a batch-strided slice (e.g. x[:, t] of a [B,T,C,H,W] sequence)."""
     B, C, H, W = src.shape
+    if n == 0:
+        return
     if not src.is_cuda or src.dtype != torch.float32 or src[0].is_contiguous() is False:
         raise _lib.RfkError("src must be a float32 CUDA tensor, dense within each sample")
     _chk(dst, torch.bfloat16, "dst")
@@ -91,6 +93,13 @@ def copy_channels(src, src_off, dst, dst_off, n):
     call("rfk_copy_channels", src.data_ptr(), Cs, src_off, dst.data_ptr(), dst.shape[1], dst_off, n, B, H * W, _stream())
 
 
+def _gemm_meta(M, n, taps, cin_pad, wgt):
+    """Algorithmic (unpadded) and issued (padded) FLOPs of one implicit-GEMM launch, for bench.py's roofline."""
+    cin = getattr(wgt, "rfk_cin", cin_pad)
+    return {"flops": 2.0 * M * n * taps * cin, "flops_padded": 2.0 * M * wgt.shape[0] * taps * cin_pad,
+            "M": M, "N": n, "K": taps * cin}
+
+
 def conv_gemm(act, cin_pad, wgt, n, taps, scale, shift, act_fn, out, out_off=0):
     """act NHWC bf16 [B,H,W,ld]; wgt bf16 [n_pad, taps*cin_pad]; out NHWC bf16 (4-D, channel last) or NCHW f32."""
     _chk(act, torch.bfloat16, "act")
@@ -103,7 +112,8 @@ def conv_gemm(act, cin_pad, wgt, n, taps, scale, shift, act_fn, out, out_off=0):
         kind, out_ld = OUT_NCHW_F32, 0
         _chk(out, name="out")
     call("rfk_conv_gemm", act.data_ptr(), B, H, W, ld, cin_pad, wgt.data_ptr(), n, wgt.shape[0], taps,
-         _p(scale), _p(shift), ACT[act_fn], kind, out.data_ptr(), out_ld, out_off, _stream())
+         _p(scale), _p(shift), ACT[act_fn], kind, out.data_ptr(), out_ld, out_off, _stream(),
+         meta=_gemm_meta(B * H * W, n, taps, cin_pad, wgt))
     return out
 
 
@@ -114,7 +124,7 @@ def conv_gemm_coupling(act, cin_pad, wgt, n, taps, scale, shift, z, clamp_type, 
     B, H, W, ld = act.shape
     call("rfk_conv_gemm_coupling", act.data_ptr(), B, H, W, ld, cin_pad, _chk(wgt, torch.bfloat16).data_ptr(), n,
          wgt.shape[0], taps, _p(scale), _p(shift), z.data_ptr(), CLAMP[clamp_type], _p(clamp_scale), _p(clamp_shift),
-         _p(logdet), int(reverse), _stream())
+         _p(logdet), int(reverse), _stream(), meta=_gemm_meta(B * H * W, n, taps, cin_pad, wgt))
 
 
 def conv_gemm_lstm(act, cin_pad, wgt, hidden, ht, ht_pad, taps, bias, c_prev, peep, c_next, h_out, h_nhwc, h_off):
@@ -123,7 +133,8 @@ def conv_gemm_lstm(act, cin_pad, wgt, hidden, ht, ht_pad, taps, bias, c_prev, pe
     call("rfk_conv_gemm_lstm", act.data_ptr(), B, H, W, ld, cin_pad, _chk(wgt, torch.bfloat16).data_ptr(), hidden, ht,
          ht_pad, taps, _p(bias), _p(c_prev), c_prev.stride(0) if c_prev is not None else 0, _p(peep),
          c_next.data_ptr(), c_next.stride(0), h_out.data_ptr(), h_out.stride(0),
-         _p(h_nhwc), h_off, h_nhwc.shape[-1] if h_nhwc is not None else 0, _stream())
+         _p(h_nhwc), h_off, h_nhwc.shape[-1] if h_nhwc is not None else 0, _stream(),
+         meta=_gemm_meta(B * H * W, 4 * hidden, taps, cin_pad, wgt))
 
 
 def coupling_tail(nn_out, z, clamp_type, clamp_scale, clamp_shift, logdet, reverse):
@@ -199,4 +210,6 @@ def pack_conv_weight(weight, in_perm=None, row_perm=None, n_pad=None):
     n_pad = n_pad or pad_to(N, 16)
     out = torch.zeros(n_pad, kh * kw, cin_pad, device=w.device, dtype=torch.bfloat16)
     out[:N, :, :Cin] = w.to(torch.bfloat16)
-    return out.reshape(n_pad, kh * kw * cin_pad).contiguous(), cin_pad
+    out = out.reshape(n_pad, kh * kw * cin_pad).contiguous()
+    out.rfk_cin = Cin  # real input channels, for FLOP accounting
+    return out, cin_pad
