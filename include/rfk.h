@@ -141,6 +141,16 @@ int rfk_coupling_tail(const float* nn_out, float* z, int B, int C, int HW,
                       int clamp_type, const float* clamp_scale, const float* clamp_shift,
                       float* logdet, int reverse, void* stream);
 
+/* Coupling tail fed by a TAP-SPLIT convolution.  For few output channels (9*C <= 256) the coupling network's
+ * last 3x3 conv (256 -> C) is cheaper as ONE 1x1 GEMM with N = 9*C (rfk_conv_gemm, taps=1, weight row
+ * t*C + c = W[c, :, ky, kx], t = 3*ky+kx, f32 NCHW output `taps` [B,9C,H,W]): the activations are read once
+ * instead of once per tap.  This kernel sums the nine planes shifted by their tap offset (zero outside the image),
+ * applies Conv2dZeros' affine (scale/shift [C]) and then the coupling update exactly like rfk_coupling_tail. */
+int rfk_coupling_tail_taps(const float* taps, float* z, int B, int C, int H, int W,
+                           const float* scale, const float* shift,
+                           int clamp_type, const float* clamp_scale, const float* clamp_shift,
+                           float* logdet, int reverse, void* stream);
+
 /* ---- a5/a7  Gaussian log-density and sampling (Flow/glow_modules.py:362-368, glow.py:139,154)
  * params [B,2n,HW] f32 (nullable = zeros) holds (mean, raw) per `pairing`; std per `std_kind`.
  * logp : logdet[b] += sum_{j<n,p} log N(z[b,z_off+j,p]; mean, std)        (z has z_C channels)
@@ -154,6 +164,11 @@ int rfk_gauss_sample(const float* eps, const float* params, int n, int B, int HW
  * cc [B,4Hc,HW] f32 in gate order i,f,o,g (bias already added); peep nullable [3,Hc,HW]. */
 int rfk_convlstm_pointwise(const float* cc, const float* c_prev, const float* peep,
                            float* h_out, float* c_next, int B, int Hc, int HW, void* stream);
+
+/* Debug aid: when buf != NULL, every conv-GEMM CTA of later launches (grids of at most capacity_ctas CTAs)
+ * writes 8 %globaltimer stamps (ns) to buf[8*cta..]: start, setup done, first/last TMA issued, first stage
+ * landed, last MMA issued, accumulator ready, epilogue done.  NULL switches it off (the default). */
+int rfk_debug_set_timeline(unsigned long long* buf, long long capacity_ctas);
 
 /* logdet[b] += *addend  (device scalar; the parameter-only log-det terms of ActNorm / InvConv) */
 int rfk_add_scalar(float* logdet, const float* addend, float alpha, int B, void* stream);

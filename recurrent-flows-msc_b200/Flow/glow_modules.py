@@ -17,6 +17,9 @@ from ..Utils.utils import split_feature  # noqa: F401  (re-exported like the ref
 from ..Utils.modules import ActFun
 
 
+TAP_SPLIT_MAX_N = 256  # AffineCoupling: use the tap-split form of the last conv while 9*C fits one N tile
+
+
 def _require_no_grad():
     if torch.is_grad_enabled():
         raise RuntimeError("recurrent-flows-msc_b200: backward kernels are not implemented yet; "
@@ -150,6 +153,10 @@ class Conv2dZeros(nn.Module):
 
     def packed(self, key="id", in_perm=None):
         return self._cache.get(("w", key), (self.conv.weight,), lambda: ops.pack_conv_weight(self.conv.weight, in_perm))
+
+    def packed_taps(self):
+        """Tap-split 1x1 form of the 3x3 weight (ops.pack_tap_split_weight), cached."""
+        return self._cache.get(("w9",), (self.conv.weight,), lambda: ops.pack_tap_split_weight(self.conv.weight))
 
     def affine(self):
         def build():
@@ -329,12 +336,21 @@ class AffineCoupling(nn.Module):
         self.net[0].fused(nn_in, h1, self.non_lin, "cz", self._perm(dev))
         self.net[2].fused(h1, h2, self.non_lin)
         last = self.net[4]
-        wgt, cin_pad = last.packed()
         scale, shift = last.affine()
         ld, extra = _ld_begin(logdet, B, dev, inplace=_ctx is not None)
         cs = self.scale.detach().reshape(-1) if self.clamp_type == "realnvp" else None
         csh = self.scale_shift.detach().reshape(-1) if self.clamp_type == "realnvp" else None
-        ops.conv_gemm_coupling(h2, cin_pad, wgt, C, last.taps, scale, shift, out, self.clamp_type, cs, csh, ld, reverse)
+        if last.taps == 9 and 9 * C <= TAP_SPLIT_MAX_N:
+            # few output channels: one 1x1 GEMM with N = 9*C (activations read once, not once per tap),
+            # then a streaming gather of the nine shifted planes fused with the coupling tail
+            wgt9, cin_pad = last.packed_taps()
+            taps = ops.workspace(("cpl_taps", C), (B, 9 * C, H, W), dev, torch.float32)
+            ops.conv_gemm(h2, cin_pad, wgt9, 9 * C, 1, None, None, "none", taps)
+            ops.coupling_tail_taps(taps, out, scale, shift, self.clamp_type, cs, csh, ld, reverse)
+        else:
+            wgt, cin_pad = last.packed()
+            ops.conv_gemm_coupling(h2, cin_pad, wgt, C, last.taps, scale, shift, out, self.clamp_type, cs, csh, ld,
+                                   reverse)
         return out, _ld_end(ld, extra)
 
 

@@ -30,11 +30,14 @@ SIGNATURES = {
                            c_void_p, c_int, c_int, c_void_p],
     "rfk_coupling_tail": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int,
                           c_void_p],
+    "rfk_coupling_tail_taps": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p,
+                               c_void_p, c_void_p, c_int, c_void_p],
     "rfk_gauss_logp": [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
     "rfk_gauss_sample": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_int, c_int,
                          c_void_p],
     "rfk_convlstm_pointwise": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
     "rfk_add_scalar": [c_void_p, c_void_p, c_float, c_int, c_void_p],
+    "rfk_debug_set_timeline": [c_void_p, c_longlong],
 }
 
 # enums of rfk.h

@@ -6,18 +6,23 @@
 //   [128 x 64] K-major block.  It is fetched by ONE 4-D TMA box {64 ch, TW, TH, NIMG} whose (x,y)
 //   origin is shifted by the tap; out-of-image pixels are zero-filled by the TMA unit, which is the
 //   convolution's zero padding -- no im2col buffer and no halo code.
-// * weights are bf16 [n_pad, taps*cin_pad] (K-major), fetched by a 2-D TMA box {64, BN}.
+// * weights are bf16 [n_pad, taps*cin_pad] (K-major).  When the whole [BN x K] slice fits in shared
+//   memory next to the pipeline it is loaded ONCE per CTA (weight-stationary) and only activations
+//   stream; otherwise a {64, BN} weight box travels with every activation stage.
 // * both land in shared memory in the 128-byte-swizzled K-major layout tcgen05.mma reads directly.
-// * one elected thread issues tcgen05.mma (M=128, N=BN, K=16) into an fp32 accumulator in TMEM;
-//   completion is tracked with tcgen05.commit -> mbarrier.  A multi-stage full/empty mbarrier ring
-//   decouples the TMA producer warp from the MMA warp.
-// * four epilogue warps read the accumulator with tcgen05.ld (one pixel per thread) and apply a fused
-//   epilogue: per-channel affine (+ReLU) to bf16 NHWC / f32 NCHW, the affine-coupling tail with the
-//   per-sample log-det reduction, or the ConvLSTM cell update.
-//
-// Two CTAs are resident per SM (<=113 KB shared memory and <=256 TMEM columns each), so one CTA's
-// epilogue overlaps the other's main loop.
+// * PERSISTENT: one CTA per SM walks the pixel tiles with a static stride.  One elected thread issues
+//   tcgen05.mma (M=128, N=BN, K=16) into one of TWO fp32 accumulators in TMEM, so the epilogue of tile
+//   i overlaps the main loop of tile i+1.  Producer -> MMA -> epilogue hand-offs are mbarriers
+//   (TMA complete_tx, tcgen05.commit, and explicit arrives).
+// * eight epilogue warps (two per TMEM lane quadrant) read the accumulator with tcgen05.ld and apply a
+//   fused epilogue from shared-memory-staged per-channel scale/shift:
+//     - affine (+ReLU) -> bf16, staged in swizzled shared memory and written with TMA stores (NHWC),
+//       or f32 NCHW with direct coalesced stores;
+//     - the affine-coupling tail with the per-sample log-det reduction (z2 updated in place);
+//     - the ConvLSTM cell update.
 #include <cuda.h>
+
+#include <algorithm>
 
 #include "common.cuh"
 
@@ -27,7 +32,11 @@ constexpr int BM = 128;          // pixels per tile = UMMA M
 constexpr int BK = 64;           // bf16 channels per pipeline stage (= one 128 B swizzle row)
 constexpr int UMMA_K = 16;       // K of one tcgen05.mma.kind::f16
 constexpr int A_STAGE_BYTES = BM * BK * 2;
-constexpr int kGemmThreads = 192;  // warp 0: TMA producer, warp 1: TMEM alloc + MMA issue, warps 2-5: epilogue
+constexpr int STG_BYTES = BM * 128;  // one 64-channel bf16 output block of a tile
+constexpr int kGemmThreads = 384;    // warp 0: TMA, warp 1: MMA, warp 2: TMEM alloc, warps 4-11: epilogue
+constexpr int kEpiWarp0 = 4;
+constexpr int kEpiWarps = 8;
+constexpr int SMEM_LIMIT = 232448;   // 227 KB opt-in maximum per CTA
 
 struct GemmArgs {
   int B, H, W;
@@ -35,24 +44,27 @@ struct GemmArgs {
   int BN;                // tile width in output channels (UMMA N), multiple of 16, <= 256
   int taps, kchunks;     // kchunks = cin_pad / 64
   int tw_log2, th_log2;  // tile = NIMG x TH x TW pixels, TW*TH*NIMG = 128
-  int tiles_x, tiles_y;
+  int tiles_x, tiles_y, m_tiles;
   int stages;
   int tmem_cols;
+  int b_resident;        // 1: the CTA's whole weight slice lives in shared memory
+  int use_stg;           // 1: shared-memory staging buffers for TMA stores are allocated
+  const float* scale;    // per output channel (length n_ss), nullable = 1
+  const float* shift;    // per output channel (length n_ss), nullable = 0
+  int n_ss;
+  unsigned long long* timeline;  // debug: 8 globaltimer stamps per CTA (rfk_debug_set_timeline), else null
 };
 
 struct PlainEpi {
-  const float* scale;
-  const float* shift;
   int act_fn;
   int out_kind;
   void* out;
   int out_ld, out_off;
   int vec_ok;
+  int tma_store;
 };
 
 struct CouplingEpi {
-  const float* scale;
-  const float* shift;
   float* z;
   int clamp_type;
   const float* cs;
@@ -62,7 +74,6 @@ struct CouplingEpi {
 };
 
 struct LstmEpi {
-  const float* bias;  // permuted like the weight rows
   int hidden, ht, ht_pad;
   const float* c_prev;
   long long c_prev_bs;
@@ -80,11 +91,24 @@ struct LstmEpi {
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define RFK_STAMP(slot)                                                                               \
+  do {                                                                                                \
+    if (g.timeline) g.timeline[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8 + (slot)] = gtime(); \
+  } while (0)
+
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
@@ -121,6 +145,18 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map),
+               "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void named_bar(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -154,17 +190,13 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
-  uint32_t r[16];
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t* r) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 __device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t* r) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
@@ -179,41 +211,107 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   return v;
 }
 
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
 // ------------------------------------------------------------------------------------------
-// epilogues: each thread owns accumulator row `row` (= one pixel), columns [0, BN) of the tile
+// epilogues.  Thread (quadrant q, lane) owns accumulator row q*32+lane (= one pixel); the two warps
+// of a quadrant (`half` 0/1) split the tile's columns.  `ss` = scale[BN] then shift[BN] in shared memory.
 // ------------------------------------------------------------------------------------------
-struct PixelCoord {
-  int b, y, x;
+struct TileCtx {
+  int b, y, x;      // this thread's pixel
   bool valid;
+  int x0, y0, n0;   // tile origin
+  int n_tile;
+  int half, q;
+  uint32_t stg;     // this half's staging buffer (shared-space address), 0 when not allocated
+  uint32_t tmem_empty_bar;
 };
 
-__device__ __forceinline__ void epilogue(const GemmArgs& g, const PlainEpi& e, uint32_t taddr, PixelCoord pc,
-                                         int n_tile) {
-  const long long pix = ((long long)pc.b * g.H + pc.y) * g.W + pc.x;
-  for (int c0 = 0; c0 < g.BN; c0 += 16) {
-    const int col0 = n_tile * g.BN + c0;
-    if (col0 >= g.n) break;  // warp-uniform
-    float v[16];
-    tmem_ld16(taddr + c0, v);
+__device__ __forceinline__ void release_accumulator(const TileCtx& t) {
+  tc_fence_before();
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) mbar_arrive(t.tmem_empty_bar);
+}
+
+__device__ __forceinline__ void epilogue(const GemmArgs& g, const PlainEpi& e, const CUtensorMap* tmO,
+                                         uint32_t taddr, const float* ss, const TileCtx& t) {
+  const int lane = threadIdx.x & 31;
+  if (e.tma_store) {
+    // ---- bf16 NHWC through swizzled shared memory + TMA store (the TMA unit clips out-of-range pixels/channels)
+    const int nblk = (g.BN + 63) >> 6;
+    const int r = t.q * 32 + lane;
+    const bool issuer = t.q == 0 && lane == 0;
+    const int last_blk = ((nblk - 1 - t.half) & ~1) + t.half;  // last block this half owns (may be < half: none)
+    bool released = false;
+    for (int blk = t.half; blk < nblk; blk += 2) {
+      const int cols = min(64, g.BN - blk * 64);
+      uint32_t pk[32];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      int col = col0 + j;
-      if (col < g.n) {
-        float s = e.scale ? __ldg(e.scale + col) : 1.0f;
-        float t = e.shift ? __ldg(e.shift + col) : 0.0f;
-        v[j] = apply_act(fmaf(v[j], s, t), e.act_fn);
+      for (int c = 0; c < 64; c += 16) {
+        if (c < cols) {  // warp-uniform
+          uint32_t v[16];
+          tmem_ld16_nowait(taddr + blk * 64 + c, v);
+          tmem_wait_ld();
+          const float4* sc = reinterpret_cast<const float4*>(ss + blk * 64 + c);
+          const float4* sh = reinterpret_cast<const float4*>(ss + g.BN + blk * 64 + c);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float4 s4 = sc[k], h4 = sh[k];
+            float a0 = apply_act(fmaf(__uint_as_float(v[4 * k + 0]), s4.x, h4.x), e.act_fn);
+            float a1 = apply_act(fmaf(__uint_as_float(v[4 * k + 1]), s4.y, h4.y), e.act_fn);
+            float a2 = apply_act(fmaf(__uint_as_float(v[4 * k + 2]), s4.z, h4.z), e.act_fn);
+            float a3 = apply_act(fmaf(__uint_as_float(v[4 * k + 3]), s4.w, h4.w), e.act_fn);
+            pk[(c >> 1) + 2 * k] = pack_bf16(a0, a1);
+            pk[(c >> 1) + 2 * k + 1] = pack_bf16(a2, a3);
+          }
+        }
+      }
+      if (blk == last_blk) { release_accumulator(t); released = true; }
+      if (issuer) bulk_wait_read0();   // the previous TMA store has finished reading this staging buffer
+      named_bar(1 + t.half, 128);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (8 * j < cols) {
+          const uint32_t dst = t.stg + r * 128 + ((j ^ (r & 7)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk[4 * j]), "r"(pk[4 * j + 1]),
+                       "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3])
+                       : "memory");
+        }
+      }
+      fence_async_smem();
+      named_bar(1 + t.half, 128);
+      if (issuer) {
+        tma_store_4d(tmO, t.stg, t.n_tile * g.BN + blk * 64, t.x0, t.y0, t.n0);
+        bulk_commit();
       }
     }
-    if (!pc.valid) continue;
+    if (!released) release_accumulator(t);
+    return;
+  }
+  // ---- direct stores: f32 NCHW (coalesced over the pixels of a warp) or unaligned bf16 NHWC
+  const long long pix = ((long long)t.b * g.H + t.y) * g.W + t.x;
+  const long long plane = (long long)g.H * g.W;
+  for (int c0 = 16 * t.half; c0 < g.BN; c0 += 32) {
+    const int col0 = t.n_tile * g.BN + c0;
+    if (col0 >= g.n) break;  // warp-uniform
+    uint32_t r[16];
+    tmem_ld16_nowait(taddr + c0, r);
+    tmem_wait_ld();
+    float v[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = apply_act(fmaf(__uint_as_float(r[j]), ss[c0 + j], ss[g.BN + c0 + j]), e.act_fn);
+    if (!t.valid) continue;
     if (e.out_kind == RFK_OUT_NHWC_BF16) {
       __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(e.out) + pix * e.out_ld + e.out_off + col0;
 #pragma unroll
       for (int h8 = 0; h8 < 2; ++h8) {
         if (e.vec_ok && col0 + 8 * h8 + 8 <= g.n) {
-          __nv_bfloat162 pk[4];
-#pragma unroll
-          for (int k = 0; k < 4; ++k) pk[k] = __floats2bfloat162_rn(v[8 * h8 + 2 * k], v[8 * h8 + 2 * k + 1]);
-          *reinterpret_cast<uint4*>(dst + 8 * h8) = *reinterpret_cast<uint4*>(pk);
+          uint4 u = make_uint4(pack_bf16(v[8 * h8], v[8 * h8 + 1]), pack_bf16(v[8 * h8 + 2], v[8 * h8 + 3]),
+                               pack_bf16(v[8 * h8 + 4], v[8 * h8 + 5]), pack_bf16(v[8 * h8 + 6], v[8 * h8 + 7]));
+          *reinterpret_cast<uint4*>(dst + 8 * h8) = u;
         } else {
 #pragma unroll
           for (int k = 0; k < 8; ++k)
@@ -221,34 +319,34 @@ __device__ __forceinline__ void epilogue(const GemmArgs& g, const PlainEpi& e, u
         }
       }
     } else {
-      float* dst = reinterpret_cast<float*>(e.out) + (((long long)pc.b * g.n + col0) * g.H + pc.y) * g.W + pc.x;
-      const long long plane = (long long)g.H * g.W;
+      float* dst = reinterpret_cast<float*>(e.out) + (((long long)t.b * g.n + col0) * g.H + t.y) * g.W + t.x;
 #pragma unroll
       for (int j = 0; j < 16; ++j)
         if (col0 + j < g.n) dst[j * plane] = v[j];
     }
   }
+  release_accumulator(t);
 }
 
-__device__ __forceinline__ void epilogue(const GemmArgs& g, const CouplingEpi& e, uint32_t taddr, PixelCoord pc,
-                                         int /*n_tile*/) {
-  const int half = g.n >> 1;
+__device__ __forceinline__ void epilogue(const GemmArgs& g, const CouplingEpi& e, const CUtensorMap*, uint32_t taddr,
+                                         const float* ss, const TileCtx& t) {
+  const int half_c = g.n >> 1;
   const long long plane = (long long)g.H * g.W;
-  float* zp = e.z + (((long long)pc.b * g.n + half) * g.H + pc.y) * g.W + pc.x;
+  float* zp = e.z + (((long long)t.b * g.n + half_c) * g.H + t.y) * g.W + t.x;
   float acc = 0.0f;
-  for (int c0 = 0; c0 < g.BN; c0 += 16) {
+  for (int c0 = 16 * t.half; c0 < g.BN; c0 += 32) {
     if (c0 >= g.n) break;
-    float v[16];
-    tmem_ld16(taddr + c0, v);
-    if (pc.valid) {
+    uint32_t r[16];
+    tmem_ld16_nowait(taddr + c0, r);
+    tmem_wait_ld();
+    if (t.valid) {
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         const int j = (c0 >> 1) + k;
-        if (j < half) {
-          const int cs_ = 2 * j, cr_ = 2 * j + 1;
-          float sh = fmaf(v[2 * k], e.scale ? __ldg(e.scale + cs_) : 1.0f, e.shift ? __ldg(e.shift + cs_) : 0.0f);
-          float raw = fmaf(v[2 * k + 1], e.scale ? __ldg(e.scale + cr_) : 1.0f,
-                           e.shift ? __ldg(e.shift + cr_) : 0.0f);
+        if (j < half_c) {
+          const int cs_ = c0 + 2 * k, cr_ = cs_ + 1;
+          float sh = fmaf(__uint_as_float(r[2 * k]), ss[cs_], ss[g.BN + cs_]);
+          float raw = fmaf(__uint_as_float(r[2 * k + 1]), ss[cr_], ss[g.BN + cr_]);
           float a = 0.0f, bsh = 0.0f;
           if (e.clamp_type == RFK_CLAMP_REALNVP) { a = __ldg(e.cs + j); bsh = __ldg(e.csh + j); }
           float ls = clamp_ls(raw, e.clamp_type, a, bsh);
@@ -259,22 +357,24 @@ __device__ __forceinline__ void epilogue(const GemmArgs& g, const CouplingEpi& e
       }
     }
   }
+  release_accumulator(t);
   if (e.logdet) {
     // rows of one image are contiguous in the tile: reduce inside aligned lane groups of min(32, TW*TH)
     const int ppi_log2 = g.tw_log2 + g.th_log2;
     const int seg = ppi_log2 >= 5 ? 32 : (1 << ppi_log2);
     for (int o = seg >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     const int lane = threadIdx.x & 31;
-    if ((lane & (seg - 1)) == 0 && pc.b < g.B) atomicAdd(e.logdet + pc.b, e.reverse ? -acc : acc);
+    if ((lane & (seg - 1)) == 0 && t.b < g.B) atomicAdd(e.logdet + t.b, e.reverse ? -acc : acc);
   }
 }
 
-__device__ __forceinline__ void epilogue(const GemmArgs& g, const LstmEpi& e, uint32_t taddr, PixelCoord pc,
-                                         int n_tile) {
+__device__ __forceinline__ void epilogue(const GemmArgs& g, const LstmEpi& e, const CUtensorMap*, uint32_t taddr,
+                                         const float* ss, const TileCtx& t) {
   const long long plane = (long long)g.H * g.W;
-  const long long pofs = (long long)pc.y * g.W + pc.x;
-  const long long pix = ((long long)pc.b * g.H + pc.y) * g.W + pc.x;
-  for (int j0 = 0; j0 < e.ht_pad; j0 += 8) {
+  const long long pofs = (long long)t.y * g.W + t.x;
+  const long long pix = ((long long)t.b * g.H + t.y) * g.W + t.x;
+  const float* bias = ss + g.BN;  // the staged `shift` vector is the (row-permuted) conv bias
+  for (int j0 = 8 * t.half; j0 < e.ht_pad; j0 += 16) {
     if (j0 >= e.ht) break;  // warp-uniform
     uint32_t ri[8], rf[8], ro[8], rg[8];
     tmem_ld8_nowait(taddr + 0 * e.ht_pad + j0, ri);
@@ -282,21 +382,17 @@ __device__ __forceinline__ void epilogue(const GemmArgs& g, const LstmEpi& e, ui
     tmem_ld8_nowait(taddr + 2 * e.ht_pad + j0, ro);
     tmem_ld8_nowait(taddr + 3 * e.ht_pad + j0, rg);
     tmem_wait_ld();
-    if (!pc.valid) continue;
-    const float* bb = e.bias ? e.bias + (long long)n_tile * g.BN + j0 : nullptr;
+    if (!t.valid) continue;
     float hv[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       hv[k] = 0.0f;
       if (j0 + k < e.ht) {
-        const int ch = n_tile * e.ht + j0 + k;
-        float bi = 0, bf = 0, bo = 0, bg = 0;
-        if (bb) {
-          bi = __ldg(bb + k); bf = __ldg(bb + e.ht_pad + k); bo = __ldg(bb + 2 * e.ht_pad + k);
-          bg = __ldg(bb + 3 * e.ht_pad + k);
-        }
+        const int ch = t.n_tile * e.ht + j0 + k;
+        const float bi = bias[j0 + k], bf = bias[e.ht_pad + j0 + k], bo = bias[2 * e.ht_pad + j0 + k],
+                    bg = bias[3 * e.ht_pad + j0 + k];
         const long long co = ch * plane + pofs;
-        float c = e.c_prev ? e.c_prev[pc.b * e.c_prev_bs + co] : 0.0f;
+        float c = e.c_prev ? e.c_prev[t.b * e.c_prev_bs + co] : 0.0f;
         float wi = 0, wf = 0, wo = 0;
         if (e.peep) {
           const long long hp = (long long)e.hidden * plane;
@@ -308,18 +404,16 @@ __device__ __forceinline__ void epilogue(const GemmArgs& g, const LstmEpi& e, ui
         float cn = fg * c + ig * gg;
         float og = sigmoidf_(__uint_as_float(ro[k]) + bo + wo * cn);
         float h = og * tanhf(cn);
-        e.c_next[pc.b * e.c_next_bs + co] = cn;
-        e.h_out[pc.b * e.h_bs + co] = h;
+        e.c_next[t.b * e.c_next_bs + co] = cn;
+        e.h_out[t.b * e.h_bs + co] = h;
         hv[k] = h;
       }
     }
     if (e.h_nhwc) {
-      __nv_bfloat16* dst = e.h_nhwc + pix * e.h_ld + e.h_off + n_tile * e.ht + j0;
+      __nv_bfloat16* dst = e.h_nhwc + pix * e.h_ld + e.h_off + t.n_tile * e.ht + j0;
       if (e.h_vec_ok && j0 + 8 <= e.ht) {
-        __nv_bfloat162 pk[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) pk[k] = __floats2bfloat162_rn(hv[2 * k], hv[2 * k + 1]);
-        *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<uint4*>(pk);
+        *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16(hv[0], hv[1]), pack_bf16(hv[2], hv[3]),
+                                                    pack_bf16(hv[4], hv[5]), pack_bf16(hv[6], hv[7]));
       } else {
 #pragma unroll
         for (int k = 0; k < 8; ++k)
@@ -327,77 +421,112 @@ __device__ __forceinline__ void epilogue(const GemmArgs& g, const LstmEpi& e, ui
       }
     }
   }
+  release_accumulator(t);
 }
 
 // ------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------
 template <class Epi>
-__global__ void __launch_bounds__(kGemmThreads, 2)
+__global__ void __launch_bounds__(kGemmThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const GemmArgs g, const Epi ep) {
+                 const __grid_constant__ CUtensorMap tmO, const GemmArgs g, const Epi ep) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024 B alignment
   uint8_t* smem = smem_raw + (base - raw_addr);
 
-  const uint32_t b_stage_bytes = (uint32_t)g.BN * BK * 2;
-  const uint32_t stage_bytes = A_STAGE_BYTES + b_stage_bytes;
-  const uint32_t bar_base = base + g.stages * stage_bytes;  // full[s], empty[s], tmem_full, then the TMEM slot
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + g.stages * stage_bytes + 8 * (2 * g.stages + 1));
+  // shared-memory map (all tile regions are multiples of 1024 B)
+  const int k_iters = g.taps * g.kchunks;
+  const uint32_t b_chunk_bytes = (uint32_t)g.BN * BK * 2;
+  const uint32_t b_res_bytes = g.b_resident ? (uint32_t)k_iters * b_chunk_bytes : 0u;
+  const uint32_t stage_bytes = A_STAGE_BYTES + (g.b_resident ? 0u : b_chunk_bytes);
+  const uint32_t stage_base = base + b_res_bytes;
+  const uint32_t stg_base = stage_base + g.stages * stage_bytes;
+  const uint32_t ss_off = b_res_bytes + g.stages * stage_bytes + (g.use_stg ? 2u * STG_BYTES : 0u);
+  float* ss = reinterpret_cast<float*>(smem + ss_off);
+  const uint32_t bar_off = ss_off + 2u * g.BN * 4u;
+  const uint32_t bar_base = base + bar_off;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (g.stages + s); };
-  const uint32_t tmem_full_bar = bar_base + 8u * (2 * g.stages);
+  auto tmem_full_bar = [&](int b) { return bar_base + 8u * (2 * g.stages + b); };
+  auto tmem_empty_bar = [&](int b) { return bar_base + 8u * (2 * g.stages + 2 + b); };
+  const uint32_t b_full_bar = bar_base + 8u * (2 * g.stages + 4);
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + bar_off + 8u * (2 * g.stages + 5));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tile = blockIdx.y;
+  if (threadIdx.x == 0) RFK_STAMP(0);  // CTA start
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmO);
     for (int s = 0; s < g.stages; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tmem_full_bar(b), 1);
+      mbar_init(tmem_empty_bar(b), kEpiWarps);
+    }
+    mbar_init(b_full_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {
+  if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)),
                  "r"((uint32_t)g.tmem_cols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  // per-channel scale / shift of this CTA's output-channel slice -> shared memory
+  for (int i = threadIdx.x; i < g.BN; i += blockDim.x) {
+    const int col = n_tile * g.BN + i;
+    ss[i] = (g.scale && col < g.n_ss) ? g.scale[col] : 1.0f;
+    ss[g.BN + i] = (g.shift && col < g.n_ss) ? g.shift[col] : 0.0f;
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) RFK_STAMP(1);  // setup done
 
-  // tile -> pixel origin
   const int nimg_log2 = 7 - g.tw_log2 - g.th_log2;
-  int mt = blockIdx.x;
-  const int tx = mt % g.tiles_x;
-  mt /= g.tiles_x;
-  const int ty = mt % g.tiles_y;
-  const int tn = mt / g.tiles_y;
-  const int x0 = tx << g.tw_log2, y0 = ty << g.th_log2, n0 = tn << nimg_log2;
-  const int n_tile = blockIdx.y;
-  const int k_iters = g.taps * g.kchunks;
+  auto tile_origin = [&](int mt, int& x0, int& y0, int& n0) {
+    const int tx = mt % g.tiles_x;
+    mt /= g.tiles_x;
+    const int ty = mt % g.tiles_y;
+    const int tn = mt / g.tiles_y;
+    x0 = tx << g.tw_log2;
+    y0 = ty << g.th_log2;
+    n0 = tn << nimg_log2;
+  };
 
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
-      for (int it = 0; it < k_iters; ++it) {
-        const int s = it % g.stages;
-        const uint32_t ph = (uint32_t)(it / g.stages) & 1u;
-        mbar_wait(empty_bar(s), ph ^ 1u);
-        const int tap = it / g.kchunks, kc = it - tap * g.kchunks;
-        const int dy = g.taps == 9 ? tap / 3 - 1 : 0;
-        const int dx = g.taps == 9 ? tap % 3 - 1 : 0;
-        const uint32_t a_dst = base + s * stage_bytes;
-        mbar_expect_tx(full_bar(s), stage_bytes);
-        tma_load_4d(a_dst, &tmA, full_bar(s), kc * BK, x0 + dx, y0 + dy, n0);
-        tma_load_2d(a_dst + A_STAGE_BYTES, &tmB, full_bar(s), it * BK, n_tile * g.BN);
+      if (g.b_resident) {
+        mbar_expect_tx(b_full_bar, b_res_bytes);
+        for (int it = 0; it < k_iters; ++it) tma_load_2d(base + it * b_chunk_bytes, &tmB, b_full_bar, it * BK, n_tile * g.BN);
       }
+      uint32_t itg = 0;
+      for (int mt = blockIdx.x; mt < g.m_tiles; mt += gridDim.x) {
+        int x0, y0, n0;
+        tile_origin(mt, x0, y0, n0);
+        for (int it = 0; it < k_iters; ++it, ++itg) {
+          const int s = itg % g.stages;
+          const uint32_t ph = (itg / g.stages) & 1u;
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          const int tap = it / g.kchunks, kc = it - tap * g.kchunks;
+          const int dy = g.taps == 9 ? tap / 3 - 1 : 0;
+          const int dx = g.taps == 9 ? tap % 3 - 1 : 0;
+          const uint32_t a_dst = stage_base + s * stage_bytes;
+          mbar_expect_tx(full_bar(s), stage_bytes);
+          tma_load_4d(a_dst, &tmA, full_bar(s), kc * BK, x0 + dx, y0 + dy, n0);
+          if (!g.b_resident) tma_load_2d(a_dst + A_STAGE_BYTES, &tmB, full_bar(s), it * BK, n_tile * g.BN);
+        }
+      }
+      RFK_STAMP(3);  // all loads issued
     }
     __syncwarp();
   } else if (warp == 1) {
@@ -405,42 +534,67 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) {
       // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at bit 17, M>>4 at bit 24
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(g.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-      for (int it = 0; it < k_iters; ++it) {
-        const int s = it % g.stages;
-        const uint32_t ph = (uint32_t)(it / g.stages) & 1u;
-        mbar_wait(full_bar(s), ph);
-        tc_fence_after();
-        const uint32_t a_addr = base + s * stage_bytes;
-        const uint64_t adesc = umma_desc_sw128(a_addr);
-        const uint64_t bdesc = umma_desc_sw128(a_addr + A_STAGE_BYTES);
-#pragma unroll
-        for (int k = 0; k < BK / UMMA_K; ++k) {
-          // advance 32 B (16 bf16) along K inside the 128 B swizzle row: +2 in 16-byte units
-          umma_bf16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (it | k) != 0);
-        }
-        umma_commit(empty_bar(s));  // frees the smem stage once these MMAs have read it
+      if (g.b_resident) {
+        mbar_wait(b_full_bar, 0);
+        RFK_STAMP(2);  // weights resident
       }
-      umma_commit(tmem_full_bar);   // accumulator complete
+      uint32_t itg = 0, tl = 0;
+      for (int mt = blockIdx.x; mt < g.m_tiles; mt += gridDim.x, ++tl) {
+        const uint32_t buf = tl & 1u;
+        mbar_wait(tmem_empty_bar(buf), ((tl >> 1) & 1u) ^ 1u);  // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * g.BN;
+        for (int it = 0; it < k_iters; ++it, ++itg) {
+          const int s = itg % g.stages;
+          const uint32_t ph = (itg / g.stages) & 1u;
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          const uint32_t a_addr = stage_base + s * stage_bytes;
+          const uint64_t adesc = umma_desc_sw128(a_addr);
+          const uint64_t bdesc = umma_desc_sw128(g.b_resident ? base + it * b_chunk_bytes : a_addr + A_STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // advance 32 B (16 bf16) along K inside the 128 B swizzle row: +2 in 16-byte units
+            umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (it | k) != 0);
+          }
+          umma_commit(empty_bar(s));  // frees the smem stage once these MMAs have read it
+        }
+        umma_commit(tmem_full_bar(buf));  // accumulator complete
+      }
+      RFK_STAMP(4);  // all MMAs issued
     }
     __syncwarp();
-  } else {
+  } else if (warp >= kEpiWarp0) {
     // ===== epilogue: warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32) =====
-    const int q = warp & 3;
-    const int row = q * 32 + lane;
+    TileCtx t;
+    t.q = warp & 3;
+    t.half = (warp - kEpiWarp0) >> 2;
+    t.n_tile = n_tile;
+    t.stg = g.use_stg ? stg_base + t.half * STG_BYTES : 0u;
+    const int row = t.q * 32 + lane;
     const int ppi_log2 = g.tw_log2 + g.th_log2;
-    PixelCoord pc;
-    pc.b = n0 + (row >> ppi_log2);
-    pc.y = y0 + ((row >> g.tw_log2) & ((1 << g.th_log2) - 1));
-    pc.x = x0 + (row & ((1 << g.tw_log2) - 1));
-    pc.valid = pc.b < g.B && pc.y < g.H && pc.x < g.W;
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-    epilogue(g, ep, tmem_base + ((uint32_t)(q * 32) << 16), pc, n_tile);
+    uint32_t tl = 0;
+    for (int mt = blockIdx.x; mt < g.m_tiles; mt += gridDim.x, ++tl) {
+      const uint32_t buf = tl & 1u;
+      tile_origin(mt, t.x0, t.y0, t.n0);
+      t.b = t.n0 + (row >> ppi_log2);
+      t.y = t.y0 + ((row >> g.tw_log2) & ((1 << g.th_log2) - 1));
+      t.x = t.x0 + (row & ((1 << g.tw_log2) - 1));
+      t.valid = t.b < g.B && t.y < g.H && t.x < g.W;
+      t.tmem_empty_bar = tmem_empty_bar(buf);
+      mbar_wait(tmem_full_bar(buf), (tl >> 1) & 1u);
+      if (tl == 0 && warp == kEpiWarp0 && lane == 0) RFK_STAMP(5);  // first accumulator ready
+      tc_fence_after();
+      epilogue(g, ep, &tmO, tmem_base + ((uint32_t)(t.q * 32) << 16) + buf * g.BN, ss, t);
+      if (tl == 0 && warp == kEpiWarp0 && lane == 0) RFK_STAMP(6);  // first epilogue done
+    }
+    if (g.use_stg && t.q == 0 && lane == 0) bulk_wait0();  // outstanding TMA stores read shared memory
+    if (warp == kEpiWarp0 && lane == 0) RFK_STAMP(7);      // all epilogues done
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == 2) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)g.tmem_cols)
                  : "memory");
   }
@@ -471,15 +625,43 @@ static int ilog2_ceil(int v) {
   return l;
 }
 
+static unsigned long long* g_timeline = nullptr;
+static long long g_timeline_cap = 0;
+
 struct Plan {
   GemmArgs g;
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmO;
   dim3 grid;
   size_t smem;
+  int TW, TH, NIMG;
 };
 
+static int encode_act_map(CUtensorMap* map, const char* who, const char* what, const void* ptr, int channels, int ld,
+                          int B, int H, int W, int TW, int TH, int NIMG) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) {
+    set_error("%s: cuTensorMapEncodeTiled is unavailable (no CUDA driver?)", who);
+    return RFK_ECUDA;
+  }
+  // NHWC bf16 viewed as 4-D {C, W, H, B}; box {64, TW, TH, NIMG}; loads: OOB -> zeros (the conv padding); stores: clipped
+  cuuint64_t dims[4] = {(cuuint64_t)channels, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)W * ld * 2, (cuuint64_t)H * W * ld * 2};
+  cuuint32_t box[4] = {BK, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)NIMG};
+  cuuint32_t ones[4] = {1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, ones,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("%s: cuTensorMapEncodeTiled(%s) failed with CUresult %d (B=%d H=%d W=%d ld=%d channels=%d)", who, what, (int)r,
+              B, H, W, ld, channels);
+    return RFK_ECUDA;
+  }
+  return RFK_OK;
+}
+
+// stg_wanted: the epilogue can use TMA stores (needs 2 x 16 KB of staging shared memory)
 static int make_plan(Plan& p, const char* who, const void* act, int B, int H, int W, int act_ld, int cin_pad,
-                     const void* wgt, int n, int n_pad, int taps, int BN) {
+                     const void* wgt, int n, int n_pad, int taps, int BN, bool stg_wanted) {
   RFK_REQUIRE(act && wgt && B > 0 && H > 0 && W > 0, "%s: null pointer or empty shape", who);
   RFK_REQUIRE(cin_pad > 0 && cin_pad % BK == 0 && cin_pad <= act_ld, "%s: cin_pad=%d must be a multiple of %d and <= act_ld=%d",
               who, cin_pad, BK, act_ld);
@@ -501,44 +683,65 @@ static int make_plan(Plan& p, const char* who, const void* act, int B, int H, in
   int thl = ilog2_ceil(H);
   if (thl > 7 - twl) thl = 7 - twl;
   g.tw_log2 = twl; g.th_log2 = thl;
-  const int TW = 1 << twl, TH = 1 << thl, NIMG = BM / (TW * TH);
-  g.tiles_x = ceil_div(W, TW);
-  g.tiles_y = ceil_div(H, TH);
-  const int tiles_n = ceil_div(B, NIMG);
-  const int stage_bytes = A_STAGE_BYTES + BN * BK * 2;
-  int stages = (112 * 1024 - 1024 - 256) / stage_bytes;  // two CTAs per SM
-  if (const char* s = getenv("RFK_GEMM_STAGES")) stages = atoi(s);
-  if (stages > 8) stages = 8;
-  if (stages > taps * g.kchunks) stages = taps * g.kchunks;
-  if (stages < 1) stages = 1;
-  g.stages = stages;
-  int cols = 32;
-  while (cols < BN) cols <<= 1;
-  g.tmem_cols = cols;
-  p.smem = (size_t)stages * stage_bytes + 1024 + 8 * (2 * stages + 1) + 16;
-  p.grid = dim3((unsigned)(g.tiles_x * g.tiles_y * tiles_n), (unsigned)(n_pad / BN));
+  p.TW = 1 << twl; p.TH = 1 << thl; p.NIMG = BM / (p.TW * p.TH);
+  g.tiles_x = ceil_div(W, p.TW);
+  g.tiles_y = ceil_div(H, p.TH);
+  g.m_tiles = g.tiles_x * g.tiles_y * ceil_div(B, p.NIMG);
+  const int n_tiles = n_pad / BN;
+  const int k_iters = taps * g.kchunks;
 
-  // A: NHWC bf16 viewed as 4-D {C, W, H, B}; box {64, TW, TH, NIMG}; OOB -> zeros (the conv padding)
-  cuuint64_t dimsA[4] = {(cuuint64_t)cin_pad, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-  cuuint64_t strA[3] = {(cuuint64_t)act_ld * 2, (cuuint64_t)W * act_ld * 2, (cuuint64_t)H * W * act_ld * 2};
-  cuuint32_t boxA[4] = {BK, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)NIMG};
-  cuuint32_t ones[4] = {1, 1, 1, 1};
-  CUresult r = enc(&p.tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(act), dimsA, strA, boxA, ones,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    set_error("%s: cuTensorMapEncodeTiled(A) failed with CUresult %d (B=%d H=%d W=%d ld=%d cin_pad=%d)", who, (int)r, B, H, W,
-              act_ld, cin_pad);
-    return RFK_ECUDA;
+  // shared-memory budget: [resident weights] [stages] [2 staging blocks] [scale/shift] [barriers]
+  const int b_chunk = BN * BK * 2;
+  const int fixed = 1024 /*alignment slack*/ + (stg_wanted ? 2 * STG_BYTES : 0) + 2 * BN * 4 + 8 * (2 * 8 + 5) + 16;
+  g.use_stg = stg_wanted ? 1 : 0;
+  int resident = 0, stages = 0;
+  {
+    const long long res_bytes = (long long)k_iters * b_chunk;
+    const long long room = (long long)SMEM_LIMIT - fixed - res_bytes;
+    if (room >= 3LL * A_STAGE_BYTES) {
+      resident = 1;
+      stages = (int)(room / A_STAGE_BYTES);
+    } else {
+      stages = (SMEM_LIMIT - fixed) / (A_STAGE_BYTES + b_chunk);
+    }
   }
+  if (const char* s = getenv("RFK_GEMM_RESIDENT")) {
+    if (atoi(s) == 0 && resident) {
+      resident = 0;
+      stages = (SMEM_LIMIT - fixed) / (A_STAGE_BYTES + b_chunk);
+    }
+  }
+  if (const char* s = getenv("RFK_GEMM_STAGES")) stages = std::min(stages, std::max(1, atoi(s)));
+  if (stages > 8) stages = 8;
+  RFK_REQUIRE(stages >= 1, "%s: tile does not fit in shared memory (BN=%d)", who, BN);
+  g.stages = stages;
+  g.b_resident = resident;
+  int cols = 32;
+  while (cols < 2 * BN) cols <<= 1;
+  g.tmem_cols = cols;  // two accumulators
+  const int stage_bytes = A_STAGE_BYTES + (resident ? 0 : b_chunk);
+  p.smem = (size_t)1024 + (resident ? (size_t)k_iters * b_chunk : 0) + (size_t)stages * stage_bytes +
+           (stg_wanted ? 2 * STG_BYTES : 0) + 2 * BN * 4 + 8 * (2 * stages + 5) + 16;
+  RFK_REQUIRE(p.smem <= (size_t)SMEM_LIMIT, "%s: internal error: %zu B of shared memory planned", who, p.smem);
+  int ctas_x = sm_count() / n_tiles;
+  if (ctas_x < 1) ctas_x = 1;
+  if (ctas_x > g.m_tiles) ctas_x = g.m_tiles;
+  p.grid = dim3((unsigned)ctas_x, (unsigned)n_tiles);
+  g.timeline = (g_timeline && (long long)ctas_x * n_tiles <= g_timeline_cap) ? g_timeline : nullptr;
+  g.scale = nullptr; g.shift = nullptr; g.n_ss = 0;
+
+  int rc = encode_act_map(&p.tmA, who, "A", act, cin_pad, act_ld, B, H, W, p.TW, p.TH, p.NIMG);
+  if (rc) return rc;
+  p.tmO = p.tmA;  // placeholder unless the epilogue stores through TMA
   // B: weights [n_pad, taps*cin_pad] viewed as 2-D {K, N}; box {64, BN}
   const cuuint64_t ktot = (cuuint64_t)taps * cin_pad;
   cuuint64_t dimsB[2] = {ktot, (cuuint64_t)n_pad};
   cuuint64_t strB[1] = {ktot * 2};
   cuuint32_t boxB[2] = {BK, (cuuint32_t)BN};
-  r = enc(&p.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(wgt), dimsB, strB, boxB, ones,
-          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  cuuint32_t ones[2] = {1, 1};
+  CUresult r = enc(&p.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(wgt), dimsB, strB, boxB, ones,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("%s: cuTensorMapEncodeTiled(B) failed with CUresult %d (n_pad=%d ktot=%llu BN=%d)", who, (int)r, n_pad,
               (unsigned long long)ktot, BN);
@@ -558,19 +761,40 @@ static int launch(const Plan& p, const Epi& ep, cudaStream_t st, const char* who
     }
     configured = p.smem;
   }
-  conv_gemm_kernel<Epi><<<p.grid, kGemmThreads, p.smem, st>>>(p.tmA, p.tmB, p.g, ep);
+  conv_gemm_kernel<Epi><<<p.grid, kGemmThreads, p.smem, st>>>(p.tmA, p.tmB, p.tmO, p.g, ep);
   return check_launch(who);
 }
 
-static int pick_bn(int n_pad) {
-  for (int bn = 256; bn >= 16; bn -= 16)
-    if (n_pad % bn == 0) return bn;
-  return 16;
+// N tile: the whole (padded) channel count when it fits one accumulator; otherwise the largest divisor that is a
+// multiple of `quantum`.  Small pixel counts get narrower tiles so that more SMs share the work.
+static int pick_bn(int n_pad, int quantum, int m_tiles_hint) {
+  int best = 0;
+  for (int bn = 256; bn >= quantum; bn -= quantum)
+    if (n_pad % bn == 0) { best = bn; break; }
+  if (!best) return 0;
+  const int sms = sm_count();
+  while (best % 2 == 0 && (best / 2) % quantum == 0 && best / 2 >= 64 && m_tiles_hint * (n_pad / best) * 2 <= sms) best /= 2;
+  return best;
+}
+
+static int m_tiles_of(int B, int H, int W) {
+  int twl = ilog2_ceil(W);
+  if (twl > 7) twl = 7;
+  int thl = ilog2_ceil(H);
+  if (thl > 7 - twl) thl = 7 - twl;
+  const int TW = 1 << twl, TH = 1 << thl;
+  return ceil_div(W, TW) * ceil_div(H, TH) * ceil_div(B, BM / (TW * TH));
 }
 
 }  // namespace rfk
 
 using namespace rfk;
+
+extern "C" int rfk_debug_set_timeline(unsigned long long* buf, long long capacity_ctas) {
+  g_timeline = buf;
+  g_timeline_cap = buf ? capacity_ctas : 0;
+  return RFK_OK;
+}
 
 extern "C" int rfk_conv_gemm(const void* act, int B, int H, int W, int act_ld, int cin_pad, const void* wgt, int n,
                              int n_pad, int taps, const float* scale, const float* shift, int act_fn, int out_kind,
@@ -578,16 +802,34 @@ extern "C" int rfk_conv_gemm(const void* act, int B, int H, int W, int act_ld, i
   RFK_REQUIRE(out, "rfk_conv_gemm: null output");
   RFK_REQUIRE(out_kind == RFK_OUT_NHWC_BF16 || out_kind == RFK_OUT_NCHW_F32, "rfk_conv_gemm: bad out_kind %d", out_kind);
   RFK_REQUIRE(act_fn >= 0 && act_fn <= 2, "rfk_conv_gemm: bad act_fn %d", act_fn);
-  Plan p;
-  int rc = make_plan(p, "rfk_conv_gemm", act, B, H, W, act_ld, cin_pad, wgt, n, n_pad, taps, pick_bn(n_pad));
-  if (rc) return rc;
+  RFK_REQUIRE(n_pad > 0 && n_pad % 16 == 0, "rfk_conv_gemm: n_pad=%d must be a positive multiple of 16", n_pad);
   PlainEpi e;
-  e.scale = scale; e.shift = shift; e.act_fn = act_fn; e.out_kind = out_kind; e.out = out;
-  e.out_ld = out_ld; e.out_off = out_off; e.vec_ok = 0;
+  e.act_fn = act_fn; e.out_kind = out_kind; e.out = out; e.out_ld = out_ld; e.out_off = out_off; e.vec_ok = 0;
+  e.tma_store = 0;
+  bool tma_ok = false;
   if (out_kind == RFK_OUT_NHWC_BF16) {
     RFK_REQUIRE(out_off >= 0 && out_off + n <= out_ld, "rfk_conv_gemm: output window [%d,%d) exceeds out_ld=%d", out_off,
                 out_off + n, out_ld);
     e.vec_ok = out_ld % 8 == 0 && out_off % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+    tma_ok = e.vec_ok && getenv("RFK_GEMM_NO_TMA_STORE") == nullptr;
+  }
+  const int mth = m_tiles_of(B, H, W);
+  int BN = 0;
+  if (tma_ok) {
+    // TMA stores move 64-channel blocks: a tile that is not the only one must be a whole number of blocks
+    BN = (n_pad <= 256 && n_pad % 64 != 0) ? n_pad : pick_bn(n_pad, 64, mth);
+    if (!BN) tma_ok = false;
+  }
+  if (!BN) BN = pick_bn(n_pad, 16, mth);
+  Plan p;
+  int rc = make_plan(p, "rfk_conv_gemm", act, B, H, W, act_ld, cin_pad, wgt, n, n_pad, taps, BN, tma_ok);
+  if (rc) return rc;
+  p.g.scale = scale; p.g.shift = shift; p.g.n_ss = n;
+  if (tma_ok) {
+    e.tma_store = 1;
+    rc = encode_act_map(&p.tmO, "rfk_conv_gemm", "out", reinterpret_cast<const __nv_bfloat16*>(out) + out_off, n, out_ld, B, H,
+                        W, p.TW, p.TH, p.NIMG);
+    if (rc) return rc;
   }
   return launch(p, e, (cudaStream_t)stream, "rfk_conv_gemm");
 }
@@ -602,11 +844,11 @@ extern "C" int rfk_conv_gemm_coupling(const void* act, int B, int H, int W, int 
   RFK_REQUIRE(clamp_type != RFK_CLAMP_REALNVP || (clamp_scale && clamp_shift),
               "rfk_conv_gemm_coupling: realnvp clamp needs scale and scale_shift");
   Plan p;
-  int rc = make_plan(p, "rfk_conv_gemm_coupling", act, B, H, W, act_ld, cin_pad, wgt, n, n_pad, taps, n_pad);
+  int rc = make_plan(p, "rfk_conv_gemm_coupling", act, B, H, W, act_ld, cin_pad, wgt, n, n_pad, taps, n_pad, false);
   if (rc) return rc;
+  p.g.scale = scale; p.g.shift = shift; p.g.n_ss = n;
   CouplingEpi e;
-  e.scale = scale; e.shift = shift; e.z = z; e.clamp_type = clamp_type; e.cs = clamp_scale; e.csh = clamp_shift;
-  e.logdet = logdet; e.reverse = reverse;
+  e.z = z; e.clamp_type = clamp_type; e.cs = clamp_scale; e.csh = clamp_shift; e.logdet = logdet; e.reverse = reverse;
   return launch(p, e, (cudaStream_t)stream, "rfk_conv_gemm_coupling");
 }
 
@@ -620,10 +862,11 @@ extern "C" int rfk_conv_gemm_lstm(const void* act, int B, int H, int W, int act_
               "rfk_conv_gemm_lstm: bad hidden tiling hidden=%d ht=%d ht_pad=%d", hidden, ht, ht_pad);
   const int n_tiles = hidden / ht, BN = 4 * ht_pad, n_pad = n_tiles * BN;
   Plan p;
-  int rc = make_plan(p, "rfk_conv_gemm_lstm", act, B, H, W, act_ld, cin_pad, wgt, n_pad, n_pad, taps, BN);
+  int rc = make_plan(p, "rfk_conv_gemm_lstm", act, B, H, W, act_ld, cin_pad, wgt, n_pad, n_pad, taps, BN, false);
   if (rc) return rc;
+  p.g.scale = nullptr; p.g.shift = bias; p.g.n_ss = n_pad;
   LstmEpi e;
-  e.bias = bias; e.hidden = hidden; e.ht = ht; e.ht_pad = ht_pad; e.c_prev = c_prev; e.c_prev_bs = c_prev_bstride;
+  e.hidden = hidden; e.ht = ht; e.ht_pad = ht_pad; e.c_prev = c_prev; e.c_prev_bs = c_prev_bstride;
   e.peep = peep; e.c_next = c_next; e.c_next_bs = c_next_bstride; e.h_out = h_out; e.h_bs = h_bstride;
   e.h_nhwc = (__nv_bfloat16*)h_nhwc; e.h_off = h_off; e.h_ld = h_ld;
   e.h_vec_ok = h_nhwc && h_ld % 8 == 0 && h_off % 8 == 0 && ht % 8 == 0 && (reinterpret_cast<uintptr_t>(h_nhwc) & 15) == 0;

@@ -308,6 +308,53 @@ __global__ void __launch_bounds__(kThreads) coupling_tail_kernel(const float* __
   if (logdet) cta_atomic_add(reverse ? -acc : acc, logdet + b, sh);
 }
 
+// Coupling tail fed by a tap-split convolution: taps [B, 9*C, H, W] holds, for every filter tap t = 3*ky+kx,
+// the 1x1 product W[:, :, ky, kx] * h at each pixel, so the 3x3 'same' convolution output is
+//   nn[c](y, x) = sum_t taps[t*C + c](y + ky - 1, x + kx - 1)        (zero outside the image)
+// followed by Conv2dZeros' per-channel affine (scale, shift) and the affine-coupling update.
+// Every element of `taps` is read exactly once (coalesced, shifted by at most one pixel).  grid = (chunks, B)
+__global__ void __launch_bounds__(kThreads) coupling_taps_kernel(const float* __restrict__ taps, float* __restrict__ z,
+                                                                int C, int H, int W, const float* __restrict__ scale,
+                                                                const float* __restrict__ shift, int clamp_type,
+                                                                const float* __restrict__ cs,
+                                                                const float* __restrict__ csh,
+                                                                float* __restrict__ logdet, int reverse) {
+  __shared__ float sh[32];
+  const int b = blockIdx.y, half = C >> 1, HW = H * W;
+  const long long per = (long long)half * HW;
+  const float* tb = taps + (long long)b * 9 * C * HW;
+  float* zb = z + ((long long)b * C + half) * HW;
+  float acc = 0.0f;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < per;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(t / HW), p = (int)(t % HW);
+    const int y = p / W, x = p - y * W;
+    float s_sum = 0.0f, r_sum = 0.0f;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int yy = y + ky - 1;
+      if (yy < 0 || yy >= H) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int xx = x + kx - 1;
+        if (xx < 0 || xx >= W) continue;
+        const float* q = tb + ((long long)((3 * ky + kx) * C + 2 * j) * HW) + yy * W + xx;
+        s_sum += __ldg(q);
+        r_sum += __ldg(q + HW);
+      }
+    }
+    const float sft = fmaf(s_sum, __ldg(scale + 2 * j), __ldg(shift + 2 * j));
+    const float raw = fmaf(r_sum, __ldg(scale + 2 * j + 1), __ldg(shift + 2 * j + 1));
+    float a = 0.0f, bb = 0.0f;
+    if (clamp_type == RFK_CLAMP_REALNVP) { a = __ldg(cs + j); bb = __ldg(csh + j); }
+    const float ls = clamp_ls(raw, clamp_type, a, bb);
+    acc += ls;
+    const float v = zb[t];
+    zb[t] = reverse ? v * expf(-ls) - sft : (v + sft) * expf(ls);
+  }
+  if (logdet) cta_atomic_add(reverse ? -acc : acc, logdet + b, sh);
+}
+
 // ------------------------------------------------------------------------------------------
 // a5/a7  Gaussian log-density / sampling.  grid = (chunks, B)
 // ------------------------------------------------------------------------------------------
@@ -553,6 +600,23 @@ extern "C" int rfk_coupling_tail(const float* nn_out, float* z, int B, int C, in
     coupling_tail_kernel<false><<<grid, kThreads, 0, st>>>(nn_out, z, C, HW, clamp_type, clamp_scale, clamp_shift,
                                                            logdet, reverse);
   return check_launch("rfk_coupling_tail");
+}
+
+extern "C" int rfk_coupling_tail_taps(const float* taps, float* z, int B, int C, int H, int W, const float* scale,
+                                      const float* shift, int clamp_type, const float* clamp_scale,
+                                      const float* clamp_shift, float* logdet, int reverse, void* stream) {
+  RFK_REQUIRE(taps && z && scale && shift && B > 0 && C > 0 && C % 2 == 0 && H > 0 && W > 0,
+              "rfk_coupling_tail_taps: null pointer or bad shape (C must be even)");
+  RFK_REQUIRE(clamp_type >= 0 && clamp_type <= 3, "rfk_coupling_tail_taps: unknown clamp_type %d", clamp_type);
+  RFK_REQUIRE(clamp_type != RFK_CLAMP_REALNVP || (clamp_scale && clamp_shift),
+              "rfk_coupling_tail_taps: realnvp clamp needs scale and scale_shift");
+  long long per = (long long)(C / 2) * H * W;
+  int chunks = ceil_div(per, kThreads);
+  int cap = ceil_div((long long)sm_count() * 8, B);
+  if (chunks > cap) chunks = cap;
+  coupling_taps_kernel<<<dim3(chunks, B), kThreads, 0, (cudaStream_t)stream>>>(
+      taps, z, C, H, W, scale, shift, clamp_type, clamp_scale, clamp_shift, logdet, reverse);
+  return check_launch("rfk_coupling_tail_taps");
 }
 
 extern "C" int rfk_gauss_logp(const float* z, int z_C, int z_off, const float* params, int n, int B, int HW,

@@ -145,6 +145,14 @@ def coupling_tail(nn_out, z, clamp_type, clamp_scale, clamp_shift, logdet, rever
          _p(clamp_shift), _p(logdet), int(reverse), _stream())
 
 
+def coupling_tail_taps(taps, z, scale, shift, clamp_type, clamp_scale, clamp_shift, logdet, reverse):
+    _chk(taps, name="taps")
+    _chk(z, name="z")
+    B, C, H, W = z.shape
+    call("rfk_coupling_tail_taps", taps.data_ptr(), z.data_ptr(), B, C, H, W, _chk(scale).data_ptr(),
+         _chk(shift).data_ptr(), CLAMP[clamp_type], _p(clamp_scale), _p(clamp_shift), _p(logdet), int(reverse), _stream())
+
+
 def gauss_logp(z, z_off, params, n, pairing, std_kind, logdet):
     _chk(z, name="z")
     B, zC, H, W = z.shape
@@ -193,6 +201,13 @@ def clear_workspaces():
 # --------------------------------------------------------------------------------------
 # weight repacking (tiny host-driven torch ops on the device, cached by the callers)
 # --------------------------------------------------------------------------------------
+def pack_tap_split_weight(weight):
+    """[C, Cin, 3, 3] -> the 1x1 weight [pad16(9C), cin_pad] whose row t*C + c is W[c, :, ky, kx], t = 3*ky+kx."""
+    C, Cin, kh, kw = weight.shape
+    w = weight.detach().float().permute(2, 3, 0, 1).reshape(kh * kw * C, Cin, 1, 1)
+    return pack_conv_weight(w)
+
+
 def pack_conv_weight(weight, in_perm=None, row_perm=None, n_pad=None):
     """[N, Cin, kh, kw] f32 -> bf16 [n_pad, taps*cin_pad] with k = tap*cin_pad + c (tap = 3*ky + kx)."""
     w = weight.detach().float()

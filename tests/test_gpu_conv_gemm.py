@@ -126,3 +126,29 @@ def test_conv_gemm_lstm(ops, B, Cin, Hc, H, W):
     with torch.no_grad():
         h1, c1 = cell(x.cuda(), [None, None])
     assert max_rel(c1.cpu(), c_ref0) < 2e-3 and max_rel(h1.cpu(), h_ref0) < 2e-3
+
+
+@pytest.mark.parametrize("clamp", ["realnvp", "glow"])
+@pytest.mark.parametrize("B,C,H,W", [(3, 4, 32, 32), (2, 8, 16, 16), (5, 16, 8, 8), (2, 12, 6, 10), (3, 28, 3, 5)])
+def test_tap_split_coupling(ops, clamp, B, C, H, W):
+    """The tap-split form (1x1 GEMM with N=9C + shifted-plane gather) equals the 3x3 conv + coupling tail."""
+    g = torch.Generator().manual_seed(C + 100)
+    hid = 64
+    h2 = bf(torch.relu(torch.randn(B, hid, H, W, generator=g)))
+    w = bf(torch.randn(C, hid, 3, 3, generator=g) * 0.02)
+    scale, shift = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.1
+    cs, csh = torch.randn(C // 2, generator=g) * 0.5, torch.randn(C // 2, generator=g) * 0.1
+    z = torch.randn(B, C, H, W, generator=g)
+    nn_out = F.conv2d(h2, w, None, 1, 1) * scale.view(1, C, 1, 1) + shift.view(1, C, 1, 1)
+    ls = O.clamp_log_scale(nn_out[:, 1::2], clamp, cs, csh)
+    z_ref = torch.cat([z[:, :C // 2], (z[:, C // 2:] + nn_out[:, 0::2]) * torch.exp(ls)], 1)
+    w9, cin_pad = ops.pack_tap_split_weight(w.cuda())
+    taps = torch.empty(B, 9 * C, H, W, device="cuda")
+    ops.conv_gemm(staged(ops, h2), cin_pad, w9, 9 * C, 1, None, None, "none", taps)
+    zc, ld = z.cuda().clone(), torch.zeros(B, device="cuda")
+    ops.coupling_tail_taps(taps, zc, scale.cuda(), shift.cuda(), clamp, cs.cuda(), csh.cuda(), ld, False)
+    assert max_rel(zc.cpu(), z_ref) < 2e-3
+    torch.testing.assert_close(ld.cpu(), ls.sum(dim=(1, 2, 3)), rtol=2e-3, atol=2e-2)
+    ops.coupling_tail_taps(taps, zc, scale.cuda(), shift.cuda(), clamp, cs.cuda(), csh.cuda(), ld, True)
+    assert max_rel(zc.cpu(), z) < 1e-4
+    assert float(ld.abs().max()) < 1e-3
