@@ -83,9 +83,12 @@ int rfk_actnorm_init(const float* x, float* bias, float* logs, float* mean_out, 
  * y[b,o,p] = sum_i Wm[o,i] * x[b,i,p] + bvec[o]   (Wm [C,C] row-major f32, bvec nullable).
  * With Wm = W*diag(exp(logs)), bvec = Wm*bias this is ActNorm followed by InvConv in one pass.
  * Optional side output: channels [0,side_n) of y are also written as bf16 into an NHWC buffer
- * at channel offset side_off with row stride side_ld (the coupling network's z1 input). */
+ * at channel offset side_off with row stride side_ld (the coupling network's z1 input).
+ * Optional log-det fold: logdet[b] += alpha * (*addend) for b < B (addend = device scalar H*W*(sum logs + log|det W|),
+ * Flow/glow_modules.py:43,196), so a GlowStep needs no separate launch for its parameter-only log-det term. */
 int rfk_mix1x1(const float* x, float* y, const float* Wm, const float* bvec, int B, int C, int HW,
-               void* side_nhwc_bf16, int side_n, int side_off, int side_ld, void* stream);
+               void* side_nhwc_bf16, int side_n, int side_off, int side_ld,
+               float* logdet, const float* addend, float alpha, void* stream);
 
 /* ---- layout helpers -----------------------------------------------------------------------
  * pack: channels [c_lo, c_lo+n) of src NCHW f32 [B,Csrc,HW] (batch stride src_bstride elements,

@@ -58,6 +58,11 @@ class GlowStep(nn.Module):
             return Wf, bf, Wr, br, (per_pixel + logs.sum()).reshape(())
         return self._cache.get("fold", (self.norm.bias, self.norm.logs) + self.invconv._params(), build)
 
+    def _dlogdet(self, hw):
+        """H*W*(sum logs + log|det W|) as a cached device scalar (Flow/glow_modules.py:43,196)."""
+        return self._cache.get(("dl", hw), (self.norm.bias, self.norm.logs) + self.invconv._params(),
+                               lambda: (self._folded()[4] * hw).reshape(1).contiguous())
+
     def forward(self, x, condition, logdet, reverse, _ctx=None):
         _require_no_grad()
         x = ops.f32c(x)
@@ -72,23 +77,21 @@ class GlowStep(nn.Module):
         ld, extra = _ld_begin(logdet, B, x.device, inplace=not own_ctx)
         if not reverse:
             self.norm.maybe_initialize(x)
-            Wf, bf, _, _, per_pixel = self._folded()
-            y = ops.mix1x1(x, Wf, bf, side=_ctx.nn_in, side_n=C // 2, side_off=cc)
+            Wf, bf, _, _, _ = self._folded()
+            y = ops.mix1x1(x, Wf, bf, side=_ctx.nn_in, side_n=C // 2, side_off=cc,
+                           logdet=ld, addend=None if ld is None else self._dlogdet(H * W), alpha=1.0)
             _ctx.z1_packed = True
             y, ld = self.affine(y, condition, ld, False, _ctx=_ctx)
             _ctx.z1_packed = False
-            if ld is not None:
-                ld.add_(per_pixel * (H * W))
             return y, _ld_end(ld, extra)
         if own_ctx:
             x = x.clone()  # the coupling inverse below works in place
         y, ld = self.affine(x, condition, ld, True, _ctx=_ctx)
         self.norm.maybe_initialize(y)
-        _, _, Wr, br, per_pixel = self._folded()
-        out = ops.mix1x1(y, Wr, br, side=_ctx.nn_in, side_n=C // 2, side_off=cc)
+        _, _, Wr, br, _ = self._folded()
+        out = ops.mix1x1(y, Wr, br, side=_ctx.nn_in, side_n=C // 2, side_off=cc,
+                         logdet=ld, addend=None if ld is None else self._dlogdet(H * W), alpha=-1.0)
         _ctx.z1_packed = True   # the next reverse step of this level reads this z1
-        if ld is not None:
-            ld.sub_(per_pixel * (H * W))
         return out, _ld_end(ld, extra)
 
 

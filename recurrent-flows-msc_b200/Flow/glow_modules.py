@@ -310,8 +310,12 @@ class AffineCoupling(nn.Module):
 
     def _perm(self, device):
         # NHWC staging order is [condition | z1]; the reference's weight expects cat[z1, condition]
-        half, cc = self._half, self._cond
-        return torch.cat([torch.arange(half, half + cc, device=device), torch.arange(0, half, device=device)])
+        hit = self.__dict__.get("_perm_cache")
+        if hit is None or hit.device != device:
+            half, cc = self._half, self._cond
+            hit = torch.cat([torch.arange(half, half + cc, device=device), torch.arange(0, half, device=device)])
+            self.__dict__["_perm_cache"] = hit
+        return hit
 
     def forward(self, x, condition, logdet, reverse, _ctx=None):
         _require_no_grad()

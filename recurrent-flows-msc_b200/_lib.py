@@ -18,7 +18,7 @@ SIGNATURES = {
     "rfk_actnorm": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "rfk_actnorm_init": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
     "rfk_mix1x1": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
-                   c_void_p, c_int, c_int, c_int, c_void_p],
+                   c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p],
     "rfk_pack_nhwc_bf16": [c_void_p, c_longlong, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p],
     "rfk_copy_channels": [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "rfk_conv_gemm": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int,

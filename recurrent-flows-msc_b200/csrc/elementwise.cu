@@ -160,49 +160,57 @@ __global__ void __launch_bounds__(512) actnorm_init_kernel(const float* __restri
 // HBM-bound (AI = C/4 flop/B): one thread per pixel, x tile and Wm staged in shared memory,
 // 8 output channels register-blocked.  Optional bf16 NHWC side output of the first side_n channels.
 // ------------------------------------------------------------------------------------------
-constexpr int kMixPix = 128;  // pixels per CTA
-
-__global__ void __launch_bounds__(kMixPix) mix1x1_kernel(const float* __restrict__ x, float* __restrict__ y,
-                                                         const float* __restrict__ Wm,
-                                                         const float* __restrict__ bvec, int C, int HW,
-                                                         long long npix, __nv_bfloat16* __restrict__ side,
-                                                         int side_n, int side_off, int side_ld, int w_smem) {
+// CTA = PT pixels x G output groups: thread (tx, ty) computes outputs [8*ty, 8*ty+8) of pixel tx, reading the
+// x tile (staged once in shared memory, conflict-free) and Wm (shared memory broadcast).  Optionally also adds
+// alpha * (*addend) to logdet[0..B) -- the parameter-only log-det term of ActNorm + InvConv -- so that a GlowStep
+// needs no separate launch for it.
+__global__ void __launch_bounds__(1024) mix1x1_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                      const float* __restrict__ Wm, const float* __restrict__ bvec,
+                                                      int C, int HW, long long npix, __nv_bfloat16* __restrict__ side,
+                                                      int side_n, int side_off, int side_ld, int w_smem,
+                                                      float* __restrict__ logdet, const float* __restrict__ addend,
+                                                      float alpha, int B) {
   extern __shared__ float smem[];
+  const int PT = blockDim.x, G = blockDim.y;
+  const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * PT + tx, nthr = PT * G;
   float* bs = smem;                 // [C]
-  float* xs = bs + C;               // [C][kMixPix]
+  float* xs = bs + C;               // [C][PT]
   const float* ws = Wm;             // [C][C]: shared memory when it fits, else L1-cached broadcast loads
   if (w_smem) {
-    float* wsm = xs + C * kMixPix;
-    for (int i = threadIdx.x; i < C * C; i += blockDim.x) wsm[i] = Wm[i];
+    float* wsm = xs + C * PT;
+    for (int i = tid; i < C * C; i += nthr) wsm[i] = Wm[i];
     ws = wsm;
   }
-  for (int i = threadIdx.x; i < C; i += blockDim.x) bs[i] = bvec ? bvec[i] : 0.0f;
-  const long long pix = blockIdx.x * (long long)kMixPix + threadIdx.x;
+  for (int i = tid; i < C; i += nthr) bs[i] = bvec ? bvec[i] : 0.0f;
+  if (logdet && blockIdx.x == 0) {
+    const float add = alpha * (*addend);
+    for (int i = tid; i < B; i += nthr) logdet[i] += add;
+  }
+  const long long pix = blockIdx.x * (long long)PT + tx;
   const bool ok = pix < npix;
   const long long b = ok ? pix / HW : 0;
   const int p = ok ? (int)(pix % HW) : 0;
   const float* xp = x + b * C * HW + p;
-  for (int i = 0; i < C; ++i) xs[i * kMixPix + threadIdx.x] = ok ? xp[(long long)i * HW] : 0.0f;
+  for (int i = ty; i < C; i += G) xs[i * PT + tx] = ok ? xp[(long long)i * HW] : 0.0f;
   __syncthreads();
-  float* yp = y + b * C * HW + p;
-  for (int o0 = 0; o0 < C; o0 += 8) {
-    float acc[8];
+  const int o0 = ty * 8;
+  float acc[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = (o0 + j < C) ? bs[o0 + j] : 0.0f;
-    for (int i = 0; i < C; ++i) {
-      float xv = xs[i * kMixPix + threadIdx.x];
+  for (int j = 0; j < 8; ++j) acc[j] = (o0 + j < C) ? bs[o0 + j] : 0.0f;
+  for (int i = 0; i < C; ++i) {
+    const float xv = xs[i * PT + tx];
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (o0 + j < C) acc[j] = fmaf(ws[(o0 + j) * C + i], xv, acc[j]);
-    }
-    if (ok) {
+    for (int j = 0; j < 8; ++j)
+      if (o0 + j < C) acc[j] = fmaf(ws[(o0 + j) * C + i], xv, acc[j]);
+  }
+  if (ok) {
+    float* yp = y + b * C * HW + p;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        int o = o0 + j;
-        if (o < C) {
-          yp[(long long)o * HW] = acc[j];
-          if (side && o < side_n) side[pix * side_ld + side_off + o] = __float2bfloat16(acc[j]);
-        }
+    for (int j = 0; j < 8; ++j) {
+      const int o = o0 + j;
+      if (o < C) {
+        yp[(long long)o * HW] = acc[j];
+        if (side && o < side_n) side[pix * side_ld + side_off + o] = __float2bfloat16(acc[j]);
       }
     }
   }
@@ -211,27 +219,30 @@ __global__ void __launch_bounds__(kMixPix) mix1x1_kernel(const float* __restrict
 // ------------------------------------------------------------------------------------------
 // layout helpers
 // ------------------------------------------------------------------------------------------
-// NCHW f32 channel slice -> NHWC bf16 (thread per pixel: coalesced reads per channel, 16 B writes)
+// NCHW f32 channel slice -> NHWC bf16.  One thread per (pixel, group of 8 channels): consecutive threads take
+// consecutive pixels (coalesced reads of each channel plane), each writes one 16-byte group.
 __global__ void __launch_bounds__(kThreads) pack_nhwc_kernel(const float* __restrict__ src, long long src_bs,
                                                              int HW, int c_lo, int n, __nv_bfloat16* __restrict__ dst,
                                                              int dst_off, int dst_ld, long long npix, int vec_ok) {
-  for (long long pix = blockIdx.x * (long long)blockDim.x + threadIdx.x; pix < npix;
-       pix += (long long)gridDim.x * blockDim.x) {
-    long long b = pix / HW;
-    int p = (int)(pix % HW);
-    const float* sp = src + b * src_bs + (long long)c_lo * HW + p;
-    __nv_bfloat16* dp = dst + pix * dst_ld + dst_off;
-    int j = 0;
-    if (vec_ok) {
-      for (; j + 8 <= n; j += 8) {
-        __nv_bfloat162 h[4];
+  const int groups = (n + 7) >> 3;
+  const long long total = npix * groups;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const long long pix = t % npix;
+    const int j = (int)(t / npix) * 8;
+    const long long b = pix / HW;
+    const int p = (int)(pix % HW);
+    const float* sp = src + b * src_bs + (long long)(c_lo + j) * HW + p;
+    __nv_bfloat16* dp = dst + pix * dst_ld + dst_off + j;
+    if (vec_ok && j + 8 <= n) {
+      __nv_bfloat162 h[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          h[k] = __floats2bfloat162_rn(sp[(long long)(j + 2 * k) * HW], sp[(long long)(j + 2 * k + 1) * HW]);
-        *reinterpret_cast<uint4*>(dp + j) = *reinterpret_cast<uint4*>(h);
-      }
+      for (int k = 0; k < 4; ++k)
+        h[k] = __floats2bfloat162_rn(sp[(long long)(2 * k) * HW], sp[(long long)(2 * k + 1) * HW]);
+      *reinterpret_cast<uint4*>(dp) = *reinterpret_cast<uint4*>(h);
+    } else {
+      for (int k = 0; k < 8 && j + k < n; ++k) dp[k] = __float2bfloat16(sp[(long long)k * HW]);
     }
-    for (; j < n; ++j) dp[j] = __float2bfloat16(sp[(long long)j * HW]);
   }
 }
 
@@ -526,12 +537,17 @@ extern "C" int rfk_actnorm_init(const float* x, float* bias, float* logs, float*
 }
 
 extern "C" int rfk_mix1x1(const float* x, float* y, const float* Wm, const float* bvec, int B, int C, int HW,
-                          void* side, int side_n, int side_off, int side_ld, void* stream) {
+                          void* side, int side_n, int side_off, int side_ld, float* logdet, const float* addend,
+                          float alpha, void* stream) {
   RFK_REQUIRE(x && y && Wm && B > 0 && C > 0 && HW > 0, "rfk_mix1x1: null pointer or empty shape");
   RFK_REQUIRE(x != y, "rfk_mix1x1: in-place is not supported");
-  size_t smem = ((size_t)C + (size_t)C * kMixPix) * sizeof(float);
-  RFK_REQUIRE(smem <= 200 * 1024, "rfk_mix1x1: C=%d too large for the shared-memory tile", C);
-  const int w_smem = smem + (size_t)C * C * sizeof(float) <= 96 * 1024;
+  RFK_REQUIRE(!logdet || addend, "rfk_mix1x1: logdet given without an addend");
+  const int G = (C + 7) / 8;
+  RFK_REQUIRE(G <= 32, "rfk_mix1x1: C=%d is too large (max 256)", C);
+  int PT = (256 / G) / 32 * 32;
+  if (PT < 32) PT = 32;
+  size_t smem = ((size_t)C + (size_t)C * PT) * sizeof(float);
+  const int w_smem = smem + (size_t)C * C * sizeof(float) <= 160 * 1024;
   if (w_smem) smem += (size_t)C * C * sizeof(float);
   if (side) RFK_REQUIRE(side_n >= 0 && side_n <= C && side_off >= 0 && side_off + side_n <= side_ld,
                         "rfk_mix1x1: bad side-output window");
@@ -542,8 +558,9 @@ extern "C" int rfk_mix1x1(const float* x, float* y, const float* Wm, const float
     configured = smem;
   }
   long long npix = (long long)B * HW;
-  mix1x1_kernel<<<ceil_div(npix, kMixPix), kMixPix, smem, (cudaStream_t)stream>>>(
-      x, y, Wm, bvec, C, HW, npix, (__nv_bfloat16*)side, side ? side_n : 0, side_off, side_ld, w_smem);
+  mix1x1_kernel<<<ceil_div(npix, PT), dim3(PT, G), smem, (cudaStream_t)stream>>>(
+      x, y, Wm, bvec, C, HW, npix, (__nv_bfloat16*)side, side ? side_n : 0, side_off, side_ld, w_smem, logdet, addend,
+      alpha, B);
   return check_launch("rfk_mix1x1");
 }
 
@@ -555,7 +572,7 @@ extern "C" int rfk_pack_nhwc_bf16(const float* src, long long src_bstride, int B
   if (n == 0) return RFK_OK;
   long long npix = (long long)B * HW;
   int vec_ok = (dst_ld % 8 == 0) && (dst_off % 8 == 0) && aligned16(dst);
-  pack_nhwc_kernel<<<stream_grid(npix, kThreads, 8), kThreads, 0, (cudaStream_t)stream>>>(
+  pack_nhwc_kernel<<<stream_grid(npix * ((n + 7) / 8), kThreads, 8), kThreads, 0, (cudaStream_t)stream>>>(
       src, src_bstride > 0 ? src_bstride : (long long)Csrc * HW, HW, c_lo, n, (__nv_bfloat16*)dst, dst_off, dst_ld,
       npix, vec_ok);
   return check_launch("rfk_pack_nhwc_bf16");

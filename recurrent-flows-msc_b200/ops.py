@@ -63,13 +63,14 @@ def actnorm_init(x, bias, logs):
     call("rfk_actnorm_init", x.data_ptr(), _chk(bias).data_ptr(), _chk(logs).data_ptr(), 0, 0, B, C, H * W, _stream())
 
 
-def mix1x1(x, Wm, bvec=None, side=None, side_n=0, side_off=0):
+def mix1x1(x, Wm, bvec=None, side=None, side_n=0, side_off=0, logdet=None, addend=None, alpha=1.0):
+    """y = Wm x + bvec per pixel; optionally logdet[b] += alpha * addend (device scalar) in the same launch."""
     _chk(x, name="x")
     B, C, H, W = x.shape
     y = torch.empty_like(x)
     side_ld = side.shape[-1] if side is not None else 0
     call("rfk_mix1x1", x.data_ptr(), y.data_ptr(), _chk(Wm).data_ptr(), _p(bvec), B, C, H * W,
-         _p(side), side_n, side_off, side_ld, _stream())
+         _p(side), side_n, side_off, side_ld, _p(logdet), _p(addend), float(alpha), _stream())
     return y
 
 
