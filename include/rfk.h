@@ -169,8 +169,10 @@ int rfk_convlstm_pointwise(const float* cc, const float* c_prev, const float* pe
                            float* h_out, float* c_next, int B, int Hc, int HW, void* stream);
 
 /* Debug aid: when buf != NULL, every conv-GEMM CTA of later launches (grids of at most capacity_ctas CTAs)
- * writes 8 %globaltimer stamps (ns) to buf[8*cta..]: start, setup done, first/last TMA issued, first stage
- * landed, last MMA issued, accumulator ready, epilogue done.  NULL switches it off (the default). */
+ * writes 16 words to buf[16*cta..]: %globaltimer stamps (ns) 0 start, 1 setup done, 2 weights resident, 3 last TMA
+ * issued, 4 last MMA issued, 5 first accumulator ready, 6 first epilogue done, 7 all done; SM-cycle totals 8 producer
+ * waiting for a free stage, 9 MMA waiting for data, 10 MMA waiting for a drained accumulator, 11 epilogue waiting for
+ * an accumulator, 12 epilogue busy.  NULL switches it off (the default). */
 int rfk_debug_set_timeline(unsigned long long* buf, long long capacity_ctas);
 
 /* logdet[b] += *addend  (device scalar; the parameter-only log-det terms of ActNorm / InvConv) */

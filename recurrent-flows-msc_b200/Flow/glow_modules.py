@@ -174,7 +174,7 @@ class Conv2dZeros(nn.Module):
         _require_no_grad()
         x = ops.f32c(input)
         B, C, H, W = x.shape
-        act = ops.workspace(("cz_in", C), (B, H, W, ops.pad_to(C, 64)), x.device)
+        act = ops.workspace(("cz_in", C), (B, H, W, ops.cin_pad(C)), x.device)
         ops.pack_nhwc(x, 0, C, act, 0)
         out = torch.empty(B, self.conv.out_channels, H, W, device=x.device, dtype=torch.float32)
         return self.fused(act, out)
@@ -219,7 +219,7 @@ class Conv2dNorm(nn.Module):
         _require_no_grad()
         x = ops.f32c(input)
         B, C, H, W = x.shape
-        act = ops.workspace(("cn_in", C), (B, H, W, ops.pad_to(C, 64)), x.device)
+        act = ops.workspace(("cn_in", C), (B, H, W, ops.cin_pad(C)), x.device)
         ops.pack_nhwc(x, 0, C, act, 0)
         out = torch.empty(B, self.conv.out_channels, H, W, device=x.device, dtype=torch.float32)
         return self.fused(act, out)
@@ -325,7 +325,7 @@ class AffineCoupling(nn.Module):
         half, cc = C // 2, condition.shape[1]
         dev = z.device
         if _ctx is None:
-            nn_in = ops.workspace(("cpl_in", half + cc), (B, H, W, ops.pad_to(half + cc, 64)), dev)
+            nn_in = ops.workspace(("cpl_in", half + cc), (B, H, W, ops.cin_pad(half + cc)), dev)
             ops.pack_nhwc(ops.f32c(condition), 0, cc, nn_in, 0)
             ops.pack_nhwc(z, 0, half, nn_in, cc)
             out = z.clone()          # module contract: inputs are never modified
@@ -334,7 +334,7 @@ class AffineCoupling(nn.Module):
             if not _ctx.z1_packed:
                 ops.pack_nhwc(z, 0, half, nn_in, cc)
             out = z                  # ListGlow owns this intermediate: update z2 in place
-        hp = ops.pad_to(self.hidden_units, 64)
+        hp = ops.cin_pad(self.hidden_units)
         h1 = ops.workspace(("cpl_h1", self.hidden_units), (B, H, W, hp), dev)
         h2 = ops.workspace(("cpl_h2", self.hidden_units), (B, H, W, hp), dev)
         self.net[0].fused(nn_in, h1, self.non_lin, "cz", self._perm(dev))
@@ -397,15 +397,15 @@ class Split2d(nn.Module):
         """(mean, raw log-scale) tensor [B, 2*half, H, W] from z1 = first `half` channels of z1_src."""
         B, _, H, W = z1_src.shape
         half, cc, dev = self._half, self._cond, z1_src.device
-        sp_in = ops.workspace(("sp_in", half + cc), (B, H, W, ops.pad_to(half + cc, 64)), dev)
+        sp_in = ops.workspace(("sp_in", half + cc), (B, H, W, ops.cin_pad(half + cc)), dev)
         perm = None
         if self.make_conditional:
             if _ctx is None:
-                cbuf = ops.workspace(("sp_c", cc), (B, H, W, ops.pad_to(cc, 64)), dev)
+                cbuf = ops.workspace(("sp_c", cc), (B, H, W, ops.cin_pad(cc)), dev)
                 ops.pack_nhwc(ops.f32c(condition), 0, cc, cbuf, 0)
             else:
                 cbuf = _ctx.nn_in   # condition already packed at channels [0, cc)
-            t1 = ops.workspace(("sp_t1", cc), (B, H, W, ops.pad_to(cc, 64)), dev)
+            t1 = ops.workspace(("sp_t1", cc), (B, H, W, ops.cin_pad(cc)), dev)
             self.convcond[0].fused(cbuf, t1, "relu")
             self.convcond[2].fused(t1, sp_in, "relu")
             perm = torch.cat([torch.arange(half, half + cc, device=dev), torch.arange(0, half, device=dev)])

@@ -112,7 +112,7 @@ class ConvLSTMLayer(nn.Module):
 
     def _staging(self, B, H, W, device):
         cin = self.in_channels + self.hidden_channels
-        shape = (B, H, W, ops.pad_to(cin, 64))
+        shape = (B, H, W, ops.cin_pad(cin))
         return [ops.workspace(("lstm_in", cin, i), shape, device) for i in range(2)]
 
     def forward(self, input_tensor, cur_state):

@@ -29,9 +29,8 @@
 namespace rfk {
 
 constexpr int BM = 128;          // pixels per tile = UMMA M
-constexpr int BK = 64;           // bf16 channels per pipeline stage (= one 128 B swizzle row)
+constexpr int BK = 64;           // bf16 channels per pipeline stage: 64 (128 B swizzle rows) or 32 (64 B rows, g.bk)
 constexpr int UMMA_K = 16;       // K of one tcgen05.mma.kind::f16
-constexpr int A_STAGE_BYTES = BM * BK * 2;
 constexpr int STG_BYTES = BM * 128;  // one 64-channel bf16 output block of a tile
 constexpr int kGemmThreads = 384;    // warp 0: TMA, warp 1: MMA, warp 2: TMEM alloc, warps 4-11: epilogue
 constexpr int kEpiWarp0 = 4;
@@ -42,7 +41,9 @@ struct GemmArgs {
   int B, H, W;
   int n;                 // real output channels
   int BN;                // tile width in output channels (UMMA N), multiple of 16, <= 256
-  int taps, kchunks;     // kchunks = cin_pad / 64
+  int taps, kchunks;     // kchunks = cin_pad / bk
+  int bk;                // K elements per chunk: 64 (SWIZZLE_128B) or 32 (SWIZZLE_64B, for Cin <= 32)
+  int kgroup;            // K chunks per pipeline stage (one mbarrier round trip per stage)
   int tw_log2, th_log2;  // tile = NIMG x TH x TW pixels, TW*TH*NIMG = 128
   int tiles_x, tiles_y, m_tiles;
   int stages;
@@ -55,7 +56,9 @@ struct GemmArgs {
   unsigned long long* timeline;  // debug: 8 globaltimer stamps per CTA (rfk_debug_set_timeline), else null
 };
 
+template <int ACT>
 struct PlainEpi {
+  static constexpr int kAct = ACT;
   int act_fn;
   int out_kind;
   void* out;
@@ -96,9 +99,16 @@ __device__ __forceinline__ unsigned long long gtime() {
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
+// debug cycle accounting: CNT_BEGIN/CNT_END accumulate clock64 deltas into a local counter when tracing is on
+#define CNT_BEGIN() const long long cnt_t0_ = g.timeline ? clock64() : 0
+#define CNT_END(var) do { if (g.timeline) var += clock64() - cnt_t0_; } while (0)
+#define RFK_PUT(slot, val)                                                                                  \
+  do {                                                                                                      \
+    if (g.timeline) g.timeline[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 16 + (slot)] = (unsigned long long)(val); \
+  } while (0)
 #define RFK_STAMP(slot)                                                                               \
   do {                                                                                                \
-    if (g.timeline) g.timeline[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8 + (slot)] = gtime(); \
+    if (g.timeline) g.timeline[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 16 + (slot)] = gtime(); \
   } while (0)
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -164,14 +174,15 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// K-major, 128-byte swizzle shared-memory matrix descriptor (8-row groups 1024 B apart)
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+// K-major swizzled shared-memory matrix descriptor.  Rows are bk*2 bytes (128 B -> SWIZZLE_128B, 64 B ->
+// SWIZZLE_64B); 8-row groups are 8*row bytes apart.
+__device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t saddr, int bk) {
   uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);  // start address, 16-byte units
-  d |= (uint64_t)1 << 16;                    // leading byte offset (ignored for swizzled K-major)
-  d |= (uint64_t)(1024 >> 4) << 32;          // stride byte offset between 8-row groups
-  d |= (uint64_t)1 << 46;                    // descriptor version (sm_100)
-  d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);        // start address, 16-byte units
+  d |= (uint64_t)1 << 16;                          // leading byte offset (ignored for swizzled K-major)
+  d |= (uint64_t)((8 * bk * 2) >> 4) << 32;        // stride byte offset between 8-row groups
+  d |= (uint64_t)1 << 46;                          // descriptor version (sm_100)
+  d |= (uint64_t)(bk == 64 ? 2 : 4) << 61;         // SWIZZLE_128B : SWIZZLE_64B
   return d;
 }
 
@@ -215,6 +226,10 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
 }
+__device__ __forceinline__ uint32_t relu_bf16x2(uint32_t p) {
+  __nv_bfloat162 h = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&p), __float2bfloat162_rn(0.0f));
+  return *reinterpret_cast<uint32_t*>(&h);
+}
 
 // ------------------------------------------------------------------------------------------
 // epilogues.  Thread (quadrant q, lane) owns accumulator row q*32+lane (= one pixel); the two warps
@@ -228,6 +243,7 @@ struct TileCtx {
   int half, q;
   uint32_t stg;     // this half's staging buffer (shared-space address), 0 when not allocated
   uint32_t tmem_empty_bar;
+  long long* dbg;   // 5 per-phase cycle counters of the TMA-store epilogue, or null
 };
 
 __device__ __forceinline__ void release_accumulator(const TileCtx& t) {
@@ -236,7 +252,8 @@ __device__ __forceinline__ void release_accumulator(const TileCtx& t) {
   if ((threadIdx.x & 31) == 0) mbar_arrive(t.tmem_empty_bar);
 }
 
-__device__ __forceinline__ void epilogue(const GemmArgs& g, const PlainEpi& e, const CUtensorMap* tmO,
+template <int ACT>
+__device__ __forceinline__ void epilogue(const GemmArgs& g, const PlainEpi<ACT>& e, const CUtensorMap* tmO,
                                          uint32_t taddr, const float* ss, const TileCtx& t) {
   const int lane = threadIdx.x & 31;
   if (e.tma_store) {
@@ -248,30 +265,46 @@ __device__ __forceinline__ void epilogue(const GemmArgs& g, const PlainEpi& e, c
     bool released = false;
     for (int blk = t.half; blk < nblk; blk += 2) {
       const int cols = min(64, g.BN - blk * 64);
+      long long t0 = t.dbg ? clock64() : 0;
+#define EPI_PHASE(i) do { if (t.dbg) { long long t1 = clock64(); t.dbg[i] += t1 - t0; t0 = t1; } } while (0)
+      uint32_t v[64];
+#pragma unroll
+      for (int c = 0; c < 64; c += 16)
+        if (c < cols) tmem_ld16_nowait(taddr + blk * 64 + c, v + c);  // warp-uniform predicate
+      tmem_wait_ld();
+      EPI_PHASE(0);
       uint32_t pk[32];
 #pragma unroll
       for (int c = 0; c < 64; c += 16) {
-        if (c < cols) {  // warp-uniform
-          uint32_t v[16];
-          tmem_ld16_nowait(taddr + blk * 64 + c, v);
-          tmem_wait_ld();
+        if (c < cols) {
           const float4* sc = reinterpret_cast<const float4*>(ss + blk * 64 + c);
           const float4* sh = reinterpret_cast<const float4*>(ss + g.BN + blk * 64 + c);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const float4 s4 = sc[k], h4 = sh[k];
-            float a0 = apply_act(fmaf(__uint_as_float(v[4 * k + 0]), s4.x, h4.x), e.act_fn);
-            float a1 = apply_act(fmaf(__uint_as_float(v[4 * k + 1]), s4.y, h4.y), e.act_fn);
-            float a2 = apply_act(fmaf(__uint_as_float(v[4 * k + 2]), s4.z, h4.z), e.act_fn);
-            float a3 = apply_act(fmaf(__uint_as_float(v[4 * k + 3]), s4.w, h4.w), e.act_fn);
-            pk[(c >> 1) + 2 * k] = pack_bf16(a0, a1);
-            pk[(c >> 1) + 2 * k + 1] = pack_bf16(a2, a3);
+            float a0 = fmaf(__uint_as_float(v[c + 4 * k + 0]), s4.x, h4.x);
+            float a1 = fmaf(__uint_as_float(v[c + 4 * k + 1]), s4.y, h4.y);
+            float a2 = fmaf(__uint_as_float(v[c + 4 * k + 2]), s4.z, h4.z);
+            float a3 = fmaf(__uint_as_float(v[c + 4 * k + 3]), s4.w, h4.w);
+            if (ACT == RFK_ACT_LEAKY) {
+              a0 = apply_act(a0, RFK_ACT_LEAKY); a1 = apply_act(a1, RFK_ACT_LEAKY);
+              a2 = apply_act(a2, RFK_ACT_LEAKY); a3 = apply_act(a3, RFK_ACT_LEAKY);
+            }
+            uint32_t p0 = pack_bf16(a0, a1), p1 = pack_bf16(a2, a3);
+            if (ACT == RFK_ACT_RELU) {  // relu(bf16(x)) == bf16(relu(x)): do it on the packed pair (one HMNMX2)
+              p0 = relu_bf16x2(p0);
+              p1 = relu_bf16x2(p1);
+            }
+            pk[(c >> 1) + 2 * k] = p0;
+            pk[(c >> 1) + 2 * k + 1] = p1;
           }
         }
       }
       if (blk == last_blk) { release_accumulator(t); released = true; }
+      EPI_PHASE(1);
       if (issuer) bulk_wait_read0();   // the previous TMA store has finished reading this staging buffer
       named_bar(1 + t.half, 128);
+      EPI_PHASE(2);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         if (8 * j < cols) {
@@ -283,10 +316,12 @@ __device__ __forceinline__ void epilogue(const GemmArgs& g, const PlainEpi& e, c
       }
       fence_async_smem();
       named_bar(1 + t.half, 128);
+      EPI_PHASE(3);
       if (issuer) {
         tma_store_4d(tmO, t.stg, t.n_tile * g.BN + blk * 64, t.x0, t.y0, t.n0);
         bulk_commit();
       }
+      EPI_PHASE(4);
     }
     if (!released) release_accumulator(t);
     return;
@@ -302,7 +337,7 @@ __device__ __forceinline__ void epilogue(const GemmArgs& g, const PlainEpi& e, c
     tmem_wait_ld();
     float v[16];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = apply_act(fmaf(__uint_as_float(r[j]), ss[c0 + j], ss[g.BN + c0 + j]), e.act_fn);
+    for (int j = 0; j < 16; ++j) v[j] = apply_act(fmaf(__uint_as_float(r[j]), ss[c0 + j], ss[g.BN + c0 + j]), ACT);
     if (!t.valid) continue;
     if (e.out_kind == RFK_OUT_NHWC_BF16) {
       __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(e.out) + pix * e.out_ld + e.out_off + col0;
@@ -438,9 +473,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   // shared-memory map (all tile regions are multiples of 1024 B)
   const int k_iters = g.taps * g.kchunks;
-  const uint32_t b_chunk_bytes = (uint32_t)g.BN * BK * 2;
+  const uint32_t a_chunk_bytes = (uint32_t)BM * g.bk * 2;
+  const int k_groups = k_iters / g.kgroup;
+  const uint32_t b_chunk_bytes = (uint32_t)g.BN * g.bk * 2;
   const uint32_t b_res_bytes = g.b_resident ? (uint32_t)k_iters * b_chunk_bytes : 0u;
-  const uint32_t stage_bytes = A_STAGE_BYTES + (g.b_resident ? 0u : b_chunk_bytes);
+  const uint32_t stage_bytes = (uint32_t)g.kgroup * (a_chunk_bytes + (g.b_resident ? 0u : b_chunk_bytes));
   const uint32_t stage_base = base + b_res_bytes;
   const uint32_t stg_base = stage_base + g.stages * stage_bytes;
   const uint32_t ss_off = b_res_bytes + g.stages * stage_bytes + (g.use_stg ? 2u * STG_BYTES : 0u);
@@ -507,26 +544,33 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) {
       if (g.b_resident) {
         mbar_expect_tx(b_full_bar, b_res_bytes);
-        for (int it = 0; it < k_iters; ++it) tma_load_2d(base + it * b_chunk_bytes, &tmB, b_full_bar, it * BK, n_tile * g.BN);
+        for (int it = 0; it < k_iters; ++it) tma_load_2d(base + it * b_chunk_bytes, &tmB, b_full_bar, it * g.bk, n_tile * g.BN);
       }
-      uint32_t itg = 0;
+      int s = 0;
+      uint32_t ph = 0;
+      long long c_wait_empty = 0;
       for (int mt = blockIdx.x; mt < g.m_tiles; mt += gridDim.x) {
         int x0, y0, n0;
         tile_origin(mt, x0, y0, n0);
-        for (int it = 0; it < k_iters; ++it, ++itg) {
-          const int s = itg % g.stages;
-          const uint32_t ph = (itg / g.stages) & 1u;
-          mbar_wait(empty_bar(s), ph ^ 1u);
-          const int tap = it / g.kchunks, kc = it - tap * g.kchunks;
-          const int dy = g.taps == 9 ? tap / 3 - 1 : 0;
-          const int dx = g.taps == 9 ? tap % 3 - 1 : 0;
+        int tap = 0, kc = 0;
+        for (int grp = 0; grp < k_groups; ++grp) {
+          { CNT_BEGIN(); mbar_wait(empty_bar(s), ph ^ 1u); CNT_END(c_wait_empty); }
           const uint32_t a_dst = stage_base + s * stage_bytes;
           mbar_expect_tx(full_bar(s), stage_bytes);
-          tma_load_4d(a_dst, &tmA, full_bar(s), kc * BK, x0 + dx, y0 + dy, n0);
-          if (!g.b_resident) tma_load_2d(a_dst + A_STAGE_BYTES, &tmB, full_bar(s), it * BK, n_tile * g.BN);
+          for (int j = 0; j < g.kgroup; ++j) {
+            const int dy = g.taps == 9 ? tap / 3 - 1 : 0;
+            const int dx = g.taps == 9 ? tap % 3 - 1 : 0;
+            tma_load_4d(a_dst + j * a_chunk_bytes, &tmA, full_bar(s), kc * g.bk, x0 + dx, y0 + dy, n0);
+            if (!g.b_resident)
+              tma_load_2d(a_dst + g.kgroup * a_chunk_bytes + j * b_chunk_bytes, &tmB, full_bar(s),
+                          (grp * g.kgroup + j) * g.bk, n_tile * g.BN);
+            if (++kc == g.kchunks) { kc = 0; ++tap; }
+          }
+          if (++s == g.stages) { s = 0; ph ^= 1u; }
         }
       }
       RFK_STAMP(3);  // all loads issued
+      RFK_PUT(8, c_wait_empty);
     }
     __syncwarp();
   } else if (warp == 1) {
@@ -534,34 +578,51 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) {
       // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at bit 17, M>>4 at bit 24
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(g.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      const uint64_t desc_hi = umma_desc_kmajor(0, g.bk);  // everything but the start address
+      const int ksteps = g.bk / UMMA_K;
       if (g.b_resident) {
         mbar_wait(b_full_bar, 0);
         RFK_STAMP(2);  // weights resident
       }
-      uint32_t itg = 0, tl = 0;
+      int s = 0;
+      uint32_t ph = 0, tl = 0;
+      long long c_wait_full = 0, c_wait_tempty = 0, c_issue = 0;
       for (int mt = blockIdx.x; mt < g.m_tiles; mt += gridDim.x, ++tl) {
         const uint32_t buf = tl & 1u;
-        mbar_wait(tmem_empty_bar(buf), ((tl >> 1) & 1u) ^ 1u);  // epilogue has drained this accumulator
+        { CNT_BEGIN(); mbar_wait(tmem_empty_bar(buf), ((tl >> 1) & 1u) ^ 1u); CNT_END(c_wait_tempty); }  // accumulator drained
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * g.BN;
-        for (int it = 0; it < k_iters; ++it, ++itg) {
-          const int s = itg % g.stages;
-          const uint32_t ph = (itg / g.stages) & 1u;
-          mbar_wait(full_bar(s), ph);
+        uint32_t b_res_addr = base;
+        uint32_t accumulate = 0;
+        for (int grp = 0; grp < k_groups; ++grp) {
+          { CNT_BEGIN(); mbar_wait(full_bar(s), ph); CNT_END(c_wait_full); }
           tc_fence_after();
-          const uint32_t a_addr = stage_base + s * stage_bytes;
-          const uint64_t adesc = umma_desc_sw128(a_addr);
-          const uint64_t bdesc = umma_desc_sw128(g.b_resident ? base + it * b_chunk_bytes : a_addr + A_STAGE_BYTES);
-#pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            // advance 32 B (16 bf16) along K inside the 128 B swizzle row: +2 in 16-byte units
-            umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (it | k) != 0);
+          CNT_BEGIN();
+          uint32_t a_addr = stage_base + s * stage_bytes;
+          uint32_t b_addr = g.b_resident ? b_res_addr : a_addr + g.kgroup * a_chunk_bytes;
+          for (int j = 0; j < g.kgroup; ++j) {
+            const uint64_t adesc = desc_hi | (uint64_t)((a_addr & 0x3FFFFu) >> 4);
+            const uint64_t bdesc = desc_hi | (uint64_t)((b_addr & 0x3FFFFu) >> 4);
+#pragma unroll 4
+            for (int k = 0; k < ksteps; ++k) {
+              // advance 32 B (16 bf16) along K inside the swizzle row: +2 in 16-byte units
+              umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, accumulate);
+              accumulate = 1;
+            }
+            a_addr += a_chunk_bytes;
+            b_addr += b_chunk_bytes;
           }
+          b_res_addr += g.kgroup * b_chunk_bytes;
           umma_commit(empty_bar(s));  // frees the smem stage once these MMAs have read it
+          CNT_END(c_issue);
+          if (++s == g.stages) { s = 0; ph ^= 1u; }
         }
         umma_commit(tmem_full_bar(buf));  // accumulator complete
       }
       RFK_STAMP(4);  // all MMAs issued
+      RFK_PUT(9, c_wait_full);
+      RFK_PUT(10, c_wait_tempty);
+      RFK_PUT(13, c_issue);
     }
     __syncwarp();
   } else if (warp >= kEpiWarp0) {
@@ -574,6 +635,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int row = t.q * 32 + lane;
     const int ppi_log2 = g.tw_log2 + g.th_log2;
     uint32_t tl = 0;
+    long long c_wait_tfull = 0, c_epi = 0;
+    long long phase_cnt[5] = {0, 0, 0, 0, 0};
+    t.dbg = g.timeline ? phase_cnt : nullptr;
     for (int mt = blockIdx.x; mt < g.m_tiles; mt += gridDim.x, ++tl) {
       const uint32_t buf = tl & 1u;
       tile_origin(mt, t.x0, t.y0, t.n0);
@@ -582,14 +646,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       t.x = t.x0 + (row & ((1 << g.tw_log2) - 1));
       t.valid = t.b < g.B && t.y < g.H && t.x < g.W;
       t.tmem_empty_bar = tmem_empty_bar(buf);
-      mbar_wait(tmem_full_bar(buf), (tl >> 1) & 1u);
+      { CNT_BEGIN(); mbar_wait(tmem_full_bar(buf), (tl >> 1) & 1u); CNT_END(c_wait_tfull); }
       if (tl == 0 && warp == kEpiWarp0 && lane == 0) RFK_STAMP(5);  // first accumulator ready
       tc_fence_after();
-      epilogue(g, ep, &tmO, tmem_base + ((uint32_t)(t.q * 32) << 16) + buf * g.BN, ss, t);
+      { CNT_BEGIN(); epilogue(g, ep, &tmO, tmem_base + ((uint32_t)(t.q * 32) << 16) + buf * g.BN, ss, t); CNT_END(c_epi); }
       if (tl == 0 && warp == kEpiWarp0 && lane == 0) RFK_STAMP(6);  // first epilogue done
     }
     if (g.use_stg && t.q == 0 && lane == 0) bulk_wait0();  // outstanding TMA stores read shared memory
-    if (warp == kEpiWarp0 && lane == 0) RFK_STAMP(7);      // all epilogues done
+    if (warp == kEpiWarp0 && lane == 0) { RFK_STAMP(7); RFK_PUT(11, c_wait_tfull); RFK_PUT(12, c_epi);
+      RFK_PUT(14, phase_cnt[0]); RFK_PUT(15, phase_cnt[1]); RFK_PUT(2, phase_cnt[2]); RFK_PUT(5, phase_cnt[3]); RFK_PUT(6, phase_cnt[4]); }
   }
 
   tc_fence_before();
@@ -637,7 +702,7 @@ struct Plan {
 };
 
 static int encode_act_map(CUtensorMap* map, const char* who, const char* what, const void* ptr, int channels, int ld,
-                          int B, int H, int W, int TW, int TH, int NIMG) {
+                          int B, int H, int W, int TW, int TH, int NIMG, int bk = BK) {
   EncodeTiledFn enc = encode_fn();
   if (!enc) {
     set_error("%s: cuTensorMapEncodeTiled is unavailable (no CUDA driver?)", who);
@@ -646,11 +711,11 @@ static int encode_act_map(CUtensorMap* map, const char* who, const char* what, c
   // NHWC bf16 viewed as 4-D {C, W, H, B}; box {64, TW, TH, NIMG}; loads: OOB -> zeros (the conv padding); stores: clipped
   cuuint64_t dims[4] = {(cuuint64_t)channels, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
   cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)W * ld * 2, (cuuint64_t)H * W * ld * 2};
-  cuuint32_t box[4] = {BK, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)NIMG};
+  cuuint32_t box[4] = {(cuuint32_t)bk, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)NIMG};
   cuuint32_t ones[4] = {1, 1, 1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, ones,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("%s: cuTensorMapEncodeTiled(%s) failed with CUresult %d (B=%d H=%d W=%d ld=%d channels=%d)", who, what, (int)r,
               B, H, W, ld, channels);
@@ -663,8 +728,9 @@ static int encode_act_map(CUtensorMap* map, const char* who, const char* what, c
 static int make_plan(Plan& p, const char* who, const void* act, int B, int H, int W, int act_ld, int cin_pad,
                      const void* wgt, int n, int n_pad, int taps, int BN, bool stg_wanted) {
   RFK_REQUIRE(act && wgt && B > 0 && H > 0 && W > 0, "%s: null pointer or empty shape", who);
-  RFK_REQUIRE(cin_pad > 0 && cin_pad % BK == 0 && cin_pad <= act_ld, "%s: cin_pad=%d must be a multiple of %d and <= act_ld=%d",
-              who, cin_pad, BK, act_ld);
+  RFK_REQUIRE(cin_pad > 0 && (cin_pad % 64 == 0 || cin_pad == 32) && cin_pad <= act_ld,
+              "%s: cin_pad=%d must be 32 or a multiple of 64, and <= act_ld=%d", who, cin_pad, act_ld);
+  const int bk = cin_pad % 64 == 0 ? 64 : 32;
   RFK_REQUIRE(act_ld % 8 == 0, "%s: act_ld=%d must be a multiple of 8 (16-byte TMA strides)", who, act_ld);
   RFK_REQUIRE(taps == 1 || taps == 9, "%s: taps=%d (only 1x1 and 3x3 kernels)", who, taps);
   RFK_REQUIRE(n > 0 && n <= n_pad && n_pad % 16 == 0, "%s: n=%d n_pad=%d (n_pad must be a multiple of 16)", who, n, n_pad);
@@ -677,7 +743,7 @@ static int make_plan(Plan& p, const char* who, const void* act, int B, int H, in
     return RFK_ECUDA;
   }
   GemmArgs& g = p.g;
-  g.B = B; g.H = H; g.W = W; g.n = n; g.BN = BN; g.taps = taps; g.kchunks = cin_pad / BK;
+  g.B = B; g.H = H; g.W = W; g.n = n; g.BN = BN; g.taps = taps; g.bk = bk; g.kchunks = cin_pad / bk;
   int twl = ilog2_ceil(W);
   if (twl > 7) twl = 7;
   int thl = ilog2_ceil(H);
@@ -688,27 +754,30 @@ static int make_plan(Plan& p, const char* who, const void* act, int B, int H, in
   g.tiles_y = ceil_div(H, p.TH);
   g.m_tiles = g.tiles_x * g.tiles_y * ceil_div(B, p.NIMG);
   const int n_tiles = n_pad / BN;
-  const int k_iters = taps * g.kchunks;
 
   // shared-memory budget: [resident weights] [stages] [2 staging blocks] [scale/shift] [barriers]
-  const int b_chunk = BN * BK * 2;
+  const int k_iters = taps * g.kchunks;
+  // 64-byte-row chunks carry only two MMAs each: group three (a filter row) or two per pipeline stage
+  g.kgroup = bk == 32 ? (k_iters % 3 == 0 ? 3 : (k_iters % 2 == 0 ? 2 : 1)) : 1;
+  const int b_chunk = g.kgroup * BN * bk * 2;
+  const int a_stage = g.kgroup * BM * bk * 2;
   const int fixed = 1024 /*alignment slack*/ + (stg_wanted ? 2 * STG_BYTES : 0) + 2 * BN * 4 + 8 * (2 * 8 + 5) + 16;
   g.use_stg = stg_wanted ? 1 : 0;
   int resident = 0, stages = 0;
   {
-    const long long res_bytes = (long long)k_iters * b_chunk;
+    const long long res_bytes = (long long)k_iters * BN * bk * 2;
     const long long room = (long long)SMEM_LIMIT - fixed - res_bytes;
-    if (room >= 3LL * A_STAGE_BYTES) {
+    if (room >= 3LL * a_stage) {
       resident = 1;
-      stages = (int)(room / A_STAGE_BYTES);
+      stages = (int)(room / a_stage);
     } else {
-      stages = (SMEM_LIMIT - fixed) / (A_STAGE_BYTES + b_chunk);
+      stages = (SMEM_LIMIT - fixed) / (a_stage + b_chunk);
     }
   }
   if (const char* s = getenv("RFK_GEMM_RESIDENT")) {
     if (atoi(s) == 0 && resident) {
       resident = 0;
-      stages = (SMEM_LIMIT - fixed) / (A_STAGE_BYTES + b_chunk);
+      stages = (SMEM_LIMIT - fixed) / (a_stage + b_chunk);
     }
   }
   if (const char* s = getenv("RFK_GEMM_STAGES")) stages = std::min(stages, std::max(1, atoi(s)));
@@ -719,8 +788,8 @@ static int make_plan(Plan& p, const char* who, const void* act, int B, int H, in
   int cols = 32;
   while (cols < 2 * BN) cols <<= 1;
   g.tmem_cols = cols;  // two accumulators
-  const int stage_bytes = A_STAGE_BYTES + (resident ? 0 : b_chunk);
-  p.smem = (size_t)1024 + (resident ? (size_t)k_iters * b_chunk : 0) + (size_t)stages * stage_bytes +
+  const int stage_bytes = a_stage + (resident ? 0 : b_chunk);
+  p.smem = (size_t)1024 + (resident ? (size_t)k_iters * BN * bk * 2 : 0) + (size_t)stages * stage_bytes +
            (stg_wanted ? 2 * STG_BYTES : 0) + 2 * BN * 4 + 8 * (2 * stages + 5) + 16;
   RFK_REQUIRE(p.smem <= (size_t)SMEM_LIMIT, "%s: internal error: %zu B of shared memory planned", who, p.smem);
   int ctas_x = sm_count() / n_tiles;
@@ -730,18 +799,18 @@ static int make_plan(Plan& p, const char* who, const void* act, int B, int H, in
   g.timeline = (g_timeline && (long long)ctas_x * n_tiles <= g_timeline_cap) ? g_timeline : nullptr;
   g.scale = nullptr; g.shift = nullptr; g.n_ss = 0;
 
-  int rc = encode_act_map(&p.tmA, who, "A", act, cin_pad, act_ld, B, H, W, p.TW, p.TH, p.NIMG);
+  int rc = encode_act_map(&p.tmA, who, "A", act, cin_pad, act_ld, B, H, W, p.TW, p.TH, p.NIMG, bk);
   if (rc) return rc;
   p.tmO = p.tmA;  // placeholder unless the epilogue stores through TMA
   // B: weights [n_pad, taps*cin_pad] viewed as 2-D {K, N}; box {64, BN}
   const cuuint64_t ktot = (cuuint64_t)taps * cin_pad;
   cuuint64_t dimsB[2] = {ktot, (cuuint64_t)n_pad};
   cuuint64_t strB[1] = {ktot * 2};
-  cuuint32_t boxB[2] = {BK, (cuuint32_t)BN};
+  cuuint32_t boxB[2] = {(cuuint32_t)bk, (cuuint32_t)BN};
   cuuint32_t ones[2] = {1, 1};
   CUresult r = enc(&p.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(wgt), dimsB, strB, boxB, ones,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("%s: cuTensorMapEncodeTiled(B) failed with CUresult %d (n_pad=%d ktot=%llu BN=%d)", who, (int)r, n_pad,
               (unsigned long long)ktot, BN);
@@ -769,7 +838,9 @@ static int launch(const Plan& p, const Epi& ep, cudaStream_t st, const char* who
 // multiple of `quantum`.  Small pixel counts get narrower tiles so that more SMs share the work.
 static int pick_bn(int n_pad, int quantum, int m_tiles_hint) {
   int best = 0;
-  for (int bn = 256; bn >= quantum; bn -= quantum)
+  int bn_max = 256;
+  if (const char* s = getenv("RFK_GEMM_BN_MAX")) bn_max = std::max(quantum, atoi(s) / quantum * quantum);
+  for (int bn = bn_max; bn >= quantum; bn -= quantum)
     if (n_pad % bn == 0) { best = bn; break; }
   if (!best) return 0;
   const int sms = sm_count();
@@ -803,7 +874,7 @@ extern "C" int rfk_conv_gemm(const void* act, int B, int H, int W, int act_ld, i
   RFK_REQUIRE(out_kind == RFK_OUT_NHWC_BF16 || out_kind == RFK_OUT_NCHW_F32, "rfk_conv_gemm: bad out_kind %d", out_kind);
   RFK_REQUIRE(act_fn >= 0 && act_fn <= 2, "rfk_conv_gemm: bad act_fn %d", act_fn);
   RFK_REQUIRE(n_pad > 0 && n_pad % 16 == 0, "rfk_conv_gemm: n_pad=%d must be a positive multiple of 16", n_pad);
-  PlainEpi e;
+  PlainEpi<0> e;
   e.act_fn = act_fn; e.out_kind = out_kind; e.out = out; e.out_ld = out_ld; e.out_off = out_off; e.vec_ok = 0;
   e.tma_store = 0;
   bool tma_ok = false;
@@ -830,6 +901,18 @@ extern "C" int rfk_conv_gemm(const void* act, int B, int H, int W, int act_ld, i
     rc = encode_act_map(&p.tmO, "rfk_conv_gemm", "out", reinterpret_cast<const __nv_bfloat16*>(out) + out_off, n, out_ld, B, H,
                         W, p.TW, p.TH, p.NIMG);
     if (rc) return rc;
+  }
+  if (act_fn == RFK_ACT_RELU) {
+    PlainEpi<RFK_ACT_RELU> e1;
+    e1.act_fn = act_fn; e1.out_kind = e.out_kind; e1.out = e.out; e1.out_ld = e.out_ld; e1.out_off = e.out_off;
+    e1.vec_ok = e.vec_ok; e1.tma_store = e.tma_store;
+    return launch(p, e1, (cudaStream_t)stream, "rfk_conv_gemm");
+  }
+  if (act_fn == RFK_ACT_LEAKY) {
+    PlainEpi<RFK_ACT_LEAKY> e2;
+    e2.act_fn = act_fn; e2.out_kind = e.out_kind; e2.out = e.out; e2.out_ld = e.out_ld; e2.out_off = e.out_off;
+    e2.vec_ok = e.vec_ok; e2.tma_store = e.tma_store;
+    return launch(p, e2, (cudaStream_t)stream, "rfk_conv_gemm");
   }
   return launch(p, e, (cudaStream_t)stream, "rfk_conv_gemm");
 }

@@ -38,6 +38,12 @@ def pad_to(v, m):
     return (v + m - 1) // m * m
 
 
+def cin_pad(c):
+    """Channels a conv consumes from an NHWC staging buffer: 32 (64-byte swizzle rows) for up to 32 real
+    channels, else the next multiple of 64 (128-byte swizzle rows).  Also the buffer's row stride."""
+    return 32 if c <= 32 else pad_to(c, 64)
+
+
 # --------------------------------------------------------------------------------------
 def squeeze2d(x, undo=False):
     _chk(x, name="x")
@@ -215,7 +221,7 @@ def pack_conv_weight(weight, in_perm=None, row_perm=None, n_pad=None):
     N, Cin, kh, kw = w.shape
     if in_perm is not None:
         w = w[:, in_perm]
-    cin_pad = pad_to(max(Cin, 1), 64)
+    cin_pad_ = cin_pad(max(Cin, 1))
     w = w.permute(0, 2, 3, 1).reshape(N, kh * kw, Cin)
     if row_perm is not None:
         rows = row_perm.numel()
@@ -224,8 +230,8 @@ def pack_conv_weight(weight, in_perm=None, row_perm=None, n_pad=None):
         full[valid] = w[row_perm[valid]]
         w, N = full, rows
     n_pad = n_pad or pad_to(N, 16)
-    out = torch.zeros(n_pad, kh * kw, cin_pad, device=w.device, dtype=torch.bfloat16)
+    out = torch.zeros(n_pad, kh * kw, cin_pad_, device=w.device, dtype=torch.bfloat16)
     out[:N, :, :Cin] = w.to(torch.bfloat16)
-    out = out.reshape(n_pad, kh * kw * cin_pad).contiguous()
+    out = out.reshape(n_pad, kh * kw * cin_pad_).contiguous()
     out.rfk_cin = Cin  # real input channels, for FLOP accounting
-    return out, cin_pad
+    return out, cin_pad_

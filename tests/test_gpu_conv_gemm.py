@@ -28,7 +28,7 @@ def max_rel(a, b):
 
 def staged(ops, x):
     B, C, H, W = x.shape
-    buf = torch.zeros(B, H, W, ops.pad_to(C, 64), device="cuda", dtype=torch.bfloat16)
+    buf = torch.zeros(B, H, W, ops.cin_pad(C), device="cuda", dtype=torch.bfloat16)
     ops.pack_nhwc(x.cuda(), 0, C, buf, 0)
     return buf
 

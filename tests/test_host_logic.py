@@ -71,7 +71,7 @@ def test_pack_conv_weight_layout(k):
     x = torch.randn(2, 5, 4, 6).to(torch.bfloat16).float()
     w = torch.randn(7, 5, k, k).to(torch.bfloat16).float()
     wp, cin_pad = rf.ops.pack_conv_weight(w)
-    assert wp.shape == (16, k * k * 64) and cin_pad == 64 and wp.dtype == torch.bfloat16
+    assert wp.shape == (16, k * k * 32) and cin_pad == 32 and wp.dtype == torch.bfloat16
     torch.testing.assert_close(im2col_gemm(x, wp, cin_pad, 7, k), F.conv2d(x, w, None, 1, (k - 1) // 2), rtol=1e-4, atol=1e-4)
     perm = torch.tensor([3, 4, 0, 1, 2])   # staging order [cond | z1] vs the reference's cat[z1, cond]
     wp2, _ = rf.ops.pack_conv_weight(w, perm)
