@@ -1,0 +1,68 @@
+"""Drop-in check against the real reference (build container only: /root/reference is absent on the GPU box).
+
+Builds the reference's RFN (RFN/RFN_new.py, main_rfn.py defaults) twice -- stock, and after
+recurrent_flows_msc_b200.install_into(Flow, Utils) -- and checks the two models expose identical
+state_dict keys and shapes, i.e. a reference checkpoint loads into the B200-backed model."""
+import importlib
+import os
+import re
+import sys
+from unittest.mock import MagicMock
+
+import pytest
+import torch
+
+REF = os.environ.get("RFMSC_REFERENCE", "/root/reference")
+pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "RFN")), reason="reference checkout not present")
+
+
+def reference_args():
+    src = open(os.path.join(REF, "main_rfn.py")).read()
+    head = src[:src.index("if __name__")]
+    body = src[src.index("if __name__"):]
+    body = body[body.index("\n") + 1:body.index("args = parser.parse_args()")]
+    body = "\n".join(l[4:] if l.startswith("    ") else l for l in body.split("\n"))
+    ns = {}
+    exec(re.sub(r"^from .*$|^import (?!argparse).*$", "", head, flags=re.M) + "\nimport argparse\n" + body, ns)
+    args = ns["parser"].parse_args([])
+    args.batch_size = 2
+    args.x_dim = [2] + list(args.x_dim[1:])
+    args.condition_dim = [2] + list(args.condition_dim[1:])
+    return args
+
+
+def test_install_into_keeps_rfn_state_dict():
+    sys.dont_write_bytecode = True
+    for m in ["matplotlib", "matplotlib.pyplot", "imageio", "torchfile", "parse"]:
+        sys.modules.setdefault(m, MagicMock())
+    sys.path.insert(0, REF)
+    try:
+        import Flow
+        import Utils
+        args = reference_args()
+        rfn_mod = importlib.import_module("RFN.RFN_new")
+        torch.manual_seed(0)
+        stock = rfn_mod.RFN(args)
+        ref_sd = {k: tuple(v.shape) for k, v in stock.state_dict().items()}
+        import recurrent_flows_msc_b200 as rfk
+        saved = {n: getattr(Flow, n) for n in ("ListGlow",)}, {n: getattr(Utils, n) for n in ("ConvLSTM", "ConvLSTMLayer")}
+        patched = rfk.install_into(Flow, Utils)
+        assert "Flow.ListGlow" in patched and "Utils.ConvLSTM" in patched
+        try:
+            rfn_mod = importlib.reload(rfn_mod)
+            torch.manual_seed(0)
+            ours = rfn_mod.RFN(args)
+            assert isinstance(ours.flow, rfk.ListGlow) and isinstance(ours.lstm, rfk.ConvLSTM)
+            our_sd = {k: tuple(v.shape) for k, v in ours.state_dict().items()}
+            assert our_sd == ref_sd
+            ours.load_state_dict(stock.state_dict())   # a reference checkpoint loads unchanged
+        finally:
+            importlib.reload(importlib.import_module("Flow.glow_modules"))
+            importlib.reload(importlib.import_module("Flow.glow"))
+            importlib.reload(Flow)
+            importlib.reload(importlib.import_module("Utils.modules"))
+            importlib.reload(Utils)
+    finally:
+        sys.path.remove(REF)
+        for name in [n for n in sys.modules if n.split(".")[0] in ("Flow", "Utils", "RFN")]:
+            del sys.modules[name]
