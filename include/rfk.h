@@ -138,6 +138,14 @@ int rfk_conv_gemm_lstm(const void* act, int B, int H, int W, int act_ld, int cin
                        float* c_next, long long c_next_bstride, float* h_out, long long h_bstride,
                        void* h_nhwc, int h_off, int h_ld, void* stream);
 
+/* Split-K form of rfk_conv_gemm for launches whose pixel tiles cannot fill the GPU (the RFN ConvLSTM runs on 2x2 maps:
+ * 120 pixels, K = 9*712): the K loop is cut into k_split slices (gridDim.z), each CTA adds its partial tile into the
+ * caller-zeroed fp32 workspace ws[pixel, ws_ld] (pixel = (b*H + y)*W + x, columns = output channels) with vector
+ * red.global.add.  No epilogue math: pair it with rfk_convlstm_pointwise_ws (or any pixel-major consumer). */
+int rfk_conv_gemm_splitk(const void* act, int B, int H, int W, int act_ld, int cin_pad,
+                         const void* wgt, int n, int n_pad, int taps, int k_split,
+                         float* ws, int ws_ld, void* stream);
+
 /* ---- a3  coupling tail, standalone (Flow/glow_modules.py:275-290) -------------------------
  * nn_out [B,C,H,W] f32 = output of the coupling network; z as in rfk_conv_gemm_coupling. */
 int rfk_coupling_tail(const float* nn_out, float* z, int B, int C, int HW,
@@ -174,6 +182,15 @@ int rfk_convlstm_pointwise(const float* cc, const float* c_prev, const float* pe
  * waiting for a free stage, 9 MMA waiting for data, 10 MMA waiting for a drained accumulator, 11 epilogue waiting for
  * an accumulator, 12 epilogue busy.  NULL switches it off (the default). */
 int rfk_debug_set_timeline(unsigned long long* buf, long long capacity_ctas);
+
+/* ConvLSTM cell update (Utils/modules.py:369-377) from a pixel-major gate buffer cc[(b*HW+p)*cc_ld + g*Hc + ch]
+ * (g in i,f,o,g; natural weight-row order) plus bias [4*Hc] (nullable).  c_prev (nullable = 0), h_out, c_next: f32 NCHW
+ * with batch strides; peep nullable [3,Hc,HW]; h_nhwc (nullable): bf16 copy of h' at channel h_off of an NHWC buffer
+ * with row stride h_ld; zero_cc != 0 clears the gate buffer behind the read (ready for the next split-K step). */
+int rfk_convlstm_pointwise_ws(float* cc, int cc_ld, const float* bias, const float* c_prev, long long c_prev_bstride,
+                              const float* peep, float* h_out, long long h_bstride, float* c_next,
+                              long long c_next_bstride, void* h_nhwc, int h_off, int h_ld,
+                              int B, int Hc, int HW, int zero_cc, void* stream);
 
 /* logdet[b] += *addend  (device scalar; the parameter-only log-det terms of ActNorm / InvConv) */
 int rfk_add_scalar(float* logdet, const float* addend, float alpha, int B, void* stream);

@@ -17,7 +17,7 @@ from ..Utils.utils import split_feature  # noqa: F401  (re-exported like the ref
 from ..Utils.modules import ActFun
 
 
-TAP_SPLIT_MAX_N = 256  # AffineCoupling: use the tap-split form of the last conv while 9*C fits one N tile
+TAP_SPLIT_MAX_N = 2304  # AffineCoupling: tap-split form of the last conv up to C = 256 (K drops from 9*256 to 256)
 
 
 def _require_no_grad():

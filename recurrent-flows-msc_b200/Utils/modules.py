@@ -29,13 +29,19 @@ class ActFun(nn.Module):
         return self.net(x)
 
 
-def _hidden_tiling(hidden):
-    """Hidden channels per N tile: largest divisor ht of `hidden` whose 4 gate blocks (padded to a
-    multiple of 8 columns each) fit one 256-column accumulator."""
-    for ht in range(min(hidden, 64), 0, -1):
-        if hidden % ht == 0 and 4 * ops.pad_to(ht, 8) <= 256:
+def _hidden_tiling(hidden, m_tiles=1 << 30):
+    """Hidden channels per N tile (ht) and its padding to a multiple of 8 columns per gate (4*ht_pad <= 256).
+
+    Large pixel counts take the widest tile (tcgen05.mma costs the same for any N <= 256, so wide tiles do the
+    most work per activation byte).  When the pixel tiles alone cannot fill the GPU (RFN: 120 pixels = 1 tile)
+    the hidden channels are cut into many narrow tiles so that more SMs stream the weights in parallel."""
+    cands = [d for d in range(1, min(hidden, 64) + 1) if hidden % d == 0]
+    exact = [d for d in cands if d % 8 == 0] or cands
+    for ht in sorted(exact, reverse=True):
+        if m_tiles * (hidden // ht) >= 128:
             return ht, ops.pad_to(ht, 8)
-    raise ValueError(hidden)
+    ht = min(d for d in exact if d >= 8) if any(d >= 8 for d in exact) else max(exact)
+    return ht, ops.pad_to(ht, 8)
 
 
 class ConvLSTMLayer(nn.Module):
@@ -78,13 +84,13 @@ class ConvLSTMLayer(nn.Module):
             self._peep = None
             self.Wci = self.Wcf = self.Wco = 0
 
-    def _weights(self):
+    def _weights(self, m_tiles=1 << 30):
         conv = self.conv[0]
+        hc = self.hidden_channels
+        ht, ht_pad = _hidden_tiling(hc, m_tiles)
         key = (conv.weight.data_ptr(), conv.weight._version,
-               None if conv.bias is None else (conv.bias.data_ptr(), conv.bias._version))
+               None if conv.bias is None else (conv.bias.data_ptr(), conv.bias._version), ht)
         if self._packed is None or self._packed[0] != key:
-            hc = self.hidden_channels
-            ht, ht_pad = _hidden_tiling(hc)
             dev = conv.weight.device
             # tile-interleaved rows: (tile t, gate g, j) <- reference row g*hc + t*ht + j
             t = torch.arange(hc // ht, device=dev)[:, None, None]
@@ -102,9 +108,39 @@ class ConvLSTMLayer(nn.Module):
             self._packed = (key, wgt, cin_pad, b, ht, ht_pad)
         return self._packed[1:]
 
+    def _split_k(self, m_tiles):
+        """K slices for launches whose pixel tiles cannot fill the GPU: one slice per filter tap (3x3) when a single
+        pixel tile would otherwise walk the whole K = taps*(Cin+Hc) loop on a handful of SMs."""
+        return self.taps if (m_tiles <= 2 and self.taps > 1 and self.in_channels + self.hidden_channels >= 256) else 1
+
+    def _weights_plain(self):
+        """Natural row order (i,f,o,g blocks of Hc rows) for the split-K path; cached."""
+        conv = self.conv[0]
+        key = (conv.weight.data_ptr(), conv.weight._version)
+        hit = self.__dict__.get("_packed_plain")
+        if hit is None or hit[0] != key:
+            with torch.no_grad():
+                wgt, cin_pad = ops.pack_conv_weight(conv.weight)
+            hit = (key, wgt, cin_pad)
+            self.__dict__["_packed_plain"] = hit
+        return hit[1], hit[2]
+
     def step(self, in_buf, c_cur, h_out, next_buf):
-        """One fused cell step on a packed NHWC bf16 input; returns c_next."""
-        wgt, cin_pad, b, ht, ht_pad = self._weights()
+        """One cell step on a packed NHWC bf16 input; returns c_next.  Fused GEMM + cell update in one kernel, or,
+        for tiny maps, a split-K GEMM into an fp32 workspace followed by the pointwise cell kernel."""
+        B, H, W, _ = in_buf.shape
+        k_split = self._split_k((B * H * W + 127) // 128)
+        if k_split > 1:
+            wgt, cin_pad = self._weights_plain()
+            hc = self.hidden_channels
+            ws = ops.workspace(("lstm_ws", hc), (B * H * W, wgt.shape[0]), in_buf.device, torch.float32)  # zero-initialised
+            c_next = torch.empty(h_out.shape, device=h_out.device, dtype=torch.float32)
+            ops.conv_gemm_splitk(in_buf, cin_pad, wgt, 4 * hc, self.taps, k_split, ws)
+            bias = self.conv[0].bias
+            ops.convlstm_pointwise_ws(ws, None if bias is None else bias.detach(), c_cur, self._peep, h_out, c_next,
+                                      next_buf, self.in_channels, zero_cc=True)   # leaves ws zeroed for the next step
+            return c_next
+        wgt, cin_pad, b, ht, ht_pad = self._weights((B * H * W + 127) // 128)
         c_next = torch.empty(h_out.shape, device=h_out.device, dtype=torch.float32)
         ops.conv_gemm_lstm(in_buf, cin_pad, wgt, self.hidden_channels, ht, ht_pad, self.taps, b, c_cur, self._peep,
                            c_next, h_out, next_buf, self.in_channels)

@@ -44,6 +44,7 @@ struct GemmArgs {
   int taps, kchunks;     // kchunks = cin_pad / bk
   int bk;                // K elements per chunk: 64 (SWIZZLE_128B) or 32 (SWIZZLE_64B, for Cin <= 32)
   int kgroup;            // K chunks per pipeline stage (one mbarrier round trip per stage)
+  int kg_per_split;      // pipeline stages of K per CTA: all of them, or a 1/gridDim.z slice (split-K)
   int tw_log2, th_log2;  // tile = NIMG x TH x TW pixels, TW*TH*NIMG = 128
   int tiles_x, tiles_y, m_tiles;
   int stages;
@@ -76,6 +77,11 @@ struct CouplingEpi {
   int reverse;
 };
 
+struct SplitKEpi {   // partial sums of a K slice: ws[pixel, col] += acc  (fp32, pixel-major, vector red)
+  float* ws;
+  int ld;
+};
+
 struct LstmEpi {
   int hidden, ht, ht_pad;
   const float* c_prev;
@@ -104,11 +110,11 @@ __device__ __forceinline__ unsigned long long gtime() {
 #define CNT_END(var) do { if (g.timeline) var += clock64() - cnt_t0_; } while (0)
 #define RFK_PUT(slot, val)                                                                                  \
   do {                                                                                                      \
-    if (g.timeline) g.timeline[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 16 + (slot)] = (unsigned long long)(val); \
+    if (g.timeline) g.timeline[(((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16 + (slot)] = (unsigned long long)(val); \
   } while (0)
 #define RFK_STAMP(slot)                                                                               \
   do {                                                                                                \
-    if (g.timeline) g.timeline[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 16 + (slot)] = gtime(); \
+    if (g.timeline) g.timeline[(((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16 + (slot)] = gtime(); \
   } while (0)
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -403,6 +409,25 @@ __device__ __forceinline__ void epilogue(const GemmArgs& g, const CouplingEpi& e
   }
 }
 
+__device__ __forceinline__ void epilogue(const GemmArgs& g, const SplitKEpi& e, const CUtensorMap*, uint32_t taddr,
+                                         const float*, const TileCtx& t) {
+  const long long pix = ((long long)t.b * g.H + t.y) * g.W + t.x;
+  for (int c0 = 16 * t.half; c0 < g.BN; c0 += 32) {
+    uint32_t r[16];
+    tmem_ld16_nowait(taddr + c0, r);
+    tmem_wait_ld();
+    if (!t.valid) continue;
+    float* dst = e.ws + pix * e.ld + t.n_tile * g.BN + c0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * k), "f"(__uint_as_float(r[4 * k])),
+                   "f"(__uint_as_float(r[4 * k + 1])), "f"(__uint_as_float(r[4 * k + 2])),
+                   "f"(__uint_as_float(r[4 * k + 3]))
+                   : "memory");
+  }
+  release_accumulator(t);
+}
+
 __device__ __forceinline__ void epilogue(const GemmArgs& g, const LstmEpi& e, const CUtensorMap*, uint32_t taddr,
                                          const float* ss, const TileCtx& t) {
   const long long plane = (long long)g.H * g.W;
@@ -474,9 +499,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   // shared-memory map (all tile regions are multiples of 1024 B)
   const int k_iters = g.taps * g.kchunks;
   const uint32_t a_chunk_bytes = (uint32_t)BM * g.bk * 2;
-  const int k_groups = k_iters / g.kgroup;
+  const int k_groups = g.kg_per_split;             // pipeline stages of K this CTA accumulates
+  const int kg0 = blockIdx.z * g.kg_per_split;      // first one (split-K: gridDim.z slices)
   const uint32_t b_chunk_bytes = (uint32_t)g.BN * g.bk * 2;
-  const uint32_t b_res_bytes = g.b_resident ? (uint32_t)k_iters * b_chunk_bytes : 0u;
+  const uint32_t b_res_bytes = g.b_resident ? (uint32_t)(k_groups * g.kgroup) * b_chunk_bytes : 0u;
   const uint32_t stage_bytes = (uint32_t)g.kgroup * (a_chunk_bytes + (g.b_resident ? 0u : b_chunk_bytes));
   const uint32_t stage_base = base + b_res_bytes;
   const uint32_t stg_base = stage_base + g.stages * stage_bytes;
@@ -544,7 +570,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) {
       if (g.b_resident) {
         mbar_expect_tx(b_full_bar, b_res_bytes);
-        for (int it = 0; it < k_iters; ++it) tma_load_2d(base + it * b_chunk_bytes, &tmB, b_full_bar, it * g.bk, n_tile * g.BN);
+        for (int it = 0; it < k_groups * g.kgroup; ++it)
+          tma_load_2d(base + it * b_chunk_bytes, &tmB, b_full_bar, (kg0 * g.kgroup + it) * g.bk, n_tile * g.BN);
       }
       int s = 0;
       uint32_t ph = 0;
@@ -552,7 +579,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int mt = blockIdx.x; mt < g.m_tiles; mt += gridDim.x) {
         int x0, y0, n0;
         tile_origin(mt, x0, y0, n0);
-        int tap = 0, kc = 0;
+        int tap = (kg0 * g.kgroup) / g.kchunks, kc = (kg0 * g.kgroup) % g.kchunks;
         for (int grp = 0; grp < k_groups; ++grp) {
           { CNT_BEGIN(); mbar_wait(empty_bar(s), ph ^ 1u); CNT_END(c_wait_empty); }
           const uint32_t a_dst = stage_base + s * stage_bytes;
@@ -563,7 +590,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             tma_load_4d(a_dst + j * a_chunk_bytes, &tmA, full_bar(s), kc * g.bk, x0 + dx, y0 + dy, n0);
             if (!g.b_resident)
               tma_load_2d(a_dst + g.kgroup * a_chunk_bytes + j * b_chunk_bytes, &tmB, full_bar(s),
-                          (grp * g.kgroup + j) * g.bk, n_tile * g.BN);
+                          ((kg0 + grp) * g.kgroup + j) * g.bk, n_tile * g.BN);
             if (++kc == g.kchunks) { kc = 0; ++tap; }
           }
           if (++s == g.stages) { s = 0; ph ^= 1u; }
@@ -726,7 +753,7 @@ static int encode_act_map(CUtensorMap* map, const char* who, const char* what, c
 
 // stg_wanted: the epilogue can use TMA stores (needs 2 x 16 KB of staging shared memory)
 static int make_plan(Plan& p, const char* who, const void* act, int B, int H, int W, int act_ld, int cin_pad,
-                     const void* wgt, int n, int n_pad, int taps, int BN, bool stg_wanted) {
+                     const void* wgt, int n, int n_pad, int taps, int BN, bool stg_wanted, int k_split = 1) {
   RFK_REQUIRE(act && wgt && B > 0 && H > 0 && W > 0, "%s: null pointer or empty shape", who);
   RFK_REQUIRE(cin_pad > 0 && (cin_pad % 64 == 0 || cin_pad == 32) && cin_pad <= act_ld,
               "%s: cin_pad=%d must be 32 or a multiple of 64, and <= act_ld=%d", who, cin_pad, act_ld);
@@ -759,13 +786,16 @@ static int make_plan(Plan& p, const char* who, const void* act, int B, int H, in
   const int k_iters = taps * g.kchunks;
   // 64-byte-row chunks carry only two MMAs each: group three (a filter row) or two per pipeline stage
   g.kgroup = bk == 32 ? (k_iters % 3 == 0 ? 3 : (k_iters % 2 == 0 ? 2 : 1)) : 1;
+  RFK_REQUIRE(k_split >= 1 && (k_iters / g.kgroup) % k_split == 0, "%s: %d K stages do not split %d ways", who,
+              k_iters / g.kgroup, k_split);
+  g.kg_per_split = k_iters / g.kgroup / k_split;
   const int b_chunk = g.kgroup * BN * bk * 2;
   const int a_stage = g.kgroup * BM * bk * 2;
   const int fixed = 1024 /*alignment slack*/ + (stg_wanted ? 2 * STG_BYTES : 0) + 2 * BN * 4 + 8 * (2 * 8 + 5) + 16;
   g.use_stg = stg_wanted ? 1 : 0;
   int resident = 0, stages = 0;
   {
-    const long long res_bytes = (long long)k_iters * BN * bk * 2;
+    const long long res_bytes = (long long)(k_iters / k_split) * BN * bk * 2;
     const long long room = (long long)SMEM_LIMIT - fixed - res_bytes;
     if (room >= 3LL * a_stage) {
       resident = 1;
@@ -789,14 +819,14 @@ static int make_plan(Plan& p, const char* who, const void* act, int B, int H, in
   while (cols < 2 * BN) cols <<= 1;
   g.tmem_cols = cols;  // two accumulators
   const int stage_bytes = a_stage + (resident ? 0 : b_chunk);
-  p.smem = (size_t)1024 + (resident ? (size_t)k_iters * BN * bk * 2 : 0) + (size_t)stages * stage_bytes +
+  p.smem = (size_t)1024 + (resident ? (size_t)(k_iters / k_split) * BN * bk * 2 : 0) + (size_t)stages * stage_bytes +
            (stg_wanted ? 2 * STG_BYTES : 0) + 2 * BN * 4 + 8 * (2 * stages + 5) + 16;
   RFK_REQUIRE(p.smem <= (size_t)SMEM_LIMIT, "%s: internal error: %zu B of shared memory planned", who, p.smem);
-  int ctas_x = sm_count() / n_tiles;
+  int ctas_x = sm_count() / (n_tiles * k_split);
   if (ctas_x < 1) ctas_x = 1;
   if (ctas_x > g.m_tiles) ctas_x = g.m_tiles;
-  p.grid = dim3((unsigned)ctas_x, (unsigned)n_tiles);
-  g.timeline = (g_timeline && (long long)ctas_x * n_tiles <= g_timeline_cap) ? g_timeline : nullptr;
+  p.grid = dim3((unsigned)ctas_x, (unsigned)n_tiles, (unsigned)k_split);
+  g.timeline = (g_timeline && (long long)ctas_x * n_tiles * k_split <= g_timeline_cap) ? g_timeline : nullptr;
   g.scale = nullptr; g.shift = nullptr; g.n_ss = 0;
 
   int rc = encode_act_map(&p.tmA, who, "A", act, cin_pad, act_ld, B, H, W, p.TW, p.TH, p.NIMG, bk);
@@ -933,6 +963,20 @@ extern "C" int rfk_conv_gemm_coupling(const void* act, int B, int H, int W, int 
   CouplingEpi e;
   e.z = z; e.clamp_type = clamp_type; e.cs = clamp_scale; e.csh = clamp_shift; e.logdet = logdet; e.reverse = reverse;
   return launch(p, e, (cudaStream_t)stream, "rfk_conv_gemm_coupling");
+}
+
+extern "C" int rfk_conv_gemm_splitk(const void* act, int B, int H, int W, int act_ld, int cin_pad, const void* wgt, int n,
+                                    int n_pad, int taps, int k_split, float* ws, int ws_ld, void* stream) {
+  RFK_REQUIRE(ws && ws_ld >= n_pad && ws_ld % 4 == 0 && (reinterpret_cast<uintptr_t>(ws) & 15) == 0,
+              "rfk_conv_gemm_splitk: workspace must be 16-byte aligned with ws_ld >= n_pad, ws_ld %% 4 == 0");
+  RFK_REQUIRE(n_pad > 0 && n_pad % 16 == 0, "rfk_conv_gemm_splitk: n_pad=%d must be a positive multiple of 16", n_pad);
+  Plan p;
+  int rc = make_plan(p, "rfk_conv_gemm_splitk", act, B, H, W, act_ld, cin_pad, wgt, n, n_pad, taps, pick_bn(n_pad, 16, 1 << 20),
+                     false, k_split);
+  if (rc) return rc;
+  SplitKEpi e;
+  e.ws = ws; e.ld = ws_ld;
+  return launch(p, e, (cudaStream_t)stream, "rfk_conv_gemm_splitk");
 }
 
 extern "C" int rfk_conv_gemm_lstm(const void* act, int B, int H, int W, int act_ld, int cin_pad, const void* wgt,

@@ -477,6 +477,37 @@ __global__ void __launch_bounds__(kThreads) lstm_pointwise_kernel(const float* _
   }
 }
 
+// ConvLSTM cell update from a pixel-major fp32 gate buffer (the split-K GEMM's workspace): cc[(b*HW+p)*ld + g*Hc + ch],
+// gate order i,f,o,g, + bias; optionally clears the workspace behind itself so the next step starts from zero, and
+// hands h to the next step as bf16 NHWC.
+__global__ void __launch_bounds__(kThreads) lstm_pointwise_ws_kernel(float* __restrict__ cc, int cc_ld,
+                                                                     const float* __restrict__ bias,
+                                                                     const float* __restrict__ c_prev, long long c_prev_bs,
+                                                                     const float* __restrict__ peep,
+                                                                     float* __restrict__ h_out, long long h_bs,
+                                                                     float* __restrict__ c_next, long long c_next_bs,
+                                                                     __nv_bfloat16* __restrict__ h_nhwc, int h_off, int h_ld,
+                                                                     int Hc, int HW, int zero_cc, long long total) {
+  const long long per = (long long)Hc * HW;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const long long b = t / per, r = t % per;
+    const int ch = (int)(r / HW), p = (int)(r % HW);
+    float* g0 = cc + (b * HW + p) * cc_ld + ch;
+    float ci = g0[0], cf = g0[Hc], co = g0[2 * Hc], cg = g0[3 * Hc];
+    if (zero_cc) { g0[0] = 0.0f; g0[Hc] = 0.0f; g0[2 * Hc] = 0.0f; g0[3 * Hc] = 0.0f; }
+    if (bias) { ci += bias[ch]; cf += bias[Hc + ch]; co += bias[2 * Hc + ch]; cg += bias[3 * Hc + ch]; }
+    const float c = c_prev ? c_prev[b * c_prev_bs + r] : 0.0f;
+    float wi = 0, wf = 0, wo = 0;
+    if (peep) { wi = peep[r]; wf = peep[per + r]; wo = peep[2 * per + r]; }
+    float h, cn;
+    lstm_point(ci, cf, co, cg, c, wi, wf, wo, h, cn);
+    h_out[b * h_bs + r] = h;
+    c_next[b * c_next_bs + r] = cn;
+    if (h_nhwc) h_nhwc[(b * HW + p) * h_ld + h_off + ch] = __float2bfloat16(h);
+  }
+}
+
 __global__ void add_scalar_kernel(float* __restrict__ logdet, const float* __restrict__ addend, float alpha, int B) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < B) logdet[i] += alpha * (*addend);
@@ -678,6 +709,20 @@ extern "C" int rfk_convlstm_pointwise(const float* cc, const float* c_prev, cons
     lstm_pointwise_kernel<false><<<stream_grid(total, kThreads, 8), kThreads, 0, st>>>(cc, c_prev, peep, h_out,
                                                                                        c_next, Hc, HW, total);
   return check_launch("rfk_convlstm_pointwise");
+}
+
+extern "C" int rfk_convlstm_pointwise_ws(float* cc, int cc_ld, const float* bias, const float* c_prev,
+                                         long long c_prev_bstride, const float* peep, float* h_out, long long h_bstride,
+                                         float* c_next, long long c_next_bstride, void* h_nhwc, int h_off, int h_ld,
+                                         int B, int Hc, int HW, int zero_cc, void* stream) {
+  RFK_REQUIRE(cc && h_out && c_next && B > 0 && Hc > 0 && HW > 0 && cc_ld >= 4 * Hc,
+              "rfk_convlstm_pointwise_ws: null pointer, empty shape or cc_ld < 4*Hc");
+  if (h_nhwc) RFK_REQUIRE(h_off >= 0 && h_off + Hc <= h_ld, "rfk_convlstm_pointwise_ws: h window exceeds h_ld");
+  long long total = (long long)B * Hc * HW;
+  lstm_pointwise_ws_kernel<<<stream_grid(total, kThreads, 8), kThreads, 0, (cudaStream_t)stream>>>(
+      cc, cc_ld, bias, c_prev, c_prev_bstride, peep, h_out, h_bstride, c_next, c_next_bstride, (__nv_bfloat16*)h_nhwc, h_off,
+      h_ld, Hc, HW, zero_cc, total);
+  return check_launch("rfk_convlstm_pointwise_ws");
 }
 
 extern "C" int rfk_add_scalar(float* logdet, const float* addend, float alpha, int B, void* stream) {

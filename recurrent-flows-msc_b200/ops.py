@@ -144,6 +144,24 @@ def conv_gemm_lstm(act, cin_pad, wgt, hidden, ht, ht_pad, taps, bias, c_prev, pe
          meta=_gemm_meta(B * H * W, 4 * hidden, taps, cin_pad, wgt))
 
 
+def conv_gemm_splitk(act, cin_pad, wgt, n, taps, k_split, ws):
+    """Partial sums of k_split K slices added into the zeroed fp32 workspace ws [B*H*W, ld]."""
+    _chk(act, torch.bfloat16, "act")
+    _chk(ws, name="ws")
+    B, H, W, ld = act.shape
+    call("rfk_conv_gemm_splitk", act.data_ptr(), B, H, W, ld, cin_pad, _chk(wgt, torch.bfloat16).data_ptr(), n,
+         wgt.shape[0], taps, k_split, ws.data_ptr(), ws.shape[-1], _stream(),
+         meta=_gemm_meta(B * H * W, n, taps, cin_pad, wgt))
+
+
+def convlstm_pointwise_ws(cc, bias, c_prev, peep, h_out, c_next, h_nhwc, h_off, zero_cc=True):
+    B, Hc, H, W = c_next.shape
+    call("rfk_convlstm_pointwise_ws", _chk(cc).data_ptr(), cc.shape[-1], _p(bias), _p(c_prev),
+         c_prev.stride(0) if c_prev is not None else 0, _p(peep), h_out.data_ptr(), h_out.stride(0), c_next.data_ptr(),
+         c_next.stride(0), _p(h_nhwc), h_off, h_nhwc.shape[-1] if h_nhwc is not None else 0, B, Hc, H * W,
+         int(zero_cc), _stream())
+
+
 def coupling_tail(nn_out, z, clamp_type, clamp_scale, clamp_shift, logdet, reverse):
     _chk(nn_out, name="nn_out")
     _chk(z, name="z")

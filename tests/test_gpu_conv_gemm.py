@@ -108,7 +108,7 @@ def test_conv_gemm_coupling(ops, clamp, B, C, H, W):
     assert float(ld.abs().max()) < 1e-3
 
 
-@pytest.mark.parametrize("B,Cin,Hc,H,W", [(2, 3, 4, 5, 6), (2, 64, 64, 16, 16), (3, 20, 60, 8, 8), (4, 40, 200, 2, 2)])
+@pytest.mark.parametrize("B,Cin,Hc,H,W", [(2, 3, 4, 5, 6), (2, 64, 64, 16, 16), (3, 20, 60, 8, 8), (4, 40, 200, 2, 2), (30, 512, 200, 2, 2), (5, 300, 24, 3, 3)])
 def test_conv_gemm_lstm(ops, B, Cin, Hc, H, W):
     import recurrent_flows_msc_b200 as r
     g = torch.Generator().manual_seed(Hc)

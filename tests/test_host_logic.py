@@ -78,11 +78,14 @@ def test_pack_conv_weight_layout(k):
     torch.testing.assert_close(im2col_gemm(x[:, perm], wp2, cin_pad, 7, k), F.conv2d(x, w, None, 1, (k - 1) // 2), rtol=1e-4, atol=1e-4)
 
 
+@pytest.mark.parametrize("m_tiles", [1, 1 << 30])
 @pytest.mark.parametrize("hidden", [4, 60, 64, 200, 256])
-def test_lstm_gate_row_interleave(hidden):
+def test_lstm_gate_row_interleave(hidden, m_tiles):
     torch.manual_seed(2)
     cell = rf.ConvLSTMLayer(3, hidden, [3, 3], True)
-    wgt, cin_pad, b, ht, ht_pad = cell._weights()
+    wgt, cin_pad, b, ht, ht_pad = cell._weights(m_tiles)
+    if m_tiles == 1 and hidden == 200:
+        assert ht == 8          # RFN: 25 narrow tiles instead of 5 wide ones
     assert hidden % ht == 0 and 4 * ht_pad <= 256 and ht_pad % 8 == 0
     n_tiles = hidden // ht
     assert wgt.shape[0] == n_tiles * 4 * ht_pad
