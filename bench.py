@@ -183,14 +183,22 @@ class KernelTimer:
 
     def table(self):
         torch.cuda.synchronize()
-        agg = {}
+        agg, shapes = {}, {}
         for name, meta, a, b in self.rec:
+            ms = a.elapsed_time(b)
             d = agg.setdefault(name, {"launches": 0, "ms": 0.0, "flops": 0.0, "flops_padded": 0.0})
             d["launches"] += 1
-            d["ms"] += a.elapsed_time(b)
+            d["ms"] += ms
             if meta:
                 d["flops"] += meta["flops"]
                 d["flops_padded"] += meta["flops_padded"]
+                k = (name, meta["M"], meta["N"], meta["K"])
+                sdict = shapes.setdefault(k, {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
+                sdict["launches"] += 1
+                sdict["ms"] += ms
+                sdict["flops"] += meta["flops"]
+                sdict["bytes"] += meta["bytes"]
+        self.shapes = shapes
         return agg
 
 
@@ -206,6 +214,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # NCCL's version banner goes to stdout and would break the one-JSON-line contract
+        os.environ["NCCL_DEBUG"] = os.environ.get("RFK_NCCL_DEBUG", "WARN")
         dist.init_process_group("nccl", device_id=dev)
     B, T = J["B"], J["T"]
     n_frames = B * (T - 1)
@@ -307,6 +317,17 @@ def run_ours(args):
                     "share_of_step": d["ms"] / total_ms, "launches_per_step": d["launches"],
                     "avg_launch_us": 1e3 * d["ms"] / d["launches"],
                     "issued_tflops_incl_padding": d["flops_padded"] / (d["ms"] / 1e3) / 1e12}
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        by_shape = []
+        for (name, M, N, K), v in sorted(kt.shapes.items(), key=lambda kv: -kv[1]["ms"])[:6]:
+            sec = v["ms"] / 1e3
+            by_shape.append({"kernel": name, "M": M, "N": N, "K": K, "launches": v["launches"],
+                             "avg_us": round(1e3 * v["ms"] / v["launches"], 1),
+                             "tflops": round(v["flops"] / sec / 1e12, 1), "tensor_frac": round(v["flops"] / sec / 1e12 / peak_tf, 3),
+                             "algorithmic_gbs": round(v["bytes"] / sec / 1e9, 1), "hbm_frac": round(v["bytes"] / sec / 1e9 / hbm_peak, 3)})
+        roofline["by_shape"] = by_shape
+        roofline["note"] = ("N <= 256 unfused conv layers sit below the ridge (AI ~ 128 flop/B): the big launches are HBM-bound, "
+                            "see by_shape[].hbm_frac (algorithmic bytes = activations in + out + weights, bf16)")
         kernels = {k: {"launches": v["launches"], "ms": round(v["ms"], 4),
                        "tflops": round(v["flops"] / (v["ms"] / 1e3) / 1e12, 1) if v["flops"] else None}
                    for k, v in sorted(table.items(), key=lambda kv: -kv[1]["ms"])}

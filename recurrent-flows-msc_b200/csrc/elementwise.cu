@@ -366,6 +366,66 @@ __global__ void __launch_bounds__(kThreads) coupling_taps_kernel(const float* __
   if (logdet) cta_atomic_add(reverse ? -acc : acc, logdet + b, sh);
 }
 
+// Same, four consecutive pixels of a row per thread (W % 4 == 0): per tap plane one aligned 128-bit load plus, for the
+// horizontally shifted taps, one scalar edge element.
+__global__ void __launch_bounds__(kThreads) coupling_taps_v4_kernel(const float* __restrict__ taps, float* __restrict__ z,
+                                                                   int C, int H, int W, const float* __restrict__ scale,
+                                                                   const float* __restrict__ shift, int clamp_type,
+                                                                   const float* __restrict__ cs,
+                                                                   const float* __restrict__ csh,
+                                                                   float* __restrict__ logdet, int reverse) {
+  __shared__ float sh[32];
+  const int b = blockIdx.y, half = C >> 1, HW = H * W, W4 = W >> 2;
+  const long long per4 = (long long)half * H * W4;
+  const float* tb = taps + (long long)b * 9 * C * HW;
+  float* zb = z + ((long long)b * C + half) * HW;
+  float acc = 0.0f;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < per4;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int x4 = (int)(t % W4);
+    const long long r = t / W4;
+    const int y = (int)(r % H), j = (int)(r / H);
+    const int x = x4 << 2;
+    float s_sum[4] = {0, 0, 0, 0}, r_sum[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int yy = y + ky - 1;
+      if (yy < 0 || yy >= H) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const float* q = tb + ((long long)((3 * ky + kx) * C + 2 * j) * HW) + yy * W + x;
+#pragma unroll
+        for (int pr = 0; pr < 2; ++pr) {  // shift plane, raw plane
+          const float* qq = q + pr * HW;
+          const float4 c4 = __ldg(reinterpret_cast<const float4*>(qq));
+          float v0, v1, v2, v3;
+          if (kx == 1) { v0 = c4.x; v1 = c4.y; v2 = c4.z; v3 = c4.w; }
+          else if (kx == 0) { v0 = x > 0 ? __ldg(qq - 1) : 0.0f; v1 = c4.x; v2 = c4.y; v3 = c4.z; }
+          else { v0 = c4.y; v1 = c4.z; v2 = c4.w; v3 = x + 4 < W ? __ldg(qq + 4) : 0.0f; }
+          float* dst = pr ? r_sum : s_sum;
+          dst[0] += v0; dst[1] += v1; dst[2] += v2; dst[3] += v3;
+        }
+      }
+    }
+    const float sc_s = __ldg(scale + 2 * j), sh_s = __ldg(shift + 2 * j);
+    const float sc_r = __ldg(scale + 2 * j + 1), sh_r = __ldg(shift + 2 * j + 1);
+    float a = 0.0f, bb = 0.0f;
+    if (clamp_type == RFK_CLAMP_REALNVP) { a = __ldg(cs + j); bb = __ldg(csh + j); }
+    float4* zp = reinterpret_cast<float4*>(zb + ((long long)j * H + y) * W + x);
+    const float4 zv = *zp;
+    float zi[4] = {zv.x, zv.y, zv.z, zv.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float sft = fmaf(s_sum[k], sc_s, sh_s);
+      const float ls = clamp_ls(fmaf(r_sum[k], sc_r, sh_r), clamp_type, a, bb);
+      acc += ls;
+      zi[k] = reverse ? zi[k] * expf(-ls) - sft : (zi[k] + sft) * expf(ls);
+    }
+    *zp = make_float4(zi[0], zi[1], zi[2], zi[3]);
+  }
+  if (logdet) cta_atomic_add(reverse ? -acc : acc, logdet + b, sh);
+}
+
 // ------------------------------------------------------------------------------------------
 // a5/a7  Gaussian log-density / sampling.  grid = (chunks, B)
 // ------------------------------------------------------------------------------------------
@@ -515,6 +575,58 @@ __global__ void add_scalar_kernel(float* __restrict__ logdet, const float* __res
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+// Small channel counts (C <= 8): no shared memory, one thread per 4 consecutive pixels, x and y in registers.
+template <int CT>
+__global__ void __launch_bounds__(kThreads) mix1x1_small_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                                const float* __restrict__ Wm,
+                                                                const float* __restrict__ bvec, int C, int HW,
+                                                                long long nquad, __nv_bfloat16* __restrict__ side,
+                                                                int side_n, int side_off, int side_ld,
+                                                                float* __restrict__ logdet,
+                                                                const float* __restrict__ addend, float alpha, int B) {
+  __shared__ float ws[CT * CT + CT];
+  for (int i = threadIdx.x; i < CT * CT + CT; i += blockDim.x) {
+    float v = 0.0f;
+    if (i < CT * CT) { int o = i / CT, c = i % CT; if (o < C && c < C) v = Wm[o * C + c]; }
+    else { int o = i - CT * CT; if (bvec && o < C) v = bvec[o]; }
+    ws[i] = v;
+  }
+  if (logdet && blockIdx.x == 0) {
+    const float add = alpha * (*addend);
+    for (int i = threadIdx.x; i < B; i += blockDim.x) logdet[i] += add;
+  }
+  __syncthreads();
+  const int HW4 = HW >> 2;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < nquad;
+       t += (long long)gridDim.x * blockDim.x) {
+    const long long b = t / HW4;
+    const int p = (int)(t % HW4) << 2;
+    const float* xp = x + b * C * HW + p;
+    float4 xi[CT];
+#pragma unroll
+    for (int i = 0; i < CT; ++i) xi[i] = i < C ? ld_stream(reinterpret_cast<const float4*>(xp + (long long)i * HW)) : make_float4(0, 0, 0, 0);
+    float* yp = y + b * C * HW + p;
+    const long long pix = b * HW + p;
+#pragma unroll
+    for (int o = 0; o < CT; ++o) {
+      if (o < C) {
+        const float bo = ws[CT * CT + o];
+        float4 a = make_float4(bo, bo, bo, bo);
+#pragma unroll
+        for (int i = 0; i < CT; ++i) {
+          const float w = ws[o * CT + i];
+          a.x = fmaf(w, xi[i].x, a.x); a.y = fmaf(w, xi[i].y, a.y); a.z = fmaf(w, xi[i].z, a.z); a.w = fmaf(w, xi[i].w, a.w);
+        }
+        st_stream(reinterpret_cast<float4*>(yp + (long long)o * HW), a);
+        if (side && o < side_n) {
+          __nv_bfloat16* sp = side + pix * side_ld + side_off + o;
+          sp[0] = __float2bfloat16(a.x); sp[side_ld] = __float2bfloat16(a.y);
+          sp[2 * side_ld] = __float2bfloat16(a.z); sp[3 * side_ld] = __float2bfloat16(a.w);
+        }
+      }
+    }
+  }
+}
 }  // namespace rfk
 
 using namespace rfk;
@@ -573,6 +685,19 @@ extern "C" int rfk_mix1x1(const float* x, float* y, const float* Wm, const float
   RFK_REQUIRE(x && y && Wm && B > 0 && C > 0 && HW > 0, "rfk_mix1x1: null pointer or empty shape");
   RFK_REQUIRE(x != y, "rfk_mix1x1: in-place is not supported");
   RFK_REQUIRE(!logdet || addend, "rfk_mix1x1: logdet given without an addend");
+  if (side) RFK_REQUIRE(side_n >= 0 && side_n <= C && side_off >= 0 && side_off + side_n <= side_ld,
+                        "rfk_mix1x1: bad side-output window");
+  if (C <= 8 && HW % 4 == 0 && aligned16(x) && aligned16(y)) {
+    const long long nquad = (long long)B * HW / 4;
+    const int grid = stream_grid(nquad, kThreads, 8);
+    if (C <= 4)
+      mix1x1_small_kernel<4><<<grid, kThreads, 0, (cudaStream_t)stream>>>(x, y, Wm, bvec, C, HW, nquad, (__nv_bfloat16*)side,
+                                                                          side ? side_n : 0, side_off, side_ld, logdet, addend, alpha, B);
+    else
+      mix1x1_small_kernel<8><<<grid, kThreads, 0, (cudaStream_t)stream>>>(x, y, Wm, bvec, C, HW, nquad, (__nv_bfloat16*)side,
+                                                                          side ? side_n : 0, side_off, side_ld, logdet, addend, alpha, B);
+    return check_launch("rfk_mix1x1");
+  }
   const int G = (C + 7) / 8;
   RFK_REQUIRE(G <= 32, "rfk_mix1x1: C=%d is too large (max 256)", C);
   int PT = (256 / G) / 32 * 32;
@@ -659,11 +784,16 @@ extern "C" int rfk_coupling_tail_taps(const float* taps, float* z, int B, int C,
   RFK_REQUIRE(clamp_type != RFK_CLAMP_REALNVP || (clamp_scale && clamp_shift),
               "rfk_coupling_tail_taps: realnvp clamp needs scale and scale_shift");
   long long per = (long long)(C / 2) * H * W;
-  int chunks = ceil_div(per, kThreads);
+  const bool v4 = W % 4 == 0 && aligned16(taps) && aligned16(z);
+  int chunks = ceil_div(v4 ? per / 4 : per, kThreads);
   int cap = ceil_div((long long)sm_count() * 8, B);
   if (chunks > cap) chunks = cap;
-  coupling_taps_kernel<<<dim3(chunks, B), kThreads, 0, (cudaStream_t)stream>>>(
-      taps, z, C, H, W, scale, shift, clamp_type, clamp_scale, clamp_shift, logdet, reverse);
+  if (v4)
+    coupling_taps_v4_kernel<<<dim3(chunks, B), kThreads, 0, (cudaStream_t)stream>>>(
+        taps, z, C, H, W, scale, shift, clamp_type, clamp_scale, clamp_shift, logdet, reverse);
+  else
+    coupling_taps_kernel<<<dim3(chunks, B), kThreads, 0, (cudaStream_t)stream>>>(
+        taps, z, C, H, W, scale, shift, clamp_type, clamp_scale, clamp_shift, logdet, reverse);
   return check_launch("rfk_coupling_tail_taps");
 }
 

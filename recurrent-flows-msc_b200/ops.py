@@ -104,7 +104,10 @@ def _gemm_meta(M, n, taps, cin_pad, wgt):
     """Algorithmic (unpadded) and issued (padded) FLOPs of one implicit-GEMM launch, for bench.py's roofline."""
     cin = getattr(wgt, "rfk_cin", cin_pad)
     return {"flops": 2.0 * M * n * taps * cin, "flops_padded": 2.0 * M * wgt.shape[0] * taps * cin_pad,
-            "M": M, "N": n, "K": taps * cin}
+            "M": M, "N": n, "K": taps * cin,
+            # algorithmic HBM bytes: activations read once (bf16, padded row), output written once as bf16
+            # (f32 outputs of the small-N launches are counted as 4 B), weights once
+            "bytes": 2.0 * M * cin_pad + (2.0 if n >= 128 else 4.0) * M * n + 2.0 * wgt.numel()}
 
 
 def conv_gemm(act, cin_pad, wgt, n, taps, scale, shift, act_fn, out, out_off=0):
