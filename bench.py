@@ -249,15 +249,26 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     resident = upload()
+    eager_hot_path = hot_path
     for _ in range(max(args.warmup, 3)):
         nll, _ = hot_path(*resident)
     torch.cuda.synchronize()
     assert torch.isfinite(nll).all(), "non-finite nll in warm-up"
+    launches_per_step = rf._lib.launches
+    eager_hot_path(*resident)
+    launches_per_step = rf._lib.launches - launches_per_step
+    if not args.no_graph:
+        # the same launches, replayed from a CUDA graph: removes ~20 us of Python/ctypes per launch from the host side
+        graphed = rf.Graphed(lambda x, c, b, f: eager_hot_path(x, c, b, f), resident[0], resident[1], resident[2], resident[3])
+        hot_path = lambda x, c, b, f: graphed(x, c, b, f)  # noqa: E731
+        for _ in range(3):
+            nll, _ = hot_path(*resident)
+        torch.cuda.synchronize()
+        assert torch.isfinite(nll).all(), "non-finite nll in graph replay"
 
     sampler = ClockSampler(local) if rank == 0 else None
     # ---- device-resident timing ---------------------------------------------------------------
     barrier()
-    l0 = rf._lib.launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.time()
     ev0.record()
@@ -266,21 +277,57 @@ def run_ours(args):
     ev1.record()
     barrier()
     t_wall1 = time.time()
-    launches = rf._lib.launches - l0
+    launches = launches_per_step * args.steps   # graph replays do not pass through the ctypes counter
     ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
     # ---- end-to-end from pinned host buffers ------------------------------------------------------
+    def e2e_step():
+        if args.no_graph:
+            return hot_path(*upload())
+        hx_, hbase_, hfeats_, *hconds_ = host      # pinned host -> the graph's static device buffers -> replay
+        return hot_path(hx_, hconds_, hbase_, hfeats_)
+
     for _ in range(2):
-        nll, h_last = hot_path(*upload())
+        nll, h_last = e2e_step()
     barrier()
     ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev2.record()
     for _ in range(args.steps):
-        nll, h_last = hot_path(*upload())
+        nll, h_last = e2e_step()
         nll_host.copy_(nll, non_blocking=True)
         h_host.copy_(h_last, non_blocking=True)
     ev3.record()
     barrier()
     ms_e2e = torch.tensor([ev2.elapsed_time(ev3)], device=dev)
+    # ---- sampling direction (RFN.predict's inner step): ConvLSTM cell + ListGlow.sample for B sequences -------
+    sconds = [c[:B].contiguous() for c in resident[1]]
+    sbase = resident[2][:B].contiguous()
+    sfeat = resident[3][:, :1].contiguous()
+
+    def sample_step_eager():
+        with torch.no_grad():
+            lstm(sfeat)
+            return flow.sample(None, sconds, sbase, num_samples=B, temperature=0.7)
+
+    def time_loop(fn, n):
+        for _ in range(3):
+            fn()
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n):
+            fn()
+        b.record()
+        barrier()
+        t = torch.tensor([a.elapsed_time(b) / n], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+
+    n_samp = max(args.steps, 10)
+    ms_sample = time_loop(sample_step_eager, n_samp)
+    gsample = rf.GraphedSample(flow, sconds, sbase, temperature=0.7)
+    ms_sample_graph = time_loop(lambda: gsample(sconds, sbase), n_samp)
+    assert torch.isfinite(gsample(sconds, sbase)).all()
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(ms_e2e, op=dist.ReduceOp.MAX)
@@ -300,7 +347,7 @@ def run_ours(args):
         kt = KernelTimer()
         rf._lib.tracer = kt
         torch.cuda.profiler.start()   # `ncu --profile-from-start off` captures exactly this one step
-        hot_path(*resident)
+        eager_hot_path(*resident)
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
         rf._lib.tracer = None
@@ -342,9 +389,14 @@ def run_ours(args):
                        "frames_per_step_per_gpu": n_frames, "sequences_per_gpu": B, "L": J["L"], "K": J["K"],
                        "hidden": J["hidden"], "conv_dtype": "bf16 in / fp32 accumulate", "flow_dtype": "f32",
                        "l2": "inputs_exceed_L2 (>=300 MB of activations per level-1 GlowStep vs 126 MB L2)",
-                       "parallelism": f"batch-sharded x{world}, no data-path collective"},
+                       "parallelism": f"batch-sharded x{world}, no data-path collective",
+                       "launch": "eager (Python/ctypes per launch)" if args.no_graph else "CUDA graph replay of the same launches"},
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "ms_per_step": ms_step_e2e},
+            "sampling": {"what": "one RFN.predict inner step: ListGlow.sample (reverse flow, T=0.7) for 30 sequences "
+                                 "(+ ConvLSTM cell in the eager figure); autoregressive, so only the batch is parallel",
+                         "eager_frames_per_s": world * B / (ms_sample / 1e3), "eager_ms": ms_sample,
+                         "cuda_graph_frames_per_s": world * B / (ms_sample_graph / 1e3), "cuda_graph_ms": ms_sample_graph},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernels_ms_per_step": kernels,
             "cpu_baseline": {"value": cpu_fps, "unit": "frames/s", "cores": cores, "kind": "port",
                              "sample": f"{n_cpu} frames: oracle ListGlow.log_prob (config J) + 1 ConvLSTM step at batch {n_cpu}, "
@@ -361,6 +413,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-graph", action="store_true", help="enqueue every launch from Python instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
