@@ -146,6 +146,17 @@ int rfk_conv_gemm_splitk(const void* act, int B, int H, int W, int act_ld, int c
                          const void* wgt, int n, int n_pad, int taps, int k_split,
                          float* ws, int ws_ld, void* stream);
 
+/* Split-K with the reduction fused in: like rfk_conv_gemm (NHWC bf16 output, per-channel affine + activation), but K
+ * is cut into k_split slices that run on different SMs; partial tiles are added into the zeroed fp32 workspace, and
+ * the CTA that contributes the last slice of a tile (per-tile counter, zero before the launch) reads the sums back,
+ * applies the epilogue, writes the bf16 tile and leaves workspace and counter zeroed again.  For layers whose pixel
+ * tiles alone cannot fill the GPU (levels 4-5 of the flow; every level when sampling a few sequences). */
+int rfk_conv_gemm_splitk_fused(const void* act, int B, int H, int W, int act_ld, int cin_pad,
+                               const void* wgt, int n, int n_pad, int taps, int k_split,
+                               float* ws, int ws_ld, unsigned int* counters,
+                               const float* scale, const float* shift, int act_fn,
+                               void* out, int out_ld, int out_off, void* stream);
+
 /* ---- a3  coupling tail, standalone (Flow/glow_modules.py:275-290) -------------------------
  * nn_out [B,C,H,W] f32 = output of the coupling network; z as in rfk_conv_gemm_coupling. */
 int rfk_coupling_tail(const float* nn_out, float* z, int B, int C, int HW,

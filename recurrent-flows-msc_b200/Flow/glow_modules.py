@@ -213,6 +213,12 @@ class Conv2dNorm(nn.Module):
                 an.initialize(raw)
             an.mark_initialized()
         scale, shift = an.affine()
+        if out.dtype == torch.bfloat16:
+            B, H, W, _ = act.shape
+            k_split = ops.choose_k_split(B * H * W, self.taps, cin_pad)
+            if k_split > 1:   # few pixel tiles, long K: spread K over the SMs (reduction fused into the kernel)
+                return ops.conv_gemm_splitk_fused(act, cin_pad, wgt, n, self.taps, k_split, scale, shift, act_fn, out,
+                                                  out_off)
         return ops.conv_gemm(act, cin_pad, wgt, n, self.taps, scale, shift, act_fn, out, out_off)
 
     def forward(self, input):

@@ -36,6 +36,8 @@ SIGNATURES = {
     "rfk_gauss_sample": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_int, c_int,
                          c_void_p],
     "rfk_convlstm_pointwise": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
+    "rfk_conv_gemm_splitk_fused": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int,
+                                   c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p],
     "rfk_conv_gemm_splitk": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int,
                              c_void_p, c_int, c_void_p],
     "rfk_convlstm_pointwise_ws": [c_void_p, c_int, c_void_p, c_void_p, c_longlong, c_void_p, c_void_p, c_longlong,

@@ -26,6 +26,15 @@ int sm_count() {
   return n;
 }
 
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("RFK_PDL");
+    v = (e && atoi(e) != 0) ? 1 : 0;   // opt-in: measured neutral on B200 for this workload
+  }
+  return v == 1;
+}
+
 }  // namespace rfk
 
 extern "C" int rfk_version(void) { return RFK_VERSION; }

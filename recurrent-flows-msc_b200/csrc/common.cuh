@@ -30,6 +30,25 @@ inline int check_launch(const char* what) {
   } while (0)
 
 int sm_count();
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                 Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#define RFK_LAUNCH(kernel, grid, block, smem, stream, ...) \
+  rfk::launch_kernel(kernel, dim3(grid), dim3(block), smem, stream, __VA_ARGS__)
 
 inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
@@ -40,6 +59,13 @@ inline int stream_grid(long long work_items, int threads, int ctas_per_sm) {
   if (need <= wave) return (int)(need > 0 ? need : 1);
   return (int)wave;
 }
+
+// Programmatic dependent launch (PDL).  Every kernel of this library is launched with the programmatic-stream-
+// serialization attribute, calls pdl_wait() before it reads anything a preceding kernel may have written, and calls
+// pdl_trigger() early so that the next kernel in the stream can be scheduled and run its own prologue (barrier init,
+// TMEM allocation, weight prefetch) while this one is still working.  Opt-in with RFK_PDL=1 (plain launches otherwise).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -80,6 +80,13 @@ struct CouplingEpi {
 struct SplitKEpi {   // partial sums of a K slice: ws[pixel, col] += acc  (fp32, pixel-major, vector red)
   float* ws;
   int ld;
+  // optional in-kernel fix-up: the CTA that adds the LAST slice of a tile reads the sums back, applies the affine +
+  // activation, writes bf16 NHWC and clears workspace and counter (so no separate reduction launch is needed)
+  unsigned int* counters;   // one per (n_tile, m_tile), zero before the launch; null = partial sums only
+  int k_split;
+  int act_fn;
+  __nv_bfloat16* out;
+  int out_ld, out_off, vec_ok;
 };
 
 struct LstmEpi {
@@ -250,6 +257,8 @@ struct TileCtx {
   uint32_t stg;     // this half's staging buffer (shared-space address), 0 when not allocated
   uint32_t tmem_empty_bar;
   long long* dbg;   // 5 per-phase cycle counters of the TMA-store epilogue, or null
+  int tile_id;      // n_tile * m_tiles + m_tile (split-K fix-up counter index)
+  volatile unsigned int* flag;  // one shared-memory word for epilogue-wide broadcasts
 };
 
 __device__ __forceinline__ void release_accumulator(const TileCtx& t) {
@@ -410,7 +419,7 @@ __device__ __forceinline__ void epilogue(const GemmArgs& g, const CouplingEpi& e
 }
 
 __device__ __forceinline__ void epilogue(const GemmArgs& g, const SplitKEpi& e, const CUtensorMap*, uint32_t taddr,
-                                         const float*, const TileCtx& t) {
+                                         const float* ss, const TileCtx& t) {
   const long long pix = ((long long)t.b * g.H + t.y) * g.W + t.x;
   for (int c0 = 16 * t.half; c0 < g.BN; c0 += 32) {
     uint32_t r[16];
@@ -426,6 +435,47 @@ __device__ __forceinline__ void epilogue(const GemmArgs& g, const SplitKEpi& e, 
                    : "memory");
   }
   release_accumulator(t);
+  if (!e.counters) return;
+  // ---- fix-up by the last-arriving slice (all 256 epilogue threads take part in the hand-shake)
+  __threadfence();
+  named_bar(3, kEpiWarps * 32);
+  volatile unsigned int* flag = t.flag;
+  if (t.q == 0 && t.half == 0 && (threadIdx.x & 31) == 0) *flag = atomicAdd(e.counters + t.tile_id, 1u);
+  named_bar(3, kEpiWarps * 32);
+  const bool last = *flag == (unsigned)(e.k_split - 1);
+  named_bar(3, kEpiWarps * 32);   // everyone has read the flag before the next tile may overwrite it
+  if (!last) return;
+  __threadfence();
+  if (t.valid) {
+    for (int c0 = 16 * t.half; c0 < g.BN; c0 += 32) {
+      const int col0 = t.n_tile * g.BN + c0;
+      if (col0 >= g.n) break;
+      float4* src = reinterpret_cast<float4*>(e.ws + pix * e.ld + col0);
+      float v[16];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float4 a = __ldcg(src + k);
+        src[k] = make_float4(0.f, 0.f, 0.f, 0.f);   // leave the workspace clean for the next launch
+        v[4 * k] = a.x; v[4 * k + 1] = a.y; v[4 * k + 2] = a.z; v[4 * k + 3] = a.w;
+      }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = apply_act(fmaf(v[j], ss[c0 + j], ss[g.BN + c0 + j]), e.act_fn);
+      __nv_bfloat16* dst = e.out + pix * e.out_ld + e.out_off + col0;
+#pragma unroll
+      for (int h8 = 0; h8 < 2; ++h8) {
+        if (e.vec_ok && col0 + 8 * h8 + 8 <= g.n) {
+          *reinterpret_cast<uint4*>(dst + 8 * h8) =
+              make_uint4(pack_bf16(v[8 * h8], v[8 * h8 + 1]), pack_bf16(v[8 * h8 + 2], v[8 * h8 + 3]),
+                         pack_bf16(v[8 * h8 + 4], v[8 * h8 + 5]), pack_bf16(v[8 * h8 + 6], v[8 * h8 + 7]));
+        } else {
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            if (col0 + 8 * h8 + k < g.n) dst[8 * h8 + k] = __float2bfloat16(v[8 * h8 + k]);
+        }
+      }
+    }
+  }
+  if (t.q == 0 && t.half == 0 && (threadIdx.x & 31) == 0) e.counters[t.tile_id] = 0u;
 }
 
 __device__ __forceinline__ void epilogue(const GemmArgs& g, const LstmEpi& e, const CUtensorMap*, uint32_t taddr,
@@ -542,6 +592,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  // Programmatic dependent launch: everything above touched only this CTA's own shared memory / TMEM.  The weights
+  // are parameters (never written by the preceding kernel), so their TMA loads also go out before the dependency wait.
+  if (warp == 0 && lane == 0 && g.b_resident) {
+    mbar_expect_tx(b_full_bar, b_res_bytes);
+    for (int it = 0; it < k_groups * g.kgroup; ++it)
+      tma_load_2d(base + it * b_chunk_bytes, &tmB, b_full_bar, (kg0 * g.kgroup + it) * g.bk, n_tile * g.BN);
+  }
+  pdl_trigger();   // the next kernel in the stream may start its own prologue
+  pdl_wait();      // from here on we read what the preceding kernel produced
   // per-channel scale / shift of this CTA's output-channel slice -> shared memory
   for (int i = threadIdx.x; i < g.BN; i += blockDim.x) {
     const int col = n_tile * g.BN + i;
@@ -568,11 +627,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
-      if (g.b_resident) {
-        mbar_expect_tx(b_full_bar, b_res_bytes);
-        for (int it = 0; it < k_groups * g.kgroup; ++it)
-          tma_load_2d(base + it * b_chunk_bytes, &tmB, b_full_bar, (kg0 * g.kgroup + it) * g.bk, n_tile * g.BN);
-      }
       int s = 0;
       uint32_t ph = 0;
       long long c_wait_empty = 0;
@@ -659,6 +713,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     t.half = (warp - kEpiWarp0) >> 2;
     t.n_tile = n_tile;
     t.stg = g.use_stg ? stg_base + t.half * STG_BYTES : 0u;
+    t.flag = reinterpret_cast<volatile unsigned int*>(tmem_slot) + 2;
     const int row = t.q * 32 + lane;
     const int ppi_log2 = g.tw_log2 + g.th_log2;
     uint32_t tl = 0;
@@ -673,6 +728,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       t.x = t.x0 + (row & ((1 << g.tw_log2) - 1));
       t.valid = t.b < g.B && t.y < g.H && t.x < g.W;
       t.tmem_empty_bar = tmem_empty_bar(buf);
+      t.tile_id = n_tile * g.m_tiles + mt;
       { CNT_BEGIN(); mbar_wait(tmem_full_bar(buf), (tl >> 1) & 1u); CNT_END(c_wait_tfull); }
       if (tl == 0 && warp == kEpiWarp0 && lane == 0) RFK_STAMP(5);  // first accumulator ready
       tc_fence_after();
@@ -860,7 +916,7 @@ static int launch(const Plan& p, const Epi& ep, cudaStream_t st, const char* who
     }
     configured = p.smem;
   }
-  conv_gemm_kernel<Epi><<<p.grid, kGemmThreads, p.smem, st>>>(p.tmA, p.tmB, p.tmO, p.g, ep);
+  launch_kernel(conv_gemm_kernel<Epi>, p.grid, dim3(kGemmThreads), p.smem, st, p.tmA, p.tmB, p.tmO, p.g, ep);
   return check_launch(who);
 }
 
@@ -965,6 +1021,26 @@ extern "C" int rfk_conv_gemm_coupling(const void* act, int B, int H, int W, int 
   return launch(p, e, (cudaStream_t)stream, "rfk_conv_gemm_coupling");
 }
 
+extern "C" int rfk_conv_gemm_splitk_fused(const void* act, int B, int H, int W, int act_ld, int cin_pad, const void* wgt,
+                                          int n, int n_pad, int taps, int k_split, float* ws, int ws_ld,
+                                          unsigned int* counters, const float* scale, const float* shift, int act_fn,
+                                          void* out, int out_ld, int out_off, void* stream) {
+  RFK_REQUIRE(ws && counters && out && ws_ld >= n_pad && ws_ld % 4 == 0 && (reinterpret_cast<uintptr_t>(ws) & 15) == 0,
+              "rfk_conv_gemm_splitk_fused: null pointer or bad workspace (16-byte aligned, ws_ld >= n_pad, ws_ld %% 4 == 0)");
+  RFK_REQUIRE(n_pad > 0 && n_pad % 16 == 0 && act_fn >= 0 && act_fn <= 2, "rfk_conv_gemm_splitk_fused: bad n_pad / act_fn");
+  RFK_REQUIRE(out_off >= 0 && out_off + n <= out_ld, "rfk_conv_gemm_splitk_fused: output window exceeds out_ld");
+  Plan p;
+  int rc = make_plan(p, "rfk_conv_gemm_splitk_fused", act, B, H, W, act_ld, cin_pad, wgt, n, n_pad, taps,
+                     pick_bn(n_pad, 16, 1 << 20), false, k_split);
+  if (rc) return rc;
+  p.g.scale = scale; p.g.shift = shift; p.g.n_ss = n;
+  SplitKEpi e;
+  e.ws = ws; e.ld = ws_ld; e.counters = counters; e.k_split = k_split; e.act_fn = act_fn;
+  e.out = (__nv_bfloat16*)out; e.out_ld = out_ld; e.out_off = out_off;
+  e.vec_ok = out_ld % 8 == 0 && out_off % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+  return launch(p, e, (cudaStream_t)stream, "rfk_conv_gemm_splitk_fused");
+}
+
 extern "C" int rfk_conv_gemm_splitk(const void* act, int B, int H, int W, int act_ld, int cin_pad, const void* wgt, int n,
                                     int n_pad, int taps, int k_split, float* ws, int ws_ld, void* stream) {
   RFK_REQUIRE(ws && ws_ld >= n_pad && ws_ld % 4 == 0 && (reinterpret_cast<uintptr_t>(ws) & 15) == 0,
@@ -975,7 +1051,8 @@ extern "C" int rfk_conv_gemm_splitk(const void* act, int B, int H, int W, int ac
                      false, k_split);
   if (rc) return rc;
   SplitKEpi e;
-  e.ws = ws; e.ld = ws_ld;
+  e.ws = ws; e.ld = ws_ld; e.counters = nullptr; e.k_split = k_split; e.act_fn = 0; e.out = nullptr;
+  e.out_ld = 0; e.out_off = 0; e.vec_ok = 0;
   return launch(p, e, (cudaStream_t)stream, "rfk_conv_gemm_splitk");
 }
 

@@ -14,6 +14,8 @@ constexpr int kThreads = 256;
 // writes 4 pixels to each of the two dx planes (1 x 128 bit each).
 __global__ void __launch_bounds__(kThreads) squeeze_fwd_v8(const float* __restrict__ x, float* __restrict__ y,
                                                            int C, int H, int W, long long total8) {
+  pdl_trigger();
+  pdl_wait();
   const int W8 = W >> 3, Ho = H >> 1, Wo = W >> 1;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total8;
        t += (long long)gridDim.x * blockDim.x) {
@@ -35,6 +37,8 @@ __global__ void __launch_bounds__(kThreads) squeeze_fwd_v8(const float* __restri
 // undo, Wout % 8 == 0: inverse of the above (reads 2 x 128 bit from the two dx planes, writes 2 x 128 bit)
 __global__ void __launch_bounds__(kThreads) squeeze_undo_v8(const float* __restrict__ x, float* __restrict__ y,
                                                             int Co, int Hout, int Wout, long long total8) {
+  pdl_trigger();
+  pdl_wait();
   const int W8 = Wout >> 3, Hi = Hout >> 1, Wi = Wout >> 1;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total8;
        t += (long long)gridDim.x * blockDim.x) {
@@ -57,6 +61,8 @@ __global__ void __launch_bounds__(kThreads) squeeze_undo_v8(const float* __restr
 // generic scalar version for narrow maps (W in {2,4,6,...}); indexed by OUTPUT element
 __global__ void __launch_bounds__(kThreads) squeeze_scalar(const float* __restrict__ x, float* __restrict__ y,
                                                            int C, int H, int W, int undo, long long total) {
+  pdl_trigger();
+  pdl_wait();
   // C,H,W describe the un-squeezed ("big") tensor [B,C,H,W]; the squeezed one is [B,4C,H/2,W/2]
   const int Ho = H >> 1, Wo = W >> 1;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
@@ -82,6 +88,8 @@ __global__ void __launch_bounds__(kThreads) actnorm_kernel(const float* __restri
                                                            const float* __restrict__ bias,
                                                            const float* __restrict__ logs, int C, int HW,
                                                            int reverse, long long total) {
+  pdl_trigger();
+  pdl_wait();
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
        t += (long long)gridDim.x * blockDim.x) {
     long long e = kVec ? t * 4 : t;
@@ -128,6 +136,8 @@ __device__ double block_sum(double v, double* sh) {
 __global__ void __launch_bounds__(512) actnorm_init_kernel(const float* __restrict__ x, float* __restrict__ bias,
                                                            float* __restrict__ logs, float* __restrict__ mean_out,
                                                            float* __restrict__ std_out, int B, int C, int HW) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ double sh[33];
   const int c = blockIdx.x;
   const long long n = (long long)B * HW;
@@ -170,6 +180,8 @@ __global__ void __launch_bounds__(1024) mix1x1_kernel(const float* __restrict__ 
                                                       int side_n, int side_off, int side_ld, int w_smem,
                                                       float* __restrict__ logdet, const float* __restrict__ addend,
                                                       float alpha, int B) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float smem[];
   const int PT = blockDim.x, G = blockDim.y;
   const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * PT + tx, nthr = PT * G;
@@ -224,6 +236,8 @@ __global__ void __launch_bounds__(1024) mix1x1_kernel(const float* __restrict__ 
 __global__ void __launch_bounds__(kThreads) pack_nhwc_kernel(const float* __restrict__ src, long long src_bs,
                                                              int HW, int c_lo, int n, __nv_bfloat16* __restrict__ dst,
                                                              int dst_off, int dst_ld, long long npix, int vec_ok) {
+  pdl_trigger();
+  pdl_wait();
   const int groups = (n + 7) >> 3;
   const long long total = npix * groups;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
@@ -250,6 +264,8 @@ template <bool kVec>
 __global__ void __launch_bounds__(kThreads) copy_channels_kernel(const float* __restrict__ src, int src_C,
                                                                  int src_off, float* __restrict__ dst, int dst_C,
                                                                  int dst_off, int n, int HW, long long total) {
+  pdl_trigger();
+  pdl_wait();
   const long long per = (long long)n * HW;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
        t += (long long)gridDim.x * blockDim.x) {
@@ -283,6 +299,8 @@ __global__ void __launch_bounds__(kThreads) coupling_tail_kernel(const float* __
                                                                  const float* __restrict__ cs,
                                                                  const float* __restrict__ csh,
                                                                  float* __restrict__ logdet, int reverse) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float sh[32];
   const int b = blockIdx.y, half = C >> 1;
   const long long per = (long long)half * HW;   // elements of z2 per sample
@@ -330,6 +348,8 @@ __global__ void __launch_bounds__(kThreads) coupling_taps_kernel(const float* __
                                                                 const float* __restrict__ cs,
                                                                 const float* __restrict__ csh,
                                                                 float* __restrict__ logdet, int reverse) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float sh[32];
   const int b = blockIdx.y, half = C >> 1, HW = H * W;
   const long long per = (long long)half * HW;
@@ -374,6 +394,8 @@ __global__ void __launch_bounds__(kThreads) coupling_taps_v4_kernel(const float*
                                                                    const float* __restrict__ cs,
                                                                    const float* __restrict__ csh,
                                                                    float* __restrict__ logdet, int reverse) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float sh[32];
   const int b = blockIdx.y, half = C >> 1, HW = H * W, W4 = W >> 2;
   const long long per4 = (long long)half * H * W4;
@@ -433,6 +455,8 @@ __global__ void __launch_bounds__(kThreads) gauss_logp_kernel(const float* __res
                                                               const float* __restrict__ params, int n, int HW,
                                                               int pairing, int std_kind,
                                                               float* __restrict__ logdet) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float sh[32];
   const int b = blockIdx.y;
   const long long per = (long long)n * HW;
@@ -462,6 +486,8 @@ __global__ void __launch_bounds__(kThreads) gauss_sample_kernel(const float* __r
                                                                 const float* __restrict__ params, int n, int HW,
                                                                 int pairing, int std_kind, float temperature,
                                                                 float* __restrict__ out, int out_C, int out_off) {
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.y;
   const long long per = (long long)n * HW;
   const float* pb = params ? params + (long long)b * 2 * n * HW : nullptr;
@@ -501,6 +527,8 @@ __global__ void __launch_bounds__(kThreads) lstm_pointwise_kernel(const float* _
                                                                   float* __restrict__ h_out,
                                                                   float* __restrict__ c_next, int Hc, int HW,
                                                                   long long total) {
+  pdl_trigger();
+  pdl_wait();
   const long long per = (long long)Hc * HW;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
        t += (long long)gridDim.x * blockDim.x) {
@@ -548,6 +576,8 @@ __global__ void __launch_bounds__(kThreads) lstm_pointwise_ws_kernel(float* __re
                                                                      float* __restrict__ c_next, long long c_next_bs,
                                                                      __nv_bfloat16* __restrict__ h_nhwc, int h_off, int h_ld,
                                                                      int Hc, int HW, int zero_cc, long long total) {
+  pdl_trigger();
+  pdl_wait();
   const long long per = (long long)Hc * HW;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
        t += (long long)gridDim.x * blockDim.x) {
@@ -569,6 +599,8 @@ __global__ void __launch_bounds__(kThreads) lstm_pointwise_ws_kernel(float* __re
 }
 
 __global__ void add_scalar_kernel(float* __restrict__ logdet, const float* __restrict__ addend, float alpha, int B) {
+  pdl_trigger();
+  pdl_wait();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < B) logdet[i] += alpha * (*addend);
 }
@@ -584,6 +616,8 @@ __global__ void __launch_bounds__(kThreads) mix1x1_small_kernel(const float* __r
                                                                 int side_n, int side_off, int side_ld,
                                                                 float* __restrict__ logdet,
                                                                 const float* __restrict__ addend, float alpha, int B) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float ws[CT * CT + CT];
   for (int i = threadIdx.x; i < CT * CT + CT; i += blockDim.x) {
     float v = 0.0f;
@@ -639,18 +673,18 @@ extern "C" int rfk_squeeze2d(const float* x, float* y, int B, int C, int H, int 
     RFK_REQUIRE(H % 2 == 0 && W % 2 == 0, "rfk_squeeze2d: H=%d, W=%d must be even", H, W);
     if (W % 8 == 0 && aligned16(x) && aligned16(y)) {
       long long t8 = total / 8;
-      squeeze_fwd_v8<<<stream_grid(t8, kThreads, 8), kThreads, 0, st>>>(x, y, C, H, W, t8);
+      RFK_LAUNCH(squeeze_fwd_v8, stream_grid(t8, kThreads, 8), kThreads, 0, st, x, y, C, H, W, t8);
     } else {
-      squeeze_scalar<<<stream_grid(total, kThreads, 8), kThreads, 0, st>>>(x, y, C, H, W, 0, total);
+      RFK_LAUNCH(squeeze_scalar, stream_grid(total, kThreads, 8), kThreads, 0, st, x, y, C, H, W, 0, total);
     }
   } else {
     RFK_REQUIRE(C % 4 == 0, "rfk_squeeze2d(undo): C=%d must be a multiple of 4", C);
     int Co = C / 4, Hout = 2 * H, Wout = 2 * W;
     if (Wout % 8 == 0 && aligned16(x) && aligned16(y)) {
       long long t8 = total / 8;
-      squeeze_undo_v8<<<stream_grid(t8, kThreads, 8), kThreads, 0, st>>>(x, y, Co, Hout, Wout, t8);
+      RFK_LAUNCH(squeeze_undo_v8, stream_grid(t8, kThreads, 8), kThreads, 0, st, x, y, Co, Hout, Wout, t8);
     } else {
-      squeeze_scalar<<<stream_grid(total, kThreads, 8), kThreads, 0, st>>>(x, y, Co, Hout, Wout, 1, total);
+      RFK_LAUNCH(squeeze_scalar, stream_grid(total, kThreads, 8), kThreads, 0, st, x, y, Co, Hout, Wout, 1, total);
     }
   }
   return check_launch("rfk_squeeze2d");
@@ -663,9 +697,9 @@ extern "C" int rfk_actnorm(const float* x, float* y, const float* bias, const fl
   long long total = (long long)B * C * HW;
   if (HW % 4 == 0 && aligned16(x) && aligned16(y)) {
     long long t4 = total / 4;
-    actnorm_kernel<true><<<stream_grid(t4, kThreads, 8), kThreads, 0, st>>>(x, y, bias, logs, C, HW, reverse, t4);
+    RFK_LAUNCH((actnorm_kernel<true>), stream_grid(t4, kThreads, 8), kThreads, 0, st, x, y, bias, logs, C, HW, reverse, t4);
   } else {
-    actnorm_kernel<false><<<stream_grid(total, kThreads, 8), kThreads, 0, st>>>(x, y, bias, logs, C, HW, reverse,
+    RFK_LAUNCH((actnorm_kernel<false>), stream_grid(total, kThreads, 8), kThreads, 0, st, x, y, bias, logs, C, HW, reverse,
                                                                                  total);
   }
   return check_launch("rfk_actnorm");
@@ -675,7 +709,7 @@ extern "C" int rfk_actnorm_init(const float* x, float* bias, float* logs, float*
                                 int C, int HW, void* stream) {
   RFK_REQUIRE(x && B > 0 && C > 0 && HW > 0, "rfk_actnorm_init: null pointer or empty shape");
   RFK_REQUIRE((long long)B * HW > 1, "rfk_actnorm_init: unbiased std needs more than one element per channel");
-  actnorm_init_kernel<<<C, 512, 0, (cudaStream_t)stream>>>(x, bias, logs, mean_out, std_out, B, C, HW);
+  RFK_LAUNCH(actnorm_init_kernel, C, 512, 0, (cudaStream_t)stream, x, bias, logs, mean_out, std_out, B, C, HW);
   return check_launch("rfk_actnorm_init");
 }
 
@@ -691,10 +725,10 @@ extern "C" int rfk_mix1x1(const float* x, float* y, const float* Wm, const float
     const long long nquad = (long long)B * HW / 4;
     const int grid = stream_grid(nquad, kThreads, 8);
     if (C <= 4)
-      mix1x1_small_kernel<4><<<grid, kThreads, 0, (cudaStream_t)stream>>>(x, y, Wm, bvec, C, HW, nquad, (__nv_bfloat16*)side,
+      RFK_LAUNCH((mix1x1_small_kernel<4>), grid, kThreads, 0, (cudaStream_t)stream, x, y, Wm, bvec, C, HW, nquad, (__nv_bfloat16*)side,
                                                                           side ? side_n : 0, side_off, side_ld, logdet, addend, alpha, B);
     else
-      mix1x1_small_kernel<8><<<grid, kThreads, 0, (cudaStream_t)stream>>>(x, y, Wm, bvec, C, HW, nquad, (__nv_bfloat16*)side,
+      RFK_LAUNCH((mix1x1_small_kernel<8>), grid, kThreads, 0, (cudaStream_t)stream, x, y, Wm, bvec, C, HW, nquad, (__nv_bfloat16*)side,
                                                                           side ? side_n : 0, side_off, side_ld, logdet, addend, alpha, B);
     return check_launch("rfk_mix1x1");
   }
@@ -714,7 +748,7 @@ extern "C" int rfk_mix1x1(const float* x, float* y, const float* Wm, const float
     configured = smem;
   }
   long long npix = (long long)B * HW;
-  mix1x1_kernel<<<ceil_div(npix, PT), dim3(PT, G), smem, (cudaStream_t)stream>>>(
+  RFK_LAUNCH(mix1x1_kernel, ceil_div(npix, PT), dim3(PT, G), smem, (cudaStream_t)stream, 
       x, y, Wm, bvec, C, HW, npix, (__nv_bfloat16*)side, side ? side_n : 0, side_off, side_ld, w_smem, logdet, addend,
       alpha, B);
   return check_launch("rfk_mix1x1");
@@ -728,7 +762,7 @@ extern "C" int rfk_pack_nhwc_bf16(const float* src, long long src_bstride, int B
   if (n == 0) return RFK_OK;
   long long npix = (long long)B * HW;
   int vec_ok = (dst_ld % 8 == 0) && (dst_off % 8 == 0) && aligned16(dst);
-  pack_nhwc_kernel<<<stream_grid(npix * ((n + 7) / 8), kThreads, 8), kThreads, 0, (cudaStream_t)stream>>>(
+  RFK_LAUNCH(pack_nhwc_kernel, stream_grid(npix * ((n + 7) / 8), kThreads, 8), kThreads, 0, (cudaStream_t)stream, 
       src, src_bstride > 0 ? src_bstride : (long long)Csrc * HW, HW, c_lo, n, (__nv_bfloat16*)dst, dst_off, dst_ld,
       npix, vec_ok);
   return check_launch("rfk_pack_nhwc_bf16");
@@ -743,10 +777,10 @@ extern "C" int rfk_copy_channels(const float* src, int src_C, int src_off, float
   long long total = (long long)B * n * HW;
   cudaStream_t st = (cudaStream_t)stream;
   if (HW % 4 == 0 && aligned16(src) && aligned16(dst)) {
-    copy_channels_kernel<true><<<stream_grid(total / 4, kThreads, 8), kThreads, 0, st>>>(
+    RFK_LAUNCH((copy_channels_kernel<true>), stream_grid(total / 4, kThreads, 8), kThreads, 0, st, 
         src, src_C, src_off, dst, dst_C, dst_off, n, HW, total / 4);
   } else {
-    copy_channels_kernel<false><<<stream_grid(total, kThreads, 8), kThreads, 0, st>>>(
+    RFK_LAUNCH((copy_channels_kernel<false>), stream_grid(total, kThreads, 8), kThreads, 0, st, 
         src, src_C, src_off, dst, dst_C, dst_off, n, HW, total);
   }
   return check_launch("rfk_copy_channels");
@@ -767,10 +801,10 @@ extern "C" int rfk_coupling_tail(const float* nn_out, float* z, int B, int C, in
   dim3 grid(chunks, B);
   cudaStream_t st = (cudaStream_t)stream;
   if (vec)
-    coupling_tail_kernel<true><<<grid, kThreads, 0, st>>>(nn_out, z, C, HW, clamp_type, clamp_scale, clamp_shift,
+    RFK_LAUNCH((coupling_tail_kernel<true>), grid, kThreads, 0, st, nn_out, z, C, HW, clamp_type, clamp_scale, clamp_shift,
                                                           logdet, reverse);
   else
-    coupling_tail_kernel<false><<<grid, kThreads, 0, st>>>(nn_out, z, C, HW, clamp_type, clamp_scale, clamp_shift,
+    RFK_LAUNCH((coupling_tail_kernel<false>), grid, kThreads, 0, st, nn_out, z, C, HW, clamp_type, clamp_scale, clamp_shift,
                                                            logdet, reverse);
   return check_launch("rfk_coupling_tail");
 }
@@ -789,10 +823,10 @@ extern "C" int rfk_coupling_tail_taps(const float* taps, float* z, int B, int C,
   int cap = ceil_div((long long)sm_count() * 8, B);
   if (chunks > cap) chunks = cap;
   if (v4)
-    coupling_taps_v4_kernel<<<dim3(chunks, B), kThreads, 0, (cudaStream_t)stream>>>(
+    RFK_LAUNCH(coupling_taps_v4_kernel, dim3(chunks, B), kThreads, 0, (cudaStream_t)stream, 
         taps, z, C, H, W, scale, shift, clamp_type, clamp_scale, clamp_shift, logdet, reverse);
   else
-    coupling_taps_kernel<<<dim3(chunks, B), kThreads, 0, (cudaStream_t)stream>>>(
+    RFK_LAUNCH(coupling_taps_kernel, dim3(chunks, B), kThreads, 0, (cudaStream_t)stream, 
         taps, z, C, H, W, scale, shift, clamp_type, clamp_scale, clamp_shift, logdet, reverse);
   return check_launch("rfk_coupling_tail_taps");
 }
@@ -805,7 +839,7 @@ extern "C" int rfk_gauss_logp(const float* z, int z_C, int z_off, const float* p
   int chunks = ceil_div(per, kThreads);
   int cap = ceil_div((long long)sm_count() * 8, B);
   if (chunks > cap) chunks = cap;
-  gauss_logp_kernel<<<dim3(chunks, B), kThreads, 0, (cudaStream_t)stream>>>(z, z_C, z_off, params, n, HW, pairing,
+  RFK_LAUNCH(gauss_logp_kernel, dim3(chunks, B), kThreads, 0, (cudaStream_t)stream, z, z_C, z_off, params, n, HW, pairing,
                                                                             std_kind, logdet);
   return check_launch("rfk_gauss_logp");
 }
@@ -819,7 +853,7 @@ extern "C" int rfk_gauss_sample(const float* eps, const float* params, int n, in
   int chunks = ceil_div(per, kThreads);
   int cap = ceil_div((long long)sm_count() * 8, B);
   if (chunks > cap) chunks = cap;
-  gauss_sample_kernel<<<dim3(chunks, B), kThreads, 0, (cudaStream_t)stream>>>(eps, params, n, HW, pairing, std_kind,
+  RFK_LAUNCH(gauss_sample_kernel, dim3(chunks, B), kThreads, 0, (cudaStream_t)stream, eps, params, n, HW, pairing, std_kind,
                                                                               temperature, out, out_C, out_off);
   return check_launch("rfk_gauss_sample");
 }
@@ -833,10 +867,10 @@ extern "C" int rfk_convlstm_pointwise(const float* cc, const float* c_prev, cons
   bool vec = HW % 4 == 0 && aligned16(cc) && aligned16(c_prev) && aligned16(h_out) && aligned16(c_next) &&
              (!peep || aligned16(peep));
   if (vec)
-    lstm_pointwise_kernel<true><<<stream_grid(total / 4, kThreads, 8), kThreads, 0, st>>>(cc, c_prev, peep, h_out,
+    RFK_LAUNCH((lstm_pointwise_kernel<true>), stream_grid(total / 4, kThreads, 8), kThreads, 0, st, cc, c_prev, peep, h_out,
                                                                                           c_next, Hc, HW, total / 4);
   else
-    lstm_pointwise_kernel<false><<<stream_grid(total, kThreads, 8), kThreads, 0, st>>>(cc, c_prev, peep, h_out,
+    RFK_LAUNCH((lstm_pointwise_kernel<false>), stream_grid(total, kThreads, 8), kThreads, 0, st, cc, c_prev, peep, h_out,
                                                                                        c_next, Hc, HW, total);
   return check_launch("rfk_convlstm_pointwise");
 }
@@ -849,7 +883,7 @@ extern "C" int rfk_convlstm_pointwise_ws(float* cc, int cc_ld, const float* bias
               "rfk_convlstm_pointwise_ws: null pointer, empty shape or cc_ld < 4*Hc");
   if (h_nhwc) RFK_REQUIRE(h_off >= 0 && h_off + Hc <= h_ld, "rfk_convlstm_pointwise_ws: h window exceeds h_ld");
   long long total = (long long)B * Hc * HW;
-  lstm_pointwise_ws_kernel<<<stream_grid(total, kThreads, 8), kThreads, 0, (cudaStream_t)stream>>>(
+  RFK_LAUNCH(lstm_pointwise_ws_kernel, stream_grid(total, kThreads, 8), kThreads, 0, (cudaStream_t)stream, 
       cc, cc_ld, bias, c_prev, c_prev_bstride, peep, h_out, h_bstride, c_next, c_next_bstride, (__nv_bfloat16*)h_nhwc, h_off,
       h_ld, Hc, HW, zero_cc, total);
   return check_launch("rfk_convlstm_pointwise_ws");
@@ -857,6 +891,6 @@ extern "C" int rfk_convlstm_pointwise_ws(float* cc, int cc_ld, const float* bias
 
 extern "C" int rfk_add_scalar(float* logdet, const float* addend, float alpha, int B, void* stream) {
   RFK_REQUIRE(logdet && addend && B > 0, "rfk_add_scalar: null pointer or empty shape");
-  add_scalar_kernel<<<ceil_div(B, 256), 256, 0, (cudaStream_t)stream>>>(logdet, addend, alpha, B);
+  RFK_LAUNCH(add_scalar_kernel, ceil_div(B, 256), 256, 0, (cudaStream_t)stream, logdet, addend, alpha, B);
   return check_launch("rfk_add_scalar");
 }

@@ -147,6 +147,41 @@ def conv_gemm_lstm(act, cin_pad, wgt, hidden, ht, ht_pad, taps, bias, c_prev, pe
          meta=_gemm_meta(B * H * W, 4 * hidden, taps, cin_pad, wgt))
 
 
+def choose_k_split(M, taps, cin_pad):
+    """K slices for a 3x3 conv whose pixel tiles cannot fill the GPU.  tcgen05.mma (M=128) costs ~131 cycles whatever
+    N is, so a CTA's time is K-iterations x 4 x 131 cycles however narrow its tile: the only way to put more SMs on a
+    small-M layer is to cut K.  One slice per filter tap (9) or per filter row (3)."""
+    # Measured on B200 (profiles/README.md): adding 128x256 fp32 partial tiles with red.global.add costs ~85 us per
+    # launch (L2 atomic throughput), far more than the 15-22 us the unsplit kernel takes, so the atomics-based split
+    # is only worth it for tiny outputs (the RFN ConvLSTM gates, 120 x 800).  Off for the flow convs unless forced.
+    import os
+    if os.environ.get("RFK_CONV_SPLITK", "0") != "1":
+        return 1
+    if taps != 9 or cin_pad % 64 != 0 or cin_pad < 128:
+        return 1
+    m_tiles = (M + 127) // 128
+    if m_tiles * 9 <= 296:
+        return 9
+    if m_tiles * 3 <= 296:
+        return 3
+    return 1
+
+
+def conv_gemm_splitk_fused(act, cin_pad, wgt, n, taps, k_split, scale, shift, act_fn, out, out_off=0):
+    """conv_gemm (bf16 NHWC output) with K cut into k_split slices and the reduction fused into the kernel."""
+    _chk(act, torch.bfloat16, "act")
+    _chk(out, torch.bfloat16, "out")
+    B, H, W, ld = act.shape
+    n_pad = wgt.shape[0]
+    m_tiles = (B * H * W + 127) // 128
+    ws = workspace(("splitk_ws", n_pad), (B * H * W, n_pad), act.device, torch.float32)        # zero, kept zero
+    cnt = workspace(("splitk_cnt",), (max(1024, 4 * m_tiles),), act.device, torch.int32)       # zero, kept zero
+    call("rfk_conv_gemm_splitk_fused", act.data_ptr(), B, H, W, ld, cin_pad, _chk(wgt, torch.bfloat16).data_ptr(), n,
+         n_pad, taps, k_split, ws.data_ptr(), n_pad, cnt.data_ptr(), _p(scale), _p(shift), ACT[act_fn],
+         out.data_ptr(), out.shape[-1], out_off, _stream(), meta=_gemm_meta(B * H * W, n, taps, cin_pad, wgt))
+    return out
+
+
 def conv_gemm_splitk(act, cin_pad, wgt, n, taps, k_split, ws):
     """Partial sums of k_split K slices added into the zeroed fp32 workspace ws [B*H*W, ld]."""
     _chk(act, torch.bfloat16, "act")

@@ -152,3 +152,23 @@ def test_tap_split_coupling(ops, clamp, B, C, H, W):
     ops.coupling_tail_taps(taps, zc, scale.cuda(), shift.cuda(), clamp, cs.cuda(), csh.cuda(), ld, True)
     assert max_rel(zc.cpu(), z) < 1e-4
     assert float(ld.abs().max()) < 1e-3
+
+
+@pytest.mark.parametrize("B,Cin,H,W,N,ks", [(30, 288, 2, 2, 256, 9), (7, 144, 4, 4, 256, 9), (40, 128, 4, 4, 256, 3),
+                                            (3, 512, 2, 2, 512, 9), (5, 130, 3, 5, 40, 3)])
+def test_conv_gemm_splitk_fused(ops, B, Cin, H, W, N, ks):
+    """Split-K with the in-kernel last-arriver fix-up equals the single-pass kernel; run twice to prove that workspace
+    and counters are left clean."""
+    g = torch.Generator().manual_seed(Cin + N)
+    x = bf(torch.randn(B, Cin, H, W, generator=g))
+    w = bf(torch.randn(N, Cin, 3, 3, generator=g) / (Cin * 9) ** 0.5)
+    scale, shift = torch.rand(N, generator=g) + 0.5, torch.randn(N, generator=g) * 0.2
+    ref = torch.relu(F.conv2d(x, w, None, 1, 1) * scale.view(1, N, 1, 1) + shift.view(1, N, 1, 1))
+    wp, cin_pad = ops.pack_conv_weight(w.cuda())
+    ld = ops.pad_to(N, 64)
+    for _ in range(2):
+        out = torch.zeros(B, H, W, ld, device="cuda", dtype=torch.bfloat16)
+        ops.conv_gemm_splitk_fused(staged(ops, x), cin_pad, wp, N, 9, ks, scale.cuda(), shift.cuda(), "relu", out)
+        got = out[..., :N].permute(0, 3, 1, 2).float().cpu()
+        assert max_rel(got, ref) < 6e-3
+        assert float(out[..., N:].abs().max()) == 0 if ld > N else True

@@ -340,3 +340,35 @@ def test_graphed_sample_matches_eager(rf):
         x_graph2 = gs0(conds2, base).clone()
         x_eager2 = m.sample(None, conds2, base, num_samples=2, temperature=0.0)
         assert max_rel(x_graph2, x_eager2) < 1e-5 and max_rel(x_graph2, x_graph) > 1e-3
+
+
+def test_listglow_config_d_shape_vs_oracle(rf):
+    """main_rfn.py defaults (config D, BASELINE config 5): 3x64x64 RGB, L=5, with_skip condition channels
+    [32,64,128,256,384], flow channels 12..192, base 261 channels -- at K=1, B=2: log_prob and sample vs the oracle."""
+    B = 2
+    a = dict(GLOW_ARGS, L=5, K=1)
+    cond_ch = [32, 64, 128, 256, 384]
+    cond_sizes = [[B, c, 32 >> l, 32 >> l] for l, c in enumerate(cond_ch)]
+    torch.manual_seed(0)
+    with torch.no_grad():
+        m = rf.ListGlow([B, 3, 64, 64], cond_sizes, [B, 261, 2, 2], ns(a)).eval()
+        trained_like(m, 4, 0.01, 0.05)
+        sd = {k: v.clone() for k, v in m.state_dict().items()}
+        m = m.cuda()
+        g = torch.Generator().manual_seed(5)
+        x = torch.floor(torch.rand(B, 3, 64, 64, generator=g) * 256) / 256 - 0.5
+        noise = torch.rand(B, 3, 64, 64, generator=g) / 256
+        conds = [torch.randn(*s, generator=g) for s in cond_sizes]
+        base = torch.randn(B, 261, 2, 2, generator=g)
+        z_ref, nll_ref = O.listglow_log_prob(x, conds, base, sd, 5, 1, 8, noise=noise, learn_prior=True)
+        z, nll = m.log_prob(x.cuda(), [c.cuda() for c in conds], base.cuda(), logdet=0, noise=noise.cuda())
+        assert z.shape == (B, 192, 2, 2)
+        assert max_rel(z, z_ref) < BF16_TOL
+        chw = 3 * 64 * 64
+        torch.testing.assert_close(nll.cpu() / (math.log(2) * chw), nll_ref / (math.log(2) * chw), rtol=BF16_TOL, atol=2e-3)
+        eps_prior = torch.randn(B, 192, 2, 2, generator=g)
+        eps = [torch.randn(B, 6 << l, 32 >> l, 32 >> l, generator=g) for l in range(4)]
+        x_ref = O.listglow_sample(conds, base, sd, 5, 1, eps_prior, eps, 0.7, learn_prior=True)
+        xs = m.sample(None, [c.cuda() for c in conds], base.cuda(), num_samples=B, temperature=0.7,
+                      eps_prior=eps_prior.cuda(), eps_list=[e.cuda() for e in eps])
+        assert max_rel(xs, x_ref) < 2 * BF16_TOL
