@@ -173,6 +173,15 @@ int rfk_coupling_tail_taps(const float* taps, float* z, int B, int C, int H, int
                            int clamp_type, const float* clamp_scale, const float* clamp_shift,
                            float* logdet, int reverse, void* stream);
 
+/* conv1x1 -> ActNorm -> activation -> tap-split conv3x3 in ONE kernel (Flow/glow_modules.py:235-237 = net.2, net.3,
+ * net.4 of the coupling network): the hidden tensor h2 is produced in tensor memory as bf16 and consumed from there
+ * by the second GEMM, so it never touches HBM.  act: NHWC bf16 h1 (first cin_pad channels, multiple of 64);
+ * w2: bf16 [hid, cin_pad]; scale2/shift2: ActNorm affine [hid]; w9: bf16 [n3_pad, hid] in tap-split row order
+ * (see rfk_coupling_tail_taps); taps: fp32 NCHW [B, n3, H, W].  hid in {64,128,192,256}, n3_pad <= 128. */
+int rfk_conv1x1_taps_fused(const void* act, int B, int H, int W, int act_ld, int cin_pad,
+                           const void* w2, int hid, const float* scale2, const float* shift2, int act_fn,
+                           const void* w9, int n3, int n3_pad, float* taps, void* stream);
+
 /* ---- a5/a7  Gaussian log-density and sampling (Flow/glow_modules.py:362-368, glow.py:139,154)
  * params [B,2n,HW] f32 (nullable = zeros) holds (mean, raw) per `pairing`; std per `std_kind`.
  * logp : logdet[b] += sum_{j<n,p} log N(z[b,z_off+j,p]; mean, std)        (z has z_C channels)

@@ -17,6 +17,7 @@ from ..Utils.utils import split_feature  # noqa: F401  (re-exported like the ref
 from ..Utils.modules import ActFun
 
 
+FUSE_CONV2_TAPS = True   # AffineCoupling: fuse net.2 (1x1 conv + ActNorm + act) with the tap-split net.4 when 9*C <= 128
 TAP_SPLIT_MAX_N = 2304  # AffineCoupling: tap-split form of the last conv up to C = 256 (K drops from 9*256 to 256)
 
 
@@ -344,8 +345,13 @@ class AffineCoupling(nn.Module):
         h1 = ops.workspace(("cpl_h1", self.hidden_units), (B, H, W, hp), dev)
         h2 = ops.workspace(("cpl_h2", self.hidden_units), (B, H, W, hp), dev)
         self.net[0].fused(nn_in, h1, self.non_lin, "cz", self._perm(dev))
-        self.net[2].fused(h1, h2, self.non_lin)
         last = self.net[4]
+        mid = self.net[2]
+        # conv1x1 -> ActNorm -> act -> tap-split conv3x3 in one kernel (h2 stays in tensor memory) when the shapes allow
+        b2b = (FUSE_CONV2_TAPS and last.taps == 9 and mid.taps == 1 and ops.pad_to(9 * C, 16) <= 128
+               and self.hidden_units % 64 == 0 and self.hidden_units <= 256 and mid.norm_type.is_initialized())
+        if not b2b:
+            mid.fused(h1, h2, self.non_lin)
         scale, shift = last.affine()
         ld, extra = _ld_begin(logdet, B, dev, inplace=_ctx is not None)
         cs = self.scale.detach().reshape(-1) if self.clamp_type == "realnvp" else None
@@ -355,7 +361,12 @@ class AffineCoupling(nn.Module):
             # then a streaming gather of the nine shifted planes fused with the coupling tail
             wgt9, cin_pad = last.packed_taps()
             taps = ops.workspace(("cpl_taps", C), (B, 9 * C, H, W), dev, torch.float32)
-            ops.conv_gemm(h2, cin_pad, wgt9, 9 * C, 1, None, None, "none", taps)
+            if b2b:
+                w2, cin_pad2 = mid.packed()
+                s2, t2 = mid.norm_type.affine()
+                ops.conv1x1_taps_fused(h1, cin_pad2, w2, self.hidden_units, s2, t2, self.non_lin, wgt9, 9 * C, taps)
+            else:
+                ops.conv_gemm(h2, cin_pad, wgt9, 9 * C, 1, None, None, "none", taps)
             ops.coupling_tail_taps(taps, out, scale, shift, self.clamp_type, cs, csh, ld, reverse)
         else:
             wgt, cin_pad = last.packed()

@@ -32,6 +32,8 @@ SIGNATURES = {
                           c_void_p],
     "rfk_coupling_tail_taps": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p,
                                c_void_p, c_void_p, c_int, c_void_p],
+    "rfk_conv1x1_taps_fused": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int,
+                               c_void_p, c_int, c_int, c_void_p, c_void_p],
     "rfk_gauss_logp": [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
     "rfk_gauss_sample": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_int, c_int,
                          c_void_p],

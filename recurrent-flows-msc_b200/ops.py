@@ -216,6 +216,21 @@ def coupling_tail_taps(taps, z, scale, shift, clamp_type, clamp_scale, clamp_shi
          _chk(shift).data_ptr(), CLAMP[clamp_type], _p(clamp_scale), _p(clamp_shift), _p(logdet), int(reverse), _stream())
 
 
+def conv1x1_taps_fused(act, cin_pad, w2, hid, scale2, shift2, act_fn, w9, n3, taps):
+    """taps = tap-split conv3x3( act_fn(scale2 * conv1x1(act) + shift2) ) with the hidden tensor kept in tensor memory."""
+    _chk(act, torch.bfloat16, "act")
+    _chk(taps, name="taps")
+    B, H, W, ld = act.shape
+    M = B * H * W
+    meta = {"flops": 2.0 * M * hid * cin_pad + 2.0 * M * n3 * hid,
+            "flops_padded": 2.0 * M * hid * cin_pad + 2.0 * M * w9.shape[0] * hid,
+            "M": M, "N": hid, "K": cin_pad, "bytes": 2.0 * M * cin_pad + 4.0 * M * n3 + 2.0 * (w2.numel() + w9.numel())}
+    call("rfk_conv1x1_taps_fused", act.data_ptr(), B, H, W, ld, cin_pad, _chk(w2, torch.bfloat16).data_ptr(), hid,
+         _p(scale2), _p(shift2), ACT[act_fn], _chk(w9, torch.bfloat16).data_ptr(), n3, w9.shape[0], taps.data_ptr(),
+         _stream(), meta=meta)
+    return taps
+
+
 def gauss_logp(z, z_off, params, n, pairing, std_kind, logdet):
     _chk(z, name="z")
     B, zC, H, W = z.shape

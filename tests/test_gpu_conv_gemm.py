@@ -172,3 +172,31 @@ def test_conv_gemm_splitk_fused(ops, B, Cin, H, W, N, ks):
         got = out[..., :N].permute(0, 3, 1, 2).float().cpu()
         assert max_rel(got, ref) < 6e-3
         assert float(out[..., N:].abs().max()) == 0 if ld > N else True
+
+
+@pytest.mark.parametrize("act", ["relu", "leakyrelu"])
+@pytest.mark.parametrize("B,C,H,W,hid", [(3, 4, 32, 32, 256), (2, 8, 16, 16, 256), (5, 14, 8, 8, 128), (2, 6, 6, 10, 64),
+                                         (40, 4, 2, 2, 192)])
+def test_conv1x1_taps_fused(ops, act, B, C, H, W, hid):
+    """conv1x1 -> affine -> act -> tap-split conv in one kernel (h2 in tensor memory) equals the two-kernel path and
+    the oracle's conv chain."""
+    g = torch.Generator().manual_seed(C * 7 + hid)
+    h1 = bf(torch.relu(torch.randn(B, hid, H, W, generator=g)))
+    w2 = bf(torch.randn(hid, hid, 1, 1, generator=g) / hid ** 0.5)
+    s2, t2 = torch.rand(hid, generator=g) + 0.5, torch.randn(hid, generator=g) * 0.2
+    w4 = bf(torch.randn(C, hid, 3, 3, generator=g) * 0.03)
+    h2_ref = bf(O.act_fun(F.conv2d(h1, w2) * s2.view(1, hid, 1, 1) + t2.view(1, hid, 1, 1), act))
+    w9 = w4.permute(2, 3, 0, 1).reshape(9 * C, hid, 1, 1)
+    taps_ref = F.conv2d(h2_ref, w9)
+    w2p, cin_pad = ops.pack_conv_weight(w2.cuda())
+    w9p, _ = ops.pack_tap_split_weight(w4.cuda())
+    a = staged(ops, h1)
+    taps = torch.full((B, 9 * C, H, W), float("nan"), device="cuda")
+    ops.conv1x1_taps_fused(a, cin_pad, w2p, hid, s2.cuda(), t2.cuda(), act, w9p, 9 * C, taps)
+    assert max_rel(taps.cpu(), taps_ref) < 4e-3
+    # two-kernel path on the same inputs
+    h2 = torch.zeros(B, H, W, ops.cin_pad(hid), device="cuda", dtype=torch.bfloat16)
+    ops.conv_gemm(a, cin_pad, w2p, hid, 1, s2.cuda(), t2.cuda(), act, h2)
+    taps2 = torch.empty(B, 9 * C, H, W, device="cuda")
+    ops.conv_gemm(h2, ops.cin_pad(hid), w9p, 9 * C, 1, None, None, "none", taps2)
+    assert max_rel(taps.cpu(), taps2.cpu()) < 1e-3
