@@ -641,6 +641,7 @@ __global__ void __launch_bounds__(kThreads) mix1x1_small_kernel(const float* __r
     for (int i = 0; i < CT; ++i) xi[i] = i < C ? ld_stream(reinterpret_cast<const float4*>(xp + (long long)i * HW)) : make_float4(0, 0, 0, 0);
     float* yp = y + b * C * HW + p;
     const long long pix = b * HW + p;
+    __nv_bfloat16 sv[4][CT / 2];   // side channels (the first half of the outputs) of the 4 pixels
 #pragma unroll
     for (int o = 0; o < CT; ++o) {
       if (o < C) {
@@ -652,10 +653,25 @@ __global__ void __launch_bounds__(kThreads) mix1x1_small_kernel(const float* __r
           a.x = fmaf(w, xi[i].x, a.x); a.y = fmaf(w, xi[i].y, a.y); a.z = fmaf(w, xi[i].z, a.z); a.w = fmaf(w, xi[i].w, a.w);
         }
         st_stream(reinterpret_cast<float4*>(yp + (long long)o * HW), a);
-        if (side && o < side_n) {
-          __nv_bfloat16* sp = side + pix * side_ld + side_off + o;
-          sp[0] = __float2bfloat16(a.x); sp[side_ld] = __float2bfloat16(a.y);
-          sp[2 * side_ld] = __float2bfloat16(a.z); sp[3 * side_ld] = __float2bfloat16(a.w);
+        if (o < CT / 2) {
+          sv[0][o] = __float2bfloat16(a.x); sv[1][o] = __float2bfloat16(a.y);
+          sv[2][o] = __float2bfloat16(a.z); sv[3][o] = __float2bfloat16(a.w);
+        }
+      }
+    }
+    if (side) {
+      // one packed store per pixel when the side window is exactly the first C/2 channels and suitably aligned
+      const bool packed = side_n == CT / 2 && ((side_off * 2) % (CT) == 0) && ((side_ld * 2) % (CT) == 0);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        __nv_bfloat16* sp = side + (pix + k) * side_ld + side_off;
+        if (packed) {
+          if (CT == 4) *reinterpret_cast<uint32_t*>(sp) = *reinterpret_cast<const uint32_t*>(sv[k]);
+          else *reinterpret_cast<uint2*>(sp) = *reinterpret_cast<const uint2*>(sv[k]);
+        } else {
+#pragma unroll
+          for (int o = 0; o < CT / 2; ++o)
+            if (o < side_n) sp[o] = sv[k][o];
         }
       }
     }
@@ -721,7 +737,7 @@ extern "C" int rfk_mix1x1(const float* x, float* y, const float* Wm, const float
   RFK_REQUIRE(!logdet || addend, "rfk_mix1x1: logdet given without an addend");
   if (side) RFK_REQUIRE(side_n >= 0 && side_n <= C && side_off >= 0 && side_off + side_n <= side_ld,
                         "rfk_mix1x1: bad side-output window");
-  if (C <= 8 && HW % 4 == 0 && aligned16(x) && aligned16(y)) {
+  if (C <= 8 && HW % 4 == 0 && aligned16(x) && aligned16(y) && (!side || side_n <= (C <= 4 ? 2 : 4))) {
     const long long nquad = (long long)B * HW / 4;
     const int grid = stream_grid(nquad, kThreads, 8);
     if (C <= 4)
