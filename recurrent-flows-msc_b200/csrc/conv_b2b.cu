@@ -15,7 +15,7 @@
 // 512 B (h1 in) + 512 B (h2 out) + 512 B (h2 in) + 4*9C B to 512 B + 4*9C B.
 //
 // Persistent, one CTA per SM.  Hand-offs (all mbarriers): smem stage full/empty (TMA <-> MMA), acc2_full (GEMM2 done),
-// a3_ready (bf16 h2 tile in TMEM, all 8 epilogue warps), acc3_full (GEMM3 done).  GEMM2 of tile i+1 overlaps the
+// a3_ready[kc] (bf16 h2 channels [64kc, 64kc+64) in TMEM, all 8 epilogue warps), acc3_full (GEMM3 done).  GEMM2 of tile i+1 overlaps the
 // tap-plane stores of tile i; program order of the two roles makes every TMEM region single-writer at any time.
 #include <algorithm>
 
@@ -63,10 +63,10 @@ conv1x1_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (g.stages + s); };
   const uint32_t acc2_full = bar_base + 8u * (2 * g.stages);
-  const uint32_t a3_ready = bar_base + 8u * (2 * g.stages + 1);
-  const uint32_t acc3_full = bar_base + 8u * (2 * g.stages + 2);
-  const uint32_t w_full = bar_base + 8u * (2 * g.stages + 3);
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + bar_off + 8u * (2 * g.stages + 4));
+  const uint32_t acc3_full = bar_base + 8u * (2 * g.stages + 1);
+  const uint32_t w_full = bar_base + 8u * (2 * g.stages + 2);
+  auto a3_ready = [&](int kc) { return bar_base + 8u * (2 * g.stages + 3 + kc); };  // one per 64-channel chunk of h2
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + bar_off + 8u * (2 * g.stages + 7));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -78,7 +78,7 @@ conv1x1_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_init(empty_bar(s), 1);
     }
     mbar_init(acc2_full, 1);
-    mbar_init(a3_ready, kB2BEpiWarps);
+    for (int kc = 0; kc < 4; ++kc) mbar_init(a3_ready(kc), kB2BEpiWarps);
     mbar_init(acc3_full, 1);
     mbar_init(w_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -161,11 +161,12 @@ conv1x1_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (++s == g.stages) { s = 0; ph ^= 1u; }
         }
         umma_commit(acc2_full);
-        // GEMM3: A = bf16 h2 tile in tensor memory (8 columns per K=16 step), B = resident W9
-        mbar_wait(a3_ready, tl & 1u);
-        tc_fence_after();
+        // GEMM3: A = bf16 h2 tile in tensor memory (8 columns per K=16 step), B = resident W9; chunk kc starts as soon
+        // as the epilogue warps have written h2 channels [64 kc, 64 kc + 64), overlapping the rest of epilogue 2
         accumulate = 0;
         for (int kc = 0; kc < k3chunks; ++kc) {
+          mbar_wait(a3_ready(kc), tl & 1u);
+          tc_fence_after();
           const uint64_t bdesc = desc_hi | (uint64_t)(((w9_base + kc * w9_chunk) & 0x3FFFFu) >> 4);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
@@ -220,11 +221,11 @@ conv1x1_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           pk[2 * k + 1] = p1;
         }
         tmem_st16(t_a3 + lane_off + (uint32_t)(c0 >> 1), pk);
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a3_ready(c0 >> 6));   // this warp's share of 64-channel chunk c0/64 is in place
       }
-      tmem_wait_st();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(a3_ready);
       // ---- epilogue 3: tap planes -> fp32 NCHW
       mbar_wait(acc3_full, tl & 1u);
       tc_fence_after();
@@ -281,12 +282,12 @@ extern "C" int rfk_conv1x1_taps_fused(const void* act, int B, int H, int W, int 
   g.tiles_y = ceil_div(H, TH);
   g.m_tiles = g.tiles_x * g.tiles_y * ceil_div(B, NIMG);
   const long long resident = (long long)g.k1chunks * hid * 128 + (long long)(hid / 64) * n3_pad * 128;
-  const long long fixed = 1024 + 2LL * hid * 4 + 8 * (2 * 8 + 4) + 16;
+  const long long fixed = 1024 + 2LL * hid * 4 + 8 * (2 * 8 + 7) + 16;
   int stages = (int)((kB2BSmemLimit - fixed - resident) / (128 * 128));
   if (stages > 8) stages = 8;
   RFK_REQUIRE(stages >= 2, "rfk_conv1x1_taps_fused: weights (%lld B) leave no room for the activation pipeline", resident);
   g.stages = stages;
-  const size_t smem = (size_t)1024 + resident + (size_t)stages * 128 * 128 + 2 * hid * 4 + 8 * (2 * stages + 4) + 16;
+  const size_t smem = (size_t)1024 + resident + (size_t)stages * 128 * 128 + 2 * hid * 4 + 8 * (2 * stages + 7) + 16;
   CUtensorMap tmA, tmW2, tmW9;
   int rc = encode_act_map(&tmA, "rfk_conv1x1_taps_fused", "A", act, cin_pad, act_ld, B, H, W, TW, TH, NIMG, 64);
   if (rc) return rc;
