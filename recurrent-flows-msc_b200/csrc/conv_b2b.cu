@@ -24,9 +24,10 @@
 
 namespace rfk {
 
-constexpr int kB2BThreads = 384;  // warp 0: TMA, warp 1: MMA, warp 2: TMEM alloc, warps 4-11: epilogue
+constexpr int kB2BThreads = 640;  // warp 0: TMA, warp 1: MMA, warp 2: TMEM alloc, warps 4-19: epilogue (4 per scheduler)
 constexpr int kB2BEpiWarp0 = 4;
-constexpr int kB2BEpiWarps = 8;
+constexpr int kB2BEpiWarps = 16;
+constexpr int kB2BChunkArrivals = 8;  // warps that write one 64-channel chunk of h2: 4 quadrants x 2 column parts
 constexpr int kB2BSmemLimit = 232448;
 
 struct B2BArgs {
@@ -78,7 +79,7 @@ conv1x1_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_init(empty_bar(s), 1);
     }
     mbar_init(acc2_full, 1);
-    for (int kc = 0; kc < 4; ++kc) mbar_init(a3_ready(kc), kB2BEpiWarps);
+    for (int kc = 0; kc < 4; ++kc) mbar_init(a3_ready(kc), kB2BChunkArrivals);
     mbar_init(acc3_full, 1);
     mbar_init(w_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -180,7 +181,7 @@ conv1x1_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     __syncwarp();
   } else if (warp >= kB2BEpiWarp0) {
     // ===== epilogue warps: quadrant q owns TMEM lanes [32q, 32q+32) = tile rows; the two warps of a quadrant split columns
-    const int q = warp & 3, half = (warp - kB2BEpiWarp0) >> 2;
+    const int q = warp & 3, part = (warp - kB2BEpiWarp0) >> 2;   // part 0..3: which 32-column slice of every 128
     const int row = q * 32 + lane;
     const int ppi_log2 = g.tw_log2 + g.th_log2;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
@@ -196,7 +197,7 @@ conv1x1_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       // ---- epilogue 2: fp32 accumulator -> ActNorm affine + activation -> bf16 -> tensor memory (A operand of GEMM3)
       mbar_wait(acc2_full, tl & 1u);
       tc_fence_after();
-      for (int c0 = 32 * half; c0 < g.hid; c0 += 64) {
+      for (int c0 = 32 * part; c0 < g.hid; c0 += 128) {
         uint32_t v[32];
         tmem_ld16_nowait(t_acc2 + lane_off + c0, v);
         tmem_ld16_nowait(t_acc2 + lane_off + c0 + 16, v + 16);
@@ -229,7 +230,7 @@ conv1x1_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       // ---- epilogue 3: tap planes -> fp32 NCHW
       mbar_wait(acc3_full, tl & 1u);
       tc_fence_after();
-      for (int c0 = 16 * half; c0 < g.n3_pad; c0 += 32) {
+      for (int c0 = 16 * part; c0 < g.n3_pad; c0 += 64) {
         if (c0 >= g.n3) break;  // warp-uniform
         uint32_t r[16];
         tmem_ld16_nowait(t_acc3 + lane_off + c0, r);
