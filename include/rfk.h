@@ -79,6 +79,14 @@ int rfk_actnorm(const float* x, float* y, const float* bias, const float* logs,
 int rfk_actnorm_init(const float* x, float* bias, float* logs, float* mean_out, float* std_out,
                      int B, int C, int HW, void* stream);
 
+/* ---- f3  BatchNormFlow (Flow/glow_modules.py:56-104), the flow_norm='batchnorm' alternative to ActNorm ---------
+ * Per-POSITION parameters [1,C,H,W], statistics over the batch dimension only.  n = C*H*W.
+ * rfk_batch_stats_pos: mean[i], var[i] = biased variance + eps over b of x[b,i]   (training-mode forward)
+ * rfk_affine_pos     : y[b,i] = x[b,i]*a[i] + c[i].  Forward a = e^{log_gamma}/sqrt(var), c = beta - mean*a;
+ *                      reverse a = sqrt(var)/e^{log_gamma}, c = mean - beta*a (the [C,H,W] algebra is the caller's). */
+int rfk_batch_stats_pos(const float* x, float* mean, float* var, int B, long long n, float eps, void* stream);
+int rfk_affine_pos(const float* x, float* y, const float* a, const float* c, int B, long long n, void* stream);
+
 /* ---- a2 (+a1 folded)  InvConv.forward apply (Flow/glow_modules.py:213,218) ----------------
  * y[b,o,p] = sum_i Wm[o,i] * x[b,i,p] + bvec[o]   (Wm [C,C] row-major f32, bvec nullable).
  * With Wm = W*diag(exp(logs)), bvec = Wm*bias this is ActNorm followed by InvConv in one pass.

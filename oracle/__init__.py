@@ -15,7 +15,7 @@ replays every fixture through this oracle.
 """
 from .glow_oracle import (  # noqa: F401
     squeeze2d, split_feature, batch_reduce, act_fun,
-    actnorm_init, actnorm, invconv_weight, invconv,
+    actnorm_init, actnorm, batchnorm_flow, invconv_weight, invconv,
     conv2d_norm, conv2d_zeros, coupling_nn, clamp_log_scale,
     affine_coupling, split2d, glow_step, listglow_layout,
     listglow_f, listglow_g, listglow_prior, listglow_log_prob, listglow_sample,

@@ -96,6 +96,33 @@ def actnorm(x, bias, logs, logdet=None, reverse=False):
     return y, logdet
 
 
+def batchnorm_flow(x, log_gamma, beta, running_mean, running_var, logdet=None, reverse=False, training=False,
+                   momentum=0.1, eps=1e-5):
+    """Flow/glow_modules.py:73-104.  Per-position (C,H,W) statistics over the batch dimension only.
+
+    Training & forward: batch mean / biased variance (+eps); the running buffers become
+    running*momentum + batch*(1-momentum) (the reference's inverted momentum convention) and are returned.
+    Otherwise the running buffers are used.  dlogdet = sum(log_gamma - 0.5*log(var)) over (C,H,W).
+    Returns (out, logdet, running_mean, running_var)."""
+    if training and not reverse:
+        mean = x.mean(0)
+        var = (x - mean).pow(2).mean(0) + eps
+        running_mean = running_mean * momentum + mean * (1 - momentum)
+        running_var = running_var * momentum + var * (1 - momentum)
+    else:
+        mean, var = running_mean, running_var
+    d = torch.sum(log_gamma - 0.5 * torch.log(var))
+    if not reverse:
+        out = torch.exp(log_gamma) * ((x - mean) / var.sqrt()) + beta
+        if logdet is not None:
+            logdet = logdet + d
+    else:
+        out = ((x - beta) / torch.exp(log_gamma)) * var.sqrt() + mean
+        if logdet is not None:
+            logdet = logdet - d
+    return out, logdet, running_mean, running_var
+
+
 # ----------------------------------------------------------------------------
 # InvConv  (Flow/glow_modules.py:150-221)
 # ----------------------------------------------------------------------------
@@ -143,8 +170,13 @@ def _same_pad(w):
 
 
 def conv2d_norm(x, sd, prefix):
-    """Flow/glow_modules.py:123-147 with norm='actnorm': bias-free conv, then ActNorm fwd."""
+    """Flow/glow_modules.py:123-147.  norm='actnorm': bias-free conv, then ActNorm fwd;
+    norm='batchnorm' (keys norm_type.running_mean present): conv with bias, then nn.BatchNorm2d in eval mode."""
     w = sd[prefix + "conv.weight"].float()
+    if prefix + "norm_type.running_mean" in sd:
+        y = F.conv2d(x, w, sd[prefix + "conv.bias"].float(), 1, _same_pad(w))
+        return F.batch_norm(y, sd[prefix + "norm_type.running_mean"].float(), sd[prefix + "norm_type.running_var"].float(),
+                            sd[prefix + "norm_type.weight"].float(), sd[prefix + "norm_type.bias"].float(), False, 0.1, 1e-5)
     y = F.conv2d(x, w, None, 1, _same_pad(w))
     y, _ = actnorm(y, sd[prefix + "norm_type.bias"].float(), sd[prefix + "norm_type.logs"].float())
     return y
@@ -231,7 +263,18 @@ def split2d(x, condition, sd, prefix, logdet=None, reverse=False, temperature=No
 # ----------------------------------------------------------------------------
 def glow_step(x, condition, sd, prefix, logdet=None, reverse=False,
               clamp_type="realnvp", non_lin="relu"):
-    """Flow/glow.py:31-41 with flow_norm='actnorm'."""
+    """Flow/glow.py:31-41; flow_norm='batchnorm' (keys norm.log_gamma present) in eval mode uses the running buffers."""
+    if prefix + "norm.log_gamma" in sd:
+        bn = lambda t, ld, rev: batchnorm_flow(t, sd[prefix + "norm.log_gamma"].float(), sd[prefix + "norm.beta"].float(),  # noqa: E731
+                                               sd[prefix + "norm.running_mean"].float(),
+                                               sd[prefix + "norm.running_var"].float(), ld, rev)[:2]
+        if not reverse:
+            x, logdet = bn(x, logdet, False)
+            x, logdet = invconv(x, sd, prefix + "invconv.", logdet, False)
+            return affine_coupling(x, condition, sd, prefix + "affine.", logdet, False, clamp_type, non_lin)
+        x, logdet = affine_coupling(x, condition, sd, prefix + "affine.", logdet, True, clamp_type, non_lin)
+        x, logdet = invconv(x, sd, prefix + "invconv.", logdet, True)
+        return bn(x, logdet, True)
     if not reverse:
         x, logdet = actnorm(x, sd[prefix + "norm.bias"].float(), sd[prefix + "norm.logs"].float(), logdet, False)
         x, logdet = invconv(x, sd, prefix + "invconv.", logdet, False)

@@ -75,6 +75,25 @@ class GlowStep(nn.Module):
             _ctx = _Ctx(nn_in, cc)
         cc = _ctx.cond_channels
         ld, extra = _ld_begin(logdet, B, x.device, inplace=not own_ctx)
+        if isinstance(self.norm, BatchNormFlow):
+            # per-position normalisation cannot be folded into the CxC mix: elementwise kernel + plain invconv
+            Wm, Wm_inv, per_pixel = self.invconv.matrices()
+            dl = self._cache.get(("dl_inv", H * W), self.invconv._params(), lambda: (per_pixel * (H * W)).reshape(1).contiguous())
+            if not reverse:
+                x, ld = self.norm(x, ld, False)
+                y = ops.mix1x1(x, Wm, None, side=_ctx.nn_in, side_n=C // 2, side_off=cc, logdet=ld,
+                               addend=None if ld is None else dl, alpha=1.0)
+                _ctx.z1_packed = True
+                y, ld = self.affine(y, condition, ld, False, _ctx=_ctx)
+                _ctx.z1_packed = False
+                return y, _ld_end(ld, extra)
+            if own_ctx:
+                x = x.clone()
+            y, ld = self.affine(x, condition, ld, True, _ctx=_ctx)
+            y = ops.mix1x1(y, Wm_inv, None, logdet=ld, addend=None if ld is None else dl, alpha=-1.0)
+            out, ld = self.norm(y, ld, True)
+            _ctx.z1_packed = False   # the next reverse step packs z1 itself (the side output would be pre-normalisation)
+            return out, _ld_end(ld, extra)
         if not reverse:
             self.norm.maybe_initialize(x)
             Wf, bf, _, _, _ = self._folded()

@@ -182,18 +182,21 @@ class Conv2dZeros(nn.Module):
 
 
 class Conv2dNorm(nn.Module):
-    """Flow/glow_modules.py:123-147: bias-free conv followed by ActNorm."""
+    """Flow/glow_modules.py:123-147: conv followed by ActNorm (bias-free conv) or, for norm='batchnorm', by
+    nn.BatchNorm2d (conv with zero-initialised bias).  Either normalisation is a per-channel affine in the conv epilogue."""
 
     def __init__(self, in_channels, out_channels, kernel_size=[3, 3], stride=[1, 1], norm="actnorm"):
         super().__init__()
         assert list(stride) == [1, 1], "only stride 1 is used on this path"
-        if norm != "actnorm":
-            raise NotImplementedError("Conv2dNorm(norm='batchnorm') is outside the B200 hot-path scope (SURVEY 8f3)")
         padding = [(kernel_size[0] - 1) // 2, (kernel_size[1] - 1) // 2]
-        self.conv = nn.Conv2d(in_channels, out_channels, kernel_size, stride, padding, bias=False)
+        self.conv = nn.Conv2d(in_channels, out_channels, kernel_size, stride, padding, bias=(norm != "actnorm"))
         self.conv.weight.data.normal_(mean=0.0, std=0.05)
         self.norm = norm
-        self.norm_type = ActNorm(out_channels)
+        if self.norm == "actnorm":
+            self.norm_type = ActNorm(out_channels)
+        elif self.norm == "batchnorm":
+            self.conv.bias.data.zero_()
+            self.norm_type = nn.BatchNorm2d(out_channels)
         self.taps = kernel_size[0] * kernel_size[1]
         assert self.taps in (1, 9), "kernel must be 1x1 or 3x3"
         self._cache = _Versioned()
@@ -201,19 +204,63 @@ class Conv2dNorm(nn.Module):
     def packed(self, key="id", in_perm=None):
         return self._cache.get(("w", key), (self.conv.weight,), lambda: ops.pack_conv_weight(self.conv.weight, in_perm))
 
+    def ready_for_fusion(self):
+        """True when the per-channel affine is known without looking at the data (no pending ActNorm init, no
+        training-mode batch statistics)."""
+        if self.norm == "actnorm":
+            return self.norm_type.is_initialized()
+        return not (self.norm == "batchnorm" and self.norm_type.training)
+
+    def _bn_eval_affine(self):
+        bn = self.norm_type
+        def build():
+            s = bn.weight.detach().float() / torch.sqrt(bn.running_var.float() + bn.eps)
+            t = (self.conv.bias.detach().float() - bn.running_mean.float()) * s + bn.bias.detach().float()
+            return s.contiguous(), t.contiguous()
+        return self._cache.get("bn", (bn.weight, bn.bias, bn.running_mean, bn.running_var, self.conv.bias), build)
+
+    def affine(self, act=None, wgt=None, cin_pad=None):
+        """(scale, shift) of the normalisation as a conv epilogue; data-dependent cases run a raw conv pass first."""
+        n = self.conv.out_channels
+        if self.norm == "actnorm":
+            an = self.norm_type
+            if not an.is_initialized():
+                if an.training:  # data-dependent init on the raw convolution output (glow_modules.py:140-142)
+                    B, H, W, _ = act.shape
+                    raw = torch.empty(B, n, H, W, device=act.device, dtype=torch.float32)
+                    ops.conv_gemm(act, cin_pad, wgt, n, self.taps, None, None, "none", raw)
+                    an.initialize(raw)
+                an.mark_initialized()
+            return an.affine()
+        if self.norm == "batchnorm":
+            bn = self.norm_type
+            if not bn.training:
+                return self._bn_eval_affine()
+            # training mode: batch statistics of (conv + bias), biased variance for the normalisation, unbiased for
+            # the running estimate (torch.nn.BatchNorm2d semantics)
+            B, H, W, _ = act.shape
+            raw = torch.empty(B, n, H, W, device=act.device, dtype=torch.float32)
+            ops.conv_gemm(act, cin_pad, wgt, n, self.taps, None, self.conv.bias.detach().float(), "none", raw)
+            mean = torch.empty(n, device=act.device)
+            std = torch.empty(n, device=act.device)
+            ops.channel_stats(raw, mean, std)
+            cnt = B * H * W
+            var_b = std * std * ((cnt - 1) / cnt)
+            with torch.no_grad():
+                m = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked + 1)
+                bn.running_mean.mul_(1 - m).add_(mean * m)
+                bn.running_var.mul_(1 - m).add_(std * std * m)
+                bn.num_batches_tracked += 1
+            s = bn.weight.detach().float() / torch.sqrt(var_b + bn.eps)
+            t = (self.conv.bias.detach().float() - mean) * s + bn.bias.detach().float()
+            return s.contiguous(), t.contiguous()
+        return None, (None if self.conv.bias is None else self.conv.bias.detach().float())
+
     def fused(self, act, out, act_fn="none", key="id", in_perm=None, out_off=0):
-        """act NHWC bf16 -> out (NHWC bf16 at channel out_off, or NCHW f32) = act_fn(ActNorm(conv(act)))."""
+        """act NHWC bf16 -> out (NHWC bf16 at channel out_off, or NCHW f32) = act_fn(norm(conv(act)))."""
         wgt, cin_pad = self.packed(key, in_perm)
         n = self.conv.out_channels
-        an = self.norm_type
-        if not an.is_initialized():
-            if an.training:  # data-dependent init on the raw convolution output (glow_modules.py:140-142)
-                B, H, W, _ = act.shape
-                raw = torch.empty(B, n, H, W, device=act.device, dtype=torch.float32)
-                ops.conv_gemm(act, cin_pad, wgt, n, self.taps, None, None, "none", raw)
-                an.initialize(raw)
-            an.mark_initialized()
-        scale, shift = an.affine()
+        scale, shift = self.affine(act, wgt, cin_pad)
         if out.dtype == torch.bfloat16:
             B, H, W, _ = act.shape
             k_split = ops.choose_k_split(B * H * W, self.taps, cin_pad)
@@ -349,7 +396,7 @@ class AffineCoupling(nn.Module):
         mid = self.net[2]
         # conv1x1 -> ActNorm -> act -> tap-split conv3x3 in one kernel (h2 stays in tensor memory) when the shapes allow
         b2b = (FUSE_CONV2_TAPS and last.taps == 9 and mid.taps == 1 and ops.pad_to(9 * C, 16) <= 128
-               and self.hidden_units % 64 == 0 and self.hidden_units <= 256 and mid.norm_type.is_initialized())
+               and self.hidden_units % 64 == 0 and self.hidden_units <= 256 and mid.ready_for_fusion())
         if not b2b:
             mid.fused(h1, h2, self.non_lin)
         scale, shift = last.affine()
@@ -363,7 +410,7 @@ class AffineCoupling(nn.Module):
             taps = ops.workspace(("cpl_taps", C), (B, 9 * C, H, W), dev, torch.float32)
             if b2b:
                 w2, cin_pad2 = mid.packed()
-                s2, t2 = mid.norm_type.affine()
+                s2, t2 = mid.affine()
                 ops.conv1x1_taps_fused(h1, cin_pad2, w2, self.hidden_units, s2, t2, self.non_lin, wgt9, 9 * C, taps)
             else:
                 ops.conv_gemm(h2, cin_pad, wgt9, 9 * C, 1, None, None, "none", taps)
@@ -452,9 +499,49 @@ class Split2d(nn.Module):
 
 
 class BatchNormFlow(nn.Module):
-    """Flow/glow_modules.py:56-104 -- alternative flow_norm; SURVEY 8(f3) 'next' row, not built yet."""
+    """Flow/glow_modules.py:56-104 (RealNVP-style batch norm as a flow layer; flow_norm='batchnorm').
+
+    Parameters and running buffers are per POSITION, [1,C,H,W]; statistics are taken over the batch dimension only.
+    Keeps the reference's conventions: running = running*momentum + batch*(1-momentum), variance + eps, batch
+    statistics only in training mode and only in the forward direction."""
 
     def __init__(self, x_size, momentum=0.1, eps=1e-5):
         super().__init__()
-        raise NotImplementedError("BatchNormFlow (flow_norm='batchnorm') is a 'next' row (SURVEY 8f3); "
-                                  "use flow_norm='actnorm'")
+        Bx, Cx, Hx, Wx = x_size
+        size = [1, Cx, Hx, Wx]
+        self.log_gamma = nn.Parameter(torch.zeros(size))
+        self.beta = nn.Parameter(torch.zeros(size))
+        self.momentum = momentum
+        self.eps = eps
+        self.register_buffer('running_mean', torch.zeros(size))
+        self.register_buffer('running_var', torch.ones(size))
+        self._cache = _Versioned()
+
+    def _affine(self, mean, var, reverse):
+        lg, beta = self.log_gamma.detach()[0], self.beta.detach()[0]
+        d = torch.sum(lg - 0.5 * torch.log(var))
+        if not reverse:
+            a = torch.exp(lg) / torch.sqrt(var)
+            c = beta - mean * a
+        else:
+            a = torch.sqrt(var) / torch.exp(lg)
+            c = mean - beta * a
+        return a.contiguous(), c.contiguous(), d
+
+    def forward(self, input, logdet, reverse):
+        _require_no_grad()
+        x = ops.f32c(input)
+        if self.training and reverse == False:  # noqa: E712  (the reference's condition)
+            mean, var = ops.batch_stats_pos(x, self.eps)
+            self.batch_mean, self.batch_var = mean, var
+            with torch.no_grad():
+                self.running_mean.mul_(self.momentum).add_(mean * (1 - self.momentum))
+                self.running_var.mul_(self.momentum).add_(var * (1 - self.momentum))
+            a, c, d = self._affine(mean, var, False)
+        else:
+            a, c, d = self._cache.get(("aff", bool(reverse)), (self.log_gamma, self.beta, self.running_mean, self.running_var),
+                                      lambda: self._affine(self.running_mean[0], self.running_var[0], bool(reverse)))
+        z = ops.affine_pos(x, a, c)
+        if logdet is not None:
+            logdet = logdet - d if reverse else logdet + d
+        return z, logdet

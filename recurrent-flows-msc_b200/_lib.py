@@ -17,6 +17,8 @@ SIGNATURES = {
     "rfk_squeeze2d": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "rfk_actnorm": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "rfk_actnorm_init": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
+    "rfk_batch_stats_pos": [c_void_p, c_void_p, c_void_p, c_int, c_longlong, c_float, c_void_p],
+    "rfk_affine_pos": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_longlong, c_void_p],
     "rfk_mix1x1": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                    c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p],
     "rfk_pack_nhwc_bf16": [c_void_p, c_longlong, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p],

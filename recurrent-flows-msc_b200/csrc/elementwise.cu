@@ -598,6 +598,49 @@ __global__ void __launch_bounds__(kThreads) lstm_pointwise_ws_kernel(float* __re
   }
 }
 
+// BatchNormFlow (Flow/glow_modules.py:56-104): per-position affine y[b,i] = x[b,i]*a[i] + c[i], i over (C,H,W)
+__global__ void __launch_bounds__(kThreads) affine_pos_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                              const float* __restrict__ a, const float* __restrict__ c,
+                                                              long long n4, long long total4) {
+  pdl_trigger();
+  pdl_wait();
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total4;
+       t += (long long)gridDim.x * blockDim.x) {
+    const long long i = t % n4;
+    const float4 v = ld_stream(reinterpret_cast<const float4*>(x) + t);
+    const float4 av = __ldg(reinterpret_cast<const float4*>(a) + i), cv = __ldg(reinterpret_cast<const float4*>(c) + i);
+    st_stream(reinterpret_cast<float4*>(y) + t,
+              make_float4(fmaf(v.x, av.x, cv.x), fmaf(v.y, av.y, cv.y), fmaf(v.z, av.z, cv.z), fmaf(v.w, av.w, cv.w)));
+  }
+}
+__global__ void __launch_bounds__(kThreads) affine_pos_scalar_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                                     const float* __restrict__ a,
+                                                                     const float* __restrict__ c, long long n,
+                                                                     long long total) {
+  pdl_trigger();
+  pdl_wait();
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x)
+    y[t] = fmaf(x[t], a[t % n], c[t % n]);
+}
+
+// per-position mean and biased variance (+eps) over the batch dimension: one thread per position, coalesced over i
+__global__ void __launch_bounds__(kThreads) batch_stats_pos_kernel(const float* __restrict__ x, float* __restrict__ mean,
+                                                                   float* __restrict__ var, int B, long long n,
+                                                                   float eps) {
+  pdl_trigger();
+  pdl_wait();
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float s = 0.0f;
+    for (int b = 0; b < B; ++b) s += x[b * n + i];
+    const float m = s / (float)B;
+    float q = 0.0f;
+    for (int b = 0; b < B; ++b) { const float d = x[b * n + i] - m; q = fmaf(d, d, q); }
+    mean[i] = m;
+    var[i] = q / (float)B + eps;
+  }
+}
+
 __global__ void add_scalar_kernel(float* __restrict__ logdet, const float* __restrict__ addend, float alpha, int B) {
   pdl_trigger();
   pdl_wait();
@@ -903,6 +946,26 @@ extern "C" int rfk_convlstm_pointwise_ws(float* cc, int cc_ld, const float* bias
       cc, cc_ld, bias, c_prev, c_prev_bstride, peep, h_out, h_bstride, c_next, c_next_bstride, (__nv_bfloat16*)h_nhwc, h_off,
       h_ld, Hc, HW, zero_cc, total);
   return check_launch("rfk_convlstm_pointwise_ws");
+}
+
+extern "C" int rfk_affine_pos(const float* x, float* y, const float* a, const float* c, int B, long long n,
+                              void* stream) {
+  RFK_REQUIRE(x && y && a && c && B > 0 && n > 0, "rfk_affine_pos: null pointer or empty shape");
+  const long long total = (long long)B * n;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n % 4 == 0 && aligned16(x) && aligned16(y) && aligned16(a) && aligned16(c))
+    RFK_LAUNCH(affine_pos_kernel, stream_grid(total / 4, kThreads, 8), kThreads, 0, st, x, y, a, c, n / 4, total / 4);
+  else
+    RFK_LAUNCH(affine_pos_scalar_kernel, stream_grid(total, kThreads, 8), kThreads, 0, st, x, y, a, c, n, total);
+  return check_launch("rfk_affine_pos");
+}
+
+extern "C" int rfk_batch_stats_pos(const float* x, float* mean, float* var, int B, long long n, float eps,
+                                   void* stream) {
+  RFK_REQUIRE(x && mean && var && B > 0 && n > 0, "rfk_batch_stats_pos: null pointer or empty shape");
+  RFK_LAUNCH(batch_stats_pos_kernel, stream_grid(n, kThreads, 8), kThreads, 0, (cudaStream_t)stream, x, mean, var, B, n,
+             eps);
+  return check_launch("rfk_batch_stats_pos");
 }
 
 extern "C" int rfk_add_scalar(float* logdet, const float* addend, float alpha, int B, void* stream) {

@@ -69,6 +69,32 @@ def actnorm_init(x, bias, logs):
     call("rfk_actnorm_init", x.data_ptr(), _chk(bias).data_ptr(), _chk(logs).data_ptr(), 0, 0, B, C, H * W, _stream())
 
 
+def batch_stats_pos(x, eps):
+    """Per-position (C,H,W) mean and biased variance + eps over the batch; returns ([C,H,W], [C,H,W])."""
+    _chk(x, name="x")
+    B, C, H, W = x.shape
+    mean = torch.empty(C, H, W, device=x.device, dtype=torch.float32)
+    var = torch.empty_like(mean)
+    call("rfk_batch_stats_pos", x.data_ptr(), mean.data_ptr(), var.data_ptr(), B, C * H * W, float(eps), _stream())
+    return mean, var
+
+
+def affine_pos(x, a, c):
+    """y[b,i] = x[b,i]*a[i] + c[i] with a, c of shape [C,H,W] (contiguous f32)."""
+    _chk(x, name="x")
+    B = x.shape[0]
+    y = torch.empty_like(x)
+    call("rfk_affine_pos", x.data_ptr(), y.data_ptr(), _chk(a).data_ptr(), _chk(c).data_ptr(), B, x[0].numel(), _stream())
+    return y
+
+
+def channel_stats(x, mean, std):
+    """Per-channel mean and UNBIASED std of x [B,C,H,W] over (B,H,W) into the given [C] tensors."""
+    _chk(x, name="x")
+    B, C, H, W = x.shape
+    call("rfk_actnorm_init", x.data_ptr(), 0, 0, _chk(mean).data_ptr(), _chk(std).data_ptr(), B, C, H * W, _stream())
+
+
 def mix1x1(x, Wm, bvec=None, side=None, side_n=0, side_off=0, logdet=None, addend=None, alpha=1.0):
     """y = Wm x + bvec per pixel; optionally logdet[b] += alpha * addend (device scalar) in the same launch."""
     _chk(x, name="x")

@@ -27,7 +27,7 @@ warnings.filterwarnings("ignore")
 
 from Flow import ListGlow  # noqa: E402
 from Flow.glow import GlowStep  # noqa: E402
-from Flow.glow_modules import ActNorm, AffineCoupling, InvConv, Split2d, Squeeze2d  # noqa: E402
+from Flow.glow_modules import ActNorm, AffineCoupling, BatchNormFlow, InvConv, Split2d, Squeeze2d  # noqa: E402
 from Utils import ConvLSTM  # noqa: E402
 
 
@@ -200,6 +200,47 @@ def main():
                              "eps_prior": eps_prior, "eps_split": eps_split, "x_sample": xs.detach(),
                              "temperature": 0.9, "args": vars(a), "x_size": [B, 1, 16, 16],
                              "cond_sizes": cond_sizes, "base_size": [B, 0, 2, 2]})
+
+    # ---- BatchNormFlow (flow_norm='batchnorm') and a GlowStep / ListGlow built on it, base_norm='batchnorm' ----------
+    torch.manual_seed(41)
+    m = BatchNormFlow([4, 3, 4, 5], momentum=0.25).train()
+    perturb(m, g, 0.3)
+    x = R(4, 3, 4, 5) * 1.5 + 0.2
+    y, ld = m(x, logdet=torch.zeros(4), reverse=False)        # training: batch statistics, running buffers updated
+    d = {"x": x, "sd0": {"log_gamma": m.log_gamma.detach().clone(), "beta": m.beta.detach().clone()},
+         "momentum": 0.25, "y_train": y.detach(), "logdet_train": ld.detach(), "sd_after": sd_of(m)}
+    m.eval()
+    y2, ld2 = m(x[:2] * 0.7, logdet=torch.zeros(2), reverse=False)
+    xr, ldr = m(y2.detach(), logdet=ld2.detach(), reverse=True)
+    d.update(x2=x[:2] * 0.7, y_eval=y2.detach(), logdet_eval=ld2.detach(), x_rev=xr.detach(), logdet_rev=ldr.detach())
+    save("batchnormflow", d)
+
+    a = glow_args(flow_norm="batchnorm", base_norm="batchnorm", flow_batchnorm_momentum=0.0, L=2, K=2)
+    cond_sizes = [[B, 4, 8, 8], [B, 6, 4, 4]]
+    torch.manual_seed(43)
+    m = ListGlow([B, 1, 16, 16], cond_sizes, [B, 5, 4, 4], a).eval()
+    perturb(m, g)
+    with torch.no_grad():
+        for name, buf in m.named_buffers():
+            if name.endswith("running_var"):
+                buf.copy_(torch.rand(buf.shape, generator=g) + 0.5)
+            elif name.endswith("running_mean"):
+                buf.copy_(torch.randn(buf.shape, generator=g) * 0.2)
+    x = torch.floor(torch.rand(B, 1, 16, 16, generator=g) * 256) / 256 - 0.5
+    conds = [R(*s) for s in cond_sizes]
+    base = R(B, 5, 4, 4)
+    torch.manual_seed(47)
+    noise = torch.zeros_like(x).uniform_(0, 1.0 / 2 ** a.n_bits)
+    torch.manual_seed(47)
+    z_lp, nll = m.log_prob(x, conds, base, logdet=0)
+    eps_prior = R(B, 8, 4, 4)
+    eps_split = [R(B, 2, 8, 8)]
+    with FixedNormalSample([eps_prior, eps_split[0]]):
+        xs = m.sample(None, conds, base, num_samples=B, temperature=0.8)
+    save("listglow_batchnorm", {"x": x, "cond": conds, "base": base, "sd": sd_of(m), "noise": noise,
+                                "z_logprob": z_lp.detach(), "nll": nll.detach(), "eps_prior": eps_prior,
+                                "eps_split": eps_split, "x_sample": xs.detach(), "temperature": 0.8, "args": vars(a),
+                                "x_size": [B, 1, 16, 16], "cond_sizes": cond_sizes, "base_size": [B, 5, 4, 4]})
 
     # ---- ConvLSTM ------------------------------------------------------------
     torch.manual_seed(37)

@@ -372,3 +372,43 @@ def test_listglow_config_d_shape_vs_oracle(rf):
         xs = m.sample(None, [c.cuda() for c in conds], base.cuda(), num_samples=B, temperature=0.7,
                       eps_prior=eps_prior.cuda(), eps_list=[e.cuda() for e in eps])
         assert max_rel(xs, x_ref) < 2 * BF16_TOL
+
+
+def test_batchnormflow_module_golden(rf):
+    g = load_golden("batchnormflow")
+    with torch.no_grad():
+        m = rf.Flow.BatchNormFlow([4, 3, 4, 5], momentum=g["momentum"]).cuda().train()
+        m.log_gamma.copy_(g["sd0"]["log_gamma"])
+        m.beta.copy_(g["sd0"]["beta"])
+        y, ld = m(g["x"].cuda(), logdet=torch.zeros(4).cuda(), reverse=False)     # batch statistics
+        torch.testing.assert_close(y.cpu(), g["y_train"], rtol=1e-4, atol=1e-4)
+        torch.testing.assert_close(ld.cpu(), g["logdet_train"], rtol=1e-4, atol=1e-4)
+        torch.testing.assert_close(m.running_mean.cpu(), g["sd_after"]["running_mean"], rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(m.running_var.cpu(), g["sd_after"]["running_var"], rtol=1e-5, atol=1e-6)
+        m.eval()
+        y2, ld2 = m(g["x2"].cuda(), logdet=torch.zeros(2).cuda(), reverse=False)
+        torch.testing.assert_close(y2.cpu(), g["y_eval"], rtol=1e-4, atol=1e-4)
+        torch.testing.assert_close(ld2.cpu(), g["logdet_eval"], rtol=1e-4, atol=1e-4)
+        xr, ldr = m(y2, logdet=ld2, reverse=True)
+        torch.testing.assert_close(xr.cpu(), g["x_rev"], rtol=1e-4, atol=1e-4)
+        torch.testing.assert_close(ldr.cpu(), g["logdet_rev"], rtol=1e-4, atol=1e-4)
+
+
+def test_listglow_batchnorm_golden(rf):
+    """flow_norm='batchnorm' (BatchNormFlow) + base_norm='batchnorm' (BatchNorm2d in the prior), eval mode."""
+    g = load_golden("listglow_batchnorm")
+    with torch.no_grad():
+        m, a = build_listglow(rf, g)
+        conds = [c.cuda() for c in g["cond"]]
+        z, nll = m.log_prob(g["x"].cuda(), conds, g["base"].cuda(), logdet=0, noise=g["noise"].cuda())
+        assert max_rel(z, g["z_logprob"]) < BF16_TOL
+        assert_ld(nll, g["nll"], atol=0.2)
+        xs = m.sample(None, conds, g["base"].cuda(), num_samples=2, temperature=g["temperature"],
+                      eps_prior=g["eps_prior"].cuda(), eps_list=[e.cuda() for e in g["eps_split"]])
+        assert max_rel(xs, g["x_sample"]) < BF16_TOL
+        # training mode runs (batch statistics for the flow norm and for the prior's BatchNorm2d) and updates buffers
+        m.train()
+        rv0 = m.prior[0].norm_type.running_var.clone()
+        z2, nll2 = m.log_prob(g["x"].cuda(), conds, g["base"].cuda(), logdet=0, noise=g["noise"].cuda())
+        assert torch.isfinite(nll2).all() and not torch.equal(rv0, m.prior[0].norm_type.running_var)
+        assert int(m.prior[0].norm_type.num_batches_tracked) == 1

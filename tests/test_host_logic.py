@@ -46,8 +46,14 @@ def test_bad_enums_assert_like_reference():
         rf.Split2d([2, 8, 4, 4], [2, 6, 4, 4], clamp_function="tanh")
     with pytest.raises(AssertionError):
         rf.ActFun("gelu")
-    with pytest.raises(NotImplementedError):
-        rf.Conv2dNorm(4, 4, norm="batchnorm")
+
+
+def test_batchnorm_options_state_dict():
+    g = load_golden("listglow_batchnorm")
+    m = rf.ListGlow(g["x_size"], g["cond_sizes"], g["base_size"], types.SimpleNamespace(**g["args"]))
+    assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == {k: tuple(v.shape) for k, v in g["sd"].items()}
+    m.load_state_dict(g["sd"])
+    assert isinstance(m.glow_frame[1].norm, rf.Flow.BatchNormFlow)
 
 
 def im2col_gemm(x, wp, cin_pad, N, k):

@@ -146,3 +146,32 @@ def test_convlstm():
     close(out2, g["out2"])
     close(h2, g["h2"])
     close(c2, g["c2"])
+
+
+def test_batchnormflow():
+    g = load_golden("batchnormflow")
+    lg, beta = g["sd0"]["log_gamma"], g["sd0"]["beta"]
+    y, ld, rm, rv = O.batchnorm_flow(g["x"], lg, beta, torch.zeros_like(lg), torch.ones_like(lg), torch.zeros(4), False,
+                                     training=True, momentum=g["momentum"])
+    close(y, g["y_train"], atol=1e-4)
+    close(ld, g["logdet_train"], atol=1e-4)
+    close(rm, g["sd_after"]["running_mean"])
+    close(rv, g["sd_after"]["running_var"])
+    y2, ld2, _, _ = O.batchnorm_flow(g["x2"], lg, beta, rm, rv, torch.zeros(2), False)
+    close(y2, g["y_eval"], atol=1e-4)
+    close(ld2, g["logdet_eval"], atol=1e-4)
+    xr, ldr, _, _ = O.batchnorm_flow(y2, lg, beta, rm, rv, ld2, True)
+    close(xr, g["x_rev"], atol=1e-4)
+    close(ldr, g["logdet_rev"], atol=1e-4)
+
+
+def test_listglow_batchnorm():
+    g = load_golden("listglow_batchnorm")
+    a = g["args"]
+    z, nll = O.listglow_log_prob(g["x"], g["cond"], g["base"], g["sd"], a["L"], a["K"], a["n_bits"],
+                                 noise=g["noise"], learn_prior=True, **_kw(a))
+    close(z, g["z_logprob"], atol=1e-4)
+    close(nll, g["nll"], rtol=1e-5, atol=1e-3)
+    xs = O.listglow_sample(g["cond"], g["base"], g["sd"], a["L"], a["K"], g["eps_prior"], g["eps_split"],
+                           g["temperature"], learn_prior=True, **_kw(a))
+    close(xs, g["x_sample"], atol=1e-4)
