@@ -3,13 +3,14 @@
 Mirrors ``Flow/glow.py`` of cdglissov/recurrent-flows-msc (class names, constructor arguments,
 method signatures, ``state_dict`` keys).  One GlowStep forward is four kernel launches:
 
-  1. rfk_mix1x1              ActNorm folded into the invertible 1x1 conv, + bf16 z1 side output
-  2. rfk_conv_gemm           conv3x3 -> ActNorm -> ReLU               (tcgen05, bf16 NHWC out)
-  3. rfk_conv_gemm           conv1x1 -> ActNorm -> ReLU               (tcgen05, bf16 NHWC out)
-  4. rfk_conv_gemm_coupling  conv3x3 -> Conv2dZeros scale -> cross split -> clamp -> affine ->
-                             per-sample log-det                       (tcgen05, z2 updated in place)
+  1. rfk_mix1x1              ActNorm folded into the invertible 1x1 conv, + bf16 z1 side output, + the
+                             parameter-only log-det term
+  2. rfk_conv_gemm           conv3x3 -> ActNorm -> ReLU                         (tcgen05, bf16 NHWC out via TMA store)
+  3. rfk_conv1x1_taps_fused  conv1x1 -> ActNorm -> ReLU -> tap-split conv3x3    (tcgen05, hidden tile kept in TMEM)
+  4. rfk_coupling_tail_taps  tap gather -> Conv2dZeros scale -> cross split -> clamp -> affine -> per-sample log-det
 
-with no host synchronisation (the reference issues ~186 ATen ops and three .item() syncs per step).
+(steps 3 falls back to two rfk_conv_gemm launches, and 3+4 to rfk_conv_gemm_coupling, for shapes the fused kernels do
+not cover) with no host synchronisation (the reference issues ~186 ATen ops and three .item() syncs per step).
 """
 import numpy as np
 import torch
