@@ -756,6 +756,12 @@ static int make_plan(Plan& p, const char* who, const void* act, int B, int H, in
       stages = (SMEM_LIMIT - fixed) / (a_stage + b_chunk);
     }
   }
+  // a CTA that only ever sees one pixel tile gains nothing from resident weights: it would wait for ALL of them
+  // before its first MMA, whereas streamed weight chunks arrive stage by stage (latency-bound small levels / sampling)
+  if (resident && g.m_tiles * n_tiles * k_split <= sm_count()) {
+    resident = 0;
+    stages = (SMEM_LIMIT - fixed) / (a_stage + b_chunk);
+  }
   if (const char* s = getenv("RFK_GEMM_RESIDENT")) {
     if (atoi(s) == 0 && resident) {
       resident = 0;

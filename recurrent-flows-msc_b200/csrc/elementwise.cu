@@ -188,9 +188,30 @@ __global__ void __launch_bounds__(1024) mix1x1_kernel(const float* __restrict__ 
   float* bs = smem;                 // [C]
   float* xs = bs + C;               // [C][PT]
   const float* ws = Wm;             // [C][C]: shared memory when it fits, else L1-cached broadcast loads
+  // issue this thread's x loads first (independent of the weight staging below) so their latency overlaps it
+  const long long pix = blockIdx.x * (long long)PT + tx;
+  const bool ok = pix < npix;
+  const long long b = ok ? pix / HW : 0;
+  const int p = ok ? (int)(pix % HW) : 0;
+  const float* xp = x + b * C * HW + p;
+  float xr[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int i = ty + k * G;
+    xr[k] = (ok && i < C) ? xp[(long long)i * HW] : 0.0f;
+  }
   if (w_smem) {
-    float* wsm = xs + C * PT;
-    for (int i = tid; i < C * C; i += nthr) wsm[i] = Wm[i];
+    float* wsm = smem + (((C + C * PT) + 3) & ~3);   // 16-byte aligned for the 128-bit staging stores
+    const int n = C * C;
+    if ((n & 3) == 0 && (reinterpret_cast<uintptr_t>(Wm) & 15) == 0) {
+      const float4* src = reinterpret_cast<const float4*>(Wm);
+      float4* dst = reinterpret_cast<float4*>(wsm);
+#pragma unroll 4
+      for (int i = tid; i < (n >> 2); i += nthr) dst[i] = __ldg(src + i);
+    } else {
+#pragma unroll 4
+      for (int i = tid; i < n; i += nthr) wsm[i] = Wm[i];
+    }
     ws = wsm;
   }
   for (int i = tid; i < C; i += nthr) bs[i] = bvec ? bvec[i] : 0.0f;
@@ -198,12 +219,11 @@ __global__ void __launch_bounds__(1024) mix1x1_kernel(const float* __restrict__ 
     const float add = alpha * (*addend);
     for (int i = tid; i < B; i += nthr) logdet[i] += add;
   }
-  const long long pix = blockIdx.x * (long long)PT + tx;
-  const bool ok = pix < npix;
-  const long long b = ok ? pix / HW : 0;
-  const int p = ok ? (int)(pix % HW) : 0;
-  const float* xp = x + b * C * HW + p;
-  for (int i = ty; i < C; i += G) xs[i * PT + tx] = ok ? xp[(long long)i * HW] : 0.0f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int i = ty + k * G;
+    if (i < C) xs[i * PT + tx] = xr[k];
+  }
   __syncthreads();
   const int o0 = ty * 8;
   float acc[8];
@@ -795,7 +815,7 @@ extern "C" int rfk_mix1x1(const float* x, float* y, const float* Wm, const float
   RFK_REQUIRE(G <= 32, "rfk_mix1x1: C=%d is too large (max 256)", C);
   int PT = (256 / G) / 32 * 32;
   if (PT < 32) PT = 32;
-  size_t smem = ((size_t)C + (size_t)C * PT) * sizeof(float);
+  size_t smem = ((((size_t)C + (size_t)C * PT) + 3) & ~(size_t)3) * sizeof(float);
   const int w_smem = smem + (size_t)C * C * sizeof(float) <= 160 * 1024;
   if (w_smem) smem += (size_t)C * C * sizeof(float);
   if (side) RFK_REQUIRE(side_n >= 0 && side_n <= C && side_off >= 0 && side_off + side_n <= side_ld,
