@@ -190,6 +190,18 @@ int rfk_conv1x1_taps_fused(const void* act, int B, int H, int W, int act_ld, int
                            const void* w2, int hid, const float* scale2, const float* shift2, int act_fn,
                            const void* w9, int n3, int n3_pad, float* taps, void* stream);
 
+/* rfk_coupling_tail_taps fused with the 1x1 mix that follows it (forward: the next GlowStep's ActNorm+InvConv;
+ * reverse: the same GlowStep's InvConv^-1 + ActNorm^-1): z [B,C,H,W] holds the coupling's input (z1 | not yet updated z2),
+ * the updated tensor is formed in shared memory only and y = Wm*(z1 | z2') + bvec is written (plus the optional bf16
+ * side output and log-det scalar exactly as in rfk_mix1x1).  cpl_logdet (nullable) receives +/- sum(ls). */
+int rfk_coupling_taps_mix(const float* taps, const float* z, float* y, int B, int C, int H, int W,
+                          const float* scale, const float* shift,
+                          int clamp_type, const float* clamp_scale, const float* clamp_shift,
+                          float* cpl_logdet, int reverse,
+                          const float* Wm, const float* bvec,
+                          void* side_nhwc_bf16, int side_n, int side_off, int side_ld,
+                          float* logdet, const float* addend, float alpha, void* stream);
+
 /* ---- a5/a7  Gaussian log-density and sampling (Flow/glow_modules.py:362-368, glow.py:139,154)
  * params [B,2n,HW] f32 (nullable = zeros) holds (mean, raw) per `pairing`; std per `std_kind`.
  * logp : logdet[b] += sum_{j<n,p} log N(z[b,z_off+j,p]; mean, std)        (z has z_C channels)

@@ -21,6 +21,14 @@ from ..Utils.modules import ActFun
 from .glow_modules import (ActNorm, AffineCoupling, BatchNormFlow, Conv2dNorm, Conv2dZeros, InvConv,  # noqa: F401
                            Split2d, Squeeze2d, _Ctx, _ld_begin, _ld_end, _require_no_grad, _Versioned)
 
+import os
+
+# Fuse a coupling's tap gather + tail with the 1x1 mix that follows it (rfk_coupling_taps_mix) from this channel count up.
+# Measured on B200 (570 frames / 30-frame sampling): the fused kernel has one thread per (pixel, 8 outputs) doing up to
+# 4 x 18 gather loads serially and LOSES to the two specialised kernels at every level (6.56 vs 6.17 ms per step,
+# sampling 2.63 vs 2.27 ms), so it is off by default; the entry point stays (tested) for shapes where launches dominate.
+FUSE_GATHER_MIX_MIN_C = int(os.environ.get("RFK_FUSE_GATHER_MIX_MIN_C", str(1 << 30)))
+
 
 class GlowStep(nn.Module):
     """Flow/glow.py:10-41: norm -> invconv -> affine coupling (and the exact inverse)."""
@@ -95,22 +103,44 @@ class GlowStep(nn.Module):
             out, ld = self.norm(y, ld, True)
             _ctx.z1_packed = False   # the next reverse step packs z1 itself (the side output would be pre-normalisation)
             return out, _ld_end(ld, extra)
+        fuse_gm = C >= FUSE_GATHER_MIX_MIN_C
         if not reverse:
-            self.norm.maybe_initialize(x)
-            Wf, bf, _, _, _ = self._folded()
-            y = ops.mix1x1(x, Wf, bf, side=_ctx.nn_in, side_n=C // 2, side_off=cc,
-                           logdet=ld, addend=None if ld is None else self._dlogdet(H * W), alpha=1.0)
+            pend = _ctx.pending
+            if pend is not None and pend[2].data_ptr() == x.data_ptr() and self.norm.is_initialized():
+                # the previous step's coupling tail (tap gather + affine) is still pending: absorb it into this step's mix
+                _ctx.pending = None
+                Wf, bf, _, _, _ = self._folded()
+                dl = None if ld is None else self._dlogdet(H * W)
+                y = ops.coupling_taps_mix(pend[1], x, *pend[0].tail_params(), pend[3], False, Wf, bf,
+                                          side=_ctx.nn_in, side_n=C // 2, side_off=cc, logdet=ld, addend=dl, alpha=1.0)
+            else:
+                _ctx.flush()
+                self.norm.maybe_initialize(x)
+                Wf, bf, _, _, _ = self._folded()
+                dl = None if ld is None else self._dlogdet(H * W)
+                y = ops.mix1x1(x, Wf, bf, side=_ctx.nn_in, side_n=C // 2, side_off=cc, logdet=ld, addend=dl, alpha=1.0)
             _ctx.z1_packed = True
-            y, ld = self.affine(y, condition, ld, False, _ctx=_ctx)
+            kind, t = self.affine.run_nn(y, condition, _ctx)
             _ctx.z1_packed = False
+            if kind == "taps" and not own_ctx and fuse_gm:
+                _ctx.pending = (self.affine, t, y, ld)    # the next module's mix (or ListGlow's flush) applies the tail
+            else:
+                self.affine.finish(kind, t, y, ld, False)
             return y, _ld_end(ld, extra)
-        if own_ctx:
-            x = x.clone()  # the coupling inverse below works in place
-        y, ld = self.affine(x, condition, ld, True, _ctx=_ctx)
-        self.norm.maybe_initialize(y)
-        _, _, Wr, br, _ = self._folded()
-        out = ops.mix1x1(y, Wr, br, side=_ctx.nn_in, side_n=C // 2, side_off=cc,
-                         logdet=ld, addend=None if ld is None else self._dlogdet(H * W), alpha=-1.0)
+        kind, t = self.affine.run_nn(x, condition, _ctx)
+        if kind == "taps" and self.norm.is_initialized() and fuse_gm:
+            # coupling inverse (tap gather) + InvConv^-1 + ActNorm^-1 in one launch; x itself is not modified
+            _, _, Wr, br, _ = self._folded()
+            dl = None if ld is None else self._dlogdet(H * W)
+            out = ops.coupling_taps_mix(t, x, *self.affine.tail_params(), ld, True, Wr, br, side=_ctx.nn_in,
+                                        side_n=C // 2, side_off=cc, logdet=ld, addend=dl, alpha=-1.0)
+        else:
+            y = x.clone() if own_ctx else x   # the coupling inverse works in place
+            self.affine.finish(kind, t, y, ld, True)
+            self.norm.maybe_initialize(y)
+            _, _, Wr, br, _ = self._folded()
+            dl = None if ld is None else self._dlogdet(H * W)
+            out = ops.mix1x1(y, Wr, br, side=_ctx.nn_in, side_n=C // 2, side_off=cc, logdet=ld, addend=dl, alpha=-1.0)
         _ctx.z1_packed = True   # the next reverse step of this level reads this z1
         return out, _ld_end(ld, extra)
 
@@ -206,6 +236,8 @@ class ListGlow(nn.Module):
         ld, extra = _ld_begin(logdet, z.shape[0], z.device)
         ctx = None
         for step in self.glow_frame:
+            if ctx is not None and not isinstance(step, GlowStep):
+                ctx.flush()   # a coupling tail left pending for a following mix: no mix follows, apply it now
             if isinstance(step, Squeeze2d):
                 z = step(z, undo_squeeze=False)
                 ctx = self._level_ctx(z, condition[l])
@@ -214,6 +246,8 @@ class ListGlow(nn.Module):
                 l = l + 1
             else:
                 z, ld = step(z, condition[l], logdet=ld, reverse=False, _ctx=ctx)
+        if ctx is not None:
+            ctx.flush()
         return z, _ld_end(ld, extra)
 
     def uniform_binning_correction(self, x):

@@ -76,6 +76,16 @@ class _Ctx:
         self.nn_in = nn_in
         self.cond_channels = cond_channels
         self.z1_packed = False
+        self.pending = None   # (coupling module, taps, z, logdet buffer): a forward coupling whose tail is not applied yet
+
+    def flush(self):
+        """Apply a pending coupling tail in place (when no 1x1 mix follows that could absorb it); returns its tensor."""
+        if self.pending is None:
+            return None
+        coupling, taps, z, ld = self.pending
+        self.pending = None
+        coupling.finish("taps", taps, z, ld, False)
+        return z
 
 
 # ----------------------------------------------------------------------------------------
@@ -111,6 +121,8 @@ class ActNorm(nn.Module):
             return
         with torch.no_grad():
             ops.actnorm_init(ops.f32c(input), self.bias.data, self.logs.data)
+            self.bias.add_(0.0)   # the kernel wrote through raw pointers: bump the version counters so that every
+            self.logs.add_(0.0)   # cache derived from these parameters (here and in GlowStep) is rebuilt
         self._cache.clear()
 
     def maybe_initialize(self, input):
@@ -371,10 +383,16 @@ class AffineCoupling(nn.Module):
             self.__dict__["_perm_cache"] = hit
         return hit
 
-    def forward(self, x, condition, logdet, reverse, _ctx=None):
-        _require_no_grad()
-        assert condition.shape[2:4] == x.shape[2:4], "condition and x in affine needs to match"
-        z = ops.f32c(x)
+    def tail_params(self):
+        """(scale, shift, clamp_type, clamp_scale, clamp_shift) of the coupling tail: Conv2dZeros' affine and the clamp."""
+        scale, shift = self.net[4].affine()
+        cs = self.scale.detach().reshape(-1) if self.clamp_type == "realnvp" else None
+        csh = self.scale_shift.detach().reshape(-1) if self.clamp_type == "realnvp" else None
+        return scale, shift, self.clamp_type, cs, csh
+
+    def run_nn(self, z, condition, _ctx):
+        """The coupling network on z1 = z[:, :C/2] and the condition.  Returns ("taps", taps [B,9C,H,W]) when the last
+        conv runs in tap-split form (the caller gathers the planes, alone or fused with a 1x1 mix), else ("h2", h2)."""
         B, C, H, W = z.shape
         half, cc = C // 2, condition.shape[1]
         dev = z.device
@@ -382,43 +400,55 @@ class AffineCoupling(nn.Module):
             nn_in = ops.workspace(("cpl_in", half + cc), (B, H, W, ops.cin_pad(half + cc)), dev)
             ops.pack_nhwc(ops.f32c(condition), 0, cc, nn_in, 0)
             ops.pack_nhwc(z, 0, half, nn_in, cc)
-            out = z.clone()          # module contract: inputs are never modified
         else:
             nn_in = _ctx.nn_in
             if not _ctx.z1_packed:
                 ops.pack_nhwc(z, 0, half, nn_in, cc)
-            out = z                  # ListGlow owns this intermediate: update z2 in place
         hp = ops.cin_pad(self.hidden_units)
         h1 = ops.workspace(("cpl_h1", self.hidden_units), (B, H, W, hp), dev)
-        h2 = ops.workspace(("cpl_h2", self.hidden_units), (B, H, W, hp), dev)
         self.net[0].fused(nn_in, h1, self.non_lin, "cz", self._perm(dev))
-        last = self.net[4]
-        mid = self.net[2]
+        last, mid = self.net[4], self.net[2]
+        tap_split = last.taps == 9 and 9 * C <= TAP_SPLIT_MAX_N
         # conv1x1 -> ActNorm -> act -> tap-split conv3x3 in one kernel (h2 stays in tensor memory) when the shapes allow
-        b2b = (FUSE_CONV2_TAPS and last.taps == 9 and mid.taps == 1 and ops.pad_to(9 * C, 16) <= 128
+        b2b = (FUSE_CONV2_TAPS and tap_split and mid.taps == 1 and ops.pad_to(9 * C, 16) <= 128
                and self.hidden_units % 64 == 0 and self.hidden_units <= 256 and mid.ready_for_fusion())
+        h2 = None
         if not b2b:
+            h2 = ops.workspace(("cpl_h2", self.hidden_units), (B, H, W, hp), dev)
             mid.fused(h1, h2, self.non_lin)
-        scale, shift = last.affine()
-        ld, extra = _ld_begin(logdet, B, dev, inplace=_ctx is not None)
-        cs = self.scale.detach().reshape(-1) if self.clamp_type == "realnvp" else None
-        csh = self.scale_shift.detach().reshape(-1) if self.clamp_type == "realnvp" else None
-        if last.taps == 9 and 9 * C <= TAP_SPLIT_MAX_N:
-            # few output channels: one 1x1 GEMM with N = 9*C (activations read once, not once per tap),
-            # then a streaming gather of the nine shifted planes fused with the coupling tail
-            wgt9, cin_pad = last.packed_taps()
-            taps = ops.workspace(("cpl_taps", C), (B, 9 * C, H, W), dev, torch.float32)
-            if b2b:
-                w2, cin_pad2 = mid.packed()
-                s2, t2 = mid.affine()
-                ops.conv1x1_taps_fused(h1, cin_pad2, w2, self.hidden_units, s2, t2, self.non_lin, wgt9, 9 * C, taps)
-            else:
-                ops.conv_gemm(h2, cin_pad, wgt9, 9 * C, 1, None, None, "none", taps)
-            ops.coupling_tail_taps(taps, out, scale, shift, self.clamp_type, cs, csh, ld, reverse)
+        if not tap_split:
+            return "h2", h2
+        # few output channels: one 1x1 GEMM with N = 9*C (activations read once, not once per tap); the nine shifted
+        # planes are gathered afterwards together with the coupling tail
+        wgt9, cin_pad = last.packed_taps()
+        taps = ops.workspace(("cpl_taps", C), (B, 9 * C, H, W), dev, torch.float32)
+        if b2b:
+            w2, cin_pad2 = mid.packed()
+            s2, t2 = mid.affine()
+            ops.conv1x1_taps_fused(h1, cin_pad2, w2, self.hidden_units, s2, t2, self.non_lin, wgt9, 9 * C, taps)
         else:
+            ops.conv_gemm(h2, cin_pad, wgt9, 9 * C, 1, None, None, "none", taps)
+        return "taps", taps
+
+    def finish(self, kind, t, out, ld, reverse):
+        """Apply the coupling tail in place on out[:, C/2:] from run_nn's result."""
+        scale, shift, clamp_type, cs, csh = self.tail_params()
+        if kind == "taps":
+            ops.coupling_tail_taps(t, out, scale, shift, clamp_type, cs, csh, ld, reverse)
+        else:
+            last = self.net[4]
             wgt, cin_pad = last.packed()
-            ops.conv_gemm_coupling(h2, cin_pad, wgt, C, last.taps, scale, shift, out, self.clamp_type, cs, csh, ld,
+            ops.conv_gemm_coupling(t, cin_pad, wgt, out.shape[1], last.taps, scale, shift, out, clamp_type, cs, csh, ld,
                                    reverse)
+
+    def forward(self, x, condition, logdet, reverse, _ctx=None):
+        _require_no_grad()
+        assert condition.shape[2:4] == x.shape[2:4], "condition and x in affine needs to match"
+        z = ops.f32c(x)
+        kind, t = self.run_nn(z, condition, _ctx)
+        out = z.clone() if _ctx is None else z   # module contract: inputs are never modified; ListGlow owns its intermediates
+        ld, extra = _ld_begin(logdet, z.shape[0], z.device, inplace=_ctx is not None)
+        self.finish(kind, t, out, ld, reverse)
         return out, _ld_end(ld, extra)
 
 

@@ -36,6 +36,9 @@ SIGNATURES = {
                                c_void_p, c_void_p, c_int, c_void_p],
     "rfk_conv1x1_taps_fused": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int,
                                c_void_p, c_int, c_int, c_void_p, c_void_p],
+    "rfk_coupling_taps_mix": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
+                              c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                              c_void_p, c_void_p, c_float, c_void_p],
     "rfk_gauss_logp": [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
     "rfk_gauss_sample": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_int, c_int,
                          c_void_p],

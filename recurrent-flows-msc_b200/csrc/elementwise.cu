@@ -170,6 +170,19 @@ __global__ void __launch_bounds__(512) actnorm_init_kernel(const float* __restri
 // HBM-bound (AI = C/4 flop/B): one thread per pixel, x tile and Wm staged in shared memory,
 // 8 output channels register-blocked.  Optional bf16 NHWC side output of the first side_n channels.
 // ------------------------------------------------------------------------------------------
+// optional producer for mix1x1_kernel's input: a pending tap-split coupling (rfk_coupling_taps_mix)
+struct CouplingSrc {
+  const float* taps;    // [B, 9C, H, W] or null = plain mix
+  const float* scale;   // Conv2dZeros affine [C]
+  const float* shift;
+  int clamp_type;
+  const float* cs;
+  const float* csh;
+  float* logdet;        // += (-=) sum of the coupling's log-scales, or null
+  int reverse;
+  int H, W;
+};
+
 // CTA = PT pixels x G output groups: thread (tx, ty) computes outputs [8*ty, 8*ty+8) of pixel tx, reading the
 // x tile (staged once in shared memory, conflict-free) and Wm (shared memory broadcast).  Optionally also adds
 // alpha * (*addend) to logdet[0..B) -- the parameter-only log-det term of ActNorm + InvConv -- so that a GlowStep
@@ -179,7 +192,7 @@ __global__ void __launch_bounds__(1024) mix1x1_kernel(const float* __restrict__ 
                                                       int C, int HW, long long npix, __nv_bfloat16* __restrict__ side,
                                                       int side_n, int side_off, int side_ld, int w_smem,
                                                       float* __restrict__ logdet, const float* __restrict__ addend,
-                                                      float alpha, int B) {
+                                                      float alpha, int B, const CouplingSrc cp) {
   pdl_trigger();
   pdl_wait();
   extern __shared__ float smem[];
@@ -199,6 +212,51 @@ __global__ void __launch_bounds__(1024) mix1x1_kernel(const float* __restrict__ 
   for (int k = 0; k < 8; ++k) {
     const int i = ty + k * G;
     xr[k] = (ok && i < C) ? xp[(long long)i * HW] : 0.0f;
+  }
+  if (cp.taps) {
+    // the input is the PREVIOUS coupling's un-finished state: channels >= C/2 still need (z2 + t)*e^{ls} (or the inverse),
+    // with (t, ls) gathered from that coupling's nine tap planes -- see coupling_taps_kernel
+    const int half = C >> 1, W_ = cp.W, H_ = cp.H;
+    const int yy0 = p / W_, xx0 = p - yy0 * W_;
+    const float* tb = cp.taps + b * 9 * C * HW;
+    float ld_acc = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int i = ty + k * G;
+      if (ok && i >= half && i < C) {
+        const int j = i - half;
+        float s_sum = 0.0f, r_sum = 0.0f;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+          const int yy = yy0 + ky - 1;
+          if (yy < 0 || yy >= H_) continue;
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) {
+            const int xx = xx0 + kx - 1;
+            if (xx < 0 || xx >= W_) continue;
+            const float* q = tb + ((long long)((3 * ky + kx) * C + 2 * j) * HW) + yy * W_ + xx;
+            s_sum += __ldg(q);
+            r_sum += __ldg(q + HW);
+          }
+        }
+        const float sft = fmaf(s_sum, __ldg(cp.scale + 2 * j), __ldg(cp.shift + 2 * j));
+        const float raw = fmaf(r_sum, __ldg(cp.scale + 2 * j + 1), __ldg(cp.shift + 2 * j + 1));
+        float a = 0.0f, bb = 0.0f;
+        if (cp.clamp_type == RFK_CLAMP_REALNVP) { a = __ldg(cp.cs + j); bb = __ldg(cp.csh + j); }
+        const float ls = clamp_ls(raw, cp.clamp_type, a, bb);
+        ld_acc += ls;
+        xr[k] = cp.reverse ? xr[k] * expf(-ls) - sft : (xr[k] + sft) * expf(ls);
+      }
+    }
+    if (cp.logdet) {
+      const float v = cp.reverse ? -ld_acc : ld_acc;
+      if ((HW & 31) == 0) {   // a warp's 32 pixels lie in one sample: one atomic per warp
+        const float r = warp_sum(ok ? v : 0.0f);
+        if ((tx & 31) == 0 && ok) atomicAdd(cp.logdet + b, r);
+      } else if (ok && v != 0.0f) {
+        atomicAdd(cp.logdet + b, v);
+      }
+    }
   }
   if (w_smem) {
     float* wsm = smem + (((C + C * PT) + 3) & ~3);   // 16-byte aligned for the 128-bit staging stores
@@ -792,6 +850,29 @@ extern "C" int rfk_actnorm_init(const float* x, float* bias, float* logs, float*
   return check_launch("rfk_actnorm_init");
 }
 
+static int launch_mix_generic(const char* who, const float* x, float* y, const float* Wm, const float* bvec, int B, int C,
+                              int HW, void* side, int side_n, int side_off, int side_ld, float* logdet,
+                              const float* addend, float alpha, const rfk::CouplingSrc& cp, void* stream) {
+  const int G = (C + 7) / 8;
+  RFK_REQUIRE(G <= 32, "%s: C=%d is too large (max 256)", who, C);
+  int PT = (256 / G) / 32 * 32;
+  if (PT < 32) PT = 32;
+  size_t smem = ((((size_t)C + (size_t)C * PT) + 3) & ~(size_t)3) * sizeof(float);
+  const int w_smem = smem + (size_t)C * C * sizeof(float) <= 160 * 1024;
+  if (w_smem) smem += (size_t)C * C * sizeof(float);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(mix1x1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("%s: %s", who, cudaGetErrorString(e)); return RFK_ECUDA; }
+    configured = smem;
+  }
+  long long npix = (long long)B * HW;
+  RFK_LAUNCH(mix1x1_kernel, ceil_div(npix, PT), dim3(PT, G), smem, (cudaStream_t)stream,
+             x, y, Wm, bvec, C, HW, npix, (__nv_bfloat16*)side, side ? side_n : 0, side_off, side_ld, w_smem, logdet, addend,
+             alpha, B, cp);
+  return check_launch(who);
+}
+
 extern "C" int rfk_mix1x1(const float* x, float* y, const float* Wm, const float* bvec, int B, int C, int HW,
                           void* side, int side_n, int side_off, int side_ld, float* logdet, const float* addend,
                           float alpha, void* stream) {
@@ -811,26 +892,32 @@ extern "C" int rfk_mix1x1(const float* x, float* y, const float* Wm, const float
                                                                           side ? side_n : 0, side_off, side_ld, logdet, addend, alpha, B);
     return check_launch("rfk_mix1x1");
   }
-  const int G = (C + 7) / 8;
-  RFK_REQUIRE(G <= 32, "rfk_mix1x1: C=%d is too large (max 256)", C);
-  int PT = (256 / G) / 32 * 32;
-  if (PT < 32) PT = 32;
-  size_t smem = ((((size_t)C + (size_t)C * PT) + 3) & ~(size_t)3) * sizeof(float);
-  const int w_smem = smem + (size_t)C * C * sizeof(float) <= 160 * 1024;
-  if (w_smem) smem += (size_t)C * C * sizeof(float);
+  rfk::CouplingSrc none;
+  none.taps = nullptr; none.scale = nullptr; none.shift = nullptr; none.clamp_type = 0; none.cs = nullptr; none.csh = nullptr;
+  none.logdet = nullptr; none.reverse = 0; none.H = 1; none.W = HW;
+  return launch_mix_generic("rfk_mix1x1", x, y, Wm, bvec, B, C, HW, side, side_n, side_off, side_ld, logdet, addend, alpha,
+                            none, stream);
+}
+
+extern "C" int rfk_coupling_taps_mix(const float* taps, const float* z, float* y, int B, int C, int H, int W,
+                                     const float* scale, const float* shift, int clamp_type, const float* clamp_scale,
+                                     const float* clamp_shift, float* cpl_logdet, int reverse, const float* Wm,
+                                     const float* bvec, void* side, int side_n, int side_off, int side_ld,
+                                     float* logdet, const float* addend, float alpha, void* stream) {
+  RFK_REQUIRE(taps && z && y && Wm && scale && shift && B > 0 && C > 0 && C % 2 == 0 && H > 0 && W > 0,
+              "rfk_coupling_taps_mix: null pointer or bad shape (C must be even)");
+  RFK_REQUIRE(z != y, "rfk_coupling_taps_mix: in-place is not supported");
+  RFK_REQUIRE(clamp_type >= 0 && clamp_type <= 3, "rfk_coupling_taps_mix: unknown clamp_type %d", clamp_type);
+  RFK_REQUIRE(clamp_type != RFK_CLAMP_REALNVP || (clamp_scale && clamp_shift),
+              "rfk_coupling_taps_mix: realnvp clamp needs scale and scale_shift");
+  RFK_REQUIRE(!logdet || addend, "rfk_coupling_taps_mix: logdet given without an addend");
   if (side) RFK_REQUIRE(side_n >= 0 && side_n <= C && side_off >= 0 && side_off + side_n <= side_ld,
-                        "rfk_mix1x1: bad side-output window");
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(mix1x1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { set_error("rfk_mix1x1: %s", cudaGetErrorString(e)); return RFK_ECUDA; }
-    configured = smem;
-  }
-  long long npix = (long long)B * HW;
-  RFK_LAUNCH(mix1x1_kernel, ceil_div(npix, PT), dim3(PT, G), smem, (cudaStream_t)stream, 
-      x, y, Wm, bvec, C, HW, npix, (__nv_bfloat16*)side, side ? side_n : 0, side_off, side_ld, w_smem, logdet, addend,
-      alpha, B);
-  return check_launch("rfk_mix1x1");
+                        "rfk_coupling_taps_mix: bad side-output window");
+  rfk::CouplingSrc cp;
+  cp.taps = taps; cp.scale = scale; cp.shift = shift; cp.clamp_type = clamp_type; cp.cs = clamp_scale; cp.csh = clamp_shift;
+  cp.logdet = cpl_logdet; cp.reverse = reverse; cp.H = H; cp.W = W;
+  return launch_mix_generic("rfk_coupling_taps_mix", z, y, Wm, bvec, B, C, H * W, side, side_n, side_off, side_ld, logdet,
+                            addend, alpha, cp, stream);
 }
 
 extern "C" int rfk_pack_nhwc_bf16(const float* src, long long src_bstride, int B, int Csrc, int HW, int c_lo, int n,

@@ -257,6 +257,20 @@ def conv1x1_taps_fused(act, cin_pad, w2, hid, scale2, shift2, act_fn, w9, n3, ta
     return taps
 
 
+def coupling_taps_mix(taps, z, scale, shift, clamp_type, clamp_scale, clamp_shift, cpl_logdet, reverse, Wm, bvec,
+                      side=None, side_n=0, side_off=0, logdet=None, addend=None, alpha=1.0):
+    """y = Wm * coupling(z; taps) + bvec: the tap gather + coupling update of one step fused with the next 1x1 mix."""
+    _chk(taps, name="taps")
+    _chk(z, name="z")
+    B, C, H, W = z.shape
+    y = torch.empty_like(z)
+    side_ld = side.shape[-1] if side is not None else 0
+    call("rfk_coupling_taps_mix", taps.data_ptr(), z.data_ptr(), y.data_ptr(), B, C, H, W, _chk(scale).data_ptr(),
+         _chk(shift).data_ptr(), CLAMP[clamp_type], _p(clamp_scale), _p(clamp_shift), _p(cpl_logdet), int(reverse),
+         _chk(Wm).data_ptr(), _p(bvec), _p(side), side_n, side_off, side_ld, _p(logdet), _p(addend), float(alpha), _stream())
+    return y
+
+
 def gauss_logp(z, z_off, params, n, pairing, std_kind, logdet):
     _chk(z, name="z")
     B, zC, H, W = z.shape

@@ -140,3 +140,34 @@ def test_lstm_pointwise(ops, shape):
     cn0 = f0 * c + i0 * g
     torch.testing.assert_close(c0.cpu(), cn0, rtol=1e-5, atol=1e-5)
     torch.testing.assert_close(h0.cpu(), torch.sigmoid(cc[:, 2 * Hc:3 * Hc]) * torch.tanh(cn0), rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("reverse", [False, True])
+@pytest.mark.parametrize("B,C,H,W", [(3, 4, 32, 32), (2, 8, 16, 16), (5, 16, 8, 8), (7, 32, 4, 4), (9, 64, 2, 2), (2, 6, 3, 5)])
+def test_coupling_taps_mix_equals_gather_then_mix(ops, reverse, B, C, H, W):
+    """The fused tap-gather + coupling tail + 1x1 mix equals the two separate kernels (which are checked against the
+    oracle elsewhere), including both log-det contributions and the bf16 side output."""
+    g = torch.Generator().manual_seed(C + 31 * int(reverse))
+    taps = (torch.randn(B, 9 * C, H, W, generator=g) * 0.2).cuda()
+    z = torch.randn(B, C, H, W, generator=g).cuda()
+    scale, shift = (torch.rand(C, generator=g) + 0.5).cuda(), (torch.randn(C, generator=g) * 0.1).cuda()
+    cs, csh = (torch.randn(C // 2, generator=g) * 0.5).cuda(), (torch.randn(C // 2, generator=g) * 0.1).cuda()
+    Wm, bv = (torch.randn(C, C, generator=g) / C ** 0.5).cuda(), torch.randn(C, generator=g).cuda()
+    addend = torch.tensor([0.37], device="cuda")
+    # reference composition
+    z_ref, ld_ref = z.clone(), torch.zeros(B, device="cuda")
+    ops.coupling_tail_taps(taps, z_ref, scale, shift, "realnvp", cs, csh, ld_ref, reverse)
+    side_ref = torch.zeros(B, H, W, 64, device="cuda", dtype=torch.bfloat16)
+    y_ref = ops.mix1x1(z_ref, Wm, bv, side=side_ref, side_n=C // 2 if C <= 64 else 0, side_off=8, logdet=ld_ref,
+                       addend=addend, alpha=-1.0 if reverse else 1.0)
+    # fused
+    ld = torch.zeros(B, device="cuda")
+    side = torch.zeros(B, H, W, 64, device="cuda", dtype=torch.bfloat16)
+    z_in = z.clone()
+    y = ops.coupling_taps_mix(taps, z_in, scale, shift, "realnvp", cs, csh, ld, reverse, Wm, bv, side=side,
+                              side_n=C // 2 if C <= 64 else 0, side_off=8, logdet=ld, addend=addend,
+                              alpha=-1.0 if reverse else 1.0)
+    assert torch.equal(z_in, z), "input must not be modified"
+    torch.testing.assert_close(y, y_ref, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(ld, ld_ref, rtol=1e-4, atol=1e-3)
+    assert rel_err(side.float(), side_ref.float()) < 1e-2
