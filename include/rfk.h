@@ -216,6 +216,20 @@ int rfk_gauss_sample(const float* eps, const float* params, int n, int B, int HW
 int rfk_convlstm_pointwise(const float* cc, const float* c_prev, const float* peep,
                            float* h_out, float* c_next, int B, int Hc, int HW, void* stream);
 
+/* ---- backward building blocks (round 1: tested primitives, module autograd wiring is next) ------------
+ * Data gradient of a conv: rfk_conv_gemm on the tap-flipped, transposed weights (Wd[ci, co, ky, kx] = W[co, ci, 2-ky, 2-kx]).
+ *
+ * rfk_act_affine_bwd: backward of h = act(a*scale + shift) (Conv2dNorm + ActFun, Flow/glow_modules.py:139-147) from the
+ *   saved output h and the upstream gradient dh (both NHWC bf16, `rows` pixels, n channels, row stride ld):
+ *   da = dh*act'(h)*scale (bf16, row stride da_ld);  r_dv[c] += sum dh*act'(h)  (d bias = scale*r_dv);
+ *   r_dvv[c] += sum dh*act'(h)*v = sum dh*h  (d logs).  r_dv / r_dvv are caller-zeroed fp32 [n].
+ * rfk_conv_wgrad: dw[tap][n][c] += sum_p dy[p, n] * x[p + off(tap), c]  (x, dy NHWC bf16; zero outside the image;
+ *   dw fp32 [taps, cout, dw_ld], caller-zeroed; tap = 3*ky + kx).  Tensor cores through mma.sync (WMMA). */
+int rfk_act_affine_bwd(const void* dh, const void* h, int ld, int n, const float* scale, int act_fn,
+                       void* da, int da_ld, float* r_dv, float* r_dvv, long long rows, void* stream);
+int rfk_conv_wgrad(const void* x, int x_ld, int cin, const void* dy, int dy_ld, int cout, int B, int H, int W, int taps,
+                   float* dw, int dw_ld, void* stream);
+
 /* Debug aid: when buf != NULL, every conv-GEMM CTA of later launches (grids of at most capacity_ctas CTAs)
  * writes 16 words to buf[16*cta..]: %globaltimer stamps (ns) 0 start, 1 setup done, 2 weights resident, 3 last TMA
  * issued, 4 last MMA issued, 5 first accumulator ready, 6 first epilogue done, 7 all done; SM-cycle totals 8 producer

@@ -49,6 +49,10 @@ SIGNATURES = {
                              c_void_p, c_int, c_void_p],
     "rfk_convlstm_pointwise_ws": [c_void_p, c_int, c_void_p, c_void_p, c_longlong, c_void_p, c_void_p, c_longlong,
                                   c_void_p, c_longlong, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    "rfk_act_affine_bwd": [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p,
+                           c_longlong, c_void_p],
+    "rfk_conv_wgrad": [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int,
+                       c_void_p],
     "rfk_add_scalar": [c_void_p, c_void_p, c_float, c_int, c_void_p],
     "rfk_debug_set_timeline": [c_void_p, c_longlong],
 }

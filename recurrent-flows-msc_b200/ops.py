@@ -298,6 +298,45 @@ def convlstm_pointwise(cc, c_prev, peep):
 
 
 # --------------------------------------------------------------------------------------
+# backward building blocks
+# --------------------------------------------------------------------------------------
+def act_affine_bwd(dh, h, n, scale, act_fn):
+    """Backward of h = act(a*scale + shift): returns (da bf16 NHWC like dh, r_dv [n], r_dvv [n]);
+    d bias = scale*r_dv, d logs = r_dvv for an ActNorm with scale = exp(logs)."""
+    _chk(dh, torch.bfloat16, "dh")
+    _chk(h, torch.bfloat16, "h")
+    rows = dh.numel() // dh.shape[-1]
+    da = torch.zeros_like(dh)
+    r = torch.zeros(2, n, device=dh.device, dtype=torch.float32)
+    call("rfk_act_affine_bwd", dh.data_ptr(), h.data_ptr(), dh.shape[-1], n, _chk(scale).data_ptr(), ACT[act_fn],
+         da.data_ptr(), da.shape[-1], r[0].data_ptr(), r[1].data_ptr(), rows, _stream())
+    return da, r[0], r[1]
+
+
+def conv_wgrad(x, cin, dy, cout, taps):
+    """Weight gradient [cout, cin, k, k] (fp32) of a 'same' conv from NHWC bf16 activations x and output gradients dy."""
+    _chk(x, torch.bfloat16, "x")
+    _chk(dy, torch.bfloat16, "dy")
+    B, H, W, xld = x.shape
+    dw = torch.zeros(taps, cout, cin, device=x.device, dtype=torch.float32)
+    call("rfk_conv_wgrad", x.data_ptr(), xld, cin, dy.data_ptr(), dy.shape[-1], cout, B, H, W, taps, dw.data_ptr(), cin,
+         _stream(), meta={"flops": 2.0 * B * H * W * cout * cin * taps, "flops_padded": 2.0 * B * H * W * cout * cin * taps,
+                          "M": B * H * W, "N": cout, "K": taps * cin, "bytes": 2.0 * B * H * W * (cin + cout)})
+    k = 3 if taps == 9 else 1
+    return dw.permute(1, 2, 0).reshape(cout, cin, k, k)
+
+
+def pack_dgrad_weight(weight, out_perm=None):
+    """Weights of the data-gradient conv: dX = conv(dY, Wd) with Wd[ci, co, ky, kx] = W[co, ci, k-1-ky, k-1-kx]; rows
+    (the dgrad's output channels = the forward conv's input channels) optionally permuted into staging-buffer order."""
+    w = weight.detach().float()
+    wd = torch.flip(w, dims=(2, 3)).permute(1, 0, 2, 3).contiguous()
+    if out_perm is not None:
+        wd = wd[out_perm]
+    return pack_conv_weight(wd)
+
+
+# --------------------------------------------------------------------------------------
 # workspace pool: NHWC bf16 staging buffers shared by all modules of one shape (one stream, in order)
 # --------------------------------------------------------------------------------------
 _WS = {}
