@@ -230,6 +230,25 @@ int rfk_act_affine_bwd(const void* dh, const void* h, int ld, int n, const float
 int rfk_conv_wgrad(const void* x, int x_ld, int cin, const void* dy, int dy_ld, int cout, int B, int H, int W, int taps,
                    float* dw, int dw_ld, void* stream);
 
+/* Affine-coupling tail backward, tap-split form (backward of rfk_coupling_tail_taps; Flow/glow_modules.py:237-273).
+ *   dz [B,C,H,W] holds the gradient w.r.t. the coupling output; its z2 half (channels C/2..C) is overwritten with the
+ *   gradient w.r.t. z2.  z_out = the coupling output, taps = the nine tap planes [B,9C,H,W], g_ld (nullable) [B] = gradient
+ *   w.r.t. logdet.  dsum [B,C,H,W] receives the gradient w.r.t. the Conv2dZeros pre-affine sums (channel 2j: shift part,
+ *   2j+1: log-scale part).  d_scale/d_shift [C] (Conv2dZeros exp(3*logs) and bias*exp(3*logs) affine) and, for the realnvp
+ *   clamp, d_clamp_scale/d_clamp_shift [C/2] are caller-zeroed fp32 accumulators.
+ * rfk_taps_scatter: dtaps[p, t*C + c] = dsum[c](p - off(t)) as NHWC bf16 (row stride ld >= 9C; pad columns untouched).
+ * rfk_mix1x1_wgrad: dW[o,i] += sum dy[b,o,p]*x[b,i,p], db[o] += sum dy[b,o,p] (fp32 NCHW, C <= 64, caller-zeroed).
+ * rfk_gauss_logp_bwd: backward of rfk_gauss_logp with upstream g[b]: dz[:, z_off:z_off+n] += ..., dparams (nullable with
+ *   params) [B,2n,HW] = gradient w.r.t. the (mean, raw-scale) planes in the same pairing. */
+int rfk_coupling_taps_bwd(const float* taps, const float* z_out, float* dz, float* dsum, int B, int C, int H, int W,
+                          const float* scale, const float* shift, int clamp_type, const float* clamp_scale,
+                          const float* clamp_shift, const float* g_ld, float* d_scale, float* d_shift,
+                          float* d_clamp_scale, float* d_clamp_shift, void* stream);
+int rfk_taps_scatter(const float* dsum, void* dtaps, int ld, int B, int C, int H, int W, void* stream);
+int rfk_mix1x1_wgrad(const float* x, const float* dy, int B, int C, int HW, float* dW, float* db, void* stream);
+int rfk_gauss_logp_bwd(const float* z, int z_C, int z_off, const float* params, int n, int B, int HW, int pairing,
+                       int std_kind, const float* g, float* dz, float* dparams, void* stream);
+
 /* Debug aid: when buf != NULL, every conv-GEMM CTA of later launches (grids of at most capacity_ctas CTAs)
  * writes 16 words to buf[16*cta..]: %globaltimer stamps (ns) 0 start, 1 setup done, 2 weights resident, 3 last TMA
  * issued, 4 last MMA issued, 5 first accumulator ready, 6 first epilogue done, 7 all done; SM-cycle totals 8 producer

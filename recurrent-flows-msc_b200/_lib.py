@@ -53,6 +53,12 @@ SIGNATURES = {
                            c_longlong, c_void_p],
     "rfk_conv_wgrad": [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int,
                        c_void_p],
+    "rfk_coupling_taps_bwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                              c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    "rfk_taps_scatter": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    "rfk_mix1x1_wgrad": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],
+    "rfk_gauss_logp_bwd": [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                           c_void_p, c_void_p],
     "rfk_add_scalar": [c_void_p, c_void_p, c_float, c_int, c_void_p],
     "rfk_debug_set_timeline": [c_void_p, c_longlong],
 }

@@ -172,9 +172,265 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(const __nv_bfloat16* __
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Affine coupling tail, backward (tap-split form; forward = coupling_taps_kernel in elementwise.cu).
+//   forward:  t = S*sc[2j] + sh[2j],  raw = R*sc[2j+1] + sh[2j+1]  (S, R = nine-tap sums),  ls = clamp(raw),
+//             z2' = (z2 + t) * e^{ls},  logdet[b] += sum ls
+//   given dz (gradient w.r.t. the coupling output, [B,C,H,W], z2 half overwritten with the gradient w.r.t. z2),
+//   z_out (the coupling output) and g_ld[b] (gradient w.r.t. logdet[b]):
+//     dls = dz2'*z2' + g_ld,  dt = dz2'*e^{ls},  dz2 = dz2'*e^{ls},  draw = dls*clamp'(raw)
+//     dsum[2j] = dt*sc[2j],  dsum[2j+1] = draw*sc[2j+1]                    (gradient w.r.t. S and R, fp32 NCHW)
+//     d sc[2j] += dt*S, d sh[2j] += dt, d sc[2j+1] += draw*R, d sh[2j+1] += draw   (Conv2dZeros affine)
+//     realnvp clamp ls = a*tanh(raw)+b:  d a += dls*tanh(raw),  d b += dls
+//   grid = (chunks, B); the eight per-channel sums are reduced per CTA (one (j) per blockIdx.z) then atomically added.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float block_sum_256(float v, float* sh) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  float r = 0.0f;
+  if (threadIdx.x < 32) {
+    r = lane < (blockDim.x >> 5) ? sh[lane] : 0.0f;
+    r = warp_sum(r);
+  }
+  return r;  // valid in thread 0
+}
+
+__global__ void __launch_bounds__(256) coupling_taps_bwd_kernel(const float* __restrict__ taps, const float* __restrict__ z_out,
+                                                                float* __restrict__ dz, float* __restrict__ dsum, int C, int H,
+                                                                int W, const float* __restrict__ scale,
+                                                                const float* __restrict__ shift, int clamp_type,
+                                                                const float* __restrict__ cs, const float* __restrict__ csh,
+                                                                const float* __restrict__ g_ld, float* __restrict__ d_scale,
+                                                                float* __restrict__ d_shift, float* __restrict__ d_cs,
+                                                                float* __restrict__ d_csh) {
+  pdl_trigger();
+  pdl_wait();
+  __shared__ float sh[32];
+  const int b = blockIdx.y, j = blockIdx.z, half = C >> 1, HW = H * W;
+  const float* tb = taps + (long long)b * 9 * C * HW;
+  const float* zo = z_out + ((long long)b * C + half + j) * HW;
+  float* dzp = dz + ((long long)b * C + half + j) * HW;
+  float* dsp = dsum + ((long long)b * C + 2 * j) * HW;
+  const float sc_s = scale[2 * j], sh_s = shift[2 * j], sc_r = scale[2 * j + 1], sh_r = shift[2 * j + 1];
+  float a = 0.0f, bb = 0.0f;
+  if (clamp_type == RFK_CLAMP_REALNVP) { a = cs[j]; bb = csh[j]; }
+  const float gl = g_ld ? g_ld[b] : 0.0f;
+  float acc[6] = {0, 0, 0, 0, 0, 0};   // d sc_s, d sh_s, d sc_r, d sh_r, d a, d b
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += gridDim.x * blockDim.x) {
+    const int y = p / W, x = p - y * W;
+    float S = 0.0f, R = 0.0f;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int yy = y + ky - 1;
+      if (yy < 0 || yy >= H) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int xx = x + kx - 1;
+        if (xx < 0 || xx >= W) continue;
+        const float* q = tb + ((long long)((3 * ky + kx) * C + 2 * j) * HW) + yy * W + xx;
+        S += __ldg(q);
+        R += __ldg(q + HW);
+      }
+    }
+    const float raw = fmaf(R, sc_r, sh_r);
+    float ls, dclamp, th = 0.0f;
+    switch (clamp_type) {
+      case RFK_CLAMP_REALNVP: th = tanhf(raw); ls = a * th + bb; dclamp = a * (1.0f - th * th); break;
+      case RFK_CLAMP_GLOW: { const float t = -(raw + 2.0f); ls = -(t > 15.0f ? t : log1pf(expf(t))); dclamp = 1.0f / (1.0f + expf(raw + 2.0f)); break; }
+      case RFK_CLAMP_SOFT: { const float u = raw * (1.0f / 2.5f); ls = 2.5f * 0.636f * atanf(u); dclamp = 0.636f / (1.0f + u * u); break; }
+      default: ls = raw; dclamp = 1.0f;
+    }
+    const float e = expf(ls);
+    const float dzo = dzp[p];
+    const float dls = dzo * zo[p] + gl;
+    const float dt = dzo * e;
+    const float draw = dls * dclamp;
+    dzp[p] = dt;                 // gradient w.r.t. z2 (the coupling's input half)
+    dsp[p] = dt * sc_s;          // gradient w.r.t. S
+    dsp[HW + p] = draw * sc_r;   // gradient w.r.t. R
+    acc[0] += dt * S; acc[1] += dt; acc[2] += draw * R; acc[3] += draw; acc[4] += dls * th; acc[5] += dls;
+  }
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    const float r = block_sum_256(acc[k], sh);
+    if (threadIdx.x == 0) {
+      if (k == 0) atomicAdd(d_scale + 2 * j, r);
+      else if (k == 1) atomicAdd(d_shift + 2 * j, r);
+      else if (k == 2) atomicAdd(d_scale + 2 * j + 1, r);
+      else if (k == 3) atomicAdd(d_shift + 2 * j + 1, r);
+      else if (clamp_type == RFK_CLAMP_REALNVP) atomicAdd((k == 4 ? d_cs : d_csh) + j, r);
+    }
+  }
+}
+
+// Gradient w.r.t. the nine tap planes, written directly as the NHWC bf16 operand of the tap GEMM's backward:
+//   dtaps[p, t*C + c] = dsum[c](p - off(t))  (zero when that pixel is outside the image)
+__global__ void __launch_bounds__(256) taps_scatter_kernel(const float* __restrict__ dsum, __nv_bfloat16* __restrict__ dtaps,
+                                                           int ld, int C, int H, int W, long long total) {
+  pdl_trigger();
+  pdl_wait();
+  const int n9 = 9 * C, HW = H * W;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int col = (int)(t % n9);
+    const long long pix = t / n9;
+    const int tap = col / C, c = col - tap * C;
+    const int p = (int)(pix % HW);
+    const long long b = pix / HW;
+    const int y = p / W - (tap / 3 - 1), x = p % W - (tap % 3 - 1);
+    float v = 0.0f;
+    if (y >= 0 && y < H && x >= 0 && x < W) v = dsum[(b * C + c) * HW + y * W + x];
+    dtaps[pix * ld + col] = __float2bfloat16(v);
+  }
+}
+
+// 1x1 mix backward, parameter part: dW[o,i] += sum_{b,p} dy[b,o,p]*x[b,i,p],  db[o] += sum dy[b,o,p]
+// (the data part dx = W^T dy is rfk_mix1x1 with the transposed matrix).  CTA = a slice of pixels, staged 64 at a time.
+__global__ void __launch_bounds__(256) mix1x1_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, int C,
+                                                           int HW, long long npix, long long pix_per_cta,
+                                                           float* __restrict__ dW, float* __restrict__ db) {
+  pdl_trigger();
+  pdl_wait();
+  extern __shared__ float sm[];
+  float* xs = sm;             // [C][64]
+  float* ds = sm + C * 64;    // [C][64]
+  const long long p0 = blockIdx.x * pix_per_cta, p1 = min(npix, p0 + pix_per_cta);
+  const int n_out = C * C;
+  constexpr int kMax = 16;    // outputs per thread: C*C <= 4096
+  float acc[kMax];
+#pragma unroll
+  for (int k = 0; k < kMax; ++k) acc[k] = 0.0f;
+  float accb = 0.0f;
+  for (long long pc = p0; pc < p1; pc += 64) {
+    for (int e = threadIdx.x; e < C * 64; e += blockDim.x) {
+      const int c = e >> 6, r = e & 63;
+      const long long p = pc + r;
+      float xv = 0.0f, dv = 0.0f;
+      if (p < p1) {
+        const long long b = p / HW;
+        const int q = (int)(p % HW);
+        xv = x[(b * C + c) * HW + q];
+        dv = dy[(b * C + c) * HW + q];
+      }
+      xs[e] = xv;
+      ds[e] = dv;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kMax; ++k) {
+      const int idx = threadIdx.x + k * 256;
+      if (idx < n_out) {
+        const int o = idx / C, i = idx - o * C;
+        float s = 0.0f;
+#pragma unroll 8
+        for (int r = 0; r < 64; ++r) s = fmaf(ds[o * 64 + r], xs[i * 64 + r], s);
+        acc[k] += s;
+      }
+    }
+    if (threadIdx.x < C) {
+      float s = 0.0f;
+      for (int r = 0; r < 64; ++r) s += ds[threadIdx.x * 64 + r];
+      accb += s;
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int k = 0; k < kMax; ++k) {
+    const int idx = threadIdx.x + k * 256;
+    if (idx < n_out) atomicAdd(dW + idx, acc[k]);
+  }
+  if (threadIdx.x < C) atomicAdd(db + threadIdx.x, accb);
+}
+
+// Gaussian log-density backward (forward = gauss_logp_kernel): upstream g[b] on logdet[b] += sum log N(z; mean, std(raw)).
+//   dz += g*(-(z-mean)/std^2);  dmean = g*(z-mean)/std^2;  draw = g*((z-mean)^2/std^3 - 1/std)*dstd/draw
+__global__ void __launch_bounds__(256) gauss_logp_bwd_kernel(const float* __restrict__ z, int z_C, int z_off,
+                                                             const float* __restrict__ params, int n, int HW, int pairing,
+                                                             int std_kind, const float* __restrict__ g,
+                                                             float* __restrict__ dz, float* __restrict__ dparams) {
+  pdl_trigger();
+  pdl_wait();
+  const int b = blockIdx.y;
+  const long long per = (long long)n * HW;
+  const float gb = g[b];
+  const float* zb = z + ((long long)b * z_C + z_off) * HW;
+  float* dzb = dz + ((long long)b * z_C + z_off) * HW;
+  const float* pb = params ? params + (long long)b * 2 * n * HW : nullptr;
+  float* dpb = dparams ? dparams + (long long)b * 2 * n * HW : nullptr;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < per; t += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(t / HW), p = (int)(t % HW);
+    const int cm = pairing == RFK_PAIR_CROSS ? 2 * j : j, cr = pairing == RFK_PAIR_CROSS ? 2 * j + 1 : n + j;
+    float mean = 0.0f, raw = 0.0f;
+    if (pb) { mean = pb[(long long)cm * HW + p]; raw = pb[(long long)cr * HW + p]; }
+    const float sd = std_from_raw(raw, std_kind);
+    const float dstd = std_kind == RFK_STD_EXP ? sd : 1.0f / (1.0f + expf(-raw));   // d std / d raw
+    const float d = zb[t] - mean, inv = 1.0f / sd;
+    const float gm = gb * d * inv * inv;
+    dzb[t] += -gm;
+    if (dpb) {
+      dpb[(long long)cm * HW + p] = gm;
+      dpb[(long long)cr * HW + p] = gb * (d * d * inv * inv * inv - inv) * dstd;
+    }
+  }
+}
+
 }  // namespace rfk
 
 using namespace rfk;
+
+extern "C" int rfk_coupling_taps_bwd(const float* taps, const float* z_out, float* dz, float* dsum, int B, int C, int H,
+                                     int W, const float* scale, const float* shift, int clamp_type, const float* clamp_scale,
+                                     const float* clamp_shift, const float* g_ld, float* d_scale, float* d_shift,
+                                     float* d_clamp_scale, float* d_clamp_shift, void* stream) {
+  RFK_REQUIRE(taps && z_out && dz && dsum && scale && shift && d_scale && d_shift && B > 0 && C > 0 && C % 2 == 0 && H > 0 && W > 0,
+              "rfk_coupling_taps_bwd: null pointer or bad shape");
+  RFK_REQUIRE(clamp_type >= 0 && clamp_type <= 3, "rfk_coupling_taps_bwd: unknown clamp_type %d", clamp_type);
+  RFK_REQUIRE(clamp_type != RFK_CLAMP_REALNVP || (clamp_scale && clamp_shift && d_clamp_scale && d_clamp_shift),
+              "rfk_coupling_taps_bwd: realnvp clamp needs scale/scale_shift and their gradient buffers");
+  RFK_REQUIRE(B <= 65535 && C / 2 <= 65535, "rfk_coupling_taps_bwd: B or C too large for the grid");
+  int chunks = ceil_div((long long)H * W, 256);
+  if (chunks > 64) chunks = 64;
+  RFK_LAUNCH(coupling_taps_bwd_kernel, dim3(chunks, B, C / 2), 256, 0, (cudaStream_t)stream, taps, z_out, dz, dsum, C, H, W,
+             scale, shift, clamp_type, clamp_scale, clamp_shift, g_ld, d_scale, d_shift, d_clamp_scale, d_clamp_shift);
+  return check_launch("rfk_coupling_taps_bwd");
+}
+
+extern "C" int rfk_taps_scatter(const float* dsum, void* dtaps, int ld, int B, int C, int H, int W, void* stream) {
+  RFK_REQUIRE(dsum && dtaps && B > 0 && C > 0 && H > 0 && W > 0 && ld >= 9 * C, "rfk_taps_scatter: null pointer or bad shape");
+  const long long total = (long long)B * H * W * 9 * C;
+  RFK_LAUNCH(taps_scatter_kernel, stream_grid(total, 256, 8), 256, 0, (cudaStream_t)stream, dsum, (__nv_bfloat16*)dtaps, ld, C,
+             H, W, total);
+  return check_launch("rfk_taps_scatter");
+}
+
+extern "C" int rfk_mix1x1_wgrad(const float* x, const float* dy, int B, int C, int HW, float* dW, float* db, void* stream) {
+  RFK_REQUIRE(x && dy && dW && db && B > 0 && C > 0 && C <= 64 && HW > 0, "rfk_mix1x1_wgrad: null pointer or bad shape (C <= 64)");
+  const long long npix = (long long)B * HW;
+  long long ctas = std::min<long long>((long long)sm_count() * 2, (npix + 255) / 256);
+  if (ctas < 1) ctas = 1;
+  long long ppc = (npix + ctas - 1) / ctas;
+  ppc = (ppc + 63) / 64 * 64;
+  ctas = (npix + ppc - 1) / ppc;
+  RFK_LAUNCH(mix1x1_wgrad_kernel, (int)ctas, 256, (size_t)2 * C * 64 * sizeof(float), (cudaStream_t)stream, x, dy, C, HW, npix,
+             ppc, dW, db);
+  return check_launch("rfk_mix1x1_wgrad");
+}
+
+extern "C" int rfk_gauss_logp_bwd(const float* z, int z_C, int z_off, const float* params, int n, int B, int HW, int pairing,
+                                  int std_kind, const float* g, float* dz, float* dparams, void* stream) {
+  RFK_REQUIRE(z && g && dz && B > 0 && n > 0 && HW > 0 && z_off >= 0 && z_off + n <= z_C, "rfk_gauss_logp_bwd: bad arguments");
+  RFK_REQUIRE((params == nullptr) == (dparams == nullptr), "rfk_gauss_logp_bwd: params and dparams go together");
+  long long per = (long long)n * HW;
+  int chunks = ceil_div(per, 256);
+  int cap = ceil_div((long long)sm_count() * 8, B);
+  if (chunks > cap) chunks = cap;
+  RFK_LAUNCH(gauss_logp_bwd_kernel, dim3(chunks, B), 256, 0, (cudaStream_t)stream, z, z_C, z_off, params, n, HW, pairing,
+             std_kind, g, dz, dparams);
+  return check_launch("rfk_gauss_logp_bwd");
+}
+
 
 extern "C" int rfk_act_affine_bwd(const void* dh, const void* h, int ld, int n, const float* scale, int act_fn, void* da,
                                   int da_ld, float* r_dv, float* r_dvv, long long rows, void* stream) {

@@ -326,6 +326,50 @@ def conv_wgrad(x, cin, dy, cout, taps):
     return dw.permute(1, 2, 0).reshape(cout, cin, k, k)
 
 
+def coupling_taps_bwd(taps, z_out, dz, scale, shift, clamp, clamp_scale, clamp_shift, g_ld):
+    """Backward of coupling_tail_taps.  dz (in/out, [B,C,H,W]): z2 half replaced by the gradient w.r.t. z2.
+    Returns (dsum [B,C,H,W], d_scale [C], d_shift [C], d_clamp_scale [C/2], d_clamp_shift [C/2])."""
+    B, C, H, W = _chk(dz, name="dz").shape
+    _chk(taps, name="taps"); _chk(z_out, name="z_out")
+    dsum = torch.empty_like(dz)
+    r = torch.zeros(3 * C, device=dz.device, dtype=torch.float32)
+    d_scale, d_shift, d_cs, d_csh = r[:C], r[C:2 * C], r[2 * C:2 * C + C // 2], r[2 * C + C // 2:]
+    p = lambda t: _chk(t).data_ptr() if t is not None else None
+    call("rfk_coupling_taps_bwd", taps.data_ptr(), z_out.data_ptr(), dz.data_ptr(), dsum.data_ptr(), B, C, H, W,
+         _chk(scale).data_ptr(), _chk(shift).data_ptr(), CLAMP[clamp], p(clamp_scale), p(clamp_shift), p(g_ld),
+         d_scale.data_ptr(), d_shift.data_ptr(), d_cs.data_ptr(), d_csh.data_ptr(), _stream())
+    return dsum, d_scale, d_shift, d_cs, d_csh
+
+
+def taps_scatter(dsum, out=None):
+    """NHWC bf16 gradient of the nine tap planes [B,H,W,pad64(9C)] from dsum [B,C,H,W] (pad columns zero)."""
+    B, C, H, W = _chk(dsum, name="dsum").shape
+    ld = pad_to(9 * C, 64)
+    if out is None:
+        out = torch.zeros(B, H, W, ld, device=dsum.device, dtype=torch.bfloat16)
+    call("rfk_taps_scatter", dsum.data_ptr(), out.data_ptr(), ld, B, C, H, W, _stream())
+    return out
+
+
+def mix1x1_wgrad(x, dy):
+    """(dW [C,C], db [C]) of y = W x + b over all pixels (fp32 NCHW)."""
+    B, C, H, W = _chk(x, name="x").shape
+    _chk(dy, name="dy")
+    r = torch.zeros(C * C + C, device=x.device, dtype=torch.float32)
+    call("rfk_mix1x1_wgrad", x.data_ptr(), dy.data_ptr(), B, C, H * W, r.data_ptr(), r[C * C:].data_ptr(), _stream())
+    return r[:C * C].view(C, C), r[C * C:]
+
+
+def gauss_logp_bwd(z, z_off, n, params, pairing, std_kind, g, dz):
+    """Backward of gauss_logp: dz[:, z_off:z_off+n] += dlogp/dz * g[b]; returns dparams [B,2n,H,W] (None without params)."""
+    B, zC, H, W = _chk(z, name="z").shape
+    _chk(dz, name="dz"); _chk(g, name="g")
+    dparams = torch.empty_like(params) if params is not None else None
+    call("rfk_gauss_logp_bwd", z.data_ptr(), zC, z_off, _p(params), n, B, H * W, pairing, STD[std_kind], g.data_ptr(), dz.data_ptr(), dparams.data_ptr() if dparams is not None else None,
+         _stream())
+    return dparams
+
+
 def pack_dgrad_weight(weight, out_perm=None):
     """Weights of the data-gradient conv: dX = conv(dY, Wd) with Wd[ci, co, ky, kx] = W[co, ci, k-1-ky, k-1-kx]; rows
     (the dgrad's output channels = the forward conv's input channels) optionally permuted into staging-buffer order."""

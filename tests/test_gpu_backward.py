@@ -80,3 +80,96 @@ def test_act_affine_bwd(ops, act, rows, n, ld):
     dlogs_ref, dbias_ref = torch.autograd.grad(h, (logs, bias), dh)
     assert max_rel(r_dvv.cpu(), dlogs_ref) < 2e-2
     assert max_rel((s * r_dv.cpu()), dbias_ref) < 2e-2
+
+
+def gather_taps(taps, C):
+    """S[c](y, x) = sum_t taps[t*C + c](y + ky - 1, x + kx - 1), zero outside the image."""
+    H, W = taps.shape[2:]
+    P = F.pad(taps, (1, 1, 1, 1))
+    return sum(P[:, (3 * ky + kx) * C:(3 * ky + kx + 1) * C, ky:ky + H, kx:kx + W] for ky in range(3) for kx in range(3))
+
+
+@pytest.mark.parametrize("clamp", ["realnvp", "glow", "softclamp", "none"])
+@pytest.mark.parametrize("B,C,H,W", [(3, 6, 16, 16), (2, 24, 8, 8), (5, 12, 5, 7), (2, 96, 2, 2)])
+def test_coupling_taps_bwd(ops, clamp, B, C, H, W):
+    g = torch.Generator().manual_seed(C * 7 + H)
+    half = C // 2
+    taps = (0.3 * torch.randn(B, 9 * C, H, W, generator=g)).requires_grad_()
+    z = torch.randn(B, C, H, W, generator=g).requires_grad_()
+    scale = (1 + 0.2 * torch.randn(C, generator=g)).requires_grad_()
+    shift = (0.2 * torch.randn(C, generator=g)).requires_grad_()
+    cs = (1 + 0.2 * torch.randn(half, generator=g)).requires_grad_()
+    csh = (0.1 * torch.randn(half, generator=g)).requires_grad_()
+    gz = torch.randn(B, C, H, W, generator=g)
+    gld = torch.randn(B, generator=g)
+
+    S = gather_taps(taps, C)
+    S.retain_grad()
+    h = S * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
+    t, raw = h[:, 0::2], h[:, 1::2]
+    ls = O.clamp_log_scale(raw, clamp, cs, csh)
+    z2o = (z[:, half:] + t) * torch.exp(ls)
+    zo = torch.cat([z[:, :half], z2o], 1)
+    ((zo * gz).sum() + (ls.sum(dim=(1, 2, 3)) * gld).sum()).backward()
+
+    dz = gz.clone().cuda()
+    dsum, d_scale, d_shift, d_cs, d_csh = ops.coupling_taps_bwd(
+        taps.detach().cuda(), zo.detach().cuda().contiguous(), dz, scale.detach().cuda(), shift.detach().cuda(), clamp,
+        cs.detach().cuda() if clamp == "realnvp" else None, csh.detach().cuda() if clamp == "realnvp" else None, gld.cuda())
+    assert torch.equal(dz[:, :half].cpu(), gz[:, :half])          # z1 half untouched (its coupling-path gradient comes later)
+    assert max_rel(dz[:, half:].cpu(), z.grad[:, half:]) < 2e-4
+    assert max_rel(dsum.cpu(), S.grad) < 2e-4
+    assert max_rel(d_scale.cpu(), scale.grad) < 2e-4
+    assert max_rel(d_shift.cpu(), shift.grad) < 2e-4
+    if clamp == "realnvp":
+        assert max_rel(d_cs.cpu(), cs.grad) < 2e-4
+        assert max_rel(d_csh.cpu(), csh.grad) < 2e-4
+    # tap scatter = the gather's adjoint, as the NHWC bf16 operand of the tap GEMM's backward
+    dt = ops.taps_scatter(dsum)
+    assert dt.shape == (B, H, W, ops.pad_to(9 * C, 64))
+    got = dt[..., :9 * C].float().permute(0, 3, 1, 2).cpu()
+    assert max_rel(got, taps.grad) < 1e-2
+    assert float(dt[..., 9 * C:].abs().max()) == 0.0 if dt.shape[-1] > 9 * C else True
+
+
+@pytest.mark.parametrize("B,C,H,W", [(3, 12, 32, 32), (2, 6, 7, 5), (4, 48, 8, 8), (5, 64, 2, 2), (2, 24, 16, 16)])
+def test_mix1x1_wgrad(ops, B, C, H, W):
+    g = torch.Generator().manual_seed(C + B)
+    x = torch.randn(B, C, H, W, generator=g)
+    dy = torch.randn(B, C, H, W, generator=g)
+    dW, db = ops.mix1x1_wgrad(x.cuda(), dy.cuda())
+    ref_W = torch.einsum("bohw,bihw->oi", dy.double(), x.double())
+    ref_b = dy.double().sum(dim=(0, 2, 3))
+    assert max_rel(dW.cpu(), ref_W) < 1e-4
+    assert max_rel(db.cpu(), ref_b) < 1e-4
+
+
+@pytest.mark.parametrize("std_kind", ["exp", "softplus"])
+@pytest.mark.parametrize("pairing", ["cross", "split"])
+@pytest.mark.parametrize("with_params", [True, False])
+def test_gauss_logp_bwd(ops, std_kind, pairing, with_params):
+    import math
+    import recurrent_flows_msc_b200 as r
+    g = torch.Generator().manual_seed(11)
+    B, zC, off, n, H, W = 3, 10, 4, 6, 5, 7
+    z = torch.randn(B, zC, H, W, generator=g).requires_grad_()
+    params = (0.5 * torch.randn(B, 2 * n, H, W, generator=g)).requires_grad_() if with_params else None
+    gb = torch.randn(B, generator=g)
+    if with_params:
+        mean, raw = (params[:, 0::2], params[:, 1::2]) if pairing == "cross" else (params[:, :n], params[:, n:])
+    else:
+        mean, raw = torch.zeros(B, n, H, W), torch.zeros(B, n, H, W)
+    sd = torch.exp(raw) if std_kind == "exp" else F.softplus(raw) + 1e-8
+    zz = z[:, off:off + n]
+    lp = (-0.5 * math.log(2 * math.pi) - torch.log(sd) - 0.5 * ((zz - mean) / sd) ** 2).sum(dim=(1, 2, 3))
+    (lp * gb).sum().backward()
+    dz0 = torch.randn(B, zC, H, W, generator=g)
+    dz = dz0.clone().cuda()
+    pair = r._lib.PAIR_CROSS if pairing == "cross" else r._lib.PAIR_SPLIT
+    dp = ops.gauss_logp_bwd(z.detach().cuda(), off, n, params.detach().cuda() if with_params else None, pair, std_kind,
+                            gb.cuda(), dz)
+    assert max_rel(dz.cpu() - dz0, z.grad) < 1e-4
+    if with_params:
+        assert max_rel(dp.cpu(), params.grad) < 1e-4
+    else:
+        assert dp is None
