@@ -276,7 +276,6 @@ class ListGlow(nn.Module):
 
     def log_prob(self, x, condition, base_condition, logdet=0, noise=None):
         """Flow/glow.py:128-141.  Returns (z, nll[B]).  ``noise`` optionally injects the dequantisation draw."""
-        _require_no_grad()
         assert isinstance(condition, list), "Condition is not a list, make sure it fits L"
         if noise is None:
             x, obj_unif = self.uniform_binning_correction(x)
@@ -284,6 +283,13 @@ class ListGlow(nn.Module):
             b, c, h, w = x.size()
             obj_unif = -np.log(2 ** self.n_bits) * (c * h * w) * torch.ones(b, device=x.device)
             x = x + noise
+        if torch.is_grad_enabled():
+            # training: tape-recording forward + hand-written backward kernels (Flow/training.py)
+            from .training import log_prob_with_grad
+            if torch.is_tensor(logdet) and logdet.requires_grad:
+                raise NotImplementedError("recurrent-flows-msc_b200: gradients w.r.t. the logdet argument are not implemented")
+            obj0 = obj_unif + (logdet.detach() if torch.is_tensor(logdet) else logdet)
+            return log_prob_with_grad(self, x, condition, base_condition, obj0)
         z, obj = self.f(x, condition, logdet)
         if not torch.is_tensor(obj) or obj.dim() != 1:
             obj = torch.zeros(z.shape[0], device=z.device) + obj

@@ -1,0 +1,333 @@
+"""Training path of ``ListGlow.log_prob``: reverse-mode differentiation of the flow on librfk's backward kernels.
+
+The reference trains the flow through PyTorch autograd over ~186 ATen ops per GlowStep (Flow/glow.py:128-141 called
+from RFN/RFN.py's loss).  Here the forward pass records a tape of the tensors each module's backward needs and the
+backward pass walks it in reverse, launching hand-written kernels:
+
+  coupling tail           rfk_coupling_taps_bwd   (gradients of the affine update, clamp and Conv2dZeros scale)
+  3x3 / 1x1 convolutions  rfk_conv_wgrad (weight gradient, tensor cores) + rfk_conv_gemm on flipped weights (data gradient)
+  ActNorm + activation    rfk_act_affine_bwd      (per-channel reductions give d logs / d bias)
+  ActNorm . InvConv mix   rfk_mix1x1_wgrad + rfk_mix1x1 with the transposed matrix
+  Split2d / prior density rfk_gauss_logp_bwd
+
+Only the map from module parameters to the folded per-step quantities (C x C mix matrix from the LU factors and the
+ActNorm scale, its log-determinant) is differentiated by torch autograd, on C x C tensors.  Activation gradients
+between convolutions are bf16 (as the activations are); parameter gradients accumulate in fp32.
+
+Not covered (raise NotImplementedError): flow_norm='batchnorm', batch-norm hidden layers in the prior, couplings with
+more than 256 channels (no tap-split form), gradients w.r.t. a tensor-valued ``logdet`` argument.
+"""
+import torch
+
+from .. import ops
+from .glow_modules import BatchNormFlow, Split2d, Squeeze2d, TAP_SPLIT_MAX_N
+
+
+class _State:
+    """What the backward sweep carries: the gradient of the current activation, the per-sample weight on the
+    log-determinant, and the accumulated parameter / condition gradients."""
+
+    def __init__(self, dz, g_ld, n_levels):
+        self.dz = dz
+        self.g_ld = g_ld
+        self.G = g_ld.sum()
+        self.dcond = [None] * n_levels
+        self.dbase = None
+        self.grads = {}
+
+    def add(self, param, g):
+        g = g.reshape(param.shape)
+        hit = self.grads.get(id(param))
+        self.grads[id(param)] = g.clone() if hit is None else hit.add_(g)
+
+    def add_cond(self, l, g):
+        self.dcond[l] = g.clone() if self.dcond[l] is None else self.dcond[l].add_(g)
+
+
+def _nhwc(B, H, W, c, dev):
+    return torch.zeros(B, H, W, ops.cin_pad(c), device=dev, dtype=torch.bfloat16)
+
+
+def _check_actnorm(mod):
+    if mod.norm != "actnorm":
+        raise NotImplementedError("recurrent-flows-msc_b200: backward through batch-norm hidden layers is not implemented")
+
+
+def _conv_bwd(st, mod, x_act, cin, da, perm=None, dgrad_out=None, key="id"):
+    """Backward of mod.conv given da (bf16 NHWC gradient of the raw convolution output): weight gradient into the
+    state, data gradient into dgrad_out (bf16 NHWC or fp32 NCHW; channels in the staging order of x_act)."""
+    n = mod.conv.out_channels
+    dw = ops.conv_wgrad(x_act, cin, da, n, mod.taps)
+    if perm is not None:   # staging order -> the weight's own input-channel order
+        full = torch.empty_like(dw)
+        full[:, perm] = dw
+        dw = full
+    st.add(mod.conv.weight, dw)
+    if dgrad_out is not None:
+        wd, cp = mod.packed_dgrad(key, perm)
+        ops.conv_gemm(da, cp, wd, cin, mod.taps, None, None, "none", dgrad_out)
+
+
+def _norm_act_bwd(st, mod, dh, h, act_fn):
+    """Backward of h = act(ActNorm(conv)) for a Conv2dNorm: returns da (bf16 NHWC), accumulates d logs / d bias."""
+    _check_actnorm(mod)
+    assert dh.shape[-1] == h.shape[-1]
+    n = mod.conv.out_channels
+    scale, _ = mod.norm_type.affine()
+    da, r_dv, r_dvv = ops.act_affine_bwd(dh, h, n, scale, act_fn)
+    st.add(mod.norm_type.logs, r_dvv)
+    st.add(mod.norm_type.bias, scale * r_dv)
+    return da
+
+
+def _zeros_out_bwd(st, mod, dout, out):
+    """Backward of a Conv2dZeros' output affine out = (conv + bias) * exp(3 logs) from fp32 NCHW (dout, out)."""
+    B, n, H, W = out.shape
+    dh, h = _nhwc(B, H, W, n, out.device), _nhwc(B, H, W, n, out.device)
+    ops.pack_nhwc(dout, 0, n, dh, 0)
+    ops.pack_nhwc(out, 0, n, h, 0)
+    scale, _ = mod.affine()
+    da, r_dv, r_dvv = ops.act_affine_bwd(dh, h, n, scale, "none")
+    st.add(mod.logs, mod.logscale_factor * r_dvv)
+    st.add(mod.conv.bias, scale * r_dv)
+    return da
+
+
+# ----------------------------------------------------------------------------------------
+# GlowStep
+# ----------------------------------------------------------------------------------------
+def _glowstep_fwd(step, x, ld, nn_template, cc, l, tape):
+    if isinstance(step.norm, BatchNormFlow):
+        raise NotImplementedError("recurrent-flows-msc_b200: backward for flow_norm='batchnorm' is not implemented")
+    aff = step.affine
+    net = aff.net
+    B, C, H, W = x.shape
+    half, hid, act, dev = C // 2, aff.hidden_units, aff.non_lin, x.device
+    if net[4].taps != 9 or 9 * C > TAP_SPLIT_MAX_N:
+        raise NotImplementedError("recurrent-flows-msc_b200: coupling backward needs the tap-split form (C <= 256)")
+    step.norm.maybe_initialize(x)
+    Wf, bf, _, _, _ = step._folded()
+    nn_in = nn_template.clone()
+    y = ops.mix1x1(x, Wf, bf, side=nn_in, side_n=half, side_off=cc, logdet=ld, addend=step._dlogdet(H * W), alpha=1.0)
+    h1, h2 = _nhwc(B, H, W, hid, dev), _nhwc(B, H, W, hid, dev)
+    net[0].fused(nn_in, h1, act, "cz", aff._perm(dev))
+    net[2].fused(h1, h2, act)
+    wgt9, cp = net[4].packed_taps()
+    taps = torch.empty(B, 9 * C, H, W, device=dev, dtype=torch.float32)
+    ops.conv_gemm(h2, cp, wgt9, 9 * C, 1, None, None, "none", taps)
+    ops.coupling_tail_taps(taps, y, *aff.tail_params(), ld, False)
+    tape.append(lambda st: _glowstep_bwd(st, step, x, y, nn_in, h1, h2, taps, cc, l))
+    return y
+
+
+def _glowstep_bwd(st, step, x, zo, nn_in, h1, h2, taps, cc, l):
+    aff = step.affine
+    net = aff.net
+    B, C, H, W = zo.shape
+    half, hid, act, dev = C // 2, aff.hidden_units, aff.non_lin, zo.device
+    dz = st.dz
+    scale, shift, clamp, cs, csh = aff.tail_params()
+    dsum, d_sc, d_sh, d_cs, d_csh = ops.coupling_taps_bwd(taps, zo, dz, scale, shift, clamp, cs, csh, st.g_ld)
+    last = net[4]
+    st.add(last.logs, last.logscale_factor * (d_sc * scale + d_sh * shift))
+    st.add(last.conv.bias, d_sh * scale)
+    if clamp == "realnvp":
+        st.add(aff.scale, d_cs)
+        st.add(aff.scale_shift, d_csh)
+    dS = _nhwc(B, H, W, C, dev)
+    ops.pack_nhwc(dsum, 0, C, dS, 0)
+    dh2 = _nhwc(B, H, W, hid, dev)
+    _conv_bwd(st, last, h2, hid, dS, dgrad_out=dh2)
+    da2 = _norm_act_bwd(st, net[2], dh2, h2, act)
+    dh1 = _nhwc(B, H, W, hid, dev)
+    _conv_bwd(st, net[2], h1, hid, da2, dgrad_out=dh1)
+    da1 = _norm_act_bwd(st, net[0], dh1, h1, act)
+    cin = half + cc
+    dnn = torch.empty(B, cin, H, W, device=dev, dtype=torch.float32)
+    _conv_bwd(st, net[0], nn_in, cin, da1, perm=aff._perm(dev), dgrad_out=dnn, key="cz")
+    dz[:, :half] += dnn[:, cc:]
+    if cc:
+        st.add_cond(l, dnn[:, :cc])
+    # ActNorm folded into the 1x1 mix: y = Wf x + bf
+    Wf = step._folded()[0]
+    dWf, dbf = ops.mix1x1_wgrad(x, dz)
+    st.dz = ops.mix1x1(dz, Wf.t().contiguous(), None)
+    _fold_bwd(st, step, dWf, dbf, H * W)
+
+
+def _fold_bwd(st, step, dWf, dbf, hw):
+    """Chain (d Wf, d bf, d logdet) back to ActNorm's (bias, logs) and InvConv's parameters (Flow/glow_modules.py:
+    33-54, 167-205) -- C x C tensors, differentiated by torch autograd."""
+    inv = step.invconv
+    params = [step.norm.bias, step.norm.logs, *inv._params()]
+    with torch.enable_grad():
+        leaf = [p.detach().float().requires_grad_() for p in params]
+        bias, logs = leaf[0].reshape(-1), leaf[1].reshape(-1)
+        if inv.LU_decomposed:
+            dev = leaf[2].device
+            l_mask, eye = inv.l_mask.to(dev), inv.eye.to(dev)
+            lower = leaf[2] * l_mask + eye
+            u = leaf[3] * l_mask.transpose(0, 1) + torch.diag(inv.sign_s * torch.exp(leaf[4]))
+            Wm = torch.matmul(inv.p, torch.matmul(lower, u))
+            ldw = torch.sum(leaf[4])
+        else:
+            Wm = leaf[2]
+            ldw = torch.linalg.slogdet(Wm)[1]
+        s = torch.exp(logs)
+        Wf = Wm * s[None, :]
+        bfv = torch.mv(Wf, bias)
+        dl = (ldw + logs.sum()) * hw
+        gs = torch.autograd.grad([Wf, bfv, dl], leaf, [dWf, dbf, st.G])
+    for p, g in zip(params, gs):
+        st.add(p, g)
+
+
+# ----------------------------------------------------------------------------------------
+# Split2d
+# ----------------------------------------------------------------------------------------
+def _split_fwd(sp, z, ld, nn_template, l, tape):
+    B, C, H, W = z.shape
+    half, cc, dev = sp._half, sp._cond, z.device
+    sp_in = _nhwc(B, H, W, half + cc, dev)
+    perm, t1 = None, None
+    if sp.make_conditional:
+        t1 = _nhwc(B, H, W, cc, dev)
+        sp.convcond[0].fused(nn_template, t1, "relu")     # the level's condition sits at channels [0, cc)
+        sp.convcond[2].fused(t1, sp_in, "relu")
+        perm = torch.cat([torch.arange(half, half + cc, device=dev), torch.arange(0, half, device=dev)])
+    ops.pack_nhwc(z, 0, half, sp_in, cc)
+    params = torch.empty(B, 2 * half, H, W, device=dev, dtype=torch.float32)
+    sp.conv[0].fused(sp_in, params, "cz", perm)
+    z1 = torch.empty(B, half, H, W, device=dev, dtype=torch.float32)
+    ops.copy_channels(z, 0, z1, 0, half)
+    ops.gauss_logp(z, half, params, half, ops.PAIR_CROSS, sp.clamp_function, ld)
+    tape.append(lambda st: _split_bwd(st, sp, z, params, sp_in, t1, nn_template, perm, l))
+    return z1
+
+
+def _split_bwd(st, sp, z, params, sp_in, t1, cbuf, perm, l):
+    B, C, H, W = z.shape
+    half, cc, dev = sp._half, sp._cond, z.device
+    dzf = torch.zeros(B, 2 * half, H, W, device=dev, dtype=torch.float32)
+    ops.copy_channels(st.dz, 0, dzf, 0, half)
+    dparams = ops.gauss_logp_bwd(z, half, half, params, ops.PAIR_CROSS, sp.clamp_function, st.g_ld, dzf)
+    conv = sp.conv[0]
+    da = _zeros_out_bwd(st, conv, dparams, params)
+    cin = half + cc
+    dsp = _nhwc(B, H, W, cin, dev) if cc else None
+    _conv_bwd(st, conv, sp_in, cin, da, perm=perm, dgrad_out=dsp, key="cz")
+    # the z1 rows once more as fp32 NCHW for the main gradient
+    dz1 = torch.empty(B, half, H, W, device=dev, dtype=torch.float32)
+    wd, cp = conv._cache.get(("wd", "z1"), (conv.conv.weight,),
+                             lambda: ops.pack_dgrad_weight(conv.conv.weight, torch.arange(0, half, device=dev)))
+    ops.conv_gemm(da, cp, wd, half, conv.taps, None, None, "none", dz1)
+    dzf[:, :half] += dz1
+    if sp.make_conditional:
+        c0, c2 = sp.convcond[0], sp.convcond[2]
+        da2 = _norm_act_bwd(st, c2, dsp, sp_in, "relu")
+        dt1 = _nhwc(B, H, W, cc, dev)
+        _conv_bwd(st, c2, t1, cc, da2, dgrad_out=dt1)
+        da1 = _norm_act_bwd(st, c0, dt1, t1, "relu")
+        dc = torch.empty(B, cc, H, W, device=dev, dtype=torch.float32)
+        _conv_bwd(st, c0, cbuf, cc, da1, dgrad_out=dc)
+        st.add_cond(l, dc)
+    st.dz = dzf
+
+
+# ----------------------------------------------------------------------------------------
+# prior
+# ----------------------------------------------------------------------------------------
+def _prior_fwd(flow, z, base_condition, obj, tape):
+    n = z.shape[1]
+    if not flow.learn_prior:
+        ops.gauss_logp(z, 0, None, n, ops.PAIR_SPLIT, "exp", obj)
+        tape.append(lambda st: ops.gauss_logp_bwd(z, 0, n, None, ops.PAIR_SPLIT, "exp", st.g_ld, st.dz))
+        return
+    bc = ops.f32c(base_condition)
+    B, Cb, H, W = bc.shape
+    dev = bc.device
+    u1, u2, act = flow.n_units_prior, flow.n_units_prior // 2, flow.non_lin_glow
+    a0, a1, a2 = _nhwc(B, H, W, Cb, dev), _nhwc(B, H, W, u1, dev), _nhwc(B, H, W, u2, dev)
+    ops.pack_nhwc(bc, 0, Cb, a0, 0)
+    _check_actnorm(flow.prior[0])
+    flow.prior[0].fused(a0, a1, act)
+    flow.prior[2].fused(a1, a2, act)
+    params = torch.empty(B, 2 * n, H, W, device=dev, dtype=torch.float32)
+    flow.prior[4].fused(a2, params)
+    ops.gauss_logp(z, 0, params, n, ops.PAIR_SPLIT, "exp", obj)
+
+    def bwd(st):
+        dparams = ops.gauss_logp_bwd(z, 0, n, params, ops.PAIR_SPLIT, "exp", st.g_ld, st.dz)
+        da = _zeros_out_bwd(st, flow.prior[4], dparams, params)
+        dh2 = _nhwc(B, H, W, u2, dev)
+        _conv_bwd(st, flow.prior[4], a2, u2, da, dgrad_out=dh2)
+        da2 = _norm_act_bwd(st, flow.prior[2], dh2, a2, act)
+        dh1 = _nhwc(B, H, W, u1, dev)
+        _conv_bwd(st, flow.prior[2], a1, u1, da2, dgrad_out=dh1)
+        da1 = _norm_act_bwd(st, flow.prior[0], dh1, a1, act)
+        st.dbase = torch.empty(B, Cb, H, W, device=dev, dtype=torch.float32)
+        _conv_bwd(st, flow.prior[0], a0, Cb, da1, dgrad_out=st.dbase)
+    tape.append(bwd)
+
+
+# ----------------------------------------------------------------------------------------
+# ListGlow.log_prob
+# ----------------------------------------------------------------------------------------
+def _log_prob_fwd(flow, x, conds, base_condition, obj0):
+    """Forward of ListGlow.f + prior with a tape.  Returns (z, obj[B], tape)."""
+    tape = []
+    z = ops.f32c(x)
+    B, dev = z.shape[0], z.device
+    obj = obj0.to(device=dev, dtype=torch.float32).clone().contiguous()
+    l = 0
+    template = None
+    for mod in flow.glow_frame:
+        if isinstance(mod, Squeeze2d):
+            z = ops.squeeze2d(z, False)
+            tape.append(lambda st: setattr(st, "dz", ops.squeeze2d(st.dz, True)))
+            cond = ops.f32c(conds[l])
+            assert cond.shape[2:4] == z.shape[2:4], "condition and x in affine needs to match"
+            cc = cond.shape[1]
+            template = _nhwc(B, z.shape[2], z.shape[3], z.shape[1] // 2 + cc, dev)
+            ops.pack_nhwc(cond, 0, cc, template, 0)
+        elif isinstance(mod, Split2d):
+            z = _split_fwd(mod, z, obj, template, l, tape)
+            l += 1
+        else:
+            z = _glowstep_fwd(mod, z, obj, template, cc, l, tape)
+    _prior_fwd(flow, z, base_condition, obj, tape)
+    return z, obj, tape
+
+
+class _LogProb(torch.autograd.Function):
+    """(z, nll) = ListGlow.log_prob with gradients for x, the conditions, the base condition and every parameter."""
+
+    @staticmethod
+    def forward(ctx, flow, n_cond, obj0, x, base_condition, *rest):
+        conds, params = list(rest[:n_cond]), rest[n_cond:]
+        z, obj, tape = _log_prob_fwd(flow, x, conds, base_condition, obj0)
+        ctx.flow, ctx.tape, ctx.n_cond, ctx.params = flow, tape, n_cond, params
+        ctx.cond_shapes = [c.shape for c in conds]
+        ctx.has_base = base_condition is not None
+        z_out = z.clone()   # the tape keeps z itself
+        return z_out, -obj
+
+    @staticmethod
+    def backward(ctx, dz, dnll):
+        if ctx.tape is None:
+            raise RuntimeError("recurrent-flows-msc_b200: log_prob's tape was already consumed (no retain_graph)")
+        dz = ops.f32c(dz).clone()
+        g_ld = (-ops.f32c(dnll)).contiguous()
+        st = _State(dz, g_ld, ctx.n_cond)
+        tape, ctx.tape = ctx.tape, None
+        while tape:
+            tape.pop()(st)
+        dconds = [st.dcond[i] for i in range(ctx.n_cond)]
+        pgrads = [st.grads.get(id(p)) for p in ctx.params]
+        pgrads = [None if g is None else g.to(p.dtype) for g, p in zip(pgrads, ctx.params)]
+        return (None, None, None, st.dz, st.dbase if ctx.has_base else None, *dconds, *pgrads)
+
+
+def log_prob_with_grad(flow, x, conds, base_condition, obj0):
+    params = [p for p in flow.parameters() if p.requires_grad]
+    return _LogProb.apply(flow, len(conds), obj0, x, base_condition, *conds, *params)

@@ -435,12 +435,13 @@ extern "C" int rfk_gauss_logp_bwd(const float* z, int z_C, int z_off, const floa
 extern "C" int rfk_act_affine_bwd(const void* dh, const void* h, int ld, int n, const float* scale, int act_fn, void* da,
                                   int da_ld, float* r_dv, float* r_dvv, long long rows, void* stream) {
   RFK_REQUIRE(dh && h && da && scale && r_dv && r_dvv && rows > 0 && n > 0, "rfk_act_affine_bwd: null pointer or empty shape");
-  RFK_REQUIRE(n % 8 == 0 && n <= 2048 && ld % 8 == 0 && da_ld % 8 == 0 && n <= ld && n <= da_ld,
-              "rfk_act_affine_bwd: n=%d must be a multiple of 8 (<= 2048) within 8-aligned row strides", n);
+  const int n8 = (n + 7) / 8 * 8;   // channels are handled in groups of 8; the tail group reads/writes pad columns
+  RFK_REQUIRE(n <= 2048 && ld % 8 == 0 && da_ld % 8 == 0 && n8 <= ld && n8 <= da_ld,
+              "rfk_act_affine_bwd: n=%d (<= 2048) rounded up to 8 must fit the 8-aligned row strides", n);
   RFK_REQUIRE(((reinterpret_cast<uintptr_t>(dh) | reinterpret_cast<uintptr_t>(h) | reinterpret_cast<uintptr_t>(da)) & 15) == 0,
               "rfk_act_affine_bwd: tensors must be 16-byte aligned");
   RFK_REQUIRE(act_fn >= 0 && act_fn <= 2, "rfk_act_affine_bwd: bad act_fn %d", act_fn);
-  RFK_REQUIRE((n / 8) <= 256, "rfk_act_affine_bwd: too many channels per row for one CTA");
+  RFK_REQUIRE((n8 / 8) <= 256, "rfk_act_affine_bwd: too many channels per row for one CTA");
   const int ctas = (int)std::min<long long>((long long)sm_count() * 4, (rows + 63) / 64);
   const long long rows_per_cta = (rows + ctas - 1) / ctas;
   RFK_LAUNCH(act_affine_bwd_kernel, ctas, 256, 0, (cudaStream_t)stream, (const __nv_bfloat16*)dh, (const __nv_bfloat16*)h,

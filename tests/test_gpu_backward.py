@@ -32,7 +32,8 @@ def staged(ops, x):
 
 
 CONVS = [(2, 18, 32, 32, 256, 3), (3, 256, 16, 16, 256, 1), (2, 64, 8, 8, 36, 1), (5, 72, 8, 8, 256, 3),
-         (30, 288, 2, 2, 256, 3), (2, 40, 5, 7, 24, 3), (2, 256, 6, 6, 72, 1)]
+         (30, 288, 2, 2, 256, 3), (2, 40, 5, 7, 24, 3), (2, 256, 6, 6, 72, 1), (3, 7, 8, 8, 64, 3), (3, 11, 4, 4, 64, 3),
+         (3, 64, 4, 4, 4, 3)]
 
 
 @pytest.mark.parametrize("B,Cin,H,W,N,k", CONVS)
@@ -55,7 +56,7 @@ def test_conv_wgrad_and_dgrad(ops, B, Cin, H, W, N, k):
 
 
 @pytest.mark.parametrize("act", ["relu", "leakyrelu", "none"])
-@pytest.mark.parametrize("rows,n,ld", [(4096, 256, 256), (1000, 64, 64), (77, 16, 32), (3000, 512, 512)])
+@pytest.mark.parametrize("rows,n,ld", [(4096, 256, 256), (1000, 64, 64), (77, 16, 32), (3000, 512, 512), (300, 4, 32), (129, 13, 32)])
 def test_act_affine_bwd(ops, act, rows, n, ld):
     g = torch.Generator().manual_seed(rows + n)
     a = torch.randn(rows, n, generator=g, requires_grad=True)
