@@ -249,6 +249,19 @@ int rfk_mix1x1_wgrad(const float* x, const float* dy, int B, int C, int HW, floa
 int rfk_gauss_logp_bwd(const float* z, int z_C, int z_off, const float* params, int n, int B, int HW, int pairing,
                        int std_kind, const float* g, float* dz, float* dparams, void* stream);
 
+/* Weight repacking (one launch per conv weight per optimizer step): fp32 [N, Cin, taps] (tap = 3*ky + kx) -> bf16 K-major
+ * GEMM operand dst[rows_pad, ktot], zero-padded.  mode 0: forward conv, row n, k = t*kp + j <- W[n, perm[j], t] (perm
+ * nullable = identity over Cin, staging-buffer channel order); mode 1: data-gradient conv, row r (rows = len(perm) or Cin),
+ * k = t*kp + co <- W[co, perm[r], taps-1-t]; mode 2: tap-split 1x1 form, row t*N + c, k = j <- W[c, j, t]. */
+int rfk_pack_weight(const float* src, int N, int Cin, int taps, int mode, const int* perm, int rows, int kp,
+                    void* dst, int rows_pad, int ktot, void* stream);
+
+/* Adam over all parameters in one launch (torch.optim.Adam without weight decay / amsgrad; the reference trains with
+ * Adam, RFN/trainer.py).  p, g, m, v: flat fp32 buffers of n elements (n % 4 == 0, 16-byte aligned); g is multiplied by
+ * grad_scale first (1/world after a sum-allreduce); *step = the 1-based step count, on the device (graph replay). */
+int rfk_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                  float eps, float grad_scale, const float* step, void* stream);
+
 /* Debug aid: when buf != NULL, every conv-GEMM CTA of later launches (grids of at most capacity_ctas CTAs)
  * writes 16 words to buf[16*cta..]: %globaltimer stamps (ns) 0 start, 1 setup done, 2 weights resident, 3 last TMA
  * issued, 4 last MMA issued, 5 first accumulator ready, 6 first epilogue done, 7 all done; SM-cycle totals 8 producer

@@ -67,10 +67,20 @@ class GlowStep(nn.Module):
             return Wf, bf, Wr, br, (per_pixel + logs.sum()).reshape(())
         return self._cache.get("fold", (self.norm.bias, self.norm.logs) + self.invconv._params(), build)
 
+    def _folded_fwd(self):
+        """(Wf, bf, per-pixel log-det) of the forward direction only (no matrix inverses: density evaluation, training)."""
+        def build():
+            W, per_pixel = self.invconv.weight_fwd()
+            logs = self.norm.logs.detach().float().reshape(-1)
+            bias = self.norm.bias.detach().float().reshape(-1)
+            Wf = (W * torch.exp(logs)[None, :]).contiguous()
+            return Wf, torch.mv(Wf, bias).contiguous(), (per_pixel + logs.sum()).reshape(())
+        return self._cache.get("fold_f", (self.norm.bias, self.norm.logs) + self.invconv._params(), build)
+
     def _dlogdet(self, hw):
         """H*W*(sum logs + log|det W|) as a cached device scalar (Flow/glow_modules.py:43,196)."""
         return self._cache.get(("dl", hw), (self.norm.bias, self.norm.logs) + self.invconv._params(),
-                               lambda: (self._folded()[4] * hw).reshape(1).contiguous())
+                               lambda: (self._folded_fwd()[2] * hw).reshape(1).contiguous())
 
     def forward(self, x, condition, logdet, reverse, _ctx=None):
         _require_no_grad()
@@ -109,14 +119,14 @@ class GlowStep(nn.Module):
             if pend is not None and pend[2].data_ptr() == x.data_ptr() and self.norm.is_initialized():
                 # the previous step's coupling tail (tap gather + affine) is still pending: absorb it into this step's mix
                 _ctx.pending = None
-                Wf, bf, _, _, _ = self._folded()
+                Wf, bf, _ = self._folded_fwd()
                 dl = None if ld is None else self._dlogdet(H * W)
                 y = ops.coupling_taps_mix(pend[1], x, *pend[0].tail_params(), pend[3], False, Wf, bf,
                                           side=_ctx.nn_in, side_n=C // 2, side_off=cc, logdet=ld, addend=dl, alpha=1.0)
             else:
                 _ctx.flush()
                 self.norm.maybe_initialize(x)
-                Wf, bf, _, _, _ = self._folded()
+                Wf, bf, _ = self._folded_fwd()
                 dl = None if ld is None else self._dlogdet(H * W)
                 y = ops.mix1x1(x, Wf, bf, side=_ctx.nn_in, side_n=C // 2, side_off=cc, logdet=ld, addend=dl, alpha=1.0)
             _ctx.z1_packed = True

@@ -27,15 +27,25 @@ def _require_no_grad():
                            "call the flow under torch.no_grad() (density evaluation / sampling)")
 
 
+_PARAM_EPOCH = [0]
+
+
+def invalidate_caches():
+    """Drop every tensor derived from parameters (packed weights, folded ActNorm/InvConv matrices).  Needed only when
+    parameters were written through raw pointers (the fused Adam kernel, a CUDA-graph replay of a training step):
+    in-place torch ops, load_state_dict and .to() are detected through the tensors' version counters."""
+    _PARAM_EPOCH[0] += 1
+
+
 class _Versioned:
     """Cache of tensors derived from parameters, rebuilt when a parameter is modified in place
-    (optimizer step, load_state_dict) or re-allocated (.to(), .cuda())."""
+    (optimizer step, load_state_dict) or re-allocated (.to(), .cuda()), or after invalidate_caches()."""
 
     def __init__(self):
         self._store = {}
 
     def get(self, key, params, build):
-        ver = tuple((p.data_ptr(), p._version) for p in params)
+        ver = (_PARAM_EPOCH[0],) + tuple((p.data_ptr(), p._version) for p in params)
         hit = self._store.get(key)
         if hit is None or hit[0] != ver:
             with torch.no_grad():
@@ -325,6 +335,16 @@ class InvConv(nn.Module):
     def _params(self):
         return (self.lower, self.upper, self.log_s) if self.LU_decomposed else (self.weight,)
 
+    def _consts(self, dev):
+        """(l_mask, eye) on the parameters' device.  The reference keeps them as plain CPU attributes and moves them on
+        every call (Flow/glow_modules.py:172-173,190-191); here the device copies are made once (also: no host-to-device
+        copy may happen inside a CUDA-graph capture)."""
+        hit = self.__dict__.get("_consts_dev")
+        if hit is None or hit[0].device != dev:
+            hit = (self.l_mask.to(dev), self.eye.to(dev))
+            self.__dict__["_consts_dev"] = hit
+        return hit
+
     def matrices(self):
         """(W, W^-1, per-pixel log|det W|) as device tensors; cached until a parameter changes.
         Follows Flow/glow_modules.py:188-205 (three triangular inverses in the LU form)."""
@@ -332,8 +352,7 @@ class InvConv(nn.Module):
             if not self.LU_decomposed:
                 w = self.weight.detach().float()
                 return w.contiguous(), torch.linalg.inv(w).contiguous(), torch.linalg.slogdet(w)[1]
-            dev = self.lower.device
-            l_mask, eye = self.l_mask.to(dev), self.eye.to(dev)
+            l_mask, eye = self._consts(self.lower.device)
             lower = self.lower.detach() * l_mask + eye
             u = self.upper.detach() * l_mask.transpose(0, 1).contiguous()
             u = u + torch.diag(self.sign_s * torch.exp(self.log_s.detach()))
@@ -341,6 +360,20 @@ class InvConv(nn.Module):
             w_inv = torch.matmul(torch.linalg.inv(u), torch.matmul(torch.linalg.inv(lower), torch.linalg.inv(self.p)))
             return w.contiguous(), w_inv.contiguous(), torch.sum(self.log_s.detach())
         return self._cache.get("m", self._params(), build)
+
+    def weight_fwd(self):
+        """(W, per-pixel log|det W|) without the inverses -- all the forward direction (density, training) needs; no
+        factorisation with a host-side status check, so it may run inside a CUDA-graph capture (LU form)."""
+        def build():
+            if not self.LU_decomposed:
+                w = self.weight.detach().float()
+                return w.contiguous(), torch.linalg.slogdet(w)[1]
+            l_mask, eye = self._consts(self.lower.device)
+            lower = self.lower.detach() * l_mask + eye
+            u = self.upper.detach() * l_mask.transpose(0, 1).contiguous()
+            u = u + torch.diag(self.sign_s * torch.exp(self.log_s.detach()))
+            return torch.matmul(self.p, torch.matmul(lower, u)).contiguous(), torch.sum(self.log_s.detach())
+        return self._cache.get("mf", self._params(), build)
 
     def get_weight(self, input, reverse):
         b, c, h, w = input.shape
@@ -495,6 +528,19 @@ class Split2d(nn.Module):
             assert False, 'Please specify a clamp function for the split2d from the set {softplus, exp}'
         self.clamp_function = clamp_function
 
+    def _perm(self, device):
+        """Staging order [convcond(condition) | z1] -> the conv weight's cat[z1, h] order (None when unconditional);
+        second element: the z1 rows alone (for the data gradient w.r.t. z1)."""
+        hit = self.__dict__.get("_perm_cache")
+        if hit is None or hit[1].device != device:
+            half, cc = self._half, self._cond
+            perm = None
+            if self.make_conditional:
+                perm = torch.cat([torch.arange(half, half + cc, device=device), torch.arange(0, half, device=device)])
+            hit = (perm, torch.arange(0, half, device=device))
+            self.__dict__["_perm_cache"] = hit
+        return hit
+
     def _params(self, z1_src, condition, _ctx):
         """(mean, raw log-scale) tensor [B, 2*half, H, W] from z1 = first `half` channels of z1_src."""
         B, _, H, W = z1_src.shape
@@ -510,7 +556,7 @@ class Split2d(nn.Module):
             t1 = ops.workspace(("sp_t1", cc), (B, H, W, ops.cin_pad(cc)), dev)
             self.convcond[0].fused(cbuf, t1, "relu")
             self.convcond[2].fused(t1, sp_in, "relu")
-            perm = torch.cat([torch.arange(half, half + cc, device=dev), torch.arange(0, half, device=dev)])
+            perm = self._perm(dev)[0]
         ops.pack_nhwc(z1_src, 0, half, sp_in, cc)
         params = torch.empty(B, 2 * half, H, W, device=dev, dtype=torch.float32)
         return self.conv[0].fused(sp_in, params, "cz", perm)

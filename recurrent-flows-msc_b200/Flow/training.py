@@ -106,7 +106,7 @@ def _glowstep_fwd(step, x, ld, nn_template, cc, l, tape):
     if net[4].taps != 9 or 9 * C > TAP_SPLIT_MAX_N:
         raise NotImplementedError("recurrent-flows-msc_b200: coupling backward needs the tap-split form (C <= 256)")
     step.norm.maybe_initialize(x)
-    Wf, bf, _, _, _ = step._folded()
+    Wf, bf, _ = step._folded_fwd()
     nn_in = nn_template.clone()
     y = ops.mix1x1(x, Wf, bf, side=nn_in, side_n=half, side_off=cc, logdet=ld, addend=step._dlogdet(H * W), alpha=1.0)
     h1, h2 = _nhwc(B, H, W, hid, dev), _nhwc(B, H, W, hid, dev)
@@ -149,7 +149,7 @@ def _glowstep_bwd(st, step, x, zo, nn_in, h1, h2, taps, cc, l):
     if cc:
         st.add_cond(l, dnn[:, :cc])
     # ActNorm folded into the 1x1 mix: y = Wf x + bf
-    Wf = step._folded()[0]
+    Wf = step._folded_fwd()[0]
     dWf, dbf = ops.mix1x1_wgrad(x, dz)
     st.dz = ops.mix1x1(dz, Wf.t().contiguous(), None)
     _fold_bwd(st, step, dWf, dbf, H * W)
@@ -164,8 +164,7 @@ def _fold_bwd(st, step, dWf, dbf, hw):
         leaf = [p.detach().float().requires_grad_() for p in params]
         bias, logs = leaf[0].reshape(-1), leaf[1].reshape(-1)
         if inv.LU_decomposed:
-            dev = leaf[2].device
-            l_mask, eye = inv.l_mask.to(dev), inv.eye.to(dev)
+            l_mask, eye = inv._consts(leaf[2].device)
             lower = leaf[2] * l_mask + eye
             u = leaf[3] * l_mask.transpose(0, 1) + torch.diag(inv.sign_s * torch.exp(leaf[4]))
             Wm = torch.matmul(inv.p, torch.matmul(lower, u))
@@ -194,7 +193,7 @@ def _split_fwd(sp, z, ld, nn_template, l, tape):
         t1 = _nhwc(B, H, W, cc, dev)
         sp.convcond[0].fused(nn_template, t1, "relu")     # the level's condition sits at channels [0, cc)
         sp.convcond[2].fused(t1, sp_in, "relu")
-        perm = torch.cat([torch.arange(half, half + cc, device=dev), torch.arange(0, half, device=dev)])
+        perm = sp._perm(dev)[0]
     ops.pack_nhwc(z, 0, half, sp_in, cc)
     params = torch.empty(B, 2 * half, H, W, device=dev, dtype=torch.float32)
     sp.conv[0].fused(sp_in, params, "cz", perm)
@@ -219,7 +218,7 @@ def _split_bwd(st, sp, z, params, sp_in, t1, cbuf, perm, l):
     # the z1 rows once more as fp32 NCHW for the main gradient
     dz1 = torch.empty(B, half, H, W, device=dev, dtype=torch.float32)
     wd, cp = conv._cache.get(("wd", "z1"), (conv.conv.weight,),
-                             lambda: ops.pack_dgrad_weight(conv.conv.weight, torch.arange(0, half, device=dev)))
+                             lambda: ops.pack_dgrad_weight(conv.conv.weight, sp._perm(dev)[1]))
     ops.conv_gemm(da, cp, wd, half, conv.taps, None, None, "none", dz1)
     dzf[:, :half] += dz1
     if sp.make_conditional:

@@ -15,7 +15,9 @@ from .Flow import (ActNorm, AffineCoupling, Conv2dNorm, Conv2dZeros, GlowStep, I
                    Split2d, Squeeze2d)
 from .Utils import ActFun, ConvLSTM, ConvLSTMLayer, batch_reduce, split_feature  # noqa: F401
 from .parallel import shard_range, shard_batch, sync_module_state  # noqa: F401
-from .graphs import Graphed, GraphedLogProb, GraphedSample  # noqa: F401
+from .graphs import Graphed, GraphedLogProb, GraphedSample, GraphedTrainStep  # noqa: F401
+from .optim import FlatAdam  # noqa: F401
+from .Flow.glow_modules import invalidate_caches  # noqa: F401
 
 __version__ = "0.1.0"
 

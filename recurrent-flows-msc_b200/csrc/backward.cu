@@ -10,9 +10,14 @@
 
 #include <algorithm>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace rfk {
+
+int conv_wgrad_tc(const void* x, int x_ld, int cin, const void* dy, int dy_ld, int cout, int B, int H, int W, int taps,
+                  float* dw, int dw_ld, cudaStream_t stream);   // wgrad_tc.cu
 
 // ------------------------------------------------------------------------------------------
 // h = act(v), v = a*scale + shift (a = raw conv output, scale = e^{logs}, shift = bias*e^{logs}).
@@ -457,6 +462,14 @@ extern "C" int rfk_conv_wgrad(const void* x, int x_ld, int cin, const void* dy, 
               "rfk_conv_wgrad: row strides must be multiples of 8 and cover the channels");
   RFK_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy)) & 15) == 0,
               "rfk_conv_wgrad: x / dy must be 16-byte aligned");
+  {
+    // tensor-core (tcgen05) path; RFK_WGRAD_WMMA=1 keeps the warp-level mma.sync kernel for A/B comparisons
+    static const bool force_wmma = [] { const char* e = getenv("RFK_WGRAD_WMMA"); return e && e[0] == '1'; }();
+    if (!force_wmma) {
+      const int rc = conv_wgrad_tc(x, x_ld, cin, dy, dy_ld, cout, B, H, W, taps, dw, dw_ld, (cudaStream_t)stream);
+      if (rc <= 0) return rc;   // ran (0) or failed (<0); positive = shape not covered, fall through
+    }
+  }
   const long long npix = (long long)B * H * W;
   const int c_tiles = (cin + WG_C - 1) / WG_C, n_tiles = (cout + WG_N - 1) / WG_N;
   const long long base_ctas = (long long)taps * c_tiles * n_tiles;
@@ -471,4 +484,50 @@ extern "C" int rfk_conv_wgrad(const void* x, int x_ld, int cin, const void* dy, 
   RFK_LAUNCH(conv_wgrad_kernel, grid, 256, 0, (cudaStream_t)stream, (const __nv_bfloat16*)x, x_ld, cin,
              (const __nv_bfloat16*)dy, dy_ld, cout, B, H, W, taps, dw, dw_ld, pps);
   return check_launch("rfk_conv_wgrad");
+}
+
+
+// ------------------------------------------------------------------------------------------
+// Adam over ALL parameters of the model in one launch (torch.optim.Adam semantics without weight decay / amsgrad:
+//   m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;  p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps)).
+// p, g, m, v are flat fp32 buffers (the parameters are views into p); g is scaled by grad_scale first (1/world after a
+// sum-allreduce); the step count t lives on the device so that the launch can be replayed from a CUDA graph.
+// HBM-bound: 4 reads + 3 writes of 4 bytes per parameter.
+// ------------------------------------------------------------------------------------------
+namespace rfk {
+__global__ void __launch_bounds__(256) adam_kernel(float4* __restrict__ p, const float4* __restrict__ g, float4* __restrict__ m,
+                                                   float4* __restrict__ v, long long n4, float lr, float b1, float b2, float eps,
+                                                   float grad_scale, const float* __restrict__ step) {
+  pdl_trigger();
+  pdl_wait();
+  const float t = *step;
+  const float step_size = lr / (1.0f - powf(b1, t));
+  const float inv_bc2 = rsqrtf(1.0f - powf(b2, t));
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 pv = p[i], gv = g[i], mv = m[i], vv = v[i];
+    float* pp = reinterpret_cast<float*>(&pv);
+    float* gp = reinterpret_cast<float*>(&gv);
+    float* mp = reinterpret_cast<float*>(&mv);
+    float* vp = reinterpret_cast<float*>(&vv);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float gg = gp[k] * grad_scale;
+      mp[k] = b1 * mp[k] + (1.0f - b1) * gg;
+      vp[k] = b2 * vp[k] + (1.0f - b2) * gg * gg;
+      pp[k] -= step_size * mp[k] / (sqrtf(vp[k]) * inv_bc2 + eps);
+    }
+    p[i] = pv; m[i] = mv; v[i] = vv;
+  }
+}
+}  // namespace rfk
+
+extern "C" int rfk_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                             float eps, float grad_scale, const float* step, void* stream) {
+  using namespace rfk;
+  RFK_REQUIRE(p && g && m && v && step && n > 0 && n % 4 == 0, "rfk_adam_step: null pointer, or n=%lld is not a multiple of 4", n);
+  RFK_REQUIRE(((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                reinterpret_cast<uintptr_t>(v)) & 15) == 0, "rfk_adam_step: buffers must be 16-byte aligned");
+  RFK_LAUNCH(adam_kernel, stream_grid(n / 4, 256, 8), 256, 0, (cudaStream_t)stream, (float4*)p, (const float4*)g, (float4*)m,
+             (float4*)v, n / 4, lr, beta1, beta2, eps, grad_scale, step);
+  return check_launch("rfk_adam_step");
 }

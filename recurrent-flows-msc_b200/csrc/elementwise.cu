@@ -1080,3 +1080,52 @@ extern "C" int rfk_add_scalar(float* logdet, const float* addend, float alpha, i
   RFK_LAUNCH(add_scalar_kernel, ceil_div(B, 256), 256, 0, (cudaStream_t)stream, logdet, addend, alpha, B);
   return check_launch("rfk_add_scalar");
 }
+
+
+// ------------------------------------------------------------------------------------------
+// Weight repacking: fp32 [N, Cin, taps] conv weights -> the bf16 K-major GEMM operand [rows_pad, ktot] of
+//   mode 0  the forward conv:        row n,        k = t*kp + j   <- W[n, perm[j], t]
+//   mode 1  the data-gradient conv:  row r,        k = t*kp + co  <- W[co, perm[r], taps-1-t]   (flipped, in/out swapped)
+//   mode 2  the tap-split 1x1 form:  row t*N + c,  k = j          <- W[c, j, t]
+// One launch per weight (the optimizer changes every weight every step, so this runs once per conv per step).
+// ------------------------------------------------------------------------------------------
+namespace rfk {
+__global__ void __launch_bounds__(256) pack_weight_kernel(const float* __restrict__ src, int N, int Cin, int taps, int mode,
+                                                          const int* __restrict__ perm, int rows, int kp,
+                                                          __nv_bfloat16* __restrict__ dst, int rows_pad, int ktot) {
+  pdl_trigger();
+  pdl_wait();
+  const long long total = (long long)rows_pad * ktot;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / ktot), k = (int)(i % ktot);
+    float v = 0.0f;
+    if (r < rows) {
+      if (mode == 0) {
+        const int t = k / kp, j = k % kp;
+        if (j < Cin) v = src[((long long)r * Cin + (perm ? perm[j] : j)) * taps + t];
+      } else if (mode == 1) {
+        const int t = k / kp, co = k % kp;
+        if (co < N) v = src[((long long)co * Cin + (perm ? perm[r] : r)) * taps + (taps - 1 - t)];
+      } else {
+        const int t = r / N, c = r % N;
+        if (k < Cin) v = src[((long long)c * Cin + k) * taps + t];
+      }
+    }
+    dst[i] = __float2bfloat16(v);
+  }
+}
+}  // namespace rfk
+
+extern "C" int rfk_pack_weight(const float* src, int N, int Cin, int taps, int mode, const int* perm, int rows, int kp,
+                               void* dst, int rows_pad, int ktot, void* stream) {
+  using namespace rfk;
+  RFK_REQUIRE(src && dst && N > 0 && Cin > 0 && taps > 0 && rows > 0 && rows <= rows_pad && kp > 0 && ktot > 0,
+              "rfk_pack_weight: null pointer or bad shape");
+  RFK_REQUIRE(mode >= 0 && mode <= 2, "rfk_pack_weight: unknown mode %d", mode);
+  RFK_REQUIRE(mode == 2 ? (ktot == kp && kp >= Cin && rows == taps * N) : (ktot == taps * kp && kp >= (mode == 0 ? Cin : N)),
+              "rfk_pack_weight: ktot=%d / kp=%d do not match mode %d", ktot, kp, mode);
+  const long long total = (long long)rows_pad * ktot;
+  RFK_LAUNCH(pack_weight_kernel, stream_grid(total, 256, 8), 256, 0, (cudaStream_t)stream, src, N, Cin, taps, mode, perm, rows,
+             kp, (__nv_bfloat16*)dst, rows_pad, ktot);
+  return check_launch("rfk_pack_weight");
+}

@@ -1,0 +1,290 @@
+// Convolution weight gradient on the 5th-generation tensor cores (sm_100a): tcgen05.mma with BOTH operands MN-major.
+//
+//   dW[tap][n][c] = sum_p dY[p, n] * X[p + off(tap), c]        X, dY: NHWC bf16; taps outside the image contribute zero
+//
+// The reduction dimension is the PIXEL index, which is the slow dimension of both NHWC operands, so each operand tile is
+// "MN-major" for the MMA: a 4-D TMA box {64 channels, TW, TH, NIMG} with SWIZZLE_128B lands in shared memory as 128 pixel
+// rows of 128 bytes -- exactly the canonical MN-major SWIZZLE_128B layout (8 K-rows x 64 MN-elements per swizzle atom,
+// 8-row groups 1024 B apart, 64-channel atoms one box = 16 KB apart).  The tap shift is a coordinate offset of the box of
+// one operand; out-of-image rows are zero-filled by TMA, which is the convolution's zero padding.
+//
+// Roles: the operand with more channels is the M side (128 channels per CTA = two boxes); the other one is the N side
+// (up to 256 columns per tap).  All taps of a CTA accumulate in tensor memory at the same time (taps x n_cols <= 512
+// columns) over the CTA's whole slice of pixel tiles, so the M-side tile is loaded once per pixel tile and reused by every
+// tap; the accumulators are read once at the end and added to dW with fp32 atomics (the pixel range is split over CTAs).
+//
+//   warp 0   TMA producer: M-side ring (2 stages x 32 KB), N-side ring (one stage per tap, nbox x 16 KB each)
+//   warp 1   MMA issuer:   8 x tcgen05.mma (K = 16 pixels each) per (pixel tile, tap)
+//   warp 2   TMEM allocation
+//   warps 4-7 epilogue:    tcgen05.ld -> atomicAdd
+#include <algorithm>
+
+#include "tc_ptx.cuh"
+
+namespace rfk {
+
+namespace {
+
+constexpr int WT_THREADS = 256;
+constexpr int WT_BOX_BYTES = 128 * 128;     // 128 pixel rows x 64 bf16 channels
+constexpr int WT_A_STAGES = 2;
+constexpr int WT_SMEM_LIMIT = 232448;
+
+struct WgradArgs {
+  int tiles_x, tiles_y, tiles;   // pixel tiles (128 pixels each)
+  int tw_log2, th_log2;
+  int taps;                      // 1 or 9
+  int sign;                      // +1: the N-side box is shifted by +off(tap); -1: by -off(tap)
+  int m_total, n_total;          // real channel counts of the M / N side
+  int m_tiles, n_chunks, tap_groups;
+  int n_cols;                    // MMA N per tap (multiple of 16, <= 256)
+  int nbox;                      // 64-channel boxes per N-side stage
+  int tpc;                       // taps per CTA
+  int b_stages;
+  int tmem_cols;
+  int transpose_out;             // 0: dw[tap][m][n]   1: dw[tap][n][m]
+  int dw_ld;                     // row stride of dw
+  int dw_rows;                   // rows per tap of dw (cout)
+  float* dw;
+};
+
+// MN-major SWIZZLE_128B shared-memory matrix descriptor: 64-element atoms 16 KB apart (LBO), 8-row K groups 1 KB apart (SBO)
+__device__ __forceinline__ uint64_t umma_desc_mnmajor(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(WT_BOX_BYTES >> 4) << 16;   // leading byte offset: next 64-channel atom
+  d |= (uint64_t)(1024 >> 4) << 32;           // stride byte offset: next group of 8 pixel rows
+  d |= (uint64_t)1 << 46;                     // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                     // SWIZZLE_128B
+  return d;
+}
+
+__global__ void __launch_bounds__(WT_THREADS, 1) conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                     const __grid_constant__ CUtensorMap tmB,
+                                                                     const WgradArgs g) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t a_bytes = 2u * WT_BOX_BYTES;
+  const uint32_t b_bytes = (uint32_t)g.nbox * WT_BOX_BYTES;
+  const uint32_t a_off = 0, b_off = WT_A_STAGES * a_bytes;
+  const uint32_t bar_off = b_off + (uint32_t)g.b_stages * b_bytes;
+  const uint32_t bar_base = base + bar_off;
+  auto a_full = [&](int s) { return bar_base + 8u * s; };
+  auto a_empty = [&](int s) { return bar_base + 8u * (WT_A_STAGES + s); };
+  auto b_full = [&](int s) { return bar_base + 8u * (2 * WT_A_STAGES + s); };
+  auto b_empty = [&](int s) { return bar_base + 8u * (2 * WT_A_STAGES + g.b_stages + s); };
+  const uint32_t done_bar = bar_base + 8u * (2 * WT_A_STAGES + 2 * g.b_stages);
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + bar_off + 8u * (2 * WT_A_STAGES + 2 * g.b_stages + 1));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // blockIdx.y -> (m tile, n chunk, tap group)
+  int w = blockIdx.y;
+  const int tg = w % g.tap_groups;
+  w /= g.tap_groups;
+  const int nc = w % g.n_chunks;
+  const int mt = w / g.n_chunks;
+  const int tap0 = tg * g.tpc;
+  const int ntap = min(g.tpc, g.taps - tap0);
+  const int n0 = nc * 256;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < WT_A_STAGES; ++s) {
+      mbar_init(a_full(s), 1);
+      mbar_init(a_empty(s), 1);
+    }
+    for (int s = 0; s < g.b_stages; ++s) {
+      mbar_init(b_full(s), 1);
+      mbar_init(b_empty(s), 1);
+    }
+    mbar_init(done_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)),
+                 "r"((uint32_t)g.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  pdl_trigger();
+  pdl_wait();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int nimg_log2 = 7 - g.tw_log2 - g.th_log2;
+  auto tile_origin = [&](int t, int& x0, int& y0, int& i0) {
+    const int tx = t % g.tiles_x;
+    t /= g.tiles_x;
+    const int ty = t % g.tiles_y;
+    x0 = tx << g.tw_log2;
+    y0 = ty << g.th_log2;
+    i0 = (t / g.tiles_y) << nimg_log2;
+  };
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int sa = 0, sb = 0;
+      uint32_t pha = 0, phb = 0;
+      for (int t = blockIdx.x; t < g.tiles; t += gridDim.x) {
+        int x0, y0, i0;
+        tile_origin(t, x0, y0, i0);
+        mbar_wait(a_empty(sa), pha ^ 1u);
+        mbar_expect_tx(a_full(sa), a_bytes);
+        const uint32_t a_dst = base + a_off + sa * a_bytes;
+        tma_load_4d(a_dst, &tmA, a_full(sa), mt * 128, x0, y0, i0);
+        tma_load_4d(a_dst + WT_BOX_BYTES, &tmA, a_full(sa), mt * 128 + 64, x0, y0, i0);
+        if (++sa == WT_A_STAGES) { sa = 0; pha ^= 1u; }
+        for (int tp = 0; tp < ntap; ++tp) {
+          const int tap = tap0 + tp;
+          const int dy = g.taps == 9 ? g.sign * (tap / 3 - 1) : 0, dx = g.taps == 9 ? g.sign * (tap % 3 - 1) : 0;
+          mbar_wait(b_empty(sb), phb ^ 1u);
+          mbar_expect_tx(b_full(sb), b_bytes);
+          const uint32_t b_dst = base + b_off + sb * b_bytes;
+          for (int bx = 0; bx < g.nbox; ++bx)
+            tma_load_4d(b_dst + bx * WT_BOX_BYTES, &tmB, b_full(sb), n0 + bx * 64, x0 + dx, y0 + dy, i0);
+          if (++sb == g.b_stages) { sb = 0; phb ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      // kind::f16, fp32 accumulate, bf16 x bf16, A and B MN-major, N = n_cols, M = 128
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                             ((uint32_t)(g.n_cols >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      int sa = 0, sb = 0;
+      uint32_t pha = 0, phb = 0;
+      bool first = true;
+      for (int t = blockIdx.x; t < g.tiles; t += gridDim.x) {
+        mbar_wait(a_full(sa), pha);
+        tc_fence_after();
+        const uint64_t adesc = umma_desc_mnmajor(base + a_off + sa * a_bytes);
+        for (int tp = 0; tp < ntap; ++tp) {
+          mbar_wait(b_full(sb), phb);
+          tc_fence_after();
+          const uint64_t bdesc = umma_desc_mnmajor(base + b_off + sb * b_bytes);
+          const uint32_t d_tmem = tmem_base + (uint32_t)(tp * g.n_cols);
+#pragma unroll
+          for (int k = 0; k < 8; ++k)   // 16 pixel rows = 2048 bytes per K step (descriptor address in 16-byte units)
+            umma_bf16(d_tmem, adesc + (uint64_t)(128 * k), bdesc + (uint64_t)(128 * k), idesc, (first && k == 0) ? 0u : 1u);
+          umma_commit(b_empty(sb));
+          if (++sb == g.b_stages) { sb = 0; phb ^= 1u; }
+        }
+        umma_commit(a_empty(sa));
+        if (++sa == WT_A_STAGES) { sa = 0; pha ^= 1u; }
+        first = false;
+      }
+      umma_commit(done_bar);
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue: accumulators -> dW (fp32 atomics; the pixel range is split over blockIdx.x) =====
+    const int q = warp & 3;                      // TMEM lane quarter this warp may read
+    const int m = mt * 128 + q * 32 + lane;
+    mbar_wait(done_bar, 0);
+    tc_fence_after();
+    if (blockIdx.x < g.tiles) {
+      for (int tp = 0; tp < ntap; ++tp) {
+        const int tap = tap0 + tp;
+        float* dwt = g.dw + (long long)tap * g.dw_rows * g.dw_ld;
+        for (int c0 = 0; c0 < g.n_cols; c0 += 16) {
+          uint32_t r[16];
+          tmem_ld16_nowait(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(tp * g.n_cols + c0), r);
+          tmem_wait_ld();
+          if (m < g.m_total) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int n = n0 + c0 + j;
+              if (n < g.n_total) {
+                float* dst = g.transpose_out ? dwt + (long long)n * g.dw_ld + m : dwt + (long long)m * g.dw_ld + n;
+                atomicAdd(dst, __uint_as_float(r[j]));
+              }
+            }
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)g.tmem_cols)
+                 : "memory");
+  }
+}
+
+}  // namespace
+
+// Returns RFK_OK when the tensor-core path ran, a positive value when the shape is not covered (caller falls back).
+int conv_wgrad_tc(const void* x, int x_ld, int cin, const void* dy, int dy_ld, int cout, int B, int H, int W, int taps,
+                  float* dw, int dw_ld, cudaStream_t stream) {
+  const char* who = "rfk_conv_wgrad";
+  if (taps != 1 && taps != 9) return 1;
+  WgradArgs g{};
+  const bool swap = cin > cout;   // M side = the operand with more channels
+  const void* a_ptr = swap ? x : dy;
+  const void* b_ptr = swap ? dy : x;
+  const int a_ld = swap ? x_ld : dy_ld, b_ld = swap ? dy_ld : x_ld;
+  g.m_total = swap ? cin : cout;
+  g.n_total = swap ? cout : cin;
+  g.sign = swap ? -1 : 1;
+  g.transpose_out = swap ? 1 : 0;
+  g.taps = taps;
+  g.dw = dw;
+  g.dw_ld = dw_ld;
+  g.dw_rows = cout;
+  int twl = ilog2_ceil(W);
+  if (twl > 7) twl = 7;
+  int thl = ilog2_ceil(H);
+  if (thl > 7 - twl) thl = 7 - twl;
+  g.tw_log2 = twl;
+  g.th_log2 = thl;
+  const int TW = 1 << twl, TH = 1 << thl, NIMG = 128 / (TW * TH);
+  g.tiles_x = ceil_div(W, TW);
+  g.tiles_y = ceil_div(H, TH);
+  g.tiles = g.tiles_x * g.tiles_y * ceil_div(B, NIMG);
+  g.m_tiles = ceil_div(g.m_total, 128);
+  const int n_cols_total = (g.n_total + 15) / 16 * 16;
+  g.n_chunks = ceil_div(n_cols_total, 256);
+  g.n_cols = g.n_chunks == 1 ? n_cols_total : 256;
+  g.nbox = ceil_div(g.n_cols, 64);
+  const int max_tpc = 512 / g.n_cols;
+  g.tap_groups = ceil_div(taps, max_tpc);
+  g.tpc = ceil_div(taps, g.tap_groups);
+  int cols = 32;
+  while (cols < g.tpc * g.n_cols) cols <<= 1;
+  g.tmem_cols = cols;
+  const int fixed = 1024 + WT_A_STAGES * 2 * WT_BOX_BYTES + 8 * (2 * WT_A_STAGES + 2 * 16 + 2) + 16;
+  g.b_stages = std::min(16, (WT_SMEM_LIMIT - fixed) / (g.nbox * WT_BOX_BYTES));
+  if (g.b_stages < 2) return 1;
+  const size_t smem = 1024 + (size_t)WT_A_STAGES * 2 * WT_BOX_BYTES + (size_t)g.b_stages * g.nbox * WT_BOX_BYTES +
+                      8 * (2 * WT_A_STAGES + 2 * g.b_stages + 2) + 16;
+
+  CUtensorMap tmA, tmB;
+  int rc = encode_act_map(&tmA, who, "M-side", a_ptr, g.m_total, a_ld, B, H, W, TW, TH, NIMG, 64);
+  if (rc != RFK_OK) return rc;
+  rc = encode_act_map(&tmB, who, "N-side", b_ptr, g.n_total, b_ld, B, H, W, TW, TH, NIMG, 64);
+  if (rc != RFK_OK) return rc;
+
+  const int work = g.m_tiles * g.n_chunks * g.tap_groups;
+  int slices = std::max(1, sm_count() / work);
+  if (slices > g.tiles) slices = g.tiles;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WT_SMEM_LIMIT);
+    if (e != cudaSuccess) {
+      set_error("%s: cudaFuncSetAttribute failed: %s", who, cudaGetErrorString(e));
+      return RFK_ECUDA;
+    }
+    attr_set = true;
+  }
+  RFK_LAUNCH(conv_wgrad_tc_kernel, dim3(slices, work), WT_THREADS, smem, stream, tmA, tmB, g);
+  return check_launch(who);
+}
+
+}  // namespace rfk

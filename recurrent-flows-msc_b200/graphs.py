@@ -74,3 +74,53 @@ class GraphedLogProb(Graphed):
 
     def __call__(self, x, condition, base_condition):
         return super().__call__(x, list(condition), base_condition)
+
+
+class GraphedTrainStep:
+    """One whole training step -- zero_grad, forward with tape, hand-written backward, gradient gather, (allreduce),
+    fused Adam, and the weight repacking the next forward needs -- captured into CUDA graphs and replayed.
+
+    ``loss_fn()`` must compute the loss from STATIC input tensors (copy new batches into them before calling) and
+    return it; ``optimizer`` is a ``FlatAdam``.  With more than one replica the NCCL allreduce runs eagerly between two
+    graphs (forward+backward+gather | Adam), so nothing depends on collective capture support.
+    """
+
+    def __init__(self, loss_fn, optimizer, warmup=3):
+        from .Flow.glow_modules import invalidate_caches
+        self._invalidate = invalidate_caches
+        self.opt = optimizer
+
+        def fwd_bwd():
+            optimizer.zero_grad(set_to_none=True)
+            loss = loss_fn()
+            loss.backward()
+            with torch.no_grad():
+                optimizer.gather_grads()
+            return loss.detach()
+
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(warmup):   # ActNorm init, function attributes, allocator warm-up; real optimizer steps
+                fwd_bwd()
+                optimizer.allreduce_grads()
+                with torch.no_grad():
+                    optimizer.apply()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self.g_fb = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.g_fb):
+            self.loss = fwd_bwd()
+        self.g_opt = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.g_opt), torch.no_grad():
+            optimizer.apply()
+        if optimizer.world == 1:
+            # the capture itself executed nothing: parameters and Adam state are unchanged, step_t too
+            pass
+
+    def __call__(self):
+        self.g_fb.replay()
+        self.opt.allreduce_grads()
+        self.g_opt.replay()
+        self._invalidate()   # eager calls after a replay must not trust caches filled before the last update
+        return self.loss

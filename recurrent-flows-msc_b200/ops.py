@@ -370,14 +370,39 @@ def gauss_logp_bwd(z, z_off, n, params, pairing, std_kind, g, dz):
     return dparams
 
 
+_PERM32 = {}
+
+
+def _perm32(perm):
+    """int32 device copy of a (cached, long) channel permutation, for the packing kernel."""
+    if perm is None:
+        return None
+    key = (perm.data_ptr(), perm.numel(), perm.device)
+    hit = _PERM32.get(key)
+    if hit is None:
+        hit = _PERM32[key] = (perm, perm.to(torch.int32).contiguous())   # keeps `perm` alive: the key is its address
+    return hit[1]
+
+
+def _pack_weight(weight, mode, perm, rows, rows_pad, kp, ktot, cin_real):
+    w = weight.detach()
+    if w.dtype != torch.float32 or not w.is_contiguous():
+        w = w.float().contiguous()
+    N, Cin, kh, kw = w.shape
+    out = torch.empty(rows_pad, ktot, device=w.device, dtype=torch.bfloat16)
+    call("rfk_pack_weight", w.data_ptr(), N, Cin, kh * kw, mode, _p(_perm32(perm)), rows, kp, out.data_ptr(), rows_pad, ktot,
+         _stream())
+    out.rfk_cin = cin_real
+    return out, kp
+
+
 def pack_dgrad_weight(weight, out_perm=None):
     """Weights of the data-gradient conv: dX = conv(dY, Wd) with Wd[ci, co, ky, kx] = W[co, ci, k-1-ky, k-1-kx]; rows
     (the dgrad's output channels = the forward conv's input channels) optionally permuted into staging-buffer order."""
-    w = weight.detach().float()
-    wd = torch.flip(w, dims=(2, 3)).permute(1, 0, 2, 3).contiguous()
-    if out_perm is not None:
-        wd = wd[out_perm]
-    return pack_conv_weight(wd)
+    N, Cin, kh, kw = weight.shape
+    rows = Cin if out_perm is None else out_perm.numel()
+    kp = cin_pad(N)
+    return _pack_weight(weight, 1, out_perm, rows, pad_to(rows, 16), kp, kh * kw * kp, N)
 
 
 # --------------------------------------------------------------------------------------
@@ -400,17 +425,21 @@ def clear_workspaces():
 
 
 # --------------------------------------------------------------------------------------
-# weight repacking (tiny host-driven torch ops on the device, cached by the callers)
+# weight repacking (one kernel launch per weight, cached by the callers until the parameter changes)
 # --------------------------------------------------------------------------------------
 def pack_tap_split_weight(weight):
     """[C, Cin, 3, 3] -> the 1x1 weight [pad16(9C), cin_pad] whose row t*C + c is W[c, :, ky, kx], t = 3*ky+kx."""
     C, Cin, kh, kw = weight.shape
-    w = weight.detach().float().permute(2, 3, 0, 1).reshape(kh * kw * C, Cin, 1, 1)
-    return pack_conv_weight(w)
+    kp = cin_pad(Cin)
+    return _pack_weight(weight, 2, None, kh * kw * C, pad_to(kh * kw * C, 16), kp, kp, Cin)
 
 
 def pack_conv_weight(weight, in_perm=None, row_perm=None, n_pad=None):
     """[N, Cin, kh, kw] f32 -> bf16 [n_pad, taps*cin_pad] with k = tap*cin_pad + c (tap = 3*ky + kx)."""
+    if row_perm is None and n_pad is None and weight.is_cuda and weight.shape[1] > 0:
+        N, Cin, kh, kw = weight.shape
+        kp = cin_pad(Cin)
+        return _pack_weight(weight, 0, in_perm, N, pad_to(N, 16), kp, kh * kw * kp, Cin)
     w = weight.detach().float()
     N, Cin, kh, kw = w.shape
     if in_perm is not None:

@@ -1,0 +1,76 @@
+"""Optimizer step of the training path: Adam over every parameter in ONE kernel launch, plus the data-parallel
+gradient allreduce (one NCCL call on the flat gradient buffer).
+
+The reference trains with ``torch.optim.Adam`` (RFN/trainer.py); for ListGlow's ~750 parameter tensors that is a
+multi-tensor foreach pass.  ``FlatAdam`` re-homes the parameters as views of one flat fp32 buffer, gathers the gradients
+into a second one (one ``torch.cat``), optionally sum-allreduces it over the process group, and runs ``rfk_adam_step``
+(include/rfk.h) on the flat buffers: 28 bytes of HBM traffic per parameter, no per-tensor launches.
+"""
+import torch
+
+from . import ops
+from ._lib import call
+from .Flow.glow_modules import invalidate_caches
+
+
+class FlatAdam:
+    """Adam with torch.optim.Adam's defaults and update rule (no weight decay, no amsgrad).  Build it AFTER moving the
+    model to its device: the parameters become views of ``self.flat_p``."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, process_group=None, world_size=1):
+        self.params = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise ValueError("FlatAdam: no parameters")
+        dev = self.params[0].device
+        if dev.type != "cuda":
+            raise RuntimeError("recurrent-flows-msc_b200: FlatAdam needs CUDA parameters (there is no CPU path)")
+        self.lr, self.betas, self.eps = float(lr), (float(betas[0]), float(betas[1])), float(eps)
+        self.group, self.world = process_group, int(world_size)
+        self.n = sum(p.numel() for p in self.params)
+        self.n_pad = (self.n + 3) // 4 * 4
+        self.flat_p = torch.zeros(self.n_pad, device=dev, dtype=torch.float32)
+        self.flat_g = torch.zeros(self.n_pad, device=dev, dtype=torch.float32)
+        self.exp_avg = torch.zeros(self.n_pad, device=dev, dtype=torch.float32)
+        self.exp_avg_sq = torch.zeros(self.n_pad, device=dev, dtype=torch.float32)
+        self.step_t = torch.zeros(1, device=dev, dtype=torch.float32)
+        off = 0
+        with torch.no_grad():
+            for p in self.params:
+                n = p.numel()
+                view = self.flat_p[off:off + n].view(p.shape)
+                view.copy_(p.detach().float())
+                p.data = view
+                off += n
+        invalidate_caches()
+
+    def zero_grad(self, set_to_none=True):
+        for p in self.params:
+            if set_to_none:
+                p.grad = None
+            elif p.grad is not None:
+                p.grad.zero_()
+
+    def gather_grads(self):
+        """All .grad tensors -> the flat gradient buffer (one concatenation kernel); absent gradients count as zero."""
+        parts = [(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in self.params]
+        torch.cat(parts, out=self.flat_g[:self.n])
+        return self.flat_g
+
+    def allreduce_grads(self):
+        """Sum over the data-parallel replicas (NCCL over NVLink); the mean's 1/world is folded into the Adam kernel."""
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.flat_g, group=self.group)
+
+    def apply(self):
+        self.step_t += 1.0
+        call("rfk_adam_step", self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.exp_avg.data_ptr(),
+             self.exp_avg_sq.data_ptr(), self.n_pad, self.lr, self.betas[0], self.betas[1], self.eps, 1.0 / self.world,
+             self.step_t.data_ptr(), ops._stream())
+        invalidate_caches()   # the kernel wrote the parameters through raw pointers
+
+    @torch.no_grad()
+    def step(self):
+        self.gather_grads()
+        self.allreduce_grads()
+        self.apply()
