@@ -17,35 +17,54 @@ bench.trained_like(flow, 0)
 flow = flow.to(dev)
 x, conds, base, _ = bench.synth_inputs(n, 1, 1)
 x, base, conds = x.to(dev), base.to(dev), [c.to(dev) for c in conds]
-opt = torch.optim.Adam(flow.parameters(), lr=1e-4)
+opt = rf.FlatAdam(flow.parameters(), lr=1e-4)
+
+
+def loss_fn():
+    _, nll = flow.log_prob(x, conds, base)
+    return nll.mean() / (0.6931 * 4096)
 
 
 def step():
-    opt.zero_grad(set_to_none=True)
-    _, nll = flow.log_prob(x, conds, base)
-    loss = nll.mean() / (0.6931 * 4096)
+    opt.zero_grad()
+    loss = loss_fn()
     loss.backward()
     return loss
+
+
+def timed(fn, n=3):
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    a.record()
+    for _ in range(n):
+        out = fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / n, float(out.detach())   # no reference to the autograd graph survives
 
 
 for _ in range(2):
     step()
 torch.cuda.synchronize()
-print("peak memory GB", torch.cuda.max_memory_allocated() / 2**30)
-a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-a.record()
-for _ in range(3):
+print("peak memory GB (eager)", torch.cuda.max_memory_allocated() / 2**30)
+ms, loss = timed(step)
+print(f"eager fwd+bwd {ms:.2f} ms   loss {loss:.4f}")
+
+
+def full():
     loss = step()
-b.record()
-torch.cuda.synchronize()
-print(f"train step (fwd+bwd, no optimizer) {a.elapsed_time(b) / 3:.2f} ms   loss {float(loss.detach()):.4f}")
-a.record()
-for _ in range(3):
-    step()
     opt.step()
-b.record()
-torch.cuda.synchronize()
-print(f"train step + Adam {a.elapsed_time(b) / 3:.2f} ms")
+    return loss
+
+
+ms, loss = timed(full)
+print(f"eager fwd+bwd+FlatAdam (weights repacked every step) {ms:.2f} ms  loss {loss:.4f}")
+print("peak memory GB", torch.cuda.max_memory_allocated() / 2**30)
+if os.environ.get("GRAPH", "1") == "1":
+    g = rf.GraphedTrainStep(loss_fn, opt, warmup=2)
+    ms, loss = timed(g, 5)
+    print(f"graphed train step {ms:.2f} ms -> {n / ms * 1e3:.0f} frames/s   loss {loss:.4f}")
+    print("peak memory GB", torch.cuda.max_memory_allocated() / 2**30)
 t0 = rf._lib.launches
 kt = bench.KernelTimer()
 rf._lib.tracer = kt
