@@ -262,6 +262,14 @@ int rfk_pack_weight(const float* src, int N, int Cin, int taps, int mode, const 
 int rfk_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                   float eps, float grad_scale, const float* step, void* stream);
 
+/* ConvLSTM cell update, backward (Utils/modules.py:369-377): gates recomputed from the saved pre-activations cc
+ * [B,4Hc,H,W] (bias included; order i,f,o,g) and c_prev (nullable = 0); dh [B,Hc,H,W] with batch stride dh_bstride,
+ * dc_in (nullable) = gradient w.r.t. c_next.  Outputs dcc [B,4Hc,H,W], dc_prev [B,Hc,H,W]; dbias [4Hc] (nullable)
+ * accumulates sum_{b,p} dcc (caller-zeroed).  Peepholes (nullable [3,Hc,HW]) are constants, as in the reference. */
+int rfk_convlstm_pointwise_bwd(const float* cc, const float* c_prev, const float* peep, const float* dh,
+                               long long dh_bstride, const float* dc_in, float* dcc, float* dc_prev, float* dbias,
+                               int B, int Hc, int HW, void* stream);
+
 /* Debug aid: when buf != NULL, every conv-GEMM CTA of later launches (grids of at most capacity_ctas CTAs)
  * writes 16 words to buf[16*cta..]: %globaltimer stamps (ns) 0 start, 1 setup done, 2 weights resident, 3 last TMA
  * issued, 4 last MMA issued, 5 first accumulator ready, 6 first epilogue done, 7 all done; SM-cycle totals 8 producer

@@ -11,6 +11,11 @@ import torch.nn as nn
 from .. import ops
 
 
+def _param_epoch():
+    from ..Flow.glow_modules import _PARAM_EPOCH   # bumped by invalidate_caches() (raw-pointer parameter updates)
+    return _PARAM_EPOCH[0]
+
+
 class ActFun(nn.Module):
     """Utils/modules.py:8-19.  Inside the fused networks the activation is a conv epilogue flag;
     called on its own it is a plain elementwise op."""
@@ -89,7 +94,7 @@ class ConvLSTMLayer(nn.Module):
         hc = self.hidden_channels
         ht, ht_pad = _hidden_tiling(hc, m_tiles)
         key = (conv.weight.data_ptr(), conv.weight._version,
-               None if conv.bias is None else (conv.bias.data_ptr(), conv.bias._version), ht)
+               None if conv.bias is None else (conv.bias.data_ptr(), conv.bias._version), ht, _param_epoch())
         if self._packed is None or self._packed[0] != key:
             dev = conv.weight.device
             # tile-interleaved rows: (tile t, gate g, j) <- reference row g*hc + t*ht + j
@@ -116,7 +121,7 @@ class ConvLSTMLayer(nn.Module):
     def _weights_plain(self):
         """Natural row order (i,f,o,g blocks of Hc rows) for the split-K path; cached."""
         conv = self.conv[0]
-        key = (conv.weight.data_ptr(), conv.weight._version)
+        key = (conv.weight.data_ptr(), conv.weight._version, _param_epoch())
         hit = self.__dict__.get("_packed_plain")
         if hit is None or hit[0] != key:
             with torch.no_grad():
@@ -153,8 +158,9 @@ class ConvLSTMLayer(nn.Module):
 
     def forward(self, input_tensor, cur_state):
         if torch.is_grad_enabled():
-            raise RuntimeError("recurrent-flows-msc_b200: backward kernels are not implemented yet; "
-                               "call ConvLSTM under torch.no_grad()")
+            from .training import convlstm_with_grad   # training: saves pre-activations, hand-written BPTT
+            _, h, c = convlstm_with_grad(self, input_tensor.unsqueeze(1), cur_state[0], cur_state[1])
+            return h, c
         x = ops.f32c(input_tensor)
         b, c, h, w = x.shape
         if not self.init_done:
@@ -186,8 +192,8 @@ class ConvLSTM(nn.Module):
 
     def forward(self, x, ht=None, ct=None):
         if torch.is_grad_enabled():
-            raise RuntimeError("recurrent-flows-msc_b200: backward kernels are not implemented yet; "
-                               "call ConvLSTM under torch.no_grad()")
+            from .training import convlstm_with_grad
+            return convlstm_with_grad(self.LSTMlayer, x, ht, ct)
         cell = self.LSTMlayer
         x = ops.f32c(x)
         b, seq_len, channel, h, w = x.size()

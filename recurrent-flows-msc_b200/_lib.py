@@ -62,6 +62,8 @@ SIGNATURES = {
     "rfk_pack_weight": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p],
     "rfk_adam_step": [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_float, c_float, c_float, c_float, c_float,
                       c_void_p, c_void_p],
+    "rfk_convlstm_pointwise_bwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_void_p, c_void_p, c_void_p, c_void_p,
+                                   c_int, c_int, c_int, c_void_p],
     "rfk_add_scalar": [c_void_p, c_void_p, c_float, c_int, c_void_p],
     "rfk_debug_set_timeline": [c_void_p, c_longlong],
 }

@@ -292,25 +292,34 @@ __global__ void __launch_bounds__(256) taps_scatter_kernel(const float* __restri
 }
 
 // 1x1 mix backward, parameter part: dW[o,i] += sum_{b,p} dy[b,o,p]*x[b,i,p],  db[o] += sum dy[b,o,p]
-// (the data part dx = W^T dy is rfk_mix1x1 with the transposed matrix).  CTA = a slice of pixels, staged 64 at a time.
+// (the data part dx = W^T dy is rfk_mix1x1 with the transposed matrix).  A CTA walks a slice of pixels, 128 at a time
+// through shared memory.  Thread t owns output (t mod n_eff) and pixel segment (t / n_eff): with few channels (C = 4:
+// 16 outputs) the 256 threads split each chunk 16 ways instead of idling; with many (C = 64: 4096 outputs) each
+// thread owns 16 outputs over the whole chunk.
+constexpr int MW_CHUNK = 128;
 __global__ void __launch_bounds__(256) mix1x1_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, int C,
                                                            int HW, long long npix, long long pix_per_cta,
                                                            float* __restrict__ dW, float* __restrict__ db) {
   pdl_trigger();
   pdl_wait();
   extern __shared__ float sm[];
-  float* xs = sm;             // [C][64]
-  float* ds = sm + C * 64;    // [C][64]
+  float* xs = sm;                    // [C][MW_CHUNK + 1]
+  float* ds = sm + C * (MW_CHUNK + 1);
+  constexpr int LD = MW_CHUNK + 1;   // odd stride: rows of different channels fall in different banks
   const long long p0 = blockIdx.x * pix_per_cta, p1 = min(npix, p0 + pix_per_cta);
   const int n_out = C * C;
-  constexpr int kMax = 16;    // outputs per thread: C*C <= 4096
+  const int n_eff = n_out < 256 ? n_out : 256;
+  const int nseg = 256 / n_eff;                       // pixel segments per chunk (1 when n_out >= 256)
+  const int seg = threadIdx.x / n_eff, oid = threadIdx.x % n_eff;
+  const bool active = seg < nseg;
+  constexpr int kMax = 16;                            // outputs per thread when n_out > 256 (C*C <= 4096)
   float acc[kMax];
 #pragma unroll
   for (int k = 0; k < kMax; ++k) acc[k] = 0.0f;
   float accb = 0.0f;
-  for (long long pc = p0; pc < p1; pc += 64) {
-    for (int e = threadIdx.x; e < C * 64; e += blockDim.x) {
-      const int c = e >> 6, r = e & 63;
+  for (long long pc = p0; pc < p1; pc += MW_CHUNK) {
+    for (int e = threadIdx.x; e < C * MW_CHUNK; e += blockDim.x) {
+      const int c = e / MW_CHUNK, r = e % MW_CHUNK;
       const long long p = pc + r;
       float xv = 0.0f, dv = 0.0f;
       if (p < p1) {
@@ -319,34 +328,40 @@ __global__ void __launch_bounds__(256) mix1x1_wgrad_kernel(const float* __restri
         xv = x[(b * C + c) * HW + q];
         dv = dy[(b * C + c) * HW + q];
       }
-      xs[e] = xv;
-      ds[e] = dv;
+      xs[c * LD + r] = xv;
+      ds[c * LD + r] = dv;
     }
     __syncthreads();
+    if (active) {
 #pragma unroll
-    for (int k = 0; k < kMax; ++k) {
-      const int idx = threadIdx.x + k * 256;
-      if (idx < n_out) {
-        const int o = idx / C, i = idx - o * C;
-        float s = 0.0f;
-#pragma unroll 8
-        for (int r = 0; r < 64; ++r) s = fmaf(ds[o * 64 + r], xs[i * 64 + r], s);
-        acc[k] += s;
+      for (int k = 0; k < kMax; ++k) {
+        const int idx = oid + k * 256;
+        if (idx < n_out) {
+          const int o = idx / C, i = idx - o * C;
+          float s = 0.0f;
+          for (int r = seg; r < MW_CHUNK; r += nseg) s = fmaf(ds[o * LD + r], xs[i * LD + r], s);
+          acc[k] += s;
+        }
       }
     }
-    if (threadIdx.x < C) {
-      float s = 0.0f;
-      for (int r = 0; r < 64; ++r) s += ds[threadIdx.x * 64 + r];
-      accb += s;
+    {  // bias: thread t -> channel t mod C, pixel lane t / C
+      const int c = threadIdx.x % C, l = threadIdx.x / C, nl = 256 / C;
+      if (l < nl) {
+        float s = 0.0f;
+        for (int r = l; r < MW_CHUNK; r += nl) s += ds[c * LD + r];
+        accb += s;
+      }
     }
     __syncthreads();
   }
+  if (active) {
 #pragma unroll
-  for (int k = 0; k < kMax; ++k) {
-    const int idx = threadIdx.x + k * 256;
-    if (idx < n_out) atomicAdd(dW + idx, acc[k]);
+    for (int k = 0; k < kMax; ++k) {
+      const int idx = oid + k * 256;
+      if (idx < n_out) atomicAdd(dW + idx, acc[k]);
+    }
   }
-  if (threadIdx.x < C) atomicAdd(db + threadIdx.x, accb);
+  if (threadIdx.x / C < 256 / C) atomicAdd(db + threadIdx.x % C, accb);
 }
 
 // Gaussian log-density backward (forward = gauss_logp_kernel): upstream g[b] on logdet[b] += sum log N(z; mean, std(raw)).
@@ -413,13 +428,18 @@ extern "C" int rfk_taps_scatter(const float* dsum, void* dtaps, int ld, int B, i
 extern "C" int rfk_mix1x1_wgrad(const float* x, const float* dy, int B, int C, int HW, float* dW, float* db, void* stream) {
   RFK_REQUIRE(x && dy && dW && db && B > 0 && C > 0 && C <= 64 && HW > 0, "rfk_mix1x1_wgrad: null pointer or bad shape (C <= 64)");
   const long long npix = (long long)B * HW;
-  long long ctas = std::min<long long>((long long)sm_count() * 2, (npix + 255) / 256);
+  long long ctas = std::min<long long>((long long)sm_count() * 4, (npix + MW_CHUNK - 1) / MW_CHUNK);
   if (ctas < 1) ctas = 1;
   long long ppc = (npix + ctas - 1) / ctas;
-  ppc = (ppc + 63) / 64 * 64;
+  ppc = (ppc + MW_CHUNK - 1) / MW_CHUNK * MW_CHUNK;
   ctas = (npix + ppc - 1) / ppc;
-  RFK_LAUNCH(mix1x1_wgrad_kernel, (int)ctas, 256, (size_t)2 * C * 64 * sizeof(float), (cudaStream_t)stream, x, dy, C, HW, npix,
-             ppc, dW, db);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(mix1x1_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 64 * (MW_CHUNK + 1) * 4);
+    attr_set = true;
+  }
+  RFK_LAUNCH(mix1x1_wgrad_kernel, (int)ctas, 256, (size_t)2 * C * (MW_CHUNK + 1) * sizeof(float), (cudaStream_t)stream, x, dy, C,
+             HW, npix, ppc, dW, db);
   return check_launch("rfk_mix1x1_wgrad");
 }
 
@@ -530,4 +550,75 @@ extern "C" int rfk_adam_step(float* p, const float* g, float* m, float* v, long 
   RFK_LAUNCH(adam_kernel, stream_grid(n / 4, 256, 8), 256, 0, (cudaStream_t)stream, (float4*)p, (const float4*)g, (float4*)m,
              (float4*)v, n / 4, lr, beta1, beta2, eps, grad_scale, step);
   return check_launch("rfk_adam_step");
+}
+
+
+// ------------------------------------------------------------------------------------------
+// ConvLSTM cell update, backward (forward = lstm_point in elementwise.cu; Utils/modules.py:369-377).
+//   i = s(ai + wi c_prev), f = s(af + wf c_prev), g = tanh(ag), c = f c_prev + i g, o = s(ao + wo c), h = o tanh(c)
+// Gates are recomputed from the saved pre-activations cc [B,4Hc,H,W] (bias included) and c_prev.  Given dh (gradient
+// w.r.t. h, batch-strided) and dc_in (w.r.t. c, nullable):
+//   dcc [B,4Hc,H,W] (w.r.t. the pre-activations, order i,f,o,g), dc_prev [B,Hc,H,W], dbias[4Hc] += sum_{b,p} dcc.
+// One CTA row (blockIdx.y) per hidden channel, so the bias reduction is a block reduction + 4 atomics.
+// The peephole tensors are constants in the reference (never registered as trainable parameters).
+// ------------------------------------------------------------------------------------------
+namespace rfk {
+__device__ __forceinline__ float sigm(float x) { return 1.0f / (1.0f + __expf(-x)); }
+
+__global__ void __launch_bounds__(256) lstm_pointwise_bwd_kernel(const float* __restrict__ cc, const float* __restrict__ c_prev,
+                                                                 const float* __restrict__ peep, const float* __restrict__ dh,
+                                                                 long long dh_bs, const float* __restrict__ dc_in,
+                                                                 float* __restrict__ dcc, float* __restrict__ dc_prev,
+                                                                 float* __restrict__ dbias, int B, int Hc, int HW) {
+  pdl_trigger();
+  pdl_wait();
+  __shared__ float sh[32];
+  const int ch = blockIdx.y;
+  const long long per = (long long)Hc * HW, n = (long long)B * HW;
+  float acc[4] = {0, 0, 0, 0};
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
+    const long long b = idx / HW;
+    const int p = (int)(idx % HW);
+    const long long r = (long long)ch * HW + p, e = b * per + r;
+    const float* g0 = cc + b * 4 * per + r;
+    const float ai = g0[0], af = g0[per], ao = g0[2 * per], ag = g0[3 * per];
+    const float cp = c_prev ? c_prev[e] : 0.0f;
+    float wi = 0.0f, wf = 0.0f, wo = 0.0f;
+    if (peep) { wi = peep[r]; wf = peep[per + r]; wo = peep[2 * per + r]; }
+    const float i = sigm(ai + wi * cp), f = sigm(af + wf * cp), g = tanhf(ag);
+    const float c = f * cp + i * g;
+    const float o = sigm(ao + wo * c), tc = tanhf(c);
+    const float dhv = dh[b * dh_bs + r];
+    const float dao = dhv * tc * o * (1.0f - o);
+    const float dct = (dc_in ? dc_in[e] : 0.0f) + dhv * o * (1.0f - tc * tc) + dao * wo;
+    const float dai = dct * g * i * (1.0f - i);
+    const float daf = dct * cp * f * (1.0f - f);
+    const float dag = dct * i * (1.0f - g * g);
+    float* d0 = dcc + b * 4 * per + r;
+    d0[0] = dai; d0[per] = daf; d0[2 * per] = dao; d0[3 * per] = dag;
+    dc_prev[e] = dct * f + dai * wi + daf * wf;
+    acc[0] += dai; acc[1] += daf; acc[2] += dao; acc[3] += dag;
+  }
+  if (dbias) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float r = block_sum_256(acc[k], sh);
+      if (threadIdx.x == 0) atomicAdd(dbias + k * Hc + ch, r);
+    }
+  }
+}
+}  // namespace rfk
+
+extern "C" int rfk_convlstm_pointwise_bwd(const float* cc, const float* c_prev, const float* peep, const float* dh,
+                                          long long dh_bstride, const float* dc_in, float* dcc, float* dc_prev, float* dbias,
+                                          int B, int Hc, int HW, void* stream) {
+  using namespace rfk;
+  RFK_REQUIRE(cc && dh && dcc && dc_prev && B > 0 && Hc > 0 && HW > 0 && Hc <= 65535,
+              "rfk_convlstm_pointwise_bwd: null pointer or bad shape");
+  int chunks = ceil_div((long long)B * HW, 256);
+  const int cap = std::max(1, ceil_div((long long)sm_count() * 8, Hc));
+  if (chunks > cap) chunks = cap;
+  RFK_LAUNCH(lstm_pointwise_bwd_kernel, dim3(chunks, Hc), 256, 0, (cudaStream_t)stream, cc, c_prev, peep, dh, dh_bstride, dc_in,
+             dcc, dc_prev, dbias, B, Hc, HW);
+  return check_launch("rfk_convlstm_pointwise_bwd");
 }

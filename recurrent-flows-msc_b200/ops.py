@@ -313,15 +313,32 @@ def act_affine_bwd(dh, h, n, scale, act_fn):
     return da, r[0], r[1]
 
 
-def conv_wgrad(x, cin, dy, cout, taps):
-    """Weight gradient [cout, cin, k, k] (fp32) of a 'same' conv from NHWC bf16 activations x and output gradients dy."""
+def convlstm_pointwise_bwd(cc, c_prev, peep, dh, dc_in, dbias):
+    """Backward of the ConvLSTM cell update: returns (dcc [B,4Hc,H,W], dc_prev [B,Hc,H,W]); dbias [4Hc] accumulates."""
+    _chk(cc, name="cc")
+    B, Hc4, H, W = cc.shape
+    Hc = Hc4 // 4
+    if not dh.is_cuda or dh.dtype != torch.float32 or not dh[0].is_contiguous():
+        raise _lib.RfkError("dh must be a float32 CUDA tensor, dense within each sample")
+    dcc = torch.empty_like(cc)
+    dc_prev = torch.empty(B, Hc, H, W, device=cc.device, dtype=torch.float32)
+    call("rfk_convlstm_pointwise_bwd", cc.data_ptr(), _p(c_prev), _p(peep), dh.data_ptr(), dh.stride(0), _p(dc_in),
+         dcc.data_ptr(), dc_prev.data_ptr(), _p(dbias), B, Hc, H * W, _stream())
+    return dcc, dc_prev
+
+
+def conv_wgrad(x, cin, dy, cout, taps, out=None):
+    """Weight gradient [cout, cin, k, k] (fp32) of a 'same' conv from NHWC bf16 activations x and output gradients dy.
+    ``out`` (fp32 [taps, cout, cin], zeroed by the caller once) accumulates over several calls and is returned as is."""
     _chk(x, torch.bfloat16, "x")
     _chk(dy, torch.bfloat16, "dy")
     B, H, W, xld = x.shape
-    dw = torch.zeros(taps, cout, cin, device=x.device, dtype=torch.float32)
+    dw = out if out is not None else torch.zeros(taps, cout, cin, device=x.device, dtype=torch.float32)
     call("rfk_conv_wgrad", x.data_ptr(), xld, cin, dy.data_ptr(), dy.shape[-1], cout, B, H, W, taps, dw.data_ptr(), cin,
          _stream(), meta={"flops": 2.0 * B * H * W * cout * cin * taps, "flops_padded": 2.0 * B * H * W * cout * cin * taps,
                           "M": B * H * W, "N": cout, "K": taps * cin, "bytes": 2.0 * B * H * W * (cin + cout)})
+    if out is not None:
+        return out
     k = 3 if taps == 9 else 1
     return dw.permute(1, 2, 0).reshape(cout, cin, k, k)
 

@@ -260,3 +260,52 @@ def test_graphed_train_step_matches_eager(rf):
         _, nll = m.log_prob(x, conds, base, logdet=0, noise=noise)
     after = float(nll.mean() / (math.log(2) * 256))
     assert after < g[-1] + 1e-3
+
+
+@pytest.mark.parametrize("B,T,C,H,W,hc,state", [(3, 4, 5, 6, 6, 8, False), (2, 3, 16, 8, 8, 32, True),
+                                                 (4, 2, 512, 2, 2, 200, True), (2, 1, 64, 16, 16, 64, False)])
+def test_convlstm_grads_vs_oracle(rf, B, T, C, H, W, hc, state):
+    """ConvLSTM under autograd (saved pre-activations + hand-written BPTT) vs torch autograd through the oracle, with the
+    oracle's conv operands rounded to bf16 where the CUDA path rounds them."""
+    torch.manual_seed(hc)
+    m = rf.ConvLSTM(C, hc, [3, 3]).train()
+    w, b = m.LSTMlayer.conv[0].weight.detach().clone(), m.LSTMlayer.conv[0].bias.detach().clone()
+    g = torch.Generator().manual_seed(B + T)
+    x = torch.randn(B, T, C, H, W, generator=g)
+    h0 = 0.5 * torch.randn(B, hc, H, W, generator=g) if state else None
+    c0 = 0.5 * torch.randn(B, hc, H, W, generator=g) if state else None
+    g_out = torch.randn(B, T, hc, H, W, generator=g)
+    g_c = torch.randn(B, hc, H, W, generator=g)
+
+    leaves = [t.clone().requires_grad_() for t in (x, w, b)] + ([h0.clone().requires_grad_(), c0.clone().requires_grad_()] if state else [])
+    with bf16_operands():
+        out_r, h_r, c_r = O.convlstm(leaves[0], leaves[1], leaves[2], leaves[3] if state else None, leaves[4] if state else None)
+    ((out_r * g_out).sum() + (c_r * g_c).sum() + h_r.sum()).backward()
+
+    m = m.cuda()
+    xs = x.cuda().requires_grad_()
+    hs = h0.cuda().requires_grad_() if state else None
+    cs = c0.cuda().requires_grad_() if state else None
+    out, h, c = m(xs, hs, cs)
+    assert rel(out.detach(), out_r.detach()) < 1e-2 and rel(c.detach(), c_r.detach()) < 1e-2
+    assert torch.equal(h, out[:, -1])
+    ((out * g_out.cuda()).sum() + (c * g_c.cuda()).sum() + h.sum()).backward()
+    conv = m.LSTMlayer.conv[0]
+    assert rel(xs.grad, leaves[0].grad) < 3e-2
+    assert rel(conv.weight.grad, leaves[1].grad) < 3e-2
+    assert rel(conv.bias.grad, leaves[2].grad) < 3e-2
+    if state:
+        assert rel(hs.grad, leaves[3].grad) < 3e-2 and rel(cs.grad, leaves[4].grad) < 3e-2
+    # the single-step cell interface used by RFN/SRNN (state threaded through autograd between calls)
+    m.zero_grad()
+    xs2 = x.cuda().requires_grad_()
+    hcur, ccur = (h0.cuda(), c0.cuda()) if state else (None, None)
+    for t in range(T):
+        hcur, ccur = m.LSTMlayer(xs2[:, t], [hcur, ccur])
+    (hcur.sum() + (ccur * g_c.cuda()).sum()).backward()
+    leaves2 = [t.clone().requires_grad_() for t in (x, w, b)]
+    with bf16_operands():
+        _, h_r2, c_r2 = O.convlstm(leaves2[0], leaves2[1], leaves2[2], h0, c0)
+    (h_r2.sum() + (c_r2 * g_c).sum()).backward()
+    assert rel(xs2.grad, leaves2[0].grad) < 3e-2
+    assert rel(conv.weight.grad, leaves2[1].grad) < 3e-2
