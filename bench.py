@@ -362,11 +362,17 @@ def run_ours(args):
     training = None
     if not args.no_train:
         import copy
-        tflow = copy.deepcopy(flow).train()
-        opt = rf.FlatAdam(tflow.parameters(), lr=1e-4, world_size=world)
-        tx, tconds, tbase = resident[0], resident[1], resident[2]
+        tflow, tlstm = copy.deepcopy(flow).train(), copy.deepcopy(lstm).train()
+        opt = rf.FlatAdam(list(tflow.parameters()) + list(tlstm.parameters()), lr=1e-4, world_size=world)
+        tx, tconds, tfeats = resident[0], resident[1], resident[3]
+        hcn = J["lstm_hidden"]
+        z_part = resident[2][:, hcn:].contiguous()   # the latent-sample part of RFN's base condition cat[h_t, z_t]
 
         def loss_fn():
+            # as in RFN.loss: the recurrence's hidden states condition the flow's prior, so the flow's gradient w.r.t. its
+            # base condition is back-propagated through all 19 ConvLSTM steps
+            hs, _, _ = tlstm(tfeats)
+            tbase = torch.cat([hs.reshape(n_frames, hcn, 2, 2), z_part], 1)
             _, nll = tflow.log_prob(tx, tconds, tbase)
             return nll.mean() / (math.log(2.0) * 64 * 64)
 
@@ -391,17 +397,18 @@ def run_ours(args):
         ms_train = time_loop(train_step, n_train)
         last_loss = float(train_step())
         assert math.isfinite(last_loss), "non-finite training loss"
-        training = {"what": "ListGlow decoder training step on 570 frames per GPU: log_prob forward recording a tape, backward on "
-                            "hand-written kernels (tcgen05 wgrad/dgrad, fused elementwise), one NCCL sum-allreduce of the flat "
-                            "gradient, Adam for all parameters in one launch, bf16 weight repacking; inputs resident in HBM; "
-                            "ConvLSTM backward not included (not written yet)",
+        training = {"what": "hot-path training step on 570 frames per GPU: 19 ConvLSTM steps whose hidden states form the flow's "
+                            "base condition, ListGlow.log_prob forward recording a tape, backward on hand-written kernels "
+                            "(coupling / ActNorm / Split2d / prior backward, tcgen05 wgrad + dgrad, BPTT through the ConvLSTM), "
+                            "one NCCL sum-allreduce of the flat gradient, Adam for all parameters in one launch, bf16 weight "
+                            "repacking; inputs resident in HBM",
                     "frames_per_s": world * n_frames / (ms_train / 1e3), "ms_per_step": ms_train, "steps": n_train,
                     "launch": "eager" if args.no_graph else "two CUDA graphs (fwd+bwd+gather | Adam) around the eager allreduce",
                     "own_kernel_launches_per_step": train_launches, "parameters": opt.n,
                     "allreduce_bytes_per_step": opt.n_pad * 4 if world > 1 else 0,
                     "bits_per_dim_first_step": first_loss, "bits_per_dim_last_step": last_loss,
                     "peak_memory_gb": torch.cuda.max_memory_allocated() / 2 ** 30}
-        del train_step, opt, tflow
+        del train_step, opt, tflow, tlstm
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(ms_e2e, op=dist.ReduceOp.MAX)
