@@ -34,18 +34,23 @@ class _State:
         self.dcond = [None] * n_levels
         self.dbase = None
         self.grads = {}
+        self.folds = []
 
     def add(self, param, g):
+        """g: a tensor this sweep owns (a fresh kernel output or a view of one) -- stored, not copied."""
         g = g.reshape(param.shape)
         hit = self.grads.get(id(param))
-        self.grads[id(param)] = g.clone() if hit is None else hit.add_(g)
+        self.grads[id(param)] = g if hit is None else hit.add_(g)
 
     def add_cond(self, l, g):
-        self.dcond[l] = g.clone() if self.dcond[l] is None else self.dcond[l].add_(g)
+        self.dcond[l] = g if self.dcond[l] is None else self.dcond[l].add_(g)
 
 
 def _nhwc(B, H, W, c, dev):
-    return torch.zeros(B, H, W, ops.cin_pad(c), device=dev, dtype=torch.bfloat16)
+    """NHWC bf16 staging buffer for c channels.  Pad columns must be finite zeros (they meet zero weights in the GEMMs);
+    a buffer without pad columns is fully written by its producer and needs no fill (a 300 MB memset at level 1)."""
+    ld = ops.cin_pad(c)
+    return (torch.empty if ld == c else torch.zeros)(B, H, W, ld, device=dev, dtype=torch.bfloat16)
 
 
 def _check_actnorm(mod):
@@ -152,33 +157,48 @@ def _glowstep_bwd(st, step, x, zo, nn_in, h1, h2, taps, cc, l):
     Wf = step._folded_fwd()[0]
     dWf, dbf = ops.mix1x1_wgrad(x, dz)
     st.dz = ops.mix1x1(dz, Wf.t().contiguous(), None)
-    _fold_bwd(st, step, dWf, dbf, H * W)
+    st.folds.append((step, dWf, dbf, H * W))   # chained to the parameters in batches at the end of the sweep
 
 
-def _fold_bwd(st, step, dWf, dbf, hw):
-    """Chain (d Wf, d bf, d logdet) back to ActNorm's (bias, logs) and InvConv's parameters (Flow/glow_modules.py:
-    33-54, 167-205) -- C x C tensors, differentiated by torch autograd."""
-    inv = step.invconv
-    params = [step.norm.bias, step.norm.logs, *inv._params()]
-    with torch.enable_grad():
-        leaf = [p.detach().float().requires_grad_() for p in params]
-        bias, logs = leaf[0].reshape(-1), leaf[1].reshape(-1)
-        if inv.LU_decomposed:
-            l_mask, eye = inv._consts(leaf[2].device)
-            lower = leaf[2] * l_mask + eye
-            u = leaf[3] * l_mask.transpose(0, 1) + torch.diag(inv.sign_s * torch.exp(leaf[4]))
-            Wm = torch.matmul(inv.p, torch.matmul(lower, u))
-            ldw = torch.sum(leaf[4])
-        else:
-            Wm = leaf[2]
-            ldw = torch.linalg.slogdet(Wm)[1]
-        s = torch.exp(logs)
-        Wf = Wm * s[None, :]
-        bfv = torch.mv(Wf, bias)
-        dl = (ldw + logs.sum()) * hw
-        gs = torch.autograd.grad([Wf, bfv, dl], leaf, [dWf, dbf, st.G])
-    for p, g in zip(params, gs):
-        st.add(p, g)
+def _fold_bwd_all(st):
+    """Chain (d Wf, d bf, d logdet) of every GlowStep back to ActNorm's (bias, logs) and InvConv's parameters
+    (Flow/glow_modules.py:33-54, 167-205).  These are C x C tensors, differentiated by torch autograd; steps with the
+    same channel count and parameterisation (one flow level) are stacked and go through ONE batched autograd call,
+    otherwise the ~50 tiny launches per step would cost more GPU time than the level-1 convolutions."""
+    groups = {}
+    for item in st.folds:
+        step = item[0]
+        groups.setdefault((step.invconv.w_shape[0], step.invconv.LU_decomposed, item[3]), []).append(item)
+    st.folds = []
+    for (C, lu, hw), items in groups.items():
+        steps = [it[0] for it in items]
+        inv0 = steps[0].invconv
+        names = ("lower", "upper", "log_s") if lu else ("weight",)
+        plist = [[s.norm.bias for s in steps], [s.norm.logs for s in steps]] + [[getattr(s.invconv, n) for s in steps] for n in names]
+        with torch.enable_grad():
+            leaf = [torch.stack([p.detach().float().reshape(p.shape if p.dim() <= 2 else (-1,)) for p in ps]).requires_grad_()
+                    for ps in plist]
+            bias, logs = leaf[0], leaf[1]                      # [K, C]
+            if lu:
+                l_mask, eye = inv0._consts(leaf[2].device)
+                sign_s = torch.stack([s.invconv.sign_s for s in steps])
+                perm = torch.stack([s.invconv.p for s in steps])
+                lower = leaf[2] * l_mask + eye
+                u = leaf[3] * l_mask.transpose(0, 1) + torch.diag_embed(sign_s * torch.exp(leaf[4]))
+                Wm = torch.matmul(perm, torch.matmul(lower, u))
+                ldw = leaf[4].sum(dim=1)
+            else:
+                Wm = leaf[2]
+                ldw = torch.linalg.slogdet(Wm)[1]
+            Wf = Wm * torch.exp(logs)[:, None, :]
+            bfv = torch.matmul(Wf, bias[:, :, None])[:, :, 0]
+            dl = (ldw + logs.sum(dim=1)) * hw
+            dWf = torch.stack([it[1] for it in items])
+            dbf = torch.stack([it[2] for it in items])
+            gs = torch.autograd.grad([Wf, bfv, dl], leaf, [dWf, dbf, st.G.expand(len(items))])
+        for ps, g in zip(plist, gs):
+            for k, p in enumerate(ps):
+                st.add(p, g[k])
 
 
 # ----------------------------------------------------------------------------------------
@@ -321,6 +341,7 @@ class _LogProb(torch.autograd.Function):
         tape, ctx.tape = ctx.tape, None
         while tape:
             tape.pop()(st)
+        _fold_bwd_all(st)
         dconds = [st.dcond[i] for i in range(ctx.n_cond)]
         pgrads = [st.grads.get(id(p)) for p in ctx.params]
         pgrads = [None if g is None else g.to(p.dtype) for g, p in zip(pgrads, ctx.params)]

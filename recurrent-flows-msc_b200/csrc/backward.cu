@@ -204,8 +204,8 @@ __device__ __forceinline__ float block_sum_256(float v, float* sh) {
 }
 
 __global__ void __launch_bounds__(256) coupling_taps_bwd_kernel(const float* __restrict__ taps, const float* __restrict__ z_out,
-                                                                float* __restrict__ dz, float* __restrict__ dsum, int C, int H,
-                                                                int W, const float* __restrict__ scale,
+                                                                float* __restrict__ dz, float* __restrict__ dsum, int B, int C,
+                                                                int H, int W, const float* __restrict__ scale,
                                                                 const float* __restrict__ shift, int clamp_type,
                                                                 const float* __restrict__ cs, const float* __restrict__ csh,
                                                                 const float* __restrict__ g_ld, float* __restrict__ d_scale,
@@ -214,17 +214,20 @@ __global__ void __launch_bounds__(256) coupling_taps_bwd_kernel(const float* __r
   pdl_trigger();
   pdl_wait();
   __shared__ float sh[32];
-  const int b = blockIdx.y, j = blockIdx.z, half = C >> 1, HW = H * W;
-  const float* tb = taps + (long long)b * 9 * C * HW;
-  const float* zo = z_out + ((long long)b * C + half + j) * HW;
-  float* dzp = dz + ((long long)b * C + half + j) * HW;
-  float* dsp = dsum + ((long long)b * C + 2 * j) * HW;
-  const float sc_s = scale[2 * j], sh_s = shift[2 * j], sc_r = scale[2 * j + 1], sh_r = shift[2 * j + 1];
+  const int j = blockIdx.y, half = C >> 1, HW = H * W;
+  const float sc_s = scale[2 * j], sc_r = scale[2 * j + 1], sh_r = shift[2 * j + 1];
   float a = 0.0f, bb = 0.0f;
   if (clamp_type == RFK_CLAMP_REALNVP) { a = cs[j]; bb = csh[j]; }
-  const float gl = g_ld ? g_ld[b] : 0.0f;
   float acc[6] = {0, 0, 0, 0, 0, 0};   // d sc_s, d sh_s, d sc_r, d sh_r, d a, d b
-  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += gridDim.x * blockDim.x) {
+  const long long n = (long long)B * HW;
+  // threads run over (sample, pixel) jointly: deep levels have only a few pixels per sample
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(idx / HW), p = (int)(idx % HW);
+    const float* tb = taps + (long long)b * 9 * C * HW;
+    const float* zo = z_out + ((long long)b * C + half + j) * HW;
+    float* dzp = dz + ((long long)b * C + half + j) * HW;
+    float* dsp = dsum + ((long long)b * C + 2 * j) * HW;
+    const float gl = g_ld ? g_ld[b] : 0.0f;
     const int y = p / W, x = p - y * W;
     float S = 0.0f, R = 0.0f;
 #pragma unroll
@@ -410,9 +413,10 @@ extern "C" int rfk_coupling_taps_bwd(const float* taps, const float* z_out, floa
   RFK_REQUIRE(clamp_type != RFK_CLAMP_REALNVP || (clamp_scale && clamp_shift && d_clamp_scale && d_clamp_shift),
               "rfk_coupling_taps_bwd: realnvp clamp needs scale/scale_shift and their gradient buffers");
   RFK_REQUIRE(B <= 65535 && C / 2 <= 65535, "rfk_coupling_taps_bwd: B or C too large for the grid");
-  int chunks = ceil_div((long long)H * W, 256);
-  if (chunks > 64) chunks = 64;
-  RFK_LAUNCH(coupling_taps_bwd_kernel, dim3(chunks, B, C / 2), 256, 0, (cudaStream_t)stream, taps, z_out, dz, dsum, C, H, W,
+  int chunks = ceil_div((long long)B * H * W, 256);
+  const int cap = std::max(1, ceil_div((long long)sm_count() * 8, C / 2));
+  if (chunks > cap) chunks = cap;
+  RFK_LAUNCH(coupling_taps_bwd_kernel, dim3(chunks, C / 2), 256, 0, (cudaStream_t)stream, taps, z_out, dz, dsum, B, C, H, W,
              scale, shift, clamp_type, clamp_scale, clamp_shift, g_ld, d_scale, d_shift, d_clamp_scale, d_clamp_shift);
   return check_launch("rfk_coupling_taps_bwd");
 }

@@ -306,7 +306,7 @@ def act_affine_bwd(dh, h, n, scale, act_fn):
     _chk(dh, torch.bfloat16, "dh")
     _chk(h, torch.bfloat16, "h")
     rows = dh.numel() // dh.shape[-1]
-    da = torch.zeros_like(dh)
+    da = torch.empty_like(dh) if (n + 7) // 8 * 8 == dh.shape[-1] else torch.zeros_like(dh)   # the kernel writes 8-channel groups
     r = torch.zeros(2, n, device=dh.device, dtype=torch.float32)
     call("rfk_act_affine_bwd", dh.data_ptr(), h.data_ptr(), dh.shape[-1], n, _chk(scale).data_ptr(), ACT[act_fn],
          da.data_ptr(), da.shape[-1], r[0].data_ptr(), r[1].data_ptr(), rows, _stream())

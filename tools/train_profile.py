@@ -57,6 +57,14 @@ def full():
     return loss
 
 
+if os.environ.get("NCU") == "1":   # ncu --profile-from-start off: exactly one eager training step (incl. repack + Adam)
+    full()
+    torch.cuda.synchronize()
+    torch.cuda.profiler.start()
+    full()
+    torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
+    sys.exit(0)
 ms, loss = timed(full)
 print(f"eager fwd+bwd+FlatAdam (weights repacked every step) {ms:.2f} ms  loss {loss:.4f}")
 print("peak memory GB", torch.cuda.max_memory_allocated() / 2**30)
