@@ -222,20 +222,25 @@ int rfk_convlstm_pointwise(const float* cc, const float* c_prev, const float* pe
  * rfk_act_affine_bwd: backward of h = act(a*scale + shift) (Conv2dNorm + ActFun, Flow/glow_modules.py:139-147) from the
  *   saved output h and the upstream gradient dh (both NHWC bf16, `rows` pixels, n channels, row stride ld):
  *   da = dh*act'(h)*scale (bf16, row stride da_ld);  r_dv[c] += sum dh*act'(h)  (d bias = scale*r_dv);
- *   r_dvv[c] += sum dh*act'(h)*v = sum dh*h  (d logs).  r_dv / r_dvv are caller-zeroed fp32 [n].
+ *   r_dvv[c] += dvv_factor * sum dh*act'(h)*v = dvv_factor * sum dh*h  (d logs; factor 3 for Conv2dZeros' exp(3*logs)).
+ *   dv_scaled != 0 multiplies the r_dv sums by scale[c], which makes them d bias directly.  r_dv / r_dvv: caller-zeroed fp32 [n].
  * rfk_conv_wgrad: dw[tap][n][c] += sum_p dy[p, n] * x[p + off(tap), c]  (x, dy NHWC bf16; zero outside the image;
- *   dw fp32 [taps, cout, dw_ld], caller-zeroed; tap = 3*ky + kx).  Tensor cores through mma.sync (WMMA). */
+ *   dw fp32, caller-zeroed, accumulated with atomics; tap = 3*ky + kx).  layout 0: dw[taps][cout][dw_ld]; layout 1: the conv
+ *   weight's own layout dw[cout][dw_ld][taps] with input channel c stored at perm[c] (perm nullable; staging order ->
+ *   weight order).  tcgen05 kernel with MN-major operands (csrc/wgrad_tc.cu); RFK_WGRAD_WMMA=1 selects the mma.sync one. */
 int rfk_act_affine_bwd(const void* dh, const void* h, int ld, int n, const float* scale, int act_fn,
-                       void* da, int da_ld, float* r_dv, float* r_dvv, long long rows, void* stream);
+                       void* da, int da_ld, float* r_dv, float* r_dvv, float dvv_factor, int dv_scaled, long long rows,
+                       void* stream);
 int rfk_conv_wgrad(const void* x, int x_ld, int cin, const void* dy, int dy_ld, int cout, int B, int H, int W, int taps,
-                   float* dw, int dw_ld, void* stream);
+                   float* dw, int dw_ld, int layout, const int* perm, void* stream);
 
 /* Affine-coupling tail backward, tap-split form (backward of rfk_coupling_tail_taps; Flow/glow_modules.py:237-273).
  *   dz [B,C,H,W] holds the gradient w.r.t. the coupling output; its z2 half (channels C/2..C) is overwritten with the
  *   gradient w.r.t. z2.  z_out = the coupling output, taps = the nine tap planes [B,9C,H,W], g_ld (nullable) [B] = gradient
  *   w.r.t. logdet.  dsum [B,C,H,W] receives the gradient w.r.t. the Conv2dZeros pre-affine sums (channel 2j: shift part,
  *   2j+1: log-scale part).  d_scale/d_shift [C] (Conv2dZeros exp(3*logs) and bias*exp(3*logs) affine) and, for the realnvp
- *   clamp, d_clamp_scale/d_clamp_shift [C/2] are caller-zeroed fp32 accumulators.
+ *   clamp, d_clamp_scale/d_clamp_shift [C/2] are caller-zeroed fp32 accumulators.  logs_factor != 0 (3 for Conv2dZeros)
+ *   converts on the fly: d_scale receives d logs = f*(d scale*scale + d shift*shift), d_shift receives d bias = d shift*scale.
  * rfk_taps_scatter: dtaps[p, t*C + c] = dsum[c](p - off(t)) as NHWC bf16 (row stride ld >= 9C; pad columns untouched).
  * rfk_mix1x1_wgrad: dW[o,i] += sum dy[b,o,p]*x[b,i,p], db[o] += sum dy[b,o,p] (fp32 NCHW, C <= 64, caller-zeroed).
  * rfk_gauss_logp_bwd: backward of rfk_gauss_logp with upstream g[b]: dz[:, z_off:z_off+n] += ..., dparams (nullable with
@@ -243,7 +248,7 @@ int rfk_conv_wgrad(const void* x, int x_ld, int cin, const void* dy, int dy_ld, 
 int rfk_coupling_taps_bwd(const float* taps, const float* z_out, float* dz, float* dsum, int B, int C, int H, int W,
                           const float* scale, const float* shift, int clamp_type, const float* clamp_scale,
                           const float* clamp_shift, const float* g_ld, float* d_scale, float* d_shift,
-                          float* d_clamp_scale, float* d_clamp_shift, void* stream);
+                          float* d_clamp_scale, float* d_clamp_shift, float logs_factor, void* stream);
 int rfk_taps_scatter(const float* dsum, void* dtaps, int ld, int B, int C, int H, int W, void* stream);
 int rfk_mix1x1_wgrad(const float* x, const float* dy, int B, int C, int HW, float* dW, float* db, void* stream);
 int rfk_gauss_logp_bwd(const float* z, int z_C, int z_off, const float* params, int n, int B, int HW, int pairing,

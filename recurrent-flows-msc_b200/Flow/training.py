@@ -62,12 +62,7 @@ def _conv_bwd(st, mod, x_act, cin, da, perm=None, dgrad_out=None, key="id"):
     """Backward of mod.conv given da (bf16 NHWC gradient of the raw convolution output): weight gradient into the
     state, data gradient into dgrad_out (bf16 NHWC or fp32 NCHW; channels in the staging order of x_act)."""
     n = mod.conv.out_channels
-    dw = ops.conv_wgrad(x_act, cin, da, n, mod.taps)
-    if perm is not None:   # staging order -> the weight's own input-channel order
-        full = torch.empty_like(dw)
-        full[:, perm] = dw
-        dw = full
-    st.add(mod.conv.weight, dw)
+    st.add(mod.conv.weight, ops.conv_wgrad(x_act, cin, da, n, mod.taps, perm=perm))   # staging order -> weight order
     if dgrad_out is not None:
         wd, cp = mod.packed_dgrad(key, perm)
         ops.conv_gemm(da, cp, wd, cin, mod.taps, None, None, "none", dgrad_out)
@@ -79,9 +74,9 @@ def _norm_act_bwd(st, mod, dh, h, act_fn):
     assert dh.shape[-1] == h.shape[-1]
     n = mod.conv.out_channels
     scale, _ = mod.norm_type.affine()
-    da, r_dv, r_dvv = ops.act_affine_bwd(dh, h, n, scale, act_fn)
-    st.add(mod.norm_type.logs, r_dvv)
-    st.add(mod.norm_type.bias, scale * r_dv)
+    da, dbias, dlogs = ops.act_affine_bwd(dh, h, n, scale, act_fn, 1.0, True)
+    st.add(mod.norm_type.logs, dlogs)
+    st.add(mod.norm_type.bias, dbias)
     return da
 
 
@@ -92,9 +87,9 @@ def _zeros_out_bwd(st, mod, dout, out):
     ops.pack_nhwc(dout, 0, n, dh, 0)
     ops.pack_nhwc(out, 0, n, h, 0)
     scale, _ = mod.affine()
-    da, r_dv, r_dvv = ops.act_affine_bwd(dh, h, n, scale, "none")
-    st.add(mod.logs, mod.logscale_factor * r_dvv)
-    st.add(mod.conv.bias, scale * r_dv)
+    da, dbias, dlogs = ops.act_affine_bwd(dh, h, n, scale, "none", float(mod.logscale_factor), True)
+    st.add(mod.logs, dlogs)
+    st.add(mod.conv.bias, dbias)
     return da
 
 
@@ -132,10 +127,11 @@ def _glowstep_bwd(st, step, x, zo, nn_in, h1, h2, taps, cc, l):
     half, hid, act, dev = C // 2, aff.hidden_units, aff.non_lin, zo.device
     dz = st.dz
     scale, shift, clamp, cs, csh = aff.tail_params()
-    dsum, d_sc, d_sh, d_cs, d_csh = ops.coupling_taps_bwd(taps, zo, dz, scale, shift, clamp, cs, csh, st.g_ld)
     last = net[4]
-    st.add(last.logs, last.logscale_factor * (d_sc * scale + d_sh * shift))
-    st.add(last.conv.bias, d_sh * scale)
+    dsum, d_logs, d_bias, d_cs, d_csh = ops.coupling_taps_bwd(taps, zo, dz, scale, shift, clamp, cs, csh, st.g_ld,
+                                                             float(last.logscale_factor))
+    st.add(last.logs, d_logs)
+    st.add(last.conv.bias, d_bias)
     if clamp == "realnvp":
         st.add(aff.scale, d_cs)
         st.add(aff.scale_shift, d_csh)
@@ -339,9 +335,10 @@ class _LogProb(torch.autograd.Function):
         g_ld = (-ops.f32c(dnll)).contiguous()
         st = _State(dz, g_ld, ctx.n_cond)
         tape, ctx.tape = ctx.tape, None
-        while tape:
-            tape.pop()(st)
-        _fold_bwd_all(st)
+        with ops.zero_arena(dz.device):
+            while tape:
+                tape.pop()(st)
+            _fold_bwd_all(st)
         dconds = [st.dcond[i] for i in range(ctx.n_cond)]
         pgrads = [st.grads.get(id(p)) for p in ctx.params]
         pgrads = [None if g is None else g.to(p.dtype) for g, p in zip(pgrads, ctx.params)]

@@ -67,7 +67,8 @@ class _ConvLSTMFn(torch.autograd.Function):
         cin = C + hc
         d_out = ops.f32c(d_out)
         dc = None if d_c is None else ops.f32c(d_c)
-        dw = torch.zeros(cell.taps, 4 * hc, cin, device=dev, dtype=torch.float32)
+        k = 3 if cell.taps == 9 else 1
+        dw = torch.zeros(4 * hc, cin, k, k, device=dev, dtype=torch.float32)
         dbias = torch.zeros(4 * hc, device=dev, dtype=torch.float32) if ctx.has_bias else None
         cache = cell.__dict__.setdefault("_wd_cache", [None, None])   # data-gradient weights, rebuilt when the weight changes
         key = (conv.weight.data_ptr(), conv.weight._version, _epoch())
@@ -89,8 +90,7 @@ class _ConvLSTMFn(torch.autograd.Function):
             ops.conv_gemm(da, cp, wd, cin, cell.taps, None, None, "none", din)
             dx[:, t].copy_(din[:, :C])
             dh_future = din[:, C:]
-        k = 3 if cell.taps == 9 else 1
-        dweight = dw.permute(1, 2, 0).reshape(4 * hc, cin, k, k)
+        dweight = dw
         d_h0 = dh_future.contiguous() if ctx.has_state else None
         d_c0 = dc if ctx.has_state else None
         return None, dx, d_h0, d_c0, dweight, dbias

@@ -17,7 +17,7 @@
 namespace rfk {
 
 int conv_wgrad_tc(const void* x, int x_ld, int cin, const void* dy, int dy_ld, int cout, int B, int H, int W, int taps,
-                  float* dw, int dw_ld, cudaStream_t stream);   // wgrad_tc.cu
+                  float* dw, int dw_ld, int layout, const int* perm, cudaStream_t stream);   // wgrad_tc.cu
 
 // ------------------------------------------------------------------------------------------
 // h = act(v), v = a*scale + shift (a = raw conv output, scale = e^{logs}, shift = bias*e^{logs}).
@@ -31,7 +31,8 @@ __global__ void __launch_bounds__(256) act_affine_bwd_kernel(const __nv_bfloat16
                                                              const float* __restrict__ scale, int act_fn,
                                                              __nv_bfloat16* __restrict__ da, int da_ld,
                                                              float* __restrict__ r_dv, float* __restrict__ r_dvv,
-                                                             long long rows, long long rows_per_cta) {
+                                                             float dvv_factor, int dv_scaled, long long rows,
+                                                             long long rows_per_cta) {
   pdl_trigger();
   pdl_wait();
   const int groups = (n + 7) >> 3;              // channel groups of 8
@@ -89,9 +90,9 @@ __global__ void __launch_bounds__(256) act_affine_bwd_kernel(const __nv_bfloat16
       t0 += a0[(rr * lanes_per_row + gg) * 8 + k];
       t1 += a1[(rr * lanes_per_row + gg) * 8 + k];
     }
-    if (c < n) {
-      atomicAdd(r_dv + c, t0);
-      atomicAdd(r_dvv + c, t1);
+    if (c < n) {   // both transforms are linear, so every CTA may apply them to its partial sums
+      atomicAdd(r_dv + c, dv_scaled ? t0 * scale[c] : t0);
+      atomicAdd(r_dvv + c, t1 * dvv_factor);
     }
   }
 }
@@ -113,7 +114,8 @@ constexpr int WG_N = 64, WG_C = 64, WG_P = 64, WG_LD = 72;   // padded leading d
 __global__ void __launch_bounds__(256) conv_wgrad_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, int cin,
                                                          const __nv_bfloat16* __restrict__ dy, int dy_ld, int cout,
                                                          int B, int H, int W, int taps, float* __restrict__ dw,
-                                                         int dw_ld, long long pix_per_slice) {
+                                                         int dw_ld, int layout, const int* __restrict__ perm,
+                                                         long long pix_per_slice) {
   using namespace nvcuda;
   pdl_trigger();
   pdl_wait();
@@ -171,7 +173,9 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(const __nv_bfloat16* __
     for (int e = lane; e < 256; e += 32) {
       const int rn = e >> 4, rc = e & 15;
       const int n = n0 + nb * 16 + rn, c = c0 + (cb + j) * 16 + rc;
-      if (n < cout && c < cin) atomicAdd(dw + ((long long)tap * cout + n) * dw_ld + c, so[warp][e]);
+      if (n < cout && c < cin)
+        atomicAdd(dw + (layout ? ((long long)n * dw_ld + (perm ? perm[c] : c)) * taps + tap
+                               : ((long long)tap * cout + n) * dw_ld + c), so[warp][e]);
     }
     __syncwarp();
   }
@@ -210,7 +214,7 @@ __global__ void __launch_bounds__(256) coupling_taps_bwd_kernel(const float* __r
                                                                 const float* __restrict__ cs, const float* __restrict__ csh,
                                                                 const float* __restrict__ g_ld, float* __restrict__ d_scale,
                                                                 float* __restrict__ d_shift, float* __restrict__ d_cs,
-                                                                float* __restrict__ d_csh) {
+                                                                float* __restrict__ d_csh, float logs_factor) {
   pdl_trigger();
   pdl_wait();
   __shared__ float sh[32];
@@ -261,15 +265,27 @@ __global__ void __launch_bounds__(256) coupling_taps_bwd_kernel(const float* __r
     dsp[HW + p] = draw * sc_r;   // gradient w.r.t. R
     acc[0] += dt * S; acc[1] += dt; acc[2] += draw * R; acc[3] += draw; acc[4] += dls * th; acc[5] += dls;
   }
+  float red[6];
 #pragma unroll
-  for (int k = 0; k < 6; ++k) {
-    const float r = block_sum_256(acc[k], sh);
-    if (threadIdx.x == 0) {
-      if (k == 0) atomicAdd(d_scale + 2 * j, r);
-      else if (k == 1) atomicAdd(d_shift + 2 * j, r);
-      else if (k == 2) atomicAdd(d_scale + 2 * j + 1, r);
-      else if (k == 3) atomicAdd(d_shift + 2 * j + 1, r);
-      else if (clamp_type == RFK_CLAMP_REALNVP) atomicAdd((k == 4 ? d_cs : d_csh) + j, r);
+  for (int k = 0; k < 6; ++k) red[k] = block_sum_256(acc[k], sh);
+  if (threadIdx.x == 0) {
+    if (logs_factor != 0.0f) {
+      // parameter form (linear in the partial sums): out = (conv + bias) * exp(f*logs) -> d logs = f*(d_sc*scale + d_sh*shift),
+      // d bias = d_sh*scale; written to d_scale (d logs) and d_shift (d bias)
+      const float sh_s = shift[2 * j];
+      atomicAdd(d_scale + 2 * j, logs_factor * (red[0] * sc_s + red[1] * sh_s));
+      atomicAdd(d_shift + 2 * j, red[1] * sc_s);
+      atomicAdd(d_scale + 2 * j + 1, logs_factor * (red[2] * sc_r + red[3] * sh_r));
+      atomicAdd(d_shift + 2 * j + 1, red[3] * sc_r);
+    } else {
+      atomicAdd(d_scale + 2 * j, red[0]);
+      atomicAdd(d_shift + 2 * j, red[1]);
+      atomicAdd(d_scale + 2 * j + 1, red[2]);
+      atomicAdd(d_shift + 2 * j + 1, red[3]);
+    }
+    if (clamp_type == RFK_CLAMP_REALNVP) {
+      atomicAdd(d_cs + j, red[4]);
+      atomicAdd(d_csh + j, red[5]);
     }
   }
 }
@@ -406,7 +422,7 @@ using namespace rfk;
 extern "C" int rfk_coupling_taps_bwd(const float* taps, const float* z_out, float* dz, float* dsum, int B, int C, int H,
                                      int W, const float* scale, const float* shift, int clamp_type, const float* clamp_scale,
                                      const float* clamp_shift, const float* g_ld, float* d_scale, float* d_shift,
-                                     float* d_clamp_scale, float* d_clamp_shift, void* stream) {
+                                     float* d_clamp_scale, float* d_clamp_shift, float logs_factor, void* stream) {
   RFK_REQUIRE(taps && z_out && dz && dsum && scale && shift && d_scale && d_shift && B > 0 && C > 0 && C % 2 == 0 && H > 0 && W > 0,
               "rfk_coupling_taps_bwd: null pointer or bad shape");
   RFK_REQUIRE(clamp_type >= 0 && clamp_type <= 3, "rfk_coupling_taps_bwd: unknown clamp_type %d", clamp_type);
@@ -417,7 +433,7 @@ extern "C" int rfk_coupling_taps_bwd(const float* taps, const float* z_out, floa
   const int cap = std::max(1, ceil_div((long long)sm_count() * 8, C / 2));
   if (chunks > cap) chunks = cap;
   RFK_LAUNCH(coupling_taps_bwd_kernel, dim3(chunks, C / 2), 256, 0, (cudaStream_t)stream, taps, z_out, dz, dsum, B, C, H, W,
-             scale, shift, clamp_type, clamp_scale, clamp_shift, g_ld, d_scale, d_shift, d_clamp_scale, d_clamp_shift);
+             scale, shift, clamp_type, clamp_scale, clamp_shift, g_ld, d_scale, d_shift, d_clamp_scale, d_clamp_shift, logs_factor);
   return check_launch("rfk_coupling_taps_bwd");
 }
 
@@ -462,7 +478,8 @@ extern "C" int rfk_gauss_logp_bwd(const float* z, int z_C, int z_off, const floa
 
 
 extern "C" int rfk_act_affine_bwd(const void* dh, const void* h, int ld, int n, const float* scale, int act_fn, void* da,
-                                  int da_ld, float* r_dv, float* r_dvv, long long rows, void* stream) {
+                                  int da_ld, float* r_dv, float* r_dvv, float dvv_factor, int dv_scaled, long long rows,
+                                  void* stream) {
   RFK_REQUIRE(dh && h && da && scale && r_dv && r_dvv && rows > 0 && n > 0, "rfk_act_affine_bwd: null pointer or empty shape");
   const int n8 = (n + 7) / 8 * 8;   // channels are handled in groups of 8; the tail group reads/writes pad columns
   RFK_REQUIRE(n <= 2048 && ld % 8 == 0 && da_ld % 8 == 0 && n8 <= ld && n8 <= da_ld,
@@ -474,12 +491,14 @@ extern "C" int rfk_act_affine_bwd(const void* dh, const void* h, int ld, int n, 
   const int ctas = (int)std::min<long long>((long long)sm_count() * 4, (rows + 63) / 64);
   const long long rows_per_cta = (rows + ctas - 1) / ctas;
   RFK_LAUNCH(act_affine_bwd_kernel, ctas, 256, 0, (cudaStream_t)stream, (const __nv_bfloat16*)dh, (const __nv_bfloat16*)h,
-             ld, n, scale, act_fn, (__nv_bfloat16*)da, da_ld, r_dv, r_dvv, rows, rows_per_cta);
+             ld, n, scale, act_fn, (__nv_bfloat16*)da, da_ld, r_dv, r_dvv, dvv_factor, dv_scaled, rows, rows_per_cta);
   return check_launch("rfk_act_affine_bwd");
 }
 
 extern "C" int rfk_conv_wgrad(const void* x, int x_ld, int cin, const void* dy, int dy_ld, int cout, int B, int H, int W,
-                              int taps, float* dw, int dw_ld, void* stream) {
+                              int taps, float* dw, int dw_ld, int layout, const int* perm, void* stream) {
+  RFK_REQUIRE(layout == 0 || layout == 1, "rfk_conv_wgrad: layout must be 0 ([taps][cout][ld]) or 1 ([cout][ld][taps])");
+  RFK_REQUIRE(layout == 1 || perm == nullptr, "rfk_conv_wgrad: a channel permutation needs layout 1");
   RFK_REQUIRE(x && dy && dw && B > 0 && H > 0 && W > 0 && cin > 0 && cout > 0, "rfk_conv_wgrad: null pointer or empty shape");
   RFK_REQUIRE(taps == 1 || taps == 9, "rfk_conv_wgrad: taps=%d (only 1x1 and 3x3 kernels)", taps);
   RFK_REQUIRE(x_ld % 8 == 0 && dy_ld % 8 == 0 && cin <= x_ld && cout <= dy_ld && dw_ld >= cin,
@@ -490,7 +509,7 @@ extern "C" int rfk_conv_wgrad(const void* x, int x_ld, int cin, const void* dy, 
     // tensor-core (tcgen05) path; RFK_WGRAD_WMMA=1 keeps the warp-level mma.sync kernel for A/B comparisons
     static const bool force_wmma = [] { const char* e = getenv("RFK_WGRAD_WMMA"); return e && e[0] == '1'; }();
     if (!force_wmma) {
-      const int rc = conv_wgrad_tc(x, x_ld, cin, dy, dy_ld, cout, B, H, W, taps, dw, dw_ld, (cudaStream_t)stream);
+      const int rc = conv_wgrad_tc(x, x_ld, cin, dy, dy_ld, cout, B, H, W, taps, dw, dw_ld, layout, perm, (cudaStream_t)stream);
       if (rc <= 0) return rc;   // ran (0) or failed (<0); positive = shape not covered, fall through
     }
   }
@@ -506,7 +525,7 @@ extern "C" int rfk_conv_wgrad(const void* x, int x_ld, int cin, const void* dy, 
   slices = (npix + pps - 1) / pps;
   dim3 grid((unsigned)(taps * c_tiles), (unsigned)n_tiles, (unsigned)slices);
   RFK_LAUNCH(conv_wgrad_kernel, grid, 256, 0, (cudaStream_t)stream, (const __nv_bfloat16*)x, x_ld, cin,
-             (const __nv_bfloat16*)dy, dy_ld, cout, B, H, W, taps, dw, dw_ld, pps);
+             (const __nv_bfloat16*)dy, dy_ld, cout, B, H, W, taps, dw, dw_ld, layout, perm, pps);
   return check_launch("rfk_conv_wgrad");
 }
 

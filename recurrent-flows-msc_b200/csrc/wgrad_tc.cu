@@ -42,9 +42,11 @@ struct WgradArgs {
   int tpc;                       // taps per CTA
   int b_stages;
   int tmem_cols;
-  int transpose_out;             // 0: dw[tap][m][n]   1: dw[tap][n][m]
+  int transpose_out;             // 0: M side = output channels (cout), N side = input channels   1: the other way round
   int dw_ld;                     // row stride of dw
   int dw_rows;                   // rows per tap of dw (cout)
+  int layout;                    // 0: dw[tap][cout][dw_ld]   1: dw[cout][dw_ld][tap] with the input channel mapped through perm
+  const int* perm;
   float* dw;
 };
 
@@ -190,7 +192,6 @@ __global__ void __launch_bounds__(WT_THREADS, 1) conv_wgrad_tc_kernel(const __gr
     if (blockIdx.x < g.tiles) {
       for (int tp = 0; tp < ntap; ++tp) {
         const int tap = tap0 + tp;
-        float* dwt = g.dw + (long long)tap * g.dw_rows * g.dw_ld;
         for (int c0 = 0; c0 < g.n_cols; c0 += 16) {
           uint32_t r[16];
           tmem_ld16_nowait(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(tp * g.n_cols + c0), r);
@@ -200,7 +201,9 @@ __global__ void __launch_bounds__(WT_THREADS, 1) conv_wgrad_tc_kernel(const __gr
             for (int j = 0; j < 16; ++j) {
               const int n = n0 + c0 + j;
               if (n < g.n_total) {
-                float* dst = g.transpose_out ? dwt + (long long)n * g.dw_ld + m : dwt + (long long)m * g.dw_ld + n;
+                const int co = g.transpose_out ? n : m, ci = g.transpose_out ? m : n;
+                float* dst = g.layout ? g.dw + ((long long)co * g.dw_ld + (g.perm ? g.perm[ci] : ci)) * g.taps + tap
+                                      : g.dw + ((long long)tap * g.dw_rows + co) * g.dw_ld + ci;
                 atomicAdd(dst, __uint_as_float(r[j]));
               }
             }
@@ -222,7 +225,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) conv_wgrad_tc_kernel(const __gr
 
 // Returns RFK_OK when the tensor-core path ran, a positive value when the shape is not covered (caller falls back).
 int conv_wgrad_tc(const void* x, int x_ld, int cin, const void* dy, int dy_ld, int cout, int B, int H, int W, int taps,
-                  float* dw, int dw_ld, cudaStream_t stream) {
+                  float* dw, int dw_ld, int layout, const int* perm, cudaStream_t stream) {
   const char* who = "rfk_conv_wgrad";
   if (taps != 1 && taps != 9) return 1;
   WgradArgs g{};
@@ -238,6 +241,8 @@ int conv_wgrad_tc(const void* x, int x_ld, int cin, const void* dy, int dy_ld, i
   g.dw = dw;
   g.dw_ld = dw_ld;
   g.dw_rows = cout;
+  g.layout = layout;
+  g.perm = perm;
   int twl = ilog2_ceil(W);
   if (twl > 7) twl = 7;
   int thl = ilog2_ceil(H);

@@ -3,6 +3,8 @@
 PyTorch is used here for device memory and the current stream only; every
 function enqueues exactly the kernel it names on ``torch.cuda.current_stream()``.
 """
+import contextlib
+
 import torch
 
 from . import _lib
@@ -300,17 +302,56 @@ def convlstm_pointwise(cc, c_prev, peep):
 # --------------------------------------------------------------------------------------
 # backward building blocks
 # --------------------------------------------------------------------------------------
-def act_affine_bwd(dh, h, n, scale, act_fn):
-    """Backward of h = act(a*scale + shift): returns (da bf16 NHWC like dh, r_dv [n], r_dvv [n]);
-    d bias = scale*r_dv, d logs = r_dvv for an ActNorm with scale = exp(logs)."""
+class _ZeroArena:
+    """One memset for all the small zero-initialised reduction / accumulation buffers of a backward sweep (per-channel
+    sums, weight gradients accumulated with atomics) instead of one fill kernel each (~450 per training step)."""
+
+    CHUNK = 1 << 23   # floats
+
+    def __init__(self, device):
+        self.device, self.buf, self.off = device, None, 0
+
+    def take(self, n):
+        n4 = (n + 3) // 4 * 4
+        if self.buf is None or self.off + n4 > self.buf.numel():
+            self.buf = torch.zeros(max(self.CHUNK, n4), device=self.device, dtype=torch.float32)
+            self.off = 0
+        out = self.buf[self.off:self.off + n]
+        self.off += n4
+        return out
+
+
+_ARENA = None
+
+
+@contextlib.contextmanager
+def zero_arena(device):
+    global _ARENA
+    prev, _ARENA = _ARENA, _ZeroArena(device)
+    try:
+        yield
+    finally:
+        _ARENA = prev
+
+
+def _zeros(n, device):
+    if _ARENA is not None and _ARENA.device == device:
+        return _ARENA.take(n)
+    return torch.zeros(n, device=device, dtype=torch.float32)
+
+
+def act_affine_bwd(dh, h, n, scale, act_fn, dvv_factor=1.0, dv_scaled=False):
+    """Backward of h = act(a*scale + shift): returns (da bf16 NHWC like dh, r_dv [n], r_dvv [n]) with r_dv = sum dv
+    (times scale when dv_scaled: d bias of an ActNorm with scale = exp(logs)) and r_dvv = dvv_factor * sum dv*v (d logs)."""
     _chk(dh, torch.bfloat16, "dh")
     _chk(h, torch.bfloat16, "h")
     rows = dh.numel() // dh.shape[-1]
     da = torch.empty_like(dh) if (n + 7) // 8 * 8 == dh.shape[-1] else torch.zeros_like(dh)   # the kernel writes 8-channel groups
-    r = torch.zeros(2, n, device=dh.device, dtype=torch.float32)
+    r = _zeros(2 * n, dh.device)
     call("rfk_act_affine_bwd", dh.data_ptr(), h.data_ptr(), dh.shape[-1], n, _chk(scale).data_ptr(), ACT[act_fn],
-         da.data_ptr(), da.shape[-1], r[0].data_ptr(), r[1].data_ptr(), rows, _stream())
-    return da, r[0], r[1]
+         da.data_ptr(), da.shape[-1], r[:n].data_ptr(), r[n:].data_ptr(), float(dvv_factor), int(bool(dv_scaled)), rows,
+         _stream())
+    return da, r[:n], r[n:]
 
 
 def convlstm_pointwise_bwd(cc, c_prev, peep, dh, dc_in, dbias):
@@ -327,34 +368,36 @@ def convlstm_pointwise_bwd(cc, c_prev, peep, dh, dc_in, dbias):
     return dcc, dc_prev
 
 
-def conv_wgrad(x, cin, dy, cout, taps, out=None):
-    """Weight gradient [cout, cin, k, k] (fp32) of a 'same' conv from NHWC bf16 activations x and output gradients dy.
-    ``out`` (fp32 [taps, cout, cin], zeroed by the caller once) accumulates over several calls and is returned as is."""
+def conv_wgrad(x, cin, dy, cout, taps, out=None, perm=None):
+    """Weight gradient [cout, cin, k, k] (fp32, the conv weight's own layout) of a 'same' conv from NHWC bf16 activations x
+    and output gradients dy.  ``perm`` (long tensor): channel c of x is the weight's input channel perm[c].  ``out``
+    (zeroed by the caller once) accumulates over several calls."""
     _chk(x, torch.bfloat16, "x")
     _chk(dy, torch.bfloat16, "dy")
     B, H, W, xld = x.shape
-    dw = out if out is not None else torch.zeros(taps, cout, cin, device=x.device, dtype=torch.float32)
-    call("rfk_conv_wgrad", x.data_ptr(), xld, cin, dy.data_ptr(), dy.shape[-1], cout, B, H, W, taps, dw.data_ptr(), cin,
-         _stream(), meta={"flops": 2.0 * B * H * W * cout * cin * taps, "flops_padded": 2.0 * B * H * W * cout * cin * taps,
-                          "M": B * H * W, "N": cout, "K": taps * cin, "bytes": 2.0 * B * H * W * (cin + cout)})
-    if out is not None:
-        return out
     k = 3 if taps == 9 else 1
-    return dw.permute(1, 2, 0).reshape(cout, cin, k, k)
+    dw = out if out is not None else _zeros(cout * cin * taps, x.device).view(cout, cin, k, k)
+    _chk(dw, name="dw")
+    call("rfk_conv_wgrad", x.data_ptr(), xld, cin, dy.data_ptr(), dy.shape[-1], cout, B, H, W, taps, dw.data_ptr(), cin,
+         1, _p(_perm32(perm)), _stream(),
+         meta={"flops": 2.0 * B * H * W * cout * cin * taps, "flops_padded": 2.0 * B * H * W * cout * cin * taps,
+               "M": B * H * W, "N": cout, "K": taps * cin, "bytes": 2.0 * B * H * W * (cin + cout)})
+    return dw
 
 
-def coupling_taps_bwd(taps, z_out, dz, scale, shift, clamp, clamp_scale, clamp_shift, g_ld):
+def coupling_taps_bwd(taps, z_out, dz, scale, shift, clamp, clamp_scale, clamp_shift, g_ld, logs_factor=0.0):
     """Backward of coupling_tail_taps.  dz (in/out, [B,C,H,W]): z2 half replaced by the gradient w.r.t. z2.
-    Returns (dsum [B,C,H,W], d_scale [C], d_shift [C], d_clamp_scale [C/2], d_clamp_shift [C/2])."""
+    Returns (dsum [B,C,H,W], d_scale [C], d_shift [C], d_clamp_scale [C/2], d_clamp_shift [C/2]); with logs_factor f != 0
+    the second and third are d logs and d bias of a Conv2dZeros whose affine is scale = exp(f*logs), shift = bias*scale."""
     B, C, H, W = _chk(dz, name="dz").shape
     _chk(taps, name="taps"); _chk(z_out, name="z_out")
     dsum = torch.empty_like(dz)
-    r = torch.zeros(3 * C, device=dz.device, dtype=torch.float32)
+    r = _zeros(3 * C, dz.device)
     d_scale, d_shift, d_cs, d_csh = r[:C], r[C:2 * C], r[2 * C:2 * C + C // 2], r[2 * C + C // 2:]
     p = lambda t: _chk(t).data_ptr() if t is not None else None
     call("rfk_coupling_taps_bwd", taps.data_ptr(), z_out.data_ptr(), dz.data_ptr(), dsum.data_ptr(), B, C, H, W,
          _chk(scale).data_ptr(), _chk(shift).data_ptr(), CLAMP[clamp], p(clamp_scale), p(clamp_shift), p(g_ld),
-         d_scale.data_ptr(), d_shift.data_ptr(), d_cs.data_ptr(), d_csh.data_ptr(), _stream())
+         d_scale.data_ptr(), d_shift.data_ptr(), d_cs.data_ptr(), d_csh.data_ptr(), float(logs_factor), _stream())
     return dsum, d_scale, d_shift, d_cs, d_csh
 
 
@@ -372,7 +415,7 @@ def mix1x1_wgrad(x, dy):
     """(dW [C,C], db [C]) of y = W x + b over all pixels (fp32 NCHW)."""
     B, C, H, W = _chk(x, name="x").shape
     _chk(dy, name="dy")
-    r = torch.zeros(C * C + C, device=x.device, dtype=torch.float32)
+    r = _zeros(C * C + C, x.device)
     call("rfk_mix1x1_wgrad", x.data_ptr(), dy.data_ptr(), B, C, H * W, r.data_ptr(), r[C * C:].data_ptr(), _stream())
     return r[:C * C].view(C, C), r[C * C:]
 
