@@ -257,7 +257,8 @@ int rfk_gauss_logp_bwd(const float* z, int z_C, int z_off, const float* params, 
 /* Weight repacking (one launch per conv weight per optimizer step): fp32 [N, Cin, taps] (tap = 3*ky + kx) -> bf16 K-major
  * GEMM operand dst[rows_pad, ktot], zero-padded.  mode 0: forward conv, row n, k = t*kp + j <- W[n, perm[j], t] (perm
  * nullable = identity over Cin, staging-buffer channel order); mode 1: data-gradient conv, row r (rows = len(perm) or Cin),
- * k = t*kp + co <- W[co, perm[r], taps-1-t]; mode 2: tap-split 1x1 form, row t*N + c, k = j <- W[c, j, t]. */
+ * k = t*kp + co <- W[co, perm[r], taps-1-t]; mode 2: tap-split 1x1 form, row t*N + c, k = j <- W[c, j, t]; mode 3: tap-split
+ * data gradient, row t*R + j (R = rows/taps), k = co <- W[co, perm[j], taps-1-t]; perm[j] < 0 (or j >= Cin without perm) = zero row. */
 int rfk_pack_weight(const float* src, int N, int Cin, int taps, int mode, const int* perm, int rows, int kp,
                     void* dst, int rows_pad, int ktot, void* stream);
 
@@ -274,6 +275,11 @@ int rfk_adam_step(float* p, const float* g, float* m, float* v, long long n, flo
 int rfk_convlstm_pointwise_bwd(const float* cc, const float* c_prev, const float* peep, const float* dh,
                                long long dh_bstride, const float* dc_in, float* dcc, float* dc_prev, float* dbias,
                                int B, int Hc, int HW, void* stream);
+
+/* Gather of nine tap planes stored NHWC bf16 (output of a tap-split 1x1 GEMM with N = 9*n_stride, row stride ld):
+ * out[b, j, y, x] = sum_t T[b, y+ky-1, x+kx-1, t*n_stride + j] (zero outside the image), fp32 NCHW [B, n, H, W];
+ * n <= n_stride <= 128, n_stride a multiple of 8 (tap segments are whole 16-byte chunks). */
+int rfk_taps_gather_nhwc(const void* T, int ld, int n, int n_stride, int B, int H, int W, float* out, void* stream);
 
 /* Debug aid: when buf != NULL, every conv-GEMM CTA of later launches (grids of at most capacity_ctas CTAs)
  * writes 16 words to buf[16*cta..]: %globaltimer stamps (ns) 0 start, 1 setup done, 2 weights resident, 3 last TMA

@@ -181,6 +181,10 @@ class Conv2dZeros(nn.Module):
         """Weights of the data-gradient convolution (flipped taps, in/out channels swapped), rows in staging order."""
         return self._cache.get(("wd", key), (self.conv.weight,), lambda: ops.pack_dgrad_weight(self.conv.weight, out_perm))
 
+    def packed_dgrad_taps(self, key="id", out_perm=None):
+        """Tap-split form of the data-gradient weights (3x3 convs with few input channels: one GEMM with N = 9*Cin)."""
+        return self._cache.get(("wd9", key), (self.conv.weight,), lambda: ops.pack_dgrad_taps_weight(self.conv.weight, out_perm))
+
     def packed_taps(self):
         """Tap-split 1x1 form of the 3x3 weight (ops.pack_tap_split_weight), cached."""
         return self._cache.get(("w9",), (self.conv.weight,), lambda: ops.pack_tap_split_weight(self.conv.weight))
@@ -233,6 +237,10 @@ class Conv2dNorm(nn.Module):
     def packed_dgrad(self, key="id", out_perm=None):
         """Weights of the data-gradient convolution (flipped taps, in/out channels swapped), rows in staging order."""
         return self._cache.get(("wd", key), (self.conv.weight,), lambda: ops.pack_dgrad_weight(self.conv.weight, out_perm))
+
+    def packed_dgrad_taps(self, key="id", out_perm=None):
+        """Tap-split form of the data-gradient weights (3x3 convs with few input channels: one GEMM with N = 9*Cin)."""
+        return self._cache.get(("wd9", key), (self.conv.weight,), lambda: ops.pack_dgrad_taps_weight(self.conv.weight, out_perm))
 
     def ready_for_fusion(self):
         """True when the per-channel affine is known without looking at the data (no pending ActNorm init, no

@@ -23,6 +23,10 @@ from .. import ops
 from .glow_modules import BatchNormFlow, Split2d, Squeeze2d, TAP_SPLIT_MAX_N
 
 
+DGRAD_TAP_SPLIT_MAX_N = 512         # tap-split data gradient when 9*Cin <= this ...
+DGRAD_TAP_SPLIT_MIN_PIXELS = 32768  # ... and the launch has enough pixels to be bandwidth- rather than latency-bound
+
+
 class _State:
     """What the backward sweep carries: the gradient of the current activation, the per-sample weight on the
     log-determinant, and the accumulated parameter / condition gradients."""
@@ -64,8 +68,18 @@ def _conv_bwd(st, mod, x_act, cin, da, perm=None, dgrad_out=None, key="id"):
     n = mod.conv.out_channels
     st.add(mod.conv.weight, ops.conv_wgrad(x_act, cin, da, n, mod.taps, perm=perm))   # staging order -> weight order
     if dgrad_out is not None:
-        wd, cp = mod.packed_dgrad(key, perm)
-        ops.conv_gemm(da, cp, wd, cin, mod.taps, None, None, "none", dgrad_out)
+        B, H, W, _ = da.shape
+        if (mod.taps == 9 and dgrad_out.dtype == torch.float32 and 9 * cin <= DGRAD_TAP_SPLIT_MAX_N
+                and B * H * W >= DGRAD_TAP_SPLIT_MIN_PIXELS):
+            # few input channels: one 1x1 GEMM with N = 9*cin reads the gradient once (instead of once per tap, with
+            # 16/32-column MMAs), then the nine shifted planes are summed
+            wd9, cp, r8 = mod.packed_dgrad_taps(key, perm)
+            planes = torch.empty(B, H, W, ops.pad_to(9 * r8, 64), device=da.device, dtype=torch.bfloat16)
+            ops.conv_gemm(da, cp, wd9, 9 * r8, 1, None, None, "none", planes)
+            ops.taps_gather_nhwc(planes, cin, r8, dgrad_out)
+        else:
+            wd, cp = mod.packed_dgrad(key, perm)
+            ops.conv_gemm(da, cp, wd, cin, mod.taps, None, None, "none", dgrad_out)
 
 
 def _norm_act_bwd(st, mod, dh, h, act_fn):

@@ -64,6 +64,7 @@ SIGNATURES = {
                       c_void_p, c_void_p],
     "rfk_convlstm_pointwise_bwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_void_p, c_void_p, c_void_p, c_void_p,
                                    c_int, c_int, c_int, c_void_p],
+    "rfk_taps_gather_nhwc": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
     "rfk_add_scalar": [c_void_p, c_void_p, c_float, c_int, c_void_p],
     "rfk_debug_set_timeline": [c_void_p, c_longlong],
 }

@@ -1087,6 +1087,7 @@ extern "C" int rfk_add_scalar(float* logdet, const float* addend, float alpha, i
 //   mode 0  the forward conv:        row n,        k = t*kp + j   <- W[n, perm[j], t]
 //   mode 1  the data-gradient conv:  row r,        k = t*kp + co  <- W[co, perm[r], taps-1-t]   (flipped, in/out swapped)
 //   mode 2  the tap-split 1x1 form:  row t*N + c,  k = j          <- W[c, j, t]
+//   mode 3  tap-split data gradient: row t*R + j,  k = co         <- W[co, perm[j], taps-1-t]   (R = rows / taps)
 // One launch per weight (the optimizer changes every weight every step, so this runs once per conv per step).
 // ------------------------------------------------------------------------------------------
 namespace rfk {
@@ -1106,9 +1107,13 @@ __global__ void __launch_bounds__(256) pack_weight_kernel(const float* __restric
       } else if (mode == 1) {
         const int t = k / kp, co = k % kp;
         if (co < N) v = src[((long long)co * Cin + (perm ? perm[r] : r)) * taps + (taps - 1 - t)];
-      } else {
+      } else if (mode == 2) {
         const int t = r / N, c = r % N;
         if (k < Cin) v = src[((long long)c * Cin + k) * taps + t];
+      } else {
+        const int R = rows / taps, t = r / R, j = r % R;
+        const int ci = perm ? perm[j] : j;       // negative / out-of-range = a padding row of the tap segment
+        if (k < N && ci >= 0 && ci < Cin) v = src[((long long)k * Cin + ci) * taps + (taps - 1 - t)];
       }
     }
     dst[i] = __float2bfloat16(v);
@@ -1121,11 +1126,88 @@ extern "C" int rfk_pack_weight(const float* src, int N, int Cin, int taps, int m
   using namespace rfk;
   RFK_REQUIRE(src && dst && N > 0 && Cin > 0 && taps > 0 && rows > 0 && rows <= rows_pad && kp > 0 && ktot > 0,
               "rfk_pack_weight: null pointer or bad shape");
-  RFK_REQUIRE(mode >= 0 && mode <= 2, "rfk_pack_weight: unknown mode %d", mode);
-  RFK_REQUIRE(mode == 2 ? (ktot == kp && kp >= Cin && rows == taps * N) : (ktot == taps * kp && kp >= (mode == 0 ? Cin : N)),
+  RFK_REQUIRE(mode >= 0 && mode <= 3, "rfk_pack_weight: unknown mode %d", mode);
+  RFK_REQUIRE(mode == 2 ? (ktot == kp && kp >= Cin && rows == taps * N)
+              : mode == 3 ? (ktot == kp && kp >= N && rows % taps == 0)
+                          : (ktot == taps * kp && kp >= (mode == 0 ? Cin : N)),
               "rfk_pack_weight: ktot=%d / kp=%d do not match mode %d", ktot, kp, mode);
   const long long total = (long long)rows_pad * ktot;
   RFK_LAUNCH(pack_weight_kernel, stream_grid(total, 256, 8), 256, 0, (cudaStream_t)stream, src, N, Cin, taps, mode, perm, rows,
              kp, (__nv_bfloat16*)dst, rows_pad, ktot);
   return check_launch("rfk_pack_weight");
+}
+
+
+// ------------------------------------------------------------------------------------------
+// Gather of nine tap planes stored NHWC bf16 (the output of a tap-split 1x1 GEMM with N = 9*ns):
+//   out[b, j, y, x] = sum_t T[b, y+ky-1, x+kx-1, t*ns + j]      (t = 3*ky + kx; zero outside the image), fp32 NCHW,
+// ns = the per-tap channel stride (n rounded up to 8, so every tap segment is a whole number of 16-byte chunks).
+// Used by the data gradient of a 3x3 conv with few input channels: the gradient tensor is read once by one GEMM instead
+// of once per tap.  Every element of T is needed exactly once.  A CTA handles 64 consecutive pixels: in phase 1 a thread
+// owns (pixel, 8-channel group) and issues nine 128-bit loads (channel-fastest = coalesced NHWC rows), phase 2 writes
+// pixel-fastest (coalesced NCHW rows) through a shared-memory transpose.
+// ------------------------------------------------------------------------------------------
+namespace rfk {
+constexpr int TG_PIX = 64;
+__global__ void __launch_bounds__(256) taps_gather_nhwc_kernel(const __nv_bfloat16* __restrict__ T, int ld, int n, int ns, int B,
+                                                               int H, int W, float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
+  extern __shared__ float tile[];   // [ns][TG_PIX + 1]
+  const int HW = H * W, G = ns >> 3;
+  const long long npix = (long long)B * HW;
+  for (long long g0 = (long long)blockIdx.x * TG_PIX; g0 < npix; g0 += (long long)gridDim.x * TG_PIX) {
+    for (int e = threadIdx.x; e < TG_PIX * G; e += blockDim.x) {
+      const int pl = e / G, gq = e - pl * G;
+      const long long g = g0 + pl;
+      float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      if (g < npix) {
+        const long long b = g / HW;
+        const int p = (int)(g % HW), y = p / W, x = p - y * W;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+          const int yy = y + ky - 1;
+          if (yy < 0 || yy >= H) continue;
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) {
+            const int xx = x + kx - 1;
+            if (xx < 0 || xx >= W) continue;
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(T + ((b * H + yy) * W + xx) * (long long)ld + (3 * ky + kx) * ns + 8 * gq));
+            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float2 f = __bfloat1622float2(h2[k]);
+              s[2 * k] += f.x;
+              s[2 * k + 1] += f.y;
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) tile[(8 * gq + k) * (TG_PIX + 1) + pl] = s[k];
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < TG_PIX * n; e += blockDim.x) {
+      const int j = e / TG_PIX, pl = e - j * TG_PIX;
+      const long long g = g0 + pl;
+      if (g < npix) {
+        const long long b = g / HW;
+        out[(b * n + j) * HW + (g % HW)] = tile[j * (TG_PIX + 1) + pl];
+      }
+    }
+    __syncthreads();
+  }
+}
+}  // namespace rfk
+
+extern "C" int rfk_taps_gather_nhwc(const void* T, int ld, int n, int n_stride, int B, int H, int W, float* out, void* stream) {
+  using namespace rfk;
+  RFK_REQUIRE(T && out && n > 0 && n <= n_stride && n_stride <= 128 && n_stride % 8 == 0 && B > 0 && H > 0 && W > 0 &&
+              ld >= 9 * n_stride && ld % 8 == 0 && (reinterpret_cast<uintptr_t>(T) & 15) == 0,
+              "rfk_taps_gather_nhwc: bad arguments (n <= n_stride <= 128, n_stride %% 8 == 0, ld >= 9*n_stride, ld %% 8 == 0)");
+  const long long npix = (long long)B * H * W;
+  long long ctas = std::min<long long>((npix + TG_PIX - 1) / TG_PIX, (long long)sm_count() * 16);
+  RFK_LAUNCH(taps_gather_nhwc_kernel, (int)ctas, 256, (size_t)n_stride * (TG_PIX + 1) * sizeof(float), (cudaStream_t)stream,
+             (const __nv_bfloat16*)T, ld, n, n_stride, B, H, W, out);
+  return check_launch("rfk_taps_gather_nhwc");
 }

@@ -430,6 +430,31 @@ def gauss_logp_bwd(z, z_off, n, params, pairing, std_kind, g, dz):
     return dparams
 
 
+def pack_dgrad_taps_weight(weight, out_perm=None):
+    """Tap-split form of the data-gradient weights of a 3x3 conv: a 1x1 weight [pad16(9*R8), cin_pad(N)] whose row
+    t*R8 + j is W[:, perm[j], 8-t] (R8 = rows per tap rounded up to 8, the extra rows zero); the nine planes of the GEMM
+    output are summed with their shifts by taps_gather_nhwc.  Returns (weight, cin_pad, R8)."""
+    N, Cin, kh, kw = weight.shape
+    R = Cin if out_perm is None else out_perm.numel()
+    R8 = pad_to(R, 8)
+    perm = None
+    if out_perm is not None:
+        perm = torch.full((R8,), -1, device=out_perm.device, dtype=out_perm.dtype)
+        perm[:R] = out_perm
+    kp = cin_pad(N)
+    wgt, _ = _pack_weight(weight, 3, perm, kh * kw * R8, pad_to(kh * kw * R8, 64), kp, kp, N)   # 64: a wide N tile always divides it
+    return wgt, kp, R8
+
+
+def taps_gather_nhwc(T, n, n_stride, out):
+    """out [B,n,H,W] fp32 = sum over the nine shifted planes of T (NHWC bf16, channel t*n_stride + j)."""
+    _chk(T, torch.bfloat16, "T")
+    _chk(out, name="out")
+    B, H, W, ld = T.shape
+    call("rfk_taps_gather_nhwc", T.data_ptr(), ld, n, n_stride, B, H, W, out.data_ptr(), _stream())
+    return out
+
+
 _PERM32 = {}
 
 

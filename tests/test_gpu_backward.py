@@ -174,3 +174,23 @@ def test_gauss_logp_bwd(ops, std_kind, pairing, with_params):
         assert max_rel(dp.cpu(), params.grad) < 1e-4
     else:
         assert dp is None
+
+
+@pytest.mark.parametrize("B,Cin,H,W,N,with_perm", [(2, 18, 32, 32, 256, True), (3, 7, 8, 8, 64, False), (2, 36, 16, 16, 256, True),
+                                                   (2, 40, 5, 7, 24, False)])
+def test_dgrad_tap_split(ops, B, Cin, H, W, N, with_perm):
+    """Data gradient of a 3x3 conv as ONE 1x1 GEMM with N = 9*Cin (bf16 NHWC planes) + the shifted nine-plane gather."""
+    g = torch.Generator().manual_seed(Cin * 3 + N)
+    w = bf(0.1 * torch.randn(N, Cin, 3, 3, generator=g))
+    dy = bf(torch.randn(B, N, H, W, generator=g))
+    x = torch.zeros(B, Cin, H, W, requires_grad=True)
+    F.conv2d(x, w, padding=1).backward(dy)
+    perm = torch.randperm(Cin, generator=g) if with_perm else None    # staging channel j = weight channel perm[j]
+    ref = x.grad if perm is None else x.grad[:, perm]
+    wd9, cp, r8 = ops.pack_dgrad_taps_weight(w.cuda(), None if perm is None else perm.cuda())
+    dys = staged(ops, dy)
+    planes = torch.empty(B, H, W, ops.pad_to(9 * r8, 64), device="cuda", dtype=torch.bfloat16)
+    ops.conv_gemm(dys, cp, wd9, 9 * r8, 1, None, None, "none", planes)
+    out = torch.empty(B, Cin, H, W, device="cuda")
+    ops.taps_gather_nhwc(planes, Cin, r8, out)
+    assert max_rel(out.cpu(), ref) < 1e-2     # the nine planes are rounded to bf16
