@@ -227,12 +227,14 @@ int rfk_convlstm_pointwise(const float* cc, const float* c_prev, const float* pe
  * rfk_conv_wgrad: dw[tap][n][c] += sum_p dy[p, n] * x[p + off(tap), c]  (x, dy NHWC bf16; zero outside the image;
  *   dw fp32, caller-zeroed, accumulated with atomics; tap = 3*ky + kx).  layout 0: dw[taps][cout][dw_ld]; layout 1: the conv
  *   weight's own layout dw[cout][dw_ld][taps] with input channel c stored at perm[c] (perm nullable; staging order ->
- *   weight order).  tcgen05 kernel with MN-major operands (csrc/wgrad_tc.cu); RFK_WGRAD_WMMA=1 selects the mma.sync one. */
+ *   weight order).  ws (nullable, 16-byte aligned, ws_bytes): scratch for the per-pixel-slice partial tiles; when it is
+ *   large enough the slices are summed by a second kernel (dw += sum, no atomics), else they are added atomically.
+ *   tcgen05 kernel with MN-major operands (csrc/wgrad_tc.cu); RFK_WGRAD_WMMA=1 selects the mma.sync one. */
 int rfk_act_affine_bwd(const void* dh, const void* h, int ld, int n, const float* scale, int act_fn,
                        void* da, int da_ld, float* r_dv, float* r_dvv, float dvv_factor, int dv_scaled, long long rows,
                        void* stream);
 int rfk_conv_wgrad(const void* x, int x_ld, int cin, const void* dy, int dy_ld, int cout, int B, int H, int W, int taps,
-                   float* dw, int dw_ld, int layout, const int* perm, void* stream);
+                   float* dw, int dw_ld, int layout, const int* perm, void* ws, long long ws_bytes, void* stream);
 
 /* Affine-coupling tail backward, tap-split form (backward of rfk_coupling_tail_taps; Flow/glow_modules.py:237-273).
  *   dz [B,C,H,W] holds the gradient w.r.t. the coupling output; its z2 half (channels C/2..C) is overwritten with the

@@ -52,7 +52,7 @@ SIGNATURES = {
     "rfk_act_affine_bwd": [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p,
                            c_float, c_int, c_longlong, c_void_p],
     "rfk_conv_wgrad": [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int,
-                       c_int, c_void_p, c_void_p],
+                       c_int, c_void_p, c_void_p, c_longlong, c_void_p],
     "rfk_coupling_taps_bwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                               c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p],
     "rfk_taps_scatter": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],

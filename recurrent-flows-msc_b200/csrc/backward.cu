@@ -17,7 +17,8 @@
 namespace rfk {
 
 int conv_wgrad_tc(const void* x, int x_ld, int cin, const void* dy, int dy_ld, int cout, int B, int H, int W, int taps,
-                  float* dw, int dw_ld, int layout, const int* perm, cudaStream_t stream);   // wgrad_tc.cu
+                  float* dw, int dw_ld, int layout, const int* perm, void* ws, long long ws_bytes,
+                  cudaStream_t stream);   // wgrad_tc.cu
 
 // ------------------------------------------------------------------------------------------
 // h = act(v), v = a*scale + shift (a = raw conv output, scale = e^{logs}, shift = bias*e^{logs}).
@@ -496,7 +497,8 @@ extern "C" int rfk_act_affine_bwd(const void* dh, const void* h, int ld, int n, 
 }
 
 extern "C" int rfk_conv_wgrad(const void* x, int x_ld, int cin, const void* dy, int dy_ld, int cout, int B, int H, int W,
-                              int taps, float* dw, int dw_ld, int layout, const int* perm, void* stream) {
+                              int taps, float* dw, int dw_ld, int layout, const int* perm, void* ws, long long ws_bytes,
+                              void* stream) {
   RFK_REQUIRE(layout == 0 || layout == 1, "rfk_conv_wgrad: layout must be 0 ([taps][cout][ld]) or 1 ([cout][ld][taps])");
   RFK_REQUIRE(layout == 1 || perm == nullptr, "rfk_conv_wgrad: a channel permutation needs layout 1");
   RFK_REQUIRE(x && dy && dw && B > 0 && H > 0 && W > 0 && cin > 0 && cout > 0, "rfk_conv_wgrad: null pointer or empty shape");
@@ -509,7 +511,8 @@ extern "C" int rfk_conv_wgrad(const void* x, int x_ld, int cin, const void* dy, 
     // tensor-core (tcgen05) path; RFK_WGRAD_WMMA=1 keeps the warp-level mma.sync kernel for A/B comparisons
     static const bool force_wmma = [] { const char* e = getenv("RFK_WGRAD_WMMA"); return e && e[0] == '1'; }();
     if (!force_wmma) {
-      const int rc = conv_wgrad_tc(x, x_ld, cin, dy, dy_ld, cout, B, H, W, taps, dw, dw_ld, layout, perm, (cudaStream_t)stream);
+      const int rc = conv_wgrad_tc(x, x_ld, cin, dy, dy_ld, cout, B, H, W, taps, dw, dw_ld, layout, perm, ws, ws_bytes,
+                                   (cudaStream_t)stream);
       if (rc <= 0) return rc;   // ran (0) or failed (<0); positive = shape not covered, fall through
     }
   }

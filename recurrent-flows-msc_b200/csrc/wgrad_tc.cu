@@ -18,6 +18,7 @@
 //   warp 2   TMEM allocation
 //   warps 4-7 epilogue:    tcgen05.ld -> atomicAdd
 #include <algorithm>
+#include <cstdlib>
 
 #include "tc_ptx.cuh"
 
@@ -48,6 +49,7 @@ struct WgradArgs {
   int layout;                    // 0: dw[tap][cout][dw_ld]   1: dw[cout][dw_ld][tap] with the input channel mapped through perm
   const int* perm;
   float* dw;
+  float* ws;                     // non-null: partial sums [slice][work item][128 rows][tpc*n_cols] with plain stores
 };
 
 // MN-major SWIZZLE_128B shared-memory matrix descriptor: 64-element atoms 16 KB apart (LBO), 8-row K groups 1 KB apart (SBO)
@@ -189,7 +191,20 @@ __global__ void __launch_bounds__(WT_THREADS, 1) conv_wgrad_tc_kernel(const __gr
     const int m = mt * 128 + q * 32 + lane;
     mbar_wait(done_bar, 0);
     tc_fence_after();
-    if (blockIdx.x < g.tiles) {
+    if (g.ws) {
+      // partial tile of this pixel slice: row-major [128][tpc*n_cols], 64 contiguous bytes per tcgen05.ld
+      const int cols_cta = g.tpc * g.n_cols;
+      float* row = g.ws + (((long long)blockIdx.x * gridDim.y + blockIdx.y) * 128 + q * 32 + lane) * cols_cta;
+      for (int c0 = 0; c0 < ntap * g.n_cols; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld16_nowait(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+        tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 16; j += 4)
+          *reinterpret_cast<float4*>(row + c0 + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                                 __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+      }
+    } else if (blockIdx.x < g.tiles) {
       for (int tp = 0; tp < ntap; ++tp) {
         const int tap = tap0 + tp;
         for (int c0 = 0; c0 < g.n_cols; c0 += 16) {
@@ -221,11 +236,37 @@ __global__ void __launch_bounds__(WT_THREADS, 1) conv_wgrad_tc_kernel(const __gr
   }
 }
 
+// Sum of the per-slice partial tiles -> dW (+=), one thread per output element of the work-item tile space.
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const WgradArgs g, int slices, int work) {
+  pdl_trigger();
+  pdl_wait();
+  const int cols_cta = g.tpc * g.n_cols;
+  const long long per_slice = (long long)work * 128 * cols_cta;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < per_slice; i += (long long)gridDim.x * blockDim.x) {
+    const int col = (int)(i % cols_cta);
+    const long long t = i / cols_cta;
+    const int rowi = (int)(t % 128);
+    int w = (int)(t / 128);
+    const int tg = w % g.tap_groups;
+    w /= g.tap_groups;
+    const int nc = w % g.n_chunks, mt = w / g.n_chunks;
+    const int tp = col / g.n_cols, tap = tg * g.tpc + tp;
+    const int m = mt * 128 + rowi, n = nc * 256 + (col - tp * g.n_cols);
+    if (tap >= g.taps || m >= g.m_total || n >= g.n_total) continue;
+    float s = 0.0f;
+    for (int sl = 0; sl < slices; ++sl) s += g.ws[sl * per_slice + i];
+    const int co = g.transpose_out ? n : m, ci = g.transpose_out ? m : n;
+    float* dst = g.layout ? g.dw + ((long long)co * g.dw_ld + (g.perm ? g.perm[ci] : ci)) * g.taps + tap
+                          : g.dw + ((long long)tap * g.dw_rows + co) * g.dw_ld + ci;
+    *dst += s;
+  }
+}
+
 }  // namespace
 
 // Returns RFK_OK when the tensor-core path ran, a positive value when the shape is not covered (caller falls back).
 int conv_wgrad_tc(const void* x, int x_ld, int cin, const void* dy, int dy_ld, int cout, int B, int H, int W, int taps,
-                  float* dw, int dw_ld, int layout, const int* perm, cudaStream_t stream) {
+                  float* dw, int dw_ld, int layout, const int* perm, void* ws, long long ws_bytes, cudaStream_t stream) {
   const char* who = "rfk_conv_wgrad";
   if (taps != 1 && taps != 9) return 1;
   WgradArgs g{};
@@ -279,6 +320,13 @@ int conv_wgrad_tc(const void* x, int x_ld, int cin, const void* dy, int dy_ld, i
   const int work = g.m_tiles * g.n_chunks * g.tap_groups;
   int slices = std::max(1, sm_count() / work);
   if (slices > g.tiles) slices = g.tiles;
+  {
+    // every pixel slice flushes its accumulators with one atomic per output element: bound the total
+    static const long long budget = [] { const char* e = getenv("RFK_WGRAD_ATOMIC_BUDGET"); return e ? atoll(e) : (1LL << 62); }();
+    const long long out_elems = (long long)taps * cout * cin;
+    const long long cap = std::max<long long>(1, budget / out_elems);
+    if (slices > cap) slices = (int)cap;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WT_SMEM_LIMIT);
@@ -288,7 +336,16 @@ int conv_wgrad_tc(const void* x, int x_ld, int cin, const void* dy, int dy_ld, i
     }
     attr_set = true;
   }
+  // several pixel slices: partial tiles through the workspace + a reduce kernel when it fits (no atomics: a flush of
+  // 128 x 256 scattered fp32 atomics per CTA costs more than the MMAs of the deep levels), else atomics straight into dw
+  const long long need = (long long)slices * work * 128 * g.tpc * g.n_cols * 4;
+  static const bool no_ws = [] { const char* e = getenv("RFK_WGRAD_ATOMICS"); return e && e[0] == '1'; }();
+  g.ws = (ws && !no_ws && need <= ws_bytes && (reinterpret_cast<uintptr_t>(ws) & 15) == 0) ? (float*)ws : nullptr;
   RFK_LAUNCH(conv_wgrad_tc_kernel, dim3(slices, work), WT_THREADS, smem, stream, tmA, tmB, g);
+  int rc2 = check_launch(who);
+  if (rc2 != RFK_OK || !g.ws) return rc2;
+  const long long per_slice = (long long)work * 128 * g.tpc * g.n_cols;
+  RFK_LAUNCH(wgrad_reduce_kernel, stream_grid(per_slice, 256, 8), 256, 0, stream, g, slices, work);
   return check_launch(who);
 }
 

@@ -368,6 +368,17 @@ def convlstm_pointwise_bwd(cc, c_prev, peep, dh, dc_in, dbias):
     return dcc, dc_prev
 
 
+_WGRAD_WS = {}
+
+
+def _wgrad_ws(device):
+    """Scratch for the weight-gradient kernel's per-slice partial tiles (one stream, launches in order): 64 MB."""
+    hit = _WGRAD_WS.get(device)
+    if hit is None:
+        hit = _WGRAD_WS[device] = torch.empty(1 << 24, device=device, dtype=torch.float32)
+    return hit
+
+
 def conv_wgrad(x, cin, dy, cout, taps, out=None, perm=None):
     """Weight gradient [cout, cin, k, k] (fp32, the conv weight's own layout) of a 'same' conv from NHWC bf16 activations x
     and output gradients dy.  ``perm`` (long tensor): channel c of x is the weight's input channel perm[c].  ``out``
@@ -378,8 +389,9 @@ def conv_wgrad(x, cin, dy, cout, taps, out=None, perm=None):
     k = 3 if taps == 9 else 1
     dw = out if out is not None else _zeros(cout * cin * taps, x.device).view(cout, cin, k, k)
     _chk(dw, name="dw")
+    ws = _wgrad_ws(x.device)
     call("rfk_conv_wgrad", x.data_ptr(), xld, cin, dy.data_ptr(), dy.shape[-1], cout, B, H, W, taps, dw.data_ptr(), cin,
-         1, _p(_perm32(perm)), _stream(),
+         1, _p(_perm32(perm)), ws.data_ptr(), ws.numel() * 4, _stream(),
          meta={"flops": 2.0 * B * H * W * cout * cin * taps, "flops_padded": 2.0 * B * H * W * cout * cin * taps,
                "M": B * H * W, "N": cout, "K": taps * cin, "bytes": 2.0 * B * H * W * (cin + cout)})
     return dw
