@@ -262,6 +262,186 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const WgradArgs g, in
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// "Tap-pair" variant for 3x3 convs where one side has at most 64 channels (the coupling network's first and last conv).
+// With the roles above such a layer issues MMAs with N = 16..64 columns, and tcgen05.mma costs ~128 cycles whatever N is
+// (it is bound by reading the 128 x 16 A tile from shared memory), so the tensor pipe idles.  Here the NARROW operand is
+// the M side and the two 64-channel atoms of one M = 128 tile hold TWO DIFFERENT TAPS (two boxes of the same tensor with
+// different shifts); the wide operand is the N side with up to 256 columns.  Nine taps = five pairs -> 5 x 8 MMAs of
+// N = 256 per pixel tile instead of 2 x 72 of N = 16/32.  Accumulators: pairs x n_cols <= 512 TMEM columns per CTA, so the
+// pairs are spread over blockIdx.y; partial tiles always go through the workspace.
+// ------------------------------------------------------------------------------------------
+struct PairArgs {
+  int tiles_x, tiles_y, tiles, tw_log2, th_log2;
+  int sign;                      // shift sign applied to the narrow operand's boxes
+  int small_total, big_total;
+  int n_chunks, n_cols, nbox;    // wide operand: columns per MMA, 64-channel boxes per stage
+  int ppc, pair_groups;          // tap pairs per CTA, groups over blockIdx.y
+  int inner_stages;              // pair-tile ring depth
+  int tmem_cols;
+  int small_is_x;                // 1: narrow = X (input channels), wide = dY;  0: narrow = dY (output channels), wide = X
+  int dw_ld, dw_rows, layout;
+  const int* perm;
+  float* dw;
+  float* ws;
+};
+
+__global__ void __launch_bounds__(WT_THREADS, 1) conv_wgrad_pairs_kernel(const __grid_constant__ CUtensorMap tmS,
+                                                                        const __grid_constant__ CUtensorMap tmW,
+                                                                        const PairArgs g) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t o_bytes = (uint32_t)g.nbox * WT_BOX_BYTES, i_bytes = 2u * WT_BOX_BYTES;
+  const uint32_t o_off = 0, i_off = 2u * o_bytes;
+  const uint32_t bar_off = i_off + (uint32_t)g.inner_stages * i_bytes;
+  const uint32_t bar_base = base + bar_off;
+  auto o_full = [&](int s) { return bar_base + 8u * s; };
+  auto o_empty = [&](int s) { return bar_base + 8u * (2 + s); };
+  auto i_full = [&](int s) { return bar_base + 8u * (4 + s); };
+  auto i_empty = [&](int s) { return bar_base + 8u * (4 + g.inner_stages + s); };
+  const uint32_t done_bar = bar_base + 8u * (4 + 2 * g.inner_stages);
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + bar_off + 8u * (4 + 2 * g.inner_stages + 1));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pg = blockIdx.y % g.pair_groups, nc = blockIdx.y / g.pair_groups;
+  const int pair0 = pg * g.ppc;
+  const int npair = min(g.ppc, 5 - pair0);
+  const int n0 = nc * 256;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmS);
+    tma_prefetch_desc(&tmW);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(o_full(s), 1);
+      mbar_init(o_empty(s), 1);
+    }
+    for (int s = 0; s < g.inner_stages; ++s) {
+      mbar_init(i_full(s), 1);
+      mbar_init(i_empty(s), 1);
+    }
+    mbar_init(done_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)),
+                 "r"((uint32_t)g.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  pdl_trigger();
+  pdl_wait();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int nimg_log2 = 7 - g.tw_log2 - g.th_log2;
+  if (warp == 0) {
+    if (lane == 0) {   // ===== TMA producer =====
+      int so = 0, si = 0;
+      uint32_t pho = 0, phi = 0;
+      for (int t = blockIdx.x; t < g.tiles; t += gridDim.x) {
+        int tt = t;
+        const int x0 = (tt % g.tiles_x) << g.tw_log2;
+        tt /= g.tiles_x;
+        const int y0 = (tt % g.tiles_y) << g.th_log2;
+        const int i0 = (tt / g.tiles_y) << nimg_log2;
+        mbar_wait(o_empty(so), pho ^ 1u);
+        mbar_expect_tx(o_full(so), o_bytes);
+        for (int bx = 0; bx < g.nbox; ++bx)
+          tma_load_4d(base + o_off + so * o_bytes + bx * WT_BOX_BYTES, &tmW, o_full(so), n0 + bx * 64, x0, y0, i0);
+        if (++so == 2) { so = 0; pho ^= 1u; }
+        for (int pl = 0; pl < npair; ++pl) {
+          const int ta = 2 * (pair0 + pl), tb = ta + 1;
+          mbar_wait(i_empty(si), phi ^ 1u);
+          mbar_expect_tx(i_full(si), tb < 9 ? i_bytes : (uint32_t)WT_BOX_BYTES);
+          const uint32_t dst = base + i_off + si * i_bytes;
+          tma_load_4d(dst, &tmS, i_full(si), 0, x0 + g.sign * (ta % 3 - 1), y0 + g.sign * (ta / 3 - 1), i0);
+          if (tb < 9)
+            tma_load_4d(dst + WT_BOX_BYTES, &tmS, i_full(si), 0, x0 + g.sign * (tb % 3 - 1), y0 + g.sign * (tb / 3 - 1), i0);
+          if (++si == g.inner_stages) { si = 0; phi ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {   // ===== MMA issuer =====
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                             ((uint32_t)(g.n_cols >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      int so = 0, si = 0;
+      uint32_t pho = 0, phi = 0;
+      bool first = true;
+      for (int t = blockIdx.x; t < g.tiles; t += gridDim.x) {
+        mbar_wait(o_full(so), pho);
+        tc_fence_after();
+        const uint64_t bdesc = umma_desc_mnmajor(base + o_off + so * o_bytes);
+        for (int pl = 0; pl < npair; ++pl) {
+          mbar_wait(i_full(si), phi);
+          tc_fence_after();
+          const uint64_t adesc = umma_desc_mnmajor(base + i_off + si * i_bytes);
+          const uint32_t d_tmem = tmem_base + (uint32_t)(pl * g.n_cols);
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            umma_bf16(d_tmem, adesc + (uint64_t)(128 * k), bdesc + (uint64_t)(128 * k), idesc, (first && k == 0) ? 0u : 1u);
+          umma_commit(i_empty(si));
+          if (++si == g.inner_stages) { si = 0; phi ^= 1u; }
+        }
+        umma_commit(o_empty(so));
+        if (++so == 2) { so = 0; pho ^= 1u; }
+        first = false;
+      }
+      umma_commit(done_bar);
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue: partial tile [128][ppc*n_cols] of this pixel slice -> workspace =====
+    const int q = warp & 3;
+    mbar_wait(done_bar, 0);
+    tc_fence_after();
+    const int cols_cta = g.ppc * g.n_cols;
+    float* row = g.ws + (((long long)blockIdx.x * gridDim.y + blockIdx.y) * 128 + q * 32 + lane) * cols_cta;
+    for (int c0 = 0; c0 < npair * g.n_cols; c0 += 16) {
+      uint32_t r[16];
+      tmem_ld16_nowait(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+      tmem_wait_ld();
+#pragma unroll
+      for (int j = 0; j < 16; j += 4)
+        *reinterpret_cast<float4*>(row + c0 + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                               __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)g.tmem_cols)
+                 : "memory");
+  }
+}
+
+__global__ void __launch_bounds__(256) wgrad_pairs_reduce_kernel(const PairArgs g, int slices, int work) {
+  pdl_trigger();
+  pdl_wait();
+  const int cols_cta = g.ppc * g.n_cols;
+  const long long per_slice = (long long)work * 128 * cols_cta;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < per_slice; i += (long long)gridDim.x * blockDim.x) {
+    const int col = (int)(i % cols_cta);
+    const long long t = i / cols_cta;
+    const int rowi = (int)(t % 128);
+    const int w = (int)(t / 128);
+    const int pg = w % g.pair_groups, nc = w / g.pair_groups;
+    const int pl = col / g.n_cols;
+    const int tap = 2 * (pg * g.ppc + pl) + (rowi >> 6);
+    const int c = rowi & 63, n = nc * 256 + (col - pl * g.n_cols);
+    if (pg * g.ppc + pl >= 5 || tap >= 9 || c >= g.small_total || n >= g.big_total) continue;
+    float s = 0.0f;
+    for (int sl = 0; sl < slices; ++sl) s += g.ws[sl * per_slice + i];
+    const int co = g.small_is_x ? n : c, ci = g.small_is_x ? c : n;
+    float* dst = g.layout ? g.dw + ((long long)co * g.dw_ld + (g.perm ? g.perm[ci] : ci)) * 9 + tap
+                          : g.dw + ((long long)tap * g.dw_rows + co) * g.dw_ld + ci;
+    *dst += s;
+  }
+}
+
 }  // namespace
 
 // Returns RFK_OK when the tensor-core path ran, a positive value when the shape is not covered (caller falls back).
@@ -269,6 +449,64 @@ int conv_wgrad_tc(const void* x, int x_ld, int cin, const void* dy, int dy_ld, i
                   float* dw, int dw_ld, int layout, const int* perm, void* ws, long long ws_bytes, cudaStream_t stream) {
   const char* who = "rfk_conv_wgrad";
   if (taps != 1 && taps != 9) return 1;
+  static const bool no_ws = [] { const char* e = getenv("RFK_WGRAD_ATOMICS"); return e && e[0] == '1'; }();
+  static const bool no_pairs = [] { const char* e = getenv("RFK_WGRAD_NO_PAIRS"); return e && e[0] == '1'; }();
+  if (taps == 9 && std::min(cin, cout) <= 64 && ws && !no_ws && !no_pairs && (reinterpret_cast<uintptr_t>(ws) & 15) == 0) {
+    PairArgs p{};
+    p.small_is_x = cin <= cout ? 1 : 0;
+    p.small_total = p.small_is_x ? cin : cout;
+    p.big_total = p.small_is_x ? cout : cin;
+    p.sign = p.small_is_x ? 1 : -1;
+    p.dw = dw; p.dw_ld = dw_ld; p.dw_rows = cout; p.layout = layout; p.perm = perm; p.ws = (float*)ws;
+    int twl = ilog2_ceil(W);
+    if (twl > 7) twl = 7;
+    int thl = ilog2_ceil(H);
+    if (thl > 7 - twl) thl = 7 - twl;
+    p.tw_log2 = twl; p.th_log2 = thl;
+    const int TW = 1 << twl, TH = 1 << thl, NIMG = 128 / (TW * TH);
+    p.tiles_x = ceil_div(W, TW);
+    p.tiles_y = ceil_div(H, TH);
+    p.tiles = p.tiles_x * p.tiles_y * ceil_div(B, NIMG);
+    const int n_cols_total = (p.big_total + 15) / 16 * 16;
+    p.n_chunks = ceil_div(n_cols_total, 256);
+    p.n_cols = p.n_chunks == 1 ? n_cols_total : 256;
+    p.nbox = ceil_div(p.n_cols, 64);
+    p.pair_groups = ceil_div(5, std::min(5, 512 / p.n_cols));
+    p.ppc = ceil_div(5, p.pair_groups);
+    int cols = 32;
+    while (cols < p.ppc * p.n_cols) cols <<= 1;
+    p.tmem_cols = cols;
+    const int outer = 2 * p.nbox * WT_BOX_BYTES;
+    p.inner_stages = std::min(8, (WT_SMEM_LIMIT - 1024 - outer - 512) / (2 * WT_BOX_BYTES));
+    const int work = p.n_chunks * p.pair_groups;
+    int slices = std::max(1, sm_count() / work);
+    if (slices > p.tiles) slices = p.tiles;
+    const long long per_slice = (long long)work * 128 * p.ppc * p.n_cols;
+    if (p.inner_stages >= 2 && per_slice * slices * 4 <= ws_bytes) {
+      const size_t smem = 1024 + (size_t)outer + (size_t)p.inner_stages * 2 * WT_BOX_BYTES + 8 * (4 + 2 * p.inner_stages + 2) + 16;
+      CUtensorMap tmS, tmW;
+      int rc = encode_act_map(&tmS, who, "narrow side", p.small_is_x ? x : dy, p.small_total, p.small_is_x ? x_ld : dy_ld, B, H, W,
+                              TW, TH, NIMG, 64);
+      if (rc != RFK_OK) return rc;
+      rc = encode_act_map(&tmW, who, "wide side", p.small_is_x ? dy : x, p.big_total, p.small_is_x ? dy_ld : x_ld, B, H, W, TW,
+                          TH, NIMG, 64);
+      if (rc != RFK_OK) return rc;
+      static bool pattr = false;
+      if (!pattr) {
+        cudaError_t e = cudaFuncSetAttribute(conv_wgrad_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WT_SMEM_LIMIT);
+        if (e != cudaSuccess) {
+          set_error("%s: cudaFuncSetAttribute failed: %s", who, cudaGetErrorString(e));
+          return RFK_ECUDA;
+        }
+        pattr = true;
+      }
+      RFK_LAUNCH(conv_wgrad_pairs_kernel, dim3(slices, work), WT_THREADS, smem, stream, tmS, tmW, p);
+      rc = check_launch(who);
+      if (rc != RFK_OK) return rc;
+      RFK_LAUNCH(wgrad_pairs_reduce_kernel, stream_grid(per_slice, 256, 8), 256, 0, stream, p, slices, work);
+      return check_launch(who);
+    }
+  }
   WgradArgs g{};
   const bool swap = cin > cout;   // M side = the operand with more channels
   const void* a_ptr = swap ? x : dy;
@@ -339,7 +577,6 @@ int conv_wgrad_tc(const void* x, int x_ld, int cin, const void* dy, int dy_ld, i
   // several pixel slices: partial tiles through the workspace + a reduce kernel when it fits (no atomics: a flush of
   // 128 x 256 scattered fp32 atomics per CTA costs more than the MMAs of the deep levels), else atomics straight into dw
   const long long need = (long long)slices * work * 128 * g.tpc * g.n_cols * 4;
-  static const bool no_ws = [] { const char* e = getenv("RFK_WGRAD_ATOMICS"); return e && e[0] == '1'; }();
   g.ws = (ws && !no_ws && need <= ws_bytes && (reinterpret_cast<uintptr_t>(ws) & 15) == 0) ? (float*)ws : nullptr;
   RFK_LAUNCH(conv_wgrad_tc_kernel, dim3(slices, work), WT_THREADS, smem, stream, tmA, tmB, g);
   int rc2 = check_launch(who);
