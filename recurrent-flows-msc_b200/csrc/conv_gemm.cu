@@ -154,7 +154,11 @@ __device__ __forceinline__ void epilogue(const GemmArgs& g, const PlainEpi<ACT>&
     // ---- bf16 NHWC through swizzled shared memory + TMA store (the TMA unit clips out-of-range pixels/channels)
     const int nblk = (g.BN + 63) >> 6;
     const int r = t.q * 32 + lane;
-    const bool issuer = t.q == 0 && lane == 0;
+    const bool issuer = lane == 0;            // every warp stores its own 32 rows (sub-box of the tile)
+    const int r0 = t.q * 32;
+    const int sub_x = t.x0 + (r0 & ((1 << g.tw_log2) - 1));
+    const int sub_y = t.y0 + ((r0 >> g.tw_log2) & ((1 << g.th_log2) - 1));
+    const int sub_n = t.n0 + (r0 >> (g.tw_log2 + g.th_log2));
     const int last_blk = ((nblk - 1 - t.half) & ~1) + t.half;  // last block this half owns (may be < half: none)
     bool released = false;
     for (int blk = t.half; blk < nblk; blk += 2) {
@@ -196,8 +200,8 @@ __device__ __forceinline__ void epilogue(const GemmArgs& g, const PlainEpi<ACT>&
       }
       if (blk == last_blk) { release_accumulator(t); released = true; }
       EPI_PHASE(1);
-      if (issuer) bulk_wait_read0();   // the previous TMA store has finished reading this staging buffer
-      named_bar(1 + t.half, 128);
+      if (issuer) bulk_wait_read0();   // this warp's previous TMA store has finished reading its staging rows
+      __syncwarp();
       EPI_PHASE(2);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -209,10 +213,10 @@ __device__ __forceinline__ void epilogue(const GemmArgs& g, const PlainEpi<ACT>&
         }
       }
       fence_async_smem();
-      named_bar(1 + t.half, 128);
+      __syncwarp();
       EPI_PHASE(3);
       if (issuer) {
-        tma_store_4d(tmO, t.stg, t.n_tile * g.BN + blk * 64, t.x0, t.y0, t.n0);
+        tma_store_4d(tmO, t.stg + r0 * 128, t.n_tile * g.BN + blk * 64, sub_x, sub_y, sub_n);
         bulk_commit();
       }
       EPI_PHASE(4);
@@ -614,7 +618,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       { CNT_BEGIN(); epilogue(g, ep, &tmO, tmem_base + ((uint32_t)(t.q * 32) << 16) + buf * g.BN, ss, t); CNT_END(c_epi); }
       if (tl == 0 && warp == kEpiWarp0 && lane == 0) RFK_STAMP(6);  // first epilogue done
     }
-    if (g.use_stg && t.q == 0 && lane == 0) bulk_wait0();  // outstanding TMA stores read shared memory
+    if (g.use_stg && lane == 0) bulk_wait0();  // this warp's outstanding TMA stores still read shared memory
     if (warp == kEpiWarp0 && lane == 0) { RFK_STAMP(7); RFK_PUT(11, c_wait_tfull); RFK_PUT(12, c_epi);
       RFK_PUT(14, phase_cnt[0]); RFK_PUT(15, phase_cnt[1]); RFK_PUT(2, phase_cnt[2]); RFK_PUT(5, phase_cnt[3]); RFK_PUT(6, phase_cnt[4]); }
   }
@@ -886,8 +890,11 @@ extern "C" int rfk_conv_gemm(const void* act, int B, int H, int W, int act_ld, i
   p.g.scale = scale; p.g.shift = shift; p.g.n_ss = n;
   if (tma_ok) {
     e.tma_store = 1;
+    // the store map's box is ONE EPILOGUE WARP's 32 pixel rows of the tile (x fastest, then y, then image): every warp
+    // stores its own sub-box, so the epilogue needs no cross-warp barrier
+    const int sx = std::min(p.TW, 32), sy = std::min(p.TH, 32 / sx), sn = 32 / (sx * sy);
     rc = encode_act_map(&p.tmO, "rfk_conv_gemm", "out", reinterpret_cast<const __nv_bfloat16*>(out) + out_off, n, out_ld, B, H,
-                        W, p.TW, p.TH, p.NIMG);
+                        W, sx, sy, sn);
     if (rc) return rc;
   }
   if (act_fn == RFK_ACT_RELU) {
