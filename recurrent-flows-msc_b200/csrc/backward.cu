@@ -316,6 +316,55 @@ __global__ void __launch_bounds__(256) taps_scatter_kernel(const float* __restri
 // through shared memory.  Thread t owns output (t mod n_eff) and pixel segment (t / n_eff): with few channels (C = 4:
 // 16 outputs) the 256 threads split each chunk 16 ways instead of idling; with many (C = 64: 4096 outputs) each
 // thread owns 16 outputs over the whole chunk.
+// Few channels (C = 4, 8: the two largest flow levels): no shared-memory staging at all -- a thread walks pixels (coalesced
+// along the pixel index for every channel plane), keeps the C x C outer-product sums in registers, and the sums are
+// reduced warp -> CTA (shared-memory atomics) -> global (C*C + C atomics per CTA).
+template <int C>
+__global__ void __launch_bounds__(256) mix1x1_wgrad_small_kernel(const float* __restrict__ x, const float* __restrict__ dy, int HW,
+                                                                 long long npix, float* __restrict__ dW, float* __restrict__ db) {
+  pdl_trigger();
+  pdl_wait();
+  __shared__ float red[C * C + C];
+  for (int i = threadIdx.x; i < C * C + C; i += blockDim.x) red[i] = 0.0f;
+  __syncthreads();
+  float acc[C][C], accb[C];
+#pragma unroll
+  for (int o = 0; o < C; ++o) {
+    accb[o] = 0.0f;
+#pragma unroll
+    for (int i = 0; i < C; ++i) acc[o][i] = 0.0f;
+  }
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < npix; p += (long long)gridDim.x * blockDim.x) {
+    const long long b = p / HW;
+    const long long base = b * C * HW + (p - b * HW);
+    float xv[C], dv[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      xv[c] = __ldg(x + base + (long long)c * HW);
+      dv[c] = __ldg(dy + base + (long long)c * HW);
+    }
+#pragma unroll
+    for (int o = 0; o < C; ++o) {
+      accb[o] += dv[o];
+#pragma unroll
+      for (int i = 0; i < C; ++i) acc[o][i] = fmaf(dv[o], xv[i], acc[o][i]);
+    }
+  }
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int o = 0; o < C; ++o) {
+#pragma unroll
+    for (int i = 0; i < C; ++i) {
+      const float v = warp_sum(acc[o][i]);
+      if (lane == 0) atomicAdd(&red[o * C + i], v);
+    }
+    const float vb = warp_sum(accb[o]);
+    if (lane == 0) atomicAdd(&red[C * C + o], vb);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C * C + C; i += blockDim.x) atomicAdd(i < C * C ? dW + i : db + (i - C * C), red[i]);
+}
+
 constexpr int MW_CHUNK = 128;
 __global__ void __launch_bounds__(256) mix1x1_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, int C,
                                                            int HW, long long npix, long long pix_per_cta,
@@ -449,6 +498,12 @@ extern "C" int rfk_taps_scatter(const float* dsum, void* dtaps, int ld, int B, i
 extern "C" int rfk_mix1x1_wgrad(const float* x, const float* dy, int B, int C, int HW, float* dW, float* db, void* stream) {
   RFK_REQUIRE(x && dy && dW && db && B > 0 && C > 0 && C <= 64 && HW > 0, "rfk_mix1x1_wgrad: null pointer or bad shape (C <= 64)");
   const long long npix = (long long)B * HW;
+  if (C == 4 || C == 8) {
+    const int grid = (int)std::min<long long>((long long)sm_count() * 2, (npix + 255) / 256);
+    if (C == 4) RFK_LAUNCH(mix1x1_wgrad_small_kernel<4>, grid, 256, 0, (cudaStream_t)stream, x, dy, HW, npix, dW, db);
+    else RFK_LAUNCH(mix1x1_wgrad_small_kernel<8>, grid, 256, 0, (cudaStream_t)stream, x, dy, HW, npix, dW, db);
+    return check_launch("rfk_mix1x1_wgrad");
+  }
   long long ctas = std::min<long long>((long long)sm_count() * 4, (npix + MW_CHUNK - 1) / MW_CHUNK);
   if (ctas < 1) ctas = 1;
   long long ppc = (npix + ctas - 1) / ctas;

@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(1024) mix1x1_kernel(const float* __restrict__ 
   for (int i = tid; i < C; i += nthr) bs[i] = bvec ? bvec[i] : 0.0f;
   if (logdet && blockIdx.x == 0) {
     const float add = alpha * (*addend);
-    for (int i = tid; i < B; i += nthr) logdet[i] += add;
+    for (int i = tid; i < B; i += nthr) atomicAdd(logdet + i, add);   // other CTAs may be adding coupling terms to the same words
   }
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
