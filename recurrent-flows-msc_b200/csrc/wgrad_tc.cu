@@ -253,8 +253,16 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const WgradArgs g, in
     const int tp = col / g.n_cols, tap = tg * g.tpc + tp;
     const int m = mt * 128 + rowi, n = nc * 256 + (col - tp * g.n_cols);
     if (tap >= g.taps || m >= g.m_total || n >= g.n_total) continue;
-    float s = 0.0f;
-    for (int sl = 0; sl < slices; ++sl) s += g.ws[sl * per_slice + i];
+    float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;   // independent chains: the loads of several slices are in flight
+    int sl = 0;
+    for (; sl + 4 <= slices; sl += 4) {
+      s0 += __ldcs(g.ws + (sl + 0) * per_slice + i);
+      s1 += __ldcs(g.ws + (sl + 1) * per_slice + i);
+      s2 += __ldcs(g.ws + (sl + 2) * per_slice + i);
+      s3 += __ldcs(g.ws + (sl + 3) * per_slice + i);
+    }
+    for (; sl < slices; ++sl) s0 += __ldcs(g.ws + sl * per_slice + i);
+    const float s = (s0 + s1) + (s2 + s3);
     const int co = g.transpose_out ? n : m, ci = g.transpose_out ? m : n;
     float* dst = g.layout ? g.dw + ((long long)co * g.dw_ld + (g.perm ? g.perm[ci] : ci)) * g.taps + tap
                           : g.dw + ((long long)tap * g.dw_rows + co) * g.dw_ld + ci;
@@ -433,8 +441,16 @@ __global__ void __launch_bounds__(256) wgrad_pairs_reduce_kernel(const PairArgs 
     const int tap = 2 * (pg * g.ppc + pl) + (rowi >> 6);
     const int c = rowi & 63, n = nc * 256 + (col - pl * g.n_cols);
     if (pg * g.ppc + pl >= 5 || tap >= 9 || c >= g.small_total || n >= g.big_total) continue;
-    float s = 0.0f;
-    for (int sl = 0; sl < slices; ++sl) s += g.ws[sl * per_slice + i];
+    float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;   // independent chains: the loads of several slices are in flight
+    int sl = 0;
+    for (; sl + 4 <= slices; sl += 4) {
+      s0 += __ldcs(g.ws + (sl + 0) * per_slice + i);
+      s1 += __ldcs(g.ws + (sl + 1) * per_slice + i);
+      s2 += __ldcs(g.ws + (sl + 2) * per_slice + i);
+      s3 += __ldcs(g.ws + (sl + 3) * per_slice + i);
+    }
+    for (; sl < slices; ++sl) s0 += __ldcs(g.ws + sl * per_slice + i);
+    const float s = (s0 + s1) + (s2 + s3);
     const int co = g.small_is_x ? n : c, ci = g.small_is_x ? c : n;
     float* dst = g.layout ? g.dw + ((long long)co * g.dw_ld + (g.perm ? g.perm[ci] : ci)) * 9 + tap
                           : g.dw + ((long long)tap * g.dw_rows + co) * g.dw_ld + ci;
