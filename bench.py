@@ -425,6 +425,8 @@ def run_ours(args):
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except OSError:
             pass
+        eager_hot_path(*resident)     # the training section invalidated the weight caches: rebuild them outside the traced step
+        torch.cuda.synchronize()
         kt = KernelTimer()
         rf._lib.tracer = kt
         torch.cuda.profiler.start()   # `ncu --profile-from-start off` captures exactly this one step
