@@ -85,10 +85,11 @@ class GraphedTrainStep:
     graphs (forward+backward+gather | Adam), so nothing depends on collective capture support.
     """
 
-    def __init__(self, loss_fn, optimizer, warmup=3):
+    def __init__(self, loss_fn, optimizer, warmup=3, static_inputs=None):
         from .Flow.glow_modules import invalidate_caches
         self._invalidate = invalidate_caches
         self.opt = optimizer
+        self.static_inputs = static_inputs   # optional (nested) list of the tensors loss_fn reads: step(*batch) copies into them
 
         def fwd_bwd():
             optimizer.zero_grad(set_to_none=True)
@@ -118,7 +119,11 @@ class GraphedTrainStep:
             # the capture itself executed nothing: parameters and Adam state are unchanged, step_t too
             pass
 
-    def __call__(self):
+    def __call__(self, *batch):
+        if batch:
+            if self.static_inputs is None:
+                raise ValueError("GraphedTrainStep: pass static_inputs= at construction to feed new batches")
+            _copy_into(self.static_inputs, list(batch))
         self.g_fb.replay()
         self.opt.allreduce_grads()
         self.g_opt.replay()
