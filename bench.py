@@ -99,6 +99,38 @@ def cpu_step_builder(n_frames):
     return step
 
 
+def time_cpu_training(n_frames, steps=2, warmup=1):
+    """CPU arm of the training step: torch autograd through the oracle port (forward + backward of ListGlow.log_prob and
+    one ConvLSTM step, no optimizer) on a bounded sample of frames."""
+    import oracle as O
+    import recurrent_flows_msc_b200 as rf
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(0)
+    flow = rf.ListGlow([n_frames, 1, 64, 64], cond_sizes(n_frames), [n_frames, J["base_ch"], 2, 2], glow_args())
+    trained_like(flow, 0)
+    leaf = {k: (v.clone().requires_grad_() if v.is_floating_point() else v.clone()) for k, v in flow.state_dict().items()}
+    lstm = rf.ConvLSTM(J["lstm_in"], J["lstm_hidden"], [3, 3])
+    w = lstm.LSTMlayer.conv[0].weight.detach().clone().requires_grad_()
+    b = lstm.LSTMlayer.conv[0].bias.detach().clone().requires_grad_()
+    x, conds, base, _ = synth_inputs(n_frames, 1, 1)
+    feats = torch.randn(n_frames, 1, J["lstm_in"], 2, 2)
+    noise = torch.rand(n_frames, 1, 64, 64) / 256
+
+    def step():
+        hs, _, _ = O.convlstm(feats, w, b)
+        bc = torch.cat([hs[:, 0], base[:, J["lstm_hidden"]:]], 1)
+        _, nll = O.listglow_log_prob(x, conds, bc, leaf, J["L"], J["K"], J["n_bits"], noise=noise, learn_prior=True)
+        (nll.mean() / (math.log(2.0) * 4096)).backward()
+    for _ in range(warmup):
+        step()
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        step()
+        ts.append(time.perf_counter() - t0)
+    return n_frames / statistics.median(ts), statistics.median(ts), torch.get_num_threads()
+
+
 def time_cpu(n_frames, steps, warmup):
     torch.set_num_threads(os.cpu_count() or 1)
     step = cpu_step_builder(n_frames)
@@ -476,12 +508,20 @@ def run_ours(args):
                    for k, v in sorted(table.items(), key=lambda kv: -kv[1]["ms"])}
         n_cpu = 64
         cpu_fps, cpu_t, cores = time_cpu(n_cpu, 3, 1)
+        if training is not None:
+            n_cpu_t = 32
+            tfps, tt, tcores = time_cpu_training(n_cpu_t)
+            training["cpu_baseline"] = {"value": tfps, "unit": "frames/s", "cores": tcores, "kind": "port",
+                                        "sample": f"{n_cpu_t} frames: torch CPU autograd through the oracle port (ListGlow.log_prob "
+                                                  f"config J + 1 ConvLSTM step, forward + backward, no optimizer), median of 2 "
+                                                  f"after 1 warm-up ({tt:.2f} s each)"}
         out = {
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": "rfn_J_hotpath_fwd",
-                       "pass": "forward (density evaluation): 19 ConvLSTM steps + ListGlow.log_prob on 570 frames; no backward yet",
+                       "pass": "forward (density evaluation): 19 ConvLSTM steps + ListGlow.log_prob on 570 frames; the training step "
+                               "(forward + hand-written backward + all-reduce + Adam) is reported under `training`",
                        "frames_per_step_per_gpu": n_frames, "sequences_per_gpu": B, "L": J["L"], "K": J["K"],
                        "hidden": J["hidden"], "conv_dtype": "bf16 in / fp32 accumulate", "flow_dtype": "f32",
                        "l2": "inputs_exceed_L2 (>=300 MB of activations per level-1 GlowStep vs 126 MB L2)",
