@@ -309,3 +309,81 @@ def test_convlstm_grads_vs_oracle(rf, B, T, C, H, W, hc, state):
     (h_r2.sum() + (c_r2 * g_c).sum()).backward()
     assert rel(xs2.grad, leaves2[0].grad) < 3e-2
     assert rel(conv.weight.grad, leaves2[1].grad) < 3e-2
+
+
+def test_directional_derivative_at_rfn_scale(rf):
+    """Size-independent check of the whole backward at a shape the CPU oracle cannot differentiate in seconds (config J
+    proportions: L=5, K=3, hidden 256, 1x64x64, 24 frames, learned prior): the loss change along the normalised gradient
+    direction, (L(theta + eps d) - L(theta - eps d)) / (2 eps), must equal |grad| (central difference)."""
+    B = 24
+    a = types.SimpleNamespace(**dict(ARGS, n_units_affine=256, n_units_prior=256, L=5, K=3))
+    cond_ch = [16, 32, 64, 128, 256]
+    cond_sizes = [[B, c, 32 >> l, 32 >> l] for l, c in enumerate(cond_ch)]
+    torch.manual_seed(11)
+    m = rf.ListGlow([B, 1, 64, 64], cond_sizes, [B, 256, 2, 2], a).train()
+    perturb(m, 11, ws=0.01, ps=0.05)
+    m = m.cuda()
+    g = torch.Generator().manual_seed(12)
+    x = (torch.floor(torch.rand(B, 1, 64, 64, generator=g) * 256) / 256 - 0.5).cuda()
+    noise = (torch.rand(B, 1, 64, 64, generator=g) / 256).cuda()
+    conds = [torch.randn(*s, generator=g).cuda() for s in cond_sizes]
+    base = torch.randn(B, 256, 2, 2, generator=g).cuda()
+
+    def loss_of():
+        _, nll = m.log_prob(x, conds, base, logdet=0, noise=noise)
+        return nll.mean() / (math.log(2) * 4096)
+
+    loss0 = loss_of()
+    loss0.backward()
+    params = [p for p in m.parameters() if p.grad is not None]
+    gnorm = math.sqrt(sum(float((p.grad.double() ** 2).sum()) for p in params))
+    assert math.isfinite(gnorm) and gnorm > 0
+    direction = [p.grad / gnorm for p in params]
+    ratios = []
+    for frac in (0.003, 0.01):
+        eps = frac * abs(float(loss0.detach())) / gnorm
+        vals = []
+        for sign in (1.0, -1.0):
+            with torch.no_grad():
+                for p, d in zip(params, direction):
+                    p.add_(d, alpha=sign * eps)
+            vals.append(float(loss_of().detach()))     # the training-mode forward (same kernels as the taped pass)
+            with torch.no_grad():
+                for p, d in zip(params, direction):
+                    p.add_(d, alpha=-sign * eps)
+        ratios.append((vals[0] - vals[1]) / (2 * eps) / gnorm)
+    assert any(abs(r - 1.0) < 0.08 for r in ratios), (ratios, float(loss0.detach()), gnorm)
+
+
+def test_convlstm_directional_derivative_cfg2_shape(rf):
+    """BASELINE config 2 proportions (64 -> 64 channels, 3x3, 64x64 maps; batch 8, 4 steps): central difference along the
+    normalised gradient of (weight, bias, input) equals the gradient norm."""
+    torch.manual_seed(3)
+    m = rf.ConvLSTM(64, 64, [3, 3]).cuda().train()
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(8, 4, 64, 64, 64, generator=g).cuda().requires_grad_()
+    tgt = torch.randn(8, 4, 64, 64, 64, generator=g).cuda()
+
+    def loss_of():
+        out, h, c = m(x)
+        return ((out - tgt) ** 2).mean() + c.mean()
+
+    loss0 = loss_of()
+    loss0.backward()
+    params = [m.LSTMlayer.conv[0].weight, m.LSTMlayer.conv[0].bias, x]
+    gnorm = math.sqrt(sum(float((p.grad.double() ** 2).sum()) for p in params))
+    direction = [p.grad / gnorm for p in params]
+    ratios = []
+    for frac in (0.003, 0.01):
+        eps = frac * abs(float(loss0.detach())) / gnorm
+        vals = []
+        for sign in (1.0, -1.0):
+            with torch.no_grad():
+                for p, d in zip(params, direction):
+                    p.add_(d, alpha=sign * eps)
+            vals.append(float(loss_of().detach()))
+            with torch.no_grad():
+                for p, d in zip(params, direction):
+                    p.add_(d, alpha=-sign * eps)
+        ratios.append((vals[0] - vals[1]) / (2 * eps) / gnorm)
+    assert any(abs(r - 1.0) < 0.05 for r in ratios), (ratios, float(loss0.detach()), gnorm)
