@@ -263,7 +263,8 @@ def test_graphed_train_step_matches_eager(rf):
 
 
 @pytest.mark.parametrize("B,T,C,H,W,hc,state", [(3, 4, 5, 6, 6, 8, False), (2, 3, 16, 8, 8, 32, True),
-                                                 (4, 2, 512, 2, 2, 200, True), (2, 1, 64, 16, 16, 64, False)])
+                                                 (4, 2, 512, 2, 2, 200, True), (2, 1, 64, 16, 16, 64, False),
+                                                 (2, 2, 256, 8, 8, 60, True)])   # last: SRNN/VRNN shape (h_dim 60 on 8x8 maps)
 def test_convlstm_grads_vs_oracle(rf, B, T, C, H, W, hc, state):
     """ConvLSTM under autograd (saved pre-activations + hand-written BPTT) vs torch autograd through the oracle, with the
     oracle's conv operands rounded to bf16 where the CUDA path rounds them."""
