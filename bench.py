@@ -204,6 +204,7 @@ class KernelTimer:
 
     def __init__(self):
         self.rec = []
+        self.elementwise = {}
 
     @contextlib.contextmanager
     def __call__(self, name, meta):
@@ -221,6 +222,13 @@ class KernelTimer:
             d = agg.setdefault(name, {"launches": 0, "ms": 0.0, "flops": 0.0, "flops_padded": 0.0})
             d["launches"] += 1
             d["ms"] += ms
+            if meta and "flops" not in meta:   # bandwidth-bound kernel: algorithmic bytes only; keep its largest launch
+                e = self.elementwise.setdefault(name, {})
+                k = meta["bytes"]
+                ee = e.setdefault(k, {"launches": 0, "ms": 0.0})
+                ee["launches"] += 1
+                ee["ms"] += ms
+                continue
             if meta:
                 d["flops"] += meta["flops"]
                 d["flops_padded"] += meta["flops_padded"]
@@ -232,6 +240,76 @@ class KernelTimer:
                 sdict["bytes"] += meta["bytes"]
         self.shapes = shapes
         return agg
+
+
+def elementwise_at_scale(dev, hbm_peak):
+    """Achieved algorithmic GB/s of the bandwidth-bound kernels on tensors larger than the 126 MB L2 (the flow tensors of
+    config J are only 9 MB per level, so inside the workload these kernels are launch-latency-bound, not HBM-bound)."""
+    import recurrent_flows_msc_b200 as rf
+    ops = rf.ops
+    out = []
+
+    def timeit(name, nbytes, fn, iters=5):
+        for _ in range(2):
+            fn()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(iters):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        us = 1e3 * a.elapsed_time(b) / iters
+        out.append({"kernel": name, "algorithmic_mb": round(nbytes / 1e6, 1), "us": round(us, 1),
+                    "gbs": round(nbytes / us / 1e3, 1), "hbm_frac": round(nbytes / us / 1e3 / hbm_peak, 3)})
+
+    B, C, H, W = 64, 48, 128, 128
+    x = torch.randn(B, C, H, W, device=dev)
+    n = x.numel()
+    bias, logs = torch.randn(1, C, 1, 1, device=dev) * 0.1, torch.randn(1, C, 1, 1, device=dev) * 0.1
+    timeit("rfk_squeeze2d", 8.0 * n, lambda: ops.squeeze2d(x, False))
+    timeit("rfk_actnorm", 8.0 * n, lambda: ops.actnorm(x, bias, logs, False))
+    for Cm in (4, 12, 48):   # the 1x1 mix runs on the fp32 pipes: HBM-bound only while 2*C flop/element stays under the ridge
+        xm = x.view(B * C // Cm, Cm, H, W)
+        Wm, bv = torch.randn(Cm, Cm, device=dev) / Cm ** 0.5, torch.randn(Cm, device=dev)
+        timeit(f"rfk_mix1x1 (ActNorm+InvConv, C={Cm})", 8.0 * n, lambda: ops.mix1x1(xm, Wm, bv))
+    nh = torch.empty(B, H, W, 64, device=dev, dtype=torch.bfloat16)
+    timeit("rfk_pack_nhwc_bf16", 6.0 * n, lambda: ops.pack_nhwc(x, 0, C, nh, 0))
+    ld = torch.zeros(B, device=dev)
+    timeit("rfk_gauss_logp", 4.0 * n, lambda: ops.gauss_logp(x, 0, None, C, ops.PAIR_SPLIT, "exp", ld))
+    del nh
+    Bt, Ct = 16, 24
+    taps = torch.randn(Bt, 9 * Ct, H, W, device=dev) * 0.1
+    z = torch.randn(Bt, Ct, H, W, device=dev)
+    sc, sh = torch.rand(Ct, device=dev) + 0.5, torch.randn(Ct, device=dev) * 0.1
+    cs, csh = torch.randn(Ct // 2, device=dev) * 0.3, torch.randn(Ct // 2, device=dev) * 0.1
+    ldt = torch.zeros(Bt, device=dev)
+    timeit("rfk_coupling_tail_taps", 4.0 * taps.numel() + 4.0 * z.numel(),
+           lambda: ops.coupling_tail_taps(taps, z, sc, sh, "realnvp", cs, csh, ldt, False))
+    dz, gl = torch.randn_like(z), torch.randn(Bt, device=dev)
+    timeit("rfk_coupling_taps_bwd", 4.0 * taps.numel() + 4.0 * z.numel() * 2.5,
+           lambda: ops.coupling_taps_bwd(taps, z, dz, sc, sh, "realnvp", cs, csh, gl, 3.0))
+    del taps, z, dz
+    Hc = 64
+    cc = torch.randn(32, 4 * Hc, 64, 64, device=dev)
+    cp = torch.randn(32, Hc, 64, 64, device=dev)
+    timeit("rfk_convlstm_pointwise", 4.0 * cp.numel() * 7, lambda: ops.convlstm_pointwise(cc, cp, None))
+    dhh = torch.randn(32, Hc, 64, 64, device=dev)
+    timeit("rfk_convlstm_pointwise_bwd", 4.0 * cp.numel() * 11, lambda: ops.convlstm_pointwise_bwd(cc, cp, None, dhh, None, None))
+    del cc, cp, dhh
+    rows = 583680
+    dh = torch.randn(rows, 256, device=dev).to(torch.bfloat16)
+    hh = torch.randn(rows, 256, device=dev).to(torch.bfloat16)
+    s256 = torch.rand(256, device=dev) + 0.5
+    timeit("rfk_act_affine_bwd", 6.0 * rows * 256, lambda: ops.act_affine_bwd(dh, hh, 256, s256, "relu"))
+    del dh, hh
+    npar = 1 << 26
+    p4 = [torch.zeros(npar, device=dev) for _ in range(4)]
+    st = torch.ones(1, device=dev)
+    timeit("rfk_adam_step", 28.0 * npar,
+           lambda: rf._lib.call("rfk_adam_step", p4[0].data_ptr(), p4[1].data_ptr(), p4[2].data_ptr(), p4[3].data_ptr(), npar,
+                                1e-3, 0.9, 0.999, 1e-8, 1.0, st.data_ptr(), ops._stream()))
+    return out
 
 
 def run_ours(args):
@@ -503,6 +581,18 @@ def run_ours(args):
                     "by_shape": by_shape,
                     "note": "per-launch figures from CUDA events on the launching stream in an instrumented extra step; "
                             "algorithmic bytes = activations in + out + weights"}
+        # bandwidth-bound kernels: achieved algorithmic GB/s of each kernel's LARGEST launch shape (level 1) vs the HBM peak
+        elementwise = []
+        for name, by_bytes in kt.elementwise.items():
+            nbytes = max(by_bytes)
+            v = by_bytes[nbytes]
+            us = 1e3 * v["ms"] / v["launches"]
+            elementwise.append({"kernel": name, "algorithmic_bytes_per_launch": nbytes, "launches": v["launches"],
+                                "avg_us": round(us, 1), "gbs": round(nbytes / us / 1e3, 1),
+                                "hbm_frac": round(nbytes / us / 1e3 / hbm_peak, 3)})
+        elementwise.sort(key=lambda e: -e["algorithmic_bytes_per_launch"])
+        roofline["elementwise_in_workload_largest_shape"] = elementwise
+        roofline["elementwise_at_scale"] = elementwise_at_scale(dev, hbm_peak)
         kernels = {k: {"launches": v["launches"], "ms": round(v["ms"], 4),
                        "tflops": round(v["flops"] / (v["ms"] / 1e3) / 1e12, 1) if v["flops"] else None}
                    for k, v in sorted(table.items(), key=lambda kv: -kv[1]["ms"])}

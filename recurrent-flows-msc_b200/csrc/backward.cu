@@ -291,6 +291,101 @@ __global__ void __launch_bounds__(256) coupling_taps_bwd_kernel(const float* __r
   }
 }
 
+// Same, four consecutive pixels of a row per thread (W % 4 == 0, 16-byte aligned tensors): per tap plane one 128-bit load
+// plus, for the horizontally shifted taps, one scalar edge element (the layout of coupling_taps_v4_kernel).
+__global__ void __launch_bounds__(256) coupling_taps_bwd_v4_kernel(const float* __restrict__ taps, const float* __restrict__ z_out,
+                                                                   float* __restrict__ dz, float* __restrict__ dsum, int B, int C,
+                                                                   int H, int W, const float* __restrict__ scale,
+                                                                   const float* __restrict__ shift, int clamp_type,
+                                                                   const float* __restrict__ cs, const float* __restrict__ csh,
+                                                                   const float* __restrict__ g_ld, float* __restrict__ d_scale,
+                                                                   float* __restrict__ d_shift, float* __restrict__ d_cs,
+                                                                   float* __restrict__ d_csh, float logs_factor) {
+  pdl_trigger();
+  pdl_wait();
+  __shared__ float sh[32];
+  const int j = blockIdx.y, half = C >> 1, HW = H * W, W4 = W >> 2, HW4 = H * W4;
+  const float sc_s = scale[2 * j], sc_r = scale[2 * j + 1], sh_r = shift[2 * j + 1];
+  float a = 0.0f, bb = 0.0f;
+  if (clamp_type == RFK_CLAMP_REALNVP) { a = cs[j]; bb = csh[j]; }
+  float acc[6] = {0, 0, 0, 0, 0, 0};
+  const long long n = (long long)B * HW4;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(idx / HW4), q = (int)(idx - (long long)b * HW4);
+    const int y = q / W4, x = (q - y * W4) << 2;
+    const float* tb = taps + (long long)b * 9 * C * HW;
+    float S[4] = {0, 0, 0, 0}, R[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int yy = y + ky - 1;
+      if (yy < 0 || yy >= H) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const float* qq0 = tb + ((long long)((3 * ky + kx) * C + 2 * j) * HW) + yy * W + x;
+#pragma unroll
+        for (int pr = 0; pr < 2; ++pr) {
+          const float* qq = qq0 + pr * HW;
+          const float4 c4 = __ldg(reinterpret_cast<const float4*>(qq));
+          float v0, v1, v2, v3;
+          if (kx == 1) { v0 = c4.x; v1 = c4.y; v2 = c4.z; v3 = c4.w; }
+          else if (kx == 0) { v0 = x > 0 ? __ldg(qq - 1) : 0.0f; v1 = c4.x; v2 = c4.y; v3 = c4.z; }
+          else { v0 = c4.y; v1 = c4.z; v2 = c4.w; v3 = x + 4 < W ? __ldg(qq + 4) : 0.0f; }
+          float* dst = pr ? R : S;
+          dst[0] += v0; dst[1] += v1; dst[2] += v2; dst[3] += v3;
+        }
+      }
+    }
+    const long long off = ((long long)b * C + half + j) * HW + y * W + x;
+    const float4 zo4 = ld_stream(reinterpret_cast<const float4*>(z_out + off));
+    const float4 dz4 = *reinterpret_cast<const float4*>(dz + off);
+    const float zo[4] = {zo4.x, zo4.y, zo4.z, zo4.w}, dzo[4] = {dz4.x, dz4.y, dz4.z, dz4.w};
+    const float gl = g_ld ? g_ld[b] : 0.0f;
+    float o_dz[4], o_s[4], o_r[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float raw = fmaf(R[k], sc_r, sh_r);
+      float ls, dclamp, th = 0.0f;
+      switch (clamp_type) {
+        case RFK_CLAMP_REALNVP: th = tanhf(raw); ls = a * th + bb; dclamp = a * (1.0f - th * th); break;
+        case RFK_CLAMP_GLOW: { const float t = -(raw + 2.0f); ls = -(t > 15.0f ? t : log1pf(expf(t))); dclamp = 1.0f / (1.0f + expf(raw + 2.0f)); break; }
+        case RFK_CLAMP_SOFT: { const float u = raw * (1.0f / 2.5f); ls = 2.5f * 0.636f * atanf(u); dclamp = 0.636f / (1.0f + u * u); break; }
+        default: ls = raw; dclamp = 1.0f;
+      }
+      const float e = expf(ls);
+      const float dls = dzo[k] * zo[k] + gl;
+      const float dt = dzo[k] * e;
+      const float draw = dls * dclamp;
+      o_dz[k] = dt; o_s[k] = dt * sc_s; o_r[k] = draw * sc_r;
+      acc[0] += dt * S[k]; acc[1] += dt; acc[2] += draw * R[k]; acc[3] += draw; acc[4] += dls * th; acc[5] += dls;
+    }
+    *reinterpret_cast<float4*>(dz + off) = make_float4(o_dz[0], o_dz[1], o_dz[2], o_dz[3]);
+    const long long so = ((long long)b * C + 2 * j) * HW + y * W + x;
+    st_stream(reinterpret_cast<float4*>(dsum + so), make_float4(o_s[0], o_s[1], o_s[2], o_s[3]));
+    st_stream(reinterpret_cast<float4*>(dsum + so + HW), make_float4(o_r[0], o_r[1], o_r[2], o_r[3]));
+  }
+  float red[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) red[k] = block_sum_256(acc[k], sh);
+  if (threadIdx.x == 0) {
+    if (logs_factor != 0.0f) {
+      const float sh_s = shift[2 * j];
+      atomicAdd(d_scale + 2 * j, logs_factor * (red[0] * sc_s + red[1] * sh_s));
+      atomicAdd(d_shift + 2 * j, red[1] * sc_s);
+      atomicAdd(d_scale + 2 * j + 1, logs_factor * (red[2] * sc_r + red[3] * sh_r));
+      atomicAdd(d_shift + 2 * j + 1, red[3] * sc_r);
+    } else {
+      atomicAdd(d_scale + 2 * j, red[0]);
+      atomicAdd(d_shift + 2 * j, red[1]);
+      atomicAdd(d_scale + 2 * j + 1, red[2]);
+      atomicAdd(d_shift + 2 * j + 1, red[3]);
+    }
+    if (clamp_type == RFK_CLAMP_REALNVP) {
+      atomicAdd(d_cs + j, red[4]);
+      atomicAdd(d_csh + j, red[5]);
+    }
+  }
+}
+
 // Gradient w.r.t. the nine tap planes, written directly as the NHWC bf16 operand of the tap GEMM's backward:
 //   dtaps[p, t*C + c] = dsum[c](p - off(t))  (zero when that pixel is outside the image)
 __global__ void __launch_bounds__(256) taps_scatter_kernel(const float* __restrict__ dsum, __nv_bfloat16* __restrict__ dtaps,
@@ -479,8 +574,15 @@ extern "C" int rfk_coupling_taps_bwd(const float* taps, const float* z_out, floa
   RFK_REQUIRE(clamp_type != RFK_CLAMP_REALNVP || (clamp_scale && clamp_shift && d_clamp_scale && d_clamp_shift),
               "rfk_coupling_taps_bwd: realnvp clamp needs scale/scale_shift and their gradient buffers");
   RFK_REQUIRE(B <= 65535 && C / 2 <= 65535, "rfk_coupling_taps_bwd: B or C too large for the grid");
-  int chunks = ceil_div((long long)B * H * W, 256);
   const int cap = std::max(1, ceil_div((long long)sm_count() * 8, C / 2));
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  if (W % 4 == 0 && al16(taps) && al16(z_out) && al16(dz) && al16(dsum)) {
+    const int chunks4 = std::min(cap, ceil_div((long long)B * H * W / 4, 256));
+    RFK_LAUNCH(coupling_taps_bwd_v4_kernel, dim3(chunks4, C / 2), 256, 0, (cudaStream_t)stream, taps, z_out, dz, dsum, B, C, H, W,
+               scale, shift, clamp_type, clamp_scale, clamp_shift, g_ld, d_scale, d_shift, d_clamp_scale, d_clamp_shift, logs_factor);
+    return check_launch("rfk_coupling_taps_bwd");
+  }
+  int chunks = ceil_div((long long)B * H * W, 256);
   if (chunks > cap) chunks = cap;
   RFK_LAUNCH(coupling_taps_bwd_kernel, dim3(chunks, C / 2), 256, 0, (cudaStream_t)stream, taps, z_out, dz, dsum, B, C, H, W,
              scale, shift, clamp_type, clamp_scale, clamp_shift, g_ld, d_scale, d_shift, d_clamp_scale, d_clamp_shift, logs_factor);
@@ -646,6 +748,24 @@ extern "C" int rfk_adam_step(float* p, const float* g, float* m, float* v, long 
 namespace rfk {
 __device__ __forceinline__ float sigm(float x) { return 1.0f / (1.0f + __expf(-x)); }
 
+struct LstmBwdOut { float dai, daf, dao, dag, dcp; };
+__device__ __forceinline__ LstmBwdOut lstm_point_bwd(float ai, float af, float ao, float ag, float cp, float wi, float wf,
+                                                     float wo, float dhv, float dci) {
+  const float i = sigm(ai + wi * cp), f = sigm(af + wf * cp), g = tanhf(ag);
+  const float c = f * cp + i * g;
+  const float o = sigm(ao + wo * c), tc = tanhf(c);
+  LstmBwdOut r;
+  r.dao = dhv * tc * o * (1.0f - o);
+  const float dct = dci + dhv * o * (1.0f - tc * tc) + r.dao * wo;
+  r.dai = dct * g * i * (1.0f - i);
+  r.daf = dct * cp * f * (1.0f - f);
+  r.dag = dct * i * (1.0f - g * g);
+  r.dcp = dct * f + r.dai * wi + r.daf * wf;
+  return r;
+}
+
+// kVec: HW % 4 == 0 and 16-byte aligned tensors -> four consecutive positions per thread, 128-bit accesses
+template <bool kVec>
 __global__ void __launch_bounds__(256) lstm_pointwise_bwd_kernel(const float* __restrict__ cc, const float* __restrict__ c_prev,
                                                                  const float* __restrict__ peep, const float* __restrict__ dh,
                                                                  long long dh_bs, const float* __restrict__ dc_in,
@@ -655,30 +775,52 @@ __global__ void __launch_bounds__(256) lstm_pointwise_bwd_kernel(const float* __
   pdl_wait();
   __shared__ float sh[32];
   const int ch = blockIdx.y;
-  const long long per = (long long)Hc * HW, n = (long long)B * HW;
+  const long long per = (long long)Hc * HW;
+  constexpr int V = kVec ? 4 : 1;
+  const int HWv = HW / V;
+  const long long n = (long long)B * HWv;
   float acc[4] = {0, 0, 0, 0};
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
-    const long long b = idx / HW;
-    const int p = (int)(idx % HW);
+    const long long b = idx / HWv;
+    const int p = (int)(idx - b * HWv) * V;
     const long long r = (long long)ch * HW + p, e = b * per + r;
     const float* g0 = cc + b * 4 * per + r;
-    const float ai = g0[0], af = g0[per], ao = g0[2 * per], ag = g0[3 * per];
-    const float cp = c_prev ? c_prev[e] : 0.0f;
-    float wi = 0.0f, wf = 0.0f, wo = 0.0f;
-    if (peep) { wi = peep[r]; wf = peep[per + r]; wo = peep[2 * per + r]; }
-    const float i = sigm(ai + wi * cp), f = sigm(af + wf * cp), g = tanhf(ag);
-    const float c = f * cp + i * g;
-    const float o = sigm(ao + wo * c), tc = tanhf(c);
-    const float dhv = dh[b * dh_bs + r];
-    const float dao = dhv * tc * o * (1.0f - o);
-    const float dct = (dc_in ? dc_in[e] : 0.0f) + dhv * o * (1.0f - tc * tc) + dao * wo;
-    const float dai = dct * g * i * (1.0f - i);
-    const float daf = dct * cp * f * (1.0f - f);
-    const float dag = dct * i * (1.0f - g * g);
     float* d0 = dcc + b * 4 * per + r;
-    d0[0] = dai; d0[per] = daf; d0[2 * per] = dao; d0[3 * per] = dag;
-    dc_prev[e] = dct * f + dai * wi + daf * wf;
-    acc[0] += dai; acc[1] += daf; acc[2] += dao; acc[3] += dag;
+    if (kVec) {
+      const float4 ai = ld_stream(reinterpret_cast<const float4*>(g0)), af = ld_stream(reinterpret_cast<const float4*>(g0 + per));
+      const float4 ao = ld_stream(reinterpret_cast<const float4*>(g0 + 2 * per)), ag = ld_stream(reinterpret_cast<const float4*>(g0 + 3 * per));
+      const float4 z4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      const float4 cp = c_prev ? ld_stream(reinterpret_cast<const float4*>(c_prev + e)) : z4;
+      const float4 dci = dc_in ? ld_stream(reinterpret_cast<const float4*>(dc_in + e)) : z4;
+      const float4 dhv = ld_stream(reinterpret_cast<const float4*>(dh + b * dh_bs + r));
+      float4 wi = z4, wf = z4, wo = z4;
+      if (peep) {
+        wi = *reinterpret_cast<const float4*>(peep + r);
+        wf = *reinterpret_cast<const float4*>(peep + per + r);
+        wo = *reinterpret_cast<const float4*>(peep + 2 * per + r);
+      }
+      const LstmBwdOut o0 = lstm_point_bwd(ai.x, af.x, ao.x, ag.x, cp.x, wi.x, wf.x, wo.x, dhv.x, dci.x);
+      const LstmBwdOut o1 = lstm_point_bwd(ai.y, af.y, ao.y, ag.y, cp.y, wi.y, wf.y, wo.y, dhv.y, dci.y);
+      const LstmBwdOut o2 = lstm_point_bwd(ai.z, af.z, ao.z, ag.z, cp.z, wi.z, wf.z, wo.z, dhv.z, dci.z);
+      const LstmBwdOut o3 = lstm_point_bwd(ai.w, af.w, ao.w, ag.w, cp.w, wi.w, wf.w, wo.w, dhv.w, dci.w);
+      st_stream(reinterpret_cast<float4*>(d0), make_float4(o0.dai, o1.dai, o2.dai, o3.dai));
+      st_stream(reinterpret_cast<float4*>(d0 + per), make_float4(o0.daf, o1.daf, o2.daf, o3.daf));
+      st_stream(reinterpret_cast<float4*>(d0 + 2 * per), make_float4(o0.dao, o1.dao, o2.dao, o3.dao));
+      st_stream(reinterpret_cast<float4*>(d0 + 3 * per), make_float4(o0.dag, o1.dag, o2.dag, o3.dag));
+      st_stream(reinterpret_cast<float4*>(dc_prev + e), make_float4(o0.dcp, o1.dcp, o2.dcp, o3.dcp));
+      acc[0] += (o0.dai + o1.dai) + (o2.dai + o3.dai);
+      acc[1] += (o0.daf + o1.daf) + (o2.daf + o3.daf);
+      acc[2] += (o0.dao + o1.dao) + (o2.dao + o3.dao);
+      acc[3] += (o0.dag + o1.dag) + (o2.dag + o3.dag);
+    } else {
+      float wi = 0.0f, wf = 0.0f, wo = 0.0f;
+      if (peep) { wi = peep[r]; wf = peep[per + r]; wo = peep[2 * per + r]; }
+      const LstmBwdOut o = lstm_point_bwd(g0[0], g0[per], g0[2 * per], g0[3 * per], c_prev ? c_prev[e] : 0.0f, wi, wf, wo,
+                                          dh[b * dh_bs + r], dc_in ? dc_in[e] : 0.0f);
+      d0[0] = o.dai; d0[per] = o.daf; d0[2 * per] = o.dao; d0[3 * per] = o.dag;
+      dc_prev[e] = o.dcp;
+      acc[0] += o.dai; acc[1] += o.daf; acc[2] += o.dao; acc[3] += o.dag;
+    }
   }
   if (dbias) {
 #pragma unroll
@@ -696,10 +838,17 @@ extern "C" int rfk_convlstm_pointwise_bwd(const float* cc, const float* c_prev, 
   using namespace rfk;
   RFK_REQUIRE(cc && dh && dcc && dc_prev && B > 0 && Hc > 0 && HW > 0 && Hc <= 65535,
               "rfk_convlstm_pointwise_bwd: null pointer or bad shape");
-  int chunks = ceil_div((long long)B * HW, 256);
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  const bool vec = HW % 4 == 0 && dh_bstride % 4 == 0 && al16(cc) && al16(dh) && al16(dcc) && al16(dc_prev) &&
+                   (!c_prev || al16(c_prev)) && (!dc_in || al16(dc_in)) && (!peep || al16(peep));
+  int chunks = ceil_div((long long)B * HW / (vec ? 4 : 1), 256);
   const int cap = std::max(1, ceil_div((long long)sm_count() * 8, Hc));
   if (chunks > cap) chunks = cap;
-  RFK_LAUNCH(lstm_pointwise_bwd_kernel, dim3(chunks, Hc), 256, 0, (cudaStream_t)stream, cc, c_prev, peep, dh, dh_bstride, dc_in,
-             dcc, dc_prev, dbias, B, Hc, HW);
+  if (vec)
+    RFK_LAUNCH((lstm_pointwise_bwd_kernel<true>), dim3(chunks, Hc), 256, 0, (cudaStream_t)stream, cc, c_prev, peep, dh, dh_bstride,
+               dc_in, dcc, dc_prev, dbias, B, Hc, HW);
+  else
+    RFK_LAUNCH((lstm_pointwise_bwd_kernel<false>), dim3(chunks, Hc), 256, 0, (cudaStream_t)stream, cc, c_prev, peep, dh, dh_bstride,
+               dc_in, dcc, dc_prev, dbias, B, Hc, HW);
   return check_launch("rfk_convlstm_pointwise_bwd");
 }

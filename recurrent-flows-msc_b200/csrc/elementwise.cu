@@ -338,6 +338,56 @@ __global__ void __launch_bounds__(kThreads) pack_nhwc_kernel(const float* __rest
   }
 }
 
+// Same, through a shared-memory transpose: a CTA takes 64 consecutive pixels x up to 64 channels (blockIdx.y = channel
+// chunk); reads are coalesced along the pixels of each channel plane, writes are coalesced along the channels of each
+// pixel row (a warp writes whole 128-byte rows instead of thirty-two 16-byte pieces of different rows).
+constexpr int PK_PIX = 128;
+__global__ void __launch_bounds__(256) pack_nhwc_tiled_kernel(const float* __restrict__ src, long long src_bs, int HW, int c_lo,
+                                                              int n, __nv_bfloat16* __restrict__ dst, int dst_off, int dst_ld,
+                                                              long long npix, int vec4) {
+  pdl_trigger();
+  pdl_wait();
+  __shared__ float tile[64][PK_PIX + 1];
+  const int c0 = blockIdx.y * 64, nc = min(64, n - c0), G = nc >> 3;   // nc is a multiple of 8 on this path
+  for (long long g0 = (long long)blockIdx.x * PK_PIX; g0 < npix; g0 += (long long)gridDim.x * PK_PIX) {
+    const long long b0 = g0 / HW;             // one 64-bit division per tile; the rest is 32-bit
+    const int p0 = (int)(g0 - b0 * HW);
+    const int valid = (int)min((long long)PK_PIX, npix - g0);
+    if (vec4) {   // HW % 4 == 0: four consecutive pixels of a plane never straddle a sample, 128-bit loads
+      for (int e = threadIdx.x; e < nc * (PK_PIX / 4); e += blockDim.x) {
+        const int c = e / (PK_PIX / 4), pl = (e - c * (PK_PIX / 4)) * 4;
+        float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (pl < valid) {
+          const int t = p0 + pl, bq = t / HW;
+          v = ld_stream(reinterpret_cast<const float4*>(src + (b0 + bq) * src_bs + (long long)(c_lo + c0 + c) * HW + (t - bq * HW)));
+        }
+        tile[c][pl] = v.x; tile[c][pl + 1] = v.y; tile[c][pl + 2] = v.z; tile[c][pl + 3] = v.w;
+      }
+    } else {
+      for (int e = threadIdx.x; e < nc * PK_PIX; e += blockDim.x) {
+        const int c = e / PK_PIX, pl = e - c * PK_PIX;
+        float v = 0.0f;
+        if (pl < valid) {
+          const int t = p0 + pl, bq = t / HW;
+          v = __ldg(src + (b0 + bq) * src_bs + (long long)(c_lo + c0 + c) * HW + (t - bq * HW));
+        }
+        tile[c][pl] = v;
+      }
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < PK_PIX * G; e += blockDim.x) {
+      const int pl = e / G, gq = e - pl * G;
+      if (pl < valid) {
+        __nv_bfloat162 h[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) h[k] = __floats2bfloat162_rn(tile[8 * gq + 2 * k][pl], tile[8 * gq + 2 * k + 1][pl]);
+        *reinterpret_cast<uint4*>(dst + (g0 + pl) * dst_ld + dst_off + c0 + 8 * gq) = *reinterpret_cast<uint4*>(h);
+      }
+    }
+    __syncthreads();
+  }
+}
+
 template <bool kVec>
 __global__ void __launch_bounds__(kThreads) copy_channels_kernel(const float* __restrict__ src, int src_C,
                                                                  int src_off, float* __restrict__ dst, int dst_C,
@@ -560,6 +610,43 @@ __global__ void __launch_bounds__(kThreads) gauss_logp_kernel(const float* __res
   cta_atomic_add(acc, logdet + b, sh);
 }
 
+// 128-bit variant (HW % 4 == 0, 16-byte aligned planes): four consecutive positions of one channel per thread, 32-bit
+// index arithmetic, no division in the density itself.
+__global__ void __launch_bounds__(kThreads) gauss_logp_v4_kernel(const float* __restrict__ z, int z_C, int z_off,
+                                                                 const float* __restrict__ params, int n, int HW,
+                                                                 int pairing, int std_kind, float* __restrict__ logdet) {
+  pdl_trigger();
+  pdl_wait();
+  __shared__ float sh[32];
+  const int b = blockIdx.y;
+  const int per4 = (int)(((long long)n * HW) >> 2), HW4 = HW >> 2;
+  const float4* zb = reinterpret_cast<const float4*>(z + ((long long)b * z_C + z_off) * HW);
+  const float4* pb = params ? reinterpret_cast<const float4*>(params + (long long)b * 2 * n * HW) : nullptr;
+  float acc = 0.0f;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < per4; t += gridDim.x * blockDim.x) {
+    const float4 zv = ld_stream(zb + t);
+    if (!pb) {   // N(0, 1)
+      acc += -0.5f * (zv.x * zv.x + zv.y * zv.y + zv.z * zv.z + zv.w * zv.w) - 4.0f * 0.91893853320467274178f;
+      continue;
+    }
+    const int j = t / HW4, p4 = t - j * HW4;
+    const int cm = pairing == RFK_PAIR_CROSS ? 2 * j : j, cr = pairing == RFK_PAIR_CROSS ? 2 * j + 1 : n + j;
+    const float4 mv = ld_stream(pb + (long long)cm * HW4 + p4), rv = ld_stream(pb + (long long)cr * HW4 + p4);
+    const float zz[4] = {zv.x, zv.y, zv.z, zv.w}, mm[4] = {mv.x, mv.y, mv.z, mv.w}, rr[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float d = zz[k] - mm[k];
+      if (std_kind == RFK_STD_EXP) {   // log(std) = raw, 1/std^2 = exp(-2 raw)
+        acc += -0.5f * d * d * expf(-2.0f * rr[k]) - rr[k] - 0.91893853320467274178f;
+      } else {
+        const float sd = std_from_raw(rr[k], std_kind), inv = 1.0f / sd;
+        acc += -0.5f * d * d * inv * inv - logf(sd) - 0.91893853320467274178f;
+      }
+    }
+  }
+  cta_atomic_add(acc, logdet + b, sh);
+}
+
 __global__ void __launch_bounds__(kThreads) gauss_sample_kernel(const float* __restrict__ eps,
                                                                 const float* __restrict__ params, int n, int HW,
                                                                 int pairing, int std_kind, float temperature,
@@ -728,7 +815,7 @@ __global__ void add_scalar_kernel(float* __restrict__ logdet, const float* __res
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-// Small channel counts (C <= 8): no shared memory, one thread per 4 consecutive pixels, x and y in registers.
+// Small channel counts (C <= 16): no shared-memory staging, one thread per 4 consecutive pixels, x and y in registers.
 template <int CT>
 __global__ void __launch_bounds__(kThreads) mix1x1_small_kernel(const float* __restrict__ x, float* __restrict__ y,
                                                                 const float* __restrict__ Wm,
@@ -762,7 +849,7 @@ __global__ void __launch_bounds__(kThreads) mix1x1_small_kernel(const float* __r
     for (int i = 0; i < CT; ++i) xi[i] = i < C ? ld_stream(reinterpret_cast<const float4*>(xp + (long long)i * HW)) : make_float4(0, 0, 0, 0);
     float* yp = y + b * C * HW + p;
     const long long pix = b * HW + p;
-    __nv_bfloat16 sv[4][CT / 2];   // side channels (the first half of the outputs) of the 4 pixels
+    __align__(16) __nv_bfloat16 sv[4][CT / 2];   // side channels (the first half of the outputs) of the 4 pixels
 #pragma unroll
     for (int o = 0; o < CT; ++o) {
       if (o < C) {
@@ -788,7 +875,8 @@ __global__ void __launch_bounds__(kThreads) mix1x1_small_kernel(const float* __r
         __nv_bfloat16* sp = side + (pix + k) * side_ld + side_off;
         if (packed) {
           if (CT == 4) *reinterpret_cast<uint32_t*>(sp) = *reinterpret_cast<const uint32_t*>(sv[k]);
-          else *reinterpret_cast<uint2*>(sp) = *reinterpret_cast<const uint2*>(sv[k]);
+          else if (CT == 8) *reinterpret_cast<uint2*>(sp) = *reinterpret_cast<const uint2*>(sv[k]);
+          else *reinterpret_cast<uint4*>(sp) = *reinterpret_cast<const uint4*>(sv[k]);
         } else {
 #pragma unroll
           for (int o = 0; o < CT / 2; ++o)
@@ -881,10 +969,13 @@ extern "C" int rfk_mix1x1(const float* x, float* y, const float* Wm, const float
   RFK_REQUIRE(!logdet || addend, "rfk_mix1x1: logdet given without an addend");
   if (side) RFK_REQUIRE(side_n >= 0 && side_n <= C && side_off >= 0 && side_off + side_n <= side_ld,
                         "rfk_mix1x1: bad side-output window");
-  if (C <= 8 && HW % 4 == 0 && aligned16(x) && aligned16(y) && (!side || side_n <= (C <= 4 ? 2 : 4))) {
+  if (C <= 16 && HW % 4 == 0 && aligned16(x) && aligned16(y) && (!side || side_n <= (C <= 4 ? 2 : C <= 8 ? 4 : 8))) {
     const long long nquad = (long long)B * HW / 4;
     const int grid = stream_grid(nquad, kThreads, 8);
-    if (C <= 4)
+    if (C > 8)
+      RFK_LAUNCH((mix1x1_small_kernel<16>), grid, kThreads, 0, (cudaStream_t)stream, x, y, Wm, bvec, C, HW, nquad, (__nv_bfloat16*)side,
+                                                                           side ? side_n : 0, side_off, side_ld, logdet, addend, alpha, B);
+    else if (C <= 4)
       RFK_LAUNCH((mix1x1_small_kernel<4>), grid, kThreads, 0, (cudaStream_t)stream, x, y, Wm, bvec, C, HW, nquad, (__nv_bfloat16*)side,
                                                                           side ? side_n : 0, side_off, side_ld, logdet, addend, alpha, B);
     else
@@ -928,6 +1019,16 @@ extern "C" int rfk_pack_nhwc_bf16(const float* src, long long src_bstride, int B
   if (n == 0) return RFK_OK;
   long long npix = (long long)B * HW;
   int vec_ok = (dst_ld % 8 == 0) && (dst_off % 8 == 0) && aligned16(dst);
+  if (vec_ok && n % 8 == 0 && n >= 16 && npix >= 4096) {
+    const int chunks = (n + 63) / 64;
+    const long long tiles = (npix + PK_PIX - 1) / PK_PIX;
+    const int gx = (int)std::min<long long>(tiles, std::max(1, sm_count() * 8 / chunks));
+    const long long bs = src_bstride > 0 ? src_bstride : (long long)Csrc * HW;
+    const int vec4 = (HW % 4 == 0) && (bs % 4 == 0) && aligned16(src);
+    RFK_LAUNCH(pack_nhwc_tiled_kernel, dim3(gx, chunks), 256, 0, (cudaStream_t)stream, src, bs, HW, c_lo, n,
+               (__nv_bfloat16*)dst, dst_off, dst_ld, npix, vec4);
+    return check_launch("rfk_pack_nhwc_bf16");
+  }
   RFK_LAUNCH(pack_nhwc_kernel, stream_grid(npix * ((n + 7) / 8), kThreads, 8), kThreads, 0, (cudaStream_t)stream, 
       src, src_bstride > 0 ? src_bstride : (long long)Csrc * HW, HW, c_lo, n, (__nv_bfloat16*)dst, dst_off, dst_ld,
       npix, vec_ok);
@@ -1005,6 +1106,12 @@ extern "C" int rfk_gauss_logp(const float* z, int z_C, int z_off, const float* p
   int chunks = ceil_div(per, kThreads);
   int cap = ceil_div((long long)sm_count() * 8, B);
   if (chunks > cap) chunks = cap;
+  if (HW % 4 == 0 && aligned16(z) && (!params || aligned16(params)) && per < (1LL << 31)) {
+    chunks = std::min(cap, ceil_div(per / 4, kThreads));
+    RFK_LAUNCH(gauss_logp_v4_kernel, dim3(chunks, B), kThreads, 0, (cudaStream_t)stream, z, z_C, z_off, params, n, HW, pairing,
+               std_kind, logdet);
+    return check_launch("rfk_gauss_logp");
+  }
   RFK_LAUNCH(gauss_logp_kernel, dim3(chunks, B), kThreads, 0, (cudaStream_t)stream, z, z_C, z_off, params, n, HW, pairing,
                                                                             std_kind, logdet);
   return check_launch("rfk_gauss_logp");

@@ -51,7 +51,7 @@ def squeeze2d(x, undo=False):
     _chk(x, name="x")
     B, C, H, W = x.shape
     y = torch.empty((B, C // 4, 2 * H, 2 * W) if undo else (B, 4 * C, H // 2, W // 2), device=x.device, dtype=x.dtype)
-    call("rfk_squeeze2d", x.data_ptr(), y.data_ptr(), B, C, H, W, int(undo), _stream())
+    call("rfk_squeeze2d", x.data_ptr(), y.data_ptr(), B, C, H, W, int(undo), _stream(), meta={"bytes": 8.0 * x.numel()})
     return y
 
 
@@ -60,7 +60,7 @@ def actnorm(x, bias, logs, reverse=False):
     B, C, H, W = x.shape
     y = torch.empty_like(x)
     call("rfk_actnorm", x.data_ptr(), y.data_ptr(), _chk(bias).data_ptr(), _chk(logs).data_ptr(), B, C, H * W,
-         int(reverse), _stream())
+         int(reverse), _stream(), meta={"bytes": 8.0 * x.numel()})
     return y
 
 
@@ -104,7 +104,8 @@ def mix1x1(x, Wm, bvec=None, side=None, side_n=0, side_off=0, logdet=None, adden
     y = torch.empty_like(x)
     side_ld = side.shape[-1] if side is not None else 0
     call("rfk_mix1x1", x.data_ptr(), y.data_ptr(), _chk(Wm).data_ptr(), _p(bvec), B, C, H * W,
-         _p(side), side_n, side_off, side_ld, _p(logdet), _p(addend), float(alpha), _stream())
+         _p(side), side_n, side_off, side_ld, _p(logdet), _p(addend), float(alpha), _stream(),
+         meta={"bytes": 8.0 * x.numel() + 2.0 * B * H * W * (side_n if side is not None else 0)})   # x in, y out, bf16 side out
     return y
 
 
@@ -118,7 +119,7 @@ def pack_nhwc(src, c_lo, n, dst, dst_off):
         raise _lib.RfkError("src must be a float32 CUDA tensor, dense within each sample")
     _chk(dst, torch.bfloat16, "dst")
     call("rfk_pack_nhwc_bf16", src.data_ptr(), src.stride(0), B, C, H * W, c_lo, n, dst.data_ptr(), dst_off,
-         dst.shape[-1], _stream())
+         dst.shape[-1], _stream(), meta={"bytes": 6.0 * B * n * H * W})
 
 
 def copy_channels(src, src_off, dst, dst_off, n):
@@ -225,7 +226,9 @@ def convlstm_pointwise_ws(cc, bias, c_prev, peep, h_out, c_next, h_nhwc, h_off, 
     call("rfk_convlstm_pointwise_ws", _chk(cc).data_ptr(), cc.shape[-1], _p(bias), _p(c_prev),
          c_prev.stride(0) if c_prev is not None else 0, _p(peep), h_out.data_ptr(), h_out.stride(0), c_next.data_ptr(),
          c_next.stride(0), _p(h_nhwc), h_off, h_nhwc.shape[-1] if h_nhwc is not None else 0, B, Hc, H * W,
-         int(zero_cc), _stream())
+         int(zero_cc), _stream(),
+         meta={"bytes": 4.0 * B * Hc * H * W * ((8 if zero_cc else 4) + (1 if c_prev is not None else 0) + 2) +
+                        (2.0 * B * Hc * H * W if h_nhwc is not None else 0)})   # gates in (+cleared), c in, h and c out, bf16 h
 
 
 def coupling_tail(nn_out, z, clamp_type, clamp_scale, clamp_shift, logdet, reverse):
@@ -241,7 +244,8 @@ def coupling_tail_taps(taps, z, scale, shift, clamp_type, clamp_scale, clamp_shi
     _chk(z, name="z")
     B, C, H, W = z.shape
     call("rfk_coupling_tail_taps", taps.data_ptr(), z.data_ptr(), B, C, H, W, _chk(scale).data_ptr(),
-         _chk(shift).data_ptr(), CLAMP[clamp_type], _p(clamp_scale), _p(clamp_shift), _p(logdet), int(reverse), _stream())
+         _chk(shift).data_ptr(), CLAMP[clamp_type], _p(clamp_scale), _p(clamp_shift), _p(logdet), int(reverse), _stream(),
+         meta={"bytes": 4.0 * taps.numel() + 4.0 * z.numel()})   # nine tap planes in, z2 half read + written
 
 
 def conv1x1_taps_fused(act, cin_pad, w2, hid, scale2, shift2, act_fn, w9, n3, taps):
@@ -277,7 +281,7 @@ def gauss_logp(z, z_off, params, n, pairing, std_kind, logdet):
     _chk(z, name="z")
     B, zC, H, W = z.shape
     call("rfk_gauss_logp", z.data_ptr(), zC, z_off, _p(params), n, B, H * W, pairing, STD[std_kind],
-         _chk(logdet).data_ptr(), _stream())
+         _chk(logdet).data_ptr(), _stream(), meta={"bytes": 4.0 * B * n * H * W * (3 if params is not None else 1)})
 
 
 def gauss_sample(eps, params, n, pairing, std_kind, temperature, out, out_off):
