@@ -815,6 +815,105 @@ __global__ void add_scalar_kernel(float* __restrict__ logdet, const float* __res
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+// Medium channel counts (16 < C <= 64, HW % 4 == 0): the weight matrix is staged ONCE per CTA (transposed, so the four
+// outputs of a thread come from one 128-bit load) and the CTA walks pixel tiles; a thread owns 4 outputs x 8 pixels
+// (32 FMAs per three 128-bit shared-memory loads).  The generic kernel above re-stages W for every 32 pixels and does
+// nine shared-memory loads per eight FMAs, which makes it fp32-issue-bound long before HBM (C = 48: 0.6 TB/s).
+__global__ void __launch_bounds__(256) mix1x1_mid_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                         const float* __restrict__ Wm, const float* __restrict__ bvec, int C,
+                                                         int HW, long long npix, __nv_bfloat16* __restrict__ side, int side_n,
+                                                         int side_off, int side_ld, float* __restrict__ logdet,
+                                                         const float* __restrict__ addend, float alpha, int B, int PO) {
+  pdl_trigger();
+  pdl_wait();
+  extern __shared__ __align__(16) float smem[];
+  const int C4 = (C + 3) & ~3, OQ = C4 >> 2, TP = PO * 8;
+  float* wT = smem;                 // [C][C4]: wT[i][o] = Wm[o][i]
+  float* bs = wT + C * C4;          // [C4]
+  float* xs = bs + C4;              // [C][TP]
+  for (int e = threadIdx.x; e < C * C4; e += blockDim.x) {
+    const int i = e / C4, o = e - i * C4;
+    wT[e] = o < C ? Wm[o * C + i] : 0.0f;
+  }
+  for (int e = threadIdx.x; e < C4; e += blockDim.x) bs[e] = (bvec && e < C) ? bvec[e] : 0.0f;
+  if (logdet && blockIdx.x == 0) {
+    const float add = alpha * (*addend);
+    for (int i = threadIdx.x; i < B; i += blockDim.x) atomicAdd(logdet + i, add);
+  }
+  const int po = threadIdx.x % PO, oq = threadIdx.x / PO;   // pixel group, output quad (oq >= OQ: helper thread, loads only)
+  const int TPh = TP >> 1;   // a thread owns pixels [4po, 4po+4) of BOTH tile halves: conflict-free 128-bit shared loads
+  for (long long g0 = (long long)blockIdx.x * TP; g0 < npix; g0 += (long long)gridDim.x * TP) {
+    const long long b0 = g0 / HW;               // one 64-bit division per tile, 32-bit arithmetic below
+    const int p0 = (int)(g0 - b0 * HW);
+    const int valid = (int)min((long long)TP, npix - g0);
+    __syncthreads();   // weights staged / previous tile consumed
+    {
+      // all of a thread's loads are issued before the first shared-memory store (a store right behind its load would
+      // serialise the HBM latencies); C * TP / 4 <= 8 * 256 + a few, so at most nine rounds of 256 threads
+      const int total = C * (TP / 4);
+      float4 v[9];
+      int dsto[9];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) {
+        const int e = threadIdx.x + k * 256;
+        v[k] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        dsto[k] = -1;
+        if (e < total) {
+          const int i = e / (TP / 4), q4 = (e - i * (TP / 4)) * 4;
+          dsto[k] = i * TP + q4;
+          if (q4 < valid) {
+            const int t = p0 + q4, bq = t / HW;
+            v[k] = ld_stream(reinterpret_cast<const float4*>(x + ((b0 + bq) * C + i) * HW + (t - bq * HW)));
+          }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 9; ++k)
+        if (dsto[k] >= 0) *reinterpret_cast<float4*>(xs + dsto[k]) = v[k];
+    }
+    __syncthreads();
+    if (oq < OQ && 4 * po < valid) {
+      const float4 b4 = *reinterpret_cast<const float4*>(bs + 4 * oq);
+      float acc[4][8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { acc[0][k] = b4.x; acc[1][k] = b4.y; acc[2][k] = b4.z; acc[3][k] = b4.w; }
+#pragma unroll 2
+      for (int i = 0; i < C; ++i) {
+        const float4 w4 = *reinterpret_cast<const float4*>(wT + i * C4 + 4 * oq);
+        const float4 xa = *reinterpret_cast<const float4*>(xs + i * TP + 4 * po);
+        const float4 xb = *reinterpret_cast<const float4*>(xs + i * TP + TPh + 4 * po);
+        const float xv[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          acc[0][k] = fmaf(w4.x, xv[k], acc[0][k]);
+          acc[1][k] = fmaf(w4.y, xv[k], acc[1][k]);
+          acc[2][k] = fmaf(w4.z, xv[k], acc[2][k]);
+          acc[3][k] = fmaf(w4.w, xv[k], acc[3][k]);
+        }
+      }
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int q4 = hh * TPh + 4 * po;
+        if (q4 >= valid) continue;
+        const int t = p0 + q4, bq = t / HW, p = t - bq * HW;
+        const long long b = b0 + bq, pix = g0 + q4;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int o = 4 * oq + j;
+          if (o < C) {
+            st_stream(reinterpret_cast<float4*>(y + (b * C + o) * HW + p),
+                      make_float4(acc[j][4 * hh], acc[j][4 * hh + 1], acc[j][4 * hh + 2], acc[j][4 * hh + 3]));
+            if (side && o < side_n) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) side[(pix + k) * side_ld + side_off + o] = __float2bfloat16(acc[j][4 * hh + k]);
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
 // Small channel counts (C <= 16): no shared-memory staging, one thread per 4 consecutive pixels, x and y in registers.
 template <int CT>
 __global__ void __launch_bounds__(kThreads) mix1x1_small_kernel(const float* __restrict__ x, float* __restrict__ y,
@@ -981,6 +1080,21 @@ extern "C" int rfk_mix1x1(const float* x, float* y, const float* Wm, const float
     else
       RFK_LAUNCH((mix1x1_small_kernel<8>), grid, kThreads, 0, (cudaStream_t)stream, x, y, Wm, bvec, C, HW, nquad, (__nv_bfloat16*)side,
                                                                           side ? side_n : 0, side_off, side_ld, logdet, addend, alpha, B);
+    return check_launch("rfk_mix1x1");
+  }
+  if (C > 16 && C <= 64 && HW % 4 == 0 && aligned16(x) && aligned16(y)) {
+    const int C4 = (C + 3) & ~3, OQ = C4 / 4, PO = 256 / OQ, TP = PO * 8;
+    const size_t smem = ((size_t)C * C4 + C4 + (size_t)C * TP) * sizeof(float);
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+      cudaError_t e = cudaFuncSetAttribute(mix1x1_mid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) { set_error("rfk_mix1x1: %s", cudaGetErrorString(e)); return RFK_ECUDA; }
+      configured = smem;
+    }
+    const long long npix = (long long)B * HW;
+    const int grid = (int)std::min<long long>((npix + TP - 1) / TP, (long long)sm_count() * 4);
+    RFK_LAUNCH(mix1x1_mid_kernel, grid, 256, smem, (cudaStream_t)stream, x, y, Wm, bvec, C, HW, npix, (__nv_bfloat16*)side,
+               side ? side_n : 0, side_off, side_ld, logdet, addend, alpha, B, PO);
     return check_launch("rfk_mix1x1");
   }
   rfk::CouplingSrc none;
