@@ -164,3 +164,56 @@ def test_two_rank_gloo_sync_and_shards():
         assert p.exitcode == 0
     assert all(same for _, _, same, _ in res)
     assert res[0][1] > 0 and res[0][3] == (0, 4) and res[1][3] == (4, 7)
+
+
+def test_invalidate_caches_epoch():
+    """Raw-pointer parameter updates (fused Adam, CUDA-graph replay) do not bump torch's version counters; the caches
+    must then be dropped through invalidate_caches()."""
+    from recurrent_flows_msc_b200.Flow.glow_modules import _Versioned, invalidate_caches
+    p = torch.nn.Parameter(torch.ones(3))
+    c = _Versioned()
+    calls = []
+
+    def build():
+        calls.append(1)
+        return p.detach().clone()
+    a = c.get("k", (p,), build)
+    assert c.get("k", (p,), build) is a and len(calls) == 1
+    p.data.view(-1)[0] = 5.0            # a write torch does not see (what a kernel writing through data_ptr() does)
+    assert c.get("k", (p,), build) is a
+    invalidate_caches()
+    b = c.get("k", (p,), build)
+    assert len(calls) == 2 and float(b[0]) == 5.0
+
+
+def test_zero_arena_hands_out_disjoint_zeroed_views():
+    from recurrent_flows_msc_b200 import ops
+    dev = torch.device("cpu")
+    with ops.zero_arena(dev):
+        a = ops._zeros(10, dev)
+        b = ops._zeros(7, dev)
+        a.add_(1.0)
+        assert float(b.abs().sum()) == 0.0 and a.data_ptr() != b.data_ptr()
+        assert (b.data_ptr() - a.data_ptr()) % 16 == 0          # 4-float granularity keeps 16-byte alignment
+        big = ops._zeros(ops._ZeroArena.CHUNK + 5, dev)           # larger than a chunk: gets its own allocation
+        assert big.numel() == ops._ZeroArena.CHUNK + 5 and float(big.abs().sum()) == 0.0
+    c = ops._zeros(3, dev)                                       # outside the context: a plain allocation
+    assert c.shape == (3,) and float(c.abs().sum()) == 0.0
+
+
+def test_training_entry_points_need_cuda():
+    """The training path has no CPU fallback either: log_prob / ConvLSTM under autograd on CPU tensors raise."""
+    import types
+    import pytest
+    import recurrent_flows_msc_b200 as rf
+    a = types.SimpleNamespace(LU_decomposed=True, n_units_affine=16, non_lin_glow="relu", clamp_type="realnvp",
+                              flow_norm="actnorm", flow_batchnorm_momentum=0.0, learn_prior=False, n_units_prior=16,
+                              make_conditional=False, base_norm="actnorm", split2d_act="softplus", L=1, K=1, n_bits=8)
+    m = rf.ListGlow([2, 1, 8, 8], [[2, 0, 4, 4]], [2, 0, 4, 4], a)
+    with pytest.raises(Exception):
+        m.log_prob(torch.zeros(2, 1, 8, 8), [torch.zeros(2, 0, 4, 4)], None)
+    lstm = rf.ConvLSTM(4, 4, [3, 3])
+    with pytest.raises(Exception):
+        lstm(torch.zeros(1, 1, 4, 4, 4))
+    with pytest.raises(RuntimeError):
+        rf.FlatAdam(lstm.parameters())
