@@ -155,10 +155,12 @@ int rfk_conv_gemm_splitk(const void* act, int B, int H, int W, int act_ld, int c
                          float* ws, int ws_ld, void* stream);
 
 /* Split-K with the reduction fused in: like rfk_conv_gemm (NHWC bf16 output, per-channel affine + activation), but K
- * is cut into k_split slices that run on different SMs; partial tiles are added into the zeroed fp32 workspace, and
- * the CTA that contributes the last slice of a tile (per-tile counter, zero before the launch) reads the sums back,
- * applies the epilogue, writes the bf16 tile and leaves workspace and counter zeroed again.  For layers whose pixel
- * tiles alone cannot fill the GPU (levels 4-5 of the flow; every level when sampling a few sequences). */
+ * is cut into k_split slices that run on different SMs.  Slice z stores its partial tile with plain stores into its own
+ * slab of the fp32 workspace (ws must hold k_split * B*H*W * ws_ld floats; contents need not be initialised), and the
+ * CTA that contributes the last slice of a tile (per-tile counter, zero before the launch, zero again after it) sums the
+ * slabs, applies the epilogue and writes the bf16 tile.  For layers whose pixel tiles alone cannot fill the GPU (deep
+ * levels of the flow; every level when sampling a few sequences).  (An earlier version added the partial tiles with
+ * red.global.add into one slab: the L2 atomic rate made it slower than not splitting at all.) */
 int rfk_conv_gemm_splitk_fused(const void* act, int B, int H, int W, int act_ld, int cin_pad,
                                const void* wgt, int n, int n_pad, int taps, int k_split,
                                float* ws, int ws_ld, unsigned int* counters,

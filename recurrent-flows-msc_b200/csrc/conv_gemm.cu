@@ -84,6 +84,7 @@ struct SplitKEpi {   // partial sums of a K slice: ws[pixel, col] += acc  (fp32,
   // optional in-kernel fix-up: the CTA that adds the LAST slice of a tile reads the sums back, applies the affine +
   // activation, writes bf16 NHWC and clears workspace and counter (so no separate reduction launch is needed)
   unsigned int* counters;   // one per (n_tile, m_tile), zero before the launch; null = partial sums only
+  long long slice_stride;   // != 0: slice z stores its partial tile at ws + z*slice_stride (no atomics, no zeroing)
   int k_split;
   int act_fn;
   __nv_bfloat16* out;
@@ -309,6 +310,14 @@ __device__ __forceinline__ void epilogue(const GemmArgs& g, const SplitKEpi& e, 
     tmem_ld16_nowait(taddr + c0, r);
     tmem_wait_ld();
     if (!t.valid) continue;
+    if (e.slice_stride) {   // every K slice owns a workspace slab: plain stores, summed by the last-arriving slice
+      float4* dst = reinterpret_cast<float4*>(e.ws + (long long)blockIdx.z * e.slice_stride + pix * e.ld + t.n_tile * g.BN + c0);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        __stcg(dst + k, make_float4(__uint_as_float(r[4 * k]), __uint_as_float(r[4 * k + 1]), __uint_as_float(r[4 * k + 2]),
+                                    __uint_as_float(r[4 * k + 3])));
+      continue;
+    }
     float* dst = e.ws + pix * e.ld + t.n_tile * g.BN + c0;
 #pragma unroll
     for (int k = 0; k < 4; ++k)
@@ -319,6 +328,78 @@ __device__ __forceinline__ void epilogue(const GemmArgs& g, const SplitKEpi& e, 
   }
   release_accumulator(t);
   if (!e.counters) return;
+  if (e.slice_stride) {
+    // ---- cooperative fix-up: all k_split CTAs of a tile are co-resident (the host only splits when pixel tiles x slices
+    // fit the GPU), so each waits until every slice has stored its slab and then reduces ITS share of the column
+    // groups -- the reduction of one tile is spread over k_split SMs instead of serialising 1 MB of loads on one.
+    // release: the CTA barrier orders every epilogue thread's slab stores before the signalling thread's gpu-scope fence
+    // (fences are cumulative), so ONE fence per CTA publishes the whole partial tile
+    named_bar(3, kEpiWarps * 32);
+    unsigned int* cnt = e.counters + t.tile_id;
+    if (t.q == 0 && t.half == 0 && (threadIdx.x & 31) == 0) {
+      __threadfence();
+      atomicAdd(cnt, 1u);
+      const long long t0 = clock64();
+      while (atomicAdd(cnt, 0u) < (unsigned)e.k_split) {    // arrivals; departures count on from k_split
+        __nanosleep(64);
+        if (clock64() - t0 > 4000000000LL) __trap();
+      }
+      __threadfence();   // acquire side, again one fence per CTA; the slabs are read with ld.global.cg (L2) below
+    }
+    named_bar(3, kEpiWarps * 32);
+    if (t.valid) {
+      const int groups = g.BN >> 4;
+      for (int gi = (int)blockIdx.z * 2 + t.half; gi < groups; gi += 2 * e.k_split) {
+        const int c0 = gi << 4, col0 = t.n_tile * g.BN + c0;
+        if (col0 >= g.n) continue;
+        float v[16];
+#pragma unroll
+        for (int hq = 0; hq < 2; ++hq) {
+          // all slices' loads of these 8 columns are issued before the first add (k_split <= 9: 18 x 128 bits in flight);
+          // a rolled loop would serialise one L2 round trip per slice
+          float4 part[9][2];
+#pragma unroll
+          for (int sl = 0; sl < 9; ++sl) {
+            if (sl < e.k_split) {
+              const float4* ss4 = reinterpret_cast<const float4*>(e.ws + (long long)sl * e.slice_stride + pix * e.ld + col0) + 2 * hq;
+              part[sl][0] = __ldcg(ss4);
+              part[sl][1] = __ldcg(ss4 + 1);
+            } else {
+              part[sl][0] = part[sl][1] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            }
+          }
+          float4 s0 = part[0][0], s1 = part[0][1];
+#pragma unroll
+          for (int sl = 1; sl < 9; ++sl) {
+            s0.x += part[sl][0].x; s0.y += part[sl][0].y; s0.z += part[sl][0].z; s0.w += part[sl][0].w;
+            s1.x += part[sl][1].x; s1.y += part[sl][1].y; s1.z += part[sl][1].z; s1.w += part[sl][1].w;
+          }
+          v[8 * hq + 0] = s0.x; v[8 * hq + 1] = s0.y; v[8 * hq + 2] = s0.z; v[8 * hq + 3] = s0.w;
+          v[8 * hq + 4] = s1.x; v[8 * hq + 5] = s1.y; v[8 * hq + 6] = s1.z; v[8 * hq + 7] = s1.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = apply_act(fmaf(v[j], ss[c0 + j], ss[g.BN + c0 + j]), e.act_fn);
+        __nv_bfloat16* dst = e.out + pix * e.out_ld + e.out_off + col0;
+#pragma unroll
+        for (int h8 = 0; h8 < 2; ++h8) {
+          if (e.vec_ok && col0 + 8 * h8 + 8 <= g.n) {
+            *reinterpret_cast<uint4*>(dst + 8 * h8) =
+                make_uint4(pack_bf16(v[8 * h8], v[8 * h8 + 1]), pack_bf16(v[8 * h8 + 2], v[8 * h8 + 3]),
+                           pack_bf16(v[8 * h8 + 4], v[8 * h8 + 5]), pack_bf16(v[8 * h8 + 6], v[8 * h8 + 7]));
+          } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              if (col0 + 8 * h8 + k < g.n) dst[8 * h8 + k] = __float2bfloat16(v[8 * h8 + k]);
+          }
+        }
+      }
+    }
+    named_bar(3, kEpiWarps * 32);   // all reads of the slabs are done before this CTA reports its departure
+    if (t.q == 0 && t.half == 0 && (threadIdx.x & 31) == 0) {
+      if (atomicAdd(cnt, 1u) == (unsigned)(2 * e.k_split - 1)) *cnt = 0u;   // last one out resets the counter
+    }
+    return;
+  }
   // ---- fix-up by the last-arriving slice (all 256 epilogue threads take part in the hand-shake)
   __threadfence();
   named_bar(3, kEpiWarps * 32);
@@ -335,11 +416,24 @@ __device__ __forceinline__ void epilogue(const GemmArgs& g, const SplitKEpi& e, 
       if (col0 >= g.n) break;
       float4* src = reinterpret_cast<float4*>(e.ws + pix * e.ld + col0);
       float v[16];
+      if (e.slice_stride) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float4 a = __ldcg(src + k);
-        src[k] = make_float4(0.f, 0.f, 0.f, 0.f);   // leave the workspace clean for the next launch
-        v[4 * k] = a.x; v[4 * k + 1] = a.y; v[4 * k + 2] = a.z; v[4 * k + 3] = a.w;
+        for (int k = 0; k < 16; ++k) v[k] = 0.0f;
+        for (int sl = 0; sl < e.k_split; ++sl) {
+          const float4* ss4 = reinterpret_cast<const float4*>(e.ws + (long long)sl * e.slice_stride + pix * e.ld + col0);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float4 a = __ldcg(ss4 + k);
+            v[4 * k] += a.x; v[4 * k + 1] += a.y; v[4 * k + 2] += a.z; v[4 * k + 3] += a.w;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float4 a = __ldcg(src + k);
+          src[k] = make_float4(0.f, 0.f, 0.f, 0.f);   // leave the workspace clean for the next launch
+          v[4 * k] = a.x; v[4 * k + 1] = a.y; v[4 * k + 2] = a.z; v[4 * k + 3] = a.w;
+        }
       }
 #pragma unroll
       for (int j = 0; j < 16; ++j) v[j] = apply_act(fmaf(v[j], ss[c0 + j], ss[g.BN + c0 + j]), e.act_fn);
@@ -943,8 +1037,13 @@ extern "C" int rfk_conv_gemm_splitk_fused(const void* act, int B, int H, int W, 
                      pick_bn(n_pad, 16, 1 << 20), false, k_split);
   if (rc) return rc;
   p.g.scale = scale; p.g.shift = shift; p.g.n_ss = n;
+  RFK_REQUIRE(k_split >= 1 && k_split <= 9, "rfk_conv_gemm_splitk_fused: k_split=%d (1..9)", k_split);
+  RFK_REQUIRE((long long)p.grid.x * p.grid.y * p.grid.z <= sm_count(),
+              "rfk_conv_gemm_splitk_fused: %u x %u x %u CTAs exceed the %d SMs (the slices of a tile wait for each other, so "
+              "all CTAs must be co-resident)", p.grid.x, p.grid.y, p.grid.z, sm_count());
   SplitKEpi e;
   e.ws = ws; e.ld = ws_ld; e.counters = counters; e.k_split = k_split; e.act_fn = act_fn;
+  e.slice_stride = (long long)B * H * W * ws_ld;   // one slab per K slice, summed by the last-arriving slice
   e.out = (__nv_bfloat16*)out; e.out_ld = out_ld; e.out_off = out_off;
   e.vec_ok = out_ld % 8 == 0 && out_off % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
   return launch(p, e, (cudaStream_t)stream, "rfk_conv_gemm_splitk_fused");
@@ -960,7 +1059,7 @@ extern "C" int rfk_conv_gemm_splitk(const void* act, int B, int H, int W, int ac
                      false, k_split);
   if (rc) return rc;
   SplitKEpi e;
-  e.ws = ws; e.ld = ws_ld; e.counters = nullptr; e.k_split = k_split; e.act_fn = 0; e.out = nullptr;
+  e.ws = ws; e.ld = ws_ld; e.counters = nullptr; e.slice_stride = 0; e.k_split = k_split; e.act_fn = 0; e.out = nullptr;
   e.out_ld = 0; e.out_off = 0; e.vec_ok = 0;
   return launch(p, e, (cudaStream_t)stream, "rfk_conv_gemm_splitk");
 }

@@ -1082,7 +1082,7 @@ extern "C" int rfk_mix1x1(const float* x, float* y, const float* Wm, const float
                                                                           side ? side_n : 0, side_off, side_ld, logdet, addend, alpha, B);
     return check_launch("rfk_mix1x1");
   }
-  if (C > 16 && C <= 64 && HW % 4 == 0 && aligned16(x) && aligned16(y)) {
+  if (C > 16 && C <= 64 && HW % 4 == 0 && aligned16(x) && aligned16(y) && (long long)B * HW >= 32768) {   // small launches: the generic kernel's many small CTAs have the lower latency
     const int C4 = (C + 3) & ~3, OQ = C4 / 4, PO = 256 / OQ, TP = PO * 8;
     const size_t smem = ((size_t)C * C4 + C4 + (size_t)C * TP) * sizeof(float);
     static size_t configured = 0;

@@ -14,13 +14,19 @@ w = torch.randn(n, cin, k, k, device="cuda") * 0.05
 wp, cin_pad = ops.pack_conv_weight(w)
 out = torch.zeros(B, H, W, ops.pad_to(n, 64), device="cuda", dtype=torch.bfloat16)
 scale, shift = torch.ones(n, device="cuda"), torch.zeros(n, device="cuda")
+KS = int(os.environ.get("SPLITK", "0"))
+def run():
+    if KS:
+        ops.conv_gemm_splitk_fused(act, cin_pad, wp, n, taps, KS, scale, shift, "relu", out)
+    else:
+        ops.conv_gemm(act, cin_pad, wp, n, taps, scale, shift, "relu", out)
 for _ in range(3):
-    ops.conv_gemm(act, cin_pad, wp, n, taps, scale, shift, "relu", out)
+    run()
 ncta = 148 * 4
 tl = torch.zeros(ncta * 16, dtype=torch.int64, device="cuda")
 _lib.call("rfk_debug_set_timeline", tl.data_ptr(), ncta)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record(); ops.conv_gemm(act, cin_pad, wp, n, taps, scale, shift, "relu", out); e1.record()
+e0.record(); run(); e1.record()
 torch.cuda.synchronize()
 _lib.call("rfk_debug_set_timeline", None, 0)
 full = tl.view(ncta, 16).cpu().double()
