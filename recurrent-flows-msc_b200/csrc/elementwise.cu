@@ -1,6 +1,8 @@
 // Bandwidth-bound kernels of the Glow step and the ConvLSTM cell (sm_100a).
 // Every kernel streams its tensors once with 128-bit accesses where the shape allows it and
 // reduces per-sample sums with warp shuffles + one atomic per CTA.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace rfk {
@@ -388,6 +390,35 @@ __global__ void __launch_bounds__(256) pack_nhwc_tiled_kernel(const float* __res
   }
 }
 
+// Register-only variant with full-sector accesses on both sides: a warp takes 8 consecutive pixels x 32 channels
+// (lane = pixel + 8 * channel-group): every load instruction reads four 32-byte runs (8 pixels of one plane each), every
+// store instruction writes eight 64-byte runs (4 groups x 16 bytes of one pixel row).  No shared memory, no barriers.
+__global__ void __launch_bounds__(256) pack_nhwc_oct_kernel(const float* __restrict__ src, long long src_bs, int HW, int c_lo,
+                                                            int n, __nv_bfloat16* __restrict__ dst, int dst_off, int dst_ld,
+                                                            long long npix) {
+  pdl_trigger();
+  pdl_wait();
+  const int G = n >> 3, Q = (G + 3) >> 2;                 // 8-channel groups, quads of groups (one warp each)
+  const long long octs = (npix + 7) >> 3, units = octs * Q;
+  const int lane = threadIdx.x & 31, pl = lane & 7, g4 = lane >> 3;
+  const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5, nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long u = warp0; u < units; u += nwarps) {
+    const long long o = u / Q;
+    const int q = (int)(u - o * Q), gq = 4 * q + g4;
+    const long long pix = 8 * o + pl;
+    if (gq >= G || pix >= npix) continue;
+    const long long b = pix / HW;
+    const float* sp = src + b * src_bs + (long long)(c_lo + 8 * gq) * HW + (pix - b * HW);
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = __ldg(sp + (long long)k * HW);
+    __nv_bfloat162 h[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) h[k] = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);
+    *reinterpret_cast<uint4*>(dst + pix * dst_ld + dst_off + 8 * gq) = *reinterpret_cast<uint4*>(h);
+  }
+}
+
 template <bool kVec>
 __global__ void __launch_bounds__(kThreads) copy_channels_kernel(const float* __restrict__ src, int src_C,
                                                                  int src_off, float* __restrict__ dst, int dst_C,
@@ -623,12 +654,30 @@ __global__ void __launch_bounds__(kThreads) gauss_logp_v4_kernel(const float* __
   const float4* zb = reinterpret_cast<const float4*>(z + ((long long)b * z_C + z_off) * HW);
   const float4* pb = params ? reinterpret_cast<const float4*>(params + (long long)b * 2 * n * HW) : nullptr;
   float acc = 0.0f;
+  if (!pb) {   // N(0, 1): read-only stream, four independent 128-bit loads in flight per thread
+    const int stride = gridDim.x * blockDim.x;
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+    for (; t + 3 * stride < per4; t += 4 * stride) {
+      const float4 v0 = ld_stream(zb + t), v1 = ld_stream(zb + t + stride), v2 = ld_stream(zb + t + 2 * stride),
+                   v3 = ld_stream(zb + t + 3 * stride);
+      a0 += v0.x * v0.x + v0.y * v0.y + v0.z * v0.z + v0.w * v0.w;
+      a1 += v1.x * v1.x + v1.y * v1.y + v1.z * v1.z + v1.w * v1.w;
+      a2 += v2.x * v2.x + v2.y * v2.y + v2.z * v2.z + v2.w * v2.w;
+      a3 += v3.x * v3.x + v3.y * v3.y + v3.z * v3.z + v3.w * v3.w;
+      acc -= 16.0f * 0.91893853320467274178f;
+    }
+    for (; t < per4; t += stride) {
+      const float4 v0 = ld_stream(zb + t);
+      a0 += v0.x * v0.x + v0.y * v0.y + v0.z * v0.z + v0.w * v0.w;
+      acc -= 4.0f * 0.91893853320467274178f;
+    }
+    acc -= 0.5f * ((a0 + a1) + (a2 + a3));
+    cta_atomic_add(acc, logdet + b, sh);
+    return;
+  }
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < per4; t += gridDim.x * blockDim.x) {
     const float4 zv = ld_stream(zb + t);
-    if (!pb) {   // N(0, 1)
-      acc += -0.5f * (zv.x * zv.x + zv.y * zv.y + zv.z * zv.z + zv.w * zv.w) - 4.0f * 0.91893853320467274178f;
-      continue;
-    }
     const int j = t / HW4, p4 = t - j * HW4;
     const int cm = pairing == RFK_PAIR_CROSS ? 2 * j : j, cr = pairing == RFK_PAIR_CROSS ? 2 * j + 1 : n + j;
     const float4 mv = ld_stream(pb + (long long)cm * HW4 + p4), rv = ld_stream(pb + (long long)cr * HW4 + p4);
@@ -1133,7 +1182,16 @@ extern "C" int rfk_pack_nhwc_bf16(const float* src, long long src_bstride, int B
   if (n == 0) return RFK_OK;
   long long npix = (long long)B * HW;
   int vec_ok = (dst_ld % 8 == 0) && (dst_off % 8 == 0) && aligned16(dst);
-  if (vec_ok && n % 8 == 0 && n >= 16 && npix >= 4096) {
+  static const int pack_mode = [] { const char* e = getenv("RFK_PACK_MODE"); return e ? atoi(e) : 2; }();   // 0 flat, 1 tiled, 2 octets
+  if (pack_mode == 2 && vec_ok && n % 8 == 0 && npix >= 4096) {
+    const int Q = (n / 8 + 3) / 4;
+    const long long units = ((npix + 7) / 8) * Q;
+    const int grid = (int)std::min<long long>((units + 7) / 8, (long long)sm_count() * 16);
+    RFK_LAUNCH(pack_nhwc_oct_kernel, grid, 256, 0, (cudaStream_t)stream, src,
+               src_bstride > 0 ? src_bstride : (long long)Csrc * HW, HW, c_lo, n, (__nv_bfloat16*)dst, dst_off, dst_ld, npix);
+    return check_launch("rfk_pack_nhwc_bf16");
+  }
+  if (pack_mode == 1 && vec_ok && n % 8 == 0 && n >= 16 && npix >= 4096) {
     const int chunks = (n + 63) / 64;
     const long long tiles = (npix + PK_PIX - 1) / PK_PIX;
     const int gx = (int)std::min<long long>(tiles, std::max(1, sm_count() * 8 / chunks));
