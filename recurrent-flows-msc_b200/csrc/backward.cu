@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(256) coupling_taps_bwd_kernel(const float* __r
 
 // Same, four consecutive pixels of a row per thread (W % 4 == 0, 16-byte aligned tensors): per tap plane one 128-bit load
 // plus, for the horizontally shifted taps, one scalar edge element (the layout of coupling_taps_v4_kernel).
-__global__ void __launch_bounds__(256) coupling_taps_bwd_v4_kernel(const float* __restrict__ taps, const float* __restrict__ z_out,
+__global__ void __launch_bounds__(256, 4) coupling_taps_bwd_v4_kernel(const float* __restrict__ taps, const float* __restrict__ z_out,
                                                                    float* __restrict__ dz, float* __restrict__ dsum, int B, int C,
                                                                    int H, int W, const float* __restrict__ scale,
                                                                    const float* __restrict__ shift, int clamp_type,

@@ -47,6 +47,7 @@ struct GemmArgs {
   int kgroup;            // K chunks per pipeline stage (one mbarrier round trip per stage)
   int kg_per_split;      // pipeline stages of K per CTA: all of them, or a 1/gridDim.z slice (split-K)
   int tw_log2, th_log2;  // tile = NIMG x TH x TW pixels, TW*TH*NIMG = 128
+  int pair;              // 1: CTA pairs (cluster of 2, cta_group::2): M = 256 per MMA, the resident weights split over the pair
   int tiles_x, tiles_y, m_tiles;
   int stages;
   int tmem_cols;
@@ -136,6 +137,7 @@ struct TileCtx {
   int half, q;
   uint32_t stg;     // this half's staging buffer (shared-space address), 0 when not allocated
   uint32_t tmem_empty_bar;
+  int remote_release;   // CTA pair, odd CTA: the accumulator-drained barrier lives in the leader CTA
   long long* dbg;   // 5 per-phase cycle counters of the TMA-store epilogue, or null
   int tile_id;      // n_tile * m_tiles + m_tile (split-K fix-up counter index)
   volatile unsigned int* flag;  // one shared-memory word for epilogue-wide broadcasts
@@ -144,7 +146,10 @@ struct TileCtx {
 __device__ __forceinline__ void release_accumulator(const TileCtx& t) {
   tc_fence_before();
   __syncwarp();
-  if ((threadIdx.x & 31) == 0) mbar_arrive(t.tmem_empty_bar);
+  if ((threadIdx.x & 31) == 0) {
+    if (t.remote_release) mbar_arrive_cluster(t.tmem_empty_bar, 0);
+    else mbar_arrive(t.tmem_empty_bar);
+  }
 }
 
 template <int ACT>
@@ -514,7 +519,9 @@ __device__ __forceinline__ void epilogue(const GemmArgs& g, const LstmEpi& e, co
 // ------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------
-template <class Epi>
+// kPair: CTA-pair build (cluster of two, tcgen05 cta_group::2).  A kernel that contains cta_group::2 instructions can only be
+// launched with an even cluster width, so the pair mode is a separate instantiation, not a run-time switch.
+template <class Epi, bool kPair>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmO, const GemmArgs g, const Epi ep) {
@@ -528,7 +535,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t a_chunk_bytes = (uint32_t)BM * g.bk * 2;
   const int k_groups = g.kg_per_split;             // pipeline stages of K this CTA accumulates
   const int kg0 = blockIdx.z * g.kg_per_split;      // first one (split-K: gridDim.z slices)
-  const uint32_t b_chunk_bytes = (uint32_t)g.BN * g.bk * 2;
+  const uint32_t rank = kPair ? cluster_ctarank() : 0u;   // CTA pair: 0 = leader (issues the MMAs, owns their barriers)
+  const int bn_local = kPair ? g.BN >> 1 : g.BN;          // weight rows held by this CTA
+  const uint32_t b_chunk_bytes = (uint32_t)bn_local * g.bk * 2;
   const uint32_t b_res_bytes = g.b_resident ? (uint32_t)(k_groups * g.kgroup) * b_chunk_bytes : 0u;
   const uint32_t stage_bytes = (uint32_t)g.kgroup * (a_chunk_bytes + (g.b_resident ? 0u : b_chunk_bytes));
   const uint32_t stage_base = base + b_res_bytes;
@@ -558,23 +567,38 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(tmem_full_bar(b), 1);
-      mbar_init(tmem_empty_bar(b), kEpiWarps);
+      mbar_init(tmem_empty_bar(b), kEpiWarps * (kPair ? 2 : 1));
     }
     mbar_init(b_full_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (kPair) cluster_sync_all();   // the peer's barriers exist before anything (TMA, commits, remote arrives) targets them
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)),
-                 "r"((uint32_t)g.tmem_cols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (kPair) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)),
+                   "r"((uint32_t)g.tmem_cols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)),
+                   "r"((uint32_t)g.tmem_cols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   // Programmatic dependent launch: everything above touched only this CTA's own shared memory / TMEM.  The weights
   // are parameters (never written by the preceding kernel), so their TMA loads also go out before the dependency wait.
   if (warp == 0 && lane == 0 && g.b_resident) {
-    mbar_expect_tx(b_full_bar, b_res_bytes);
-    for (int it = 0; it < k_groups * g.kgroup; ++it)
-      tma_load_2d(base + it * b_chunk_bytes, &tmB, b_full_bar, (kg0 * g.kgroup + it) * g.bk, n_tile * g.BN);
+    if (kPair) {   // each CTA fetches its half of the rows; both halves count on the leader's barrier
+      if (rank == 0) mbar_expect_tx(b_full_bar, 2u * b_res_bytes);
+      for (int it = 0; it < k_groups * g.kgroup; ++it)
+        tma_load_2d_2sm(base + it * b_chunk_bytes, &tmB, b_full_bar & kPeerBitMask, (kg0 * g.kgroup + it) * g.bk,
+                        n_tile * g.BN + (int)rank * bn_local);
+    } else {
+      mbar_expect_tx(b_full_bar, b_res_bytes);
+      for (int it = 0; it < k_groups * g.kgroup; ++it)
+        tma_load_2d(base + it * b_chunk_bytes, &tmB, b_full_bar, (kg0 * g.kgroup + it) * g.bk, n_tile * g.BN);
+    }
   }
   pdl_trigger();   // the next kernel in the stream may start its own prologue
   pdl_wait();      // from here on we read what the preceding kernel produced
@@ -601,24 +625,36 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     n0 = tn << nimg_log2;
   };
 
+  // tile schedule: CTA i takes tiles i, i + grid, ...; a CTA pair takes tile PAIRS (2*it + rank); with an odd tile count
+  // the odd CTA's last tile does not exist (its loads are zero-filled, its stores clipped)
+  const int it0 = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int it_step = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int it_end = kPair ? (g.m_tiles + 1) >> 1 : g.m_tiles;
+  auto tile_of = [&](int it) { return kPair ? 2 * it + (int)rank : it; };
+
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
       long long c_wait_empty = 0;
-      for (int mt = blockIdx.x; mt < g.m_tiles; mt += gridDim.x) {
+      for (int it = it0; it < it_end; it += it_step) {
+        const int mt = tile_of(it);
         int x0, y0, n0;
         tile_origin(mt, x0, y0, n0);
         int tap = (kg0 * g.kgroup) / g.kchunks, kc = (kg0 * g.kgroup) % g.kchunks;
         for (int grp = 0; grp < k_groups; ++grp) {
           { CNT_BEGIN(); mbar_wait(empty_bar(s), ph ^ 1u); CNT_END(c_wait_empty); }
           const uint32_t a_dst = stage_base + s * stage_bytes;
-          mbar_expect_tx(full_bar(s), stage_bytes);
+          if (!kPair) mbar_expect_tx(full_bar(s), stage_bytes);
+          else if (rank == 0) mbar_expect_tx(full_bar(s), 2u * stage_bytes);   // both CTAs' tiles land on the leader's barrier
           for (int j = 0; j < g.kgroup; ++j) {
             const int dy = g.taps == 9 ? tap / 3 - 1 : 0;
             const int dx = g.taps == 9 ? tap % 3 - 1 : 0;
-            tma_load_4d(a_dst + j * a_chunk_bytes, &tmA, full_bar(s), kc * g.bk, x0 + dx, y0 + dy, n0);
+            if (kPair)
+              tma_load_4d_2sm(a_dst + j * a_chunk_bytes, &tmA, full_bar(s) & kPeerBitMask, kc * g.bk, x0 + dx, y0 + dy, n0);
+            else
+              tma_load_4d(a_dst + j * a_chunk_bytes, &tmA, full_bar(s), kc * g.bk, x0 + dx, y0 + dy, n0);
             if (!g.b_resident)
               tma_load_2d(a_dst + g.kgroup * a_chunk_bytes + j * b_chunk_bytes, &tmB, full_bar(s),
                           ((kg0 + grp) * g.kgroup + j) * g.bk, n_tile * g.BN);
@@ -633,9 +669,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     __syncwarp();
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    if (lane == 0) {
-      // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at bit 17, M>>4 at bit 24
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(g.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    if (lane == 0 && rank == 0) {   // CTA pair: only the leader issues
+      // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at bit 17, M>>4 at bit 24 (M = 256 for a pair)
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(g.BN >> 3) << 17) |
+                             ((uint32_t)((kPair ? 2 * BM : BM) >> 4) << 24);
       const uint64_t desc_hi = umma_desc_kmajor(0, g.bk);  // everything but the start address
       const int ksteps = g.bk / UMMA_K;
       if (g.b_resident) {
@@ -645,7 +682,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int s = 0;
       uint32_t ph = 0, tl = 0;
       long long c_wait_full = 0, c_wait_tempty = 0, c_issue = 0;
-      for (int mt = blockIdx.x; mt < g.m_tiles; mt += gridDim.x, ++tl) {
+      for (int it = it0; it < it_end; it += it_step, ++tl) {
         const uint32_t buf = tl & 1u;
         { CNT_BEGIN(); mbar_wait(tmem_empty_bar(buf), ((tl >> 1) & 1u) ^ 1u); CNT_END(c_wait_tempty); }  // accumulator drained
         tc_fence_after();
@@ -664,18 +701,21 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll 4
             for (int k = 0; k < ksteps; ++k) {
               // advance 32 B (16 bf16) along K inside the swizzle row: +2 in 16-byte units
-              umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, accumulate);
+              if (kPair) umma_bf16_2sm(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, accumulate);
+              else umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, accumulate);
               accumulate = 1;
             }
             a_addr += a_chunk_bytes;
             b_addr += b_chunk_bytes;
           }
           b_res_addr += g.kgroup * b_chunk_bytes;
-          umma_commit(empty_bar(s));  // frees the smem stage once these MMAs have read it
+          if (kPair) umma_commit_2sm(empty_bar(s));   // frees the stage in BOTH CTAs
+          else umma_commit(empty_bar(s));  // frees the smem stage once these MMAs have read it
           CNT_END(c_issue);
           if (++s == g.stages) { s = 0; ph ^= 1u; }
         }
-        umma_commit(tmem_full_bar(buf));  // accumulator complete
+        if (kPair) umma_commit_2sm(tmem_full_bar(buf));
+        else umma_commit(tmem_full_bar(buf));  // accumulator complete
       }
       RFK_STAMP(4);  // all MMAs issued
       RFK_PUT(9, c_wait_full);
@@ -697,13 +737,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     long long c_wait_tfull = 0, c_epi = 0;
     long long phase_cnt[5] = {0, 0, 0, 0, 0};
     t.dbg = g.timeline ? phase_cnt : nullptr;
-    for (int mt = blockIdx.x; mt < g.m_tiles; mt += gridDim.x, ++tl) {
+    t.remote_release = kPair && rank != 0;
+    for (int it = it0; it < it_end; it += it_step, ++tl) {
+      const int mt = tile_of(it);
       const uint32_t buf = tl & 1u;
       tile_origin(mt, t.x0, t.y0, t.n0);
       t.b = t.n0 + (row >> ppi_log2);
       t.y = t.y0 + ((row >> g.tw_log2) & ((1 << g.th_log2) - 1));
       t.x = t.x0 + (row & ((1 << g.tw_log2) - 1));
-      t.valid = t.b < g.B && t.y < g.H && t.x < g.W;
+      t.valid = mt < g.m_tiles && t.b < g.B && t.y < g.H && t.x < g.W;
       t.tmem_empty_bar = tmem_empty_bar(buf);
       t.tile_id = n_tile * g.m_tiles + mt;
       { CNT_BEGIN(); mbar_wait(tmem_full_bar(buf), (tl >> 1) & 1u); CNT_END(c_wait_tfull); }
@@ -719,9 +761,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   tc_fence_before();
   __syncthreads();
+  if (kPair) cluster_sync_all();   // the peer may still be arriving on this CTA's barriers / reading its weights
   if (warp == 2) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)g.tmem_cols)
-                 : "memory");
+    if (kPair)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)g.tmem_cols)
+                   : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)g.tmem_cols)
+                   : "memory");
   }
 }
 
@@ -803,7 +850,8 @@ int encode_act_map(CUtensorMap* map, const char* who, const char* what, const vo
 
 // stg_wanted: the epilogue can use TMA stores (needs 2 x 16 KB of staging shared memory)
 static int make_plan(Plan& p, const char* who, const void* act, int B, int H, int W, int act_ld, int cin_pad,
-                     const void* wgt, int n, int n_pad, int taps, int BN, bool stg_wanted, int k_split = 1) {
+                     const void* wgt, int n, int n_pad, int taps, int BN, bool stg_wanted, int k_split = 1,
+                     bool allow_pair = false) {
   RFK_REQUIRE(act && wgt && B > 0 && H > 0 && W > 0, "%s: null pointer or empty shape", who);
   RFK_REQUIRE(cin_pad > 0 && (cin_pad % 64 == 0 || cin_pad == 32) && cin_pad <= act_ld,
               "%s: cin_pad=%d must be 32 or a multiple of 64, and <= act_ld=%d", who, cin_pad, act_ld);
@@ -844,8 +892,20 @@ static int make_plan(Plan& p, const char* who, const void* act, int B, int H, in
   const int fixed = 1024 /*alignment slack*/ + (stg_wanted ? 2 * STG_BYTES : 0) + 2 * BN * 4 + 8 * (2 * 8 + 5) + 16;
   g.use_stg = stg_wanted ? 1 : 0;
   int resident = 0, stages = 0;
+  g.pair = 0;
   {
-    const long long res_bytes = (long long)(k_iters / k_split) * BN * bk * 2;
+    // CTA pairs: when the resident weights leave room for only a few activation stages (the MMA warp then waits ~2k cycles
+    // per tile for TMA data), two CTAs of a cluster share ONE copy of the weights -- half the rows each -- and issue
+    // M = 256 MMAs (tcgen05 cta_group::2): twice the pipeline depth at the same shared-memory size.
+    static const int pair_mode = [] { const char* e = getenv("RFK_GEMM_PAIR"); return e ? atoi(e) : 1; }();
+    const long long full_res = (long long)k_iters * BN * bk * 2;
+    if (allow_pair && pair_mode && stg_wanted && k_split == 1 && n_tiles == 1 && BN % 32 == 0 &&
+        full_res >= (pair_mode == 2 ? 0 : 96 * 1024) && g.m_tiles >= 2 * sm_count() &&
+        (long long)SMEM_LIMIT - fixed - full_res / 2 >= 3LL * a_stage)
+      g.pair = 1;
+  }
+  {
+    const long long res_bytes = (long long)(k_iters / k_split) * BN * bk * 2 / (g.pair ? 2 : 1);
     const long long room = (long long)SMEM_LIMIT - fixed - res_bytes;
     if (room >= 3LL * a_stage) {
       resident = 1;
@@ -875,12 +935,16 @@ static int make_plan(Plan& p, const char* who, const void* act, int B, int H, in
   while (cols < 2 * BN) cols <<= 1;
   g.tmem_cols = cols;  // two accumulators
   const int stage_bytes = a_stage + (resident ? 0 : b_chunk);
-  p.smem = (size_t)1024 + (resident ? (size_t)(k_iters / k_split) * BN * bk * 2 : 0) + (size_t)stages * stage_bytes +
+  p.smem = (size_t)1024 + (resident ? (size_t)(k_iters / k_split) * BN * bk * 2 / (g.pair ? 2 : 1) : 0) + (size_t)stages * stage_bytes +
            (stg_wanted ? 2 * STG_BYTES : 0) + 2 * BN * 4 + 8 * (2 * stages + 5) + 16;
   RFK_REQUIRE(p.smem <= (size_t)SMEM_LIMIT, "%s: internal error: %zu B of shared memory planned", who, p.smem);
   int ctas_x = sm_count() / (n_tiles * k_split);
   if (ctas_x < 1) ctas_x = 1;
   if (ctas_x > g.m_tiles) ctas_x = g.m_tiles;
+  if (g.pair) {
+    RFK_REQUIRE(resident, "%s: internal error: CTA pairs need resident weights", who);
+    ctas_x &= ~1;   // whole pairs
+  }
   p.grid = dim3((unsigned)ctas_x, (unsigned)n_tiles, (unsigned)k_split);
   g.timeline = (g_timeline && (long long)ctas_x * n_tiles * k_split <= g_timeline_cap) ? g_timeline : nullptr;
   g.scale = nullptr; g.shift = nullptr; g.n_ss = 0;
@@ -892,7 +956,7 @@ static int make_plan(Plan& p, const char* who, const void* act, int B, int H, in
   const cuuint64_t ktot = (cuuint64_t)taps * cin_pad;
   cuuint64_t dimsB[2] = {ktot, (cuuint64_t)n_pad};
   cuuint64_t strB[1] = {ktot * 2};
-  cuuint32_t boxB[2] = {(cuuint32_t)bk, (cuuint32_t)BN};
+  cuuint32_t boxB[2] = {(cuuint32_t)bk, (cuuint32_t)(g.pair ? BN / 2 : BN)};
   cuuint32_t ones[2] = {1, 1};
   CUresult r = enc(&p.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(wgt), dimsB, strB, boxB, ones,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
@@ -905,19 +969,51 @@ static int make_plan(Plan& p, const char* who, const void* act, int B, int H, in
   return RFK_OK;
 }
 
-template <class Epi>
-static int launch(const Plan& p, const Epi& ep, cudaStream_t st, const char* who) {
+template <class T> struct PairCapable { static constexpr bool value = false; };
+template <int ACT> struct PairCapable<PlainEpi<ACT>> { static constexpr bool value = true; };
+
+template <class Epi, bool kPair>
+static int launch_impl(const Plan& p, const Epi& ep, cudaStream_t st, const char* who) {
   static size_t configured = 0;
   if (p.smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<Epi, kPair>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
     if (e != cudaSuccess) {
       set_error("%s: cudaFuncSetAttribute(%zu B smem): %s", who, p.smem, cudaGetErrorString(e));
       return RFK_ECUDA;
     }
     configured = p.smem;
   }
-  launch_kernel(conv_gemm_kernel<Epi>, p.grid, dim3(kGemmThreads), p.smem, st, p.tmA, p.tmB, p.tmO, p.g, ep);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = p.grid;
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = p.smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (kPair) {   // two CTAs along x = the two SMs of a TPC
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  cudaLaunchKernelEx(&cfg, conv_gemm_kernel<Epi, kPair>, p.tmA, p.tmB, p.tmO, p.g, ep);
   return check_launch(who);
+}
+
+template <class Epi>
+static int launch(const Plan& p, const Epi& ep, cudaStream_t st, const char* who) {
+  if constexpr (PairCapable<Epi>::value) {
+    if (p.g.pair) return launch_impl<Epi, true>(p, ep, st, who);
+  }
+  return launch_impl<Epi, false>(p, ep, st, who);
 }
 
 // N tile: the whole (padded) channel count when it fits one accumulator; otherwise the largest divisor that is a
@@ -979,7 +1075,7 @@ extern "C" int rfk_conv_gemm(const void* act, int B, int H, int W, int act_ld, i
   }
   if (!BN) BN = pick_bn(n_pad, 16, mth);
   Plan p;
-  int rc = make_plan(p, "rfk_conv_gemm", act, B, H, W, act_ld, cin_pad, wgt, n, n_pad, taps, BN, tma_ok);
+  int rc = make_plan(p, "rfk_conv_gemm", act, B, H, W, act_ld, cin_pad, wgt, n, n_pad, taps, BN, tma_ok, 1, tma_ok);
   if (rc) return rc;
   p.g.scale = scale; p.g.shift = shift; p.g.n_ss = n;
   if (tma_ok) {

@@ -31,6 +31,8 @@ torch.cuda.synchronize()
 _lib.call("rfk_debug_set_timeline", None, 0)
 full = tl.view(ncta, 16).cpu().double()
 full = full[full[:, 7] > 0]
+if os.environ.get('EVEN') == '1':
+    full = full[0::2]   # CTA-pair mode: the leader CTAs hold the MMA-side counters
 ncta = full.shape[0]
 t = full[:, :8]
 t0 = t[:, 0].min()
