@@ -899,15 +899,16 @@ static int make_plan(Plan& p, const char* who, const void* act, int B, int H, in
     // M = 256 MMAs (tcgen05 cta_group::2): twice the pipeline depth at the same shared-memory size.
     static const int pair_mode = [] { const char* e = getenv("RFK_GEMM_PAIR"); return e ? atoi(e) : 1; }();
     const long long full_res = (long long)k_iters * BN * bk * 2;
+    static const int pair_min_stages = [] { const char* e = getenv("RFK_GEMM_PAIR_MIN_STAGES"); return e ? atoi(e) : 3; }();
     if (allow_pair && pair_mode && stg_wanted && k_split == 1 && n_tiles == 1 && BN % 32 == 0 &&
         full_res >= (pair_mode == 2 ? 0 : 96 * 1024) && g.m_tiles >= 2 * sm_count() &&
-        (long long)SMEM_LIMIT - fixed - full_res / 2 >= 3LL * a_stage)
+        (long long)SMEM_LIMIT - fixed - full_res / 2 >= (long long)pair_min_stages * a_stage)
       g.pair = 1;
   }
   {
     const long long res_bytes = (long long)(k_iters / k_split) * BN * bk * 2 / (g.pair ? 2 : 1);
     const long long room = (long long)SMEM_LIMIT - fixed - res_bytes;
-    if (room >= 3LL * a_stage) {
+    if (room >= 3LL * a_stage || g.pair) {
       resident = 1;
       stages = (int)(room / a_stage);
     } else {
