@@ -200,3 +200,25 @@ def test_conv1x1_taps_fused(ops, act, B, C, H, W, hid):
     taps2 = torch.empty(B, 9 * C, H, W, device="cuda")
     ops.conv_gemm(h2, ops.cin_pad(hid), w9p, 9 * C, 1, None, None, "none", taps2)
     assert max_rel(taps.cpu(), taps2.cpu()) < 1e-3
+
+
+@pytest.mark.parametrize("B,Cin,H,W,N,k,act", [(40, 18, 32, 32, 256, 3, "relu"), (38, 256, 32, 32, 256, 1, "leakyrelu"),
+                                               (593, 20, 8, 8, 256, 3, "none"), (75, 4, 32, 32, 224, 3, "relu")])
+def test_conv_gemm_cta_pair_shapes(ops, B, Cin, H, W, N, k, act):
+    """Shapes with at least two pixel tiles per SM and resident weights: these launch as clusters of two CTAs
+    (tcgen05 cta_group::2, weights split over the pair); 593 x 8x8 gives an ODD tile count (the odd CTA's last tile does
+    not exist).  The reference is evaluated on a few samples at both ends of the batch."""
+    g = torch.Generator().manual_seed(B + Cin)
+    x = bf(torch.randn(B, Cin, H, W, generator=g))
+    w = bf(torch.randn(N, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5)
+    scale, shift = torch.rand(N, generator=g) + 0.5, torch.randn(N, generator=g) * 0.3
+    wp, cin_pad = ops.pack_conv_weight(w.cuda())
+    ld = ops.pad_to(N, 64)
+    out = torch.zeros(B, H, W, ld, device="cuda", dtype=torch.bfloat16)
+    ops.conv_gemm(staged(ops, x), cin_pad, wp, N, k * k, scale.cuda(), shift.cuda(), act, out)
+    for sl in (slice(0, 3), slice(B // 2, B // 2 + 2), slice(B - 3, B)):
+        ref = F.conv2d(x[sl], w, None, 1, (k - 1) // 2) * scale.view(1, N, 1, 1) + shift.view(1, N, 1, 1)
+        ref = ref if act == "none" else O.act_fun(ref, act)
+        got = out[sl][..., :N].permute(0, 3, 1, 2).float().cpu()
+        assert max_rel(got, ref) < 6e-3
+    assert float(out[..., N:].abs().max()) == 0 if ld > N else True
