@@ -156,7 +156,8 @@ int rfk_conv_gemm_splitk(const void* act, int B, int H, int W, int act_ld, int c
 
 /* Split-K with the reduction fused in: like rfk_conv_gemm (NHWC bf16 output, per-channel affine + activation), but K
  * is cut into k_split slices that run on different SMs.  Slice z stores its partial tile with plain stores into its own
- * slab of the fp32 workspace (ws must hold k_split * B*H*W * ws_ld floats; contents need not be initialised), and the
+ * slab of the fp32 workspace (ws must hold k_split * ceil(pixels/128)*128 * n_pad floats with ws_ld == n_pad; tile-local
+ * layout, contents need not be initialised), and the
  * CTA that contributes the last slice of a tile (per-tile counter, zero before the launch, zero again after it) sums the
  * slabs, applies the epilogue and writes the bf16 tile.  For layers whose pixel tiles alone cannot fill the GPU (deep
  * levels of the flow; every level when sampling a few sequences).  (An earlier version added the partial tiles with

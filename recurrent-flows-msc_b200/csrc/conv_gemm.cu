@@ -316,7 +316,9 @@ __device__ __forceinline__ void epilogue(const GemmArgs& g, const SplitKEpi& e, 
     tmem_wait_ld();
     if (!t.valid) continue;
     if (e.slice_stride) {   // every K slice owns a workspace slab: plain stores, summed by the last-arriving slice
-      float4* dst = reinterpret_cast<float4*>(e.ws + (long long)blockIdx.z * e.slice_stride + pix * e.ld + t.n_tile * g.BN + c0);
+      // slab layout [tile][16-column group][128 rows][16 floats]: the 32 lanes of a warp (32 rows) write 2 KB contiguously
+      float4* dst = reinterpret_cast<float4*>(e.ws + (long long)blockIdx.z * e.slice_stride + (long long)t.tile_id * g.BN * 128 +
+                                              ((long long)(c0 >> 4) * 128 + (t.q * 32 + (threadIdx.x & 31))) * 16);
 #pragma unroll
       for (int k = 0; k < 4; ++k)
         __stcg(dst + k, make_float4(__uint_as_float(r[4 * k]), __uint_as_float(r[4 * k + 1]), __uint_as_float(r[4 * k + 2]),
@@ -366,7 +368,9 @@ __device__ __forceinline__ void epilogue(const GemmArgs& g, const SplitKEpi& e, 
 #pragma unroll
           for (int sl = 0; sl < 9; ++sl) {
             if (sl < e.k_split) {
-              const float4* ss4 = reinterpret_cast<const float4*>(e.ws + (long long)sl * e.slice_stride + pix * e.ld + col0) + 2 * hq;
+              const float4* ss4 = reinterpret_cast<const float4*>(e.ws + (long long)sl * e.slice_stride +
+                                                                  (long long)t.tile_id * g.BN * 128 +
+                                                                  ((long long)gi * 128 + (t.q * 32 + (threadIdx.x & 31))) * 16) + 2 * hq;
               part[sl][0] = __ldcg(ss4);
               part[sl][1] = __ldcg(ss4 + 1);
             } else {
@@ -1140,7 +1144,8 @@ extern "C" int rfk_conv_gemm_splitk_fused(const void* act, int B, int H, int W, 
               "all CTAs must be co-resident)", p.grid.x, p.grid.y, p.grid.z, sm_count());
   SplitKEpi e;
   e.ws = ws; e.ld = ws_ld; e.counters = counters; e.k_split = k_split; e.act_fn = act_fn;
-  e.slice_stride = (long long)B * H * W * ws_ld;   // one slab per K slice, summed by the last-arriving slice
+  e.slice_stride = (long long)p.g.m_tiles * 128 * n_pad;   // one slab per K slice: [tile][16-col group][128 rows][16]
+  RFK_REQUIRE(ws_ld == n_pad, "rfk_conv_gemm_splitk_fused: ws_ld must equal n_pad (%d)", n_pad);
   e.out = (__nv_bfloat16*)out; e.out_ld = out_ld; e.out_off = out_off;
   e.vec_ok = out_ld % 8 == 0 && out_off % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
   return launch(p, e, (cudaStream_t)stream, "rfk_conv_gemm_splitk_fused");

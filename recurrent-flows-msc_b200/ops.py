@@ -176,28 +176,39 @@ def conv_gemm_lstm(act, cin_pad, wgt, hidden, ht, ht_pad, taps, bias, c_prev, pe
          meta=_gemm_meta(B * H * W, 4 * hidden, taps, cin_pad, wgt))
 
 
-SPLITK_MAX_UNITS = int(__import__('os').environ.get('RFK_SPLITK_MAX_UNITS', '74'))   # (pixel tiles x K slices) up to which K is split
-
-
 def choose_k_split(M, taps, cin_pad):
     """K slices for a 3x3 conv whose pixel tiles cannot fill the GPU.  tcgen05.mma (M=128) costs ~131 cycles whatever
     N is, so a CTA's time is K-iterations x 4 x 131 cycles however narrow its tile: the only way to put more SMs on a
-    small-M layer is to cut K.  One slice per filter tap (9) or per filter row (3)."""
-    # Measured on B200 (tools/splitk_bench.py, 30 sequences): the fused split (slabs + cooperative fix-up, no atomics)
-    # finishes its main loop in 4 us but spends ~16 us in the hand-shake and the slab reduction, so it only ties the
-    # unsplit kernel on 2x2 maps (22.0 vs 24.0 us) and loses on 4x4 / 8x8 (23.7 vs 16.3, 23.5 vs 12.7 us).  Off unless
-    # forced; the RFN ConvLSTM uses the non-fused split (rfk_conv_gemm_splitk + the pointwise kernel).
+    small-M layer is to cut K (one slice per filter tap)."""
+    # Measured on B200 (tools/splitk_bench.py, 30 sequences): with per-slice slabs in a tile-local layout and a cooperative
+    # fix-up the split kernel's main loop takes 4 us but the hand-shake + slab reduction add ~12 us, so it wins only on
+    # the deepest level (one pixel tile, K = 9*320: 24.1 -> 16.4 us) and loses on 4x4 / 8x8 maps (17.3 vs 16.3, 17.9 vs
+    # 12.7 us).  RFK_CONV_SPLITK=0 disables it, =2 also splits up to SPLITK_MAX_UNITS (pixel tiles x slices).
     import os
-    if os.environ.get("RFK_CONV_SPLITK", "0") != "1":
-        return 1
-    if taps != 9 or cin_pad % 64 != 0 or cin_pad < 128:
+    mode = os.environ.get("RFK_CONV_SPLITK", "1")
+    if mode == "0" or taps != 9 or cin_pad % 64 != 0 or cin_pad < 128:
         return 1
     m_tiles = (M + 127) // 128
-    if m_tiles * 9 <= SPLITK_MAX_UNITS:
+    if m_tiles == 1 and taps * cin_pad >= 2048:
         return 9
-    if m_tiles * 3 <= SPLITK_MAX_UNITS:
-        return 3
+    if mode == "2":
+        if m_tiles * 9 <= SPLITK_MAX_UNITS:
+            return 9
+        if m_tiles * 3 <= SPLITK_MAX_UNITS:
+            return 3
     return 1
+
+
+SPLITK_MAX_UNITS = 74
+
+
+def gemm_m_tiles(B, H, W):
+    """Number of 128-pixel tiles the conv kernel cuts [B,H,W] into (tile = NIMG x TH x TW with power-of-two TW, TH)."""
+    twl = min(max(W - 1, 0).bit_length(), 7)
+    thl = min(max(H - 1, 0).bit_length(), 7 - twl)
+    TW, TH = 1 << twl, 1 << thl
+    nimg = 128 // (TW * TH)
+    return -(-W // TW) * -(-H // TH) * -(-B // nimg)
 
 
 def conv_gemm_splitk_fused(act, cin_pad, wgt, n, taps, k_split, scale, shift, act_fn, out, out_off=0):
@@ -206,8 +217,8 @@ def conv_gemm_splitk_fused(act, cin_pad, wgt, n, taps, k_split, scale, shift, ac
     _chk(out, torch.bfloat16, "out")
     B, H, W, ld = act.shape
     n_pad = wgt.shape[0]
-    m_tiles = (B * H * W + 127) // 128
-    ws = workspace(("splitk_ws", n_pad, k_split), (k_split * B * H * W, n_pad), act.device, torch.float32)   # one slab per slice
+    m_tiles = gemm_m_tiles(B, H, W)
+    ws = workspace(("splitk_ws", n_pad, k_split, m_tiles), (k_split * m_tiles * 128, n_pad), act.device, torch.float32)   # one slab per slice
     cnt = workspace(("splitk_cnt",), (max(1024, 4 * m_tiles),), act.device, torch.int32)       # zero, kept zero
     call("rfk_conv_gemm_splitk_fused", act.data_ptr(), B, H, W, ld, cin_pad, _chk(wgt, torch.bfloat16).data_ptr(), n,
          n_pad, taps, k_split, ws.data_ptr(), n_pad, cnt.data_ptr(), _p(scale), _p(shift), ACT[act_fn],
