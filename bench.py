@@ -155,7 +155,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "rfn_J_hotpath_fwd", "pass": "forward (density evaluation); no backward", "frames_per_step": n},
+        "config": {"workload": "rfn_J_hotpath_fwd", "pass": "forward (density evaluation)", "frames_per_step": n},
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))

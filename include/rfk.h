@@ -219,7 +219,7 @@ int rfk_gauss_sample(const float* eps, const float* params, int n, int B, int HW
 int rfk_convlstm_pointwise(const float* cc, const float* c_prev, const float* peep,
                            float* h_out, float* c_next, int B, int Hc, int HW, void* stream);
 
-/* ---- backward building blocks (round 1: tested primitives, module autograd wiring is next) ------------
+/* ---- backward kernels (driven by Flow/training.py and Utils/training.py behind ListGlow.log_prob / ConvLSTM) -------------
  * Data gradient of a conv: rfk_conv_gemm on the tap-flipped, transposed weights (Wd[ci, co, ky, kx] = W[co, ci, 2-ky, 2-kx]).
  *
  * rfk_act_affine_bwd: backward of h = act(a*scale + shift) (Conv2dNorm + ActFun, Flow/glow_modules.py:139-147) from the

@@ -5,9 +5,9 @@ constructor arguments, ``forward`` signatures and ``state_dict`` keys (SURVEY.md
 checkpoint of the reference loads unchanged.  The arithmetic is not PyTorch's: every forward
 enqueues hand-written CUDA kernels through the C ABI (include/rfk.h).  There is no CPU path.
 
-Round-1 scope: forward / reverse evaluation (density, sampling).  Backward kernels are not
-written yet, so the modules refuse to run with autograd recording enabled instead of silently
-returning tensors without a graph.
+Training: ``ListGlow.log_prob`` (and ``ConvLSTM``) run under autograd through a tape-recording forward and a
+hand-written backward (Flow/training.py, Utils/training.py).  The individual modules below, called on their own
+with autograd recording enabled, refuse to run instead of silently returning tensors without a graph.
 """
 import torch
 import torch.nn as nn
@@ -23,8 +23,9 @@ TAP_SPLIT_MAX_N = 2304  # AffineCoupling: tap-split form of the last conv up to 
 
 def _require_no_grad():
     if torch.is_grad_enabled():
-        raise RuntimeError("recurrent-flows-msc_b200: backward kernels are not implemented yet; "
-                           "call the flow under torch.no_grad() (density evaluation / sampling)")
+        raise RuntimeError("recurrent-flows-msc_b200: this module has no stand-alone autograd path; call it under "
+                           "torch.no_grad() (density evaluation / sampling) or train through ListGlow.log_prob / ConvLSTM, "
+                           "which run the hand-written backward")
 
 
 _PARAM_EPOCH = [0]
