@@ -388,3 +388,25 @@ def test_convlstm_directional_derivative_cfg2_shape(rf):
                     p.add_(d, alpha=-sign * eps)
         ratios.append((vals[0] - vals[1]) / (2 * eps) / gnorm)
     assert any(abs(r - 1.0) < 0.05 for r in ratios), (ratios, float(loss0.detach()), gnorm)
+
+
+def test_graphed_train_step_with_new_batches(rf):
+    """GraphedTrainStep(static_inputs=...): step(batch) copies the batch into the captured tensors before the replay."""
+    m, x, conds, base, noise = _small_flow(rf, seed=9)
+    with torch.no_grad():
+        m.log_prob(x, conds, base, logdet=0, noise=noise)
+    opt = rf.FlatAdam(m.parameters(), lr=1e-3)
+    xs = x.clone()
+
+    def loss_fn():
+        _, nll = m.log_prob(xs, conds, base, logdet=0, noise=noise)
+        return nll.mean() / (math.log(2) * 256)
+
+    step = rf.GraphedTrainStep(loss_fn, opt, warmup=2, static_inputs=[xs])
+    l_same = float(step(x))
+    x2 = torch.flip(x, dims=(0, 3))
+    l_other = float(step(x2))
+    assert torch.equal(xs, x2)                      # the static tensor now holds the new batch
+    assert math.isfinite(l_same) and math.isfinite(l_other) and l_same != l_other
+    with pytest.raises(ValueError):
+        rf.GraphedTrainStep(loss_fn, opt, warmup=1)(x)   # no static_inputs declared
