@@ -410,3 +410,16 @@ def test_graphed_train_step_with_new_batches(rf):
     assert math.isfinite(l_same) and math.isfinite(l_other) and l_same != l_other
     with pytest.raises(ValueError):
         rf.GraphedTrainStep(loss_fn, opt, warmup=1)(x)   # no static_inputs declared
+
+
+def test_taped_forward_equals_inference_forward(rf):
+    """The tape-recording forward (unfused convs, fresh buffers) and the inference forward (fused back-to-back kernel,
+    workspace pool) evaluate the same function: z and nll agree to bf16-forward tolerance."""
+    m, x, conds, base, noise = _small_flow(rf, seed=13)
+    with torch.no_grad():
+        m.log_prob(x, conds, base, logdet=0, noise=noise)          # ActNorm init
+        z0, nll0 = m.log_prob(x, conds, base, logdet=0, noise=noise)
+    z1, nll1 = m.log_prob(x, conds, base, logdet=0, noise=noise)   # autograd recording on: taped path
+    assert nll1.requires_grad
+    assert rel(z1.detach(), z0) < 1e-2
+    torch.testing.assert_close(nll1.detach() / (math.log(2) * 256), nll0 / (math.log(2) * 256), rtol=1e-2, atol=2e-3)
