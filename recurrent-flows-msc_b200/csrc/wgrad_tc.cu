@@ -288,11 +288,23 @@ struct PairArgs {
   int inner_stages;              // pair-tile ring depth
   int tmem_cols;
   int small_is_x;                // 1: narrow = X (input channels), wide = dY;  0: narrow = dY (output channels), wide = X
+  int tpt;                       // taps per M = 128 tile: 2 (64-channel atoms, SWIZZLE_128B) or 4 (32-channel atoms, SWIZZLE_64B)
   int dw_ld, dw_rows, layout;
   const int* perm;
   float* dw;
   float* ws;
 };
+
+// MN-major SWIZZLE_64B descriptor: 32-element atoms (64-byte rows) one 8 KB box apart, 8-row K groups 512 B apart
+__device__ __forceinline__ uint64_t umma_desc_mnmajor64(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((128 * 64) >> 4) << 16;     // leading byte offset: next 32-channel atom (= next tap's box)
+  d |= (uint64_t)(512 >> 4) << 32;            // stride byte offset: next group of 8 pixel rows
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;                     // SWIZZLE_64B
+  return d;
+}
 
 __global__ void __launch_bounds__(WT_THREADS, 1) conv_wgrad_pairs_kernel(const __grid_constant__ CUtensorMap tmS,
                                                                         const __grid_constant__ CUtensorMap tmW,
@@ -300,7 +312,9 @@ __global__ void __launch_bounds__(WT_THREADS, 1) conv_wgrad_pairs_kernel(const _
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
-  const uint32_t o_bytes = (uint32_t)g.nbox * WT_BOX_BYTES, i_bytes = 2u * WT_BOX_BYTES;
+  const uint32_t o_bytes = (uint32_t)g.nbox * WT_BOX_BYTES, i_bytes = 2u * WT_BOX_BYTES;   // 2 x 16 KB or 4 x 8 KB
+  const uint32_t s_box = i_bytes / (uint32_t)g.tpt;          // one tap's box of the narrow operand
+  const int ngrp = (9 + g.tpt - 1) / g.tpt;                  // tap groups (one accumulator each): 5 pairs or 3 quads
   const uint32_t o_off = 0, i_off = 2u * o_bytes;
   const uint32_t bar_off = i_off + (uint32_t)g.inner_stages * i_bytes;
   const uint32_t bar_base = base + bar_off;
@@ -314,8 +328,8 @@ __global__ void __launch_bounds__(WT_THREADS, 1) conv_wgrad_pairs_kernel(const _
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int pg = blockIdx.y % g.pair_groups, nc = blockIdx.y / g.pair_groups;
   const int pair0 = pg * g.ppc;
-  const int npair = min(g.ppc, 5 - pair0);
-  const int n0 = nc * 256;
+  const int npair = min(g.ppc, ngrp - pair0);
+  const int n0 = nc * g.n_cols;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmS);
@@ -361,13 +375,14 @@ __global__ void __launch_bounds__(WT_THREADS, 1) conv_wgrad_pairs_kernel(const _
           tma_load_4d(base + o_off + so * o_bytes + bx * WT_BOX_BYTES, &tmW, o_full(so), n0 + bx * 64, x0, y0, i0);
         if (++so == 2) { so = 0; pho ^= 1u; }
         for (int pl = 0; pl < npair; ++pl) {
-          const int ta = 2 * (pair0 + pl), tb = ta + 1;
+          const int ta = g.tpt * (pair0 + pl), nt = min(g.tpt, 9 - ta);   // this group's taps (the last group is short)
           mbar_wait(i_empty(si), phi ^ 1u);
-          mbar_expect_tx(i_full(si), tb < 9 ? i_bytes : (uint32_t)WT_BOX_BYTES);
+          mbar_expect_tx(i_full(si), (uint32_t)nt * s_box);
           const uint32_t dst = base + i_off + si * i_bytes;
-          tma_load_4d(dst, &tmS, i_full(si), 0, x0 + g.sign * (ta % 3 - 1), y0 + g.sign * (ta / 3 - 1), i0);
-          if (tb < 9)
-            tma_load_4d(dst + WT_BOX_BYTES, &tmS, i_full(si), 0, x0 + g.sign * (tb % 3 - 1), y0 + g.sign * (tb / 3 - 1), i0);
+          for (int k = 0; k < nt; ++k) {
+            const int tp = ta + k;
+            tma_load_4d(dst + k * s_box, &tmS, i_full(si), 0, x0 + g.sign * (tp % 3 - 1), y0 + g.sign * (tp / 3 - 1), i0);
+          }
           if (++si == g.inner_stages) { si = 0; phi ^= 1u; }
         }
       }
@@ -386,11 +401,15 @@ __global__ void __launch_bounds__(WT_THREADS, 1) conv_wgrad_pairs_kernel(const _
         for (int pl = 0; pl < npair; ++pl) {
           mbar_wait(i_full(si), phi);
           tc_fence_after();
-          const uint64_t adesc = umma_desc_mnmajor(base + i_off + si * i_bytes);
+          // narrow side: 64-channel atoms (128-byte rows) or 32-channel atoms (64-byte rows, SWIZZLE_64B: atoms 8 KB apart,
+          // 8-row groups 512 B apart, 16 pixel rows = 1024 B per K step)
+          const uint64_t adesc = g.tpt == 2 ? umma_desc_mnmajor(base + i_off + si * i_bytes)
+                                            : umma_desc_mnmajor64(base + i_off + si * i_bytes);
+          const uint64_t a_step = g.tpt == 2 ? 128u : 64u;
           const uint32_t d_tmem = tmem_base + (uint32_t)(pl * g.n_cols);
 #pragma unroll
           for (int k = 0; k < 8; ++k)
-            umma_bf16(d_tmem, adesc + (uint64_t)(128 * k), bdesc + (uint64_t)(128 * k), idesc, (first && k == 0) ? 0u : 1u);
+            umma_bf16(d_tmem, adesc + a_step * k, bdesc + (uint64_t)(128 * k), idesc, (first && k == 0) ? 0u : 1u);
           umma_commit(i_empty(si));
           if (++si == g.inner_stages) { si = 0; phi ^= 1u; }
         }
@@ -438,9 +457,10 @@ __global__ void __launch_bounds__(256) wgrad_pairs_reduce_kernel(const PairArgs 
     const int w = (int)(t / 128);
     const int pg = w % g.pair_groups, nc = w / g.pair_groups;
     const int pl = col / g.n_cols;
-    const int tap = 2 * (pg * g.ppc + pl) + (rowi >> 6);
-    const int c = rowi & 63, n = nc * 256 + (col - pl * g.n_cols);
-    if (pg * g.ppc + pl >= 5 || tap >= 9 || c >= g.small_total || n >= g.big_total) continue;
+    const int atom = 128 / g.tpt;                                   // channels per tap inside the M = 128 tile
+    const int tap = g.tpt * (pg * g.ppc + pl) + rowi / atom;
+    const int c = rowi % atom, n = nc * g.n_cols + (col - pl * g.n_cols);
+    if (tap >= 9 || c >= g.small_total || n >= g.big_total) continue;
     float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;   // independent chains: the loads of several slices are in flight
     int sl = 0;
     for (; sl + 4 <= slices; sl += 4) {
@@ -484,11 +504,18 @@ int conv_wgrad_tc(const void* x, int x_ld, int cin, const void* dy, int dy_ld, i
     p.tiles_y = ceil_div(H, TH);
     p.tiles = p.tiles_x * p.tiles_y * ceil_div(B, NIMG);
     const int n_cols_total = (p.big_total + 15) / 16 * 16;
-    p.n_chunks = ceil_div(n_cols_total, 256);
-    p.n_cols = p.n_chunks == 1 ? n_cols_total : 256;
+    // narrow side <= 32 channels: FOUR taps per M = 128 tile (32-channel SWIZZLE_64B atoms) and the wide side in chunks of
+    // 128 columns -> three accumulators x 128 columns fit one CTA, so the wide operand is read once per chunk instead of
+    // once per tap-pair group (the pair form moves 3x the wide operand through L2 -> SM and is bound by that)
+    static const bool no_quads = [] { const char* e = getenv("RFK_WGRAD_NO_QUADS"); return e && e[0] == '1'; }();
+    p.tpt = (p.small_total <= 32 && !no_quads) ? 4 : 2;
+    const int chunk = p.tpt == 4 ? 128 : 256;
+    const int ngrp = (9 + p.tpt - 1) / p.tpt;
+    p.n_chunks = ceil_div(n_cols_total, chunk);
+    p.n_cols = p.n_chunks == 1 ? n_cols_total : chunk;
     p.nbox = ceil_div(p.n_cols, 64);
-    p.pair_groups = ceil_div(5, std::min(5, 512 / p.n_cols));
-    p.ppc = ceil_div(5, p.pair_groups);
+    p.pair_groups = ceil_div(ngrp, std::min(ngrp, 512 / p.n_cols));
+    p.ppc = ceil_div(ngrp, p.pair_groups);
     int cols = 32;
     while (cols < p.ppc * p.n_cols) cols <<= 1;
     p.tmem_cols = cols;
@@ -501,8 +528,12 @@ int conv_wgrad_tc(const void* x, int x_ld, int cin, const void* dy, int dy_ld, i
     if (p.inner_stages >= 2 && per_slice * slices * 4 <= ws_bytes) {
       const size_t smem = 1024 + (size_t)outer + (size_t)p.inner_stages * 2 * WT_BOX_BYTES + 8 * (4 + 2 * p.inner_stages + 2) + 16;
       CUtensorMap tmS, tmW;
-      int rc = encode_act_map(&tmS, who, "narrow side", p.small_is_x ? x : dy, p.small_total, p.small_is_x ? x_ld : dy_ld, B, H, W,
-                              TW, TH, NIMG, 64);
+      // the narrow side's map covers whole box rows when the row stride allows it (a 4-channel tensor declared as 4 channels
+      // makes every box row an 8-byte request, which TMA handles far slower than one 64-byte row); the extra channels are
+      // rows of the M tile that the reduce kernel never reads, so their contents do not matter
+      const int s_ld = p.small_is_x ? x_ld : dy_ld, s_box = p.tpt == 4 ? 32 : 64;
+      int rc = encode_act_map(&tmS, who, "narrow side", p.small_is_x ? x : dy, std::max(p.small_total, std::min(s_ld, s_box)),
+                              s_ld, B, H, W, TW, TH, NIMG, s_box);
       if (rc != RFK_OK) return rc;
       rc = encode_act_map(&tmW, who, "wide side", p.small_is_x ? dy : x, p.big_total, p.small_is_x ? dy_ld : x_ld, B, H, W, TW,
                           TH, NIMG, 64);
@@ -566,9 +597,13 @@ int conv_wgrad_tc(const void* x, int x_ld, int cin, const void* dy, int dy_ld, i
                       8 * (2 * WT_A_STAGES + 2 * g.b_stages + 2) + 16;
 
   CUtensorMap tmA, tmB;
-  int rc = encode_act_map(&tmA, who, "M-side", a_ptr, g.m_total, a_ld, B, H, W, TW, TH, NIMG, 64);
+  // maps cover whole box rows where the row stride allows it (short inner extents make TMA slow; the extra channels land in
+  // accumulator rows / columns that are never written back)
+  int rc = encode_act_map(&tmA, who, "M-side", a_ptr, std::max(g.m_total, std::min(a_ld, g.m_tiles * 128)), a_ld, B, H, W, TW,
+                          TH, NIMG, 64);
   if (rc != RFK_OK) return rc;
-  rc = encode_act_map(&tmB, who, "N-side", b_ptr, g.n_total, b_ld, B, H, W, TW, TH, NIMG, 64);
+  rc = encode_act_map(&tmB, who, "N-side", b_ptr, std::max(g.n_total, std::min(b_ld, g.n_chunks * g.nbox * 64)), b_ld, B, H, W,
+                      TW, TH, NIMG, 64);
   if (rc != RFK_OK) return rc;
 
   const int work = g.m_tiles * g.n_chunks * g.tap_groups;
