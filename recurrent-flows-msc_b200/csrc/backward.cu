@@ -414,7 +414,7 @@ __global__ void __launch_bounds__(256) taps_scatter_kernel(const float* __restri
 // Few channels (C = 4, 8: the two largest flow levels): no shared-memory staging at all -- a thread walks pixels (coalesced
 // along the pixel index for every channel plane), keeps the C x C outer-product sums in registers, and the sums are
 // reduced warp -> CTA (shared-memory atomics) -> global (C*C + C atomics per CTA).
-template <int C>
+template <int C, int OB>   // OB output rows per pass (C*OB accumulators in registers); C % OB == 0
 __global__ void __launch_bounds__(256) mix1x1_wgrad_small_kernel(const float* __restrict__ x, const float* __restrict__ dy, int HW,
                                                                  long long npix, float* __restrict__ dW, float* __restrict__ db) {
   pdl_trigger();
@@ -422,39 +422,41 @@ __global__ void __launch_bounds__(256) mix1x1_wgrad_small_kernel(const float* __
   __shared__ float red[C * C + C];
   for (int i = threadIdx.x; i < C * C + C; i += blockDim.x) red[i] = 0.0f;
   __syncthreads();
-  float acc[C][C], accb[C];
-#pragma unroll
-  for (int o = 0; o < C; ++o) {
-    accb[o] = 0.0f;
-#pragma unroll
-    for (int i = 0; i < C; ++i) acc[o][i] = 0.0f;
-  }
-  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < npix; p += (long long)gridDim.x * blockDim.x) {
-    const long long b = p / HW;
-    const long long base = b * C * HW + (p - b * HW);
-    float xv[C], dv[C];
-#pragma unroll
-    for (int c = 0; c < C; ++c) {
-      xv[c] = __ldg(x + base + (long long)c * HW);
-      dv[c] = __ldg(dy + base + (long long)c * HW);
-    }
-#pragma unroll
-    for (int o = 0; o < C; ++o) {
-      accb[o] += dv[o];
-#pragma unroll
-      for (int i = 0; i < C; ++i) acc[o][i] = fmaf(dv[o], xv[i], acc[o][i]);
-    }
-  }
   const int lane = threadIdx.x & 31;
+#pragma unroll 1
+  for (int o0 = 0; o0 < C; o0 += OB) {
+    float acc[OB][C], accb[OB];
 #pragma unroll
-  for (int o = 0; o < C; ++o) {
+    for (int o = 0; o < OB; ++o) {
+      accb[o] = 0.0f;
 #pragma unroll
-    for (int i = 0; i < C; ++i) {
-      const float v = warp_sum(acc[o][i]);
-      if (lane == 0) atomicAdd(&red[o * C + i], v);
+      for (int i = 0; i < C; ++i) acc[o][i] = 0.0f;
     }
-    const float vb = warp_sum(accb[o]);
-    if (lane == 0) atomicAdd(&red[C * C + o], vb);
+    for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < npix; p += (long long)gridDim.x * blockDim.x) {
+      const long long b = p / HW;
+      const long long base = b * C * HW + (p - b * HW);
+      float xv[C], dv[OB];
+#pragma unroll
+      for (int c = 0; c < C; ++c) xv[c] = __ldg(x + base + (long long)c * HW);
+#pragma unroll
+      for (int o = 0; o < OB; ++o) dv[o] = __ldg(dy + base + (long long)(o0 + o) * HW);
+#pragma unroll
+      for (int o = 0; o < OB; ++o) {
+        accb[o] += dv[o];
+#pragma unroll
+        for (int i = 0; i < C; ++i) acc[o][i] = fmaf(dv[o], xv[i], acc[o][i]);
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < OB; ++o) {
+#pragma unroll
+      for (int i = 0; i < C; ++i) {
+        const float v = warp_sum(acc[o][i]);
+        if (lane == 0) atomicAdd(&red[(o0 + o) * C + i], v);
+      }
+      const float vb = warp_sum(accb[o]);
+      if (lane == 0) atomicAdd(&red[C * C + o0 + o], vb);
+    }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < C * C + C; i += blockDim.x) atomicAdd(i < C * C ? dW + i : db + (i - C * C), red[i]);
@@ -597,13 +599,84 @@ extern "C" int rfk_taps_scatter(const float* dsum, void* dtaps, int ld, int B, i
   return check_launch("rfk_taps_scatter");
 }
 
+// Register-blocked variant for C % 4 == 0 (C = 12 ... 64): a thread owns a 4 x 4 block of dW and a share of the chunk's pixels,
+// so every pixel costs it 8 shared-memory loads for 16 FMAs (the kernel above does 2 loads per FMA and is LSU-bound on the
+// deep levels: 60-80 us for a few thousand pixels).
+__global__ void __launch_bounds__(256) mix1x1_wgrad_blocked_kernel(const float* __restrict__ x, const float* __restrict__ dy, int C,
+                                                                   int HW, long long npix, long long pix_per_cta,
+                                                                   float* __restrict__ dW, float* __restrict__ db) {
+  pdl_trigger();
+  pdl_wait();
+  extern __shared__ float sm[];
+  constexpr int LD = MW_CHUNK + 1;
+  float* xs = sm;
+  float* ds = sm + C * LD;
+  const long long p0 = blockIdx.x * pix_per_cta, p1 = min(npix, p0 + pix_per_cta);
+  const int Cq = C >> 2, nb = Cq * Cq;                 // 4 x 4 output blocks
+  const int nseg = max(1, 256 / nb);                   // pixel segments per chunk
+  const int blk = threadIdx.x % nb, seg = threadIdx.x / nb;
+  const bool active = threadIdx.x < nb * nseg;
+  const int bo = blk / Cq, bi = blk - bo * Cq;
+  float acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.0f;
+  float accb = 0.0f;
+  for (long long pc = p0; pc < p1; pc += MW_CHUNK) {
+    for (int e = threadIdx.x; e < C * MW_CHUNK; e += blockDim.x) {
+      const int c = e / MW_CHUNK, r = e % MW_CHUNK;
+      const long long p = pc + r;
+      float xv = 0.0f, dv = 0.0f;
+      if (p < p1) {
+        const long long b = p / HW;
+        const int q = (int)(p - b * HW);
+        xv = x[(b * C + c) * HW + q];
+        dv = dy[(b * C + c) * HW + q];
+      }
+      xs[c * LD + r] = xv;
+      ds[c * LD + r] = dv;
+    }
+    __syncthreads();
+    if (active) {
+      const float* dr = ds + 4 * bo * LD;
+      const float* xr = xs + 4 * bi * LD;
+      for (int r = seg; r < MW_CHUNK; r += nseg) {
+        const float d0 = dr[r], d1 = dr[LD + r], d2 = dr[2 * LD + r], d3 = dr[3 * LD + r];
+        const float x0 = xr[r], x1 = xr[LD + r], x2 = xr[2 * LD + r], x3 = xr[3 * LD + r];
+        acc[0][0] = fmaf(d0, x0, acc[0][0]); acc[0][1] = fmaf(d0, x1, acc[0][1]); acc[0][2] = fmaf(d0, x2, acc[0][2]); acc[0][3] = fmaf(d0, x3, acc[0][3]);
+        acc[1][0] = fmaf(d1, x0, acc[1][0]); acc[1][1] = fmaf(d1, x1, acc[1][1]); acc[1][2] = fmaf(d1, x2, acc[1][2]); acc[1][3] = fmaf(d1, x3, acc[1][3]);
+        acc[2][0] = fmaf(d2, x0, acc[2][0]); acc[2][1] = fmaf(d2, x1, acc[2][1]); acc[2][2] = fmaf(d2, x2, acc[2][2]); acc[2][3] = fmaf(d2, x3, acc[2][3]);
+        acc[3][0] = fmaf(d3, x0, acc[3][0]); acc[3][1] = fmaf(d3, x1, acc[3][1]); acc[3][2] = fmaf(d3, x2, acc[3][2]); acc[3][3] = fmaf(d3, x3, acc[3][3]);
+      }
+    }
+    {
+      const int c = threadIdx.x % C, l = threadIdx.x / C, nl = 256 / C;
+      if (l < nl) {
+        float sb = 0.0f;
+        for (int r = l; r < MW_CHUNK; r += nl) sb += ds[c * LD + r];
+        accb += sb;
+      }
+    }
+    __syncthreads();
+  }
+  if (active) {
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) atomicAdd(dW + (4 * bo + a) * C + 4 * bi + b, acc[a][b]);
+  }
+  if (threadIdx.x / C < 256 / C) atomicAdd(db + threadIdx.x % C, accb);
+}
+
 extern "C" int rfk_mix1x1_wgrad(const float* x, const float* dy, int B, int C, int HW, float* dW, float* db, void* stream) {
   RFK_REQUIRE(x && dy && dW && db && B > 0 && C > 0 && C <= 64 && HW > 0, "rfk_mix1x1_wgrad: null pointer or bad shape (C <= 64)");
   const long long npix = (long long)B * HW;
-  if (C == 4 || C == 8) {
+  if (C == 4 || C == 8 || (C == 12 && npix >= 65536)) {
     const int grid = (int)std::min<long long>((long long)sm_count() * 2, (npix + 255) / 256);
-    if (C == 4) RFK_LAUNCH(mix1x1_wgrad_small_kernel<4>, grid, 256, 0, (cudaStream_t)stream, x, dy, HW, npix, dW, db);
-    else RFK_LAUNCH(mix1x1_wgrad_small_kernel<8>, grid, 256, 0, (cudaStream_t)stream, x, dy, HW, npix, dW, db);
+    if (C == 4) RFK_LAUNCH((mix1x1_wgrad_small_kernel<4, 4>), grid, 256, 0, (cudaStream_t)stream, x, dy, HW, npix, dW, db);
+    else if (C == 8) RFK_LAUNCH((mix1x1_wgrad_small_kernel<8, 8>), grid, 256, 0, (cudaStream_t)stream, x, dy, HW, npix, dW, db);
+    else RFK_LAUNCH((mix1x1_wgrad_small_kernel<12, 6>), grid, 256, 0, (cudaStream_t)stream, x, dy, HW, npix, dW, db);
     return check_launch("rfk_mix1x1_wgrad");
   }
   long long ctas = std::min<long long>((long long)sm_count() * 4, (npix + MW_CHUNK - 1) / MW_CHUNK);
@@ -615,6 +688,17 @@ extern "C" int rfk_mix1x1_wgrad(const float* x, const float* dy, int B, int C, i
   if (!attr_set) {
     cudaFuncSetAttribute(mix1x1_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 64 * (MW_CHUNK + 1) * 4);
     attr_set = true;
+  }
+  static const bool blocked = [] { const char* e = getenv("RFK_MIXW_BLOCKED"); return !(e && e[0] == '0'); }();
+  if (C % 4 == 0 && C >= 32 && blocked) {   // fewer 4x4 blocks than threads would only multiply the atomics (C=16: 185 vs 17 us)
+    static bool battr = false;
+    if (!battr) {
+      cudaFuncSetAttribute(mix1x1_wgrad_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 64 * (MW_CHUNK + 1) * 4);
+      battr = true;
+    }
+    RFK_LAUNCH(mix1x1_wgrad_blocked_kernel, (int)ctas, 256, (size_t)2 * C * (MW_CHUNK + 1) * sizeof(float), (cudaStream_t)stream, x,
+               dy, C, HW, npix, ppc, dW, db);
+    return check_launch("rfk_mix1x1_wgrad");
   }
   RFK_LAUNCH(mix1x1_wgrad_kernel, (int)ctas, 256, (size_t)2 * C * (MW_CHUNK + 1) * sizeof(float), (cudaStream_t)stream, x, dy, C,
              HW, npix, ppc, dW, db);

@@ -133,7 +133,8 @@ def test_coupling_taps_bwd(ops, clamp, B, C, H, W):
     assert float(dt[..., 9 * C:].abs().max()) == 0.0 if dt.shape[-1] > 9 * C else True
 
 
-@pytest.mark.parametrize("B,C,H,W", [(3, 12, 32, 32), (2, 6, 7, 5), (4, 48, 8, 8), (5, 64, 2, 2), (2, 24, 16, 16)])
+@pytest.mark.parametrize("B,C,H,W", [(3, 12, 32, 32), (2, 6, 7, 5), (4, 48, 8, 8), (5, 64, 2, 2), (2, 24, 16, 16),
+                                     (70, 12, 32, 32), (40, 4, 32, 32), (30, 8, 16, 16), (9, 32, 4, 4)])
 def test_mix1x1_wgrad(ops, B, C, H, W):
     g = torch.Generator().manual_seed(C + B)
     x = torch.randn(B, C, H, W, generator=g)
