@@ -147,7 +147,17 @@ class GlowStep(nn.Module):
         else:
             y = x.clone() if own_ctx else x   # the coupling inverse works in place
             self.affine.finish(kind, t, y, ld, True)
-            self.norm.maybe_initialize(y)
+            if not self.norm.is_initialized():
+                # reference order (Flow/glow.py:37-40): affine^-1, invconv^-1, THEN the ActNorm -- a fresh training-mode
+                # ActNorm takes its data-dependent statistics from the invconv^-1 output
+                _, W_inv, per_pixel = self.invconv.matrices()
+                y = ops.mix1x1(y, W_inv, None)
+                self.norm.maybe_initialize(y)
+                out = ops.actnorm(y, self.norm.bias.data, self.norm.logs.data, True)
+                if ld is not None:
+                    ld -= self._dlogdet(H * W)
+                _ctx.z1_packed = False
+                return out, _ld_end(ld, extra)
             _, _, Wr, br, _ = self._folded()
             dl = None if ld is None else self._dlogdet(H * W)
             out = ops.mix1x1(y, Wr, br, side=_ctx.nn_in, side_n=C // 2, side_off=cc, logdet=ld, addend=dl, alpha=-1.0)
@@ -284,6 +294,14 @@ class ListGlow(nn.Module):
         params = torch.empty(B, 2 * self._z_channels, H, W, device=dev, dtype=torch.float32)
         return self.prior[4].fused(a2, params)
 
+    def _wants_grad(self, x, condition, base_condition):
+        """The tape-recording path is taken only when something could receive a gradient: a parameter of a training-mode
+        flow, or an input that requires grad.  An eval-mode call outside torch.no_grad() (the reference's evaluation code)
+        whose inputs need no gradient runs the inference kernels."""
+        if any(torch.is_tensor(t) and t.requires_grad for t in [x, base_condition] + list(condition)):
+            return True
+        return self.training and any(p.requires_grad for p in self.parameters())
+
     def log_prob(self, x, condition, base_condition, logdet=0, noise=None):
         """Flow/glow.py:128-141.  Returns (z, nll[B]).  ``noise`` optionally injects the dequantisation draw."""
         assert isinstance(condition, list), "Condition is not a list, make sure it fits L"
@@ -293,19 +311,20 @@ class ListGlow(nn.Module):
             b, c, h, w = x.size()
             obj_unif = -np.log(2 ** self.n_bits) * (c * h * w) * torch.ones(b, device=x.device)
             x = x + noise
-        if torch.is_grad_enabled():
+        if torch.is_grad_enabled() and self._wants_grad(x, condition, base_condition):
             # training: tape-recording forward + hand-written backward kernels (Flow/training.py)
             from .training import log_prob_with_grad
             if torch.is_tensor(logdet) and logdet.requires_grad:
                 raise NotImplementedError("recurrent-flows-msc_b200: gradients w.r.t. the logdet argument are not implemented")
             obj0 = obj_unif + (logdet.detach() if torch.is_tensor(logdet) else logdet)
             return log_prob_with_grad(self, x, condition, base_condition, obj0)
-        z, obj = self.f(x, condition, logdet)
-        if not torch.is_tensor(obj) or obj.dim() != 1:
-            obj = torch.zeros(z.shape[0], device=z.device) + obj
-        obj = obj + obj_unif
-        ops.gauss_logp(z, 0, self._prior_params(base_condition), z.shape[1], ops.PAIR_SPLIT, "exp", obj)
-        return z, -obj
+        with torch.no_grad():
+            z, obj = self.f(x, condition, logdet)
+            if not torch.is_tensor(obj) or obj.dim() != 1:
+                obj = torch.zeros(z.shape[0], device=z.device) + obj
+            obj = obj + obj_unif
+            ops.gauss_logp(z, 0, self._prior_params(base_condition), z.shape[1], ops.PAIR_SPLIT, "exp", obj)
+            return z, -obj
 
     def sample(self, z, condition, base_condition, num_samples=32, temperature=0.8, eval_params=False,
                eps_prior=None, eps_list=None):

@@ -317,7 +317,11 @@ def _log_prob_fwd(flow, x, conds, base_condition, obj0):
             cond = ops.f32c(conds[l])
             assert cond.shape[2:4] == z.shape[2:4], "condition and x in affine needs to match"
             cc = cond.shape[1]
-            template = _nhwc(B, z.shape[2], z.shape[3], z.shape[1] // 2 + cc, dev)
+            # zero-filled ALWAYS: only the condition channels [0, cc) are written here (every GlowStep fills the z1 region of its
+            # own clone), but Split2d's convcond reads cin_pad(cc) channels of the template itself -- stale bf16 bit patterns
+            # there (NaN times a zero weight is NaN) would poison the log-density
+            ld_t = ops.cin_pad(z.shape[1] // 2 + cc)
+            template = torch.zeros(B, z.shape[2], z.shape[3], ld_t, device=dev, dtype=torch.bfloat16)
             ops.pack_nhwc(cond, 0, cc, template, 0)
         elif isinstance(mod, Split2d):
             z = _split_fwd(mod, z, obj, template, l, tape)

@@ -24,7 +24,9 @@ class FlatAdam:
         dev = self.params[0].device
         if dev.type != "cuda":
             raise RuntimeError("recurrent-flows-msc_b200: FlatAdam needs CUDA parameters (there is no CPU path)")
-        self.lr, self.betas, self.eps = float(lr), (float(betas[0]), float(betas[1])), float(eps)
+        self.betas, self.eps = (float(betas[0]), float(betas[1])), float(eps)
+        # torch.optim-style handle for LR schedulers (RFN/trainer.py:100,200 write param_groups[0]['lr'])
+        self.param_groups = [{"params": self.params, "lr": float(lr), "betas": self.betas, "eps": self.eps}]
         self.group, self.world = process_group, int(world_size)
         self.n = sum(p.numel() for p in self.params)
         self.n_pad = (self.n + 3) // 4 * 4
@@ -42,6 +44,31 @@ class FlatAdam:
                 p.data = view
                 off += n
         invalidate_caches()
+
+    @property
+    def lr(self):
+        return float(self.param_groups[0]["lr"])
+
+    @lr.setter
+    def lr(self, v):
+        self.param_groups[0]["lr"] = float(v)
+
+    def state_dict(self):
+        """exp_avg / exp_avg_sq / step (flat, in parameter order) + the hyper-parameters; what Solver.checkpoint stores as
+        'optimizer_state_dict' (RFN/trainer.py:281)."""
+        return {"state": {"exp_avg": self.exp_avg[:self.n].clone(), "exp_avg_sq": self.exp_avg_sq[:self.n].clone(),
+                          "step": self.step_t.clone()},
+                "param_groups": [{"lr": self.lr, "betas": self.betas, "eps": self.eps, "n_params": self.n}]}
+
+    def load_state_dict(self, sd):
+        g = sd["param_groups"][0]
+        if g.get("n_params", self.n) != self.n:
+            raise ValueError(f"FlatAdam.load_state_dict: {g.get('n_params')} parameters saved, {self.n} here")
+        self.lr, self.betas, self.eps = g["lr"], tuple(g["betas"]), g["eps"]
+        with torch.no_grad():
+            self.exp_avg[:self.n].copy_(sd["state"]["exp_avg"])
+            self.exp_avg_sq[:self.n].copy_(sd["state"]["exp_avg_sq"])
+            self.step_t.copy_(sd["state"]["step"])
 
     def zero_grad(self, set_to_none=True):
         for p in self.params:

@@ -1,0 +1,151 @@
+"""GPU parity at the FULL depth and batch of the BASELINE configurations: the bf16 error of the
+coupling convolutions grows through L5 K10 / K15, which is where the 1e-2 gate matters.
+
+  * configuration J (RFN/default_rfn_job.sh): L=5, K=10, B=30: log_prob and sample vs the CPU oracle;
+  * configuration D (main_rfn.py defaults): 3x64x64, L=5, K=15, B=4;
+  * BASELINE config 2: ConvLSTM 64 -> 64, 3x3, 64x64 maps, T=10, B=32;
+  * the training path with a level whose NHWC template has no pad columns (half + cc == 32, cc == 16: ADVICE round 1);
+  * eval-mode log_prob outside torch.no_grad() runs the inference kernels."""
+import math
+import types
+
+import pytest
+import torch
+
+import oracle as O
+
+pytestmark = pytest.mark.gpu
+BF16_TOL = 1e-2
+
+GLOW_ARGS = dict(LU_decomposed=True, n_units_affine=256, non_lin_glow="relu", clamp_type="realnvp",
+                 flow_norm="actnorm", flow_batchnorm_momentum=0.0, learn_prior=True, n_units_prior=512,
+                 make_conditional=True, base_norm="actnorm", split2d_act="softplus", L=5, K=10, n_bits=8)
+
+
+@pytest.fixture(scope="module")
+def rf():
+    import recurrent_flows_msc_b200 as r
+    return r
+
+
+def max_rel(a, b):
+    b = b.double().cpu()
+    return float((a.double().cpu() - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def trained_like(m, seed, ws=0.01, ps=0.05):
+    gen = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for name, p in m.named_parameters():
+            p.add_(torch.randn(p.shape, generator=gen) * (ws if "conv.weight" in name else ps))
+        for name, b in m.named_buffers():
+            if name.endswith("initialized"):
+                b.fill_(1)
+
+
+def _full_depth(rf, B, C, K, cond_ch, base_ch, seed):
+    a = dict(GLOW_ARGS, K=K)
+    cond_sizes = [[B, c, 32 >> l, 32 >> l] for l, c in enumerate(cond_ch)]
+    torch.manual_seed(0)
+    with torch.no_grad():
+        m = rf.ListGlow([B, C, 64, 64], cond_sizes, [B, base_ch, 2, 2], types.SimpleNamespace(**a)).eval()
+        trained_like(m, seed)
+        sd = {k: v.clone() for k, v in m.state_dict().items()}
+        m = m.cuda()
+        g = torch.Generator().manual_seed(seed + 1)
+        x = torch.floor(torch.rand(B, C, 64, 64, generator=g) * 256) / 256 - 0.5
+        noise = torch.rand(B, C, 64, 64, generator=g) / 256
+        conds = [torch.randn(*s, generator=g) for s in cond_sizes]
+        base = torch.randn(B, base_ch, 2, 2, generator=g)
+        z_ref, nll_ref = O.listglow_log_prob(x, conds, base, sd, 5, K, 8, noise=noise, learn_prior=True)
+        z, nll = m.log_prob(x.cuda(), [c.cuda() for c in conds], base.cuda(), logdet=0, noise=noise.cuda())
+        chw = C * 64 * 64
+        bpd, bpd_ref = nll.cpu() / (math.log(2) * chw), nll_ref / (math.log(2) * chw)
+        ez, eb = max_rel(z, z_ref), float((bpd - bpd_ref).abs().max())
+        cz = C * 64
+        eps_prior = torch.randn(B, cz, 2, 2, generator=g)
+        eps = [torch.randn(B, (2 * C) << l, 32 >> l, 32 >> l, generator=g) for l in range(4)]
+        x_ref = O.listglow_sample(conds, base, sd, 5, K, eps_prior, eps, 0.7, learn_prior=True)
+        xs = m.sample(None, [c.cuda() for c in conds], base.cuda(), num_samples=B, temperature=0.7,
+                      eps_prior=eps_prior.cuda(), eps_list=[e.cuda() for e in eps])
+        ex = max_rel(xs, x_ref)
+        print(f"L5 K{K} B{B} C{C}: z err {ez:.3e} (max-norm rel), bits/dim abs err {eb:.3e} (ref mean {float(bpd_ref.mean()):.3f}), "
+              f"sample err {ex:.3e}")
+        assert ez < BF16_TOL
+        torch.testing.assert_close(bpd, bpd_ref, rtol=BF16_TOL, atol=2e-3)
+        assert ex < 2 * BF16_TOL
+
+
+def test_listglow_config_J_full_depth(rf):
+    _full_depth(rf, 30, 1, 10, [16, 32, 64, 128, 256], 256, 2)
+
+
+def test_listglow_config_D_full_depth(rf):
+    _full_depth(rf, 4, 3, 15, [32, 64, 128, 256, 384], 261, 4)
+
+
+def test_convlstm_cfg2_full_size(rf):
+    """BASELINE config 2 at full size: 64 hidden channels, 3x3, 64x64 maps, T=10, B=32 (the fused GEMM + cell-update
+    kernel on 131 072 pixels per step)."""
+    torch.manual_seed(0)
+    with torch.no_grad():
+        m = rf.ConvLSTM(64, 64, [3, 3]).eval()
+        w, b = m.LSTMlayer.conv[0].weight.clone(), m.LSTMlayer.conv[0].bias.clone()
+        m = m.cuda()
+        x = torch.randn(32, 10, 64, 64, 64, generator=torch.Generator().manual_seed(1))
+        out_ref, h_ref, c_ref = O.convlstm(x, w, b)
+        out, h, c = m(x.cuda())
+        eo, ec = max_rel(out, out_ref), max_rel(c, c_ref)
+        print(f"cfg2 B32 T10: h err {eo:.3e}, c err {ec:.3e}")
+        assert eo < BF16_TOL and ec < BF16_TOL
+        assert torch.equal(h, out[:, -1])
+
+
+def test_training_template_without_pad_columns(rf):
+    """half + cc == 32 with cc == 16: the level's NHWC template has no pad columns, and Split2d's convcond reads
+    cin_pad(cc) = 32 channels of it.  A template allocated with torch.empty would expose stale memory (NaN x 0 = NaN)."""
+    B = 3
+    a = dict(GLOW_ARGS, L=2, K=2, n_units_affine=64, n_units_prior=32)
+    cond_sizes = [[B, 16, 8, 8], [B, 16, 4, 4]]          # level 1: C = 32 -> half 16, cc 16 -> 32 = cin_pad
+    torch.manual_seed(0)
+    m = rf.ListGlow([B, 8, 16, 16], cond_sizes, [B, 8, 4, 4], types.SimpleNamespace(**a)).train()
+    trained_like(m, 3, 0.03, 0.1)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    m = m.cuda()
+    g = torch.Generator().manual_seed(1)
+    x = torch.floor(torch.rand(B, 8, 16, 16, generator=g) * 256) / 256 - 0.5
+    noise = torch.rand(B, 8, 16, 16, generator=g) / 256
+    conds = [torch.randn(*s, generator=g) for s in cond_sizes]
+    base = torch.randn(B, 8, 4, 4, generator=g)
+    # poison the caching allocator's free blocks with NaN bit patterns of the sizes the template would take
+    for _ in range(3):
+        junk = [torch.full((B, 8, 8, 32), float("nan"), device="cuda", dtype=torch.bfloat16) for _ in range(8)]
+        del junk
+    z, nll = m.log_prob(x.cuda(), [c.cuda() for c in conds], base.cuda(), logdet=0, noise=noise.cuda())
+    assert torch.isfinite(nll).all() and nll.requires_grad
+    nll.mean().backward()
+    assert all(torch.isfinite(p.grad).all() for p in m.parameters() if p.grad is not None)
+    _, nll_ref = O.listglow_log_prob(x, conds, base, sd, 2, 2, 8, noise=noise, learn_prior=True)
+    torch.testing.assert_close(nll.detach().cpu(), nll_ref, rtol=BF16_TOL, atol=0.5)
+
+
+def test_eval_log_prob_outside_no_grad_uses_inference_path(rf):
+    B = 2
+    a = dict(GLOW_ARGS, L=2, K=1, n_units_affine=64, n_units_prior=32)
+    cond_sizes = [[B, 4, 8, 8], [B, 4, 4, 4]]
+    torch.manual_seed(0)
+    m = rf.ListGlow([B, 1, 16, 16], cond_sizes, [B, 8, 4, 4], types.SimpleNamespace(**a))
+    trained_like(m, 3, 0.03, 0.1)
+    m = m.cuda().eval()
+    x = torch.rand(B, 1, 16, 16).cuda() - 0.5
+    conds = [torch.randn(*s).cuda() for s in cond_sizes]
+    base = torch.randn(B, 8, 4, 4).cuda()
+    noise = torch.rand(B, 1, 16, 16).cuda() / 256
+    z, nll = m.log_prob(x, conds, base, noise=noise)           # grad enabled, eval mode, no input needs a gradient
+    assert not nll.requires_grad and not z.requires_grad
+    with torch.no_grad():
+        z2, nll2 = m.log_prob(x, conds, base, noise=noise)
+    assert torch.equal(nll, nll2)
+    xg = x.clone().requires_grad_()                              # an input that needs a gradient -> tape path
+    _, nll3 = m.log_prob(xg, conds, base, noise=noise)
+    assert nll3.requires_grad

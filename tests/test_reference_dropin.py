@@ -1,4 +1,4 @@
-"""Drop-in check against the real reference (build container only: /root/reference is absent on the GPU box).
+"""Drop-in check against the real reference (/root/reference in the build container, baseline/_ref on the GPU box).
 
 Builds the reference's RFN (RFN/RFN_new.py, main_rfn.py defaults) twice -- stock, and after
 recurrent_flows_msc_b200.install_into(Flow, Utils) -- and checks the two models expose identical
@@ -12,7 +12,9 @@ from unittest.mock import MagicMock
 import pytest
 import torch
 
-REF = os.environ.get("RFMSC_REFERENCE", "/root/reference")
+from ref_helpers import reference_dir
+
+REF = reference_dir() or "/nonexistent"   # /root/reference here, the staged baseline/_ref on the GPU box
 pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "RFN")), reason="reference checkout not present")
 
 
