@@ -44,12 +44,15 @@ def trained_like(m, seed, ws=0.01, ps=0.05):
 
 
 def _full_depth(rf, B, C, K, cond_ch, base_ch, seed):
+    """Weights: random init + a perturbation small enough that the 50..75-step flow stays in a trained model's regime
+    (bits/dim O(10); the K=2 tests' scale compounds to > 8000 bits/dim at K=10, where exp(-log_scale) of the reverse pass
+    amplifies every rounding error and the comparison measures the conditioning of the map, not the kernels)."""
     a = dict(GLOW_ARGS, K=K)
     cond_sizes = [[B, c, 32 >> l, 32 >> l] for l, c in enumerate(cond_ch)]
     torch.manual_seed(0)
     with torch.no_grad():
         m = rf.ListGlow([B, C, 64, 64], cond_sizes, [B, base_ch, 2, 2], types.SimpleNamespace(**a)).eval()
-        trained_like(m, seed)
+        trained_like(m, seed, 0.004, 0.02)
         sd = {k: v.clone() for k, v in m.state_dict().items()}
         m = m.cuda()
         g = torch.Generator().manual_seed(seed + 1)
