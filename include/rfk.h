@@ -267,6 +267,25 @@ int rfk_gauss_logp_bwd(const float* z, int z_C, int z_off, const float* params, 
 int rfk_pack_weight(const float* src, int N, int Cin, int taps, int mode, const int* perm, int rows, int kp,
                     void* dst, int rows_pad, int ktot, void* stream);
 
+/* Batched refresh of parameter-derived tensors: ONE launch per kind for a whole model, driven by a device table of
+ * 24 x 64-bit words per entry (pointers and integers alike; csrc/prepare.cu documents the word layout of each kind).
+ * They replace, per optimizer step, ~340 rfk_pack_weight launches and ~1500 ATen launches that rebuilt the folded
+ * ActNorm . InvConv matrices (Flow/glow_modules.py:188-205) and the per-channel (scale, shift) of every ActNorm /
+ * Conv2dZeros (Flow/glow_modules.py:41-50,120).
+ *   rfk_pack_weights_batched    entries = the arguments of rfk_pack_weight; max_elements = largest rows_pad*ktot
+ *   rfk_affine_prepare_batched  scale = exp(f*logs), shift = bias*scale
+ *   rfk_fold_prepare_batched    Wf = P (L o mask + I)(U o mask^T + diag(sign_s e^log_s)) diag(e^logs), its transpose,
+ *                               bf = Wf bias, {per-pixel log-det, HW * per-pixel log-det}
+ *   rfk_fold_backward_batched   (dWf, dbf, g_sum = sum_b dloss/dlogdet[b]) -> ACCUMULATES d bias, d logs, d lower, d upper,
+ *                               d log_s (autograd equivalent of Flow/glow_modules.py:33-54,188-205)
+ * rfk_add_channels: dst[:, dst_off : dst_off+n] += src[:, src_off : src_off+n] (fp32 NCHW). */
+int rfk_pack_weights_batched(const long long* table, int n_entries, long long max_elements, void* stream);
+int rfk_affine_prepare_batched(const long long* table, int n_entries, void* stream);
+int rfk_fold_prepare_batched(const long long* table, int n_entries, void* stream);
+int rfk_fold_backward_batched(const long long* table, int n_entries, const float* g_sum, void* stream);
+int rfk_add_channels(float* dst, int dst_C, int dst_off, const float* src, int src_C, int src_off, int n, int B, int HW,
+                     void* stream);
+
 /* Adam over all parameters in one launch (torch.optim.Adam without weight decay / amsgrad; the reference trains with
  * Adam, RFN/trainer.py).  p, g, m, v: flat fp32 buffers of n elements (n % 4 == 0, 16-byte aligned); g is multiplied by
  * grad_scale first (1/world after a sum-allreduce); *step = the 1-based step count, on the device (graph replay). */

@@ -18,6 +18,7 @@ import torch.nn as nn
 
 from .. import ops
 from ..Utils.modules import ActFun
+from .. import derived
 from .glow_modules import (ActNorm, AffineCoupling, BatchNormFlow, Conv2dNorm, Conv2dZeros, InvConv,  # noqa: F401
                            Split2d, Squeeze2d, _Ctx, _ld_begin, _ld_end, _require_no_grad, _Versioned)
 
@@ -67,20 +68,41 @@ class GlowStep(nn.Module):
             return Wf, bf, Wr, br, (per_pixel + logs.sum()).reshape(())
         return self._cache.get("fold", (self.norm.bias, self.norm.logs) + self.invconv._params(), build)
 
-    def _folded_fwd(self):
-        """(Wf, bf, per-pixel log-det) of the forward direction only (no matrix inverses: density evaluation, training)."""
+    def _folded_fwd(self, hw):
+        """Forward direction only (no matrix inverses: density evaluation, training), for maps of hw pixels:
+        (Wf, bf, per-pixel log-det (0-dim), Wf^T, hw * per-pixel log-det [1]).  In the LU form the entry is registered for
+        the batched in-place refresh after optimizer steps (derived.py, rfk_fold_prepare_batched)."""
+        inv = self.invconv
+
         def build():
-            W, per_pixel = self.invconv.weight_fwd()
+            W, per_pixel = inv.weight_fwd()
             logs = self.norm.logs.detach().float().reshape(-1)
             bias = self.norm.bias.detach().float().reshape(-1)
             Wf = (W * torch.exp(logs)[None, :]).contiguous()
-            return Wf, torch.mv(Wf, bias).contiguous(), (per_pixel + logs.sum()).reshape(())
-        return self._cache.get("fold_f", (self.norm.bias, self.norm.logs) + self.invconv._params(), build)
+            pp = (per_pixel + logs.sum()).reshape(1)
+            ld = torch.cat([pp, pp * hw]).contiguous()
+            return Wf, torch.mv(Wf, bias).contiguous(), ld[0], Wf.t().contiguous(), ld[1:2], ld
+
+        def register(cache, key, params, slot):
+            if not inv.LU_decomposed:
+                return
+            Wf, bf, _, WfT, _, ld = slot[1]
+            perm = inv.__dict__.get("_perm32")
+            if perm is None or perm.device != Wf.device:
+                perm = inv.p.argmax(dim=1).to(torch.int32).contiguous()    # row i of P has its one at column perm[i]
+                inv.__dict__["_perm32"] = perm
+            ptrs = [self.norm.bias, self.norm.logs, inv.lower, inv.upper, inv.log_s, inv.sign_s]
+            if not all(t.dtype == torch.float32 and t.is_contiguous() and t.is_cuda for t in ptrs):
+                return
+            C = inv.w_shape[0]
+            derived.REFRESHER.register("fold", cache, key, params, slot,
+                                       [t.data_ptr() for t in ptrs] + [perm.data_ptr(), C, hw, Wf.data_ptr(), WfT.data_ptr(),
+                                                                       bf.data_ptr(), ld.data_ptr()], (Wf, bf, WfT, ld, perm))
+        return self._cache.get(("fold_f", hw), (self.norm.bias, self.norm.logs) + inv._params(), build, register)
 
     def _dlogdet(self, hw):
         """H*W*(sum logs + log|det W|) as a cached device scalar (Flow/glow_modules.py:43,196)."""
-        return self._cache.get(("dl", hw), (self.norm.bias, self.norm.logs) + self.invconv._params(),
-                               lambda: (self._folded_fwd()[2] * hw).reshape(1).contiguous())
+        return self._folded_fwd(hw)[4]
 
     def forward(self, x, condition, logdet, reverse, _ctx=None):
         _require_no_grad()
@@ -119,14 +141,14 @@ class GlowStep(nn.Module):
             if pend is not None and pend[2].data_ptr() == x.data_ptr() and self.norm.is_initialized():
                 # the previous step's coupling tail (tap gather + affine) is still pending: absorb it into this step's mix
                 _ctx.pending = None
-                Wf, bf, _ = self._folded_fwd()
+                Wf, bf = self._folded_fwd(H * W)[:2]
                 dl = None if ld is None else self._dlogdet(H * W)
                 y = ops.coupling_taps_mix(pend[1], x, *pend[0].tail_params(), pend[3], False, Wf, bf,
                                           side=_ctx.nn_in, side_n=C // 2, side_off=cc, logdet=ld, addend=dl, alpha=1.0)
             else:
                 _ctx.flush()
                 self.norm.maybe_initialize(x)
-                Wf, bf, _ = self._folded_fwd()
+                Wf, bf = self._folded_fwd(H * W)[:2]
                 dl = None if ld is None else self._dlogdet(H * W)
                 y = ops.mix1x1(x, Wf, bf, side=_ctx.nn_in, side_n=C // 2, side_off=cc, logdet=ld, addend=dl, alpha=1.0)
             _ctx.z1_packed = True

@@ -12,7 +12,7 @@ with autograd recording enabled, refuse to run instead of silently returning ten
 import torch
 import torch.nn as nn
 
-from .. import ops
+from .. import derived, ops
 from ..Utils.utils import split_feature  # noqa: F401  (re-exported like the reference)
 from ..Utils.modules import ActFun
 
@@ -38,20 +38,30 @@ def invalidate_caches():
     _PARAM_EPOCH[0] += 1
 
 
+def _ver_of(params):
+    return (_PARAM_EPOCH[0],) + tuple((p.data_ptr(), p._version) for p in params)
+
+
 class _Versioned:
     """Cache of tensors derived from parameters, rebuilt when a parameter is modified in place
-    (optimizer step, load_state_dict) or re-allocated (.to(), .cuda()), or after invalidate_caches()."""
+    (optimizer step, load_state_dict) or re-allocated (.to(), .cuda()), or after invalidate_caches().
+
+    ``refresh`` (optional callback(cache, key, params, slot)) registers a freshly built entry with derived.REFRESHER, which
+    rewrites such entries IN PLACE with one batched kernel per kind after an optimizer step and re-stamps them, so that a
+    training loop never takes the rebuild path again."""
 
     def __init__(self):
         self._store = {}
 
-    def get(self, key, params, build):
-        ver = (_PARAM_EPOCH[0],) + tuple((p.data_ptr(), p._version) for p in params)
+    def get(self, key, params, build, refresh=None):
+        ver = _ver_of(params)
         hit = self._store.get(key)
         if hit is None or hit[0] != ver:
             with torch.no_grad():
-                hit = (ver, build())
+                hit = [ver, build()]
             self._store[key] = hit
+            if refresh is not None:
+                refresh(self, key, params, hit)
         return hit[1]
 
     def clear(self):
@@ -146,7 +156,7 @@ class ActNorm(nn.Module):
         def build():
             s = torch.exp(self.logs.detach().float().reshape(-1))
             return s.contiguous(), (self.bias.detach().float().reshape(-1) * s).contiguous()
-        return self._cache.get("affine", (self.bias, self.logs), build)
+        return self._cache.get("affine", (self.bias, self.logs), build, derived.reg_affine(self.logs, self.bias, 1))
 
     def forward(self, input, logdet, reverse):
         _require_no_grad()
@@ -176,25 +186,26 @@ class Conv2dZeros(nn.Module):
         self._cache = _Versioned()
 
     def packed(self, key="id", in_perm=None):
-        return self._cache.get(("w", key), (self.conv.weight,), lambda: ops.pack_conv_weight(self.conv.weight, in_perm))
+        return self._cache.get(("w", key), (self.conv.weight,), lambda: ops.pack_conv_weight(self.conv.weight, in_perm), derived.reg_pack)
 
     def packed_dgrad(self, key="id", out_perm=None):
         """Weights of the data-gradient convolution (flipped taps, in/out channels swapped), rows in staging order."""
-        return self._cache.get(("wd", key), (self.conv.weight,), lambda: ops.pack_dgrad_weight(self.conv.weight, out_perm))
+        return self._cache.get(("wd", key), (self.conv.weight,), lambda: ops.pack_dgrad_weight(self.conv.weight, out_perm), derived.reg_pack)
 
     def packed_dgrad_taps(self, key="id", out_perm=None):
         """Tap-split form of the data-gradient weights (3x3 convs with few input channels: one GEMM with N = 9*Cin)."""
-        return self._cache.get(("wd9", key), (self.conv.weight,), lambda: ops.pack_dgrad_taps_weight(self.conv.weight, out_perm))
+        return self._cache.get(("wd9", key), (self.conv.weight,), lambda: ops.pack_dgrad_taps_weight(self.conv.weight, out_perm), derived.reg_pack)
 
     def packed_taps(self):
         """Tap-split 1x1 form of the 3x3 weight (ops.pack_tap_split_weight), cached."""
-        return self._cache.get(("w9",), (self.conv.weight,), lambda: ops.pack_tap_split_weight(self.conv.weight))
+        return self._cache.get(("w9",), (self.conv.weight,), lambda: ops.pack_tap_split_weight(self.conv.weight), derived.reg_pack)
 
     def affine(self):
         def build():
             s = torch.exp(self.logs.detach().float().reshape(-1) * self.logscale_factor)
             return s.contiguous(), (self.conv.bias.detach().float() * s).contiguous()
-        return self._cache.get("affine", (self.logs, self.conv.bias), build)
+        return self._cache.get("affine", (self.logs, self.conv.bias), build,
+                               derived.reg_affine(self.logs, self.conv.bias, self.logscale_factor))
 
     def fused(self, act, out, key="id", in_perm=None):
         """act NHWC bf16 -> out NCHW f32 = (conv + bias) * exp(3 logs)."""
@@ -233,15 +244,15 @@ class Conv2dNorm(nn.Module):
         self._cache = _Versioned()
 
     def packed(self, key="id", in_perm=None):
-        return self._cache.get(("w", key), (self.conv.weight,), lambda: ops.pack_conv_weight(self.conv.weight, in_perm))
+        return self._cache.get(("w", key), (self.conv.weight,), lambda: ops.pack_conv_weight(self.conv.weight, in_perm), derived.reg_pack)
 
     def packed_dgrad(self, key="id", out_perm=None):
         """Weights of the data-gradient convolution (flipped taps, in/out channels swapped), rows in staging order."""
-        return self._cache.get(("wd", key), (self.conv.weight,), lambda: ops.pack_dgrad_weight(self.conv.weight, out_perm))
+        return self._cache.get(("wd", key), (self.conv.weight,), lambda: ops.pack_dgrad_weight(self.conv.weight, out_perm), derived.reg_pack)
 
     def packed_dgrad_taps(self, key="id", out_perm=None):
         """Tap-split form of the data-gradient weights (3x3 convs with few input channels: one GEMM with N = 9*Cin)."""
-        return self._cache.get(("wd9", key), (self.conv.weight,), lambda: ops.pack_dgrad_taps_weight(self.conv.weight, out_perm))
+        return self._cache.get(("wd9", key), (self.conv.weight,), lambda: ops.pack_dgrad_taps_weight(self.conv.weight, out_perm), derived.reg_pack)
 
     def ready_for_fusion(self):
         """True when the per-channel affine is known without looking at the data (no pending ActNorm init, no

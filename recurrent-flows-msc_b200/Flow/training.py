@@ -34,20 +34,58 @@ class _State:
     def __init__(self, dz, g_ld, n_levels):
         self.dz = dz
         self.g_ld = g_ld
-        self.G = g_ld.sum()
+        self.G = g_ld.sum().reshape(1)
         self.dcond = [None] * n_levels
         self.dbase = None
         self.grads = {}
+        self.direct = set()
         self.folds = []
 
-    def add(self, param, g):
-        """g: a tensor this sweep owns (a fresh kernel output or a view of one) -- stored, not copied."""
-        g = g.reshape(param.shape)
+    def out(self, param):
+        """fp32 buffer (flat, zero or holding earlier contributions) the kernels ACCUMULATE the gradient of `param` into.
+        For parameters whose .grad storage is owned by FlatAdam (views of its flat gradient buffer, marked _rfk_direct)
+        that IS the .grad -- exactly autograd's accumulate semantics, without a per-parameter add or the 750-way
+        concatenation afterwards; otherwise a zeroed slice of this sweep's arena, returned to autograd at the end."""
+        g = param.grad
+        if g is not None and getattr(param, "_rfk_direct", False) and g.dtype == torch.float32 and g.is_contiguous():
+            self.direct.add(id(param))
+            return g.view(-1)
         hit = self.grads.get(id(param))
-        self.grads[id(param)] = g if hit is None else hit.add_(g)
+        if hit is None:
+            hit = self.grads[id(param)] = ops._zeros(param.numel(), param.device)
+        return hit
 
-    def add_cond(self, l, g):
-        self.dcond[l] = g if self.dcond[l] is None else self.dcond[l].add_(g)
+    def add(self, param, g):
+        """Legacy path: g is a tensor this sweep owns; added into the parameter's accumulation buffer."""
+        self.out(param).add_(g.reshape(-1))
+
+    def add_cond(self, l, src, n):
+        """dcond[l] += src[:, :n] (src fp32 NCHW with the condition's channels first)."""
+        if self.dcond[l] is None:
+            B, _, H, W = src.shape
+            self.dcond[l] = torch.zeros(B, n, H, W, device=src.device, dtype=torch.float32)
+        ops.add_channels(self.dcond[l], 0, src, 0, n)
+
+    def fold_buf(self, flow, step, C):
+        """Zeroed scratch of one GlowStep's fold backward: dWf [C,C] | dbf [C] | A [C,C].  One persistent flat buffer per
+        flow (pointer-stable, so the backward table is built once and the sweep can be captured in a CUDA graph), cleared
+        by a single memset at the start of every sweep."""
+        hit = flow.__dict__.get("_fold_flat")
+        if hit is None or hit[0].device != self.dz.device:
+            offs, total = {}, 0
+            for m in flow.glow_frame:
+                if hasattr(m, "invconv"):
+                    c = m.invconv.w_shape[0]
+                    offs[id(m)] = (total, 2 * c * c + c)
+                    total += (2 * c * c + c + 3) // 4 * 4
+            hit = (torch.zeros(total, device=self.dz.device, dtype=torch.float32), offs)
+            flow.__dict__["_fold_flat"] = hit
+            self.fold_cleared = True
+        if not getattr(self, "fold_cleared", False):
+            hit[0].zero_()
+            self.fold_cleared = True
+        off, n = hit[1][id(step)]
+        return hit[0][off:off + n]
 
 
 def _nhwc(B, H, W, c, dev):
@@ -66,7 +104,9 @@ def _conv_bwd(st, mod, x_act, cin, da, perm=None, dgrad_out=None, key="id"):
     """Backward of mod.conv given da (bf16 NHWC gradient of the raw convolution output): weight gradient into the
     state, data gradient into dgrad_out (bf16 NHWC or fp32 NCHW; channels in the staging order of x_act)."""
     n = mod.conv.out_channels
-    st.add(mod.conv.weight, ops.conv_wgrad(x_act, cin, da, n, mod.taps, perm=perm))   # staging order -> weight order
+    k = 3 if mod.taps == 9 else 1
+    ops.conv_wgrad(x_act, cin, da, n, mod.taps, out=st.out(mod.conv.weight).view(n, mod.conv.weight.shape[1], k, k),
+                   perm=perm)   # staging order -> weight order
     if dgrad_out is not None:
         B, H, W, _ = da.shape
         if (mod.taps == 9 and dgrad_out.dtype == torch.float32 and 9 * cin <= DGRAD_TAP_SPLIT_MAX_N
@@ -88,9 +128,8 @@ def _norm_act_bwd(st, mod, dh, h, act_fn):
     assert dh.shape[-1] == h.shape[-1]
     n = mod.conv.out_channels
     scale, _ = mod.norm_type.affine()
-    da, dbias, dlogs = ops.act_affine_bwd(dh, h, n, scale, act_fn, 1.0, True)
-    st.add(mod.norm_type.logs, dlogs)
-    st.add(mod.norm_type.bias, dbias)
+    da, _, _ = ops.act_affine_bwd(dh, h, n, scale, act_fn, 1.0, True, out_dv=st.out(mod.norm_type.bias),
+                                  out_dvv=st.out(mod.norm_type.logs))
     return da
 
 
@@ -101,16 +140,15 @@ def _zeros_out_bwd(st, mod, dout, out):
     ops.pack_nhwc(dout, 0, n, dh, 0)
     ops.pack_nhwc(out, 0, n, h, 0)
     scale, _ = mod.affine()
-    da, dbias, dlogs = ops.act_affine_bwd(dh, h, n, scale, "none", float(mod.logscale_factor), True)
-    st.add(mod.logs, dlogs)
-    st.add(mod.conv.bias, dbias)
+    da, _, _ = ops.act_affine_bwd(dh, h, n, scale, "none", float(mod.logscale_factor), True, out_dv=st.out(mod.conv.bias),
+                                  out_dvv=st.out(mod.logs))
     return da
 
 
 # ----------------------------------------------------------------------------------------
 # GlowStep
 # ----------------------------------------------------------------------------------------
-def _glowstep_fwd(step, x, ld, nn_template, cc, l, tape):
+def _glowstep_fwd(flow, step, x, ld, nn_template, cc, l, tape):
     if isinstance(step.norm, BatchNormFlow):
         raise NotImplementedError("recurrent-flows-msc_b200: backward for flow_norm='batchnorm' is not implemented")
     aff = step.affine
@@ -120,7 +158,7 @@ def _glowstep_fwd(step, x, ld, nn_template, cc, l, tape):
     if net[4].taps != 9 or 9 * C > TAP_SPLIT_MAX_N:
         raise NotImplementedError("recurrent-flows-msc_b200: coupling backward needs the tap-split form (C <= 256)")
     step.norm.maybe_initialize(x)
-    Wf, bf, _ = step._folded_fwd()
+    Wf, bf = step._folded_fwd(H * W)[:2]
     nn_in = nn_template.clone()
     y = ops.mix1x1(x, Wf, bf, side=nn_in, side_n=half, side_off=cc, logdet=ld, addend=step._dlogdet(H * W), alpha=1.0)
     h1, h2 = _nhwc(B, H, W, hid, dev), _nhwc(B, H, W, hid, dev)
@@ -130,11 +168,11 @@ def _glowstep_fwd(step, x, ld, nn_template, cc, l, tape):
     taps = torch.empty(B, 9 * C, H, W, device=dev, dtype=torch.float32)
     ops.conv_gemm(h2, cp, wgt9, 9 * C, 1, None, None, "none", taps)
     ops.coupling_tail_taps(taps, y, *aff.tail_params(), ld, False)
-    tape.append(lambda st: _glowstep_bwd(st, step, x, y, nn_in, h1, h2, taps, cc, l))
+    tape.append(lambda st: _glowstep_bwd(st, flow, step, x, y, nn_in, h1, h2, taps, cc, l))
     return y
 
 
-def _glowstep_bwd(st, step, x, zo, nn_in, h1, h2, taps, cc, l):
+def _glowstep_bwd(st, flow, step, x, zo, nn_in, h1, h2, taps, cc, l):
     aff = step.affine
     net = aff.net
     B, C, H, W = zo.shape
@@ -142,13 +180,11 @@ def _glowstep_bwd(st, step, x, zo, nn_in, h1, h2, taps, cc, l):
     dz = st.dz
     scale, shift, clamp, cs, csh = aff.tail_params()
     last = net[4]
-    dsum, d_logs, d_bias, d_cs, d_csh = ops.coupling_taps_bwd(taps, zo, dz, scale, shift, clamp, cs, csh, st.g_ld,
-                                                             float(last.logscale_factor))
-    st.add(last.logs, d_logs)
-    st.add(last.conv.bias, d_bias)
     if clamp == "realnvp":
-        st.add(aff.scale, d_cs)
-        st.add(aff.scale_shift, d_csh)
+        outs = (st.out(last.logs), st.out(last.conv.bias), st.out(aff.scale), st.out(aff.scale_shift))
+    else:
+        outs = (st.out(last.logs), st.out(last.conv.bias)) + tuple(ops._zeros(half, dev) for _ in range(2))
+    dsum = ops.coupling_taps_bwd(taps, zo, dz, scale, shift, clamp, cs, csh, st.g_ld, float(last.logscale_factor), outs)[0]
     dS = _nhwc(B, H, W, C, dev)
     ops.pack_nhwc(dsum, 0, C, dS, 0)
     dh2 = _nhwc(B, H, W, hid, dev)
@@ -160,26 +196,61 @@ def _glowstep_bwd(st, step, x, zo, nn_in, h1, h2, taps, cc, l):
     cin = half + cc
     dnn = torch.empty(B, cin, H, W, device=dev, dtype=torch.float32)
     _conv_bwd(st, net[0], nn_in, cin, da1, perm=aff._perm(dev), dgrad_out=dnn, key="cz")
-    dz[:, :half] += dnn[:, cc:]
+    ops.add_channels(dz, 0, dnn, cc, half)          # dz[:, :half] += d z1 (the network's input after the condition)
     if cc:
-        st.add_cond(l, dnn[:, :cc])
+        st.add_cond(l, dnn, cc)
     # ActNorm folded into the 1x1 mix: y = Wf x + bf
-    Wf = step._folded_fwd()[0]
-    dWf, dbf = ops.mix1x1_wgrad(x, dz)
-    st.dz = ops.mix1x1(dz, Wf.t().contiguous(), None)
-    st.folds.append((step, dWf, dbf, H * W))   # chained to the parameters in batches at the end of the sweep
+    fold = step._folded_fwd(H * W)
+    buf = st.fold_buf(flow, step, C)
+    dWf, dbf = ops.mix1x1_wgrad(x, dz, out=buf)
+    st.dz = ops.mix1x1(dz, fold[3], None)           # Wf^T
+    st.folds.append((step, dWf, dbf, H * W, buf))   # chained to the parameters in one batch at the end of the sweep
 
 
-def _fold_bwd_all(st):
+def _fold_bwd_all(st, flow):
+    """Chain (d Wf, d bf, d logdet) of every GlowStep back to ActNorm's (bias, logs) and InvConv's parameters
+    (Flow/glow_modules.py:33-54, 167-205).  LU-parameterised steps whose forward fold is registered for batched refresh go
+    through ONE launch of rfk_fold_backward_batched over a pointer table (rebuilt only when a pointer changed); the rest
+    take the batched-autograd path below."""
+    folds, st.folds = st.folds, []
+    fast, slow = [], []
+    for it in folds:
+        step = it[0]
+        ok = step.invconv.LU_decomposed and step.invconv.__dict__.get("_perm32") is not None
+        (fast if ok else slow).append(it)
+    if fast:
+        rows, key = [], []
+        for step, dWf, dbf, hw, buf in fast:
+            inv, C = step.invconv, step.invconv.w_shape[0]
+            fold = step._folded_fwd(hw)
+            outs = [st.out(p) for p in (step.norm.bias, step.norm.logs, inv.lower, inv.upper, inv.log_s)]
+            row = [step.norm.bias.data_ptr(), step.norm.logs.data_ptr(), inv.lower.data_ptr(), inv.upper.data_ptr(),
+                   inv.log_s.data_ptr(), inv.sign_s.data_ptr(), inv.__dict__["_perm32"].data_ptr(), C, hw, fold[0].data_ptr(),
+                   dWf.data_ptr(), dbf.data_ptr(), buf[C * C + C:].data_ptr()] + [o.data_ptr() for o in outs]
+            rows.append(row + [0] * (24 - len(row)))
+            key.extend(row)
+        key = tuple(key)
+        cache = flow.__dict__.get("_fold_bwd_table")
+        if cache is None or cache[0] != key:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("recurrent-flows-msc_b200: the fold-backward table changed inside a CUDA-graph capture; run the "
+                                   "training step eagerly once with the same optimizer before capturing")
+            cache = (key, torch.tensor([w for r in rows for w in r], dtype=torch.int64).to(st.dz.device))
+            flow.__dict__["_fold_bwd_table"] = cache
+        ops.call("rfk_fold_backward_batched", cache[1].data_ptr(), len(rows), st.G.data_ptr(), ops._stream())
+    if slow:
+        _fold_bwd_legacy(st, slow)
+
+
+def _fold_bwd_legacy(st, folds):
     """Chain (d Wf, d bf, d logdet) of every GlowStep back to ActNorm's (bias, logs) and InvConv's parameters
     (Flow/glow_modules.py:33-54, 167-205).  These are C x C tensors, differentiated by torch autograd; steps with the
     same channel count and parameterisation (one flow level) are stacked and go through ONE batched autograd call,
     otherwise the ~50 tiny launches per step would cost more GPU time than the level-1 convolutions."""
     groups = {}
-    for item in st.folds:
+    for item in folds:
         step = item[0]
         groups.setdefault((step.invconv.w_shape[0], step.invconv.LU_decomposed, item[3]), []).append(item)
-    st.folds = []
     for (C, lu, hw), items in groups.items():
         steps = [it[0] for it in items]
         inv0 = steps[0].invconv
@@ -205,7 +276,7 @@ def _fold_bwd_all(st):
             dl = (ldw + logs.sum(dim=1)) * hw
             dWf = torch.stack([it[1] for it in items])
             dbf = torch.stack([it[2] for it in items])
-            gs = torch.autograd.grad([Wf, bfv, dl], leaf, [dWf, dbf, st.G.expand(len(items))])
+            gs = torch.autograd.grad([Wf, bfv, dl], leaf, [dWf, dbf, st.G.reshape(()).expand(len(items))])
         for ps, g in zip(plist, gs):
             for k, p in enumerate(ps):
                 st.add(p, g[k])
@@ -250,7 +321,7 @@ def _split_bwd(st, sp, z, params, sp_in, t1, cbuf, perm, l):
     wd, cp = conv._cache.get(("wd", "z1"), (conv.conv.weight,),
                              lambda: ops.pack_dgrad_weight(conv.conv.weight, sp._perm(dev)[1]))
     ops.conv_gemm(da, cp, wd, half, conv.taps, None, None, "none", dz1)
-    dzf[:, :half] += dz1
+    ops.add_channels(dzf, 0, dz1, 0, half)
     if sp.make_conditional:
         c0, c2 = sp.convcond[0], sp.convcond[2]
         da2 = _norm_act_bwd(st, c2, dsp, sp_in, "relu")
@@ -259,7 +330,7 @@ def _split_bwd(st, sp, z, params, sp_in, t1, cbuf, perm, l):
         da1 = _norm_act_bwd(st, c0, dt1, t1, "relu")
         dc = torch.empty(B, cc, H, W, device=dev, dtype=torch.float32)
         _conv_bwd(st, c0, cbuf, cc, da1, dgrad_out=dc)
-        st.add_cond(l, dc)
+        st.add_cond(l, dc, cc)
     st.dz = dzf
 
 
@@ -327,7 +398,7 @@ def _log_prob_fwd(flow, x, conds, base_condition, obj0):
             z = _split_fwd(mod, z, obj, template, l, tape)
             l += 1
         else:
-            z = _glowstep_fwd(mod, z, obj, template, cc, l, tape)
+            z = _glowstep_fwd(flow, mod, z, obj, template, cc, l, tape)
     _prior_fwd(flow, z, base_condition, obj, tape)
     return z, obj, tape
 
@@ -356,10 +427,11 @@ class _LogProb(torch.autograd.Function):
         with ops.zero_arena(dz.device):
             while tape:
                 tape.pop()(st)
-            _fold_bwd_all(st)
+            _fold_bwd_all(st, ctx.flow)
         dconds = [st.dcond[i] for i in range(ctx.n_cond)]
-        pgrads = [st.grads.get(id(p)) for p in ctx.params]
-        pgrads = [None if g is None else g.to(p.dtype) for g, p in zip(pgrads, ctx.params)]
+        # parameters whose .grad was accumulated into directly get None here (nothing left for autograd to add)
+        pgrads = [None if id(p) in st.direct else st.grads.get(id(p)) for p in ctx.params]
+        pgrads = [None if g is None else g.view(p.shape).to(p.dtype) for g, p in zip(pgrads, ctx.params)]
         return (None, None, None, st.dz, st.dbase if ctx.has_base else None, *dconds, *pgrads)
 
 

@@ -66,6 +66,11 @@ SIGNATURES = {
                                    c_int, c_int, c_int, c_void_p],
     "rfk_taps_gather_nhwc": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
     "rfk_add_scalar": [c_void_p, c_void_p, c_float, c_int, c_void_p],
+    "rfk_pack_weights_batched": [c_void_p, c_int, c_longlong, c_void_p],
+    "rfk_affine_prepare_batched": [c_void_p, c_int, c_void_p],
+    "rfk_fold_prepare_batched": [c_void_p, c_int, c_void_p],
+    "rfk_fold_backward_batched": [c_void_p, c_int, c_void_p, c_void_p],
+    "rfk_add_channels": [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "rfk_debug_set_timeline": [c_void_p, c_longlong],
 }
 

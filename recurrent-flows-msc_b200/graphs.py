@@ -92,7 +92,7 @@ class GraphedTrainStep:
         self.static_inputs = static_inputs   # optional (nested) list of the tensors loss_fn reads: step(*batch) copies into them
 
         def fwd_bwd():
-            optimizer.zero_grad(set_to_none=True)
+            optimizer.zero_grad()      # one memset of the flat gradient buffer; .grad tensors stay views of it
             loss = loss_fn()
             loss.backward()
             with torch.no_grad():
@@ -127,5 +127,7 @@ class GraphedTrainStep:
         self.g_fb.replay()
         self.opt.allreduce_grads()
         self.g_opt.replay()
-        self._invalidate()   # eager calls after a replay must not trust caches filled before the last update
+        self._invalidate()   # eager calls after a replay must not trust caches filled before the last update ...
+        from .derived import REFRESHER
+        REFRESHER.restamp()  # ... except the registered ones: the optimizer graph has just rewritten them in place
         return self.loss

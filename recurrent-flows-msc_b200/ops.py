@@ -307,6 +307,14 @@ def gauss_sample(eps, params, n, pairing, std_kind, temperature, out, out_off):
          out.data_ptr(), oC, out_off, _stream())
 
 
+def add_channels(dst, dst_off, src, src_off, n):
+    """dst[:, dst_off:dst_off+n] += src[:, src_off:src_off+n] (fp32 NCHW, same B, H, W)."""
+    _chk(dst, name="dst")
+    _chk(src, name="src")
+    B, Cd, H, W = dst.shape
+    call("rfk_add_channels", dst.data_ptr(), Cd, dst_off, src.data_ptr(), src.shape[1], src_off, n, B, H * W, _stream())
+
+
 def convlstm_pointwise(cc, c_prev, peep):
     _chk(cc, name="cc")
     _chk(c_prev, name="c_prev")
@@ -359,18 +367,21 @@ def _zeros(n, device):
     return torch.zeros(n, device=device, dtype=torch.float32)
 
 
-def act_affine_bwd(dh, h, n, scale, act_fn, dvv_factor=1.0, dv_scaled=False):
+def act_affine_bwd(dh, h, n, scale, act_fn, dvv_factor=1.0, dv_scaled=False, out_dv=None, out_dvv=None):
     """Backward of h = act(a*scale + shift): returns (da bf16 NHWC like dh, r_dv [n], r_dvv [n]) with r_dv = sum dv
-    (times scale when dv_scaled: d bias of an ActNorm with scale = exp(logs)) and r_dvv = dvv_factor * sum dv*v (d logs)."""
+    (times scale when dv_scaled: d bias of an ActNorm with scale = exp(logs)) and r_dvv = dvv_factor * sum dv*v (d logs).
+    ``out_dv`` / ``out_dvv``: fp32 buffers of n elements the reductions are ACCUMULATED into (e.g. the parameters' .grad)."""
     _chk(dh, torch.bfloat16, "dh")
     _chk(h, torch.bfloat16, "h")
     rows = dh.numel() // dh.shape[-1]
     da = torch.empty_like(dh) if (n + 7) // 8 * 8 == dh.shape[-1] else torch.zeros_like(dh)   # the kernel writes 8-channel groups
-    r = _zeros(2 * n, dh.device)
+    if out_dv is None or out_dvv is None:
+        r = _zeros(2 * n, dh.device)
+        out_dv, out_dvv = r[:n], r[n:]
     call("rfk_act_affine_bwd", dh.data_ptr(), h.data_ptr(), dh.shape[-1], n, _chk(scale).data_ptr(), ACT[act_fn],
-         da.data_ptr(), da.shape[-1], r[:n].data_ptr(), r[n:].data_ptr(), float(dvv_factor), int(bool(dv_scaled)), rows,
+         da.data_ptr(), da.shape[-1], out_dv.data_ptr(), out_dvv.data_ptr(), float(dvv_factor), int(bool(dv_scaled)), rows,
          _stream())
-    return da, r[:n], r[n:]
+    return da, out_dv, out_dvv
 
 
 def convlstm_pointwise_bwd(cc, c_prev, peep, dh, dc_in, dbias):
@@ -416,15 +427,17 @@ def conv_wgrad(x, cin, dy, cout, taps, out=None, perm=None):
     return dw
 
 
-def coupling_taps_bwd(taps, z_out, dz, scale, shift, clamp, clamp_scale, clamp_shift, g_ld, logs_factor=0.0):
+def coupling_taps_bwd(taps, z_out, dz, scale, shift, clamp, clamp_scale, clamp_shift, g_ld, logs_factor=0.0, outs=None):
     """Backward of coupling_tail_taps.  dz (in/out, [B,C,H,W]): z2 half replaced by the gradient w.r.t. z2.
     Returns (dsum [B,C,H,W], d_scale [C], d_shift [C], d_clamp_scale [C/2], d_clamp_shift [C/2]); with logs_factor f != 0
     the second and third are d logs and d bias of a Conv2dZeros whose affine is scale = exp(f*logs), shift = bias*scale."""
     B, C, H, W = _chk(dz, name="dz").shape
     _chk(taps, name="taps"); _chk(z_out, name="z_out")
     dsum = torch.empty_like(dz)
-    r = _zeros(3 * C, dz.device)
-    d_scale, d_shift, d_cs, d_csh = r[:C], r[C:2 * C], r[2 * C:2 * C + C // 2], r[2 * C + C // 2:]
+    if outs is None:     # else: four fp32 buffers ([C], [C], [C/2], [C/2]) the reductions are ACCUMULATED into
+        r = _zeros(3 * C, dz.device)
+        outs = r[:C], r[C:2 * C], r[2 * C:2 * C + C // 2], r[2 * C + C // 2:]
+    d_scale, d_shift, d_cs, d_csh = outs
     p = lambda t: _chk(t).data_ptr() if t is not None else None
     call("rfk_coupling_taps_bwd", taps.data_ptr(), z_out.data_ptr(), dz.data_ptr(), dsum.data_ptr(), B, C, H, W,
          _chk(scale).data_ptr(), _chk(shift).data_ptr(), CLAMP[clamp], p(clamp_scale), p(clamp_shift), p(g_ld),
@@ -442,11 +455,11 @@ def taps_scatter(dsum, out=None):
     return out
 
 
-def mix1x1_wgrad(x, dy):
-    """(dW [C,C], db [C]) of y = W x + b over all pixels (fp32 NCHW)."""
+def mix1x1_wgrad(x, dy, out=None):
+    """(dW [C,C], db [C]) of y = W x + b over all pixels (fp32 NCHW); ``out``: zeroed fp32 buffer of C*C + C elements."""
     B, C, H, W = _chk(x, name="x").shape
     _chk(dy, name="dy")
-    r = _zeros(C * C + C, x.device)
+    r = _zeros(C * C + C, x.device) if out is None else out
     call("rfk_mix1x1_wgrad", x.data_ptr(), dy.data_ptr(), B, C, H * W, r.data_ptr(), r[C * C:].data_ptr(), _stream())
     return r[:C * C].view(C, C), r[C * C:]
 
@@ -506,9 +519,13 @@ def _pack_weight(weight, mode, perm, rows, rows_pad, kp, ktot, cin_real):
         w = w.float().contiguous()
     N, Cin, kh, kw = w.shape
     out = torch.empty(rows_pad, ktot, device=w.device, dtype=torch.bfloat16)
-    call("rfk_pack_weight", w.data_ptr(), N, Cin, kh * kw, mode, _p(_perm32(perm)), rows, kp, out.data_ptr(), rows_pad, ktot,
+    p32 = _perm32(perm)
+    call("rfk_pack_weight", w.data_ptr(), N, Cin, kh * kw, mode, _p(p32), rows, kp, out.data_ptr(), rows_pad, ktot,
          _stream())
     out.rfk_cin = cin_real
+    if w.data_ptr() == weight.data_ptr():   # packed straight from the parameter's storage: refreshable in place (derived.py)
+        out.rfk_pack = [w.data_ptr(), out.data_ptr(), _p(p32), N, Cin, kh * kw, mode, rows, kp, rows_pad, ktot]
+        out.rfk_perm = p32
     return out, kp
 
 

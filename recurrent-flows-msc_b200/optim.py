@@ -8,7 +8,7 @@ into a second one (one ``torch.cat``), optionally sum-allreduces it over the pro
 """
 import torch
 
-from . import ops
+from . import derived, ops
 from ._lib import call
 from .Flow.glow_modules import invalidate_caches
 
@@ -28,21 +28,29 @@ class FlatAdam:
         # torch.optim-style handle for LR schedulers (RFN/trainer.py:100,200 write param_groups[0]['lr'])
         self.param_groups = [{"params": self.params, "lr": float(lr), "betas": self.betas, "eps": self.eps}]
         self.group, self.world = process_group, int(world_size)
-        self.n = sum(p.numel() for p in self.params)
-        self.n_pad = (self.n + 3) // 4 * 4
+        self.n = sum(p.numel() for p in self.params)                       # real parameters
+        offs, off = [], 0
+        for p in self.params:                                               # every tensor starts on a 16-byte boundary
+            offs.append(off)
+            off += (p.numel() + 3) // 4 * 4
+        self.n_pad = off                                                    # flat length incl. alignment padding (stays zero)
         self.flat_p = torch.zeros(self.n_pad, device=dev, dtype=torch.float32)
         self.flat_g = torch.zeros(self.n_pad, device=dev, dtype=torch.float32)
         self.exp_avg = torch.zeros(self.n_pad, device=dev, dtype=torch.float32)
         self.exp_avg_sq = torch.zeros(self.n_pad, device=dev, dtype=torch.float32)
         self.step_t = torch.zeros(1, device=dev, dtype=torch.float32)
-        off = 0
+        self.grad_views = []
         with torch.no_grad():
-            for p in self.params:
+            for p, off in zip(self.params, offs):
                 n = p.numel()
                 view = self.flat_p[off:off + n].view(p.shape)
                 view.copy_(p.detach().float())
                 p.data = view
-                off += n
+                # .grad lives in the flat gradient buffer: the hand-written backward accumulates into it directly
+                # (Flow/training.py _State.out) and autograd's own accumulation adds in place, so no gather is needed
+                self.grad_views.append(self.flat_g[off:off + n].view(p.shape))
+                p._rfk_direct = True
+        self.offsets = offs
         invalidate_caches()
 
     @property
@@ -56,31 +64,36 @@ class FlatAdam:
     def state_dict(self):
         """exp_avg / exp_avg_sq / step (flat, in parameter order) + the hyper-parameters; what Solver.checkpoint stores as
         'optimizer_state_dict' (RFN/trainer.py:281)."""
-        return {"state": {"exp_avg": self.exp_avg[:self.n].clone(), "exp_avg_sq": self.exp_avg_sq[:self.n].clone(),
+        return {"state": {"exp_avg": self.exp_avg.clone(), "exp_avg_sq": self.exp_avg_sq.clone(),
                           "step": self.step_t.clone()},
-                "param_groups": [{"lr": self.lr, "betas": self.betas, "eps": self.eps, "n_params": self.n}]}
+                "param_groups": [{"lr": self.lr, "betas": self.betas, "eps": self.eps, "n_params": self.n_pad}]}
 
     def load_state_dict(self, sd):
         g = sd["param_groups"][0]
-        if g.get("n_params", self.n) != self.n:
-            raise ValueError(f"FlatAdam.load_state_dict: {g.get('n_params')} parameters saved, {self.n} here")
+        if g.get("n_params", self.n_pad) != self.n_pad:
+            raise ValueError(f"FlatAdam.load_state_dict: flat length {g.get('n_params')} saved, {self.n_pad} here")
         self.lr, self.betas, self.eps = g["lr"], tuple(g["betas"]), g["eps"]
         with torch.no_grad():
-            self.exp_avg[:self.n].copy_(sd["state"]["exp_avg"])
-            self.exp_avg_sq[:self.n].copy_(sd["state"]["exp_avg_sq"])
+            self.exp_avg.copy_(sd["state"]["exp_avg"])
+            self.exp_avg_sq.copy_(sd["state"]["exp_avg_sq"])
             self.step_t.copy_(sd["state"]["step"])
 
-    def zero_grad(self, set_to_none=True):
-        for p in self.params:
-            if set_to_none:
-                p.grad = None
-            elif p.grad is not None:
-                p.grad.zero_()
+    def zero_grad(self, set_to_none=False):
+        """One memset of the flat gradient buffer; every .grad is (re)pointed at its view of it.  ``set_to_none`` is accepted
+        for torch.optim compatibility but gradients stay allocated (zero), which is what makes them graph-capturable."""
+        self.flat_g.zero_()
+        for p, v in zip(self.params, self.grad_views):
+            if p.grad is not v:
+                p.grad = v
 
     def gather_grads(self):
-        """All .grad tensors -> the flat gradient buffer (one concatenation kernel); absent gradients count as zero."""
-        parts = [(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in self.params]
-        torch.cat(parts, out=self.flat_g[:self.n])
+        """Gradients that did not land in the flat buffer (a .grad re-assigned by user code) are copied into it; with the
+        views installed by zero_grad() this is a no-op.  Absent gradients count as zero."""
+        for p, v in zip(self.params, self.grad_views):
+            g = p.grad
+            if g is None or g is v or g.data_ptr() == v.data_ptr():
+                continue
+            v.copy_(g)
         return self.flat_g
 
     def allreduce_grads(self):
@@ -95,6 +108,8 @@ class FlatAdam:
              self.exp_avg_sq.data_ptr(), self.n_pad, self.lr, self.betas[0], self.betas[1], self.eps, 1.0 / self.world,
              self.step_t.data_ptr(), ops._stream())
         invalidate_caches()   # the kernel wrote the parameters through raw pointers
+        # ... and everything derived from them that registered for it is rewritten in place: one launch per kind
+        derived.REFRESHER.refresh_all(self.flat_p.device, ops._stream())
 
     @torch.no_grad()
     def step(self):

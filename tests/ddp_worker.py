@@ -63,12 +63,12 @@ def main():
     loss_of(m, lstm, sl).backward()
     opt.gather_grads()
     opt.allreduce_grads()
-    g_dp = opt.flat_g[:opt.n].clone() / world
+    g_dp = opt.flat_g.clone() / world
     m1, lstm1, opt1 = build(Bg, 1)
     opt1.zero_grad()
     loss_of(m1, lstm1, slice(0, Bg)).backward()
     opt1.gather_grads()
-    g_single = opt1.flat_g[:opt1.n]
+    g_single = opt1.flat_g
     err = float((g_dp - g_single).abs().max() / g_single.abs().max())
     cos = float(torch.dot(g_dp.double(), g_single.double()) / (g_dp.double().norm() * g_single.double().norm()))
     # ---- 2. replicas identical after 5 steps (eager, then graph replay) ---------------------------------------------
@@ -80,11 +80,11 @@ def main():
     for _ in range(2):
         step()
     torch.cuda.synchronize()
-    mine = opt.flat_p[:opt.n].clone()
+    mine = opt.flat_p.clone()
     allp = [torch.empty_like(mine) for _ in range(world)]
     dist.all_gather(allp, mine)
     same = all(torch.equal(allp[0], q) for q in allp)
-    moved = float((mine - opt1.flat_p[:opt1.n]).abs().max())
+    moved = float((mine - opt1.flat_p).abs().max())
     ok = err < 2e-3 and cos > 0.9999 and same and moved > 0 and bool(torch.isfinite(mine).all())
     if rank == 0:
         print(f"ddp_worker: world {world}: allreduced-gradient vs single-GPU max-norm rel err {err:.3e}, cosine {cos:.6f}; "
