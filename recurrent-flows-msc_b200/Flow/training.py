@@ -17,6 +17,8 @@ between convolutions are bf16 (as the activations are); parameter gradients accu
 Not covered (raise NotImplementedError): flow_norm='batchnorm', batch-norm hidden layers in the prior, couplings with
 more than 256 channels (no tap-split form), gradients w.r.t. a tensor-valued ``logdet`` argument.
 """
+import os
+
 import torch
 
 from .. import ops
@@ -25,6 +27,21 @@ from .glow_modules import BatchNormFlow, Split2d, Squeeze2d, TAP_SPLIT_MAX_N
 
 DGRAD_TAP_SPLIT_MAX_N = 512         # tap-split data gradient when 9*Cin <= this ...
 DGRAD_TAP_SPLIT_MIN_PIXELS = 32768  # ... and the launch has enough pixels to be bandwidth- rather than latency-bound
+# Weight gradients are off the critical path of the sweep (nothing downstream reads them).  For launches too small to fill
+# the GPU (levels 3-5 at RFN sizes: <= 72 pixel tiles on 148 SMs) they go to a second stream and overlap the data-gradient
+# chain; in a captured training step this becomes a parallel branch of the CUDA graph.  RFK_WGRAD_SIDE_STREAM=0 disables.
+WGRAD_SIDE_MAX_PIXELS = int(os.environ.get("RFK_WGRAD_SIDE_MAX_PIXELS", "32768"))
+WGRAD_SIDE_STREAM = os.environ.get("RFK_WGRAD_SIDE_STREAM", "1") != "0"
+
+
+_SIDE = {}
+
+
+def _side_stream(device):
+    s = _SIDE.get(device)
+    if s is None:
+        s = _SIDE[device] = torch.cuda.Stream(device=device)
+    return s
 
 
 class _State:
@@ -40,6 +57,32 @@ class _State:
         self.grads = {}
         self.direct = set()
         self.folds = []
+        self.side = None          # second stream for small weight-gradient launches
+        self.side_keep = []       # tensors the side stream still reads (kept alive until the join)
+
+    def wgrad(self, x_act, cin, da, n, taps, out, perm):
+        """Weight gradient launch; small ones go to the side stream."""
+        B, H, W, _ = da.shape
+        if not WGRAD_SIDE_STREAM or B * H * W > WGRAD_SIDE_MAX_PIXELS:
+            ops.conv_wgrad(x_act, cin, da, n, taps, out=out, perm=perm)
+            return
+        main = torch.cuda.current_stream()
+        if self.side is None:
+            self.side = _side_stream(da.device)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        self.side.wait_event(ev)
+        with torch.cuda.stream(self.side):
+            ops.conv_wgrad(x_act, cin, da, n, taps, out=out, perm=perm, ws_slot=1)
+        self.side_keep.append((x_act, da, out))
+
+    def join(self):
+        """The main stream waits for the side stream; the tensors it was reading may be released afterwards."""
+        if self.side is not None and self.side_keep:
+            ev = torch.cuda.Event()
+            ev.record(self.side)
+            torch.cuda.current_stream().wait_event(ev)
+            self.side_keep.clear()
 
     def out(self, param):
         """fp32 buffer (flat, zero or holding earlier contributions) the kernels ACCUMULATE the gradient of `param` into.
@@ -105,8 +148,8 @@ def _conv_bwd(st, mod, x_act, cin, da, perm=None, dgrad_out=None, key="id"):
     state, data gradient into dgrad_out (bf16 NHWC or fp32 NCHW; channels in the staging order of x_act)."""
     n = mod.conv.out_channels
     k = 3 if mod.taps == 9 else 1
-    ops.conv_wgrad(x_act, cin, da, n, mod.taps, out=st.out(mod.conv.weight).view(n, mod.conv.weight.shape[1], k, k),
-                   perm=perm)   # staging order -> weight order
+    st.wgrad(x_act, cin, da, n, mod.taps, st.out(mod.conv.weight).view(n, mod.conv.weight.shape[1], k, k),
+             perm)   # staging order -> weight order
     if dgrad_out is not None:
         B, H, W, _ = da.shape
         if (mod.taps == 9 and dgrad_out.dtype == torch.float32 and 9 * cin <= DGRAD_TAP_SPLIT_MAX_N
@@ -384,7 +427,7 @@ def _log_prob_fwd(flow, x, conds, base_condition, obj0):
     for mod in flow.glow_frame:
         if isinstance(mod, Squeeze2d):
             z = ops.squeeze2d(z, False)
-            tape.append(lambda st: setattr(st, "dz", ops.squeeze2d(st.dz, True)))
+            tape.append(lambda st: (st.join(), setattr(st, "dz", ops.squeeze2d(st.dz, True))))
             cond = ops.f32c(conds[l])
             assert cond.shape[2:4] == z.shape[2:4], "condition and x in affine needs to match"
             cc = cond.shape[1]
@@ -427,6 +470,7 @@ class _LogProb(torch.autograd.Function):
         with ops.zero_arena(dz.device):
             while tape:
                 tape.pop()(st)
+            st.join()
             _fold_bwd_all(st, ctx.flow)
         dconds = [st.dcond[i] for i in range(ctx.n_cond)]
         # parameters whose .grad was accumulated into directly get None here (nothing left for autograd to add)

@@ -28,8 +28,11 @@ def _forward(cell, x, ht, ct):
     out = torch.empty(B, T, hc, H, W, device=dev, dtype=torch.float32)
     saved = []
     h_prev, c_prev = ht, ct
+    # the packed inputs [x_t | h_{t-1}] of all steps in ONE buffer, time-major: the weight gradient, a reduction over
+    # pixels, then runs once over T*B*H*W pixels instead of once per step
+    bufs = torch.zeros(T * B, H, W, ops.cin_pad(cin), device=dev, dtype=torch.bfloat16)
     for t in range(T):
-        buf = torch.zeros(B, H, W, ops.cin_pad(cin), device=dev, dtype=torch.bfloat16)
+        buf = bufs[t * B:(t + 1) * B]
         ops.pack_nhwc(x[:, t], 0, C, buf, 0)
         if h_prev is not None:
             ops.pack_nhwc(h_prev, 0, hc, buf, C)
@@ -40,7 +43,7 @@ def _forward(cell, x, ht, ct):
         out[:, t].copy_(h)
         saved.append((buf, cc, c_prev))
         h_prev, c_prev = h, c
-    return out, c_prev, saved
+    return out, c_prev, (saved, bufs)
 
 
 class _ConvLSTMFn(torch.autograd.Function):
@@ -57,9 +60,10 @@ class _ConvLSTMFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, d_out, d_c):
-        cell, saved = ctx.cell, ctx.saved
-        if saved is None:
+        cell = ctx.cell
+        if ctx.saved is None:
             raise RuntimeError("recurrent-flows-msc_b200: ConvLSTM's saved activations were already consumed (no retain_graph)")
+        saved, bufs = ctx.saved
         ctx.saved = None
         B, T, C, H, W = ctx.shape
         hc, dev = cell.hidden_channels, d_out.device
@@ -74,8 +78,20 @@ class _ConvLSTMFn(torch.autograd.Function):
         key = (conv.weight.data_ptr(), conv.weight._version, _epoch())
         if cache[0] != key:
             cache[0], cache[1] = key, ops.pack_dgrad_weight(conv.weight)
-        wd, cp = cache[1]
-        dx = torch.empty(B, T, C, H, W, device=dev, dtype=torch.float32)
+        need_dx = ctx.needs_input_grad[1]
+        if need_dx:
+            wd, cp = cache[1]
+            n_rows, h_lo = cin, C
+        else:
+            # the input sequence needs no gradient (e.g. detached features): only the h_{t-1} rows of the data gradient
+            hkey = key + ("h",)
+            if cache[0] != key or cell.__dict__.get("_wdh_cache", (None,))[0] != hkey:
+                rows = torch.arange(C, cin, device=dev)
+                cell.__dict__["_wdh_cache"] = (hkey, ops.pack_dgrad_weight(conv.weight, rows))
+            wd, cp = cell.__dict__["_wdh_cache"][1]
+            n_rows, h_lo = hc, 0
+        dx = torch.empty(B, T, C, H, W, device=dev, dtype=torch.float32) if need_dx else None
+        das = torch.zeros(T * B, H, W, ops.cin_pad(4 * hc), device=dev, dtype=torch.bfloat16)
         dh_future = None
         for t in reversed(range(T)):
             buf, cc, c_prev = saved[t]
@@ -83,13 +99,17 @@ class _ConvLSTMFn(torch.autograd.Function):
             if dh_future is not None:
                 dh = dh + dh_future
             dcc, dc = ops.convlstm_pointwise_bwd(cc, c_prev, cell._peep, dh, dc, dbias)
-            da = torch.zeros(B, H, W, ops.cin_pad(4 * hc), device=dev, dtype=torch.bfloat16)
+            da = das[t * B:(t + 1) * B]
             ops.pack_nhwc(dcc, 0, 4 * hc, da, 0)
-            ops.conv_wgrad(buf, cin, da, 4 * hc, cell.taps, out=dw)
-            din = torch.empty(B, cin, H, W, device=dev, dtype=torch.float32)
-            ops.conv_gemm(da, cp, wd, cin, cell.taps, None, None, "none", din)
-            dx[:, t].copy_(din[:, :C])
-            dh_future = din[:, C:]
+            if t == 0 and not need_dx and not ctx.has_state:
+                break       # nothing upstream of the first step needs a data gradient
+            din = torch.empty(B, n_rows, H, W, device=dev, dtype=torch.float32)
+            ops.conv_gemm(da, cp, wd, n_rows, cell.taps, None, None, "none", din)
+            if need_dx:
+                dx[:, t].copy_(din[:, :C])
+            dh_future = din[:, h_lo:]
+        # d weight = sum_t [x_t | h_{t-1}]^T dcc_t: one launch over all T*B*H*W pixels
+        ops.conv_wgrad(bufs, cin, das, 4 * hc, cell.taps, out=dw)
         dweight = dw
         d_h0 = dh_future.contiguous() if ctx.has_state else None
         d_c0 = dc if ctx.has_state else None

@@ -401,15 +401,16 @@ def convlstm_pointwise_bwd(cc, c_prev, peep, dh, dc_in, dbias):
 _WGRAD_WS = {}
 
 
-def _wgrad_ws(device):
-    """Scratch for the weight-gradient kernel's per-slice partial tiles (one stream, launches in order): 64 MB."""
-    hit = _WGRAD_WS.get(device)
+def _wgrad_ws(device, slot=0):
+    """Scratch for the weight-gradient kernel's per-slice partial tiles: 64 MB per slot.  Launches that share a slot must be
+    stream-ordered (slot 0: the main stream; slot 1: the side stream of Flow/training.py)."""
+    hit = _WGRAD_WS.get((device, slot))
     if hit is None:
-        hit = _WGRAD_WS[device] = torch.empty(1 << 24, device=device, dtype=torch.float32)
+        hit = _WGRAD_WS[(device, slot)] = torch.empty(1 << 24, device=device, dtype=torch.float32)
     return hit
 
 
-def conv_wgrad(x, cin, dy, cout, taps, out=None, perm=None):
+def conv_wgrad(x, cin, dy, cout, taps, out=None, perm=None, ws_slot=0, dw_ld=None):
     """Weight gradient [cout, cin, k, k] (fp32, the conv weight's own layout) of a 'same' conv from NHWC bf16 activations x
     and output gradients dy.  ``perm`` (long tensor): channel c of x is the weight's input channel perm[c].  ``out``
     (zeroed by the caller once) accumulates over several calls."""
@@ -419,9 +420,9 @@ def conv_wgrad(x, cin, dy, cout, taps, out=None, perm=None):
     k = 3 if taps == 9 else 1
     dw = out if out is not None else _zeros(cout * cin * taps, x.device).view(cout, cin, k, k)
     _chk(dw, name="dw")
-    ws = _wgrad_ws(x.device)
-    call("rfk_conv_wgrad", x.data_ptr(), xld, cin, dy.data_ptr(), dy.shape[-1], cout, B, H, W, taps, dw.data_ptr(), cin,
-         1, _p(_perm32(perm)), ws.data_ptr(), ws.numel() * 4, _stream(),
+    ws = _wgrad_ws(x.device, ws_slot)
+    call("rfk_conv_wgrad", x.data_ptr(), xld, cin, dy.data_ptr(), dy.shape[-1], cout, B, H, W, taps, dw.data_ptr(),
+         cin if dw_ld is None else dw_ld, 1, _p(_perm32(perm)), ws.data_ptr(), ws.numel() * 4, _stream(),
          meta={"flops": 2.0 * B * H * W * cout * cin * taps, "flops_padded": 2.0 * B * H * W * cout * cin * taps,
                "M": B * H * W, "N": cout, "K": taps * cin, "bytes": 2.0 * B * H * W * (cin + cout)})
     return dw
@@ -461,7 +462,7 @@ def mix1x1_wgrad(x, dy, out=None):
     _chk(dy, name="dy")
     r = _zeros(C * C + C, x.device) if out is None else out
     call("rfk_mix1x1_wgrad", x.data_ptr(), dy.data_ptr(), B, C, H * W, r.data_ptr(), r[C * C:].data_ptr(), _stream())
-    return r[:C * C].view(C, C), r[C * C:]
+    return r[:C * C].view(C, C), r[C * C:C * C + C]
 
 
 def gauss_logp_bwd(z, z_off, n, params, pairing, std_kind, g, dz):
