@@ -856,7 +856,7 @@ def wl_rfn_train(env, rf, args, smooth=False):
                    "how": "pinned host -> device copy of step i+1 on a copy stream overlaps step i; loss copied back every step"},
            "gpu_launches": launches_per_step * args.steps,
            "training": {"own_kernel_launches_per_step": launches_per_step, "parameters": opt.n,
-                        "launch": "eager" if args.no_graph else "CUDA graphs" + (" around the NCCL all-reduce" if world > 1 else ""),
+                        "launch": "eager" if args.no_graph else train_step.mode,
                         "allreduce_bytes_per_step": opt.n_pad * 4 if world > 1 else 0,
                         "loss_first_step": first_loss, "loss_last_step": last_loss,
                         "peak_memory_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 2)}}

@@ -109,24 +109,47 @@ class GraphedTrainStep:
                     optimizer.apply()
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
-        self.g_fb = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.g_fb):
-            self.loss = fwd_bwd()
-        self.g_opt = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.g_opt), torch.no_grad():
-            optimizer.apply()
-        if optimizer.world == 1:
-            # the capture itself executed nothing: parameters and Adam state are unchanged, step_t too
-            pass
+        # ONE graph for the whole step, the NCCL all-reduce of the flat gradient included (captured like any other stream
+        # work: no host round trip between backward, collective and Adam).  RFK_GRAPH_ALLREDUCE=0, or a failed capture
+        # of the collective, falls back to two graphs around an eager all-reduce.
+        import os
+        self.g_all = self.g_fb = self.g_opt = None
+        if optimizer.world == 1 or os.environ.get("RFK_GRAPH_ALLREDUCE", "1") != "0":
+            try:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self.loss = fwd_bwd()
+                    optimizer.allreduce_grads()
+                    with torch.no_grad():
+                        optimizer.apply()
+                self.g_all = g
+            except Exception as e:  # noqa: BLE001
+                if optimizer.world == 1:
+                    raise
+                import warnings
+                warnings.warn(f"recurrent-flows-msc_b200: capturing the NCCL all-reduce failed ({e!r}); using two graphs around an eager all-reduce")
+                torch.cuda.synchronize()
+        if self.g_all is None:
+            self.g_fb = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.g_fb):
+                self.loss = fwd_bwd()
+            self.g_opt = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.g_opt), torch.no_grad():
+                optimizer.apply()
+        self.mode = "one CUDA graph (forward + backward + all-reduce + Adam)" if self.g_all is not None else \
+            "two CUDA graphs (forward + backward | Adam) around an eager all-reduce"
 
     def __call__(self, *batch):
         if batch:
             if self.static_inputs is None:
                 raise ValueError("GraphedTrainStep: pass static_inputs= at construction to feed new batches")
             _copy_into(self.static_inputs, list(batch))
-        self.g_fb.replay()
-        self.opt.allreduce_grads()
-        self.g_opt.replay()
+        if self.g_all is not None:
+            self.g_all.replay()
+        else:
+            self.g_fb.replay()
+            self.opt.allreduce_grads()
+            self.g_opt.replay()
         self._invalidate()   # eager calls after a replay must not trust caches filled before the last update ...
         from .derived import REFRESHER
         REFRESHER.restamp()  # ... except the registered ones: the optimizer graph has just rewritten them in place

@@ -109,9 +109,12 @@ def test_rfn_loss_and_predict_stock_vs_patched():
         stock = rfn_mod.RFN(args).cuda().train()
         with torch.no_grad():
             g = torch.Generator().manual_seed(5)
-            for n, p in stock.named_parameters():   # trained-like: zero-init Conv2dZeros / realnvp scale would make the flow trivial
+            # trained-like: zero-init Conv2dZeros / realnvp scale would make the flow trivial.  The scale keeps the 50-step
+            # reverse flow in a trained model's regime (samples within the image range; 2.5x larger perturbations give
+            # |x| ~ 1e5, where the comparison measures the conditioning of the random map: tools/dropin_debug.py)
+            for n, p in stock.named_parameters():
                 if n.startswith("flow."):
-                    p.add_((torch.randn(p.shape, generator=g) * (0.01 if "conv.weight" in n else 0.05)).cuda())
+                    p.add_((torch.randn(p.shape, generator=g) * (0.004 if "conv.weight" in n else 0.02)).cuda())
         sd0 = {k: v.clone() for k, v in stock.state_dict().items()}
         x = _data(B, T).cuda()
 
@@ -131,7 +134,7 @@ def test_rfn_loss_and_predict_stock_vs_patched():
         kl_fb_o, kl_o, nll_o = ours.loss(x, 0)
         (kl_fb_o + nll_o).backward()
         chw_t = 64 * 64 * (T - 1)
-        bpd_s, bpd_o = float(nll_s) / (0.6931 * chw_t), float(nll_o) / (0.6931 * chw_t)
+        bpd_s, bpd_o = float(nll_s.detach()) / (0.6931 * chw_t), float(nll_o.detach()) / (0.6931 * chw_t)
         print(f"RFN.loss stock vs patched: nll {float(nll_s):.4f} / {float(nll_o):.4f}  bits/dim {bpd_s:.5f} / {bpd_o:.5f}  "
               f"kl {float(kl_s):.5f} / {float(kl_o):.5f}")
         assert abs(float(nll_o) - float(nll_s)) <= 1e-2 * abs(float(nll_s)) + 1e-3 * chw_t * 0.6931   # 1e-2 rel or 1e-3 bits/dim
@@ -176,8 +179,8 @@ def test_rfn_loss_and_predict_stock_vs_patched():
         e0 = _max_rel(pred_o[0], pred_s[0])
         e_all = float((pred_o - pred_s).abs().mean() / pred_s.abs().mean().clamp_min(1e-12))
         print(f"predict(10,10): first frame max-norm rel err {e0:.3e}, all frames mean abs rel {e_all:.3e}")
-        assert e0 < 3e-2          # one pass through the reverse flow
-        assert e_all < 0.15       # ten autoregressive passes: errors feed back through extractor and ConvLSTM
+        assert e0 < 2e-2          # one pass through the reverse flow (bf16 gate 1e-2, doubled for the 50-step inverse)
+        assert e_all < 5e-2       # ten autoregressive passes: errors feed back through extractor and ConvLSTM
     finally:
         for name in ("Flow.glow_modules", "Flow.glow", "Flow", "Utils.modules", "Utils"):
             if name in sys.modules:
