@@ -559,15 +559,10 @@ class Env:
         if self.world > 1:
             # NCCL's INFO lines (communicator ranks, NVLS / ring choice) go to per-rank files next to the bench output; stdout
             # stays one JSON line
-            os.environ.setdefault("NCCL_DEBUG", "INFO")
-            os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT,GRAPH")
-            if "NCCL_DEBUG_FILE" not in os.environ:
-                d = os.path.join(ROOT, "gpurun_out")
-                try:
-                    os.makedirs(d, exist_ok=True)
-                    os.environ["NCCL_DEBUG_FILE"] = os.path.join(d, f"nccl_n{self.world}_rank%h_%p.log")
-                except OSError:
-                    os.environ["NCCL_DEBUG"] = "WARN"
+            if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
+                os.environ["NCCL_DEBUG"] = "INFO"
+                os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT,GRAPH")
+            os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
             dist.init_process_group("nccl", device_id=self.dev)
         self.args = args
         self.peaks = {}

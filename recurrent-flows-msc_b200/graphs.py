@@ -117,7 +117,8 @@ class GraphedTrainStep:
         if optimizer.world == 1 or os.environ.get("RFK_GRAPH_ALLREDUCE", "1") != "0":
             try:
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
+                # thread_local: the NCCL watchdog thread may touch the CUDA API (event queries) while this thread captures
+                with torch.cuda.graph(g, capture_error_mode="thread_local"):
                     self.loss = fwd_bwd()
                     optimizer.allreduce_grads()
                     with torch.no_grad():
@@ -131,10 +132,10 @@ class GraphedTrainStep:
                 torch.cuda.synchronize()
         if self.g_all is None:
             self.g_fb = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.g_fb):
+            with torch.cuda.graph(self.g_fb, capture_error_mode="thread_local"):
                 self.loss = fwd_bwd()
             self.g_opt = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.g_opt), torch.no_grad():
+            with torch.cuda.graph(self.g_opt, capture_error_mode="thread_local"), torch.no_grad():
                 optimizer.apply()
         self.mode = "one CUDA graph (forward + backward + all-reduce + Adam)" if self.g_all is not None else \
             "two CUDA graphs (forward + backward | Adam) around an eager all-reduce"

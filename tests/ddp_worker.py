@@ -56,6 +56,10 @@ def main():
         _, nll = m.log_prob(x[sl], [c[sl] for c in conds], base, noise=noise[sl])
         return nll.mean() / (math.log(2.0) * 256)
 
+    def mark(msg):
+        print(f"[rank {rank}] {msg}", file=sys.stderr, flush=True)
+
+    mark("data ready")
     # ---- 1. gradient equality --------------------------------------------------------------------------------------
     m, lstm, opt = build(Bs, world)
     sl = slice(rank * Bs, (rank + 1) * Bs)
@@ -64,6 +68,7 @@ def main():
     opt.gather_grads()
     opt.allreduce_grads()
     g_dp = opt.flat_g.clone() / world
+    mark("all-reduced gradient ready")
     m1, lstm1, opt1 = build(Bg, 1)
     opt1.zero_grad()
     loss_of(m1, lstm1, slice(0, Bg)).backward()
@@ -76,10 +81,13 @@ def main():
         opt.zero_grad()
         loss_of(m, lstm, sl).backward()
         opt.step()
+    mark("eager steps done")
     step = rf.GraphedTrainStep(lambda: loss_of(m, lstm, sl), opt, warmup=1)
+    mark("captured: " + step.mode)
     for _ in range(2):
         step()
     torch.cuda.synchronize()
+    mark("graph replays done")
     mine = opt.flat_p.clone()
     allp = [torch.empty_like(mine) for _ in range(world)]
     dist.all_gather(allp, mine)
