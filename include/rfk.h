@@ -267,6 +267,17 @@ int rfk_gauss_logp_bwd(const float* z, int z_C, int z_off, const float* params, 
 int rfk_pack_weight(const float* src, int N, int Cin, int taps, int mode, const int* perm, int rows, int kp,
                     void* dst, int rows_pad, int ktot, void* stream);
 
+/* Split-precision ("bf16x3") convolutions: the fp32-accurate mode behind the 1e-3 parity gate (BASELINE.json north_star:
+ * "bf16/tf32 ... within rtol 1e-3"; tf32 keeps 11 significant bits, this mode 16).  Every conv operand is the sum of two
+ * bf16 words, a = a_hi + a_lo: activation buffers hold [hi | lo] halves per row (row stride 2 x cin_pad; written by
+ * rfk_pack_nhwc_bf16 + rfk_pack_nhwc_bf16_lo and by the conv epilogues), packed weights hold [w_hi | w_hi | w_lo] per tap,
+ * and the SAME tcgen05 kernels run a K loop three times as long that visits the activation halves as hi, lo, hi:
+ * a_hi w_hi + a_lo w_hi + a_hi w_lo, accumulated in fp32.  Process-global switch (set once at start-up, not thread-safe);
+ * the bf16-only fusions (rfk_conv1x1_taps_fused, rfk_conv_gemm_splitk_fused, TMA-store epilogue) refuse / step aside. */
+int rfk_set_conv_split(int on);
+int rfk_pack_nhwc_bf16_lo(const float* src, long long src_bstride, int B, int Csrc, int HW, int c_lo, int n, void* dst,
+                          int dst_off, int dst_ld, void* stream);
+
 /* Batched refresh of parameter-derived tensors: ONE launch per kind for a whole model, driven by a device table of
  * 24 x 64-bit words per entry (pointers and integers alike; csrc/prepare.cu documents the word layout of each kind).
  * They replace, per optimizer step, ~340 rfk_pack_weight launches and ~1500 ATen launches that rebuilt the folded

@@ -111,7 +111,7 @@ class GlowStep(nn.Module):
         own_ctx = _ctx is None
         if own_ctx:
             cc = condition.shape[1]
-            nn_in = ops.workspace(("cpl_in", C // 2 + cc), (B, H, W, ops.cin_pad(C // 2 + cc)), x.device)
+            nn_in = ops.workspace(("cpl_in", C // 2 + cc), (B, H, W, ops.buf_ld(C // 2 + cc)), x.device)
             ops.pack_nhwc(ops.f32c(condition), 0, cc, nn_in, 0)
             _ctx = _Ctx(nn_in, cc)
         cc = _ctx.cond_channels
@@ -236,7 +236,7 @@ class ListGlow(nn.Module):
         B, C, H, W = z.shape
         cc = cond.shape[1]
         assert cond.shape[2:4] == z.shape[2:4], "condition and x in affine needs to match"
-        nn_in = ops.workspace(("lvl_in", C // 2 + cc), (B, H, W, ops.cin_pad(C // 2 + cc)), z.device)
+        nn_in = ops.workspace(("lvl_in", C // 2 + cc), (B, H, W, ops.buf_ld(C // 2 + cc)), z.device)
         ops.pack_nhwc(ops.f32c(cond), 0, cc, nn_in, 0)
         return _Ctx(nn_in, cc)
 
@@ -266,7 +266,7 @@ class ListGlow(nn.Module):
         # reverse direction: the level's tensor has 2*half channels once Split2d has re-attached z2
         B, half, H, W = z1.shape
         cc = cond.shape[1]
-        nn_in = ops.workspace(("lvl_in", half + cc), (B, H, W, ops.cin_pad(half + cc)), z1.device)
+        nn_in = ops.workspace(("lvl_in", half + cc), (B, H, W, ops.buf_ld(half + cc)), z1.device)
         ops.pack_nhwc(ops.f32c(cond), 0, cc, nn_in, 0)
         return _Ctx(nn_in, cc)
 
@@ -307,9 +307,9 @@ class ListGlow(nn.Module):
         B, Cb, H, W = bc.shape
         dev = bc.device
         u1, u2 = self.n_units_prior, self.n_units_prior // 2
-        a0 = ops.workspace(("pr_in", Cb), (B, H, W, ops.cin_pad(Cb)), dev)
-        a1 = ops.workspace(("pr_h1", u1), (B, H, W, ops.cin_pad(u1)), dev)
-        a2 = ops.workspace(("pr_h2", u2), (B, H, W, ops.cin_pad(u2)), dev)
+        a0 = ops.workspace(("pr_in", Cb), (B, H, W, ops.buf_ld(Cb)), dev)
+        a1 = ops.workspace(("pr_h1", u1), (B, H, W, ops.buf_ld(u1)), dev)
+        a2 = ops.workspace(("pr_h2", u2), (B, H, W, ops.buf_ld(u2)), dev)
         ops.pack_nhwc(bc, 0, Cb, a0, 0)
         self.prior[0].fused(a0, a1, self.non_lin_glow)
         self.prior[2].fused(a1, a2, self.non_lin_glow)
@@ -335,6 +335,9 @@ class ListGlow(nn.Module):
             x = x + noise
         if torch.is_grad_enabled() and self._wants_grad(x, condition, base_condition):
             # training: tape-recording forward + hand-written backward kernels (Flow/training.py)
+            if ops.SPLIT:
+                raise NotImplementedError("recurrent-flows-msc_b200: RFK_CONV_PRECISION=bf16x3 covers density evaluation and sampling; "
+                                          "train in the default bf16 mode")
             from .training import log_prob_with_grad
             if torch.is_tensor(logdet) and logdet.requires_grad:
                 raise NotImplementedError("recurrent-flows-msc_b200: gradients w.r.t. the logdet argument are not implemented")

@@ -217,7 +217,7 @@ class Conv2dZeros(nn.Module):
         _require_no_grad()
         x = ops.f32c(input)
         B, C, H, W = x.shape
-        act = ops.workspace(("cz_in", C), (B, H, W, ops.cin_pad(C)), x.device)
+        act = ops.workspace(("cz_in", C), (B, H, W, ops.buf_ld(C)), x.device)
         ops.pack_nhwc(x, 0, C, act, 0)
         out = torch.empty(B, self.conv.out_channels, H, W, device=x.device, dtype=torch.float32)
         return self.fused(act, out)
@@ -323,7 +323,7 @@ class Conv2dNorm(nn.Module):
         _require_no_grad()
         x = ops.f32c(input)
         B, C, H, W = x.shape
-        act = ops.workspace(("cn_in", C), (B, H, W, ops.cin_pad(C)), x.device)
+        act = ops.workspace(("cn_in", C), (B, H, W, ops.buf_ld(C)), x.device)
         ops.pack_nhwc(x, 0, C, act, 0)
         out = torch.empty(B, self.conv.out_channels, H, W, device=x.device, dtype=torch.float32)
         return self.fused(act, out)
@@ -458,20 +458,20 @@ class AffineCoupling(nn.Module):
         half, cc = C // 2, condition.shape[1]
         dev = z.device
         if _ctx is None:
-            nn_in = ops.workspace(("cpl_in", half + cc), (B, H, W, ops.cin_pad(half + cc)), dev)
+            nn_in = ops.workspace(("cpl_in", half + cc), (B, H, W, ops.buf_ld(half + cc)), dev)
             ops.pack_nhwc(ops.f32c(condition), 0, cc, nn_in, 0)
             ops.pack_nhwc(z, 0, half, nn_in, cc)
         else:
             nn_in = _ctx.nn_in
             if not _ctx.z1_packed:
                 ops.pack_nhwc(z, 0, half, nn_in, cc)
-        hp = ops.cin_pad(self.hidden_units)
+        hp = ops.buf_ld(self.hidden_units)
         h1 = ops.workspace(("cpl_h1", self.hidden_units), (B, H, W, hp), dev)
         self.net[0].fused(nn_in, h1, self.non_lin, "cz", self._perm(dev))
         last, mid = self.net[4], self.net[2]
         tap_split = last.taps == 9 and 9 * C <= TAP_SPLIT_MAX_N
         # conv1x1 -> ActNorm -> act -> tap-split conv3x3 in one kernel (h2 stays in tensor memory) when the shapes allow
-        b2b = (FUSE_CONV2_TAPS and tap_split and mid.taps == 1 and ops.pad_to(9 * C, 16) <= 128
+        b2b = (FUSE_CONV2_TAPS and not ops.SPLIT and tap_split and mid.taps == 1 and ops.pad_to(9 * C, 16) <= 128
                and self.hidden_units % 64 == 0 and self.hidden_units <= 256 and mid.ready_for_fusion())
         h2 = None
         if not b2b:
@@ -565,15 +565,15 @@ class Split2d(nn.Module):
         """(mean, raw log-scale) tensor [B, 2*half, H, W] from z1 = first `half` channels of z1_src."""
         B, _, H, W = z1_src.shape
         half, cc, dev = self._half, self._cond, z1_src.device
-        sp_in = ops.workspace(("sp_in", half + cc), (B, H, W, ops.cin_pad(half + cc)), dev)
+        sp_in = ops.workspace(("sp_in", half + cc), (B, H, W, ops.buf_ld(half + cc)), dev)
         perm = None
         if self.make_conditional:
             if _ctx is None:
-                cbuf = ops.workspace(("sp_c", cc), (B, H, W, ops.cin_pad(cc)), dev)
+                cbuf = ops.workspace(("sp_c", cc), (B, H, W, ops.buf_ld(cc)), dev)
                 ops.pack_nhwc(ops.f32c(condition), 0, cc, cbuf, 0)
             else:
                 cbuf = _ctx.nn_in   # condition already packed at channels [0, cc)
-            t1 = ops.workspace(("sp_t1", cc), (B, H, W, ops.cin_pad(cc)), dev)
+            t1 = ops.workspace(("sp_t1", cc), (B, H, W, ops.buf_ld(cc)), dev)
             self.convcond[0].fused(cbuf, t1, "relu")
             self.convcond[2].fused(t1, sp_in, "relu")
             perm = self._perm(dev)[0]

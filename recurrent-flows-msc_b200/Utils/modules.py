@@ -16,6 +16,11 @@ def _param_epoch():
     return _PARAM_EPOCH[0]
 
 
+def _no_split_training():
+    if ops.SPLIT:
+        raise NotImplementedError("recurrent-flows-msc_b200: RFK_CONV_PRECISION=bf16x3 covers the forward direction; train in bf16")
+
+
 class ActFun(nn.Module):
     """Utils/modules.py:8-19.  Inside the fused networks the activation is a conv epilogue flag;
     called on its own it is a plain elementwise op."""
@@ -116,6 +121,8 @@ class ConvLSTMLayer(nn.Module):
     def _split_k(self, m_tiles):
         """K slices for launches whose pixel tiles cannot fill the GPU: one slice per filter tap (3x3) when a single
         pixel tile would otherwise walk the whole K = taps*(Cin+Hc) loop on a handful of SMs."""
+        if ops.SPLIT:
+            return 1      # the split-K path hands h to the next step as one bf16 word; the fused kernel writes hi and lo
         return self.taps if (m_tiles <= 2 and self.taps > 1 and self.in_channels + self.hidden_channels >= 256) else 1
 
     def _weights_plain(self):
@@ -153,11 +160,12 @@ class ConvLSTMLayer(nn.Module):
 
     def _staging(self, B, H, W, device):
         cin = self.in_channels + self.hidden_channels
-        shape = (B, H, W, ops.cin_pad(cin))
+        shape = (B, H, W, ops.buf_ld(cin))
         return [ops.workspace(("lstm_in", cin, i), shape, device) for i in range(2)]
 
     def forward(self, input_tensor, cur_state):
         if torch.is_grad_enabled():
+            _no_split_training()
             from .training import convlstm_with_grad   # training: saves pre-activations, hand-written BPTT
             _, h, c = convlstm_with_grad(self, input_tensor.unsqueeze(1), cur_state[0], cur_state[1])
             return h, c
@@ -170,6 +178,9 @@ class ConvLSTMLayer(nn.Module):
         ops.pack_nhwc(x, 0, c, buf, 0)
         if cur_state[0] is None:
             buf[..., c:c + self.hidden_channels].zero_()
+            if ops.SPLIT:
+                lo = buf.shape[-1] // 2
+                buf[..., lo + c:lo + c + self.hidden_channels].zero_()
             c_cur = None
         else:
             h_cur, c_cur = ops.f32c(cur_state[0]), ops.f32c(cur_state[1])
@@ -192,6 +203,7 @@ class ConvLSTM(nn.Module):
 
     def forward(self, x, ht=None, ct=None):
         if torch.is_grad_enabled():
+            _no_split_training()
             from .training import convlstm_with_grad
             return convlstm_with_grad(self.LSTMlayer, x, ht, ct)
         cell = self.LSTMlayer
@@ -205,6 +217,9 @@ class ConvLSTM(nn.Module):
         out = torch.empty(b, seq_len, hc, h, w, device=x.device, dtype=torch.float32)
         if ht is None:
             bufs[0][..., channel:channel + hc].zero_()
+            if ops.SPLIT:
+                lo = bufs[0].shape[-1] // 2
+                bufs[0][..., lo + channel:lo + channel + hc].zero_()
             c_cur = None
         else:
             ops.pack_nhwc(ops.f32c(ht), 0, hc, bufs[0], channel)

@@ -263,6 +263,7 @@ extern "C" int rfk_conv1x1_taps_fused(const void* act, int B, int H, int W, int 
                                       int hid, const float* scale2, const float* shift2, int act_fn, const void* w9,
                                       int n3, int n3_pad, float* taps, void* stream) {
   RFK_REQUIRE(act && w2 && w9 && taps && B > 0 && H > 0 && W > 0, "rfk_conv1x1_taps_fused: null pointer or empty shape");
+  RFK_REQUIRE(!conv_split_mode(), "rfk_conv1x1_taps_fused: the hidden tile is bf16 in tensor memory; not available in split-precision mode");
   RFK_REQUIRE(cin_pad > 0 && cin_pad % 64 == 0 && cin_pad <= act_ld && act_ld % 8 == 0,
               "rfk_conv1x1_taps_fused: cin_pad=%d must be a multiple of 64 and <= act_ld=%d (multiple of 8)", cin_pad, act_ld);
   RFK_REQUIRE(hid >= 64 && hid % 64 == 0 && hid <= 256, "rfk_conv1x1_taps_fused: hidden=%d must be 64, 128, 192 or 256", hid);

@@ -42,7 +42,10 @@ struct GemmArgs {
   int B, H, W;
   int n;                 // real output channels
   int BN;                // tile width in output channels (UMMA N), multiple of 16, <= 256
-  int taps, kchunks;     // kchunks = cin_pad / bk
+  int taps, kchunks;     // kchunks = cin_pad / bk (3 * cin_pad / bk in split-precision mode)
+  int kch, lo_coord;     // split mode: the K loop of a tap has 3 parts of kch chunks that read the activation row's hi half,
+                         // its lo half (channel lo_coord + ...) and the hi half again, against weights [hi | hi | lo];
+                         // otherwise kch = kchunks (one part)
   int bk;                // K elements per chunk: 64 (SWIZZLE_128B) or 32 (SWIZZLE_64B, for Cin <= 32)
   int kgroup;            // K chunks per pipeline stage (one mbarrier round trip per stage)
   int kg_per_split;      // pipeline stages of K per CTA: all of them, or a 1/gridDim.z slice (split-K)
@@ -68,6 +71,7 @@ struct PlainEpi {
   int out_ld, out_off;
   int vec_ok;
   int tma_store;
+  int lo_off;            // split-precision mode: the bf16 residual v - bf16(v) goes to channel + lo_off (0 = off)
 };
 
 struct CouplingEpi {
@@ -103,6 +107,7 @@ struct LstmEpi {
   long long h_bs;
   __nv_bfloat16* h_nhwc;
   int h_off, h_ld, h_vec_ok;
+  int h_lo_off;          // split-precision mode: residual of h at channel + h_lo_off (0 = off)
 };
 
 // ------------------------------------------------------------------------------------------
@@ -256,6 +261,11 @@ __device__ __forceinline__ void epilogue(const GemmArgs& g, const PlainEpi<ACT>&
           for (int k = 0; k < 8; ++k)
             if (col0 + 8 * h8 + k < g.n) dst[8 * h8 + k] = __float2bfloat16(v[8 * h8 + k]);
         }
+      }
+      if (e.lo_off) {   // split precision: second bf16 word holds what the first one rounded away
+#pragma unroll
+        for (int k = 0; k < 16; ++k)
+          if (col0 + k < g.n) dst[e.lo_off + k] = __float2bfloat16(v[k] - __bfloat162float(__float2bfloat16(v[k])));
       }
     } else {
       float* dst = reinterpret_cast<float*>(e.out) + (((long long)t.b * g.n + col0) * g.H + t.y) * g.W + t.x;
@@ -515,6 +525,11 @@ __device__ __forceinline__ void epilogue(const GemmArgs& g, const LstmEpi& e, co
         for (int k = 0; k < 8; ++k)
           if (j0 + k < e.ht) dst[k] = __float2bfloat16(hv[k]);
       }
+      if (e.h_lo_off) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (j0 + k < e.ht) dst[e.h_lo_off + k] = __float2bfloat16(hv[k] - __bfloat162float(__float2bfloat16(hv[k])));
+      }
     }
   }
   release_accumulator(t);
@@ -655,10 +670,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int j = 0; j < g.kgroup; ++j) {
             const int dy = g.taps == 9 ? tap / 3 - 1 : 0;
             const int dx = g.taps == 9 ? tap % 3 - 1 : 0;
+            const int part = kc / g.kch;
+            const int ch0 = (kc - part * g.kch) * g.bk + (part == 1 ? g.lo_coord : 0);
             if (kPair)
-              tma_load_4d_2sm(a_dst + j * a_chunk_bytes, &tmA, full_bar(s) & kPeerBitMask, kc * g.bk, x0 + dx, y0 + dy, n0);
+              tma_load_4d_2sm(a_dst + j * a_chunk_bytes, &tmA, full_bar(s) & kPeerBitMask, ch0, x0 + dx, y0 + dy, n0);
             else
-              tma_load_4d(a_dst + j * a_chunk_bytes, &tmA, full_bar(s), kc * g.bk, x0 + dx, y0 + dy, n0);
+              tma_load_4d(a_dst + j * a_chunk_bytes, &tmA, full_bar(s), ch0, x0 + dx, y0 + dy, n0);
             if (!g.b_resident)
               tma_load_2d(a_dst + g.kgroup * a_chunk_bytes + j * b_chunk_bytes, &tmB, full_bar(s),
                           ((kg0 + grp) * g.kgroup + j) * g.bk, n_tile * g.BN);
@@ -799,6 +816,8 @@ int ilog2_ceil(int v) {
 
 static unsigned long long* g_timeline = nullptr;
 static long long g_timeline_cap = 0;
+static int g_conv_split = 0;   // rfk_set_conv_split: bf16x3 split-precision operands (process-global, set once at start-up)
+int conv_split_mode() { return g_conv_split; }
 
 struct Plan {
   GemmArgs g;
@@ -857,8 +876,9 @@ static int make_plan(Plan& p, const char* who, const void* act, int B, int H, in
                      const void* wgt, int n, int n_pad, int taps, int BN, bool stg_wanted, int k_split = 1,
                      bool allow_pair = false) {
   RFK_REQUIRE(act && wgt && B > 0 && H > 0 && W > 0, "%s: null pointer or empty shape", who);
-  RFK_REQUIRE(cin_pad > 0 && (cin_pad % 64 == 0 || cin_pad == 32) && cin_pad <= act_ld,
-              "%s: cin_pad=%d must be 32 or a multiple of 64, and <= act_ld=%d", who, cin_pad, act_ld);
+  const int parts_ld = g_conv_split ? 2 : 1, parts_k = g_conv_split ? 3 : 1;
+  RFK_REQUIRE(cin_pad > 0 && (cin_pad % 64 == 0 || cin_pad == 32) && parts_ld * cin_pad <= act_ld,
+              "%s: cin_pad=%d must be 32 or a multiple of 64, and %d x cin_pad <= act_ld=%d", who, cin_pad, parts_ld, act_ld);
   const int bk = cin_pad % 64 == 0 ? 64 : 32;
   RFK_REQUIRE(act_ld % 8 == 0, "%s: act_ld=%d must be a multiple of 8 (16-byte TMA strides)", who, act_ld);
   RFK_REQUIRE(taps == 1 || taps == 9, "%s: taps=%d (only 1x1 and 3x3 kernels)", who, taps);
@@ -872,7 +892,10 @@ static int make_plan(Plan& p, const char* who, const void* act, int B, int H, in
     return RFK_ECUDA;
   }
   GemmArgs& g = p.g;
-  g.B = B; g.H = H; g.W = W; g.n = n; g.BN = BN; g.taps = taps; g.bk = bk; g.kchunks = cin_pad / bk;
+  g.B = B; g.H = H; g.W = W; g.n = n; g.BN = BN; g.taps = taps; g.bk = bk; g.kchunks = parts_k * cin_pad / bk;
+  g.kch = cin_pad / bk;
+  g.lo_coord = act_ld / 2;
+  if (g_conv_split) RFK_REQUIRE(act_ld % 16 == 0 && cin_pad <= act_ld / 2, "%s: split precision needs rows of [hi | lo] halves (act_ld=%d, cin_pad=%d)", who, act_ld, cin_pad);
   int twl = ilog2_ceil(W);
   if (twl > 7) twl = 7;
   int thl = ilog2_ceil(H);
@@ -954,11 +977,11 @@ static int make_plan(Plan& p, const char* who, const void* act, int B, int H, in
   g.timeline = (g_timeline && (long long)ctas_x * n_tiles * k_split <= g_timeline_cap) ? g_timeline : nullptr;
   g.scale = nullptr; g.shift = nullptr; g.n_ss = 0;
 
-  int rc = encode_act_map(&p.tmA, who, "A", act, cin_pad, act_ld, B, H, W, p.TW, p.TH, p.NIMG, bk);
+  int rc = encode_act_map(&p.tmA, who, "A", act, g_conv_split ? act_ld : cin_pad, act_ld, B, H, W, p.TW, p.TH, p.NIMG, bk);
   if (rc) return rc;
   p.tmO = p.tmA;  // placeholder unless the epilogue stores through TMA
   // B: weights [n_pad, taps*cin_pad] viewed as 2-D {K, N}; box {64, BN}
-  const cuuint64_t ktot = (cuuint64_t)taps * cin_pad;
+  const cuuint64_t ktot = (cuuint64_t)taps * parts_k * cin_pad;
   cuuint64_t dimsB[2] = {ktot, (cuuint64_t)n_pad};
   cuuint64_t strB[1] = {ktot * 2};
   cuuint32_t boxB[2] = {(cuuint32_t)bk, (cuuint32_t)(g.pair ? BN / 2 : BN)};
@@ -1048,6 +1071,11 @@ static int m_tiles_of(int B, int H, int W) {
 
 using namespace rfk;
 
+extern "C" int rfk_set_conv_split(int on) {
+  g_conv_split = on ? 1 : 0;
+  return RFK_OK;
+}
+
 extern "C" int rfk_debug_set_timeline(unsigned long long* buf, long long capacity_ctas) {
   g_timeline = buf;
   g_timeline_cap = buf ? capacity_ctas : 0;
@@ -1063,13 +1091,15 @@ extern "C" int rfk_conv_gemm(const void* act, int B, int H, int W, int act_ld, i
   RFK_REQUIRE(n_pad > 0 && n_pad % 16 == 0, "rfk_conv_gemm: n_pad=%d must be a positive multiple of 16", n_pad);
   PlainEpi<0> e;
   e.act_fn = act_fn; e.out_kind = out_kind; e.out = out; e.out_ld = out_ld; e.out_off = out_off; e.vec_ok = 0;
-  e.tma_store = 0;
+  e.tma_store = 0; e.lo_off = 0;
   bool tma_ok = false;
   if (out_kind == RFK_OUT_NHWC_BF16) {
-    RFK_REQUIRE(out_off >= 0 && out_off + n <= out_ld, "rfk_conv_gemm: output window [%d,%d) exceeds out_ld=%d", out_off,
-                out_off + n, out_ld);
+    const int span = g_conv_split ? out_ld / 2 : out_ld;   // split precision: [hi | lo] halves of the row
+    RFK_REQUIRE(out_off >= 0 && out_off + n <= span, "rfk_conv_gemm: output window [%d,%d) exceeds %d channels", out_off,
+                out_off + n, span);
     e.vec_ok = out_ld % 8 == 0 && out_off % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
-    tma_ok = e.vec_ok && getenv("RFK_GEMM_NO_TMA_STORE") == nullptr;
+    tma_ok = e.vec_ok && getenv("RFK_GEMM_NO_TMA_STORE") == nullptr && !g_conv_split;
+    if (g_conv_split) e.lo_off = span;
   }
   const int mth = m_tiles_of(B, H, W);
   int BN = 0;
@@ -1095,13 +1125,13 @@ extern "C" int rfk_conv_gemm(const void* act, int B, int H, int W, int act_ld, i
   if (act_fn == RFK_ACT_RELU) {
     PlainEpi<RFK_ACT_RELU> e1;
     e1.act_fn = act_fn; e1.out_kind = e.out_kind; e1.out = e.out; e1.out_ld = e.out_ld; e1.out_off = e.out_off;
-    e1.vec_ok = e.vec_ok; e1.tma_store = e.tma_store;
+    e1.vec_ok = e.vec_ok; e1.tma_store = e.tma_store; e1.lo_off = e.lo_off;
     return launch(p, e1, (cudaStream_t)stream, "rfk_conv_gemm");
   }
   if (act_fn == RFK_ACT_LEAKY) {
     PlainEpi<RFK_ACT_LEAKY> e2;
     e2.act_fn = act_fn; e2.out_kind = e.out_kind; e2.out = e.out; e2.out_ld = e.out_ld; e2.out_off = e.out_off;
-    e2.vec_ok = e.vec_ok; e2.tma_store = e.tma_store;
+    e2.vec_ok = e.vec_ok; e2.tma_store = e.tma_store; e2.lo_off = e.lo_off;
     return launch(p, e2, (cudaStream_t)stream, "rfk_conv_gemm");
   }
   return launch(p, e, (cudaStream_t)stream, "rfk_conv_gemm");
@@ -1132,6 +1162,7 @@ extern "C" int rfk_conv_gemm_splitk_fused(const void* act, int B, int H, int W, 
   RFK_REQUIRE(ws && counters && out && ws_ld >= n_pad && ws_ld % 4 == 0 && (reinterpret_cast<uintptr_t>(ws) & 15) == 0,
               "rfk_conv_gemm_splitk_fused: null pointer or bad workspace (16-byte aligned, ws_ld >= n_pad, ws_ld %% 4 == 0)");
   RFK_REQUIRE(n_pad > 0 && n_pad % 16 == 0 && act_fn >= 0 && act_fn <= 2, "rfk_conv_gemm_splitk_fused: bad n_pad / act_fn");
+  RFK_REQUIRE(!g_conv_split, "rfk_conv_gemm_splitk_fused: not available in split-precision mode");
   RFK_REQUIRE(out_off >= 0 && out_off + n <= out_ld, "rfk_conv_gemm_splitk_fused: output window exceeds out_ld");
   Plan p;
   int rc = make_plan(p, "rfk_conv_gemm_splitk_fused", act, B, H, W, act_ld, cin_pad, wgt, n, n_pad, taps,
@@ -1184,6 +1215,7 @@ extern "C" int rfk_conv_gemm_lstm(const void* act, int B, int H, int W, int act_
   e.peep = peep; e.c_next = c_next; e.c_next_bs = c_next_bstride; e.h_out = h_out; e.h_bs = h_bstride;
   e.h_nhwc = (__nv_bfloat16*)h_nhwc; e.h_off = h_off; e.h_ld = h_ld;
   e.h_vec_ok = h_nhwc && h_ld % 8 == 0 && h_off % 8 == 0 && ht % 8 == 0 && (reinterpret_cast<uintptr_t>(h_nhwc) & 15) == 0;
-  if (h_nhwc) RFK_REQUIRE(h_off >= 0 && h_off + hidden <= h_ld, "rfk_conv_gemm_lstm: h window exceeds h_ld");
+  e.h_lo_off = (h_nhwc && g_conv_split) ? h_ld / 2 : 0;
+  if (h_nhwc) RFK_REQUIRE(h_off >= 0 && h_off + hidden <= (g_conv_split ? h_ld / 2 : h_ld), "rfk_conv_gemm_lstm: h window exceeds h_ld");
   return launch(p, e, (cudaStream_t)stream, "rfk_conv_gemm_lstm");
 }

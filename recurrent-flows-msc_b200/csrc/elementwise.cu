@@ -315,7 +315,7 @@ __global__ void __launch_bounds__(1024) mix1x1_kernel(const float* __restrict__ 
 // consecutive pixels (coalesced reads of each channel plane), each writes one 16-byte group.
 __global__ void __launch_bounds__(kThreads) pack_nhwc_kernel(const float* __restrict__ src, long long src_bs,
                                                              int HW, int c_lo, int n, __nv_bfloat16* __restrict__ dst,
-                                                             int dst_off, int dst_ld, long long npix, int vec_ok) {
+                                                             int dst_off, int dst_ld, long long npix, int vec_ok, int residual) {
   pdl_trigger();
   pdl_wait();
   const int groups = (n + 7) >> 3;
@@ -328,7 +328,12 @@ __global__ void __launch_bounds__(kThreads) pack_nhwc_kernel(const float* __rest
     const int p = (int)(pix % HW);
     const float* sp = src + b * src_bs + (long long)(c_lo + j) * HW + p;
     __nv_bfloat16* dp = dst + pix * dst_ld + dst_off + j;
-    if (vec_ok && j + 8 <= n) {
+    if (residual) {   // split precision: what the bf16 rounding of the value discarded
+      for (int k = 0; k < 8 && j + k < n; ++k) {
+        const float v = sp[(long long)k * HW];
+        dp[k] = __float2bfloat16(v - __bfloat162float(__float2bfloat16(v)));
+      }
+    } else if (vec_ok && j + 8 <= n) {
       __nv_bfloat162 h[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k)
@@ -1203,8 +1208,21 @@ extern "C" int rfk_pack_nhwc_bf16(const float* src, long long src_bstride, int B
   }
   RFK_LAUNCH(pack_nhwc_kernel, stream_grid(npix * ((n + 7) / 8), kThreads, 8), kThreads, 0, (cudaStream_t)stream, 
       src, src_bstride > 0 ? src_bstride : (long long)Csrc * HW, HW, c_lo, n, (__nv_bfloat16*)dst, dst_off, dst_ld,
-      npix, vec_ok);
+      npix, vec_ok, 0);
   return check_launch("rfk_pack_nhwc_bf16");
+}
+
+extern "C" int rfk_pack_nhwc_bf16_lo(const float* src, long long src_bstride, int B, int Csrc, int HW, int c_lo, int n,
+                                     void* dst, int dst_off, int dst_ld, void* stream) {
+  RFK_REQUIRE(src && dst && B > 0 && HW > 0, "rfk_pack_nhwc_bf16_lo: null pointer or empty shape");
+  RFK_REQUIRE(c_lo >= 0 && n >= 0 && c_lo + n <= Csrc && dst_off >= 0 && dst_off + n <= dst_ld,
+              "rfk_pack_nhwc_bf16_lo: bad channel window");
+  if (n == 0) return RFK_OK;
+  long long npix = (long long)B * HW;
+  RFK_LAUNCH(pack_nhwc_kernel, stream_grid(npix * ((n + 7) / 8), kThreads, 8), kThreads, 0, (cudaStream_t)stream,
+      src, src_bstride > 0 ? src_bstride : (long long)Csrc * HW, HW, c_lo, n, (__nv_bfloat16*)dst, dst_off, dst_ld,
+      npix, 0, 1);
+  return check_launch("rfk_pack_nhwc_bf16_lo");
 }
 
 extern "C" int rfk_copy_channels(const float* src, int src_C, int src_off, float* dst, int dst_C, int dst_off,

@@ -42,8 +42,27 @@ def pad_to(v, m):
 
 def cin_pad(c):
     """Channels a conv consumes from an NHWC staging buffer: 32 (64-byte swizzle rows) for up to 32 real
-    channels, else the next multiple of 64 (128-byte swizzle rows).  Also the buffer's row stride."""
+    channels, else the next multiple of 64 (128-byte swizzle rows)."""
     return 32 if c <= 32 else pad_to(c, 64)
+
+
+# Split-precision ("bf16x3") mode, RFK_CONV_PRECISION=bf16x3 (alias tf32): every conv operand is a_hi + a_lo (two bf16
+# words), rows of the staging buffers are [hi | lo] halves, weights are packed [w_hi | w_hi | w_lo] per tap, and the same
+# tcgen05 kernels accumulate a_hi w_hi + a_lo w_hi + a_hi w_lo in fp32 (include/rfk.h, rfk_set_conv_split).  16 significant
+# bits instead of bf16's 8 (tf32: 11): the mode behind the 1e-3 parity gate.  Forward / reverse only (no training path).
+import os as _os
+PRECISION = {"tf32": "bf16x3", "fp32": "bf16x3"}.get(_os.environ.get("RFK_CONV_PRECISION", "bf16").lower(),
+                                                    _os.environ.get("RFK_CONV_PRECISION", "bf16").lower())
+if PRECISION not in ("bf16", "bf16x3"):
+    raise _lib.RfkError(f"RFK_CONV_PRECISION={PRECISION!r}: expected bf16 or bf16x3 (alias tf32)")
+SPLIT = PRECISION == "bf16x3"
+if SPLIT:
+    call("rfk_set_conv_split", 1)
+
+
+def buf_ld(c):
+    """Row stride (channels) of an NHWC staging buffer for c real channels: cin_pad(c), or two such halves [hi | lo]."""
+    return (2 if SPLIT else 1) * cin_pad(c)
 
 
 # --------------------------------------------------------------------------------------
@@ -102,6 +121,11 @@ def mix1x1(x, Wm, bvec=None, side=None, side_n=0, side_off=0, logdet=None, adden
     _chk(x, name="x")
     B, C, H, W = x.shape
     y = torch.empty_like(x)
+    if SPLIT and side is not None:    # the side output is a single bf16 word per value: pack hi and lo from y instead
+        call("rfk_mix1x1", x.data_ptr(), y.data_ptr(), _chk(Wm).data_ptr(), _p(bvec), B, C, H * W, 0, 0, 0, 0, _p(logdet),
+             _p(addend), float(alpha), _stream(), meta={"bytes": 8.0 * x.numel()})
+        pack_nhwc(y, 0, side_n, side, side_off)
+        return y
     side_ld = side.shape[-1] if side is not None else 0
     call("rfk_mix1x1", x.data_ptr(), y.data_ptr(), _chk(Wm).data_ptr(), _p(bvec), B, C, H * W,
          _p(side), side_n, side_off, side_ld, _p(logdet), _p(addend), float(alpha), _stream(),
@@ -120,6 +144,9 @@ def pack_nhwc(src, c_lo, n, dst, dst_off):
     _chk(dst, torch.bfloat16, "dst")
     call("rfk_pack_nhwc_bf16", src.data_ptr(), src.stride(0), B, C, H * W, c_lo, n, dst.data_ptr(), dst_off,
          dst.shape[-1], _stream(), meta={"bytes": 6.0 * B * n * H * W})
+    if SPLIT:
+        call("rfk_pack_nhwc_bf16_lo", src.data_ptr(), src.stride(0), B, C, H * W, c_lo, n, dst.data_ptr(),
+             dst_off + dst.shape[-1] // 2, dst.shape[-1], _stream(), meta={"bytes": 6.0 * B * n * H * W})
 
 
 def copy_channels(src, src_off, dst, dst_off, n):
@@ -132,6 +159,8 @@ def copy_channels(src, src_off, dst, dst_off, n):
 def _gemm_meta(M, n, taps, cin_pad, wgt):
     """Algorithmic (unpadded) and issued (padded) FLOPs of one implicit-GEMM launch, for bench.py's roofline."""
     cin = getattr(wgt, "rfk_cin", cin_pad)
+    if SPLIT:
+        cin, cin_pad = 3 * cin, 3 * cin_pad    # three bf16 products per real multiply
     return {"flops": 2.0 * M * n * taps * cin, "flops_padded": 2.0 * M * wgt.shape[0] * taps * cin_pad,
             "M": M, "N": n, "K": taps * cin,
             # algorithmic HBM bytes: activations read once (bf16, padded row), output written once as bf16
@@ -186,7 +215,7 @@ def choose_k_split(M, taps, cin_pad):
     # 12.7 us).  RFK_CONV_SPLITK=0 disables it, =2 also splits up to SPLITK_MAX_UNITS (pixel tiles x slices).
     import os
     mode = os.environ.get("RFK_CONV_SPLITK", "1")
-    if mode == "0" or taps != 9 or cin_pad % 64 != 0 or cin_pad < 128:
+    if mode == "0" or SPLIT or taps != 9 or cin_pad % 64 != 0 or cin_pad < 128:
         return 1
     m_tiles = (M + 127) // 128
     if m_tiles == 1 and taps * cin_pad >= 2048:
@@ -514,7 +543,47 @@ def _perm32(perm):
     return hit[1]
 
 
+def _split3(packed_f32, taps, kp):
+    """[rows, taps*kp] fp32 in GEMM layout -> bf16 [rows, taps*3*kp] with [w_hi | w_hi | w_lo] per tap."""
+    rows = packed_f32.shape[0]
+    w = packed_f32.view(rows, taps, kp)
+    hi = w.to(torch.bfloat16)
+    lo = (w - hi.float()).to(torch.bfloat16)
+    return torch.stack([hi, hi, lo], 2).reshape(rows, taps * 3 * kp).contiguous()
+
+
+def _pack_weight_split(weight, mode, perm, rows, rows_pad, kp, ktot, cin_real):
+    """Split-precision form of _pack_weight: the same index maps, built with torch ops (cached per parameter version)."""
+    w = weight.detach().float()
+    N, Cin, kh, kw = w.shape
+    taps = kh * kw
+    w = w.reshape(N, Cin, taps)
+    dev = w.device
+    if mode == 0:      # row n, k = t*kp + j <- W[n, perm[j], t]
+        src = w if perm is None else w[:, perm.long().clamp_min(0)] * (perm >= 0).float()[None, :, None]
+        full = torch.zeros(rows_pad, taps, kp, device=dev)
+        full[:N, :, :src.shape[1]] = src.permute(0, 2, 1)
+        k_taps = taps
+    elif mode == 1:    # row r, k = t*kp + co <- W[co, perm[r], taps-1-t]
+        sel = w if perm is None else w[:, perm.long()]
+        full = torch.zeros(rows_pad, taps, kp, device=dev)
+        full[:rows, :, :N] = sel.flip(2).permute(1, 2, 0)
+        k_taps = taps
+    elif mode == 2:    # row t*N + c, k = j <- W[c, j, t]
+        full = torch.zeros(rows_pad, 1, kp, device=dev)
+        full[:taps * N, 0, :Cin] = w.permute(2, 0, 1).reshape(taps * N, Cin)
+        k_taps = 1
+    else:
+        raise _lib.RfkError("split precision: the tap-split data-gradient weights belong to the training path, which this mode "
+                            "does not cover")
+    out = _split3(full.reshape(rows_pad, k_taps * kp), k_taps, kp)
+    out.rfk_cin = cin_real
+    return out, kp
+
+
 def _pack_weight(weight, mode, perm, rows, rows_pad, kp, ktot, cin_real):
+    if SPLIT:
+        return _pack_weight_split(weight, mode, perm, rows, rows_pad, kp, ktot, cin_real)
     w = weight.detach()
     if w.dtype != torch.float32 or not w.is_contiguous():
         w = w.float().contiguous()
@@ -587,6 +656,12 @@ def pack_conv_weight(weight, in_perm=None, row_perm=None, n_pad=None):
         full[valid] = w[row_perm[valid]]
         w, N = full, rows
     n_pad = n_pad or pad_to(N, 16)
+    if SPLIT:
+        full = torch.zeros(n_pad, kh * kw, cin_pad_, device=w.device)
+        full[:N, :, :Cin] = w
+        out = _split3(full.reshape(n_pad, kh * kw * cin_pad_), kh * kw, cin_pad_)
+        out.rfk_cin = Cin
+        return out, cin_pad_
     out = torch.zeros(n_pad, kh * kw, cin_pad_, device=w.device, dtype=torch.bfloat16)
     out[:N, :, :Cin] = w.to(torch.bfloat16)
     out = out.reshape(n_pad, kh * kw * cin_pad_).contiguous()

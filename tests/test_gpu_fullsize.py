@@ -7,6 +7,7 @@ coupling convolutions grows through L5 K10 / K15, which is where the 1e-2 gate m
   * the training path with a level whose NHWC template has no pad columns (half + cc == 32, cc == 16: ADVICE round 1);
   * eval-mode log_prob outside torch.no_grad() runs the inference kernels."""
 import math
+import os
 import types
 
 import pytest
@@ -15,7 +16,8 @@ import torch
 import oracle as O
 
 pytestmark = pytest.mark.gpu
-BF16_TOL = 1e-2
+BF16_TOL = float(os.environ.get("RFK_TEST_TOL", "1e-2"))     # 1e-3 when re-run in bf16x3 mode (tests/test_gpu_precise.py)
+ATOL_SCALE = BF16_TOL / 1e-2
 
 GLOW_ARGS = dict(LU_decomposed=True, n_units_affine=256, non_lin_glow="relu", clamp_type="realnvp",
                  flow_norm="actnorm", flow_batchnorm_momentum=0.0, learn_prior=True, n_units_prior=512,
@@ -75,7 +77,7 @@ def _full_depth(rf, B, C, K, cond_ch, base_ch, seed):
         print(f"L5 K{K} B{B} C{C}: z err {ez:.3e} (max-norm rel), bits/dim abs err {eb:.3e} (ref mean {float(bpd_ref.mean()):.3f}), "
               f"sample err {ex:.3e}")
         assert ez < BF16_TOL
-        torch.testing.assert_close(bpd, bpd_ref, rtol=BF16_TOL, atol=2e-3)
+        torch.testing.assert_close(bpd, bpd_ref, rtol=BF16_TOL, atol=2e-3 * ATOL_SCALE)
         assert ex < 2 * BF16_TOL
 
 

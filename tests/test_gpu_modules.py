@@ -7,6 +7,7 @@ run in bf16 with fp32 accumulation, so tensors that pass through them are held t
 reference tensor's max-norm, and logdet / nll / bits-per-dim to 1e-2 relative (plus a small absolute
 term for near-zero log-dets); fp32-only pieces (ActNorm, InvConv) to 1e-5."""
 import math
+import os
 import types
 
 import pytest
@@ -16,7 +17,10 @@ import oracle as O
 from conftest import load_golden
 
 pytestmark = pytest.mark.gpu
-BF16_TOL = 1e-2
+# 1e-2 for bf16 convolutions; tests/test_gpu_precise.py re-runs this file with RFK_CONV_PRECISION=bf16x3 and
+# RFK_TEST_TOL=1e-3 (BASELINE.json: "within rtol 1e-3 ... (1e-2 for bf16 convs)"); absolute terms scale with the gate
+BF16_TOL = float(os.environ.get("RFK_TEST_TOL", "1e-2"))
+ATOL_SCALE = BF16_TOL / 1e-2
 
 
 @pytest.fixture(scope="module")
@@ -31,7 +35,7 @@ def max_rel(a, b):
 
 
 def assert_ld(a, b, rtol=BF16_TOL, atol=5e-2):
-    torch.testing.assert_close(a.cpu().float(), b.cpu().float(), rtol=rtol, atol=atol)
+    torch.testing.assert_close(a.cpu().float(), b.cpu().float(), rtol=rtol, atol=atol * ATOL_SCALE)
 
 
 def cuda_sd(sd):
@@ -160,7 +164,7 @@ def test_listglow_cond_golden(rf):
         assert max_rel(z2, g["z_logprob"]) < BF16_TOL
         assert_ld(nll, g["nll"], atol=0.2)
         bpd = nll / (math.log(2.0) * 256)
-        torch.testing.assert_close(bpd.cpu(), g["bpd"], rtol=BF16_TOL, atol=1e-3)
+        torch.testing.assert_close(bpd.cpu(), g["bpd"], rtol=BF16_TOL, atol=1e-3 * ATOL_SCALE)
         xs = m.sample(None, conds, g["base"].cuda(), num_samples=2, temperature=g["temperature"],
                       eps_prior=g["eps_prior"].cuda(), eps_list=[e.cuda() for e in g["eps_split"]])
         assert max_rel(xs, g["x_sample"]) < BF16_TOL
@@ -219,7 +223,7 @@ def test_listglow_cfg1_vs_oracle(rf):
         z, nll = m.log_prob(x.cuda(), [c.cuda() for c in conds], None, logdet=0, noise=noise.cuda())
         assert max_rel(z, z_ref) < BF16_TOL
         bpd, bpd_ref = nll.cpu() / (math.log(2) * 1024), nll_ref / (math.log(2) * 1024)
-        torch.testing.assert_close(bpd, bpd_ref, rtol=BF16_TOL, atol=2e-3)
+        torch.testing.assert_close(bpd, bpd_ref, rtol=BF16_TOL, atol=2e-3 * ATOL_SCALE)
         # z -> x through g with the draws that f discarded replaced by fresh eps: x must be finite and,
         # for the last level (no split), g inverts f exactly -- checked through GlowStep round trips above
         xs = m.sample(None, [c.cuda() for c in conds], None, num_samples=B, temperature=0.7)
@@ -245,7 +249,7 @@ def test_listglow_rfn_shape_vs_oracle(rf):
         z_ref, nll_ref = O.listglow_log_prob(x, conds, base, sd, 5, 2, 8, noise=noise, learn_prior=True)
         z, nll = m.log_prob(x.cuda(), [c.cuda() for c in conds], base.cuda(), logdet=0, noise=noise.cuda())
         assert max_rel(z, z_ref) < BF16_TOL
-        torch.testing.assert_close(nll.cpu() / (math.log(2) * 4096), nll_ref / (math.log(2) * 4096), rtol=BF16_TOL, atol=2e-3)
+        torch.testing.assert_close(nll.cpu() / (math.log(2) * 4096), nll_ref / (math.log(2) * 4096), rtol=BF16_TOL, atol=2e-3 * ATOL_SCALE)
         eps_prior = torch.randn(B, 64, 2, 2, generator=g)
         eps = [torch.randn(B, 2 << l, 32 >> l, 32 >> l, generator=g) for l in range(4)]
         x_ref = O.listglow_sample(conds, base, sd, 5, 2, eps_prior, eps, 0.7, learn_prior=True)
@@ -281,8 +285,8 @@ def test_hidden_actnorm_data_dependent_init(rf):
         y, _ = O.invconv(y, sd0, "glow_frame.1.invconv.")
         h = torch.nn.functional.conv2d(torch.cat([y[:, :2], conds[0]], 1), sd0["glow_frame.1.affine.net.0.conv.weight"], None, 1, 1)
         bh, lh = O.actnorm_init(h)
-        torch.testing.assert_close(st.affine.net[0].norm_type.logs.cpu(), lh, rtol=2e-2, atol=2e-2)
-        torch.testing.assert_close(st.affine.net[0].norm_type.bias.cpu(), bh, rtol=2e-2, atol=2e-2)
+        torch.testing.assert_close(st.affine.net[0].norm_type.logs.cpu(), lh, rtol=2 * BF16_TOL, atol=2 * BF16_TOL)
+        torch.testing.assert_close(st.affine.net[0].norm_type.bias.cpu(), bh, rtol=2 * BF16_TOL, atol=2 * BF16_TOL)
         assert torch.isfinite(nll).all()
 
 
@@ -365,7 +369,7 @@ def test_listglow_config_d_shape_vs_oracle(rf):
         assert z.shape == (B, 192, 2, 2)
         assert max_rel(z, z_ref) < BF16_TOL
         chw = 3 * 64 * 64
-        torch.testing.assert_close(nll.cpu() / (math.log(2) * chw), nll_ref / (math.log(2) * chw), rtol=BF16_TOL, atol=2e-3)
+        torch.testing.assert_close(nll.cpu() / (math.log(2) * chw), nll_ref / (math.log(2) * chw), rtol=BF16_TOL, atol=2e-3 * ATOL_SCALE)
         eps_prior = torch.randn(B, 192, 2, 2, generator=g)
         eps = [torch.randn(B, 6 << l, 32 >> l, 32 >> l, generator=g) for l in range(4)]
         x_ref = O.listglow_sample(conds, base, sd, 5, 1, eps_prior, eps, 0.7, learn_prior=True)
