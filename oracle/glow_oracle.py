@@ -169,12 +169,16 @@ def _same_pad(w):
     return ((w.shape[2] - 1) // 2, (w.shape[3] - 1) // 2)
 
 
-def conv2d_norm(x, sd, prefix):
+def conv2d_norm(x, sd, prefix, training=False):
     """Flow/glow_modules.py:123-147.  norm='actnorm': bias-free conv, then ActNorm fwd;
-    norm='batchnorm' (keys norm_type.running_mean present): conv with bias, then nn.BatchNorm2d in eval mode."""
+    norm='batchnorm' (keys norm_type.running_mean present): conv with bias, then nn.BatchNorm2d (eval mode: running
+    buffers; ``training``: batch statistics, the buffers are left alone -- they do not enter the output)."""
     w = sd[prefix + "conv.weight"].float()
     if prefix + "norm_type.running_mean" in sd:
         y = F.conv2d(x, w, sd[prefix + "conv.bias"].float(), 1, _same_pad(w))
+        if training:
+            return F.batch_norm(y, None, None, sd[prefix + "norm_type.weight"].float(), sd[prefix + "norm_type.bias"].float(),
+                                True, 0.1, 1e-5)
         return F.batch_norm(y, sd[prefix + "norm_type.running_mean"].float(), sd[prefix + "norm_type.running_var"].float(),
                             sd[prefix + "norm_type.weight"].float(), sd[prefix + "norm_type.bias"].float(), False, 0.1, 1e-5)
     y = F.conv2d(x, w, None, 1, _same_pad(w))
@@ -262,12 +266,13 @@ def split2d(x, condition, sd, prefix, logdet=None, reverse=False, temperature=No
 # GlowStep / ListGlow  (Flow/glow.py)
 # ----------------------------------------------------------------------------
 def glow_step(x, condition, sd, prefix, logdet=None, reverse=False,
-              clamp_type="realnvp", non_lin="relu"):
-    """Flow/glow.py:31-41; flow_norm='batchnorm' (keys norm.log_gamma present) in eval mode uses the running buffers."""
+              clamp_type="realnvp", non_lin="relu", training=False):
+    """Flow/glow.py:31-41; flow_norm='batchnorm' (keys norm.log_gamma present) in eval mode uses the running buffers,
+    with ``training`` the batch statistics (Flow/glow_modules.py:73-87)."""
     if prefix + "norm.log_gamma" in sd:
         bn = lambda t, ld, rev: batchnorm_flow(t, sd[prefix + "norm.log_gamma"].float(), sd[prefix + "norm.beta"].float(),  # noqa: E731
                                                sd[prefix + "norm.running_mean"].float(),
-                                               sd[prefix + "norm.running_var"].float(), ld, rev)[:2]
+                                               sd[prefix + "norm.running_var"].float(), ld, rev, training)[:2]
         if not reverse:
             x, logdet = bn(x, logdet, False)
             x, logdet = invconv(x, sd, prefix + "invconv.", logdet, False)
@@ -298,7 +303,7 @@ def listglow_layout(L, K):
 
 
 def listglow_f(x, condition, sd, L, K, logdet=0.0, prefix="", clamp_type="realnvp",
-               non_lin="relu", make_conditional=True, split2d_act="softplus"):
+               non_lin="relu", make_conditional=True, split2d_act="softplus", training=False):
     """Flow/glow.py:105-117.  x -> z."""
     z = x
     for i, (kind, l) in enumerate(listglow_layout(L, K)):
@@ -308,7 +313,7 @@ def listglow_f(x, condition, sd, L, K, logdet=0.0, prefix="", clamp_type="realnv
         elif kind == "split":
             z, logdet = split2d(z, condition[l], sd, p, logdet, False, None, make_conditional, split2d_act)
         else:
-            z, logdet = glow_step(z, condition[l], sd, p, logdet, False, clamp_type, non_lin)
+            z, logdet = glow_step(z, condition[l], sd, p, logdet, False, clamp_type, non_lin, training)
     return z, logdet
 
 
@@ -331,11 +336,11 @@ def listglow_g(z, condition, sd, L, K, logdet=None, temperature=1.0, prefix="",
     return x, logdet
 
 
-def listglow_prior(base_condition, sd, n, z_shape, learn_prior=True, non_lin="relu", prefix=""):
+def listglow_prior(base_condition, sd, n, z_shape, learn_prior=True, non_lin="relu", prefix="", training=False):
     """Flow/glow.py:133-137.  Returns (mean, log_scale) as 'split' halves of the prior net."""
     if learn_prior:
-        h = act_fun(conv2d_norm(base_condition, sd, prefix + "prior.0."), non_lin)
-        h = act_fun(conv2d_norm(h, sd, prefix + "prior.2."), non_lin)
+        h = act_fun(conv2d_norm(base_condition, sd, prefix + "prior.0.", training), non_lin)
+        h = act_fun(conv2d_norm(h, sd, prefix + "prior.2.", training), non_lin)
         out = conv2d_zeros(h, sd, prefix + "prior.4.")
     else:
         out = torch.zeros(n, 2 * z_shape[0], z_shape[1], z_shape[2])
@@ -352,7 +357,7 @@ def listglow_log_prob(x, condition, base_condition, sd, L, K, n_bits, noise=None
     z, obj = listglow_f(x, condition, sd, L, K, logdet, prefix, **kw)
     obj = obj + obj_unif
     mean, log_scale = listglow_prior(base_condition, sd, b, z.shape[1:], learn_prior,
-                                     kw.get("non_lin", "relu"), prefix)
+                                     kw.get("non_lin", "relu"), prefix, kw.get("training", False))
     obj = obj + batch_reduce(_normal_log_prob(z, mean, torch.exp(log_scale)))
     return z, -obj
 

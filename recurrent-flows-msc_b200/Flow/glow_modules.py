@@ -269,8 +269,10 @@ class Conv2dNorm(nn.Module):
             return s.contiguous(), t.contiguous()
         return self._cache.get("bn", (bn.weight, bn.bias, bn.running_mean, bn.running_var, self.conv.bias), build)
 
-    def affine(self, act=None, wgt=None, cin_pad=None):
-        """(scale, shift) of the normalisation as a conv epilogue; data-dependent cases run a raw conv pass first."""
+    def affine(self, act=None, wgt=None, cin_pad=None, keep=None):
+        """(scale, shift) of the normalisation as a conv epilogue; data-dependent cases run a raw conv pass first.
+        ``keep`` (dict): in training-mode batch norm, receives the raw conv output and the batch statistics the backward
+        needs (Flow/training.py)."""
         n = self.conv.out_channels
         if self.norm == "actnorm":
             an = self.norm_type
@@ -303,14 +305,16 @@ class Conv2dNorm(nn.Module):
                 bn.num_batches_tracked += 1
             s = bn.weight.detach().float() / torch.sqrt(var_b + bn.eps)
             t = (self.conv.bias.detach().float() - mean) * s + bn.bias.detach().float()
+            if keep is not None:
+                keep.update(raw=raw, mean=mean, var=var_b)
             return s.contiguous(), t.contiguous()
         return None, (None if self.conv.bias is None else self.conv.bias.detach().float())
 
-    def fused(self, act, out, act_fn="none", key="id", in_perm=None, out_off=0):
+    def fused(self, act, out, act_fn="none", key="id", in_perm=None, out_off=0, keep=None):
         """act NHWC bf16 -> out (NHWC bf16 at channel out_off, or NCHW f32) = act_fn(norm(conv(act)))."""
         wgt, cin_pad = self.packed(key, in_perm)
         n = self.conv.out_channels
-        scale, shift = self.affine(act, wgt, cin_pad)
+        scale, shift = self.affine(act, wgt, cin_pad, keep)
         if out.dtype == torch.bfloat16:
             B, H, W, _ = act.shape
             k_split = ops.choose_k_split(B * H * W, self.taps, cin_pad)

@@ -14,8 +14,10 @@ Only the map from module parameters to the folded per-step quantities (C x C mix
 ActNorm scale, its log-determinant) is differentiated by torch autograd, on C x C tensors.  Activation gradients
 between convolutions are bf16 (as the activations are); parameter gradients accumulate in fp32.
 
-Not covered (raise NotImplementedError): flow_norm='batchnorm', batch-norm hidden layers in the prior, couplings with
-more than 256 channels (no tap-split form), gradients w.r.t. a tensor-valued ``logdet`` argument.
+The batch-norm options of the reference (flow_norm='batchnorm': per-position BatchNormFlow; base_norm='batchnorm':
+nn.BatchNorm2d in the prior) are differentiated with torch ops around the same conv kernels (small tensors, non-default).
+Not covered (raise NotImplementedError): couplings with more than 256 channels (no tap-split form), gradients w.r.t. a
+tensor-valued ``logdet`` argument.
 """
 import os
 
@@ -138,9 +140,36 @@ def _nhwc(B, H, W, c, dev):
     return (torch.empty if ld == c else torch.zeros)(B, H, W, ld, device=dev, dtype=torch.bfloat16)
 
 
-def _check_actnorm(mod):
-    if mod.norm != "actnorm":
-        raise NotImplementedError("recurrent-flows-msc_b200: backward through batch-norm hidden layers is not implemented")
+def _act_grad(h, act_fn):
+    if act_fn == "relu":
+        return (h > 0).to(h.dtype)
+    if act_fn == "leakyrelu":
+        return torch.where(h > 0, torch.ones_like(h), torch.full_like(h, 0.2))
+    return torch.ones_like(h)
+
+
+def _batchnorm_act_bwd(st, mod, dh, h, act_fn, keep):
+    """Backward of h = act(BatchNorm2d(conv + bias)) in training mode (Flow/glow_modules.py:134-137,144-145; the
+    reference's base_norm='batchnorm' option, used only by the prior on the coarsest maps): per-channel batch-norm backward
+    over (B,H,W) written with torch ops on the fp32 raw conv output kept by the forward -- a handful of launches on
+    [B,n,2,2] tensors.  Returns da (bf16 NHWC) for the conv's weight / data gradients."""
+    bn, n = mod.norm_type, mod.conv.out_channels
+    B, H, W, ld = dh.shape
+    a = keep["raw"]                                                     # conv + bias, fp32 NCHW
+    mean, var = keep["mean"].view(1, n, 1, 1), keep["var"].view(1, n, 1, 1)
+    inv_std = torch.rsqrt(var + bn.eps)
+    xhat = (a - mean) * inv_std
+    dv = dh[..., :n].float().permute(0, 3, 1, 2) * _act_grad(h[..., :n].float().permute(0, 3, 1, 2), act_fn)
+    gamma = bn.weight.detach().float().view(1, n, 1, 1)
+    st.add(bn.weight, (dv * xhat).sum((0, 2, 3)))
+    st.add(bn.bias, dv.sum((0, 2, 3)))
+    m1 = dv.mean((0, 2, 3), keepdim=True)
+    m2 = (dv * xhat).mean((0, 2, 3), keepdim=True)
+    da32 = (gamma * inv_std * (dv - m1 - xhat * m2)).contiguous()
+    st.add(mod.conv.bias, da32.sum((0, 2, 3)))
+    da = _nhwc(B, H, W, n, dh.device)
+    ops.pack_nhwc(da32, 0, n, da, 0)
+    return da
 
 
 def _conv_bwd(st, mod, x_act, cin, da, perm=None, dgrad_out=None, key="id"):
@@ -165,9 +194,12 @@ def _conv_bwd(st, mod, x_act, cin, da, perm=None, dgrad_out=None, key="id"):
             ops.conv_gemm(da, cp, wd, cin, mod.taps, None, None, "none", dgrad_out)
 
 
-def _norm_act_bwd(st, mod, dh, h, act_fn):
+def _norm_act_bwd(st, mod, dh, h, act_fn, keep=None):
     """Backward of h = act(ActNorm(conv)) for a Conv2dNorm: returns da (bf16 NHWC), accumulates d logs / d bias."""
-    _check_actnorm(mod)
+    if mod.norm == "batchnorm":
+        if not keep:
+            raise NotImplementedError("recurrent-flows-msc_b200: eval-mode batch norm inside a training step is not supported")
+        return _batchnorm_act_bwd(st, mod, dh, h, act_fn, keep)
     assert dh.shape[-1] == h.shape[-1]
     n = mod.conv.out_channels
     scale, _ = mod.norm_type.affine()
@@ -191,19 +223,83 @@ def _zeros_out_bwd(st, mod, dout, out):
 # ----------------------------------------------------------------------------------------
 # GlowStep
 # ----------------------------------------------------------------------------------------
+def _bnflow_fwd(step, x, ld):
+    """flow_norm='batchnorm' (Flow/glow_modules.py:56-104) in a training step: batch statistics per POSITION over the batch
+    dimension; the normalisation cannot be folded into the C x C mix, so it is its own elementwise kernel.  Returns the
+    normalised tensor and what the backward needs."""
+    bn = step.norm
+    if bn.training:
+        mean, var = ops.batch_stats_pos(x, bn.eps)            # [C,H,W]; var includes + eps
+        with torch.no_grad():
+            bn.running_mean.mul_(bn.momentum).add_(mean * (1 - bn.momentum))
+            bn.running_var.mul_(bn.momentum).add_(var * (1 - bn.momentum))
+    else:
+        mean, var = bn.running_mean[0].float().contiguous(), bn.running_var[0].float().contiguous()
+    a, c, d = bn._affine(mean, var, False)
+    xn = ops.affine_pos(x, a, c)
+    ld.add_(d)
+    return xn, (mean, var, bn.training)
+
+
+def _bnflow_bwd(st, step, x, dxn, saved):
+    """Reverse mode of the batch-norm flow layer (torch ops on [B, C*H*W] views; a non-default option of the reference)."""
+    bn = step.norm
+    mean, var, batch_stats = saved
+    lg, G = bn.log_gamma.detach()[0].float(), st.G.reshape(())
+    sigma = var.sqrt()
+    xc = x - mean
+    xhat = xc / sigma
+    gamma = torch.exp(lg)
+    st.add(bn.beta, dxn.sum(0))
+    st.add(bn.log_gamma, (dxn * xhat).sum(0) * gamma + G)
+    dxhat = dxn * gamma
+    if not batch_stats:                                        # running statistics: constants
+        return (dxhat / sigma).contiguous()
+    B = x.shape[0]
+    dvar = (dxhat * xc).sum(0) * (-0.5) / (var * sigma) - 0.5 * G / var
+    dmean = -(dxhat.sum(0)) / sigma
+    return (dxhat / sigma + dvar * (2.0 / B) * xc + dmean / B).contiguous()
+
+
+def _invconv_param_bwd(st, inv, dW, hw):
+    """d loss / d InvConv parameters from d W and the log-det term, through the C x C assembly (torch autograd; the batched
+    kernel covers the ActNorm-folded default, this the batch-norm variant)."""
+    names = ("lower", "upper", "log_s") if inv.LU_decomposed else ("weight",)
+    params = [getattr(inv, n) for n in names]
+    with torch.enable_grad():
+        leaf = [p.detach().float().requires_grad_() for p in params]
+        if inv.LU_decomposed:
+            l_mask, eye = inv._consts(leaf[0].device)
+            lower = leaf[0] * l_mask + eye
+            u = leaf[1] * l_mask.transpose(0, 1) + torch.diag(inv.sign_s * torch.exp(leaf[2]))
+            Wm = torch.matmul(inv.p, torch.matmul(lower, u))
+            ldw = leaf[2].sum()
+        else:
+            Wm = leaf[0]
+            ldw = torch.linalg.slogdet(Wm)[1]
+        gs = torch.autograd.grad([Wm, ldw * hw], leaf, [dW, st.G.reshape(())])
+    for p, g in zip(params, gs):
+        st.add(p, g)
+
+
 def _glowstep_fwd(flow, step, x, ld, nn_template, cc, l, tape):
-    if isinstance(step.norm, BatchNormFlow):
-        raise NotImplementedError("recurrent-flows-msc_b200: backward for flow_norm='batchnorm' is not implemented")
     aff = step.affine
     net = aff.net
     B, C, H, W = x.shape
     half, hid, act, dev = C // 2, aff.hidden_units, aff.non_lin, x.device
     if net[4].taps != 9 or 9 * C > TAP_SPLIT_MAX_N:
         raise NotImplementedError("recurrent-flows-msc_b200: coupling backward needs the tap-split form (C <= 256)")
-    step.norm.maybe_initialize(x)
-    Wf, bf = step._folded_fwd(H * W)[:2]
     nn_in = nn_template.clone()
-    y = ops.mix1x1(x, Wf, bf, side=nn_in, side_n=half, side_off=cc, logdet=ld, addend=step._dlogdet(H * W), alpha=1.0)
+    bn_saved = xn = None
+    if isinstance(step.norm, BatchNormFlow):
+        xn, bn_saved = _bnflow_fwd(step, x, ld)
+        Wm, per_pixel = step.invconv.weight_fwd()
+        y = ops.mix1x1(xn, Wm, None, side=nn_in, side_n=half, side_off=cc, logdet=ld,
+                       addend=(per_pixel * (H * W)).reshape(1).contiguous(), alpha=1.0)
+    else:
+        step.norm.maybe_initialize(x)
+        Wf, bf = step._folded_fwd(H * W)[:2]
+        y = ops.mix1x1(x, Wf, bf, side=nn_in, side_n=half, side_off=cc, logdet=ld, addend=step._dlogdet(H * W), alpha=1.0)
     h1, h2 = _nhwc(B, H, W, hid, dev), _nhwc(B, H, W, hid, dev)
     net[0].fused(nn_in, h1, act, "cz", aff._perm(dev))
     net[2].fused(h1, h2, act)
@@ -211,11 +307,11 @@ def _glowstep_fwd(flow, step, x, ld, nn_template, cc, l, tape):
     taps = torch.empty(B, 9 * C, H, W, device=dev, dtype=torch.float32)
     ops.conv_gemm(h2, cp, wgt9, 9 * C, 1, None, None, "none", taps)
     ops.coupling_tail_taps(taps, y, *aff.tail_params(), ld, False)
-    tape.append(lambda st: _glowstep_bwd(st, flow, step, x, y, nn_in, h1, h2, taps, cc, l))
+    tape.append(lambda st: _glowstep_bwd(st, flow, step, x, y, nn_in, h1, h2, taps, cc, l, xn, bn_saved))
     return y
 
 
-def _glowstep_bwd(st, flow, step, x, zo, nn_in, h1, h2, taps, cc, l):
+def _glowstep_bwd(st, flow, step, x, zo, nn_in, h1, h2, taps, cc, l, xn=None, bn_saved=None):
     aff = step.affine
     net = aff.net
     B, C, H, W = zo.shape
@@ -242,6 +338,13 @@ def _glowstep_bwd(st, flow, step, x, zo, nn_in, h1, h2, taps, cc, l):
     ops.add_channels(dz, 0, dnn, cc, half)          # dz[:, :half] += d z1 (the network's input after the condition)
     if cc:
         st.add_cond(l, dnn, cc)
+    if bn_saved is not None:     # flow_norm='batchnorm': plain InvConv mix, then the per-position batch-norm layer
+        Wm = step.invconv.weight_fwd()[0]
+        dWm, _ = ops.mix1x1_wgrad(xn, dz)
+        dxn = ops.mix1x1(dz, Wm.t().contiguous(), None)
+        _invconv_param_bwd(st, step.invconv, dWm, H * W)
+        st.dz = _bnflow_bwd(st, step, x, dxn, bn_saved)
+        return
     # ActNorm folded into the 1x1 mix: y = Wf x + bf
     fold = step._folded_fwd(H * W)
     buf = st.fold_buf(flow, step, C)
@@ -392,9 +495,9 @@ def _prior_fwd(flow, z, base_condition, obj, tape):
     u1, u2, act = flow.n_units_prior, flow.n_units_prior // 2, flow.non_lin_glow
     a0, a1, a2 = _nhwc(B, H, W, Cb, dev), _nhwc(B, H, W, u1, dev), _nhwc(B, H, W, u2, dev)
     ops.pack_nhwc(bc, 0, Cb, a0, 0)
-    _check_actnorm(flow.prior[0])
-    flow.prior[0].fused(a0, a1, act)
-    flow.prior[2].fused(a1, a2, act)
+    k0, k2 = {}, {}
+    flow.prior[0].fused(a0, a1, act, keep=k0)
+    flow.prior[2].fused(a1, a2, act, keep=k2)
     params = torch.empty(B, 2 * n, H, W, device=dev, dtype=torch.float32)
     flow.prior[4].fused(a2, params)
     ops.gauss_logp(z, 0, params, n, ops.PAIR_SPLIT, "exp", obj)
@@ -404,10 +507,10 @@ def _prior_fwd(flow, z, base_condition, obj, tape):
         da = _zeros_out_bwd(st, flow.prior[4], dparams, params)
         dh2 = _nhwc(B, H, W, u2, dev)
         _conv_bwd(st, flow.prior[4], a2, u2, da, dgrad_out=dh2)
-        da2 = _norm_act_bwd(st, flow.prior[2], dh2, a2, act)
+        da2 = _norm_act_bwd(st, flow.prior[2], dh2, a2, act, k2)
         dh1 = _nhwc(B, H, W, u1, dev)
         _conv_bwd(st, flow.prior[2], a1, u1, da2, dgrad_out=dh1)
-        da1 = _norm_act_bwd(st, flow.prior[0], dh1, a1, act)
+        da1 = _norm_act_bwd(st, flow.prior[0], dh1, a1, act, k0)
         st.dbase = torch.empty(B, Cb, H, W, device=dev, dtype=torch.float32)
         _conv_bwd(st, flow.prior[0], a0, Cb, da1, dgrad_out=st.dbase)
     tape.append(bwd)

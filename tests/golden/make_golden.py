@@ -253,6 +253,29 @@ def main():
     save("convlstm", {"x": x, "sd": sd, "out": out.detach(), "h": h.detach(), "c": c.detach(),
                       "h0": h0, "c0": c0, "out2": out2.detach(), "h2": h2.detach(), "c2": c2.detach()})
 
+    # training mode of the same options: batch statistics in BatchNormFlow (per position) and in the prior's BatchNorm2d,
+    # with the gradients torch autograd gives through the reference's modules (pins the oracle's training flag)
+    B4 = 4
+    a = glow_args(flow_norm="batchnorm", base_norm="batchnorm", flow_batchnorm_momentum=0.0, L=2, K=2)
+    cond_sizes = [[B4, 4, 8, 8], [B4, 6, 4, 4]]
+    torch.manual_seed(53)
+    m = ListGlow([B4, 1, 16, 16], cond_sizes, [B4, 5, 4, 4], a).train()
+    perturb(m, g)
+    sd0 = sd_of(m)
+    x = torch.floor(torch.rand(B4, 1, 16, 16, generator=g) * 256) / 256 - 0.5
+    conds = [R(*s) for s in cond_sizes]
+    base = R(B4, 5, 4, 4)
+    torch.manual_seed(59)
+    noise = torch.zeros_like(x).uniform_(0, 1.0 / 2 ** a.n_bits)
+    torch.manual_seed(59)
+    z_lp, nll = m.log_prob(x, conds, base, logdet=0)
+    wts = torch.rand(B4, generator=g) + 0.5
+    ((nll * wts).sum() / (0.6931471805599453 * 256 * B4)).backward()
+    grads = {n: p.grad.detach().clone() for n, p in m.named_parameters() if p.grad is not None}
+    save("listglow_batchnorm_train", {"x": x, "cond": conds, "base": base, "sd": sd0, "noise": noise, "wts": wts,
+                                      "z_logprob": z_lp.detach(), "nll": nll.detach(), "grads": grads, "args": vars(a),
+                                      "x_size": [B4, 1, 16, 16], "cond_sizes": cond_sizes, "base_size": [B4, 5, 4, 4]})
+
 
 if __name__ == "__main__":
     main()

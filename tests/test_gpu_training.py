@@ -423,3 +423,37 @@ def test_taped_forward_equals_inference_forward(rf):
     assert nll1.requires_grad
     assert rel(z1.detach(), z0) < 1e-2
     torch.testing.assert_close(nll1.detach() / (math.log(2) * 256), nll0 / (math.log(2) * 256), rtol=1e-2, atol=2e-3)
+
+
+def test_batchnorm_options_train_against_reference_gradients(rf):
+    """flow_norm='batchnorm' (BatchNormFlow, per-position batch statistics) and base_norm='batchnorm' (BatchNorm2d in the
+    prior) in train() mode: forward, running-buffer updates and every parameter gradient against the fixture made from the
+    REFERENCE's own modules and torch autograd (tests/golden/make_golden.py)."""
+    from conftest import load_golden
+    g = load_golden("listglow_batchnorm_train")
+    a = types.SimpleNamespace(**g["args"])
+    m = rf.ListGlow(g["x_size"], g["cond_sizes"], g["base_size"], a)
+    m.load_state_dict(g["sd"])
+    m = m.cuda().train()
+    rm0 = m.glow_frame[1].norm.running_mean.clone()
+    z, nll = m.log_prob(g["x"].cuda(), [c.cuda() for c in g["cond"]], g["base"].cuda(), logdet=0, noise=g["noise"].cuda())
+    assert nll.requires_grad
+    assert rel(z.detach(), g["z_logprob"]) < 1e-2
+    torch.testing.assert_close(nll.detach().cpu(), g["nll"], rtol=1e-2, atol=0.5)
+    assert not torch.equal(rm0, m.glow_frame[1].norm.running_mean)            # batch statistics were taken
+    assert int(m.prior[0].norm_type.num_batches_tracked) == 1
+    B = z.shape[0]
+    ((nll * g["wts"].cuda()).sum() / (math.log(2) * 256 * B)).backward()
+    scale = max(float(v.abs().max()) for v in g["grads"].values())
+    bad = []
+    for name, p in m.named_parameters():
+        ref = g["grads"].get(name)
+        if ref is None:
+            continue
+        assert p.grad is not None, f"no gradient for {name}"
+        if float(ref.abs().max()) < 1e-5 * scale:
+            continue
+        c = cosine(p.grad, ref)
+        if c < 0.97 or rel(p.grad, ref) > 0.15:
+            bad.append((name, round(c, 4), round(rel(p.grad, ref), 4)))
+    assert not bad, bad

@@ -175,3 +175,21 @@ def test_listglow_batchnorm():
     xs = O.listglow_sample(g["cond"], g["base"], g["sd"], a["L"], a["K"], g["eps_prior"], g["eps_split"],
                            g["temperature"], learn_prior=True, **_kw(a))
     close(xs, g["x_sample"], atol=1e-4)
+
+
+def test_listglow_batchnorm_training_mode_and_grads():
+    """flow_norm='batchnorm' + base_norm='batchnorm' in train() mode: batch statistics, and autograd through the oracle
+    gives the reference's gradients."""
+    g = load_golden("listglow_batchnorm_train")
+    a = g["args"]
+    leaf = {k: (v.clone().requires_grad_() if v.is_floating_point() and "running" not in k else v) for k, v in g["sd"].items()}
+    z, nll = O.listglow_log_prob(g["x"], g["cond"], g["base"], leaf, a["L"], a["K"], a["n_bits"],
+                                 noise=g["noise"], learn_prior=True, training=True, **_kw(a))
+    close(z.detach(), g["z_logprob"], atol=1e-4)
+    close(nll.detach(), g["nll"], rtol=1e-5, atol=1e-3)
+    ((nll * g["wts"]).sum() / (0.6931471805599453 * 256 * z.shape[0])).backward()
+    for name, ref in g["grads"].items():
+        got = leaf[name].grad
+        assert got is not None, name
+        scale = float(ref.abs().max()) + 1e-12
+        assert float((got - ref).abs().max()) <= 2e-4 * scale + 1e-7, name
