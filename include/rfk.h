@@ -296,6 +296,9 @@ int rfk_fold_prepare_batched(const long long* table, int n_entries, void* stream
 int rfk_fold_backward_batched(const long long* table, int n_entries, const float* g_sum, void* stream);
 int rfk_add_channels(float* dst, int dst_C, int dst_off, const float* src, int src_C, int src_off, int n, int B, int HW,
                      void* stream);
+/* out[b,c,p] (fp32 NCHW) = ws[(b*HW + p)*ld + c] + bias[c] (bias nullable): the pixel-major accumulator of rfk_conv_gemm_splitk
+ * in the layout the cell-update / backward kernels read; zero != 0 clears ws for the next split-K launch. */
+int rfk_ws_to_nchw(float* ws, int ld, const float* bias, float* out, int B, int C, int HW, int zero, void* stream);
 
 /* Adam over all parameters in one launch (torch.optim.Adam without weight decay / amsgrad; the reference trains with
  * Adam, RFN/trainer.py).  p, g, m, v: flat fp32 buffers of n elements (n % 4 == 0, 16-byte aligned); g is multiplied by

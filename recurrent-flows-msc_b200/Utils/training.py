@@ -37,7 +37,10 @@ def _forward(cell, x, ht, ct):
         if h_prev is not None:
             ops.pack_nhwc(h_prev, 0, hc, buf, C)
         cc = torch.empty(B, 4 * hc, H, W, device=dev, dtype=torch.float32)
-        ops.conv_gemm(buf, cin_pad, wgt, 4 * hc, cell.taps, None, bias, "none", cc)
+        if ops.use_small_gemm(B, H, W, cell.taps, cin_pad):
+            ops.conv_gemm_small(buf, cin_pad, wgt, 4 * hc, cell.taps, bias, cc)
+        else:
+            ops.conv_gemm(buf, cin_pad, wgt, 4 * hc, cell.taps, None, bias, "none", cc)
         cp = c_prev if c_prev is not None else torch.zeros(B, hc, H, W, device=dev, dtype=torch.float32)
         h, c = ops.convlstm_pointwise(cc, cp, cell._peep)
         out[:, t].copy_(h)
@@ -104,7 +107,10 @@ class _ConvLSTMFn(torch.autograd.Function):
             if t == 0 and not need_dx and not ctx.has_state:
                 break       # nothing upstream of the first step needs a data gradient
             din = torch.empty(B, n_rows, H, W, device=dev, dtype=torch.float32)
-            ops.conv_gemm(da, cp, wd, n_rows, cell.taps, None, None, "none", din)
+            if ops.use_small_gemm(B, H, W, cell.taps, cp):
+                ops.conv_gemm_small(da, cp, wd, n_rows, cell.taps, None, din)
+            else:
+                ops.conv_gemm(da, cp, wd, n_rows, cell.taps, None, None, "none", din)
             if need_dx:
                 dx[:, t].copy_(din[:, :C])
             dh_future = din[:, h_lo:]

@@ -213,9 +213,33 @@ __global__ void __launch_bounds__(256) add_channels_v4_kernel(float4* __restrict
   }
 }
 
+// out[b, c, p] = ws[(b*HW + p)*ld + c] + bias[c]  (fp32; ws = the pixel-major accumulator of a split-K GEMM); optionally
+// clears ws so that the next split-K launch finds zeros.  Small tensors (a few hundred pixels): one thread per element.
+__global__ void __launch_bounds__(256) ws_to_nchw_kernel(float* __restrict__ ws, int ld, const float* __restrict__ bias,
+                                                         float* __restrict__ out, int C, int HW, long long total, int zero) {
+  pdl_trigger();
+  pdl_wait();
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const long long pix = i / C;
+    const long long b = pix / HW;
+    const int p = (int)(pix - b * HW);
+    float* src = ws + pix * ld + c;
+    out[(b * C + c) * HW + p] = *src + (bias ? bias[c] : 0.0f);
+    if (zero) *src = 0.0f;
+  }
+}
+
 }  // namespace rfk
 
 using namespace rfk;
+
+extern "C" int rfk_ws_to_nchw(float* ws, int ld, const float* bias, float* out, int B, int C, int HW, int zero, void* stream) {
+  RFK_REQUIRE(ws && out && B > 0 && C > 0 && HW > 0 && ld >= C, "rfk_ws_to_nchw: null pointer or bad shape");
+  const long long total = (long long)B * HW * C;
+  RFK_LAUNCH(ws_to_nchw_kernel, stream_grid(total, 256, 8), 256, 0, (cudaStream_t)stream, ws, ld, bias, out, C, HW, total, zero);
+  return check_launch("rfk_ws_to_nchw");
+}
 
 extern "C" int rfk_pack_weights_batched(const long long* table, int n_entries, long long max_elements, void* stream) {
   RFK_REQUIRE(table && n_entries > 0 && max_elements > 0, "rfk_pack_weights_batched: null table or no entries");

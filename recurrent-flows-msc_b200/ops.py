@@ -265,6 +265,22 @@ def conv_gemm_splitk(act, cin_pad, wgt, n, taps, k_split, ws):
          meta=_gemm_meta(B * H * W, n, taps, cin_pad, wgt))
 
 
+def conv_gemm_small(act, cin_pad, wgt, n, taps, bias, out):
+    """conv (fp32 NCHW out, + bias) for launches of one or two pixel tiles with a long K (3x3, >= 256 channels: the ConvLSTM
+    of RFN on 2x2 maps): K is cut into one slice per filter tap so that nine times as many SMs stream the weights (a single
+    CTA is limited by its own L2 bandwidth), the slices add into a zero fp32 accumulator, and a tiny kernel moves the sum
+    into NCHW and leaves the accumulator zero again."""
+    B, H, W, _ = act.shape
+    ws = workspace(("small_ws", wgt.shape[0]), (B * H * W, wgt.shape[0]), act.device, torch.float32)   # zero between uses
+    conv_gemm_splitk(act, cin_pad, wgt, n, taps, taps, ws)
+    call("rfk_ws_to_nchw", ws.data_ptr(), ws.shape[-1], _p(bias), _chk(out, name="out").data_ptr(), B, n, H * W, 1, _stream())
+    return out
+
+
+def use_small_gemm(B, H, W, taps, cin_pad):
+    return taps == 9 and B * H * W <= 256 and cin_pad >= 256 and not SPLIT
+
+
 def convlstm_pointwise_ws(cc, bias, c_prev, peep, h_out, c_next, h_nhwc, h_off, zero_cc=True):
     B, Hc, H, W = c_next.shape
     call("rfk_convlstm_pointwise_ws", _chk(cc).data_ptr(), cc.shape[-1], _p(bias), _p(c_prev),
