@@ -97,9 +97,17 @@ def main():
     if rank == 0:
         print(f"ddp_worker: world {world}: allreduced-gradient vs single-GPU max-norm rel err {err:.3e}, cosine {cos:.6f}; "
               f"replicas bit-identical after 5 steps: {same}; parameters moved {moved:.3e}; {'OK' if ok else 'FAIL'}", flush=True)
+    # the captured graph holds NCCL work: release it before the communicator goes away (destroying the process group with
+    # a live graph that contains a collective hung at exit on the 2-GPU box)
+    del step
+    import gc
+    gc.collect()
+    torch.cuda.synchronize()
     dist.barrier()
-    dist.destroy_process_group()
-    sys.exit(0 if ok else 1)
+    mark("exiting")
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0 if ok else 1)
 
 
 if __name__ == "__main__":
