@@ -1128,8 +1128,13 @@ def run_ours(args):
                                      "sample": "timed at N=1 only (see the --impl reference arm)"}
         emit(env, args, wl, res, extra)
     if world > 1:
+        # every rank is done; leave without tearing the communicator down under live CUDA graphs that contain collectives
+        # (destroy_process_group() has been seen to hang in that state)
+        torch.cuda.synchronize()
         env.dist.barrier()
-        env.dist.destroy_process_group()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():
