@@ -9,7 +9,7 @@
 All arithmetic runs in hand-written CUDA kernels reached through the C ABI in include/rfk.h
 (librfk.so, built in-tree by ``__graft_entry__.build()``).  There is no CPU or PyTorch fallback.
 """
-from . import _lib, ops  # noqa: F401
+from . import _lib, derived, ops  # noqa: F401
 from . import Flow, Utils  # noqa: F401
 from .Flow import (ActNorm, AffineCoupling, Conv2dNorm, Conv2dZeros, GlowStep, InvConv, ListGlow,  # noqa: F401
                    Split2d, Squeeze2d)
@@ -17,6 +17,7 @@ from .Utils import ActFun, ConvLSTM, ConvLSTMLayer, batch_reduce, split_feature 
 from .parallel import shard_range, shard_batch, sync_module_state  # noqa: F401
 from .graphs import Graphed, GraphedLogProb, GraphedSample, GraphedTrainStep  # noqa: F401
 from .optim import FlatAdam  # noqa: F401
+from .rfn_driver import time_batched_loss  # noqa: F401
 from .Flow.glow_modules import invalidate_caches  # noqa: F401
 
 __version__ = "0.1.0"

@@ -461,3 +461,44 @@ def test_batchnorm_options_train_against_reference_gradients(rf):
         if c < 0.98 or rel(p.grad, ref) > (0.15 if tight else 0.3):
             bad.append((name, round(c, 4), round(rel(p.grad, ref), 4)))
     assert not bad, bad
+
+
+def test_flatadam_state_dict_and_param_groups(rf):
+    """What Solver.checkpoint / Solver.load and the LR schedules need from the optimizer (RFN/trainer.py:100,200,281,304):
+    state_dict round trip resumes bit-identically; param_groups[0]['lr'] is what the next step uses."""
+    B = 4
+    a = types.SimpleNamespace(**dict(ARGS, L=2, K=1))
+    torch.manual_seed(0)
+    m = rf.ListGlow([B, 1, 16, 16], [[B, 4, 8, 8], [B, 4, 4, 4]], [B, 4, 4, 4], a).cuda().train()
+    perturb(m, 1)
+    g = torch.Generator().manual_seed(3)
+    x = (torch.floor(torch.rand(B, 1, 16, 16, generator=g) * 256) / 256 - 0.5).cuda()
+    conds = [torch.randn(B, 4, 8, 8, generator=g).cuda(), torch.randn(B, 4, 4, 4, generator=g).cuda()]
+    base = torch.randn(B, 4, 4, 4, generator=g).cuda()
+    noise = (torch.rand(B, 1, 16, 16, generator=g) / 256).cuda()
+    opt = rf.FlatAdam(m.parameters(), lr=1e-3)
+
+    def step():
+        opt.zero_grad()
+        _, nll = m.log_prob(x, conds, base, noise=noise)
+        (nll.mean() / (math.log(2) * 256)).backward()
+        opt.step()
+
+    step(); step()
+    sd = opt.state_dict()
+    p_saved = opt.flat_p.clone()
+    step()
+    p_next = opt.flat_p.clone()
+    with torch.no_grad():
+        opt.flat_p.copy_(p_saved)
+    rf.invalidate_caches()
+    rf.derived.REFRESHER.refresh_all(opt.flat_p.device, rf.ops._stream())
+    opt.load_state_dict(sd)
+    step()
+    assert torch.equal(opt.flat_p, p_next)
+    for group in opt.param_groups:          # the trainer's linear LR decay writes here
+        group["lr"] = 0.0
+    before = opt.flat_p.clone()
+    step()
+    assert torch.equal(opt.flat_p, before)
+    assert all(p.grad is not None and p.grad.data_ptr() == v.data_ptr() for p, v in zip(opt.params, opt.grad_views))

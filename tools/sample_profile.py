@@ -8,10 +8,11 @@ import recurrent_flows_msc_b200 as rf
 
 B = 30
 torch.manual_seed(0)
-flow = rf.ListGlow([B, 1, 64, 64], bench.cond_sizes(B), [B, 256, 2, 2], bench.glow_args()).eval()
+flow = rf.ListGlow([B, 1, 64, 64], bench.cond_sizes(bench.J, B), [B, 256, 2, 2], bench.glow_args(bench.J)).eval()
 bench.trained_like(flow, 0)
 flow = flow.cuda()
-_, conds, base, _ = bench.synth_inputs(B, 1, 1)
+_, conds, _, _ = bench.synth_inputs(bench.J, B, 1, 1)
+base = torch.randn(B, bench.J["base_ch"], 2, 2)
 conds = [c.cuda() for c in conds]
 base = base.cuda()
 with torch.no_grad():

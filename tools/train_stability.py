@@ -7,10 +7,11 @@ import recurrent_flows_msc_b200 as rf
 n, steps = 570, int(sys.argv[1]) if len(sys.argv) > 1 else 60
 dev = torch.device("cuda", 0)
 torch.manual_seed(0)
-flow = rf.ListGlow([n, 1, 64, 64], bench.cond_sizes(n), [n, bench.J["base_ch"], 2, 2], bench.glow_args()).train()
+flow = rf.ListGlow([n, 1, 64, 64], bench.cond_sizes(bench.J, n), [n, bench.J["base_ch"], 2, 2], bench.glow_args(bench.J)).train()
 bench.trained_like(flow, 0)
 flow = flow.to(dev)
-x, conds, base, _ = bench.synth_inputs(n, 1, 1)
+x, conds, _, _ = bench.synth_inputs(bench.J, n, 1, 1)
+base = torch.randn(n, bench.J["base_ch"], 2, 2)
 x, base, conds = x.to(dev), base.to(dev), [c.to(dev) for c in conds]
 opt = rf.FlatAdam(flow.parameters(), lr=1e-4)
 def loss_fn():
