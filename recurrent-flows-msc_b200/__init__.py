@@ -18,6 +18,7 @@ from .parallel import shard_range, shard_batch, sync_module_state  # noqa: F401
 from .graphs import Graphed, GraphedLogProb, GraphedSample, GraphedTrainStep  # noqa: F401
 from .optim import FlatAdam  # noqa: F401
 from .rfn_driver import time_batched_loss  # noqa: F401
+from .scalers import accelerate_scalers  # noqa: F401
 from .Flow.glow_modules import invalidate_caches  # noqa: F401
 
 __version__ = "0.1.0"
