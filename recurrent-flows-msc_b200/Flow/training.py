@@ -324,7 +324,12 @@ def _glowstep_bwd(st, flow, step, x, zo, nn_in, h1, h2, taps, cc, l, xn=None, bn
     else:
         outs = (st.out(last.logs), st.out(last.conv.bias)) + tuple(ops._zeros(half, dev) for _ in range(2))
     dsum = ops.coupling_taps_bwd(taps, zo, dz, scale, shift, clamp, cs, csh, st.g_ld, float(last.logscale_factor), outs)[0]
-    dS = _nhwc(B, H, W, C, dev)
+    if not WGRAD_SIDE_STREAM or B * H * W > WGRAD_SIDE_MAX_PIXELS:
+        # everything that reads dS is stream-ordered before the next step's pack: one persistent buffer per shape whose pad
+        # columns stay zero (a fresh zero-filled buffer per step was a 37 MB memset at level 1)
+        dS = ops.workspace(("bwd_dS", C), (B, H, W, ops.cin_pad(C)), dev)
+    else:
+        dS = _nhwc(B, H, W, C, dev)      # small level: the side-stream weight gradient may still be reading the previous one
     ops.pack_nhwc(dsum, 0, C, dS, 0)
     dh2 = _nhwc(B, H, W, hid, dev)
     _conv_bwd(st, last, h2, hid, dS, dgrad_out=dh2)

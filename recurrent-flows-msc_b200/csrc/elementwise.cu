@@ -1391,7 +1391,7 @@ namespace rfk {
 __global__ void __launch_bounds__(256) pack_weight_kernel(const float* __restrict__ src, int N, int Cin, int taps, int mode,
                                                           const int* __restrict__ perm, int rows, int kp,
                                                           __nv_bfloat16* __restrict__ dst, int rows_pad, int ktot) {
-  pdl_trigger();
+  // no pdl_trigger(): the next conv kernel prefetches these weights BEFORE its dependency wait
   pdl_wait();
   const long long total = (long long)rows_pad * ktot;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {

@@ -25,7 +25,7 @@ __device__ __forceinline__ T* eptr(const long long* e, int i) { return reinterpr
 // ---- weights -------------------------------------------------------------------------------------------------------
 // entry: 0 src f32, 1 dst bf16, 2 perm i32 (0 = none), 3 N, 4 Cin, 5 taps, 6 mode, 7 rows, 8 kp, 9 rows_pad, 10 ktot
 __global__ void __launch_bounds__(256) pack_weights_batched_kernel(const long long* __restrict__ table) {
-  pdl_trigger();
+  // no pdl_trigger(): conv kernels prefetch weights BEFORE their dependency wait, so dependents must not start early
   pdl_wait();
   const long long* e = table + (size_t)blockIdx.y * kEntryWords;
   const float* __restrict__ src = eptr<const float>(e, 0);
@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(256) pack_weights_batched_kernel(const long lo
 // ---- per-channel affines ---------------------------------------------------------------------------------------------
 // entry: 0 logs, 1 bias (nullable), 2 out scale, 3 out shift, 4 n, 5 factor (integer multiplier of logs)
 __global__ void __launch_bounds__(128) affine_prepare_batched_kernel(const long long* __restrict__ table) {
-  pdl_trigger();
+  // no pdl_trigger(): conv kernels prefetch weights BEFORE their dependency wait, so dependents must not start early
   pdl_wait();
   const long long* e = table + (size_t)blockIdx.x * kEntryWords;
   const float* logs = eptr<const float>(e, 0);
@@ -87,7 +87,7 @@ __device__ __forceinline__ float lu_upper(const float* upper, const float* log_s
 }
 
 __global__ void __launch_bounds__(256) fold_prepare_batched_kernel(const long long* __restrict__ table) {
-  pdl_trigger();
+  // no pdl_trigger(): conv kernels prefetch weights BEFORE their dependency wait, so dependents must not start early
   pdl_wait();
   const long long* e = table + (size_t)blockIdx.x * kEntryWords;
   const float* bias = eptr<const float>(e, 0);

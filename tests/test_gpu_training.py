@@ -469,8 +469,9 @@ def test_flatadam_state_dict_and_param_groups(rf):
     B = 4
     a = types.SimpleNamespace(**dict(ARGS, L=2, K=1))
     torch.manual_seed(0)
-    m = rf.ListGlow([B, 1, 16, 16], [[B, 4, 8, 8], [B, 4, 4, 4]], [B, 4, 4, 4], a).cuda().train()
+    m = rf.ListGlow([B, 1, 16, 16], [[B, 4, 8, 8], [B, 4, 4, 4]], [B, 4, 4, 4], a)
     perturb(m, 1)
+    m = m.cuda().train()
     g = torch.Generator().manual_seed(3)
     x = (torch.floor(torch.rand(B, 1, 16, 16, generator=g) * 256) / 256 - 0.5).cuda()
     conds = [torch.randn(B, 4, 8, 8, generator=g).cuda(), torch.randn(B, 4, 4, 4, generator=g).cuda()]
