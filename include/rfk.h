@@ -296,6 +296,17 @@ int rfk_fold_prepare_batched(const long long* table, int n_entries, void* stream
 int rfk_fold_backward_batched(const long long* table, int n_entries, const float* g_sum, void* stream);
 int rfk_add_channels(float* dst, int dst_C, int dst_off, const float* src, int src_C, int src_off, int n, int B, int HW,
                      void* stream);
+/* Data gradient of a convolution FUSED with the backward of the h = act(ActNorm(.)) that produced its input (the coupling
+ * network's hidden layers, Flow/glow_modules.py:229-238): out (bf16 NHWC, TMA stores) = (act (*) wgt)[p,c] * act'(h[p,c]) *
+ * scale[c] with h the saved activation (its sign decides act'), and colsum[c] += sum_p out[p,c] (atomics).  Replaces a
+ * rfk_conv_gemm + rfk_act_affine_bwd pair: the dh tensor never exists in HBM.  n must be a multiple of 64 without padding.
+ * rfk_actnorm_param_bwd then gives the ActNorm gradients of that layer from the layer's own weight gradient:
+ *   d bias[c] += colsum[c];  d logs[c] += sum_k W[c,k] dW[c,k] + bias[c] colsum[c];  grad_W += dW   (K = Cin*taps). */
+int rfk_conv_gemm_actbwd(const void* act, int B, int H, int W, int act_ld, int cin_pad, const void* wgt, int n, int n_pad,
+                         int taps, const float* scale, int act_fn, const void* h, int h_ld, void* out, int out_ld,
+                         float* colsum, void* stream);
+int rfk_actnorm_param_bwd(const float* W, const float* dW, long long K, const float* colsum, const float* bias,
+                          float* grad_W, float* d_logs, float* d_bias, int n, void* stream);
 /* out[b,c,p] (fp32 NCHW) = ws[(b*HW + p)*ld + c] + bias[c] (bias nullable): the pixel-major accumulator of rfk_conv_gemm_splitk
  * in the layout the cell-update / backward kernels read; zero != 0 clears ws for the next split-K launch. */
 int rfk_ws_to_nchw(float* ws, int ld, const float* bias, float* out, int B, int C, int HW, int zero, void* stream);

@@ -34,6 +34,10 @@ DGRAD_TAP_SPLIT_MIN_PIXELS = 32768  # ... and the launch has enough pixels to be
 # chain; in a captured training step this becomes a parallel branch of the CUDA graph.  RFK_WGRAD_SIDE_STREAM=0 disables.
 WGRAD_SIDE_MAX_PIXELS = int(os.environ.get("RFK_WGRAD_SIDE_MAX_PIXELS", "32768"))
 WGRAD_SIDE_STREAM = os.environ.get("RFK_WGRAD_SIDE_STREAM", "1") != "0"
+# Hidden layers of the coupling network: fold the ActNorm + activation backward into the epilogue of the data-gradient GEMM
+# that produces its input (rfk_conv_gemm_actbwd) and take the ActNorm parameter gradients from the layer's own weight
+# gradient (rfk_actnorm_param_bwd) instead of a separate 6 B/element pass over the activations.  RFK_FUSE_ACT_BWD=0 disables.
+FUSE_ACT_BWD = os.environ.get("RFK_FUSE_ACT_BWD", "1") != "0"
 
 
 _SIDE = {}
@@ -62,11 +66,14 @@ class _State:
         self.side = None          # second stream for small weight-gradient launches
         self.side_keep = []       # tensors the side stream still reads (kept alive until the join)
 
-    def wgrad(self, x_act, cin, da, n, taps, out, perm):
-        """Weight gradient launch; small ones go to the side stream."""
+    def wgrad(self, x_act, cin, da, n, taps, out, perm, after=None):
+        """Weight gradient launch; small ones go to the side stream.  ``after``: work that consumes the weight gradient,
+        enqueued right behind it on the same stream."""
         B, H, W, _ = da.shape
         if not WGRAD_SIDE_STREAM or B * H * W > WGRAD_SIDE_MAX_PIXELS:
             ops.conv_wgrad(x_act, cin, da, n, taps, out=out, perm=perm)
+            if after is not None:
+                after()
             return
         main = torch.cuda.current_stream()
         if self.side is None:
@@ -76,6 +83,8 @@ class _State:
         self.side.wait_event(ev)
         with torch.cuda.stream(self.side):
             ops.conv_wgrad(x_act, cin, da, n, taps, out=out, perm=perm, ws_slot=1)
+            if after is not None:
+                after()
         self.side_keep.append((x_act, da, out))
 
     def join(self):
@@ -172,13 +181,40 @@ def _batchnorm_act_bwd(st, mod, dh, h, act_fn, keep):
     return da
 
 
-def _conv_bwd(st, mod, x_act, cin, da, perm=None, dgrad_out=None, key="id"):
+def _dgrad_actbwd(st, conv_mod, da_in, prev_mod, h, act_fn):
+    """Data gradient of conv_mod fused with the backward of h = act(ActNorm(prev_mod.conv(...))), the tensor conv_mod read:
+    returns (da, colsum) = gradient w.r.t. prev_mod's raw conv output (bf16 NHWC) and its per-channel sums."""
+    B, H, W, _ = da_in.shape
+    n = prev_mod.conv.out_channels
+    wd, cp = conv_mod.packed_dgrad("id", None)
+    scale, _ = prev_mod.norm_type.affine()
+    da = torch.empty(B, H, W, n, device=da_in.device, dtype=torch.bfloat16)
+    colsum = ops._zeros(n, da_in.device)
+    ops.conv_gemm_actbwd(da_in, cp, wd, n, conv_mod.taps, scale, act_fn, h, da, colsum)
+    return da, colsum
+
+
+def _wgrad_actnorm(st, mod, x_act, cin, da, colsum, perm=None):
+    """Weight gradient of a Conv2dNorm(ActNorm) layer into a zeroed scratch, then its ActNorm gradients from that scratch
+    and the column sums of da (rfk_actnorm_param_bwd also adds the scratch into the weight's gradient buffer)."""
+    w = mod.conv.weight
+    n = mod.conv.out_channels
+    k = 3 if mod.taps == 9 else 1
+    dWp = ops._zeros(w.numel(), da.device)
+    g_w, g_logs, g_bias = st.out(w), st.out(mod.norm_type.logs), st.out(mod.norm_type.bias)
+    bias = mod.norm_type.bias.detach().reshape(-1)
+    st.wgrad(x_act, cin, da, n, mod.taps, dWp.view(n, w.shape[1], k, k), perm,
+             after=lambda: ops.actnorm_param_bwd(w.detach(), dWp, colsum, bias, g_w, g_logs, g_bias))
+
+
+def _conv_bwd(st, mod, x_act, cin, da, perm=None, dgrad_out=None, key="id", skip_wgrad=False):
     """Backward of mod.conv given da (bf16 NHWC gradient of the raw convolution output): weight gradient into the
     state, data gradient into dgrad_out (bf16 NHWC or fp32 NCHW; channels in the staging order of x_act)."""
     n = mod.conv.out_channels
     k = 3 if mod.taps == 9 else 1
-    st.wgrad(x_act, cin, da, n, mod.taps, st.out(mod.conv.weight).view(n, mod.conv.weight.shape[1], k, k),
-             perm)   # staging order -> weight order
+    if not skip_wgrad:
+        st.wgrad(x_act, cin, da, n, mod.taps, st.out(mod.conv.weight).view(n, mod.conv.weight.shape[1], k, k),
+                 perm)   # staging order -> weight order
     if dgrad_out is not None:
         B, H, W, _ = da.shape
         if (mod.taps == 9 and dgrad_out.dtype == torch.float32 and 9 * cin <= DGRAD_TAP_SPLIT_MAX_N
@@ -331,15 +367,26 @@ def _glowstep_bwd(st, flow, step, x, zo, nn_in, h1, h2, taps, cc, l, xn=None, bn
     else:
         dS = _nhwc(B, H, W, C, dev)      # small level: the side-stream weight gradient may still be reading the previous one
     ops.pack_nhwc(dsum, 0, C, dS, 0)
-    dh2 = _nhwc(B, H, W, hid, dev)
-    _conv_bwd(st, last, h2, hid, dS, dgrad_out=dh2)
-    da2 = _norm_act_bwd(st, net[2], dh2, h2, act)
-    dh1 = _nhwc(B, H, W, hid, dev)
-    _conv_bwd(st, net[2], h1, hid, da2, dgrad_out=dh1)
-    da1 = _norm_act_bwd(st, net[0], dh1, h1, act)
     cin = half + cc
     dnn = torch.empty(B, cin, H, W, device=dev, dtype=torch.float32)
-    _conv_bwd(st, net[0], nn_in, cin, da1, perm=aff._perm(dev), dgrad_out=dnn, key="cz")
+    if (FUSE_ACT_BWD and hid % 64 == 0 and hid <= 512 and net[0].norm == "actnorm" and net[2].norm == "actnorm"
+            and ops.cin_pad(hid) == hid):
+        # dh2 / dh1 never exist in HBM: each data-gradient GEMM applies act' and the ActNorm scale of the layer below in its
+        # epilogue; the ActNorm parameter gradients come from the layers' own weight gradients
+        _conv_bwd(st, last, h2, hid, dS)                                   # weight gradient of the last conv
+        da2, r2 = _dgrad_actbwd(st, last, dS, net[2], h2, act)
+        _wgrad_actnorm(st, net[2], h1, hid, da2, r2)
+        da1, r1 = _dgrad_actbwd(st, net[2], da2, net[0], h1, act)
+        _wgrad_actnorm(st, net[0], nn_in, cin, da1, r1, perm=aff._perm(dev))
+        _conv_bwd(st, net[0], nn_in, cin, da1, perm=aff._perm(dev), dgrad_out=dnn, key="cz", skip_wgrad=True)
+    else:
+        dh2 = _nhwc(B, H, W, hid, dev)
+        _conv_bwd(st, last, h2, hid, dS, dgrad_out=dh2)
+        da2 = _norm_act_bwd(st, net[2], dh2, h2, act)
+        dh1 = _nhwc(B, H, W, hid, dev)
+        _conv_bwd(st, net[2], h1, hid, da2, dgrad_out=dh1)
+        da1 = _norm_act_bwd(st, net[0], dh1, h1, act)
+        _conv_bwd(st, net[0], nn_in, cin, da1, perm=aff._perm(dev), dgrad_out=dnn, key="cz")
     ops.add_channels(dz, 0, dnn, cc, half)          # dz[:, :half] += d z1 (the network's input after the condition)
     if cc:
         st.add_cond(l, dnn, cc)

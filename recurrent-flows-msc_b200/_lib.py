@@ -72,6 +72,9 @@ SIGNATURES = {
     "rfk_affine_prepare_batched": [c_void_p, c_int, c_void_p],
     "rfk_fold_prepare_batched": [c_void_p, c_int, c_void_p],
     "rfk_fold_backward_batched": [c_void_p, c_int, c_void_p, c_void_p],
+    "rfk_conv_gemm_actbwd": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_int,
+                             c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p],
+    "rfk_actnorm_param_bwd": [c_void_p, c_void_p, c_longlong, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p],
     "rfk_ws_to_nchw": [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "rfk_add_channels": [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "rfk_debug_set_timeline": [c_void_p, c_longlong],

@@ -23,6 +23,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <type_traits>
 
 #include "common.cuh"
 #include "tc_ptx.cuh"
@@ -72,6 +73,16 @@ struct PlainEpi {
   int vec_ok;
   int tma_store;
   int lo_off;            // split-precision mode: the bf16 residual v - bf16(v) goes to channel + lo_off (0 = off)
+};
+
+// Data gradient of a conv whose INPUT was h = act(ActNorm(previous conv)): the epilogue turns the accumulator dh into
+// da = dh * act'(h) * scale (bf16 NHWC through the TMA-store path) and accumulates the per-channel column sums of da.
+// Replaces the separate rfk_act_affine_bwd pass (6 B/element) -- see rfk_conv_gemm_actbwd in rfk.h.
+struct ActBwdEpi {
+  const __nv_bfloat16* h;   // NHWC bf16 [pixels, h_ld]: the activation the previous layer produced (its sign = act')
+  int h_ld;
+  int act_fn;
+  float* colsum;            // [n] fp32, accumulated with atomics: sum over pixels of da
 };
 
 struct CouplingEpi {
@@ -276,6 +287,119 @@ __device__ __forceinline__ void epilogue(const GemmArgs& g, const PlainEpi<ACT>&
   }
   release_accumulator(t);
 }
+
+// Butterfly reduce-scatter over the 32 lanes of a warp: every lane holds 32 values (one row of a 32-row x 32-column block);
+// afterwards lane l holds the sum over all 32 rows of column colsum_col(l).  31 shuffles instead of 32 x 5.
+__device__ __forceinline__ int colsum_col(int lane) {
+  return ((lane >> 4) & 1) * 16 + ((lane >> 3) & 1) * 8 + ((lane >> 2) & 1) * 4 + ((lane >> 1) & 1) * 2 + (lane & 1);
+}
+__device__ __forceinline__ float warp_colsum32(float (&d)[32], int lane) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const bool up = lane & 16;
+    const float send = up ? d[i] : d[i + 16];
+    const float keep = up ? d[i + 16] : d[i];
+    d[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const bool up = lane & 8;
+    const float send = up ? d[i] : d[i + 8];
+    const float keep = up ? d[i + 8] : d[i];
+    d[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const bool up = lane & 4;
+    const float send = up ? d[i] : d[i + 4];
+    const float keep = up ? d[i + 4] : d[i];
+    d[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const bool up = lane & 2;
+    const float send = up ? d[i] : d[i + 2];
+    const float keep = up ? d[i + 2] : d[i];
+    d[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  {
+    const bool up = lane & 1;
+    const float send = up ? d[0] : d[1];
+    const float keep = up ? d[1] : d[0];
+    d[0] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+  }
+  return d[0];
+}
+
+// csum: this thread's running column sums, index = (block / 2) * 2 + pass (a warp owns every second 64-column block)
+__device__ __forceinline__ void epilogue_actbwd(const GemmArgs& g, const ActBwdEpi& e, const CUtensorMap* tmO, uint32_t taddr,
+                                                const float* ss, const TileCtx& t, float (&csum)[4]) {
+  const int lane = threadIdx.x & 31;
+  const int nblk = g.BN >> 6;                 // whole 64-column blocks (the host guarantees BN % 64 == 0)
+  const int r = t.q * 32 + lane;
+  const bool issuer = lane == 0;
+  const int r0 = t.q * 32;
+  const int sub_x = t.x0 + (r0 & ((1 << g.tw_log2) - 1));
+  const int sub_y = t.y0 + ((r0 >> g.tw_log2) & ((1 << g.th_log2) - 1));
+  const int sub_n = t.n0 + (r0 >> (g.tw_log2 + g.th_log2));
+  const int last_blk = ((nblk - 1 - t.half) & ~1) + t.half;
+  const long long pix = ((long long)t.b * g.H + t.y) * g.W + t.x;
+  bool released = false;
+  int bi = 0;
+  for (int blk = t.half; blk < nblk; blk += 2, ++bi) {
+    uint32_t pk[32];
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+      const int c0 = blk * 64 + pass * 32;
+      uint32_t v[32];
+      tmem_ld16_nowait(taddr + c0, v);
+      tmem_ld16_nowait(taddr + c0 + 16, v + 16);
+      uint4 hv[4];
+      if (t.valid) {
+        const uint4* hp = reinterpret_cast<const uint4*>(e.h + pix * e.h_ld + t.n_tile * g.BN + c0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) hv[k] = __ldg(hp + k);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) hv[k] = make_uint4(0u, 0u, 0u, 0u);
+      }
+      tmem_wait_ld();
+      float d[32];
+      const __nv_bfloat16* hb = reinterpret_cast<const __nv_bfloat16*>(hv);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float hval = __bfloat162float(hb[j]);
+        float m = 1.0f;
+        if (e.act_fn == RFK_ACT_RELU) m = hval > 0.0f ? 1.0f : 0.0f;
+        else if (e.act_fn == RFK_ACT_LEAKY) m = hval > 0.0f ? 1.0f : 0.2f;
+        d[j] = t.valid ? __uint_as_float(v[j]) * m * ss[c0 + j] : 0.0f;
+      }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) pk[pass * 16 + j] = pack_bf16(d[2 * j], d[2 * j + 1]);
+      if (blk == last_blk && pass == 1) { release_accumulator(t); released = true; }
+      csum[(bi & 1) * 2 + pass] += warp_colsum32(d, lane);
+    }
+    if (issuer) bulk_wait_read0();
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint32_t dst = t.stg + r * 128 + ((j ^ (r & 7)) << 4);
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk[4 * j]), "r"(pk[4 * j + 1]),
+                   "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3])
+                   : "memory");
+    }
+    fence_async_smem();
+    __syncwarp();
+    if (issuer) {
+      tma_store_4d(tmO, t.stg + r0 * 128, t.n_tile * g.BN + blk * 64, sub_x, sub_y, sub_n);
+      bulk_commit();
+    }
+  }
+  if (!released) release_accumulator(t);
+}
+
+__device__ __forceinline__ void epilogue(const GemmArgs& g, const ActBwdEpi& e, const CUtensorMap* tmO, uint32_t taddr,
+                                         const float* ss, const TileCtx& t) {}   // (dispatched through epilogue_actbwd)
 
 __device__ __forceinline__ void epilogue(const GemmArgs& g, const CouplingEpi& e, const CUtensorMap*, uint32_t taddr,
                                          const float* ss, const TileCtx& t) {
@@ -759,6 +883,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     long long phase_cnt[5] = {0, 0, 0, 0, 0};
     t.dbg = g.timeline ? phase_cnt : nullptr;
     t.remote_release = kPair && rank != 0;
+    float csum[4] = {0.0f, 0.0f, 0.0f, 0.0f};   // ActBwdEpi: running column sums of this thread's (block, pass) columns
     for (int it = it0; it < it_end; it += it_step, ++tl) {
       const int mt = tile_of(it);
       const uint32_t buf = tl & 1u;
@@ -772,8 +897,24 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       { CNT_BEGIN(); mbar_wait(tmem_full_bar(buf), (tl >> 1) & 1u); CNT_END(c_wait_tfull); }
       if (tl == 0 && warp == kEpiWarp0 && lane == 0) RFK_STAMP(5);  // first accumulator ready
       tc_fence_after();
-      { CNT_BEGIN(); epilogue(g, ep, &tmO, tmem_base + ((uint32_t)(t.q * 32) << 16) + buf * g.BN, ss, t); CNT_END(c_epi); }
+      if constexpr (std::is_same<Epi, ActBwdEpi>::value) {
+        epilogue_actbwd(g, ep, &tmO, tmem_base + ((uint32_t)(t.q * 32) << 16) + buf * g.BN, ss, t, csum);
+      } else {
+        CNT_BEGIN(); epilogue(g, ep, &tmO, tmem_base + ((uint32_t)(t.q * 32) << 16) + buf * g.BN, ss, t); CNT_END(c_epi);
+      }
       if (tl == 0 && warp == kEpiWarp0 && lane == 0) RFK_STAMP(6);  // first epilogue done
+    }
+    if constexpr (std::is_same<Epi, ActBwdEpi>::value) {
+      // flush the column sums: lane l of a warp holds, for its k-th 64-column block and pass p, column colsum_col(l)
+      const int nblk = g.BN >> 6;
+      int bi = 0;
+      for (int blk = t.half; blk < nblk; blk += 2, ++bi) {
+#pragma unroll
+        for (int pass = 0; pass < 2; ++pass) {
+          const int col = n_tile * g.BN + blk * 64 + pass * 32 + colsum_col(lane);
+          if (col < g.n) atomicAdd(ep.colsum + col, csum[(bi & 1) * 2 + pass]);
+        }
+      }
     }
     if (g.use_stg && lane == 0) bulk_wait0();  // this warp's outstanding TMA stores still read shared memory
     if (warp == kEpiWarp0 && lane == 0) { RFK_STAMP(7); RFK_PUT(11, c_wait_tfull); RFK_PUT(12, c_epi);
@@ -999,6 +1140,7 @@ static int make_plan(Plan& p, const char* who, const void* act, int B, int H, in
 
 template <class T> struct PairCapable { static constexpr bool value = false; };
 template <int ACT> struct PairCapable<PlainEpi<ACT>> { static constexpr bool value = true; };
+template <> struct PairCapable<ActBwdEpi> { static constexpr bool value = true; };
 
 template <class Epi, bool kPair>
 static int launch_impl(const Plan& p, const Epi& ep, cudaStream_t st, const char* who) {
@@ -1135,6 +1277,30 @@ extern "C" int rfk_conv_gemm(const void* act, int B, int H, int W, int act_ld, i
     return launch(p, e2, (cudaStream_t)stream, "rfk_conv_gemm");
   }
   return launch(p, e, (cudaStream_t)stream, "rfk_conv_gemm");
+}
+
+extern "C" int rfk_conv_gemm_actbwd(const void* act, int B, int H, int W, int act_ld, int cin_pad, const void* wgt, int n,
+                                    int n_pad, int taps, const float* scale, int act_fn, const void* h, int h_ld, void* out,
+                                    int out_ld, float* colsum, void* stream) {
+  RFK_REQUIRE(out && h && scale && colsum, "rfk_conv_gemm_actbwd: null pointer");
+  RFK_REQUIRE(act_fn >= 0 && act_fn <= 2, "rfk_conv_gemm_actbwd: bad act_fn %d", act_fn);
+  RFK_REQUIRE(!g_conv_split, "rfk_conv_gemm_actbwd: training kernels do not run in split-precision mode");
+  RFK_REQUIRE(n == n_pad && n % 64 == 0 && n <= 512, "rfk_conv_gemm_actbwd: n=%d must be a multiple of 64 (<= 512) without padding", n);
+  RFK_REQUIRE(out_ld % 8 == 0 && n <= out_ld && h_ld % 8 == 0 && n <= h_ld &&
+              ((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(h)) & 15) == 0,
+              "rfk_conv_gemm_actbwd: out / h must be 16-byte aligned NHWC bf16 with row strides that are multiples of 8");
+  const int BN = n <= 256 ? n : pick_bn(n_pad, 64, m_tiles_of(B, H, W));
+  RFK_REQUIRE(BN > 0 && BN % 64 == 0 && BN <= 256, "rfk_conv_gemm_actbwd: no N tile for n=%d", n);
+  Plan p;
+  int rc = make_plan(p, "rfk_conv_gemm_actbwd", act, B, H, W, act_ld, cin_pad, wgt, n, n_pad, taps, BN, true, 1, true);
+  if (rc) return rc;
+  p.g.scale = scale; p.g.shift = nullptr; p.g.n_ss = n;
+  const int sx = std::min(p.TW, 32), sy = std::min(p.TH, 32 / sx), sn = 32 / (sx * sy);
+  rc = encode_act_map(&p.tmO, "rfk_conv_gemm_actbwd", "out", out, n, out_ld, B, H, W, sx, sy, sn);
+  if (rc) return rc;
+  ActBwdEpi e;
+  e.h = (const __nv_bfloat16*)h; e.h_ld = h_ld; e.act_fn = act_fn; e.colsum = colsum;
+  return launch(p, e, (cudaStream_t)stream, "rfk_conv_gemm_actbwd");
 }
 
 extern "C" int rfk_conv_gemm_coupling(const void* act, int B, int H, int W, int act_ld, int cin_pad, const void* wgt,

@@ -230,9 +230,52 @@ __global__ void __launch_bounds__(256) ws_to_nchw_kernel(float* __restrict__ ws,
   }
 }
 
+// ActNorm parameter gradients of a Conv2dNorm layer WITHOUT a pass over the activations.  With v = (a + b) e^{logs} the
+// pre-activation, a = conv(x, W) and da = dv e^{logs} the gradient w.r.t. the conv output:
+//   d b[c]    = sum_p da[p,c]                                                   (= the column sums the fused data-gradient
+//                                                                                  epilogue of the NEXT layer accumulated)
+//   d logs[c] = sum_p dv v = sum_p da (a + b) = sum_k W[c,k] dW[c,k] + b[c] d b[c]   because dW[c,k] = sum_p da[p,c] x[p,k]
+// One CTA per output channel c; K = Cin * taps.  dW is this backward's own weight gradient (a zeroed scratch the
+// weight-gradient kernel just filled); it is also accumulated into the parameter's gradient buffer here.
+__global__ void __launch_bounds__(256) actnorm_param_bwd_kernel(const float* __restrict__ W, const float* __restrict__ dW, long long K,
+                                                                const float* __restrict__ colsum, const float* __restrict__ bias,
+                                                                float* __restrict__ grad_W, float* __restrict__ d_logs,
+                                                                float* __restrict__ d_bias) {
+  pdl_trigger();
+  pdl_wait();
+  const int c = blockIdx.x;
+  const float* w = W + (long long)c * K;
+  const float* g = dW + (long long)c * K;
+  float* gw = grad_W + (long long)c * K;
+  float acc = 0.0f;
+  for (long long k = threadIdx.x; k < K; k += blockDim.x) {
+    const float gv = g[k];
+    acc += w[k] * gv;
+    gw[k] += gv;
+  }
+  __shared__ float part[8];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.0f;
+    for (int i = 0; i < 8; ++i) s += part[i];
+    const float db = colsum[c];
+    d_bias[c] += db;
+    d_logs[c] += s + bias[c] * db;
+  }
+}
+
 }  // namespace rfk
 
 using namespace rfk;
+
+extern "C" int rfk_actnorm_param_bwd(const float* W, const float* dW, long long K, const float* colsum, const float* bias,
+                                     float* grad_W, float* d_logs, float* d_bias, int n, void* stream) {
+  RFK_REQUIRE(W && dW && colsum && bias && grad_W && d_logs && d_bias && n > 0 && K > 0, "rfk_actnorm_param_bwd: null pointer or empty shape");
+  RFK_LAUNCH(actnorm_param_bwd_kernel, n, 256, 0, (cudaStream_t)stream, W, dW, K, colsum, bias, grad_W, d_logs, d_bias);
+  return check_launch("rfk_actnorm_param_bwd");
+}
 
 extern "C" int rfk_ws_to_nchw(float* ws, int ld, const float* bias, float* out, int B, int C, int HW, int zero, void* stream) {
   RFK_REQUIRE(ws && out && B > 0 && C > 0 && HW > 0 && ld >= C, "rfk_ws_to_nchw: null pointer or bad shape");

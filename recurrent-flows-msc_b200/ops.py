@@ -429,6 +429,28 @@ def act_affine_bwd(dh, h, n, scale, act_fn, dvv_factor=1.0, dv_scaled=False, out
     return da, out_dv, out_dvv
 
 
+def conv_gemm_actbwd(act, cin_pad, wgt, n, taps, scale, act_fn, h, out, colsum):
+    """out (bf16 NHWC) = conv(act, wgt) * act'(h) * scale: a data gradient fused with the backward of the activation +
+    ActNorm that produced the conv's input h; colsum [n] += column sums of out (include/rfk.h, rfk_conv_gemm_actbwd)."""
+    _chk(act, torch.bfloat16, "act")
+    _chk(h, torch.bfloat16, "h")
+    _chk(out, torch.bfloat16, "out")
+    B, H, W, ld = act.shape
+    meta = _gemm_meta(B * H * W, n, taps, cin_pad, wgt)
+    meta["bytes"] += 2.0 * B * H * W * n      # + the saved activation read by the epilogue
+    call("rfk_conv_gemm_actbwd", act.data_ptr(), B, H, W, ld, cin_pad, _chk(wgt, torch.bfloat16).data_ptr(), n, wgt.shape[0],
+         taps, _chk(scale).data_ptr(), ACT[act_fn], h.data_ptr(), h.shape[-1], out.data_ptr(), out.shape[-1],
+         _chk(colsum).data_ptr(), _stream(), meta=meta)
+    return out
+
+
+def actnorm_param_bwd(weight, dW, colsum, bias, grad_W, d_logs, d_bias):
+    """ActNorm gradients of a Conv2dNorm from its own weight gradient dW and the column sums of da; grad_W += dW."""
+    n = weight.shape[0]
+    call("rfk_actnorm_param_bwd", _chk(weight).data_ptr(), _chk(dW).data_ptr(), weight[0].numel(), _chk(colsum).data_ptr(),
+         _chk(bias).data_ptr(), _chk(grad_W).data_ptr(), _chk(d_logs).data_ptr(), _chk(d_bias).data_ptr(), n, _stream())
+
+
 def convlstm_pointwise_bwd(cc, c_prev, peep, dh, dc_in, dbias):
     """Backward of the ConvLSTM cell update: returns (dcc [B,4Hc,H,W], dc_prev [B,Hc,H,W]); dbias [4Hc] accumulates."""
     _chk(cc, name="cc")
