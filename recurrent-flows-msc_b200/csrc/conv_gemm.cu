@@ -331,6 +331,30 @@ __device__ __forceinline__ float warp_colsum32(float (&d)[32], int lane) {
   return d[0];
 }
 
+// The saved activation h is read by the epilogue straight from global memory (each thread its own row: whole 128-byte
+// lines).  To keep that latency off the critical path the rows of the NEXT tile are prefetched into L2 while the epilogue
+// warps wait for its accumulator, and the loads of the next 32-column pass are issued before the current one is processed.
+__device__ __forceinline__ void actbwd_prefetch(const GemmArgs& g, const ActBwdEpi& e, const TileCtx& t) {
+  if (!t.valid) return;
+  const long long pix = ((long long)t.b * g.H + t.y) * g.W + t.x;
+  const int nblk = g.BN >> 6;
+  for (int blk = t.half; blk < nblk; blk += 2) {
+    const __nv_bfloat16* p = e.h + pix * e.h_ld + t.n_tile * g.BN + blk * 64;
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+  }
+}
+
+__device__ __forceinline__ void actbwd_load_h(const ActBwdEpi& e, const TileCtx& t, long long pix, int col, uint4 (&hv)[4]) {
+  if (t.valid) {
+    const uint4* hp = reinterpret_cast<const uint4*>(e.h + pix * e.h_ld + col);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) hv[k] = __ldg(hp + k);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) hv[k] = make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+
 // csum: this thread's running column sums, index = (block / 2) * 2 + pass (a warp owns every second 64-column block)
 __device__ __forceinline__ void epilogue_actbwd(const GemmArgs& g, const ActBwdEpi& e, const CUtensorMap* tmO, uint32_t taddr,
                                                 const float* ss, const TileCtx& t, float (&csum)[4]) {
@@ -344,8 +368,11 @@ __device__ __forceinline__ void epilogue_actbwd(const GemmArgs& g, const ActBwdE
   const int sub_n = t.n0 + (r0 >> (g.tw_log2 + g.th_log2));
   const int last_blk = ((nblk - 1 - t.half) & ~1) + t.half;
   const long long pix = ((long long)t.b * g.H + t.y) * g.W + t.x;
+  const int col_base = t.n_tile * g.BN;
   bool released = false;
   int bi = 0;
+  uint4 hv[4], hn[4];
+  if (t.half < nblk) actbwd_load_h(e, t, pix, col_base + t.half * 64, hv);
   for (int blk = t.half; blk < nblk; blk += 2, ++bi) {
     uint32_t pk[32];
 #pragma unroll
@@ -354,15 +381,9 @@ __device__ __forceinline__ void epilogue_actbwd(const GemmArgs& g, const ActBwdE
       uint32_t v[32];
       tmem_ld16_nowait(taddr + c0, v);
       tmem_ld16_nowait(taddr + c0 + 16, v + 16);
-      uint4 hv[4];
-      if (t.valid) {
-        const uint4* hp = reinterpret_cast<const uint4*>(e.h + pix * e.h_ld + t.n_tile * g.BN + c0);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) hv[k] = __ldg(hp + k);
-      } else {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) hv[k] = make_uint4(0u, 0u, 0u, 0u);
-      }
+      // next pass's activation row segment: in flight while this one is processed
+      const int c_next = pass == 0 ? c0 + 32 : c0 + 96;     // second half of this block, or first half of the warp's next block
+      if (pass == 0 || blk + 2 < nblk) actbwd_load_h(e, t, pix, col_base + c_next, hn);
       tmem_wait_ld();
       float d[32];
       const __nv_bfloat16* hb = reinterpret_cast<const __nv_bfloat16*>(hv);
@@ -378,6 +399,8 @@ __device__ __forceinline__ void epilogue_actbwd(const GemmArgs& g, const ActBwdE
       for (int j = 0; j < 16; ++j) pk[pass * 16 + j] = pack_bf16(d[2 * j], d[2 * j + 1]);
       if (blk == last_blk && pass == 1) { release_accumulator(t); released = true; }
       csum[(bi & 1) * 2 + pass] += warp_colsum32(d, lane);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) hv[k] = hn[k];
     }
     if (issuer) bulk_wait_read0();
     __syncwarp();
@@ -894,6 +917,20 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       t.valid = mt < g.m_tiles && t.b < g.B && t.y < g.H && t.x < g.W;
       t.tmem_empty_bar = tmem_empty_bar(buf);
       t.tile_id = n_tile * g.m_tiles + mt;
+      if constexpr (std::is_same<Epi, ActBwdEpi>::value) {
+        // the saved-activation rows of the NEXT tile -> L2 while this tile's epilogue runs (and this tile's, the first time)
+        if (tl == 0) actbwd_prefetch(g, ep, t);
+        if (it + it_step < it_end) {
+          TileCtx tn = t;
+          const int mtn = tile_of(it + it_step);
+          tile_origin(mtn, tn.x0, tn.y0, tn.n0);
+          tn.b = tn.n0 + (row >> ppi_log2);
+          tn.y = tn.y0 + ((row >> g.tw_log2) & ((1 << g.th_log2) - 1));
+          tn.x = tn.x0 + (row & ((1 << g.tw_log2) - 1));
+          tn.valid = mtn < g.m_tiles && tn.b < g.B && tn.y < g.H && tn.x < g.W;
+          actbwd_prefetch(g, ep, tn);
+        }
+      }
       { CNT_BEGIN(); mbar_wait(tmem_full_bar(buf), (tl >> 1) & 1u); CNT_END(c_wait_tfull); }
       if (tl == 0 && warp == kEpiWarp0 && lane == 0) RFK_STAMP(5);  // first accumulator ready
       tc_fence_after();
