@@ -331,94 +331,48 @@ __device__ __forceinline__ float warp_colsum32(float (&d)[32], int lane) {
   return d[0];
 }
 
-// The saved activation h is read by the epilogue straight from global memory (each thread its own row: whole 128-byte
-// lines).  To keep that latency off the critical path the rows of the NEXT tile are prefetched into L2 while the epilogue
-// warps wait for its accumulator, and the loads of the next 32-column pass are issued before the current one is processed.
-__device__ __forceinline__ void actbwd_prefetch(const GemmArgs& g, const ActBwdEpi& e, const TileCtx& t) {
-  if (!t.valid) return;
-  const long long pix = ((long long)t.b * g.H + t.y) * g.W + t.x;
-  const int nblk = g.BN >> 6;
-  for (int blk = t.half; blk < nblk; blk += 2) {
-    const __nv_bfloat16* p = e.h + pix * e.h_ld + t.n_tile * g.BN + blk * 64;
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-  }
-}
-
-__device__ __forceinline__ void actbwd_load_h(const ActBwdEpi& e, const TileCtx& t, long long pix, int col, uint4 (&hv)[4]) {
-  if (t.valid) {
-    const uint4* hp = reinterpret_cast<const uint4*>(e.h + pix * e.h_ld + col);
+// One 64-column block of the fused data-gradient + activation-backward epilogue.  The warp's 32 rows x 64 columns of the saved
+// activation h were brought into `buf` (this warp's slice of a staging block, 128-byte swizzled) by a TMA load; every thread
+// reads its own row from there, turns the accumulator into da = dh * act'(h) * scale, writes da back IN PLACE (same thread,
+// same 128 bytes) and the caller TMA-stores the slice.  Returns the column sums through csum[2] (lane l: column colsum_col(l)
+// of each 32-column half).
+__device__ __forceinline__ void actbwd_block(const GemmArgs& g, const ActBwdEpi& e, uint32_t taddr, const float* ss, int c0,
+                                             uint32_t row_smem, int rsw, bool valid, int lane, float (&cs)[2]) {
+  uint32_t pk[32];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) hv[k] = __ldg(hp + k);
-  } else {
+  for (int pass = 0; pass < 2; ++pass) {
+    uint32_t v[32];
+    tmem_ld16_nowait(taddr + c0 + pass * 32, v);
+    tmem_ld16_nowait(taddr + c0 + pass * 32 + 16, v + 16);
+    uint32_t hw[16];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) hv[k] = make_uint4(0u, 0u, 0u, 0u);
-  }
-}
-
-// csum: this thread's running column sums, index = (block / 2) * 2 + pass (a warp owns every second 64-column block)
-__device__ __forceinline__ void epilogue_actbwd(const GemmArgs& g, const ActBwdEpi& e, const CUtensorMap* tmO, uint32_t taddr,
-                                                const float* ss, const TileCtx& t, float (&csum)[4]) {
-  const int lane = threadIdx.x & 31;
-  const int nblk = g.BN >> 6;                 // whole 64-column blocks (the host guarantees BN % 64 == 0)
-  const int r = t.q * 32 + lane;
-  const bool issuer = lane == 0;
-  const int r0 = t.q * 32;
-  const int sub_x = t.x0 + (r0 & ((1 << g.tw_log2) - 1));
-  const int sub_y = t.y0 + ((r0 >> g.tw_log2) & ((1 << g.th_log2) - 1));
-  const int sub_n = t.n0 + (r0 >> (g.tw_log2 + g.th_log2));
-  const int last_blk = ((nblk - 1 - t.half) & ~1) + t.half;
-  const long long pix = ((long long)t.b * g.H + t.y) * g.W + t.x;
-  const int col_base = t.n_tile * g.BN;
-  bool released = false;
-  int bi = 0;
-  uint4 hv[4], hn[4];
-  if (t.half < nblk) actbwd_load_h(e, t, pix, col_base + t.half * 64, hv);
-  for (int blk = t.half; blk < nblk; blk += 2, ++bi) {
-    uint32_t pk[32];
-#pragma unroll
-    for (int pass = 0; pass < 2; ++pass) {
-      const int c0 = blk * 64 + pass * 32;
-      uint32_t v[32];
-      tmem_ld16_nowait(taddr + c0, v);
-      tmem_ld16_nowait(taddr + c0 + 16, v + 16);
-      // next pass's activation row segment: in flight while this one is processed
-      const int c_next = pass == 0 ? c0 + 32 : c0 + 96;     // second half of this block, or first half of the warp's next block
-      if (pass == 0 || blk + 2 < nblk) actbwd_load_h(e, t, pix, col_base + c_next, hn);
-      tmem_wait_ld();
-      float d[32];
-      const __nv_bfloat16* hb = reinterpret_cast<const __nv_bfloat16*>(hv);
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float hval = __bfloat162float(hb[j]);
-        float m = 1.0f;
-        if (e.act_fn == RFK_ACT_RELU) m = hval > 0.0f ? 1.0f : 0.0f;
-        else if (e.act_fn == RFK_ACT_LEAKY) m = hval > 0.0f ? 1.0f : 0.2f;
-        d[j] = t.valid ? __uint_as_float(v[j]) * m * ss[c0 + j] : 0.0f;
-      }
-#pragma unroll
-      for (int j = 0; j < 16; ++j) pk[pass * 16 + j] = pack_bf16(d[2 * j], d[2 * j + 1]);
-      if (blk == last_blk && pass == 1) { release_accumulator(t); released = true; }
-      csum[(bi & 1) * 2 + pass] += warp_colsum32(d, lane);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) hv[k] = hn[k];
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t src = row_smem + (((4 * pass + j) ^ rsw) << 4);
+      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(hw[4 * j]), "=r"(hw[4 * j + 1]), "=r"(hw[4 * j + 2]),
+                   "=r"(hw[4 * j + 3]) : "r"(src));
     }
-    if (issuer) bulk_wait_read0();
-    __syncwarp();
+    tmem_wait_ld();
+    float d[32];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const uint32_t dst = t.stg + r * 128 + ((j ^ (r & 7)) << 4);
-      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk[4 * j]), "r"(pk[4 * j + 1]),
-                   "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3])
-                   : "memory");
+    for (int j = 0; j < 16; ++j) {
+      const float2 hf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hw[j]));
+      float m0 = 1.0f, m1 = 1.0f;
+      if (e.act_fn == RFK_ACT_RELU) { m0 = hf.x > 0.0f ? 1.0f : 0.0f; m1 = hf.y > 0.0f ? 1.0f : 0.0f; }
+      else if (e.act_fn == RFK_ACT_LEAKY) { m0 = hf.x > 0.0f ? 1.0f : 0.2f; m1 = hf.y > 0.0f ? 1.0f : 0.2f; }
+      const int c = c0 + pass * 32 + 2 * j;
+      d[2 * j] = valid ? __uint_as_float(v[2 * j]) * m0 * ss[c] : 0.0f;
+      d[2 * j + 1] = valid ? __uint_as_float(v[2 * j + 1]) * m1 * ss[c + 1] : 0.0f;
+      pk[pass * 16 + j] = pack_bf16(d[2 * j], d[2 * j + 1]);
     }
-    fence_async_smem();
-    __syncwarp();
-    if (issuer) {
-      tma_store_4d(tmO, t.stg + r0 * 128, t.n_tile * g.BN + blk * 64, sub_x, sub_y, sub_n);
-      bulk_commit();
-    }
+    cs[pass] = warp_colsum32(d, lane);
   }
-  if (!released) release_accumulator(t);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const uint32_t dst = row_smem + ((j ^ rsw) << 4);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk[4 * j]), "r"(pk[4 * j + 1]), "r"(pk[4 * j + 2]),
+                 "r"(pk[4 * j + 3])
+                 : "memory");
+  }
 }
 
 __device__ __forceinline__ void epilogue(const GemmArgs& g, const ActBwdEpi& e, const CUtensorMap* tmO, uint32_t taddr,
@@ -690,7 +644,7 @@ __device__ __forceinline__ void epilogue(const GemmArgs& g, const LstmEpi& e, co
 template <class Epi, bool kPair>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const __grid_constant__ CUtensorMap tmO, const GemmArgs g, const Epi ep) {
+                 const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmH, const GemmArgs g, const Epi ep) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024 B alignment
@@ -708,7 +662,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t stage_bytes = (uint32_t)g.kgroup * (a_chunk_bytes + (g.b_resident ? 0u : b_chunk_bytes));
   const uint32_t stage_base = base + b_res_bytes;
   const uint32_t stg_base = stage_base + g.stages * stage_bytes;
-  const uint32_t ss_off = b_res_bytes + g.stages * stage_bytes + (g.use_stg ? 2u * STG_BYTES : 0u);
+  const uint32_t ss_off = b_res_bytes + g.stages * stage_bytes + (uint32_t)g.use_stg * STG_BYTES;   // use_stg = staging blocks (0, 2, 4)
   float* ss = reinterpret_cast<float*>(smem + ss_off);
   const uint32_t bar_off = ss_off + 2u * g.BN * 4u;
   const uint32_t bar_base = base + bar_off;
@@ -718,6 +672,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   auto tmem_empty_bar = [&](int b) { return bar_base + 8u * (2 * g.stages + 2 + b); };
   const uint32_t b_full_bar = bar_base + 8u * (2 * g.stages + 4);
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + bar_off + 8u * (2 * g.stages + 5));
+  auto h_bar = [&](int w, int b) { return bar_base + 8u * (2 * g.stages + 5) + 16u + 8u * (2 * w + b); };   // ActBwdEpi: per warp, per buffer
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tile = blockIdx.y;
@@ -727,6 +682,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmO);
+    tma_prefetch_desc(&tmH);
     for (int s = 0; s < g.stages; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
@@ -736,6 +692,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(tmem_empty_bar(b), kEpiWarps * (kPair ? 2 : 1));
     }
     mbar_init(b_full_bar, 1);
+    for (int w = 0; w < kEpiWarps; ++w) { mbar_init(h_bar(w, 0), 1); mbar_init(h_bar(w, 1), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (kPair) cluster_sync_all();   // the peer's barriers exist before anything (TMA, commits, remote arrives) targets them
@@ -906,51 +863,95 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     long long phase_cnt[5] = {0, 0, 0, 0, 0};
     t.dbg = g.timeline ? phase_cnt : nullptr;
     t.remote_release = kPair && rank != 0;
-    float csum[4] = {0.0f, 0.0f, 0.0f, 0.0f};   // ActBwdEpi: running column sums of this thread's (block, pass) columns
-    for (int it = it0; it < it_end; it += it_step, ++tl) {
-      const int mt = tile_of(it);
-      const uint32_t buf = tl & 1u;
-      tile_origin(mt, t.x0, t.y0, t.n0);
-      t.b = t.n0 + (row >> ppi_log2);
-      t.y = t.y0 + ((row >> g.tw_log2) & ((1 << g.th_log2) - 1));
-      t.x = t.x0 + (row & ((1 << g.tw_log2) - 1));
-      t.valid = mt < g.m_tiles && t.b < g.B && t.y < g.H && t.x < g.W;
-      t.tmem_empty_bar = tmem_empty_bar(buf);
-      t.tile_id = n_tile * g.m_tiles + mt;
-      if constexpr (std::is_same<Epi, ActBwdEpi>::value) {
-        // the saved-activation rows of the NEXT tile -> L2 while this tile's epilogue runs (and this tile's, the first time)
-        if (tl == 0) actbwd_prefetch(g, ep, t);
-        if (it + it_step < it_end) {
-          TileCtx tn = t;
-          const int mtn = tile_of(it + it_step);
-          tile_origin(mtn, tn.x0, tn.y0, tn.n0);
-          tn.b = tn.n0 + (row >> ppi_log2);
-          tn.y = tn.y0 + ((row >> g.tw_log2) & ((1 << g.th_log2) - 1));
-          tn.x = tn.x0 + (row & ((1 << g.tw_log2) - 1));
-          tn.valid = mtn < g.m_tiles && tn.b < g.B && tn.y < g.H && tn.x < g.W;
-          actbwd_prefetch(g, ep, tn);
-        }
-      }
-      { CNT_BEGIN(); mbar_wait(tmem_full_bar(buf), (tl >> 1) & 1u); CNT_END(c_wait_tfull); }
-      if (tl == 0 && warp == kEpiWarp0 && lane == 0) RFK_STAMP(5);  // first accumulator ready
-      tc_fence_after();
-      if constexpr (std::is_same<Epi, ActBwdEpi>::value) {
-        epilogue_actbwd(g, ep, &tmO, tmem_base + ((uint32_t)(t.q * 32) << 16) + buf * g.BN, ss, t, csum);
-      } else {
-        CNT_BEGIN(); epilogue(g, ep, &tmO, tmem_base + ((uint32_t)(t.q * 32) << 16) + buf * g.BN, ss, t); CNT_END(c_epi);
-      }
-      if (tl == 0 && warp == kEpiWarp0 && lane == 0) RFK_STAMP(6);  // first epilogue done
-    }
     if constexpr (std::is_same<Epi, ActBwdEpi>::value) {
-      // flush the column sums: lane l of a warp holds, for its k-th 64-column block and pass p, column colsum_col(l)
+      // ---- fused data gradient + activation backward: the warp's 32 x 64 slices of h arrive by TMA, double-buffered ----
+      const int ew = warp - kEpiWarp0;
       const int nblk = g.BN >> 6;
-      int bi = 0;
-      for (int blk = t.half; blk < nblk; blk += 2, ++bi) {
+      const int nb = t.half < nblk ? (nblk - t.half + 1) >> 1 : 0;          // 64-column blocks per tile owned by this warp
+      const int r0 = t.q * 32, r = r0 + lane, rsw = r & 7;
+      float csum[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+      auto sub_origin = [&](int x0, int y0, int n0, int& sx, int& sy, int& sn) {
+        sx = x0 + (r0 & ((1 << g.tw_log2) - 1));
+        sy = y0 + ((r0 >> g.tw_log2) & ((1 << g.th_log2) - 1));
+        sn = n0 + (r0 >> (g.tw_log2 + g.th_log2));
+      };
+      auto slice = [&](uint32_t b) { return stg_base + (uint32_t)(t.half * 2 + b) * STG_BYTES + (uint32_t)r0 * 128u; };
+      auto issue_load = [&](int it2, int j, uint32_t b) {     // lane 0: block j of tile it2 -> buffer b
+        int x0, y0, n0, sx, sy, sn;
+        tile_origin(tile_of(it2), x0, y0, n0);
+        sub_origin(x0, y0, n0, sx, sy, sn);
+        bulk_wait_read0();   // the TMA store that last read buffer b (issued one block ago) has let go of it
+        mbar_expect_tx(h_bar(ew, b), 32u * 128u);
+        tma_load_4d(slice(b), &tmH, h_bar(ew, b), n_tile * g.BN + (t.half + 2 * j) * 64, sx, sy, sn);
+      };
+      auto prefetch_tile = [&](int it2) {                     // lane 0: this warp's slices of tile it2 -> L2, a whole tile ahead
+        int x0, y0, n0, sx, sy, sn;
+        tile_origin(tile_of(it2), x0, y0, n0);
+        sub_origin(x0, y0, n0, sx, sy, sn);
+        for (int j = 0; j < nb; ++j) tma_prefetch_4d(&tmH, n_tile * g.BN + (t.half + 2 * j) * 64, sx, sy, sn);
+      };
+      uint32_t gb = 0;                                        // blocks processed so far: buffer = gb & 1, phase = (gb >> 1) & 1
+      if (nb > 0 && it0 < it_end && lane == 0) issue_load(it0, 0, 0);
+      for (int it = it0; it < it_end; it += it_step, ++tl) {
+        const int mt = tile_of(it);
+        const uint32_t buf = tl & 1u;
+        tile_origin(mt, t.x0, t.y0, t.n0);
+        t.b = t.n0 + (row >> ppi_log2);
+        t.y = t.y0 + ((row >> g.tw_log2) & ((1 << g.th_log2) - 1));
+        t.x = t.x0 + (row & ((1 << g.tw_log2) - 1));
+        t.valid = mt < g.m_tiles && t.b < g.B && t.y < g.H && t.x < g.W;
+        t.tmem_empty_bar = tmem_empty_bar(buf);
+        if (lane == 0 && it + it_step < it_end) prefetch_tile(it + it_step);
+        mbar_wait(tmem_full_bar(buf), (tl >> 1) & 1u);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(t.q * 32) << 16) + buf * g.BN;
+        int sx, sy, sn;
+        sub_origin(t.x0, t.y0, t.n0, sx, sy, sn);
+        for (int j = 0; j < nb; ++j, ++gb) {
+          const uint32_t b = gb & 1u;
+          if (lane == 0) {                                    // next block (of this tile or the first of the next) -> other buffer
+            if (j + 1 < nb) issue_load(it, j + 1, b ^ 1u);
+            else if (it + it_step < it_end) issue_load(it + it_step, 0, b ^ 1u);
+          }
+          mbar_wait(h_bar(ew, b), (gb >> 1) & 1u);
+          float cs[2];
+          const int blk = t.half + 2 * j;
+          actbwd_block(g, ep, taddr, ss, blk * 64, slice(b) + (uint32_t)lane * 128u, rsw, t.valid, lane, cs);
+          csum[(j & 1) * 2] += cs[0];
+          csum[(j & 1) * 2 + 1] += cs[1];
+          if (j == nb - 1) release_accumulator(t);
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_4d(&tmO, slice(b), n_tile * g.BN + blk * 64, sx, sy, sn);
+            bulk_commit();
+          }
+        }
+        if (nb == 0) release_accumulator(t);
+      }
+      for (int j = 0; j < nb; ++j) {
 #pragma unroll
         for (int pass = 0; pass < 2; ++pass) {
-          const int col = n_tile * g.BN + blk * 64 + pass * 32 + colsum_col(lane);
-          if (col < g.n) atomicAdd(ep.colsum + col, csum[(bi & 1) * 2 + pass]);
+          const int col = n_tile * g.BN + (t.half + 2 * j) * 64 + pass * 32 + colsum_col(lane);
+          if (col < g.n) atomicAdd(ep.colsum + col, csum[(j & 1) * 2 + pass]);
         }
+      }
+    } else {
+      for (int it = it0; it < it_end; it += it_step, ++tl) {
+        const int mt = tile_of(it);
+        const uint32_t buf = tl & 1u;
+        tile_origin(mt, t.x0, t.y0, t.n0);
+        t.b = t.n0 + (row >> ppi_log2);
+        t.y = t.y0 + ((row >> g.tw_log2) & ((1 << g.th_log2) - 1));
+        t.x = t.x0 + (row & ((1 << g.tw_log2) - 1));
+        t.valid = mt < g.m_tiles && t.b < g.B && t.y < g.H && t.x < g.W;
+        t.tmem_empty_bar = tmem_empty_bar(buf);
+        t.tile_id = n_tile * g.m_tiles + mt;
+        { CNT_BEGIN(); mbar_wait(tmem_full_bar(buf), (tl >> 1) & 1u); CNT_END(c_wait_tfull); }
+        if (tl == 0 && warp == kEpiWarp0 && lane == 0) RFK_STAMP(5);  // first accumulator ready
+        tc_fence_after();
+        { CNT_BEGIN(); epilogue(g, ep, &tmO, tmem_base + ((uint32_t)(t.q * 32) << 16) + buf * g.BN, ss, t); CNT_END(c_epi); }
+        if (tl == 0 && warp == kEpiWarp0 && lane == 0) RFK_STAMP(6);  // first epilogue done
       }
     }
     if (g.use_stg && lane == 0) bulk_wait0();  // this warp's outstanding TMA stores still read shared memory
@@ -999,7 +1000,7 @@ int conv_split_mode() { return g_conv_split; }
 
 struct Plan {
   GemmArgs g;
-  CUtensorMap tmA, tmB, tmO;
+  CUtensorMap tmA, tmB, tmO, tmH;
   dim3 grid;
   size_t smem;
   int TW, TH, NIMG;
@@ -1052,7 +1053,7 @@ int encode_act_map(CUtensorMap* map, const char* who, const char* what, const vo
 // stg_wanted: the epilogue can use TMA stores (needs 2 x 16 KB of staging shared memory)
 static int make_plan(Plan& p, const char* who, const void* act, int B, int H, int W, int act_ld, int cin_pad,
                      const void* wgt, int n, int n_pad, int taps, int BN, bool stg_wanted, int k_split = 1,
-                     bool allow_pair = false) {
+                     bool allow_pair = false, int stg_blocks = 2) {
   RFK_REQUIRE(act && wgt && B > 0 && H > 0 && W > 0, "%s: null pointer or empty shape", who);
   const int parts_ld = g_conv_split ? 2 : 1, parts_k = g_conv_split ? 3 : 1;
   RFK_REQUIRE(cin_pad > 0 && (cin_pad % 64 == 0 || cin_pad == 32) && parts_ld * cin_pad <= act_ld,
@@ -1094,8 +1095,9 @@ static int make_plan(Plan& p, const char* who, const void* act, int B, int H, in
   g.kg_per_split = k_iters / g.kgroup / k_split;
   const int b_chunk = g.kgroup * BN * bk * 2;
   const int a_stage = g.kgroup * BM * bk * 2;
-  const int fixed = 1024 /*alignment slack*/ + (stg_wanted ? 2 * STG_BYTES : 0) + 2 * BN * 4 + 8 * (2 * 8 + 5) + 16;
-  g.use_stg = stg_wanted ? 1 : 0;
+  const int kHBars = 8 * 2 * kEpiWarps;   // ActBwdEpi's per-warp h-tile barriers (allocated for every epilogue: 128 B)
+  const int fixed = 1024 /*alignment slack*/ + (stg_wanted ? stg_blocks * STG_BYTES : 0) + 2 * BN * 4 + 8 * (2 * 8 + 5) + 16 + kHBars;
+  g.use_stg = stg_wanted ? stg_blocks : 0;
   int resident = 0, stages = 0;
   g.pair = 0;
   {
@@ -1142,7 +1144,7 @@ static int make_plan(Plan& p, const char* who, const void* act, int B, int H, in
   g.tmem_cols = cols;  // two accumulators
   const int stage_bytes = a_stage + (resident ? 0 : b_chunk);
   p.smem = (size_t)1024 + (resident ? (size_t)(k_iters / k_split) * BN * bk * 2 / (g.pair ? 2 : 1) : 0) + (size_t)stages * stage_bytes +
-           (stg_wanted ? 2 * STG_BYTES : 0) + 2 * BN * 4 + 8 * (2 * stages + 5) + 16;
+           (stg_wanted ? stg_blocks * STG_BYTES : 0) + 2 * BN * 4 + 8 * (2 * stages + 5) + 16 + kHBars;
   RFK_REQUIRE(p.smem <= (size_t)SMEM_LIMIT, "%s: internal error: %zu B of shared memory planned", who, p.smem);
   int ctas_x = sm_count() / (n_tiles * k_split);
   if (ctas_x < 1) ctas_x = 1;
@@ -1158,6 +1160,7 @@ static int make_plan(Plan& p, const char* who, const void* act, int B, int H, in
   int rc = encode_act_map(&p.tmA, who, "A", act, g_conv_split ? act_ld : cin_pad, act_ld, B, H, W, p.TW, p.TH, p.NIMG, bk);
   if (rc) return rc;
   p.tmO = p.tmA;  // placeholder unless the epilogue stores through TMA
+  p.tmH = p.tmA;  // placeholder unless the epilogue loads a saved activation (ActBwdEpi)
   // B: weights [n_pad, taps*cin_pad] viewed as 2-D {K, N}; box {64, BN}
   const cuuint64_t ktot = (cuuint64_t)taps * parts_k * cin_pad;
   cuuint64_t dimsB[2] = {ktot, (cuuint64_t)n_pad};
@@ -1211,7 +1214,7 @@ static int launch_impl(const Plan& p, const Epi& ep, cudaStream_t st, const char
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  cudaLaunchKernelEx(&cfg, conv_gemm_kernel<Epi, kPair>, p.tmA, p.tmB, p.tmO, p.g, ep);
+  cudaLaunchKernelEx(&cfg, conv_gemm_kernel<Epi, kPair>, p.tmA, p.tmB, p.tmO, p.tmH, p.g, ep);
   return check_launch(who);
 }
 
@@ -1329,11 +1332,13 @@ extern "C" int rfk_conv_gemm_actbwd(const void* act, int B, int H, int W, int ac
   const int BN = n <= 256 ? n : pick_bn(n_pad, 64, m_tiles_of(B, H, W));
   RFK_REQUIRE(BN > 0 && BN % 64 == 0 && BN <= 256, "rfk_conv_gemm_actbwd: no N tile for n=%d", n);
   Plan p;
-  int rc = make_plan(p, "rfk_conv_gemm_actbwd", act, B, H, W, act_ld, cin_pad, wgt, n, n_pad, taps, BN, true, 1, true);
+  int rc = make_plan(p, "rfk_conv_gemm_actbwd", act, B, H, W, act_ld, cin_pad, wgt, n, n_pad, taps, BN, true, 1, true, 4);
   if (rc) return rc;
   p.g.scale = scale; p.g.shift = nullptr; p.g.n_ss = n;
   const int sx = std::min(p.TW, 32), sy = std::min(p.TH, 32 / sx), sn = 32 / (sx * sy);
   rc = encode_act_map(&p.tmO, "rfk_conv_gemm_actbwd", "out", out, n, out_ld, B, H, W, sx, sy, sn);
+  if (rc) return rc;
+  rc = encode_act_map(&p.tmH, "rfk_conv_gemm_actbwd", "h", h, n, h_ld, B, H, W, sx, sy, sn);   // same 32-row slices, loaded
   if (rc) return rc;
   ActBwdEpi e;
   e.h = (const __nv_bfloat16*)h; e.h_ld = h_ld; e.act_fn = act_fn; e.colsum = colsum;
