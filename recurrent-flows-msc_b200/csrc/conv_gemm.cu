@@ -353,16 +353,28 @@ __device__ __forceinline__ void actbwd_block(const GemmArgs& g, const ActBwdEpi&
     }
     tmem_wait_ld();
     float d[32];
+    const float4* sc4 = reinterpret_cast<const float4*>(ss + c0 + pass * 32);
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const float2 hf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hw[j]));
-      float m0 = 1.0f, m1 = 1.0f;
-      if (e.act_fn == RFK_ACT_RELU) { m0 = hf.x > 0.0f ? 1.0f : 0.0f; m1 = hf.y > 0.0f ? 1.0f : 0.0f; }
-      else if (e.act_fn == RFK_ACT_LEAKY) { m0 = hf.x > 0.0f ? 1.0f : 0.2f; m1 = hf.y > 0.0f ? 1.0f : 0.2f; }
-      const int c = c0 + pass * 32 + 2 * j;
-      d[2 * j] = valid ? __uint_as_float(v[2 * j]) * m0 * ss[c] : 0.0f;
-      d[2 * j + 1] = valid ? __uint_as_float(v[2 * j + 1]) * m1 * ss[c + 1] : 0.0f;
-      pk[pass * 16 + j] = pack_bf16(d[2 * j], d[2 * j + 1]);
+    for (int q4 = 0; q4 < 8; ++q4) {
+      const float4 s4 = sc4[q4];
+      const float2 ha = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hw[2 * q4]));
+      const float2 hb = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hw[2 * q4 + 1]));
+      float m0, m1, m2, m3;
+      if (e.act_fn == RFK_ACT_RELU) {
+        m0 = ha.x > 0.0f ? s4.x : 0.0f; m1 = ha.y > 0.0f ? s4.y : 0.0f; m2 = hb.x > 0.0f ? s4.z : 0.0f; m3 = hb.y > 0.0f ? s4.w : 0.0f;
+      } else if (e.act_fn == RFK_ACT_LEAKY) {
+        m0 = ha.x > 0.0f ? s4.x : 0.2f * s4.x; m1 = ha.y > 0.0f ? s4.y : 0.2f * s4.y;
+        m2 = hb.x > 0.0f ? s4.z : 0.2f * s4.z; m3 = hb.y > 0.0f ? s4.w : 0.2f * s4.w;
+      } else {
+        m0 = s4.x; m1 = s4.y; m2 = s4.z; m3 = s4.w;
+      }
+      if (!valid) m0 = m1 = m2 = m3 = 0.0f;   // a row outside the image can still see inside pixels through the 3x3 taps
+      d[4 * q4] = __uint_as_float(v[4 * q4]) * m0;
+      d[4 * q4 + 1] = __uint_as_float(v[4 * q4 + 1]) * m1;
+      d[4 * q4 + 2] = __uint_as_float(v[4 * q4 + 2]) * m2;
+      d[4 * q4 + 3] = __uint_as_float(v[4 * q4 + 3]) * m3;
+      pk[pass * 16 + 2 * q4] = pack_bf16(d[4 * q4], d[4 * q4 + 1]);
+      pk[pass * 16 + 2 * q4 + 1] = pack_bf16(d[4 * q4 + 2], d[4 * q4 + 3]);
     }
     cs[pass] = warp_colsum32(d, lane);
   }
@@ -672,7 +684,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   auto tmem_empty_bar = [&](int b) { return bar_base + 8u * (2 * g.stages + 2 + b); };
   const uint32_t b_full_bar = bar_base + 8u * (2 * g.stages + 4);
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + bar_off + 8u * (2 * g.stages + 5));
-  auto h_bar = [&](int w, int b) { return bar_base + 8u * (2 * g.stages + 5) + 16u + 8u * (2 * w + b); };   // ActBwdEpi: per warp, per buffer
+  auto h_bar = [&](int w, int b) { return bar_base + 8u * (2 * g.stages + 5) + 16u + 8u * (3 * w + b); };   // ActBwdEpi: per warp, per buffer
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tile = blockIdx.y;
@@ -692,7 +704,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(tmem_empty_bar(b), kEpiWarps * (kPair ? 2 : 1));
     }
     mbar_init(b_full_bar, 1);
-    for (int w = 0; w < kEpiWarps; ++w) { mbar_init(h_bar(w, 0), 1); mbar_init(h_bar(w, 1), 1); }
+    for (int w = 0; w < kEpiWarps; ++w)
+      for (int b = 0; b < 3; ++b) mbar_init(h_bar(w, b), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (kPair) cluster_sync_all();   // the peer's barriers exist before anything (TMA, commits, remote arrives) targets them
@@ -875,12 +888,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         sy = y0 + ((r0 >> g.tw_log2) & ((1 << g.th_log2) - 1));
         sn = n0 + (r0 >> (g.tw_log2 + g.th_log2));
       };
-      auto slice = [&](uint32_t b) { return stg_base + (uint32_t)(t.half * 2 + b) * STG_BYTES + (uint32_t)r0 * 128u; };
+      auto slice = [&](uint32_t b) { return stg_base + (uint32_t)(t.half * 3 + b) * STG_BYTES + (uint32_t)r0 * 128u; };
       auto issue_load = [&](int it2, int j, uint32_t b) {     // lane 0: block j of tile it2 -> buffer b
         int x0, y0, n0, sx, sy, sn;
         tile_origin(tile_of(it2), x0, y0, n0);
         sub_origin(x0, y0, n0, sx, sy, sn);
-        bulk_wait_read0();   // the TMA store that last read buffer b (issued one block ago) has let go of it
+        // three buffers: the TMA store that last read buffer b was issued two blocks ago; only the newest may be pending
+        asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
         mbar_expect_tx(h_bar(ew, b), 32u * 128u);
         tma_load_4d(slice(b), &tmH, h_bar(ew, b), n_tile * g.BN + (t.half + 2 * j) * 64, sx, sy, sn);
       };
@@ -890,7 +904,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         sub_origin(x0, y0, n0, sx, sy, sn);
         for (int j = 0; j < nb; ++j) tma_prefetch_4d(&tmH, n_tile * g.BN + (t.half + 2 * j) * 64, sx, sy, sn);
       };
-      uint32_t gb = 0;                                        // blocks processed so far: buffer = gb & 1, phase = (gb >> 1) & 1
+      uint32_t gb = 0;                                        // blocks processed so far: buffer = gb % 3, phase = (gb / 3) & 1
       if (nb > 0 && it0 < it_end && lane == 0) issue_load(it0, 0, 0);
       for (int it = it0; it < it_end; it += it_step, ++tl) {
         const int mt = tile_of(it);
@@ -908,12 +922,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         int sx, sy, sn;
         sub_origin(t.x0, t.y0, t.n0, sx, sy, sn);
         for (int j = 0; j < nb; ++j, ++gb) {
-          const uint32_t b = gb & 1u;
-          if (lane == 0) {                                    // next block (of this tile or the first of the next) -> other buffer
-            if (j + 1 < nb) issue_load(it, j + 1, b ^ 1u);
-            else if (it + it_step < it_end) issue_load(it + it_step, 0, b ^ 1u);
+          const uint32_t b = gb % 3u, bn = (gb + 1u) % 3u;
+          if (lane == 0) {                                    // next block (of this tile or the first of the next) -> next buffer
+            if (j + 1 < nb) issue_load(it, j + 1, bn);
+            else if (it + it_step < it_end) issue_load(it + it_step, 0, bn);
           }
-          mbar_wait(h_bar(ew, b), (gb >> 1) & 1u);
+          mbar_wait(h_bar(ew, b), (gb / 3u) & 1u);
           float cs[2];
           const int blk = t.half + 2 * j;
           actbwd_block(g, ep, taddr, ss, blk * 64, slice(b) + (uint32_t)lane * 128u, rsw, t.valid, lane, cs);
@@ -1095,7 +1109,7 @@ static int make_plan(Plan& p, const char* who, const void* act, int B, int H, in
   g.kg_per_split = k_iters / g.kgroup / k_split;
   const int b_chunk = g.kgroup * BN * bk * 2;
   const int a_stage = g.kgroup * BM * bk * 2;
-  const int kHBars = 8 * 2 * kEpiWarps;   // ActBwdEpi's per-warp h-tile barriers (allocated for every epilogue: 128 B)
+  const int kHBars = 8 * 3 * kEpiWarps;   // ActBwdEpi's per-warp h-tile barriers (allocated for every epilogue: 192 B)
   const int fixed = 1024 /*alignment slack*/ + (stg_wanted ? stg_blocks * STG_BYTES : 0) + 2 * BN * 4 + 8 * (2 * 8 + 5) + 16 + kHBars;
   g.use_stg = stg_wanted ? stg_blocks : 0;
   int resident = 0, stages = 0;
@@ -1332,7 +1346,7 @@ extern "C" int rfk_conv_gemm_actbwd(const void* act, int B, int H, int W, int ac
   const int BN = n <= 256 ? n : pick_bn(n_pad, 64, m_tiles_of(B, H, W));
   RFK_REQUIRE(BN > 0 && BN % 64 == 0 && BN <= 256, "rfk_conv_gemm_actbwd: no N tile for n=%d", n);
   Plan p;
-  int rc = make_plan(p, "rfk_conv_gemm_actbwd", act, B, H, W, act_ld, cin_pad, wgt, n, n_pad, taps, BN, true, 1, true, 4);
+  int rc = make_plan(p, "rfk_conv_gemm_actbwd", act, B, H, W, act_ld, cin_pad, wgt, n, n_pad, taps, BN, true, 1, true, 6);
   if (rc) return rc;
   p.g.scale = scale; p.g.shift = nullptr; p.g.n_ss = n;
   const int sx = std::min(p.TW, 32), sy = std::min(p.TH, 32 / sx), sn = 32 / (sx * sy);
