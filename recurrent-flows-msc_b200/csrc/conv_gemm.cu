@@ -888,13 +888,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         sy = y0 + ((r0 >> g.tw_log2) & ((1 << g.th_log2) - 1));
         sn = n0 + (r0 >> (g.tw_log2 + g.th_log2));
       };
-      auto slice = [&](uint32_t b) { return stg_base + (uint32_t)(t.half * 3 + b) * STG_BYTES + (uint32_t)r0 * 128u; };
+      const uint32_t nbuf = (uint32_t)g.use_stg >> 1;         // staging buffers per warp: 3 (6 blocks) or 2 (4 blocks, when shared memory is short)
+      auto slice = [&](uint32_t b) { return stg_base + ((uint32_t)t.half * nbuf + b) * STG_BYTES + (uint32_t)r0 * 128u; };
       auto issue_load = [&](int it2, int j, uint32_t b) {     // lane 0: block j of tile it2 -> buffer b
         int x0, y0, n0, sx, sy, sn;
         tile_origin(tile_of(it2), x0, y0, n0);
         sub_origin(x0, y0, n0, sx, sy, sn);
-        // three buffers: the TMA store that last read buffer b was issued two blocks ago; only the newest may be pending
-        asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        // the TMA store that last read buffer b was issued nbuf - 1 blocks ago: with three buffers the newest store may
+        // still be pending, with two it has to be waited for
+        if (nbuf == 3) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        else bulk_wait_read0();
         mbar_expect_tx(h_bar(ew, b), 32u * 128u);
         tma_load_4d(slice(b), &tmH, h_bar(ew, b), n_tile * g.BN + (t.half + 2 * j) * 64, sx, sy, sn);
       };
@@ -904,7 +907,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         sub_origin(x0, y0, n0, sx, sy, sn);
         for (int j = 0; j < nb; ++j) tma_prefetch_4d(&tmH, n_tile * g.BN + (t.half + 2 * j) * 64, sx, sy, sn);
       };
-      uint32_t gb = 0;                                        // blocks processed so far: buffer = gb % 3, phase = (gb / 3) & 1
+      uint32_t gb = 0;                                        // blocks processed so far: buffer = gb % nbuf, phase = (gb / nbuf) & 1
       if (nb > 0 && it0 < it_end && lane == 0) issue_load(it0, 0, 0);
       for (int it = it0; it < it_end; it += it_step, ++tl) {
         const int mt = tile_of(it);
@@ -922,12 +925,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         int sx, sy, sn;
         sub_origin(t.x0, t.y0, t.n0, sx, sy, sn);
         for (int j = 0; j < nb; ++j, ++gb) {
-          const uint32_t b = gb % 3u, bn = (gb + 1u) % 3u;
+          const uint32_t b = gb % nbuf, bn = (gb + 1u) % nbuf;
           if (lane == 0) {                                    // next block (of this tile or the first of the next) -> next buffer
             if (j + 1 < nb) issue_load(it, j + 1, bn);
             else if (it + it_step < it_end) issue_load(it + it_step, 0, bn);
           }
-          mbar_wait(h_bar(ew, b), (gb / 3u) & 1u);
+          mbar_wait(h_bar(ew, b), (gb / nbuf) & 1u);
           float cs[2];
           const int blk = t.half + 2 * j;
           actbwd_block(g, ep, taddr, ss, blk * 64, slice(b) + (uint32_t)lane * 128u, rsw, t.valid, lane, cs);
@@ -1346,7 +1349,14 @@ extern "C" int rfk_conv_gemm_actbwd(const void* act, int B, int H, int W, int ac
   const int BN = n <= 256 ? n : pick_bn(n_pad, 64, m_tiles_of(B, H, W));
   RFK_REQUIRE(BN > 0 && BN % 64 == 0 && BN <= 256, "rfk_conv_gemm_actbwd: no N tile for n=%d", n);
   Plan p;
+  // three staging buffers per epilogue warp (96 KB) unless that starves the main loop of pipeline stages or of the CTA-pair
+  // mode: then two (64 KB)
   int rc = make_plan(p, "rfk_conv_gemm_actbwd", act, B, H, W, act_ld, cin_pad, wgt, n, n_pad, taps, BN, true, 1, true, 6);
+  if (rc || (!p.g.pair && (p.g.stages < 3 || !p.g.b_resident))) {
+    Plan p4;
+    const int rc4 = make_plan(p4, "rfk_conv_gemm_actbwd", act, B, H, W, act_ld, cin_pad, wgt, n, n_pad, taps, BN, true, 1, true, 4);
+    if (rc4 == 0 && (rc || p4.g.pair || p4.g.stages > p.g.stages || (p4.g.b_resident && !p.g.b_resident))) { p = p4; rc = 0; }
+  }
   if (rc) return rc;
   p.g.scale = scale; p.g.shift = nullptr; p.g.n_ss = n;
   const int sx = std::min(p.TW, 32), sy = std::min(p.TH, 32 / sx), sn = 32 / (sx * sy);

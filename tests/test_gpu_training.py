@@ -496,7 +496,9 @@ def test_flatadam_state_dict_and_param_groups(rf):
     rf.derived.REFRESHER.refresh_all(opt.flat_p.device, rf.ops._stream())
     opt.load_state_dict(sd)
     step()
-    assert torch.equal(opt.flat_p, p_next)
+    # same update up to the summation order of the atomically accumulated gradients
+    torch.testing.assert_close(opt.flat_p, p_next, rtol=1e-4, atol=1e-6)
+    assert float((opt.flat_p - p_saved).abs().max()) > 1e-5
     for group in opt.param_groups:          # the trainer's linear LR decay writes here
         group["lr"] = 0.0
     before = opt.flat_p.clone()
