@@ -275,6 +275,11 @@ int rfk_pack_weight(const float* src, int N, int Cin, int taps, int mode, const 
  * a_hi w_hi + a_lo w_hi + a_hi w_lo, accumulated in fp32.  Process-global switch (set once at start-up, not thread-safe);
  * the bf16-only fusions (rfk_conv1x1_taps_fused, rfk_conv_gemm_splitk_fused, TMA-store epilogue) refuse / step aside. */
 int rfk_set_conv_split(int on);
+/* Programmatic dependent launch for the launches that follow (process-global; returns the previous setting, which is NOT an
+ * error code).  Every kernel of the library waits (griddepcontrol.wait) before reading what a predecessor wrote and lets
+ * its successor's prologue start early; kernels that write packed weights do not release their dependents early, because
+ * the convolution kernels prefetch weights before their own wait.  The environment variable RFK_PDL=1/0 overrides. */
+int rfk_set_pdl(int on);
 int rfk_pack_nhwc_bf16_lo(const float* src, long long src_bstride, int B, int Csrc, int HW, int c_lo, int n, void* dst,
                           int dst_off, int dst_ld, void* stream);
 

@@ -371,7 +371,10 @@ class ListGlow(nn.Module):
                         mean, std = torch.zeros_like(z), torch.ones_like(z)
                     else:
                         mean, std = params[:, :cz], torch.exp(params[:, cz:])
-            x, _ = self.g(z, condition, logdet=None, temperature=temperature, eps_list=eps_list)
+            # the reverse pass is a chain of ~280 small dependent launches: programmatic dependent launch lets every kernel's
+            # prologue overlap its predecessor's tail (-6 % per frame; the throughput-bound passes do not use it)
+            with ops.pdl(True):
+                x, _ = self.g(z, condition, logdet=None, temperature=temperature, eps_list=eps_list)
         if eval_params:
             return x, (mean, std)
         return x

@@ -67,6 +67,7 @@ SIGNATURES = {
     "rfk_taps_gather_nhwc": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
     "rfk_add_scalar": [c_void_p, c_void_p, c_float, c_int, c_void_p],
     "rfk_set_conv_split": [c_int],
+    "rfk_set_pdl": [c_int],
     "rfk_pack_nhwc_bf16_lo": [c_void_p, c_longlong, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p],
     "rfk_pack_weights_batched": [c_void_p, c_int, c_longlong, c_void_p],
     "rfk_affine_prepare_batched": [c_void_p, c_int, c_void_p],

@@ -26,18 +26,28 @@ int sm_count() {
   return n;
 }
 
+// Programmatic dependent launch.  RFK_PDL=1 / 0 forces it on / off for every launch; otherwise it follows rfk_set_pdl(),
+// which the host side switches on around the sampling direction (latency-bound chains of small launches: -6 % per frame)
+// and leaves off elsewhere (the training step loses 4 % with it).
+static int g_pdl_mode = 0;
 bool pdl_enabled() {
-  static int v = -1;
-  if (v < 0) {
+  static int env = -2;
+  if (env == -2) {
     const char* e = getenv("RFK_PDL");
-    v = (e && atoi(e) != 0) ? 1 : 0;   // opt-in: measured neutral on B200 for this workload
+    env = e ? (atoi(e) != 0 ? 1 : 0) : -1;
   }
-  return v == 1;
+  return env >= 0 ? env == 1 : g_pdl_mode == 1;
 }
 
 }  // namespace rfk
 
 extern "C" int rfk_version(void) { return RFK_VERSION; }
+
+extern "C" int rfk_set_pdl(int on) {
+  const int prev = rfk::g_pdl_mode;
+  rfk::g_pdl_mode = on ? 1 : 0;
+  return prev;
+}
 
 extern "C" const char* rfk_last_error(void) { return rfk::g_err; }
 

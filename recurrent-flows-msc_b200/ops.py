@@ -60,6 +60,16 @@ if SPLIT:
     call("rfk_set_conv_split", 1)
 
 
+@contextlib.contextmanager
+def pdl(on=True):
+    """Programmatic dependent launch for the launches enqueued inside the block (rfk_set_pdl)."""
+    prev = _lib.lib().rfk_set_pdl(int(on))
+    try:
+        yield
+    finally:
+        _lib.lib().rfk_set_pdl(prev)
+
+
 def buf_ld(c):
     """Row stride (channels) of an NHWC staging buffer for c real channels: cin_pad(c), or two such halves [hi | lo]."""
     return (2 if SPLIT else 1) * cin_pad(c)
