@@ -797,6 +797,7 @@ def wl_rfn_train(env, rf, args, smooth=False):
     tx, tz, tfeats, tconds = static[0], static[1], static[2], static[3:]
     params = list(flow.parameters()) + list(lstm.parameters()) + (list(slstm.parameters()) if slstm else [])
     opt = rf.FlatAdam(params, lr=1e-4, world_size=world)
+    opt.attach(flow)      # per-level gradient slices are all-reduced while the shallower levels are still in the backward sweep
 
     def loss_fn():
         # as in RFN.loss: the recurrence's hidden states condition the flow's prior, so the flow's gradient w.r.t. its
@@ -855,6 +856,8 @@ def wl_rfn_train(env, rf, args, smooth=False):
            "training": {"own_kernel_launches_per_step": launches_per_step, "parameters": opt.n,
                         "launch": "eager" if args.no_graph else train_step.mode,
                         "allreduce_bytes_per_step": opt.n_pad * 4 if world > 1 else 0,
+                        "allreduce": "per-level slices of the flat gradient, asynchronous, overlapped with the backward sweep; "
+                                     "level 1 + ConvLSTM at the end" if world > 1 else "none (one replica)",
                         "loss_first_step": first_loss, "loss_last_step": last_loss,
                         "peak_memory_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 2)}}
     state = dict(flow=flow, lstm=lstm, opt=opt, eager_step=eager_step_local, static=static, host=host, n_frames=n_frames)

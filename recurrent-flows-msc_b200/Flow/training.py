@@ -63,6 +63,7 @@ class _State:
         self.grads = {}
         self.direct = set()
         self.folds = []
+        self.prior_announced = False
         self.side = None          # second stream for small weight-gradient launches
         self.side_keep = []       # tensors the side stream still reads (kept alive until the join)
 
@@ -405,7 +406,7 @@ def _glowstep_bwd(st, flow, step, x, zo, nn_in, h1, h2, taps, cc, l, xn=None, bn
     st.folds.append((step, dWf, dbf, H * W, buf))   # chained to the parameters in one batch at the end of the sweep
 
 
-def _fold_bwd_all(st, flow):
+def _fold_bwd_all(st, flow, level=None):
     """Chain (d Wf, d bf, d logdet) of every GlowStep back to ActNorm's (bias, logs) and InvConv's parameters
     (Flow/glow_modules.py:33-54, 167-205).  LU-parameterised steps whose forward fold is registered for batched refresh go
     through ONE launch of rfk_fold_backward_batched over a pointer table (rebuilt only when a pointer changed); the rest
@@ -428,13 +429,14 @@ def _fold_bwd_all(st, flow):
             rows.append(row + [0] * (24 - len(row)))
             key.extend(row)
         key = tuple(key)
-        cache = flow.__dict__.get("_fold_bwd_table")
+        tables = flow.__dict__.setdefault("_fold_bwd_tables", {})
+        cache = tables.get(level)
         if cache is None or cache[0] != key:
             if torch.cuda.is_current_stream_capturing():
                 raise RuntimeError("recurrent-flows-msc_b200: the fold-backward table changed inside a CUDA-graph capture; run the "
                                    "training step eagerly once with the same optimizer before capturing")
             cache = (key, torch.tensor([w for r in rows for w in r], dtype=torch.int64).to(st.dz.device))
-            flow.__dict__["_fold_bwd_table"] = cache
+            tables[level] = cache
         ops.call("rfk_fold_backward_batched", cache[1].data_ptr(), len(rows), st.G.data_ptr(), ops._stream())
     if slow:
         _fold_bwd_legacy(st, slow)
@@ -568,6 +570,21 @@ def _prior_fwd(flow, z, base_condition, obj, tape):
     tape.append(bwd)
 
 
+def _level_done(st, flow, l):
+    """End of level l in the reverse sweep: every parameter gradient of the level (and, the first time, of the prior) is
+    final once the side stream has joined and the level's ActNorm / InvConv folds are chained back; a data-parallel
+    optimizer may start all-reducing them (FlatAdam.attach)."""
+    st.join()
+    _fold_bwd_all(st, flow, l)
+    hook = flow.__dict__.get("_rfk_grad_hook")
+    if hook is not None:
+        if not st.prior_announced:
+            st.prior_announced = True
+            hook("prior")
+        hook(l)
+    st.dz = ops.squeeze2d(st.dz, True)
+
+
 # ----------------------------------------------------------------------------------------
 # ListGlow.log_prob
 # ----------------------------------------------------------------------------------------
@@ -582,7 +599,7 @@ def _log_prob_fwd(flow, x, conds, base_condition, obj0):
     for mod in flow.glow_frame:
         if isinstance(mod, Squeeze2d):
             z = ops.squeeze2d(z, False)
-            tape.append(lambda st: (st.join(), setattr(st, "dz", ops.squeeze2d(st.dz, True))))
+            tape.append(lambda st, l=l: _level_done(st, flow, l))
             cond = ops.f32c(conds[l])
             assert cond.shape[2:4] == z.shape[2:4], "condition and x in affine needs to match"
             cc = cond.shape[1]

@@ -96,11 +96,57 @@ class FlatAdam:
             v.copy_(g)
         return self.flat_g
 
+    def attach(self, flow):
+        """Overlap the gradient all-reduce with the backward sweep of `flow` (a ListGlow whose parameters this optimizer owns):
+        the sweep runs from the prior and the deepest level up to level 1 and tells the optimizer when every gradient of a
+        level is final (Flow/training.py); that level's contiguous slice of the flat gradient buffer is all-reduced
+        asynchronously while the shallower -- and far more expensive -- levels are still being differentiated.  What is
+        left for allreduce_grads() at the end of the step is level 1 and whatever does not belong to the flow."""
+        index = {id(p): i for i, p in enumerate(self.params)}
+        ranges, cur, level = {}, [], -1
+
+        def close(key):
+            ids = sorted(index[id(p)] for p in cur if id(p) in index)
+            if ids and ids == list(range(ids[0], ids[-1] + 1)):
+                last = self.params[ids[-1]]
+                ranges[key] = (self.offsets[ids[0]], self.offsets[ids[-1]] + (last.numel() + 3) // 4 * 4)
+        for m in flow.glow_frame:
+            if type(m).__name__ == "Squeeze2d":
+                if level >= 0:
+                    close(level)
+                level, cur = level + 1, []
+            else:
+                cur.extend(m.parameters())
+        close(level)
+        if getattr(flow, "learn_prior", False):
+            cur = list(flow.prior.parameters())
+            close("prior")
+        self._ranges, self._pending, self._reduced = ranges, [], []
+        flow.__dict__["_rfk_grad_hook"] = self._level_ready
+        return ranges
+
+    def _level_ready(self, key):
+        if self.world <= 1 or key not in getattr(self, "_ranges", {}):
+            return
+        import torch.distributed as dist
+        lo, hi = self._ranges[key]
+        self._pending.append(dist.all_reduce(self.flat_g[lo:hi], group=self.group, async_op=True))
+        self._reduced.append((lo, hi))
+
     def allreduce_grads(self):
-        """Sum over the data-parallel replicas (NCCL over NVLink); the mean's 1/world is folded into the Adam kernel."""
+        """Sum over the data-parallel replicas (NCCL over NVLink); the mean's 1/world is folded into the Adam kernel.
+        Slices already handed to NCCL during the backward sweep (attach()) are skipped and waited for."""
         if self.world > 1:
             import torch.distributed as dist
-            dist.all_reduce(self.flat_g, group=self.group)
+            done = sorted(getattr(self, "_reduced", []))
+            pos = 0
+            for lo, hi in done + [(self.n_pad, self.n_pad)]:
+                if lo > pos:
+                    dist.all_reduce(self.flat_g[pos:lo], group=self.group)
+                pos = max(pos, hi)
+            for w in getattr(self, "_pending", []):
+                w.wait()
+            self._pending, self._reduced = [], []
 
     def apply(self):
         self.step_t += 1.0

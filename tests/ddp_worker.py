@@ -41,6 +41,8 @@ def main():
         lstm = rf.ConvLSTM(6, 8, [3, 3]).train()
         m, lstm = m.to(dev), lstm.to(dev)
         opt = rf.FlatAdam(list(m.parameters()) + list(lstm.parameters()), lr=1e-3, world_size=ws)
+        ranges = opt.attach(m)      # per-level slices all-reduced during the backward sweep
+        assert set(ranges) == {0, 1, "prior"}, ranges
         return m, lstm, opt
 
     g = torch.Generator().manual_seed(7)
