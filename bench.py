@@ -822,12 +822,16 @@ def wl_rfn_train(env, rf, args, smooth=False):
         return loss.detach()
 
     def eager_step_local():   # the instrumented (rank-0 only) pass: same kernels, no collective
-        opt.zero_grad()
-        loss = loss_fn()
-        loss.backward()
-        with torch.no_grad():
-            opt.gather_grads()
-            opt.apply()
+        opt.overlap = False   # ... including the per-level all-reduces the backward sweep would start
+        try:
+            opt.zero_grad()
+            loss = loss_fn()
+            loss.backward()
+            with torch.no_grad():
+                opt.gather_grads()
+                opt.apply()
+        finally:
+            opt.overlap = True
         return loss.detach()
 
     first_loss = float(eager_step())

@@ -28,6 +28,7 @@ class FlatAdam:
         # torch.optim-style handle for LR schedulers (RFN/trainer.py:100,200 write param_groups[0]['lr'])
         self.param_groups = [{"params": self.params, "lr": float(lr), "betas": self.betas, "eps": self.eps}]
         self.group, self.world = process_group, int(world_size)
+        self.overlap = True      # attach(): all-reduce per-level slices during the backward sweep (False: one call at the end)
         self.n = sum(p.numel() for p in self.params)                       # real parameters
         offs, off = [], 0
         for p in self.params:                                               # every tensor starts on a 16-byte boundary
@@ -126,7 +127,7 @@ class FlatAdam:
         return ranges
 
     def _level_ready(self, key):
-        if self.world <= 1 or key not in getattr(self, "_ranges", {}):
+        if self.world <= 1 or not self.overlap or key not in getattr(self, "_ranges", {}):
             return
         import torch.distributed as dist
         lo, hi = self._ranges[key]
