@@ -15,10 +15,10 @@ def reference_dir():
     return None
 
 
-def reference_args(ref, argv=()):
-    """argparse Namespace of main_rfn.py (its defaults = configuration D) with `argv` overrides, without importing the
-    trainer (which needs matplotlib)."""
-    src = open(os.path.join(ref, "main_rfn.py")).read()
+def reference_args(ref, argv=(), script="main_rfn.py"):
+    """argparse Namespace of main_rfn.py (its defaults = configuration D) or another main_*.py with `argv` overrides,
+    without importing the trainer (which needs matplotlib)."""
+    src = open(os.path.join(ref, script)).read()
     head = src[:src.index("if __name__")]
     body = src[src.index("if __name__"):]
     body = body[body.index("\n") + 1:body.index("args = parser.parse_args()")]
