@@ -310,50 +310,31 @@ __global__ void __launch_bounds__(256, 4) coupling_taps_bwd_v4_kernel(const floa
   if (clamp_type == RFK_CLAMP_REALNVP) { a = cs[j]; bb = csh[j]; }
   float acc[6] = {0, 0, 0, 0, 0, 0};
   const long long n = (long long)B * HW4;
-  const int lane = threadIdx.x & 31;
-  // warp-uniform trip count: every lane runs the body (inactive ones with zeros), so the horizontally shifted taps can take
-  // their edge element from the neighbouring lane's 128-bit load by shuffle instead of a second, scalar load
-  for (long long base = blockIdx.x * (long long)blockDim.x + (threadIdx.x & ~31); base < n; base += (long long)gridDim.x * blockDim.x) {
-    const long long idx = base + lane;
-    const bool act = idx < n;
-    const long long idc = act ? idx : n - 1;
-    const int b = (int)(idc / HW4), q = (int)(idc - (long long)b * HW4);
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(idx / HW4), q = (int)(idx - (long long)b * HW4);
     const int y = q / W4, x = (q - y * W4) << 2;
     const float* tb = taps + (long long)b * 9 * C * HW;
     float S[4] = {0, 0, 0, 0}, R[4] = {0, 0, 0, 0};
-    const bool left_in_warp = lane > 0, right_in_warp = lane < 31 && idx + 1 < n;
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
       const int yy = y + ky - 1;
-      const bool rowok = act && yy >= 0 && yy < H;
-      const int yc = min(max(yy, 0), H - 1);
+      if (yy < 0 || yy >= H) continue;
 #pragma unroll
       for (int kx = 0; kx < 3; ++kx) {
-        const float* qq0 = tb + ((long long)((3 * ky + kx) * C + 2 * j) * HW) + yc * W + x;
+        const float* qq0 = tb + ((long long)((3 * ky + kx) * C + 2 * j) * HW) + yy * W + x;
 #pragma unroll
         for (int pr = 0; pr < 2; ++pr) {
           const float* qq = qq0 + pr * HW;
-          float4 c4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-          if (rowok) c4 = __ldg(reinterpret_cast<const float4*>(qq));
+          const float4 c4 = __ldg(reinterpret_cast<const float4*>(qq));
           float v0, v1, v2, v3;
           if (kx == 1) { v0 = c4.x; v1 = c4.y; v2 = c4.z; v3 = c4.w; }
-          else if (kx == 0) {
-            const float nb = __shfl_up_sync(0xffffffffu, c4.w, 1);      // the previous group of the same row (when x > 0)
-            v0 = 0.0f;
-            if (rowok && x > 0) v0 = left_in_warp ? nb : __ldg(qq - 1);
-            v1 = c4.x; v2 = c4.y; v3 = c4.z;
-          } else {
-            const float nb = __shfl_down_sync(0xffffffffu, c4.x, 1);    // the next group of the same row (when x + 4 < W)
-            v3 = 0.0f;
-            if (rowok && x + 4 < W) v3 = right_in_warp ? nb : __ldg(qq + 4);
-            v0 = c4.y; v1 = c4.z; v2 = c4.w;
-          }
+          else if (kx == 0) { v0 = x > 0 ? __ldg(qq - 1) : 0.0f; v1 = c4.x; v2 = c4.y; v3 = c4.z; }
+          else { v0 = c4.y; v1 = c4.z; v2 = c4.w; v3 = x + 4 < W ? __ldg(qq + 4) : 0.0f; }
           float* dst = pr ? R : S;
           dst[0] += v0; dst[1] += v1; dst[2] += v2; dst[3] += v3;
         }
       }
     }
-    if (!act) continue;
     const long long off = ((long long)b * C + half + j) * HW + y * W + x;
     const float4 zo4 = ld_stream(reinterpret_cast<const float4*>(z_out + off));
     const float4 dz4 = *reinterpret_cast<const float4*>(dz + off);
