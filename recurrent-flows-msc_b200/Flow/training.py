@@ -29,10 +29,13 @@ from .glow_modules import BatchNormFlow, Split2d, Squeeze2d, TAP_SPLIT_MAX_N
 
 DGRAD_TAP_SPLIT_MAX_N = 512         # tap-split data gradient when 9*Cin <= this ...
 DGRAD_TAP_SPLIT_MIN_PIXELS = 32768  # ... and the launch has enough pixels to be bandwidth- rather than latency-bound
-# Weight gradients are off the critical path of the sweep (nothing downstream reads them).  For launches too small to fill
-# the GPU (levels 3-5 at RFN sizes: <= 72 pixel tiles on 148 SMs) they go to a second stream and overlap the data-gradient
-# chain; in a captured training step this becomes a parallel branch of the CUDA graph.  RFK_WGRAD_SIDE_STREAM=0 disables.
-WGRAD_SIDE_MAX_PIXELS = int(os.environ.get("RFK_WGRAD_SIDE_MAX_PIXELS", "32768"))
+# Weight gradients are off the critical path of the sweep (nothing downstream reads them): they go to a second stream and
+# overlap the data-gradient chain; in a captured training step this becomes a parallel branch of the CUDA graph.  Measured
+# on the 570-frame step (one B200): levels 3-5 only (<= 72 pixel tiles on 148 SMs) 28.7 ms, + level 3 28.2, + level 2 27.5,
+# all levels 27.1 -- the two kernel families complement each other (the weight gradients are MMA-issue / HBM bound, the
+# data gradients epilogue bound) and fill each other's tail waves.  RFK_WGRAD_SIDE_STREAM=0 disables,
+# RFK_WGRAD_SIDE_MAX_PIXELS limits it to launches of at most that many pixels.
+WGRAD_SIDE_MAX_PIXELS = int(os.environ.get("RFK_WGRAD_SIDE_MAX_PIXELS", str(1 << 40)))
 WGRAD_SIDE_STREAM = os.environ.get("RFK_WGRAD_SIDE_STREAM", "1") != "0"
 # Hidden layers of the coupling network: fold the ActNorm + activation backward into the epilogue of the data-gradient GEMM
 # that produces its input (rfk_conv_gemm_actbwd) and take the ActNorm parameter gradients from the layer's own weight
@@ -87,6 +90,21 @@ class _State:
             if after is not None:
                 after()
         self.side_keep.append((x_act, da, out))
+
+    def side_run(self, pixels, fn, keep):
+        """Run fn() (launches whose results are only needed after the next join) on the side stream."""
+        if not WGRAD_SIDE_STREAM or pixels > WGRAD_SIDE_MAX_PIXELS:
+            fn()
+            return
+        main = torch.cuda.current_stream()
+        if self.side is None:
+            self.side = _side_stream(self.dz.device)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        self.side.wait_event(ev)
+        with torch.cuda.stream(self.side):
+            fn()
+        self.side_keep.append(keep)
 
     def join(self):
         """The main stream waits for the side stream; the tensors it was reading may be released afterwards."""
@@ -401,7 +419,8 @@ def _glowstep_bwd(st, flow, step, x, zo, nn_in, h1, h2, taps, cc, l, xn=None, bn
     # ActNorm folded into the 1x1 mix: y = Wf x + bf
     fold = step._folded_fwd(H * W)
     buf = st.fold_buf(flow, step, C)
-    dWf, dbf = ops.mix1x1_wgrad(x, dz, out=buf)
+    dWf, dbf = buf[:C * C].view(C, C), buf[C * C:C * C + C]
+    st.side_run(B * H * W, lambda: ops.mix1x1_wgrad(x, dz, out=buf), (x, dz, buf))   # only the fold backward at the level's end reads it
     st.dz = ops.mix1x1(dz, fold[3], None)           # Wf^T
     st.folds.append((step, dWf, dbf, H * W, buf))   # chained to the parameters in one batch at the end of the sweep
 
