@@ -42,6 +42,8 @@ class Graphed:
             self.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph):
                 self.out = fn(*self.static_in)
+        from . import ops
+        ops.register_graph(self)
 
     def __call__(self, *inputs):
         _copy_into(self.static_in, list(inputs))
@@ -137,6 +139,8 @@ class GraphedTrainStep:
             self.g_opt = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.g_opt, capture_error_mode="thread_local"), torch.no_grad():
                 optimizer.apply()
+        from . import ops
+        ops.register_graph(self)
         self.mode = "one CUDA graph (forward + backward + all-reduce + Adam)" if self.g_all is not None else \
             "two CUDA graphs (forward + backward | Adam) around an eager all-reduce"
 

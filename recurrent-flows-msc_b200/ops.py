@@ -671,7 +671,21 @@ def workspace(tag, shape, device, dtype=torch.bfloat16):
     return t
 
 
+_LIVE_GRAPHS = []     # weak references to captured graphs (graphs.py): their kernels hold raw pointers into the pools above
+
+
+def register_graph(obj):
+    import weakref
+    _LIVE_GRAPHS.append(weakref.ref(obj))
+
+
 def clear_workspaces():
+    """Release the staging-buffer pool.  Refuses while a captured CUDA graph is alive: its kernels were recorded with raw
+    pointers into these buffers and a replay after the release would read freed memory."""
+    _LIVE_GRAPHS[:] = [r for r in _LIVE_GRAPHS if r() is not None]
+    if _LIVE_GRAPHS:
+        raise _lib.RfkError(f"clear_workspaces(): {len(_LIVE_GRAPHS)} captured graph(s) still reference the workspaces; "
+                            "delete them first")
     _WS.clear()
 
 

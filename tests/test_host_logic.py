@@ -217,3 +217,19 @@ def test_training_entry_points_need_cuda():
         lstm(torch.zeros(1, 1, 4, 4, 4))
     with pytest.raises(RuntimeError):
         rf.FlatAdam(lstm.parameters())
+
+
+def test_clear_workspaces_refuses_while_a_graph_is_alive():
+    """a captured graph holds raw pointers into the workspace pool."""
+    import recurrent_flows_msc_b200 as rf
+
+    class FakeGraph:
+        pass
+    g = FakeGraph()
+    rf.ops.register_graph(g)
+    with pytest.raises(rf._lib.RfkError):
+        rf.ops.clear_workspaces()
+    del g
+    import gc
+    gc.collect()
+    rf.ops.clear_workspaces()
