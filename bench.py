@@ -762,7 +762,8 @@ def roofline_block(env, rf, eager_step, what):
     roofline["step"] = what
     roofline["by_shape"] = by_shape
     roofline["instrumented_step_ms"] = {"sum_of_own_kernels": round(total_ms, 3), "wall_on_stream": round(ev0.elapsed_time(ev1), 3)}
-    roofline["note"] = ("per-launch figures from CUDA events on the launching stream in an instrumented eager step; algorithmic "
+    roofline["note"] = ("per-launch figures from CUDA events on the launching stream in an instrumented, single-stream eager step "
+                        "(the timed step additionally overlaps the weight gradients on a second stream); algorithmic "
                         "bytes = activations in + out + weights; flops = 2*M*N*K on real (unpadded) channels")
     elementwise = []
     for name, by_bytes in kt.elementwise.items():
@@ -822,7 +823,9 @@ def wl_rfn_train(env, rf, args, smooth=False):
         return loss.detach()
 
     def eager_step_local():   # the instrumented (rank-0 only) pass: same kernels, no collective
+        from recurrent_flows_msc_b200.Flow import training as T
         opt.overlap = False   # ... including the per-level all-reduces the backward sweep would start
+        side, T.WGRAD_SIDE_STREAM = T.WGRAD_SIDE_STREAM, False   # one stream: per-kernel event times are not inflated by overlap
         try:
             opt.zero_grad()
             loss = loss_fn()
@@ -832,6 +835,7 @@ def wl_rfn_train(env, rf, args, smooth=False):
                 opt.apply()
         finally:
             opt.overlap = True
+            T.WGRAD_SIDE_STREAM = side
         return loss.detach()
 
     first_loss = float(eager_step())
