@@ -193,6 +193,19 @@ int rfk_conv1x1_taps_fused(const void* act, int B, int H, int W, int act_ld, int
                            const void* w2, int hid, const float* scale2, const float* shift2, int act_fn,
                            const void* w9, int n3, int n3_pad, float* taps, void* stream);
 
+/* The WHOLE coupling network in one kernel (Flow/glow_modules.py:229-240 = net.0 .. net.4 of AffineCoupling):
+ * conv3x3 (or 1x1) -> ActNorm -> activation -> conv1x1 -> ActNorm -> activation -> tap-split conv3x3, with BOTH hidden
+ * tensors kept in tensor memory (CTA pairs, tcgen05 cta_group::2; csrc/coupling_nn.cu).  act: NHWC bf16 network input
+ * [cond | z1] (first cin_pad channels: 32 or a multiple of 64); w1f: bf16 [hid, taps*cin_pad + 16] and w2f: bf16
+ * [hid, hid + 16], both with their ActNorm folded in (rfk_pack_weight_folded: the per-channel scale lives in the weight rows,
+ * the shift rides through the GEMM against a constant-one operand, so the epilogues are activation + rounding only);
+ * w9: bf16 [w9_rows >= n3, hid] in tap-split row order (see rfk_coupling_tail_taps); taps_out: fp32 NCHW [B, n3, H, W],
+ * n3 <= 128.  h1_out / h2_out (both or neither; NHWC bf16, row stride h_ld): the hidden activations as side outputs for a
+ * backward pass -- written once by TMA store, never read back here. */
+int rfk_coupling_nn_fused(const void* act, int B, int H, int W, int act_ld, int cin_pad, int taps, const void* w1f,
+                          int hid, const void* w2f, int act_fn, const void* w9, int n3, int w9_rows, float* taps_out,
+                          void* h1_out, void* h2_out, int h_ld, void* stream);
+
 /* rfk_coupling_tail_taps fused with the 1x1 mix that follows it (forward: the next GlowStep's ActNorm+InvConv;
  * reverse: the same GlowStep's InvConv^-1 + ActNorm^-1): z [B,C,H,W] holds the coupling's input (z1 | not yet updated z2),
  * the updated tensor is formed in shared memory only and y = Wm*(z1 | z2') + bvec is written (plus the optional bf16
@@ -266,6 +279,13 @@ int rfk_gauss_logp_bwd(const float* z, int z_C, int z_off, const float* params, 
  * data gradient, row t*R + j (R = rows/taps), k = co <- W[co, perm[j], taps-1-t]; perm[j] < 0 (or j >= Cin without perm) = zero row. */
 int rfk_pack_weight(const float* src, int N, int Cin, int taps, int mode, const int* perm, int rows, int kp,
                     void* dst, int rows_pad, int ktot, void* stream);
+
+/* Forward conv weight with the ActNorm that follows the conv folded in (Flow/glow_modules.py:140-146: Conv2dNorm =
+ * conv, then ActNorm): dst bf16 [rows_pad, ktot], ktot = taps*kp + 16; row n, k = t*kp + j <- W[n, perm[j], t] * exp(logs[n]);
+ * columns taps*kp and taps*kp + 1 hold the shift bias[n] * exp(logs[n]) split into two bf16 words (hi, lo), the other 14
+ * extra columns are zero.  Operand of rfk_coupling_nn_fused, which multiplies the extra columns by a constant one. */
+int rfk_pack_weight_folded(const float* src, int N, int Cin, int taps, const int* perm, int kp, const float* logs,
+                           const float* bias, void* dst, int rows_pad, int ktot, void* stream);
 
 /* Split-precision ("bf16x3") convolutions: the fp32-accurate mode behind the 1e-3 parity gate (BASELINE.json north_star:
  * "bf16/tf32 ... within rtol 1e-3"; tf32 keeps 11 significant bits, this mode 16).  Every conv operand is the sum of two

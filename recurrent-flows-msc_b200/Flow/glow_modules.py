@@ -9,6 +9,8 @@ Training: ``ListGlow.log_prob`` (and ``ConvLSTM``) run under autograd through a 
 hand-written backward (Flow/training.py, Utils/training.py).  The individual modules below, called on their own
 with autograd recording enabled, refuse to run instead of silently returning tensors without a graph.
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -18,6 +20,8 @@ from ..Utils.modules import ActFun
 
 
 FUSE_CONV2_TAPS = True   # AffineCoupling: fuse net.2 (1x1 conv + ActNorm + act) with the tap-split net.4 when 9*C <= 128
+FUSE_COUPLING_NN = os.environ.get("RFK_FUSE_NN", "1") != "0"   # AffineCoupling: all three convs in ONE kernel (h1 and h2 in tensor memory)
+FUSE_NN_MIN_TILES = 148  # ... when there are at least this many 128-pixel tiles (below that the per-layer split-K launches win)
 TAP_SPLIT_MAX_N = 2304  # AffineCoupling: tap-split form of the last conv up to C = 256 (K drops from 9*256 to 256)
 
 
@@ -254,6 +258,17 @@ class Conv2dNorm(nn.Module):
         """Tap-split form of the data-gradient weights (3x3 convs with few input channels: one GEMM with N = 9*Cin)."""
         return self._cache.get(("wd9", key), (self.conv.weight,), lambda: ops.pack_dgrad_taps_weight(self.conv.weight, out_perm), derived.reg_pack)
 
+    def packed_folded(self, key="id", in_perm=None):
+        """Forward weights with this layer's (initialised) ActNorm folded in: rows scaled by exp(logs), the shift in 16 extra K
+        columns (ops.pack_conv_weight_folded) -- the operand form of the one-kernel coupling network."""
+        an = self.norm_type
+        return self._cache.get(("wf", key), (self.conv.weight, an.logs, an.bias),
+                               lambda: ops.pack_conv_weight_folded(self.conv.weight, an.logs, an.bias, in_perm), derived.reg_pack)
+
+    def foldable(self):
+        """True when packed_folded applies: an ActNorm whose statistics are already known (no pending data-dependent init)."""
+        return self.norm == "actnorm" and self.norm_type.is_initialized() and self.conv.weight.is_cuda
+
     def ready_for_fusion(self):
         """True when the per-channel affine is known without looking at the data (no pending ActNorm init, no
         training-mode batch statistics)."""
@@ -470,10 +485,20 @@ class AffineCoupling(nn.Module):
             if not _ctx.z1_packed:
                 ops.pack_nhwc(z, 0, half, nn_in, cc)
         hp = ops.buf_ld(self.hidden_units)
-        h1 = ops.workspace(("cpl_h1", self.hidden_units), (B, H, W, hp), dev)
-        self.net[0].fused(nn_in, h1, self.non_lin, "cz", self._perm(dev))
-        last, mid = self.net[4], self.net[2]
+        first, last, mid = self.net[0], self.net[4], self.net[2]
         tap_split = last.taps == 9 and 9 * C <= TAP_SPLIT_MAX_N
+        # the whole network in one kernel (csrc/coupling_nn.cu) on the big levels: neither hidden tensor touches HBM
+        if (FUSE_COUPLING_NN and FUSE_CONV2_TAPS and not ops.SPLIT and tap_split and mid.taps == 1 and 9 * C <= 128
+                and self.hidden_units % 64 == 0 and self.hidden_units <= 256 and first.foldable() and mid.foldable()
+                and ops.gemm_m_tiles(B, H, W) >= FUSE_NN_MIN_TILES):
+            w1f, cin_pad1 = first.packed_folded("cz", self._perm(dev))
+            w2f, _ = mid.packed_folded()
+            wgt9, _ = last.packed_taps()
+            taps = ops.workspace(("cpl_taps", C), (B, 9 * C, H, W), dev, torch.float32)
+            ops.coupling_nn_fused(nn_in, cin_pad1, first.taps, w1f, self.hidden_units, w2f, self.non_lin, wgt9, 9 * C, taps)
+            return "taps", taps
+        h1 = ops.workspace(("cpl_h1", self.hidden_units), (B, H, W, hp), dev)
+        first.fused(nn_in, h1, self.non_lin, "cz", self._perm(dev))
         # conv1x1 -> ActNorm -> act -> tap-split conv3x3 in one kernel (h2 stays in tensor memory) when the shapes allow
         b2b = (FUSE_CONV2_TAPS and not ops.SPLIT and tap_split and mid.taps == 1 and ops.pad_to(9 * C, 16) <= 128
                and self.hidden_units % 64 == 0 and self.hidden_units <= 256 and mid.ready_for_fusion())

@@ -24,7 +24,7 @@ import os
 import torch
 
 from .. import ops
-from .glow_modules import BatchNormFlow, Split2d, Squeeze2d, TAP_SPLIT_MAX_N
+from .glow_modules import BatchNormFlow, Split2d, Squeeze2d, TAP_SPLIT_MAX_N, FUSE_NN_MIN_TILES
 
 
 DGRAD_TAP_SPLIT_MAX_N = 512         # tap-split data gradient when 9*Cin <= this ...
@@ -41,6 +41,10 @@ WGRAD_SIDE_STREAM = os.environ.get("RFK_WGRAD_SIDE_STREAM", "1") != "0"
 # that produces its input (rfk_conv_gemm_actbwd) and take the ActNorm parameter gradients from the layer's own weight
 # gradient (rfk_actnorm_param_bwd) instead of a separate 6 B/element pass over the activations.  RFK_FUSE_ACT_BWD=0 disables.
 FUSE_ACT_BWD = os.environ.get("RFK_FUSE_ACT_BWD", "1") != "0"
+
+
+# Training forward of the coupling network as ONE kernel with h1 / h2 as side outputs (RFK_FUSE_NN_TRAIN=0: three launches).
+FUSE_NN_TRAIN = os.environ.get("RFK_FUSE_NN_TRAIN", os.environ.get("RFK_FUSE_NN", "1")) != "0"
 
 
 _SIDE = {}
@@ -356,11 +360,18 @@ def _glowstep_fwd(flow, step, x, ld, nn_template, cc, l, tape):
         Wf, bf = step._folded_fwd(H * W)[:2]
         y = ops.mix1x1(x, Wf, bf, side=nn_in, side_n=half, side_off=cc, logdet=ld, addend=step._dlogdet(H * W), alpha=1.0)
     h1, h2 = _nhwc(B, H, W, hid, dev), _nhwc(B, H, W, hid, dev)
-    net[0].fused(nn_in, h1, act, "cz", aff._perm(dev))
-    net[2].fused(h1, h2, act)
     wgt9, cp = net[4].packed_taps()
     taps = torch.empty(B, 9 * C, H, W, device=dev, dtype=torch.float32)
-    ops.conv_gemm(h2, cp, wgt9, 9 * C, 1, None, None, "none", taps)
+    if (FUSE_NN_TRAIN and not ops.SPLIT and net[2].taps == 1 and 9 * C <= 128 and hid % 64 == 0 and hid <= 256
+            and net[0].foldable() and net[2].foldable() and ops.gemm_m_tiles(B, H, W) >= FUSE_NN_MIN_TILES):
+        # one kernel for the three convolutions (csrc/coupling_nn.cu); h1 / h2 leave as side outputs for the backward and
+        # are not read back by the forward
+        w1f, cp1 = net[0].packed_folded("cz", aff._perm(dev))
+        ops.coupling_nn_fused(nn_in, cp1, net[0].taps, w1f, hid, net[2].packed_folded()[0], act, wgt9, 9 * C, taps, h1, h2)
+    else:
+        net[0].fused(nn_in, h1, act, "cz", aff._perm(dev))
+        net[2].fused(h1, h2, act)
+        ops.conv_gemm(h2, cp, wgt9, 9 * C, 1, None, None, "none", taps)
     ops.coupling_tail_taps(taps, y, *aff.tail_params(), ld, False)
     tape.append(lambda st: _glowstep_bwd(st, flow, step, x, y, nn_in, h1, h2, taps, cc, l, xn, bn_saved))
     return y

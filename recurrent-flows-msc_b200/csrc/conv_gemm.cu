@@ -1014,6 +1014,7 @@ static unsigned long long* g_timeline = nullptr;
 static long long g_timeline_cap = 0;
 static int g_conv_split = 0;   // rfk_set_conv_split: bf16x3 split-precision operands (process-global, set once at start-up)
 int conv_split_mode() { return g_conv_split; }
+unsigned long long* debug_timeline(long long* capacity_ctas) { *capacity_ctas = g_timeline_cap; return g_timeline; }
 
 struct Plan {
   GemmArgs g;

@@ -1435,6 +1435,50 @@ extern "C" int rfk_pack_weight(const float* src, int N, int Cin, int taps, int m
 }
 
 
+// Forward conv weight with the ActNorm that follows it FOLDED IN (rfk_coupling_nn_fused): row n is scaled by
+// s = exp(logs[n]) and 16 extra K columns carry the shift t = bias[n] * s as two bf16 words (t_hi, t_lo, 0 ...), which the
+// kernel multiplies by a constant-one operand: act(ActNorm(conv(x)))[n] = act(sum_k W'[n,k] x[k] + t_hi + t_lo).
+namespace rfk {
+__global__ void __launch_bounds__(256) pack_weight_folded_kernel(const float* __restrict__ src, int N, int Cin, int taps,
+                                                                 const int* __restrict__ perm, int kp,
+                                                                 const float* __restrict__ logs, const float* __restrict__ bias,
+                                                                 __nv_bfloat16* __restrict__ dst, int rows_pad, int ktot) {
+  // no pdl_trigger(): the next conv kernel prefetches these weights BEFORE its dependency wait
+  pdl_wait();
+  const long long total = (long long)rows_pad * ktot;
+  const int kmain = taps * kp;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / ktot), k = (int)(i % ktot);
+    float v = 0.0f;
+    if (r < N) {
+      const float sc = expf(logs[r]);
+      if (k < kmain) {
+        const int t = k / kp, j = k % kp;
+        if (j < Cin) v = src[((long long)r * Cin + (perm ? perm[j] : j)) * taps + t] * sc;
+      } else if (k < kmain + 2) {
+        const float sh = bias[r] * sc;
+        const float hi = __bfloat162float(__float2bfloat16(sh));
+        v = k == kmain ? hi : sh - hi;
+      }
+    }
+    dst[i] = __float2bfloat16(v);
+  }
+}
+}  // namespace rfk
+
+extern "C" int rfk_pack_weight_folded(const float* src, int N, int Cin, int taps, const int* perm, int kp, const float* logs,
+                                      const float* bias, void* dst, int rows_pad, int ktot, void* stream) {
+  using namespace rfk;
+  RFK_REQUIRE(src && dst && logs && bias && N > 0 && Cin > 0 && taps > 0 && N <= rows_pad && kp >= Cin,
+              "rfk_pack_weight_folded: null pointer or bad shape");
+  RFK_REQUIRE(ktot == taps * kp + 16, "rfk_pack_weight_folded: ktot=%d must be taps*kp + 16 = %d", ktot, taps * kp + 16);
+  const long long total = (long long)rows_pad * ktot;
+  RFK_LAUNCH(pack_weight_folded_kernel, stream_grid(total, 256, 8), 256, 0, (cudaStream_t)stream, src, N, Cin, taps, perm, kp,
+             logs, bias, (__nv_bfloat16*)dst, rows_pad, ktot);
+  return check_launch("rfk_pack_weight_folded");
+}
+
+
 // ------------------------------------------------------------------------------------------
 // Gather of nine tap planes stored NHWC bf16 (the output of a tap-split 1x1 GEMM with N = 9*ns):
 //   out[b, j, y, x] = sum_t T[b, y+ky-1, x+kx-1, t*ns + j]      (t = 3*ky + kx; zero outside the image), fp32 NCHW,

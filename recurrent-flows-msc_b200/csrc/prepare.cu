@@ -23,7 +23,8 @@ template <typename T>
 __device__ __forceinline__ T* eptr(const long long* e, int i) { return reinterpret_cast<T*>(static_cast<uintptr_t>(e[i])); }
 
 // ---- weights -------------------------------------------------------------------------------------------------------
-// entry: 0 src f32, 1 dst bf16, 2 perm i32 (0 = none), 3 N, 4 Cin, 5 taps, 6 mode, 7 rows, 8 kp, 9 rows_pad, 10 ktot
+// entry: 0 src f32, 1 dst bf16, 2 perm i32 (0 = none), 3 N, 4 Cin, 5 taps, 6 mode, 7 rows, 8 kp, 9 rows_pad, 10 ktot,
+//        11 logs, 12 bias (mode 4 only: forward weight with the following ActNorm folded in, see rfk_pack_weight_folded)
 __global__ void __launch_bounds__(256) pack_weights_batched_kernel(const long long* __restrict__ table) {
   // no pdl_trigger(): conv kernels prefetch weights BEFORE their dependency wait, so dependents must not start early
   pdl_wait();
@@ -33,12 +34,25 @@ __global__ void __launch_bounds__(256) pack_weights_batched_kernel(const long lo
   const int* __restrict__ perm = eptr<const int>(e, 2);
   const int N = (int)e[3], Cin = (int)e[4], taps = (int)e[5], mode = (int)e[6], rows = (int)e[7], kp = (int)e[8];
   const int rows_pad = (int)e[9], ktot = (int)e[10];
+  const float* __restrict__ logs = eptr<const float>(e, 11);
+  const float* __restrict__ bias = eptr<const float>(e, 12);
   const long long total = (long long)rows_pad * ktot;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int r = (int)(i / ktot), k = (int)(i % ktot);
     float v = 0.0f;
     if (r < rows) {
-      if (mode == 0) {
+      if (mode == 4) {
+        const int kmain = taps * kp;
+        const float sc = expf(logs[r]);
+        if (k < kmain) {
+          const int t = k / kp, j = k % kp;
+          if (j < Cin) v = src[((long long)r * Cin + (perm ? perm[j] : j)) * taps + t] * sc;
+        } else if (k < kmain + 2) {
+          const float sh = bias[r] * sc;
+          const float hi = __bfloat162float(__float2bfloat16(sh));
+          v = k == kmain ? hi : sh - hi;
+        }
+      } else if (mode == 0) {
         const int t = k / kp, j = k % kp;
         if (j < Cin) v = src[((long long)r * Cin + (perm ? perm[j] : j)) * taps + t];
       } else if (mode == 1) {

@@ -215,6 +215,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 EncodeTiledFn encode_fn();
 int conv_split_mode();   // 1: bf16x3 split-precision operands (rfk_set_conv_split)
 int ilog2_ceil(int v);
+unsigned long long* debug_timeline(long long* capacity_ctas);   // rfk_debug_set_timeline's buffer (null = off)
 // NHWC bf16 [B,H,W,ld] as a 4-D {C, W, H, B} map with box {bk, TW, TH, NIMG} (loads zero-fill, stores clip)
 int encode_act_map(CUtensorMap* map, const char* who, const char* what, const void* ptr, int channels, int ld, int B,
                    int H, int W, int TW, int TH, int NIMG, int bk = 64);

@@ -333,6 +333,29 @@ def conv1x1_taps_fused(act, cin_pad, w2, hid, scale2, shift2, act_fn, w9, n3, ta
     return taps
 
 
+def coupling_nn_fused(act, cin_pad, taps_k, w1f, hid, w2f, act_fn, w9, n3, taps, h1=None, h2=None):
+    """The whole coupling network in one kernel: taps = tap-split conv3x3( act(ActNorm(conv1x1( act(ActNorm(conv(act))) ))) ),
+    both hidden tensors in tensor memory.  w1f / w2f: weights with their ActNorm folded in (pack_conv_weight_folded);
+    h1 / h2 (NHWC bf16, optional): side outputs for the backward pass."""
+    _chk(act, torch.bfloat16, "act")
+    _chk(taps, name="taps")
+    B, H, W, ld = act.shape
+    M = B * H * W
+    cin = getattr(w1f, "rfk_cin", cin_pad)
+    store = h1 is not None
+    assert w1f.shape == (hid, taps_k * cin_pad + 16) and w2f.shape == (hid, hid + 16), "folded weights: 16 shift columns behind K"
+    meta = {"flops": 2.0 * M * hid * (taps_k * cin + hid + n3),
+            "flops_padded": 2.0 * M * hid * (taps_k * cin_pad + 16 + hid + 16 + pad_to(n3, 16)),
+            "M": M, "N": hid, "K": taps_k * cin,
+            "bytes": 2.0 * M * cin_pad + 4.0 * M * n3 + 2.0 * (w1f.numel() + w2f.numel() + w9.numel())
+                     + (4.0 * M * hid if store else 0.0)}
+    call("rfk_coupling_nn_fused", act.data_ptr(), B, H, W, ld, cin_pad, taps_k, _chk(w1f, torch.bfloat16).data_ptr(), hid,
+         _chk(w2f, torch.bfloat16).data_ptr(), ACT[act_fn], _chk(w9, torch.bfloat16).data_ptr(), n3, w9.shape[0],
+         taps.data_ptr(), _chk(h1, torch.bfloat16).data_ptr() if store else None,
+         _chk(h2, torch.bfloat16).data_ptr() if store else None, h1.shape[-1] if store else 0, _stream(), meta=meta)
+    return taps
+
+
 def coupling_taps_mix(taps, z, scale, shift, clamp_type, clamp_scale, clamp_shift, cpl_logdet, reverse, Wm, bvec,
                       side=None, side_n=0, side_off=0, logdet=None, addend=None, alpha=1.0):
     """y = Wm * coupling(z; taps) + bvec: the tap gather + coupling update of one step fused with the next 1x1 mix."""
@@ -643,6 +666,32 @@ def _pack_weight(weight, mode, perm, rows, rows_pad, kp, ktot, cin_real):
     out.rfk_cin = cin_real
     if w.data_ptr() == weight.data_ptr():   # packed straight from the parameter's storage: refreshable in place (derived.py)
         out.rfk_pack = [w.data_ptr(), out.data_ptr(), _p(p32), N, Cin, kh * kw, mode, rows, kp, rows_pad, ktot]
+        out.rfk_perm = p32
+    return out, kp
+
+
+def pack_conv_weight_folded(weight, logs, bias, in_perm=None):
+    """[N, Cin, kh, kw] f32 + the ActNorm (logs, bias [1,N,1,1]) that follows the conv -> bf16 [pad16(N), taps*cin_pad + 16]:
+    rows scaled by exp(logs), 16 extra K columns with the shift bias*exp(logs) as (hi, lo) bf16 words
+    (rfk_pack_weight_folded; operand of coupling_nn_fused)."""
+    w = weight.detach()
+    lg, bs = logs.detach(), bias.detach()
+    for t in (w, lg, bs):
+        if t.dtype != torch.float32 or not t.is_contiguous() or not t.is_cuda:
+            raise _lib.RfkError("pack_conv_weight_folded: contiguous fp32 CUDA parameters expected")
+    N, Cin, kh, kw = w.shape
+    kp = cin_pad(Cin)
+    ktot = kh * kw * kp + 16
+    rows_pad = pad_to(N, 16)
+    out = torch.empty(rows_pad, ktot, device=w.device, dtype=torch.bfloat16)
+    p32 = _perm32(in_perm)
+    call("rfk_pack_weight_folded", w.data_ptr(), N, Cin, kh * kw, _p(p32), kp, lg.data_ptr(), bs.data_ptr(), out.data_ptr(),
+         rows_pad, ktot, _stream())
+    out.rfk_cin = Cin
+    if w.data_ptr() == weight.data_ptr() and lg.data_ptr() == logs.data_ptr() and bs.data_ptr() == bias.data_ptr():
+        # refreshable in place after an optimizer step (derived.py; mode 4 of rfk_pack_weights_batched)
+        out.rfk_pack = [w.data_ptr(), out.data_ptr(), _p(p32), N, Cin, kh * kw, 4, N, kp, rows_pad, ktot, lg.data_ptr(),
+                        bs.data_ptr()]
         out.rfk_perm = p32
     return out, kp
 
