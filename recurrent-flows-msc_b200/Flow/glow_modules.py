@@ -21,7 +21,7 @@ from ..Utils.modules import ActFun
 
 FUSE_CONV2_TAPS = True   # AffineCoupling: fuse net.2 (1x1 conv + ActNorm + act) with the tap-split net.4 when 9*C <= 128
 FUSE_COUPLING_NN = os.environ.get("RFK_FUSE_NN", "1") != "0"   # AffineCoupling: all three convs in ONE kernel (h1 and h2 in tensor memory)
-FUSE_NN_MIN_TILES = 148  # ... when there are at least this many 128-pixel tiles (below that the per-layer split-K launches win)
+FUSE_NN_MIN_TILES = int(os.environ.get("RFK_FUSE_NN_MIN_TILES", "48"))  # ... when there are at least this many 128-pixel tiles (below that the per-layer split-K launches win)
 TAP_SPLIT_MAX_N = 2304  # AffineCoupling: tap-split form of the last conv up to C = 256 (K drops from 9*256 to 256)
 
 

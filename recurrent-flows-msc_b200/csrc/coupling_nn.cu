@@ -41,7 +41,7 @@ constexpr int kNNThreads = 640;   // warp 0: TMA, warp 1: MMA (leader CTA only),
 constexpr int kNNEpiWarp0 = 4;
 constexpr int kNNEpiWarps = 16;
 constexpr int kNNSmemLimit = 232448;
-constexpr int kNNStoreSlice = 32 * 32;   // one warp's staging buffer of a side output: 32 pixels x 16 channels bf16
+constexpr int kNNStoreSlice = 32 * 32;   // staging of the side outputs per epilogue warp: four warps share a 32 pixels x 64 channels block
 
 struct NNArgs {
   int B, H, W;
@@ -309,7 +309,9 @@ coupling_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         }
         umma_commit_2sm(acc_full(1));
         if (stp) stp[4] = (unsigned)clock();                       // GEMM2 issued + committed
-        // ---- GEMM3 -> R0 + 128, A = bf16 h2 (compact, R0 columns [0, hid/2))
+        // ---- GEMM3 -> R0 + 128, A = bf16 h2 (compact, R0 columns [0, hid/2)).  (Two accumulators fed by alternate K steps or by
+        // alternate chunks were tried -- a dependent MMA starts ~160 cycles after its predecessor whatever N is -- and left the
+        // kernel time unchanged: the chunks arrive at the pace of epilogue 2.)
         accumulate = 0;
         for (int kc = 0; kc < k2chunks; ++kc) {
           { NN_CNT_BEGIN(); mbar_wait(a3_ready(kc), par); if (kc == 0) NN_CNT_END(c_a3_0); else NN_CNT_END(c_a3_n); }
@@ -342,9 +344,7 @@ coupling_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const int ppi_log2 = g.tw_log2 + g.th_log2;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     const long long plane = (long long)g.H * g.W;
-    const uint32_t stg = stg_base + (uint32_t)(warp - kNNEpiWarp0) * kNNStoreSlice;   // side outputs: this warp's staging buffer
-    const uint32_t stg_lane = (uint32_t)lane * 32u;
-    const uint32_t sw = (uint32_t)(lane >> 2) & 1u;                                    // SWIZZLE_32B: address bit 4 ^= bit 7
+    const uint32_t qstg = stg_base + (uint32_t)q * 4096u;   // side outputs: this quadrant's staging block (32 pixels x 64 channels)
     const int r0row = q * 32;
     auto arrive_leader = [&](uint32_t bar) {
       if (rank == 0) mbar_arrive(bar);
@@ -367,20 +367,17 @@ coupling_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       const int sub_y = y0 + ((r0row >> g.tw_log2) & ((1 << g.th_log2) - 1));
       const int sub_n = n0 + (r0row >> ppi_log2);
       // one activation epilogue: accumulator `src` -> activation -> bf16 at `dst` (8 columns per 16 channels); a 64-channel
-      // chunk is announced as soon as this warp's 16 channels of it are in place.  Side outputs: the packed words stay in
-      // registers and go out AFTER the loop (staging buffer with swizzled 32-byte rows -> TMA store), i.e. in the time this
-      // warp would otherwise spend waiting for the next GEMM to finish.
+      // chunk is announced as soon as this warp's 16 channels of it are in place.
       auto convert = [&](uint32_t src, uint32_t dst, bool in_place, int bar0, const CUtensorMap* map) {
-        uint32_t keep[4][8];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const int c0 = 16 * part + 64 * u;
           if (c0 < g.hid) {
-            uint32_t v[16];
+            uint32_t v[16], pk[8];
             tmem_ld16_nowait(src + c0, v);
             tmem_wait_ld();
-            act_pack(v, g.act_fn, keep[u]);
-            tmem_st8(dst + (uint32_t)(in_place ? c0 : c0 >> 1), keep[u]);
+            act_pack(v, g.act_fn, pk);
+            tmem_st8(dst + (uint32_t)(in_place ? c0 : c0 >> 1), pk);
             if (in_place && c0 == 0) {   // the constant-one columns of GEMM2's shift MMA: channels (1, 1, 0, ... 0) in the first gap
               const uint32_t one[8] = {0x3F803F80u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
               tmem_st8(dst + 8u, one);
@@ -392,22 +389,31 @@ coupling_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           }
         }
         if (kStore) {
+          // Side outputs, AFTER the loop (i.e. in the time this warp would otherwise wait for the next GEMM): the bf16 words are
+          // read back from tensor memory; the four warps of a quadrant hold the four 16-channel pieces of the same 32 pixels x
+          // 64 channels, assemble 128-byte rows in the quadrant's staging block (128-byte swizzle) and ONE TMA store moves it.
+          // The quadrant barriers also make the read-back safe: tensor-memory lanes belong to a quadrant, and a warp can only
+          // move on to overwrite them (next epilogue) after all four have passed the last barrier, i.e. finished reading.
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            const int c0 = 16 * part + 64 * u;
-            if (c0 < g.hid) {
-              if (lane == 0) bulk_wait_read0();   // this warp's previous TMA store has finished reading the buffer
-              __syncwarp();
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + stg_lane + (sw << 4)), "r"(keep[u][0]),
-                           "r"(keep[u][1]), "r"(keep[u][2]), "r"(keep[u][3])
+            if (64 * u < g.hid) {
+              const int c0 = 16 * part + 64 * u;
+              uint32_t w[8];
+              tmem_ld8_nowait(dst + (uint32_t)(in_place ? c0 : c0 >> 1), w);
+              tmem_wait_ld();
+              if (part == 0 && lane == 0) bulk_wait_read0();   // the quadrant's previous store has finished reading the block
+              named_bar(1 + q, 128);
+              const uint32_t rowa = qstg + (uint32_t)lane * 128u, x7 = (uint32_t)lane & 7u;
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowa + ((((uint32_t)(2 * part)) ^ x7) << 4)), "r"(w[0]),
+                           "r"(w[1]), "r"(w[2]), "r"(w[3])
                            : "memory");
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + stg_lane + ((sw ^ 1u) << 4)), "r"(keep[u][4]),
-                           "r"(keep[u][5]), "r"(keep[u][6]), "r"(keep[u][7])
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowa + ((((uint32_t)(2 * part + 1)) ^ x7) << 4)),
+                           "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
                            : "memory");
               fence_async_smem();
-              __syncwarp();
-              if (lane == 0 && mt < g.m_tiles) {
-                tma_store_4d(map, stg, c0, sub_x, sub_y, sub_n);
+              named_bar(1 + q, 128);
+              if (part == 0 && lane == 0 && mt < g.m_tiles) {
+                tma_store_4d(map, qstg, 64 * u, sub_x, sub_y, sub_n);
                 bulk_commit();
               }
             }
@@ -437,20 +443,31 @@ coupling_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       tc_fence_after();
       c_t = dbg ? (unsigned)clock() : 0u;
       if (stp) stp[12] = c_t;                                      // GEMM3 accumulator seen
-      for (int c0 = 16 * part; c0 < g.n3_pad; c0 += 64) {
-        if (c0 >= g.n3) break;  // warp-uniform
+      // this warp's (at most two) 16-plane slices; the accumulator is handed back as soon as it is in registers, before the
+      // global stores go out
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int c0 = 16 * part + 64 * i;
         uint32_t r[16];
-        { NN_CNT_BEGIN(); tmem_ld16_nowait(r0 + 128u + c0, r); tmem_wait_ld(); NN_CNT_END(c_e3ld); }
-        if (valid) {
+        if (c0 < g.n3) {   // warp-uniform
+          NN_CNT_BEGIN();
+          tmem_ld16_nowait(r0 + 128u + c0, r);
+          tmem_wait_ld();
+          NN_CNT_END(c_e3ld);
+        }
+        if (i == (g.n3_pad > 64 ? 1 : 0)) {   // nothing left to drain
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) arrive_leader(d3_empty);
+        }
+        if (c0 < g.n3 && valid) {
           float* dst = g.taps_out + (((long long)b * g.n3 + c0) * g.H + y) * g.W + x;
 #pragma unroll
           for (int j = 0; j < 16; ++j)
             if (c0 + j < g.n3) dst[j * plane] = __uint_as_float(r[j]);
         }
+        if (g.n3_pad <= 64) break;
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) arrive_leader(d3_empty);
       if (dbg) c_e3 += (unsigned)clock() - c_t;
       if (stp) stp[13] = (unsigned)clock();                        // epilogue 3 done
     }
@@ -459,7 +476,7 @@ coupling_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       d[8] = c_w0; d[9] = c_e1; d[10] = c_w1; d[11] = c_e2; d[12] = c_w2; d[13] = c_e3; d[14] = c_e3ld;
       d[15] = (unsigned)clock() - c_start;
     }
-    if (kStore && lane == 0) bulk_wait0();   // outstanding TMA stores still read shared memory
+    if (kStore && part == 0 && lane == 0) bulk_wait0();   // outstanding TMA stores still read shared memory
   }
 
   tc_fence_before();
@@ -576,24 +593,12 @@ extern "C" int rfk_coupling_nn_fused(const void* act, int B, int H, int W, int a
   tmH1 = tmA;
   tmH2 = tmA;
   if (store_h) {
-    // the store maps' box is ONE EPILOGUE WARP's 32 pixel rows x 16 channels (32-byte rows, SWIZZLE_32B)
+    // the store maps' box is one QUADRANT's 32 pixel rows x 64 channels (128-byte rows, SWIZZLE_128B)
     const int sx = std::min(TW, 32), sy = std::min(TH, 32 / sx), sn = 32 / (sx * sy);
-    EncodeTiledFn enc = encode_fn();
-    RFK_REQUIRE(enc, "%s: cuTensorMapEncodeTiled is unavailable (no CUDA driver?)", who);
-    void* outs[2] = {h1_out, h2_out};
-    CUtensorMap* maps[2] = {&tmH1, &tmH2};
-    for (int i = 0; i < 2; ++i) {
-      cuuint64_t dims[4] = {(cuuint64_t)hid, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-      cuuint64_t strides[3] = {(cuuint64_t)h_ld * 2, (cuuint64_t)W * h_ld * 2, (cuuint64_t)H * W * h_ld * 2};
-      cuuint32_t box[4] = {16u, (cuuint32_t)sx, (cuuint32_t)sy, (cuuint32_t)sn};
-      cuuint32_t ones[4] = {1, 1, 1, 1};
-      CUresult r = enc(maps[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, outs[i], dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                       CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-      if (r != CUDA_SUCCESS) {
-        set_error("%s: cuTensorMapEncodeTiled(h%d) failed with CUresult %d (B=%d H=%d W=%d ld=%d)", who, i + 1, (int)r, B, H, W, h_ld);
-        return RFK_ECUDA;
-      }
-    }
+    rc = encode_act_map(&tmH1, who, "h1", h1_out, hid, h_ld, B, H, W, sx, sy, sn, 64);
+    if (rc) return rc;
+    rc = encode_act_map(&tmH2, who, "h2", h2_out, hid, h_ld, B, H, W, sx, sy, sn, 64);
+    if (rc) return rc;
   }
   using KernelFn = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap,
                             NNArgs);
