@@ -43,6 +43,8 @@ WGRAD_SIDE_STREAM = os.environ.get("RFK_WGRAD_SIDE_STREAM", "1") != "0"
 FUSE_ACT_BWD = os.environ.get("RFK_FUSE_ACT_BWD", "1") != "0"
 
 
+# Recompute mode for every flow that does not set flow.recompute itself (see _glowstep_fwd).
+RECOMPUTE = os.environ.get("RFK_RECOMPUTE", "0") == "1"
 # Training forward of the coupling network as ONE kernel with h1 / h2 as side outputs (RFK_FUSE_NN_TRAIN=0: three launches).
 FUSE_NN_TRAIN = os.environ.get("RFK_FUSE_NN_TRAIN", os.environ.get("RFK_FUSE_NN", "1")) != "0"
 
@@ -71,6 +73,7 @@ class _State:
         self.direct = set()
         self.folds = []
         self.prior_announced = False
+        self.recomputed = 0       # GlowSteps whose activations were regenerated in this sweep (recompute mode)
         self.side = None          # second stream for small weight-gradient launches
         self.side_keep = []       # tensors the side stream still reads (kept alive until the join)
 
@@ -359,29 +362,58 @@ def _glowstep_fwd(flow, step, x, ld, nn_template, cc, l, tape):
         step.norm.maybe_initialize(x)
         Wf, bf = step._folded_fwd(H * W)[:2]
         y = ops.mix1x1(x, Wf, bf, side=nn_in, side_n=half, side_off=cc, logdet=ld, addend=step._dlogdet(H * W), alpha=1.0)
-    h1, h2 = _nhwc(B, H, W, hid, dev), _nhwc(B, H, W, hid, dev)
+    # Recompute mode (flow.recompute / RFK_RECOMPUTE=1): the hidden tensors are NOT kept.  The coupling leaves
+    # z1 = y[:, :C/2] unchanged, so the network's input is part of the step's OUTPUT: the backward regenerates
+    # [cond | z1] -> h1, h2, tap planes from y with the same kernels (bit-identical), two steps at a time at most.  Only the
+    # flow tensors x, y (C channels) stay on the tape: 10.8 GB -> 2.1 GB at the 570-frame workload.  Needs ActNorms whose
+    # statistics are settled (a data-dependent init or batch-norm statistics must not run twice).
+    recompute = (getattr(flow, "recompute", RECOMPUTE) and bn_saved is None and net[0].foldable() and net[2].foldable())
+    h1, h2, taps = _coupling_nn(aff, nn_in, C, keep=not recompute)
+    ops.coupling_tail_taps(taps, y, *aff.tail_params(), ld, False)
+    if recompute:
+        tape.append(lambda st: _glowstep_bwd(st, flow, step, x, y, None, None, None, None, cc, l, nn_template=nn_template))
+    else:
+        tape.append(lambda st: _glowstep_bwd(st, flow, step, x, y, nn_in, h1, h2, taps, cc, l, xn, bn_saved))
+    return y
+
+
+def _coupling_nn(aff, nn_in, C, keep):
+    """The coupling network on the staged input: returns (h1, h2, taps); h1 / h2 are None when they were not asked for
+    (keep=False) and the one-kernel path, which never materialises them, applies."""
+    net = aff.net
+    B, H, W, _ = nn_in.shape
+    hid, act, dev = aff.hidden_units, aff.non_lin, nn_in.device
     wgt9, cp = net[4].packed_taps()
     taps = torch.empty(B, 9 * C, H, W, device=dev, dtype=torch.float32)
     if (FUSE_NN_TRAIN and not ops.SPLIT and net[2].taps == 1 and 9 * C <= 128 and hid % 64 == 0 and hid <= 256
             and net[0].foldable() and net[2].foldable() and ops.gemm_m_tiles(B, H, W) >= FUSE_NN_MIN_TILES):
         # one kernel for the three convolutions (csrc/coupling_nn.cu); h1 / h2 leave as side outputs for the backward and
         # are not read back by the forward
+        h1, h2 = (_nhwc(B, H, W, hid, dev), _nhwc(B, H, W, hid, dev)) if keep else (None, None)
         w1f, cp1 = net[0].packed_folded("cz", aff._perm(dev))
         ops.coupling_nn_fused(nn_in, cp1, net[0].taps, w1f, hid, net[2].packed_folded()[0], act, wgt9, 9 * C, taps, h1, h2)
-    else:
-        net[0].fused(nn_in, h1, act, "cz", aff._perm(dev))
-        net[2].fused(h1, h2, act)
-        ops.conv_gemm(h2, cp, wgt9, 9 * C, 1, None, None, "none", taps)
-    ops.coupling_tail_taps(taps, y, *aff.tail_params(), ld, False)
-    tape.append(lambda st: _glowstep_bwd(st, flow, step, x, y, nn_in, h1, h2, taps, cc, l, xn, bn_saved))
-    return y
+        return h1, h2, taps
+    h1, h2 = _nhwc(B, H, W, hid, dev), _nhwc(B, H, W, hid, dev)
+    net[0].fused(nn_in, h1, act, "cz", aff._perm(dev))
+    net[2].fused(h1, h2, act)
+    ops.conv_gemm(h2, cp, wgt9, 9 * C, 1, None, None, "none", taps)
+    return h1, h2, taps
 
 
-def _glowstep_bwd(st, flow, step, x, zo, nn_in, h1, h2, taps, cc, l, xn=None, bn_saved=None):
+def _glowstep_bwd(st, flow, step, x, zo, nn_in, h1, h2, taps, cc, l, xn=None, bn_saved=None, nn_template=None):
     aff = step.affine
     net = aff.net
     B, C, H, W = zo.shape
     half, hid, act, dev = C // 2, aff.hidden_units, aff.non_lin, zo.device
+    if taps is None:
+        # recompute mode: regenerate the network's activations from the step's output.  At most two steps' worth is alive: the
+        # side stream's weight gradients of the step before last must be done before their inputs are released.
+        st.recomputed += 1
+        if st.recomputed % 2 == 0:
+            st.join()
+        nn_in = nn_template.clone()
+        ops.pack_nhwc(zo, 0, half, nn_in, cc)
+        h1, h2, taps = _coupling_nn(aff, nn_in, C, keep=True)
     dz = st.dz
     scale, shift, clamp, cs, csh = aff.tail_params()
     last = net[4]
