@@ -280,12 +280,16 @@ int rfk_gauss_logp_bwd(const float* z, int z_C, int z_off, const float* params, 
 int rfk_pack_weight(const float* src, int N, int Cin, int taps, int mode, const int* perm, int rows, int kp,
                     void* dst, int rows_pad, int ktot, void* stream);
 
-/* Forward conv weight with the ActNorm that follows the conv folded in (Flow/glow_modules.py:140-146: Conv2dNorm =
- * conv, then ActNorm): dst bf16 [rows_pad, ktot], ktot = taps*kp + 16; row n, k = t*kp + j <- W[n, perm[j], t] * exp(logs[n]);
- * columns taps*kp and taps*kp + 1 hold the shift bias[n] * exp(logs[n]) split into two bf16 words (hi, lo), the other 14
- * extra columns are zero.  Operand of rfk_coupling_nn_fused, which multiplies the extra columns by a constant one. */
-int rfk_pack_weight_folded(const float* src, int N, int Cin, int taps, const int* perm, int kp, const float* logs,
-                           const float* bias, void* dst, int rows_pad, int ktot, void* stream);
+/* Conv weights with an ActNorm folded in (Flow/glow_modules.py:140-146: Conv2dNorm = conv, then ActNorm).
+ * mode 4 -- forward weight + the ActNorm that FOLLOWS the conv: dst bf16 [rows_pad, ktot], ktot = taps*kp + 16, rows = N;
+ *   row n, k = t*kp + j <- W[n, perm[j], t] * exp(logs[n]); columns taps*kp and taps*kp + 1 hold the shift
+ *   bias[n] * exp(logs[n]) split into two bf16 words (hi, lo), the other 14 extra columns are zero.  Operand of
+ *   rfk_coupling_nn_fused, which multiplies the extra columns by a constant one.
+ * mode 5 -- data-gradient weight (rfk_pack_weight mode 1 without perm) + the ActNorm that PRODUCED the conv's input: row r
+ *   (rows = Cin), k = t*kp + co <- W[co, r, taps-1-t] * exp(logs[r]); ktot = taps*kp, bias unused.  Operand of
+ *   rfk_conv_gemm_actbwd called with scale = NULL. */
+int rfk_pack_weight_folded(const float* src, int N, int Cin, int taps, int mode, const int* perm, int rows, int kp,
+                           const float* logs, const float* bias, void* dst, int rows_pad, int ktot, void* stream);
 
 /* Split-precision ("bf16x3") convolutions: the fp32-accurate mode behind the 1e-3 parity gate (BASELINE.json north_star:
  * "bf16/tf32 ... within rtol 1e-3"; tf32 keeps 11 significant bits, this mode 16).  Every conv operand is the sum of two

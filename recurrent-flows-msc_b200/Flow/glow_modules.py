@@ -196,6 +196,12 @@ class Conv2dZeros(nn.Module):
         """Weights of the data-gradient convolution (flipped taps, in/out channels swapped), rows in staging order."""
         return self._cache.get(("wd", key), (self.conv.weight,), lambda: ops.pack_dgrad_weight(self.conv.weight, out_perm), derived.reg_pack)
 
+    def packed_dgrad_scaled(self, prev_logs):
+        """Data-gradient weights with the scale of the ActNorm that produced this conv's input folded into the rows
+        (ops.pack_dgrad_weight_scaled): conv_gemm_actbwd then needs no per-channel factor in its epilogue."""
+        return self._cache.get(("wds", prev_logs.data_ptr()), (self.conv.weight, prev_logs),
+                               lambda: ops.pack_dgrad_weight_scaled(self.conv.weight, prev_logs), derived.reg_pack)
+
     def packed_dgrad_taps(self, key="id", out_perm=None):
         """Tap-split form of the data-gradient weights (3x3 convs with few input channels: one GEMM with N = 9*Cin)."""
         return self._cache.get(("wd9", key), (self.conv.weight,), lambda: ops.pack_dgrad_taps_weight(self.conv.weight, out_perm), derived.reg_pack)
@@ -253,6 +259,12 @@ class Conv2dNorm(nn.Module):
     def packed_dgrad(self, key="id", out_perm=None):
         """Weights of the data-gradient convolution (flipped taps, in/out channels swapped), rows in staging order."""
         return self._cache.get(("wd", key), (self.conv.weight,), lambda: ops.pack_dgrad_weight(self.conv.weight, out_perm), derived.reg_pack)
+
+    def packed_dgrad_scaled(self, prev_logs):
+        """Data-gradient weights with the scale of the ActNorm that produced this conv's input folded into the rows
+        (ops.pack_dgrad_weight_scaled): conv_gemm_actbwd then needs no per-channel factor in its epilogue."""
+        return self._cache.get(("wds", prev_logs.data_ptr()), (self.conv.weight, prev_logs),
+                               lambda: ops.pack_dgrad_weight_scaled(self.conv.weight, prev_logs), derived.reg_pack)
 
     def packed_dgrad_taps(self, key="id", out_perm=None):
         """Tap-split form of the data-gradient weights (3x3 convs with few input channels: one GEMM with N = 9*Cin)."""

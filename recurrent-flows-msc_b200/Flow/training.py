@@ -43,6 +43,9 @@ WGRAD_SIDE_STREAM = os.environ.get("RFK_WGRAD_SIDE_STREAM", "1") != "0"
 FUSE_ACT_BWD = os.environ.get("RFK_FUSE_ACT_BWD", "1") != "0"
 
 
+# e^{logs} of the ActNorm below folded into the data-gradient weight rows (conv_gemm_actbwd with scale = None).  Measured neutral
+# (level 1: 160 / 166 us against 154 / 159 us -- that epilogue is not bound by its per-channel loads), so it stays opt-in.
+FOLD_ACTBWD_SCALE = os.environ.get("RFK_FOLD_ACTBWD_SCALE", "0") == "1"
 # Recompute mode for every flow that does not set flow.recompute itself (see _glowstep_fwd).
 RECOMPUTE = os.environ.get("RFK_RECOMPUTE", "0") == "1"
 # Training forward of the coupling network as ONE kernel with h1 / h2 as side outputs (RFK_FUSE_NN_TRAIN=0: three launches).
@@ -212,8 +215,15 @@ def _dgrad_actbwd(st, conv_mod, da_in, prev_mod, h, act_fn):
     returns (da, colsum) = gradient w.r.t. prev_mod's raw conv output (bf16 NHWC) and its per-channel sums."""
     B, H, W, _ = da_in.shape
     n = prev_mod.conv.out_channels
-    wd, cp = conv_mod.packed_dgrad("id", None)
-    scale, _ = prev_mod.norm_type.affine()
+    an = prev_mod.norm_type
+    if FOLD_ACTBWD_SCALE and conv_mod.conv.weight.is_cuda and an.logs.dtype == torch.float32:
+        # e^{logs} of the ActNorm below rides in the weight rows: the epilogue (bound by its shared-memory loads) reads no
+        # per-channel factor
+        wd, cp = conv_mod.packed_dgrad_scaled(an.logs)
+        scale = None
+    else:
+        wd, cp = conv_mod.packed_dgrad("id", None)
+        scale, _ = an.affine()
     da = torch.empty(B, H, W, n, device=da_in.device, dtype=torch.bfloat16)
     colsum = ops._zeros(n, da_in.device)
     ops.conv_gemm_actbwd(da_in, cp, wd, n, conv_mod.taps, scale, act_fn, h, da, colsum)

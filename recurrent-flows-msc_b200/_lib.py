@@ -38,8 +38,8 @@ SIGNATURES = {
                                c_void_p, c_int, c_int, c_void_p, c_void_p],
     "rfk_coupling_nn_fused": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int,
                               c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p],
-    "rfk_pack_weight_folded": [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int,
-                               c_void_p],
+    "rfk_pack_weight_folded": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                               c_int, c_int, c_void_p],
     "rfk_coupling_taps_mix": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
                               c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                               c_void_p, c_void_p, c_float, c_void_p],

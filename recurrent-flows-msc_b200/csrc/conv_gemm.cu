@@ -354,9 +354,10 @@ __device__ __forceinline__ void actbwd_block(const GemmArgs& g, const ActBwdEpi&
     tmem_wait_ld();
     float d[32];
     const float4* sc4 = reinterpret_cast<const float4*>(ss + c0 + pass * 32);
+    const bool has_scale = g.scale != nullptr;   // null: the ActNorm scale is folded into the weight rows (pack mode 5)
 #pragma unroll
     for (int q4 = 0; q4 < 8; ++q4) {
-      const float4 s4 = sc4[q4];
+      const float4 s4 = has_scale ? sc4[q4] : make_float4(1.0f, 1.0f, 1.0f, 1.0f);
       const float2 ha = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hw[2 * q4]));
       const float2 hb = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hw[2 * q4 + 1]));
       float m0, m1, m2, m3;
@@ -1340,7 +1341,7 @@ extern "C" int rfk_conv_gemm(const void* act, int B, int H, int W, int act_ld, i
 extern "C" int rfk_conv_gemm_actbwd(const void* act, int B, int H, int W, int act_ld, int cin_pad, const void* wgt, int n,
                                     int n_pad, int taps, const float* scale, int act_fn, const void* h, int h_ld, void* out,
                                     int out_ld, float* colsum, void* stream) {
-  RFK_REQUIRE(out && h && scale && colsum, "rfk_conv_gemm_actbwd: null pointer");
+  RFK_REQUIRE(out && h && colsum, "rfk_conv_gemm_actbwd: null pointer");
   RFK_REQUIRE(act_fn >= 0 && act_fn <= 2, "rfk_conv_gemm_actbwd: bad act_fn %d", act_fn);
   RFK_REQUIRE(!g_conv_split, "rfk_conv_gemm_actbwd: training kernels do not run in split-precision mode");
   RFK_REQUIRE(n == n_pad && n % 64 == 0 && n <= 512, "rfk_conv_gemm_actbwd: n=%d must be a multiple of 64 (<= 512) without padding", n);

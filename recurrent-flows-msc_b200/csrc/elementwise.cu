@@ -1435,12 +1435,16 @@ extern "C" int rfk_pack_weight(const float* src, int N, int Cin, int taps, int m
 }
 
 
-// Forward conv weight with the ActNorm that follows it FOLDED IN (rfk_coupling_nn_fused): row n is scaled by
-// s = exp(logs[n]) and 16 extra K columns carry the shift t = bias[n] * s as two bf16 words (t_hi, t_lo, 0 ...), which the
-// kernel multiplies by a constant-one operand: act(ActNorm(conv(x)))[n] = act(sum_k W'[n,k] x[k] + t_hi + t_lo).
+// Conv weights with an ActNorm FOLDED IN.
+//   mode 4 (forward, operand of rfk_coupling_nn_fused): the ActNorm that FOLLOWS the conv: row n is scaled by
+//     s = exp(logs[n]) and 16 extra K columns carry the shift t = bias[n] * s as two bf16 words (t_hi, t_lo, 0 ...), which the
+//     kernel multiplies by a constant-one operand: act(ActNorm(conv(x)))[n] = act(sum_k W'[n,k] x[k] + t_hi + t_lo).
+//   mode 5 (data gradient, operand of rfk_conv_gemm_actbwd with scale = NULL): the ActNorm that PRODUCED the conv's input:
+//     row r (the dgrad's output channel = the forward conv's input channel) is scaled by exp(logs[r]), so that the
+//     epilogue's da = dh * act'(h) * e^{logs} needs no per-channel factor.
 namespace rfk {
-__global__ void __launch_bounds__(256) pack_weight_folded_kernel(const float* __restrict__ src, int N, int Cin, int taps,
-                                                                 const int* __restrict__ perm, int kp,
+__global__ void __launch_bounds__(256) pack_weight_folded_kernel(const float* __restrict__ src, int N, int Cin, int taps, int mode,
+                                                                 const int* __restrict__ perm, int rows, int kp,
                                                                  const float* __restrict__ logs, const float* __restrict__ bias,
                                                                  __nv_bfloat16* __restrict__ dst, int rows_pad, int ktot) {
   // no pdl_trigger(): the next conv kernel prefetches these weights BEFORE its dependency wait
@@ -1450,9 +1454,12 @@ __global__ void __launch_bounds__(256) pack_weight_folded_kernel(const float* __
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int r = (int)(i / ktot), k = (int)(i % ktot);
     float v = 0.0f;
-    if (r < N) {
+    if (r < rows) {
       const float sc = expf(logs[r]);
-      if (k < kmain) {
+      if (mode == 5) {
+        const int t = k / kp, co = k % kp;
+        if (co < N) v = src[((long long)co * Cin + (perm ? perm[r] : r)) * taps + (taps - 1 - t)] * sc;
+      } else if (k < kmain) {
         const int t = k / kp, j = k % kp;
         if (j < Cin) v = src[((long long)r * Cin + (perm ? perm[j] : j)) * taps + t] * sc;
       } else if (k < kmain + 2) {
@@ -1466,15 +1473,21 @@ __global__ void __launch_bounds__(256) pack_weight_folded_kernel(const float* __
 }
 }  // namespace rfk
 
-extern "C" int rfk_pack_weight_folded(const float* src, int N, int Cin, int taps, const int* perm, int kp, const float* logs,
-                                      const float* bias, void* dst, int rows_pad, int ktot, void* stream) {
+extern "C" int rfk_pack_weight_folded(const float* src, int N, int Cin, int taps, int mode, const int* perm, int rows, int kp,
+                                      const float* logs, const float* bias, void* dst, int rows_pad, int ktot, void* stream) {
   using namespace rfk;
-  RFK_REQUIRE(src && dst && logs && bias && N > 0 && Cin > 0 && taps > 0 && N <= rows_pad && kp >= Cin,
+  RFK_REQUIRE(src && dst && logs && N > 0 && Cin > 0 && taps > 0 && rows > 0 && rows <= rows_pad,
               "rfk_pack_weight_folded: null pointer or bad shape");
-  RFK_REQUIRE(ktot == taps * kp + 16, "rfk_pack_weight_folded: ktot=%d must be taps*kp + 16 = %d", ktot, taps * kp + 16);
+  RFK_REQUIRE(mode == 4 || mode == 5, "rfk_pack_weight_folded: mode %d (4 = forward + following ActNorm, 5 = data gradient + preceding ActNorm)", mode);
+  if (mode == 4)
+    RFK_REQUIRE(bias && rows == N && kp >= Cin && ktot == taps * kp + 16,
+                "rfk_pack_weight_folded: mode 4 needs bias, rows = N, kp >= Cin and ktot = taps*kp + 16 (got rows=%d ktot=%d)", rows, ktot);
+  else
+    RFK_REQUIRE(perm == nullptr && rows == Cin && kp >= N && ktot == taps * kp,
+                "rfk_pack_weight_folded: mode 5 needs perm = NULL, rows = Cin, kp >= N and ktot = taps*kp (got rows=%d ktot=%d)", rows, ktot);
   const long long total = (long long)rows_pad * ktot;
-  RFK_LAUNCH(pack_weight_folded_kernel, stream_grid(total, 256, 8), 256, 0, (cudaStream_t)stream, src, N, Cin, taps, perm, kp,
-             logs, bias, (__nv_bfloat16*)dst, rows_pad, ktot);
+  RFK_LAUNCH(pack_weight_folded_kernel, stream_grid(total, 256, 8), 256, 0, (cudaStream_t)stream, src, N, Cin, taps, mode, perm, rows,
+             kp, logs, bias, (__nv_bfloat16*)dst, rows_pad, ktot);
   return check_launch("rfk_pack_weight_folded");
 }
 

@@ -24,7 +24,7 @@ __device__ __forceinline__ T* eptr(const long long* e, int i) { return reinterpr
 
 // ---- weights -------------------------------------------------------------------------------------------------------
 // entry: 0 src f32, 1 dst bf16, 2 perm i32 (0 = none), 3 N, 4 Cin, 5 taps, 6 mode, 7 rows, 8 kp, 9 rows_pad, 10 ktot,
-//        11 logs, 12 bias (mode 4 only: forward weight with the following ActNorm folded in, see rfk_pack_weight_folded)
+//        11 logs, 12 bias (modes 4 / 5 only: weights with an ActNorm folded in, see rfk_pack_weight_folded)
 __global__ void __launch_bounds__(256) pack_weights_batched_kernel(const long long* __restrict__ table) {
   // no pdl_trigger(): conv kernels prefetch weights BEFORE their dependency wait, so dependents must not start early
   pdl_wait();
@@ -52,6 +52,9 @@ __global__ void __launch_bounds__(256) pack_weights_batched_kernel(const long lo
           const float hi = __bfloat162float(__float2bfloat16(sh));
           v = k == kmain ? hi : sh - hi;
         }
+      } else if (mode == 5) {
+        const int t = k / kp, co = k % kp;
+        if (co < N) v = src[((long long)co * Cin + (perm ? perm[r] : r)) * taps + (taps - 1 - t)] * expf(logs[r]);
       } else if (mode == 0) {
         const int t = k / kp, j = k % kp;
         if (j < Cin) v = src[((long long)r * Cin + (perm ? perm[j] : j)) * taps + t];

@@ -472,7 +472,7 @@ def conv_gemm_actbwd(act, cin_pad, wgt, n, taps, scale, act_fn, h, out, colsum):
     meta = _gemm_meta(B * H * W, n, taps, cin_pad, wgt)
     meta["bytes"] += 2.0 * B * H * W * n      # + the saved activation read by the epilogue
     call("rfk_conv_gemm_actbwd", act.data_ptr(), B, H, W, ld, cin_pad, _chk(wgt, torch.bfloat16).data_ptr(), n, wgt.shape[0],
-         taps, _chk(scale).data_ptr(), ACT[act_fn], h.data_ptr(), h.shape[-1], out.data_ptr(), out.shape[-1],
+         taps, _p(scale), ACT[act_fn], h.data_ptr(), h.shape[-1], out.data_ptr(), out.shape[-1],
          _chk(colsum).data_ptr(), _stream(), meta=meta)
     return out
 
@@ -685,7 +685,7 @@ def pack_conv_weight_folded(weight, logs, bias, in_perm=None):
     rows_pad = pad_to(N, 16)
     out = torch.empty(rows_pad, ktot, device=w.device, dtype=torch.bfloat16)
     p32 = _perm32(in_perm)
-    call("rfk_pack_weight_folded", w.data_ptr(), N, Cin, kh * kw, _p(p32), kp, lg.data_ptr(), bs.data_ptr(), out.data_ptr(),
+    call("rfk_pack_weight_folded", w.data_ptr(), N, Cin, kh * kw, 4, _p(p32), N, kp, lg.data_ptr(), bs.data_ptr(), out.data_ptr(),
          rows_pad, ktot, _stream())
     out.rfk_cin = Cin
     if w.data_ptr() == weight.data_ptr() and lg.data_ptr() == logs.data_ptr() and bs.data_ptr() == bias.data_ptr():
@@ -693,6 +693,28 @@ def pack_conv_weight_folded(weight, logs, bias, in_perm=None):
         out.rfk_pack = [w.data_ptr(), out.data_ptr(), _p(p32), N, Cin, kh * kw, 4, N, kp, rows_pad, ktot, lg.data_ptr(),
                         bs.data_ptr()]
         out.rfk_perm = p32
+    return out, kp
+
+
+def pack_dgrad_weight_scaled(weight, logs):
+    """pack_dgrad_weight with row r (the forward conv's input channel r) scaled by exp(logs[r]), logs [1,Cin,1,1] = the
+    ActNorm that produced the conv's input: operand of conv_gemm_actbwd(scale=None)."""
+    w, lg = weight.detach(), logs.detach()
+    for t in (w, lg):
+        if t.dtype != torch.float32 or not t.is_contiguous() or not t.is_cuda:
+            raise _lib.RfkError("pack_dgrad_weight_scaled: contiguous fp32 CUDA parameters expected")
+    N, Cin, kh, kw = w.shape
+    assert lg.numel() == Cin
+    kp = cin_pad(N)
+    ktot = kh * kw * kp
+    rows_pad = pad_to(Cin, 16)
+    out = torch.empty(rows_pad, ktot, device=w.device, dtype=torch.bfloat16)
+    call("rfk_pack_weight_folded", w.data_ptr(), N, Cin, kh * kw, 5, None, Cin, kp, lg.data_ptr(), None, out.data_ptr(), rows_pad,
+         ktot, _stream())
+    out.rfk_cin = N
+    if w.data_ptr() == weight.data_ptr() and lg.data_ptr() == logs.data_ptr():
+        out.rfk_pack = [w.data_ptr(), out.data_ptr(), 0, N, Cin, kh * kw, 5, Cin, kp, rows_pad, ktot, lg.data_ptr(), 0]
+        out.rfk_perm = None
     return out, kp
 
 

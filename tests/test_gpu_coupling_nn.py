@@ -147,3 +147,15 @@ def test_coupling_nn_fused_many_tiles_per_pair(ops):
     for sl in (slice(0, 2), slice(149, 151), slice(B - 2, B)):
         _, _, ref = oracle_chain(x[sl], w1, l1, b1, w2, l2, b2, w4, k, act)
         assert max_rel(taps[sl].cpu(), ref) < 6e-3
+
+
+def test_scaled_dgrad_weight_layout(ops):
+    """rfk_pack_weight_folded mode 5: the data-gradient weights with row r scaled by exp(logs[r]) equal the plain
+    data-gradient packing of the weight whose input channel r was scaled before."""
+    g = torch.Generator().manual_seed(4)
+    w = torch.randn(256, 64, 3, 3, generator=g).cuda()
+    logs = (torch.randn(1, 64, 1, 1, generator=g) * 0.3).cuda()
+    got, kp = ops.pack_dgrad_weight_scaled(w, logs)
+    ref, kp2 = ops.pack_dgrad_weight((w * torch.exp(logs)).contiguous())
+    assert kp == kp2 and got.shape == ref.shape
+    assert torch.equal(got, ref)
