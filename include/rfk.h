@@ -358,6 +358,12 @@ int rfk_convlstm_pointwise_bwd(const float* cc, const float* c_prev, const float
  * out[b, j, y, x] = sum_t T[b, y+ky-1, x+kx-1, t*n_stride + j] (zero outside the image), fp32 NCHW [B, n, H, W];
  * n <= n_stride <= 128, n_stride a multiple of 8 (tap segments are whole 16-byte chunks). */
 int rfk_taps_gather_nhwc(const void* T, int ld, int n, int n_stride, int B, int H, int W, float* out, void* stream);
+/* The same gather ACCUMULATED into two fp32 NCHW tensors instead of written to a fresh one: channels [0, n0) are added to
+ * acc0[:, 0:n0] (acc0_C channels per sample), channels [n0, n) to acc1[:, 0:n-n0] (acc1_C channels).  In the coupling
+ * backward (Flow/glow_modules.py:271-291 differentiated) these are the condition's gradient and dz[:, :C/2] += d z1: the
+ * network-input gradient tensor and two rfk_add_channels launches per GlowStep disappear. */
+int rfk_taps_gather_nhwc_acc(const void* T, int ld, int n, int n_stride, int B, int H, int W, float* acc0, int acc0_C,
+                             int n0, float* acc1, int acc1_C, void* stream);
 
 /* Debug aid: when buf != NULL, every conv-GEMM CTA of later launches (grids of at most capacity_ctas CTAs)
  * writes 16 words to buf[16*cta..]: %globaltimer stamps (ns) 0 start, 1 setup done, 2 weights resident, 3 last TMA

@@ -46,6 +46,8 @@ FUSE_ACT_BWD = os.environ.get("RFK_FUSE_ACT_BWD", "1") != "0"
 # e^{logs} of the ActNorm below folded into the data-gradient weight rows (conv_gemm_actbwd with scale = None).  Measured neutral
 # (level 1: 160 / 166 us against 154 / 159 us -- that epilogue is not bound by its per-channel loads), so it stays opt-in.
 FOLD_ACTBWD_SCALE = os.environ.get("RFK_FOLD_ACTBWD_SCALE", "0") == "1"
+# Tap-split data gradient of the coupling network's first conv gathered straight into dz / the condition's gradient.
+FUSE_GATHER_ACC = os.environ.get("RFK_FUSE_GATHER_ACC", "1") != "0"
 # Recompute mode for every flow that does not set flow.recompute itself (see _glowstep_fwd).
 RECOMPUTE = os.environ.get("RFK_RECOMPUTE", "0") == "1"
 # Training forward of the coupling network as ONE kernel with h1 / h2 as side outputs (RFK_FUSE_NN_TRAIN=0: three launches).
@@ -141,6 +143,12 @@ class _State:
     def add(self, param, g):
         """Legacy path: g is a tensor this sweep owns; added into the parameter's accumulation buffer."""
         self.out(param).add_(g.reshape(-1))
+
+    def cond_acc(self, l, B, n, H, W):
+        """The (zero-initialised) gradient of level l's condition, for kernels that accumulate into it in place."""
+        if self.dcond[l] is None:
+            self.dcond[l] = torch.zeros(B, n, H, W, device=self.dz.device, dtype=torch.float32)
+        return self.dcond[l]
 
     def add_cond(self, l, src, n):
         """dcond[l] += src[:, :n] (src fp32 NCHW with the condition's channels first)."""
@@ -243,9 +251,15 @@ def _wgrad_actnorm(st, mod, x_act, cin, da, colsum, perm=None):
              after=lambda: ops.actnorm_param_bwd(w.detach(), dWp, colsum, bias, g_w, g_logs, g_bias))
 
 
-def _conv_bwd(st, mod, x_act, cin, da, perm=None, dgrad_out=None, key="id", skip_wgrad=False):
+def _conv_bwd(st, mod, x_act, cin, da, perm=None, dgrad_out=None, key="id", skip_wgrad=False, acc=None):
     """Backward of mod.conv given da (bf16 NHWC gradient of the raw convolution output): weight gradient into the
-    state, data gradient into dgrad_out (bf16 NHWC or fp32 NCHW; channels in the staging order of x_act)."""
+    state, data gradient into dgrad_out (bf16 NHWC or fp32 NCHW; channels in the staging order of x_act).
+    ``acc`` = (acc0, n0, acc1) instead of dgrad_out: the data gradient is ADDED in place, channels [0, n0) into acc0 and the
+    rest into the first channels of acc1 (tap-split path only; returns False when that path does not apply)."""
+    if acc is not None:
+        B, H, W, _ = da.shape
+        if not (mod.taps == 9 and 9 * cin <= DGRAD_TAP_SPLIT_MAX_N and B * H * W >= DGRAD_TAP_SPLIT_MIN_PIXELS):
+            return False
     n = mod.conv.out_channels
     k = 3 if mod.taps == 9 else 1
     if not skip_wgrad:
@@ -264,6 +278,12 @@ def _conv_bwd(st, mod, x_act, cin, da, perm=None, dgrad_out=None, key="id", skip
         else:
             wd, cp = mod.packed_dgrad(key, perm)
             ops.conv_gemm(da, cp, wd, cin, mod.taps, None, None, "none", dgrad_out)
+    if acc is not None:
+        wd9, cp, r8 = mod.packed_dgrad_taps(key, perm)
+        planes = torch.empty(B, H, W, ops.pad_to(9 * r8, 64), device=da.device, dtype=torch.bfloat16)
+        ops.conv_gemm(da, cp, wd9, 9 * r8, 1, None, None, "none", planes)
+        ops.taps_gather_nhwc_acc(planes, cin, r8, acc[0], acc[1], acc[2])
+        return True
 
 
 def _norm_act_bwd(st, mod, dh, h, act_fn, keep=None):
@@ -440,7 +460,7 @@ def _glowstep_bwd(st, flow, step, x, zo, nn_in, h1, h2, taps, cc, l, xn=None, bn
         dS = _nhwc(B, H, W, C, dev)      # small level: the side-stream weight gradient may still be reading the previous one
     ops.pack_nhwc(dsum, 0, C, dS, 0)
     cin = half + cc
-    dnn = torch.empty(B, cin, H, W, device=dev, dtype=torch.float32)
+    dnn = None
     if (FUSE_ACT_BWD and hid % 64 == 0 and hid <= 512 and net[0].norm == "actnorm" and net[2].norm == "actnorm"
             and ops.cin_pad(hid) == hid):
         # dh2 / dh1 never exist in HBM: each data-gradient GEMM applies act' and the ActNorm scale of the layer below in its
@@ -450,8 +470,14 @@ def _glowstep_bwd(st, flow, step, x, zo, nn_in, h1, h2, taps, cc, l, xn=None, bn
         _wgrad_actnorm(st, net[2], h1, hid, da2, r2)
         da1, r1 = _dgrad_actbwd(st, net[2], da2, net[0], h1, act)
         _wgrad_actnorm(st, net[0], nn_in, cin, da1, r1, perm=aff._perm(dev))
-        _conv_bwd(st, net[0], nn_in, cin, da1, perm=aff._perm(dev), dgrad_out=dnn, key="cz", skip_wgrad=True)
+        # network-input gradient: on the large levels the gather of the tap-split data gradient ADDS straight into the
+        # condition's gradient and into dz[:, :half] (no dnn tensor, no rfk_add_channels launches)
+        if not (FUSE_GATHER_ACC and _conv_bwd(st, net[0], nn_in, cin, da1, perm=aff._perm(dev), key="cz", skip_wgrad=True,
+                                              acc=(st.cond_acc(l, B, cc, H, W) if cc else None, cc, dz))):
+            dnn = torch.empty(B, cin, H, W, device=dev, dtype=torch.float32)
+            _conv_bwd(st, net[0], nn_in, cin, da1, perm=aff._perm(dev), dgrad_out=dnn, key="cz", skip_wgrad=True)
     else:
+        dnn = torch.empty(B, cin, H, W, device=dev, dtype=torch.float32)
         dh2 = _nhwc(B, H, W, hid, dev)
         _conv_bwd(st, last, h2, hid, dS, dgrad_out=dh2)
         da2 = _norm_act_bwd(st, net[2], dh2, h2, act)
@@ -459,9 +485,10 @@ def _glowstep_bwd(st, flow, step, x, zo, nn_in, h1, h2, taps, cc, l, xn=None, bn
         _conv_bwd(st, net[2], h1, hid, da2, dgrad_out=dh1)
         da1 = _norm_act_bwd(st, net[0], dh1, h1, act)
         _conv_bwd(st, net[0], nn_in, cin, da1, perm=aff._perm(dev), dgrad_out=dnn, key="cz")
-    ops.add_channels(dz, 0, dnn, cc, half)          # dz[:, :half] += d z1 (the network's input after the condition)
-    if cc:
-        st.add_cond(l, dnn, cc)
+    if dnn is not None:
+        ops.add_channels(dz, 0, dnn, cc, half)          # dz[:, :half] += d z1 (the network's input after the condition)
+        if cc:
+            st.add_cond(l, dnn, cc)
     if bn_saved is not None:     # flow_norm='batchnorm': plain InvConv mix, then the per-position batch-norm layer
         Wm = step.invconv.weight_fwd()[0]
         dWm, _ = ops.mix1x1_wgrad(xn, dz)

@@ -69,6 +69,8 @@ SIGNATURES = {
     "rfk_convlstm_pointwise_bwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_void_p, c_void_p, c_void_p, c_void_p,
                                    c_int, c_int, c_int, c_void_p],
     "rfk_taps_gather_nhwc": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
+    "rfk_taps_gather_nhwc_acc": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int,
+                                 c_void_p],
     "rfk_add_scalar": [c_void_p, c_void_p, c_float, c_int, c_void_p],
     "rfk_set_conv_split": [c_int],
     "rfk_set_pdl": [c_int],

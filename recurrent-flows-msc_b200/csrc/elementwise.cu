@@ -1504,7 +1504,8 @@ extern "C" int rfk_pack_weight_folded(const float* src, int N, int Cin, int taps
 namespace rfk {
 constexpr int TG_PIX = 64;
 __global__ void __launch_bounds__(256) taps_gather_nhwc_kernel(const __nv_bfloat16* __restrict__ T, int ld, int n, int ns, int B,
-                                                               int H, int W, float* __restrict__ out) {
+                                                               int H, int W, float* __restrict__ out, float* __restrict__ acc0,
+                                                               int acc0_C, int n0, float* __restrict__ acc1, int acc1_C) {
   pdl_trigger();
   pdl_wait();
   extern __shared__ float tile[];   // [ns][TG_PIX + 1]
@@ -1546,7 +1547,10 @@ __global__ void __launch_bounds__(256) taps_gather_nhwc_kernel(const __nv_bfloat
       const long long g = g0 + pl;
       if (g < npix) {
         const long long b = g / HW;
-        out[(b * n + j) * HW + (g % HW)] = tile[j * (TG_PIX + 1) + pl];
+        const float v = tile[j * (TG_PIX + 1) + pl];
+        if (out) out[(b * n + j) * HW + (g % HW)] = v;
+        else if (j < n0) acc0[(b * acc0_C + j) * HW + (g % HW)] += v;          // accumulate form: channels [0, n0) -> acc0,
+        else acc1[(b * acc1_C + (j - n0)) * HW + (g % HW)] += v;               // the rest -> the first channels of acc1
       }
     }
     __syncthreads();
@@ -1562,6 +1566,22 @@ extern "C" int rfk_taps_gather_nhwc(const void* T, int ld, int n, int n_stride, 
   const long long npix = (long long)B * H * W;
   long long ctas = std::min<long long>((npix + TG_PIX - 1) / TG_PIX, (long long)sm_count() * 16);
   RFK_LAUNCH(taps_gather_nhwc_kernel, (int)ctas, 256, (size_t)n_stride * (TG_PIX + 1) * sizeof(float), (cudaStream_t)stream,
-             (const __nv_bfloat16*)T, ld, n, n_stride, B, H, W, out);
+             (const __nv_bfloat16*)T, ld, n, n_stride, B, H, W, out, (float*)nullptr, 0, 0, (float*)nullptr, 0);
   return check_launch("rfk_taps_gather_nhwc");
+}
+
+extern "C" int rfk_taps_gather_nhwc_acc(const void* T, int ld, int n, int n_stride, int B, int H, int W, float* acc0, int acc0_C,
+                                        int n0, float* acc1, int acc1_C, void* stream) {
+  using namespace rfk;
+  RFK_REQUIRE(T && n > 0 && n <= n_stride && n_stride <= 128 && n_stride % 8 == 0 && B > 0 && H > 0 && W > 0 &&
+              ld >= 9 * n_stride && ld % 8 == 0 && (reinterpret_cast<uintptr_t>(T) & 15) == 0,
+              "rfk_taps_gather_nhwc_acc: bad arguments (n <= n_stride <= 128, n_stride %% 8 == 0, ld >= 9*n_stride, ld %% 8 == 0)");
+  RFK_REQUIRE(n0 >= 0 && n0 <= n && (n0 == 0 || (acc0 && acc0_C >= n0)) && (n0 == n || (acc1 && acc1_C >= n - n0)),
+              "rfk_taps_gather_nhwc_acc: accumulation targets do not cover the %d channels (n0=%d, acc0_C=%d, acc1_C=%d)", n, n0,
+              acc0_C, acc1_C);
+  const long long npix = (long long)B * H * W;
+  long long ctas = std::min<long long>((npix + TG_PIX - 1) / TG_PIX, (long long)sm_count() * 16);
+  RFK_LAUNCH(taps_gather_nhwc_kernel, (int)ctas, 256, (size_t)n_stride * (TG_PIX + 1) * sizeof(float), (cudaStream_t)stream,
+             (const __nv_bfloat16*)T, ld, n, n_stride, B, H, W, (float*)nullptr, acc0, acc0_C, n0, acc1, acc1_C);
+  return check_launch("rfk_taps_gather_nhwc_acc");
 }

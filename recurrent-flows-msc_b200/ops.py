@@ -600,6 +600,21 @@ def taps_gather_nhwc(T, n, n_stride, out):
     return out
 
 
+def taps_gather_nhwc_acc(T, n, n_stride, acc0, n0, acc1):
+    """The gather of taps_gather_nhwc accumulated in place: channels [0, n0) += into acc0[:, :n0], channels [n0, n) into
+    acc1[:, :n - n0] (fp32 NCHW)."""
+    _chk(T, torch.bfloat16, "T")
+    B, H, W, ld = T.shape
+    if n0 > 0:
+        _chk(acc0, name="acc0")
+    if n0 < n:
+        _chk(acc1, name="acc1")
+    call("rfk_taps_gather_nhwc_acc", T.data_ptr(), ld, n, n_stride, B, H, W, acc0.data_ptr() if n0 > 0 else None,
+         acc0.shape[1] if n0 > 0 else 0, n0, acc1.data_ptr() if n0 < n else None, acc1.shape[1] if n0 < n else 0, _stream(),
+         meta={"bytes": 2.0 * B * H * W * 9 * n_stride + 8.0 * B * H * W * n})
+    return acc1
+
+
 _PERM32 = {}
 
 

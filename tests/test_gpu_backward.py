@@ -195,3 +195,11 @@ def test_dgrad_tap_split(ops, B, Cin, H, W, N, with_perm):
     out = torch.empty(B, Cin, H, W, device="cuda")
     ops.taps_gather_nhwc(planes, Cin, r8, out)
     assert max_rel(out.cpu(), ref) < 1e-2     # the nine planes are rounded to bf16
+    # accumulate form: channels [0, n0) += into one tensor, the rest += into the first channels of another
+    for n0 in (0, Cin // 3, Cin):
+        acc0 = torch.randn(B, n0 + 2, H, W, generator=g).cuda()
+        acc1 = torch.randn(B, Cin - n0 + 3, H, W, generator=g).cuda()
+        a0, a1 = acc0.clone(), acc1.clone()
+        ops.taps_gather_nhwc_acc(planes, Cin, r8, acc0, n0, acc1)
+        assert torch.equal(acc0[:, :n0], a0[:, :n0] + out[:, :n0]) and torch.equal(acc0[:, n0:], a0[:, n0:])
+        assert torch.equal(acc1[:, :Cin - n0], a1[:, :Cin - n0] + out[:, n0:]) and torch.equal(acc1[:, Cin - n0:], a1[:, Cin - n0:])
