@@ -200,7 +200,7 @@ int rfk_conv1x1_taps_fused(const void* act, int B, int H, int W, int act_ld, int
  * [hid, hid + 16], both with their ActNorm folded in (rfk_pack_weight_folded: the per-channel scale lives in the weight rows,
  * the shift rides through the GEMM against a constant-one operand, so the epilogues are activation + rounding only);
  * w9: bf16 [w9_rows >= n3, hid] in tap-split row order (see rfk_coupling_tail_taps); taps_out: fp32 NCHW [B, n3, H, W],
- * n3 <= 128.  h1_out / h2_out (both or neither; NHWC bf16, row stride h_ld): the hidden activations as side outputs for a
+ * n3 <= 256 (GEMM3 runs in passes of 128 accumulator columns).  h1_out / h2_out (both or neither; NHWC bf16, row stride h_ld): the hidden activations as side outputs for a
  * backward pass -- written once by TMA store, never read back here. */
 int rfk_coupling_nn_fused(const void* act, int B, int H, int W, int act_ld, int cin_pad, int taps, const void* w1f,
                           int hid, const void* w2f, int act_fn, const void* w9, int n3, int w9_rows, float* taps_out,

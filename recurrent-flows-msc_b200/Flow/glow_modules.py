@@ -22,6 +22,9 @@ from ..Utils.modules import ActFun
 FUSE_CONV2_TAPS = True   # AffineCoupling: fuse net.2 (1x1 conv + ActNorm + act) with the tap-split net.4 when 9*C <= 128
 FUSE_COUPLING_NN = os.environ.get("RFK_FUSE_NN", "1") != "0"   # AffineCoupling: all three convs in ONE kernel (h1 and h2 in tensor memory)
 FUSE_NN_MIN_TILES = int(os.environ.get("RFK_FUSE_NN_MIN_TILES", "48"))  # ... when there are at least this many 128-pixel tiles (below that the per-layer split-K launches win)
+# ... and at most this many tap planes 9*C: the kernel takes up to 256 (two passes of its last GEMM), but beyond 128 it only
+# matched the per-layer launches (config J level 3: forward 5.77 vs 5.70 ms; config D level 2: no change)
+FUSE_NN_MAX_PLANES = int(os.environ.get("RFK_FUSE_NN_MAX_PLANES", "128"))
 TAP_SPLIT_MAX_N = 2304  # AffineCoupling: tap-split form of the last conv up to C = 256 (K drops from 9*256 to 256)
 
 
@@ -500,7 +503,7 @@ class AffineCoupling(nn.Module):
         first, last, mid = self.net[0], self.net[4], self.net[2]
         tap_split = last.taps == 9 and 9 * C <= TAP_SPLIT_MAX_N
         # the whole network in one kernel (csrc/coupling_nn.cu) on the big levels: neither hidden tensor touches HBM
-        if (FUSE_COUPLING_NN and FUSE_CONV2_TAPS and not ops.SPLIT and tap_split and mid.taps == 1 and 9 * C <= 128
+        if (FUSE_COUPLING_NN and FUSE_CONV2_TAPS and not ops.SPLIT and tap_split and mid.taps == 1 and 9 * C <= FUSE_NN_MAX_PLANES
                 and self.hidden_units % 64 == 0 and self.hidden_units <= 256 and first.foldable() and mid.foldable()
                 and ops.gemm_m_tiles(B, H, W) >= FUSE_NN_MIN_TILES):
             w1f, cin_pad1 = first.packed_folded("cz", self._perm(dev))

@@ -24,7 +24,7 @@ import os
 import torch
 
 from .. import ops
-from .glow_modules import BatchNormFlow, Split2d, Squeeze2d, TAP_SPLIT_MAX_N, FUSE_NN_MIN_TILES
+from .glow_modules import BatchNormFlow, Split2d, Squeeze2d, TAP_SPLIT_MAX_N, FUSE_NN_MIN_TILES, FUSE_NN_MAX_PLANES
 
 
 DGRAD_TAP_SPLIT_MAX_N = 512         # tap-split data gradient when 9*Cin <= this ...
@@ -415,7 +415,7 @@ def _coupling_nn(aff, nn_in, C, keep):
     hid, act, dev = aff.hidden_units, aff.non_lin, nn_in.device
     wgt9, cp = net[4].packed_taps()
     taps = torch.empty(B, 9 * C, H, W, device=dev, dtype=torch.float32)
-    if (FUSE_NN_TRAIN and not ops.SPLIT and net[2].taps == 1 and 9 * C <= 128 and hid % 64 == 0 and hid <= 256
+    if (FUSE_NN_TRAIN and not ops.SPLIT and net[2].taps == 1 and 9 * C <= FUSE_NN_MAX_PLANES and hid % 64 == 0 and hid <= 256
             and net[0].foldable() and net[2].foldable() and ops.gemm_m_tiles(B, H, W) >= FUSE_NN_MIN_TILES):
         # one kernel for the three convolutions (csrc/coupling_nn.cu); h1 / h2 leave as side outputs for the backward and
         # are not read back by the forward

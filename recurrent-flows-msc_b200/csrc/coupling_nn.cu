@@ -49,7 +49,7 @@ struct NNArgs {
   int taps, kchunks, bk, kgroup, k_groups;   // GEMM1: taps * kchunks chunks of bk channels, kgroup chunks per pipeline stage
   int w1_resident;
   int hid;                                   // N of GEMM1 and GEMM2, K of GEMM2 and GEMM3 (multiple of 64, <= 256)
-  int n3, n3_pad;                            // tap planes 9*C, padded to a multiple of 32 (<= 128)
+  int n3, n3_pad;                            // tap planes 9*C, padded to a multiple of 16 (<= 256)
   int stages;
   int act_fn;
   int store_h;                               // 1: h1 / h2 leave as bf16 NHWC side outputs
@@ -116,6 +116,7 @@ coupling_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 
   const uint32_t rank = cluster_ctarank();           // 0 = leader: issues the MMAs, owns the barriers that gate them
   const int hid_local = g.hid >> 1, n3_local = g.n3_pad >> 1;   // weight rows held by this CTA
+  const int n3_passes = (g.n3_pad + 127) >> 7;                  // GEMM3 runs in passes of up to 128 accumulator columns
   const int k1_iters = g.taps * g.kchunks, k2chunks = g.hid >> 6;
   const uint32_t a_chunk = 128u * (uint32_t)g.bk * 2u, b1_chunk = (uint32_t)hid_local * (uint32_t)g.bk * 2u;
   const uint32_t w2_chunk = (uint32_t)hid_local * 128u, w9_chunk = (uint32_t)n3_local * 128u;
@@ -244,7 +245,6 @@ coupling_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     if (lane == 0 && rank == 0) {
       // kind::f16 instruction descriptor: D=f32, A=B=bf16, K-major, N>>3 at bit 17, M>>4 at bit 24 (M = 256 for the pair)
       const uint32_t idesc12 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(g.hid >> 3) << 17) | (16u << 24);
-      const uint32_t idesc3 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(g.n3_pad >> 3) << 17) | (16u << 24);
       const uint64_t desc_hi1 = umma_desc_kmajor(0, g.bk), desc_hi64 = umma_desc_kmajor(0, 64);
       const int ksteps1 = g.bk / 16;
       mbar_wait(w_full, 0);
@@ -291,7 +291,7 @@ coupling_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         // ---- GEMM2 -> R1, A = bf16 h1 (in place in R0: channels [16u, 16u+16) sit in columns [16u, 16u+8)).  R1 held the
         // previous tile's h2 and tap accumulator: GEMM3 of that tile precedes us in the pipe, its accumulator must be drained.
         if (tl > 0) {
-          { NN_CNT_BEGIN(); mbar_wait(d3_empty, (tl - 1u) & 1u); NN_CNT_END(c_d3); }
+          { NN_CNT_BEGIN(); mbar_wait(d3_empty, (tl * (uint32_t)n3_passes - 1u) & 1u); NN_CNT_END(c_d3); }
           tc_fence_after();
         }
         accumulate = 0;
@@ -314,20 +314,32 @@ coupling_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         // ---- GEMM3 -> R0 + 128, A = bf16 h2 (compact, R0 columns [0, hid/2)).  (Two accumulators fed by alternate K steps or by
         // alternate chunks were tried -- a dependent MMA starts ~160 cycles after its predecessor whatever N is -- and left the
         // kernel time unchanged: the chunks arrive at the pace of epilogue 2.)
-        accumulate = 0;
-        for (int kc = 0; kc < k2chunks; ++kc) {
-          { NN_CNT_BEGIN(); mbar_wait(a3_ready(kc), par); if (kc == 0) NN_CNT_END(c_a3_0); else NN_CNT_END(c_a3_n); }
-          tc_fence_after();
-          if (stp && kc == 0) stp[5] = (unsigned)clock();          // h2 chunk 0 seen
-          if (stp && kc == 3) stp[6] = (unsigned)clock();          // h2 chunk 3 seen
-          const uint64_t bdesc = desc_hi64 | (uint64_t)(((w9_base + kc * w9_chunk) & 0x3FFFFu) >> 4);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            umma_bf16_ts_2sm(r0 + 128u, r0 + (uint32_t)(kc * 32 + k * 8), bdesc + (uint64_t)(2 * k), idesc3, accumulate);
-            accumulate = 1;
+        // More than 128 tap planes: passes of up to 128 accumulator columns, each drained by epilogue 3 before the next starts
+        // (pass p takes weight rows [64p, 64p + N_p/2) of BOTH CTAs' halves, see the column -> plane map in epilogue 3).
+        for (int ps = 0; ps < n3_passes; ++ps) {
+          const int n_p = min(128, g.n3_pad - 128 * ps);
+          const uint32_t idesc3 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n_p >> 3) << 17) | (16u << 24);
+          if (ps > 0) {
+            mbar_wait(d3_empty, (tl * (uint32_t)n3_passes + (uint32_t)ps - 1u) & 1u);
+            tc_fence_after();
           }
+          accumulate = 0;
+          for (int kc = 0; kc < k2chunks; ++kc) {
+            if (ps == 0) {
+              { NN_CNT_BEGIN(); mbar_wait(a3_ready(kc), par); if (kc == 0) NN_CNT_END(c_a3_0); else NN_CNT_END(c_a3_n); }
+              tc_fence_after();
+              if (stp && kc == 0) stp[5] = (unsigned)clock();          // h2 chunk 0 seen
+              if (stp && kc == 3) stp[6] = (unsigned)clock();          // h2 chunk 3 seen
+            }
+            const uint64_t bdesc = desc_hi64 | (uint64_t)(((w9_base + kc * w9_chunk + (uint32_t)ps * 64u * 128u) & 0x3FFFFu) >> 4);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              umma_bf16_ts_2sm(r0 + 128u, r0 + (uint32_t)(kc * 32 + k * 8), bdesc + (uint64_t)(2 * k), idesc3, accumulate);
+              accumulate = 1;
+            }
+          }
+          umma_commit_2sm(acc_full(2));
         }
-        umma_commit_2sm(acc_full(2));
         if (stp) stp[7] = (unsigned)clock();                       // GEMM3 issued + committed
       }
       if (dbg) {
@@ -441,34 +453,44 @@ coupling_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       if (stp) stp[11] = (unsigned)clock();                        // epilogue 2 done
       // ---- epilogue 3: tap planes -> fp32 NCHW
       if (dbg) c_e2 += (unsigned)clock() - c_t;
-      { NN_CNT_BEGIN(); mbar_wait(acc_full(2), par); NN_CNT_END(c_w2); }
-      tc_fence_after();
-      c_t = dbg ? (unsigned)clock() : 0u;
-      if (stp) stp[12] = c_t;                                      // GEMM3 accumulator seen
-      // this warp's (at most two) 16-plane slices; the accumulator is handed back as soon as it is in registers, before the
-      // global stores go out
+      for (int ps = 0; ps < n3_passes; ++ps) {
+        { NN_CNT_BEGIN(); mbar_wait(acc_full(2), (tl * (uint32_t)n3_passes + (uint32_t)ps) & 1u); NN_CNT_END(c_w2); }
+        tc_fence_after();
+        if (ps == 0) {
+          c_t = dbg ? (unsigned)clock() : 0u;
+          if (stp) stp[12] = c_t;                                    // GEMM3 accumulator seen
+        }
+        // accumulator column c of pass ps holds tap plane 64 ps + c (weight rows of the leader's half) for c < N_p / 2, else
+        // n3_pad / 2 + 64 ps + (c - N_p / 2) (the peer's half); with a single pass that is plane c
+        const int n_p = min(128, g.n3_pad - 128 * ps), half_p = n_p >> 1;
+        // this warp's (at most two) 16-column slices; the accumulator is handed back as soon as it is in registers, before
+        // the global stores go out
 #pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const int c0 = 16 * part + 64 * i;
-        uint32_t r[16];
-        if (c0 < g.n3) {   // warp-uniform
-          NN_CNT_BEGIN();
-          tmem_ld16_nowait(r0 + 128u + c0, r);
-          tmem_wait_ld();
-          NN_CNT_END(c_e3ld);
-        }
-        if (i == (g.n3_pad > 64 ? 1 : 0)) {   // nothing left to drain
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) arrive_leader(d3_empty);
-        }
-        if (c0 < g.n3 && valid) {
-          float* dst = g.taps_out + (((long long)b * g.n3 + c0) * g.H + y) * g.W + x;
+        for (int i = 0; i < 2; ++i) {
+          const int c0 = 16 * part + 64 * i;
+          uint32_t r[16];
+          if (c0 < n_p) {   // warp-uniform
+            NN_CNT_BEGIN();
+            tmem_ld16_nowait(r0 + 128u + c0, r);
+            tmem_wait_ld();
+            NN_CNT_END(c_e3ld);
+          }
+          if (i == (n_p > 64 ? 1 : 0)) {   // nothing left to drain
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) arrive_leader(d3_empty);
+          }
+          if (c0 < n_p && valid) {
+            float* dst = g.taps_out + ((long long)b * g.n3 * g.H + y) * g.W + x;
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (c0 + j < g.n3) dst[j * plane] = __uint_as_float(r[j]);
+            for (int j = 0; j < 16; ++j) {
+              const int c = c0 + j;
+              const int pl = c < half_p ? 64 * ps + c : n3_local + 64 * ps + (c - half_p);
+              if (c < n_p && pl < g.n3) dst[pl * plane] = __uint_as_float(r[j]);
+            }
+          }
+          if (n_p <= 64) break;
         }
-        if (g.n3_pad <= 64) break;
       }
       if (dbg) c_e3 += (unsigned)clock() - c_t;
       if (stp) stp[13] = (unsigned)clock();                        // epilogue 3 done
@@ -504,7 +526,7 @@ extern "C" int rfk_coupling_nn_fused(const void* act, int B, int H, int W, int a
   RFK_REQUIRE(taps == 1 || taps == 9, "%s: taps=%d (only 1x1 and 3x3 kernels)", who, taps);
   RFK_REQUIRE(hid >= 64 && hid % 64 == 0 && hid <= 256, "%s: hidden=%d must be 64, 128, 192 or 256", who, hid);
   const int n3_pad = (n3 + 15) / 16 * 16;   // N of a cta_group::2 MMA: multiples of 16
-  RFK_REQUIRE(n3 > 0 && n3_pad <= 128 && w9_rows >= n3, "%s: n3=%d (at most 128 tap planes), w9_rows=%d", who, n3, w9_rows);
+  RFK_REQUIRE(n3 > 0 && n3_pad <= 256 && w9_rows >= n3, "%s: n3=%d (at most 256 tap planes), w9_rows=%d", who, n3, w9_rows);
   RFK_REQUIRE(act_fn >= 0 && act_fn <= 2, "%s: bad act_fn %d", who, act_fn);
   RFK_REQUIRE((h1_out == nullptr) == (h2_out == nullptr), "%s: h1_out and h2_out go together", who);
   const int store_h = h1_out != nullptr;

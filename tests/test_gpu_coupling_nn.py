@@ -71,6 +71,9 @@ SHAPES = [
     (7, 20, 6, 12, 20, 128, 3),     # ragged image, odd tile count, hidden 128
     (3, 256, 4, 32, 32, 256, 1),    # 1x1 first conv
     (1, 5, 2, 4, 4, 64, 3),         # a single, partly empty tile: the peer CTA's tile does not exist
+    (9, 72, 16, 8, 8, 256, 3),      # config J level 3: 144 tap planes = two passes of GEMM3 (128 + 16 accumulator columns)
+    (4, 76, 24, 16, 16, 256, 3),    # config D level 2: 216 tap planes
+    (2, 40, 28, 8, 8, 192, 3),      # 252 tap planes, hidden 192
 ]
 
 
