@@ -369,7 +369,11 @@ int rfk_taps_gather_nhwc_acc(const void* T, int ld, int n, int n_stride, int B, 
  * writes 16 words to buf[16*cta..]: %globaltimer stamps (ns) 0 start, 1 setup done, 2 weights resident, 3 last TMA
  * issued, 4 last MMA issued, 5 first accumulator ready, 6 first epilogue done, 7 all done; SM-cycle totals 8 producer
  * waiting for a free stage, 9 MMA waiting for data, 10 MMA waiting for a drained accumulator, 11 epilogue waiting for
- * an accumulator, 12 epilogue busy.  NULL switches it off (the default). */
+ * an accumulator, 12 epilogue busy.  rfk_coupling_nn_fused uses the same buffer when capacity_ctas >= 2 x the SM count: 16
+ * SM-cycle counters per CTA (MMA thread: GEMM1 section, waits for TMA data / the drained tap accumulator / the first and later
+ * chunks of h1 and h2; epilogue warp 0: waits for the three accumulators, busy in each epilogue) followed, after all
+ * counter blocks, by 16 clock stamps of one tile per CTA (tools/nn_fused_timeline.py prints both).  NULL switches it off
+ * (the default). */
 int rfk_debug_set_timeline(unsigned long long* buf, long long capacity_ctas);
 
 /* ConvLSTM cell update (Utils/modules.py:369-377) from a pixel-major gate buffer cc[(b*HW+p)*cc_ld + g*Hc + ch]

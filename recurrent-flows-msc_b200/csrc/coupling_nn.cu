@@ -8,8 +8,9 @@
 // net.4 = Conv2dZeros 3x3; the tap-split form of net.4 is described at rfk_coupling_tail_taps in rfk.h.)
 //
 // Neither 256-channel hidden tensor touches HBM: 2 x 299 MB written + 2 x 299 MB read per GlowStep at level 1 of the
-// 570-frame workload become 21 MB in + 84 MB out.  (Training keeps h1 / h2 for the backward: they leave as side outputs by
-// TMA store, written once and never read back by this pass.)
+// 570-frame workload become 37 MB in + 84 MB out (ncu: 37.7 MB read, 29.1 MB written to DRAM -- most of the tap planes stay
+// in L2).  (Training keeps h1 / h2 for the backward: they leave as side outputs by TMA store, written once and never read
+// back by this pass.)
 //
 // W1 (up to 147 KB) + W2 (128 KB) + W9 do not fit one CTA's shared memory, so the kernel runs as CTA PAIRS
 // (cluster of two, tcgen05 cta_group::2): every MMA is M = 256 (128 pixels per CTA), each CTA holds HALF of the rows of
@@ -25,7 +26,8 @@
 // Tensor memory (512 columns, two 256-column regions whose roles alternate from tile to tile):
 //   R0: GEMM1 accumulator (fp32) -> overwritten IN PLACE by bf16 h1 (16 fp32 columns become 8 packed columns, each epilogue
 //       warp rewrites only columns it has itself read; the constant-one columns sit in the first gap) -> after GEMM2: bf16 h2
-//       (compact, columns [0, hid/2)) and the GEMM3 accumulator (columns [128, 128 + n3_pad))
+//       (compact, columns [0, hid/2)) and the GEMM3 accumulator (columns [128, 128 + min(n3_pad, 128)); more than 128 tap
+//       planes run as two passes over it)
 //   R1: GEMM2 accumulator (fp32); it is the next tile's R0.
 // GEMM1 of tile t+1 is issued right behind GEMM3 of tile t, so the tensor pipe idles only while the first chunk of an
 // activation epilogue is being produced.  All hand-offs are mbarriers; barriers that gate MMAs live in the leader CTA (the
@@ -54,7 +56,7 @@ struct NNArgs {
   int act_fn;
   int store_h;                               // 1: h1 / h2 leave as bf16 NHWC side outputs
   float* taps_out;                           // fp32 NCHW [B, n3, H, W]
-  unsigned long long* dbg;                   // debug: 16 cycle counters per CTA (rfk_debug_set_timeline), else null
+  unsigned long long* dbg;                   // debug: 16 cycle counters + 16 stamps per CTA (rfk_debug_set_timeline; tools/nn_fused_timeline.py), else null
 };
 
 #define NN_CNT_BEGIN() const unsigned cnt_t0_ = dbg ? (unsigned)clock() : 0u

@@ -233,3 +233,42 @@ def test_clear_workspaces_refuses_while_a_graph_is_alive():
     import gc
     gc.collect()
     rf.ops.clear_workspaces()
+
+
+def test_split_k_heuristic():
+    """ops.choose_k_split: nine slices for a single pixel tile with a long K (sampling, deepest level), three filter rows for
+    16..24 pixel tiles (deepest level of the 570-frame workload), none for short K, 1x1 convs, narrow inputs or many tiles."""
+    from recurrent_flows_msc_b200 import ops
+    if ops.SPLIT:
+        pytest.skip("split-precision mode never splits K")
+    assert ops.choose_k_split(120, 9, 320) == 9            # 30 sequences at 2x2: one tile, K = 2880
+    assert ops.choose_k_split(2280, 9, 320) == 3           # 570 frames at 2x2: 18 tiles
+    assert ops.choose_k_split(2280, 9, 128) == 1           # K = 1152: too short to pay for the reduction
+    assert ops.choose_k_split(9120, 9, 192) == 1           # 72 tiles already cover the GPU
+    assert ops.choose_k_split(1920, 9, 128) == 1           # 15 tiles (sampling, 8x8 maps): measured slower when split
+    assert ops.choose_k_split(2280, 1, 320) == 1 and ops.choose_k_split(2280, 9, 32) == 1
+
+
+def test_gemm_m_tiles_matches_the_kernel_tiling():
+    """ops.gemm_m_tiles mirrors the conv kernels' tile = NIMG x TH x TW pixels with power-of-two TW, TH (csrc/conv_gemm.cu
+    m_tiles_of): the thresholds of the one-kernel coupling network are expressed in these tiles."""
+    from recurrent_flows_msc_b200 import ops
+    assert ops.gemm_m_tiles(570, 32, 32) == 4560 and ops.gemm_m_tiles(570, 16, 16) == 1140
+    assert ops.gemm_m_tiles(30, 32, 32) == 240 and ops.gemm_m_tiles(30, 16, 16) == 60
+    assert ops.gemm_m_tiles(30, 2, 2) == 1 and ops.gemm_m_tiles(570, 2, 2) == 18
+    assert ops.gemm_m_tiles(7, 12, 20) == 21               # ragged: tiles of 32 x 4 pixels, three per image
+    assert ops.gemm_m_tiles(1, 200, 200) == 2 * 200        # tiles of 128 x 1 pixels
+
+
+def test_one_kernel_coupling_network_is_gated():
+    """The module-level switch to rfk_coupling_nn_fused needs settled ActNorms (foldable), at least FUSE_NN_MIN_TILES pixel
+    tiles and at most FUSE_NN_MAX_PLANES tap planes; recompute mode is an attribute / environment default."""
+    import recurrent_flows_msc_b200 as rf
+    from recurrent_flows_msc_b200.Flow import glow_modules as gm, training
+    assert gm.FUSE_NN_MIN_TILES == int(os.environ.get("RFK_FUSE_NN_MIN_TILES", "48"))
+    assert gm.FUSE_NN_MAX_PLANES == int(os.environ.get("RFK_FUSE_NN_MAX_PLANES", "128"))
+    layer = rf.Flow.Conv2dNorm(18, 64)
+    assert not layer.foldable()                            # ActNorm not initialised (and not on a GPU)
+    layer.norm_type.mark_initialized()
+    assert layer.norm_type.is_initialized() and not layer.foldable()   # CPU parameters: the packing kernel needs CUDA
+    assert training.RECOMPUTE == (os.environ.get("RFK_RECOMPUTE", "0") == "1")
