@@ -193,6 +193,9 @@ class ListGlow(nn.Module):
     def __init__(self, x_size, condition_size, base_dist_size, args):
         super().__init__()
         assert isinstance(condition_size, list), "condition_size is not a list, make sure it fits L"
+        # training memory mode (not a parameter, not in the state_dict): True = regenerate the coupling networks' activations
+        # from each GlowStep's output in the backward instead of keeping them (Flow/training.py), None = RFK_RECOMPUTE
+        self.recompute = None
         self.learn_prior = args.learn_prior
         self.n_units_prior = args.n_units_prior
         self.make_conditional = args.make_conditional

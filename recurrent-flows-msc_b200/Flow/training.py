@@ -397,7 +397,9 @@ def _glowstep_fwd(flow, step, x, ld, nn_template, cc, l, tape):
     # [cond | z1] -> h1, h2, tap planes from y with the same kernels (bit-identical), two steps at a time at most.  Only the
     # flow tensors x, y (C channels) stay on the tape: 10.8 GB -> 2.1 GB at the 570-frame workload.  Needs ActNorms whose
     # statistics are settled (a data-dependent init or batch-norm statistics must not run twice).
-    recompute = (getattr(flow, "recompute", RECOMPUTE) and bn_saved is None and net[0].foldable() and net[2].foldable())
+    recompute = getattr(flow, "recompute", None)
+    recompute = ((RECOMPUTE if recompute is None else recompute) and bn_saved is None and net[0].foldable()
+                 and net[2].foldable())
     h1, h2, taps = _coupling_nn(aff, nn_in, C, keep=not recompute)
     ops.coupling_tail_taps(taps, y, *aff.tail_params(), ld, False)
     if recompute:
